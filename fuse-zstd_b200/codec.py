@@ -1,0 +1,176 @@
+"""ctypes bindings of libfzgpu.so (include/fzgpu.h).  No torch types cross this boundary."""
+import ctypes as C
+import errno
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libfzgpu.so")
+
+OK, E_MAGIC, E_TRUNCATED, E_UNSUPPORTED, E_CORRUPT, E_DSTSIZE, E_CHECKSUM, E_FCS = range(8)
+SRC_DEVICE, DST_DEVICE, NO_VERIFY_CHECKSUM, PROFILE = 1, 2, 4, 8
+
+EXPORTS = ["fzg_init", "fzg_shutdown", "fzg_device_count", "fzg_decode_fd", "fzg_encode_fd", "fzg_decode_batch",
+           "fzg_encode_batch", "fzg_encode_bound", "fzg_frame_info", "fzg_strerror", "fzg_last_timing",
+           "fzg_stage_name", "fzg_stream"]
+
+
+class Timing(C.Structure):
+    _fields_ = [("total_ms", C.c_float), ("kernel_ms", C.c_float * 16), ("launches", C.c_int),
+                ("bytes_in", C.c_uint64), ("bytes_out", C.c_uint64)]
+
+
+def build(force=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... (csrc/Makefile); cross-compiles without a GPU."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "csrc")] + (["-B"] if force else []))
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C ABI.  Raises if the CUDA library has not been built -- there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO):
+            raise ImportError("libfzgpu.so is not built (run __graft_entry__.build()); fuse-zstd_b200 has no CPU path")
+        L = C.CDLL(SO)
+        L.fzg_init.restype = C.c_int; L.fzg_init.argtypes = [C.POINTER(C.c_int), C.c_int]
+        L.fzg_shutdown.restype = None
+        L.fzg_device_count.restype = C.c_int
+        L.fzg_decode_fd.restype = C.c_int
+        L.fzg_decode_fd.argtypes = [C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.fzg_encode_fd.restype = C.c_int
+        L.fzg_encode_fd.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.fzg_decode_batch.restype = C.c_int
+        L.fzg_decode_batch.argtypes = [C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_int]
+        L.fzg_encode_batch.restype = C.c_int
+        L.fzg_encode_batch.argtypes = [C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_int, C.c_size_t, C.c_int]
+        L.fzg_encode_bound.restype = C.c_size_t; L.fzg_encode_bound.argtypes = [C.c_size_t, C.c_size_t]
+        L.fzg_frame_info.restype = C.c_int
+        L.fzg_frame_info.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.fzg_strerror.restype = C.c_char_p; L.fzg_strerror.argtypes = [C.c_int]
+        L.fzg_last_timing.restype = C.c_int; L.fzg_last_timing.argtypes = [C.c_int, C.POINTER(Timing)]
+        L.fzg_stage_name.restype = C.c_char_p; L.fzg_stage_name.argtypes = [C.c_int]
+        L.fzg_stream.restype = C.c_void_p; L.fzg_stream.argtypes = [C.c_int]
+        _lib = L
+    return _lib
+
+
+def _check(rc, what):
+    if rc < 0:
+        raise OSError(-rc, "%s: %s" % (what, os.strerror(-rc)))
+    return rc
+
+
+def init(devices=None):
+    if devices is None:
+        return _check(lib().fzg_init(None, 0), "fzg_init")
+    arr = (C.c_int * len(devices))(*devices)
+    return _check(lib().fzg_init(arr, len(devices)), "fzg_init")
+
+
+def shutdown():
+    lib().fzg_shutdown()
+
+
+def strerror(code):
+    return lib().fzg_strerror(code).decode()
+
+
+def frame_info(data):
+    """-> (status, content_size or None, compressed_size).  Host-side header walk, no GPU."""
+    a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    cs, zs = C.c_uint64(0), C.c_uint64(0)
+    st = lib().fzg_frame_info(a.ctypes.data if a.size else None, a.size, C.byref(cs), C.byref(zs))
+    return st, (None if cs.value == 2**64 - 1 else cs.value), zs.value
+
+
+def _u64(seq):
+    return np.ascontiguousarray(np.asarray(seq, dtype=np.uint64))
+
+
+def decode_batch_ptrs(device, src_ptrs, src_lens, dst_ptrs, dst_caps, flags=0):
+    """Raw form: arrays of pointers/sizes (host or device memory per `flags`) -> (dst_len[], status[])."""
+    sp, sl, dp, dc = _u64(src_ptrs), _u64(src_lens), _u64(dst_ptrs), _u64(dst_caps)
+    n = len(sp)
+    dl = np.zeros(n, dtype=np.uint64); st = np.zeros(n, dtype=np.int32)
+    _check(lib().fzg_decode_batch(device, n, sp.ctypes.data, sl.ctypes.data, dp.ctypes.data, dc.ctypes.data,
+                                  dl.ctypes.data, st.ctypes.data, flags), "fzg_decode_batch")
+    return dl, st
+
+
+def encode_batch_ptrs(device, src_ptrs, src_lens, dst_ptrs, dst_caps, level=3, chunk_size=0, flags=0):
+    sp, sl, dp, dc = _u64(src_ptrs), _u64(src_lens), _u64(dst_ptrs), _u64(dst_caps)
+    n = len(sp)
+    dl = np.zeros(n, dtype=np.uint64); st = np.zeros(n, dtype=np.int32)
+    _check(lib().fzg_encode_batch(device, n, sp.ctypes.data, sl.ctypes.data, dp.ctypes.data, dc.ctypes.data,
+                                  dl.ctypes.data, st.ctypes.data, level, chunk_size, flags), "fzg_encode_batch")
+    return dl, st
+
+
+def decode_batch(blobs, caps=None, device=0, flags=0):
+    """Host convenience: list of bytes-like .zst files -> list of (status, bytes)."""
+    arrs = [np.frombuffer(b, dtype=np.uint8) if not isinstance(b, np.ndarray) else b for b in blobs]
+    if caps is None:
+        caps = []
+        for a in arrs:
+            st, cs, _ = frame_info(a)
+            caps.append(cs if (st == 0 and cs is not None) else max(1 << 16, 64 * a.size))
+    outs = [np.empty(max(int(c), 1), dtype=np.uint8) for c in caps]
+    dl, st = decode_batch_ptrs(device, [a.ctypes.data if a.size else 0 for a in arrs], [a.size for a in arrs],
+                               [o.ctypes.data for o in outs], [int(c) for c in caps], flags & ~(SRC_DEVICE | DST_DEVICE))
+    return [(int(s), o[:int(l)].tobytes()) for s, l, o in zip(st, dl, outs)]
+
+
+def encode_bound(n, chunk_size=0):
+    return lib().fzg_encode_bound(n, chunk_size)
+
+
+def encode_batch(blobs, level=3, chunk_size=0, device=0, flags=0):
+    """Host convenience: list of bytes-like plain files -> list of (status, zstd bytes)."""
+    arrs = [np.frombuffer(b, dtype=np.uint8) if not isinstance(b, np.ndarray) else b for b in blobs]
+    caps = [encode_bound(a.size, chunk_size) for a in arrs]
+    outs = [np.empty(max(c, 1), dtype=np.uint8) for c in caps]
+    dl, st = encode_batch_ptrs(device, [a.ctypes.data if a.size else 0 for a in arrs], [a.size for a in arrs],
+                               [o.ctypes.data for o in outs], caps, level, chunk_size, flags & ~(SRC_DEVICE | DST_DEVICE))
+    return [(int(s), o[:int(l)].tobytes()) for s, l, o in zip(st, dl, outs)]
+
+
+def last_timing(device=0):
+    t = Timing()
+    _check(lib().fzg_last_timing(device, C.byref(t)), "fzg_last_timing")
+    stages = {}
+    for k in range(16):
+        nm = lib().fzg_stage_name(k).decode()
+        if nm:
+            stages[nm] = t.kernel_ms[k]
+    return dict(total_ms=t.total_ms, launches=t.launches, bytes_in=t.bytes_in, bytes_out=t.bytes_out, stages=stages)
+
+
+def stream_handle(device=0):
+    return lib().fzg_stream(device)
+
+
+def decode_fd(src_fd, dst_fd, shard_key=0):
+    """fzg_decode_fd -> plain size; raises OSError(EFAULT) on any codec failure (src/main.rs:467)."""
+    out = C.c_uint64(0)
+    rc = lib().fzg_decode_fd(src_fd, dst_fd, shard_key, C.byref(out))
+    if rc < 0:
+        raise OSError(-rc, os.strerror(-rc))
+    if rc > 0:
+        raise OSError(errno.EFAULT, "zstd decode failed: " + strerror(rc))
+    return out.value
+
+
+def encode_fd(src_fd, dst_fd, level, src_size, shard_key=0):
+    """fzg_encode_fd -> compressed size; failures surface as EIO (src/errors.rs:4-10)."""
+    out = C.c_uint64(0)
+    rc = lib().fzg_encode_fd(src_fd, dst_fd, level, src_size, shard_key, C.byref(out))
+    if rc != 0:
+        raise OSError(-rc if rc < 0 else errno.EIO, "zstd encode failed")
+    return out.value

@@ -1,0 +1,340 @@
+/*
+ * fz_api.cu -- the C ABI of libfzgpu.so (include/fzgpu.h): contexts, host<->device staging and
+ * the fd entry points that replace fuse-zstd's two codec call sites
+ * (/root/reference/src/main.rs:463-467 and :781-791).  No CPU codec path exists in this
+ * library: every compute entry point needs a CUDA device and fails with -ENODEV without one.
+ */
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <vector>
+
+#include "fz_core.cuh"
+#include "fz_kernels.cuh"
+#include "fz_host.h"
+
+using namespace fz;
+
+int fzh_encode_setup(void);
+int fzh_encode_run(FzCtx* c, uint32_t n, int level, size_t chunk, int flags);
+size_t fzh_encode_bound(size_t src_len, size_t chunk);
+const char* fzh_encode_stage_name(int s);
+
+static std::mutex g_mu;
+static std::vector<FzCtx*> g_ctx;       // index = position in the init list
+static std::vector<int> g_dev;
+
+#define CKR(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "fzgpu: %s failed: %s (%s:%d)\n", #x, cudaGetErrorString(e_), __FILE__, __LINE__); return -EIO; } } while (0)
+
+extern "C" int fzg_init(const int* devices, int n_devices)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx.empty()) return 0;
+    int visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess || visible == 0) { cudaGetLastError(); return -ENODEV; }
+    std::vector<int> devs;
+    if (n_devices <= 0) for (int i = 0; i < visible; i++) devs.push_back(i);
+    else for (int i = 0; i < n_devices; i++) devs.push_back(devices ? devices[i] : i);
+    for (int d : devs) if (d < 0 || d >= visible) return -EINVAL;
+    for (int d : devs) {
+        CKR(cudaSetDevice(d));
+        FzCtx* c = new FzCtx();
+        c->dev = d;
+        CKR(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CKR(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (auto& e : c->ev) CKR(cudaEventCreate(&e));
+        int rc = fzh_decode_setup(); if (rc) return rc;
+        rc = fzh_encode_setup(); if (rc) return rc;
+        g_ctx.push_back(c); g_dev.push_back(d);
+    }
+    return 0;
+}
+
+extern "C" void fzg_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (FzCtx* c : g_ctx) {
+        cudaSetDevice(c->dev);
+        cudaStreamSynchronize(c->stream);
+        FzDevBuf* db[] = { &c->d_items, &c->d_infos, &c->d_bases, &c->d_outs, &c->d_totals, &c->d_frames, &c->d_blocks,
+                           &c->d_seq_jobs, &c->d_huf_jobs, &c->d_lit, &c->d_seq, &c->d_stage_src, &c->d_stage_dst,
+                           &c->e_items, &c->e_outs, &c->e_work };
+        for (auto* b : db) b->release();
+        FzPinBuf* pb[] = { &c->h_items, &c->h_outs, &c->h_totals, &c->h_stage_src, &c->h_stage_dst };
+        for (auto* b : pb) b->release();
+        for (auto& e : c->ev) cudaEventDestroy(e);
+        cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copy_stream);
+        delete c;
+    }
+    g_ctx.clear(); g_dev.clear();
+}
+
+extern "C" int fzg_device_count(void) { std::lock_guard<std::mutex> lk(g_mu); return (int)g_ctx.size(); }
+
+static FzCtx* ctx_for(int device)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (size_t i = 0; i < g_ctx.size(); i++) if (g_dev[i] == device) return g_ctx[i];
+    return nullptr;
+}
+static FzCtx* ctx_for_key(uint64_t key)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g_ctx.empty() ? nullptr : g_ctx[key % g_ctx.size()];
+}
+static int ensure_init(void)
+{
+    { std::lock_guard<std::mutex> lk(g_mu); if (!g_ctx.empty()) return 0; }
+    return fzg_init(nullptr, 0);
+}
+
+static bool is_pinned(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+static inline size_t al16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+// ---------------------------------------------------------------------------------- batched decode / encode
+// Shared staging logic: direction-agnostic.  `encode` selects the pipeline.
+static int run_batch(bool encode, int device, size_t n, const void* const* src, const size_t* src_len, void* const* dst,
+                     const size_t* dst_cap, size_t* dst_len, int* status, int flags, int level, size_t chunk)
+{
+    if (n == 0) return 0;
+    if (!src || !src_len || !dst || !dst_cap || !dst_len || !status) return -EINVAL;
+    if (n >= (1ull << 31)) return -EINVAL;
+    int rc = ensure_init(); if (rc) return rc;
+    FzCtx* c = ctx_for(device);
+    if (!c) return -ENODEV;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CKR(cudaSetDevice(c->dev));
+    cudaStream_t s = c->stream;
+    const bool src_dev = flags & FZG_SRC_DEVICE, dst_dev = flags & FZG_DST_DEVICE;
+    if ((rc = c->h_items.reserve(n * sizeof(Item)))) return rc;
+    if ((rc = c->h_outs.reserve(n * sizeof(ItemOut)))) return rc;
+    if ((rc = c->h_totals.reserve(64))) return rc;
+    Item* items = (Item*)c->h_items.p;
+
+    // ---- sources
+    size_t src_total = 0, dst_total = 0;
+    for (size_t i = 0; i < n; i++) { src_total += al16(src_len[i]) + 16; dst_total += al16(dst_cap[i]) + 16; }
+    if (!src_dev) {
+        if ((rc = c->d_stage_src.reserve(src_total + 64))) return rc;
+        uint8_t* dbase = (uint8_t*)c->d_stage_src.p;
+        bool contiguous = true;
+        for (size_t i = 0; i + 1 < n && contiguous; i++) contiguous = (const uint8_t*)src[i] + src_len[i] == (const uint8_t*)src[i + 1];
+        const bool pinned = n && src_len[0] && is_pinned(src[0]) && is_pinned((const uint8_t*)src[n - 1] + (src_len[n - 1] ? src_len[n - 1] - 1 : 0));
+        if (contiguous && pinned) {               // one bulk copy straight from the caller's pinned buffer
+            size_t total = (const uint8_t*)src[n - 1] + src_len[n - 1] - (const uint8_t*)src[0];
+            if ((rc = c->d_stage_src.reserve(total + 64))) return rc;
+            dbase = (uint8_t*)c->d_stage_src.p;
+            CKR(cudaMemcpyAsync(dbase, src[0], total, cudaMemcpyHostToDevice, s));
+            for (size_t i = 0; i < n; i++) items[i].src = dbase + ((const uint8_t*)src[i] - (const uint8_t*)src[0]);
+        } else {                                  // pack into pinned staging, then one bulk copy
+            if ((rc = c->h_stage_src.reserve(src_total))) return rc;
+            uint8_t* hbase = (uint8_t*)c->h_stage_src.p; size_t off = 0;
+            for (size_t i = 0; i < n; i++) {
+                if (src_len[i]) memcpy(hbase + off, src[i], src_len[i]);
+                items[i].src = dbase + off; off += al16(src_len[i]) + 16;
+            }
+            CKR(cudaMemcpyAsync(dbase, hbase, off, cudaMemcpyHostToDevice, s));
+        }
+    } else for (size_t i = 0; i < n; i++) items[i].src = (const uint8_t*)src[i];
+    // ---- destinations
+    bool dst_contig = true;
+    if (!dst_dev) {
+        for (size_t i = 0; i + 1 < n && dst_contig; i++) dst_contig = (uint8_t*)dst[i] + dst_cap[i] == (uint8_t*)dst[i + 1];
+        if ((rc = c->d_stage_dst.reserve(dst_total + 64))) return rc;
+        uint8_t* dbase = (uint8_t*)c->d_stage_dst.p; size_t off = 0;
+        for (size_t i = 0; i < n; i++) {
+            if (dst_contig) { items[i].dst = dbase + ((uint8_t*)dst[i] - (uint8_t*)dst[0]); }
+            else { items[i].dst = dbase + off; off += al16(dst_cap[i]) + 16; }
+        }
+    } else for (size_t i = 0; i < n; i++) items[i].dst = (uint8_t*)dst[i];
+    for (size_t i = 0; i < n; i++) { items[i].src_len = src_len[i]; items[i].dst_cap = dst_cap[i]; }
+
+    rc = encode ? fzh_encode_run(c, (uint32_t)n, level, chunk, flags) : fzh_decode_run(c, (uint32_t)n, flags);
+    if (rc) return rc;
+    const ItemOut* outs = (const ItemOut*)c->h_outs.p;
+    uint64_t bytes_in = 0, bytes_out = 0;
+    bool all_full = true;
+    for (size_t i = 0; i < n; i++) {
+        dst_len[i] = (size_t)outs[i].dst_len; status[i] = outs[i].status;
+        bytes_in += src_len[i]; bytes_out += outs[i].dst_len;
+        if (outs[i].status || outs[i].dst_len != dst_cap[i]) all_full = false;
+    }
+    c->timing.bytes_in = bytes_in; c->timing.bytes_out = bytes_out;
+    // ---- results back to the host
+    if (!dst_dev) {
+        if (dst_contig && all_full && is_pinned(dst[0])) {
+            CKR(cudaMemcpyAsync(dst[0], items[0].dst, (uint8_t*)dst[n - 1] + dst_cap[n - 1] - (uint8_t*)dst[0], cudaMemcpyDeviceToHost, s));
+        } else {
+            for (size_t i = 0; i < n; i++)
+                if (!outs[i].status && outs[i].dst_len) CKR(cudaMemcpyAsync(dst[i], items[i].dst, outs[i].dst_len, cudaMemcpyDeviceToHost, s));
+        }
+        CKR(cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
+extern "C" int fzg_decode_batch(int device, size_t n, const void* const* src, const size_t* src_len, void* const* dst,
+                                const size_t* dst_cap, size_t* dst_len, int* status, int flags)
+{
+    return run_batch(false, device, n, src, src_len, dst, dst_cap, dst_len, status, flags, 0, 0);
+}
+
+extern "C" int fzg_encode_batch(int device, size_t n, const void* const* src, const size_t* src_len, void* const* dst,
+                                const size_t* dst_cap, size_t* dst_len, int* status, int level, size_t chunk_size, int flags)
+{
+    return run_batch(true, device, n, src, src_len, dst, dst_cap, dst_len, status, flags, level, chunk_size);
+}
+
+extern "C" size_t fzg_encode_bound(size_t src_len, size_t chunk_size) { return fzh_encode_bound(src_len, chunk_size); }
+
+// ---------------------------------------------------------------------------------- host header walk
+extern "C" int fzg_frame_info(const void* src_, size_t len, uint64_t* content_size, uint64_t* compressed_size)
+{
+    const uint8_t* src = (const uint8_t*)src_;
+    uint64_t ip = 0, total = 0; bool unknown = false;
+    while (ip < len) {
+        if (len - ip < 4) return FZG_E_TRUNCATED;
+        uint32_t magic = rd32u(src + ip);
+        if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {
+            if (len - ip < 8) return FZG_E_TRUNCATED;
+            uint64_t sz = rd32u(src + ip + 4);
+            if (len - ip - 8 < sz) return FZG_E_TRUNCATED;
+            ip += 8 + sz; continue;
+        }
+        if (magic != kMagic) return FZG_E_MAGIC;
+        FrameHdr h; int st = parse_frame_header(src + ip, len - ip, h);
+        if (st) return st;
+        ip += h.hsize;
+        if (h.has_fcs) total += h.fcs; else unknown = true;
+        for (;;) {
+            if (len - ip < 3) return FZG_E_TRUNCATED;
+            uint32_t bh = rd24(src + ip); ip += 3;
+            uint32_t type = (bh >> 1) & 3, bsize = bh >> 3;
+            if (type == 3) return FZG_E_CORRUPT;
+            uint64_t adv = type == BT_RLE ? 1 : bsize;
+            if (len - ip < adv) return FZG_E_TRUNCATED;
+            ip += adv;
+            if (bh & 1) break;
+        }
+        if (h.checksum) { if (len - ip < 4) return FZG_E_TRUNCATED; ip += 4; }
+    }
+    if (content_size) *content_size = unknown ? UINT64_MAX : total;
+    if (compressed_size) *compressed_size = ip;
+    return FZG_OK;
+}
+
+// ---------------------------------------------------------------------------------- fd entry points
+static int read_all(int fd, std::vector<uint8_t>& buf, uint64_t want /*0 = to EOF*/)
+{
+    size_t got = 0;
+    if (want) buf.resize(want); else buf.resize(1 << 20);
+    for (;;) {
+        if (!want && got == buf.size()) buf.resize(buf.size() * 2);
+        size_t room = buf.size() - got;
+        if (want && room == 0) break;
+        ssize_t r = read(fd, buf.data() + got, room);
+        if (r < 0) { if (errno == EINTR) continue; return -errno; }
+        if (r == 0) break;
+        got += (size_t)r;
+    }
+    buf.resize(got);
+    return 0;
+}
+static int write_all(int fd, const uint8_t* p, size_t n)
+{
+    while (n) {
+        ssize_t w = write(fd, p, n);
+        if (w < 0) { if (errno == EINTR) continue; return -errno; }
+        p += w; n -= (size_t)w;
+    }
+    return 0;
+}
+
+extern "C" int fzg_decode_fd(int src_fd, int dst_fd, uint64_t shard_key, uint64_t* out_size)
+{
+    int rc = ensure_init(); if (rc) return rc;
+    FzCtx* c = ctx_for_key(shard_key);
+    if (!c) return -ENODEV;
+    std::vector<uint8_t> in;
+    if ((rc = read_all(src_fd, in, 0))) return rc;
+    if (out_size) *out_size = 0;
+    if (in.empty()) return 0;                      // empty input: success, empty output
+    uint64_t content = 0, csize = 0;
+    int st = fzg_frame_info(in.data(), in.size(), &content, &csize);
+    if (st) return st;
+    uint64_t cap = content == UINT64_MAX ? (uint64_t)in.size() * 8 + (1 << 20) : content;
+    for (int attempt = 0; attempt < 6; attempt++) {
+        std::vector<uint8_t> out(cap ? cap : 1);
+        const void* sp = in.data(); size_t sl = in.size(); void* dp = out.data(); size_t dc = cap, dl = 0; int ist = 0;
+        rc = fzg_decode_batch(c->dev, 1, &sp, &sl, &dp, &dc, &dl, &ist, 0);
+        if (rc) return rc;
+        if (ist == FZG_E_DSTSIZE && content == UINT64_MAX) { cap *= 4; continue; }
+        if (ist) return ist;
+        if ((rc = write_all(dst_fd, out.data(), dl))) return rc;
+        if (out_size) *out_size = dl;
+        return 0;
+    }
+    return FZG_E_DSTSIZE;
+}
+
+extern "C" int fzg_encode_fd(int src_fd, int dst_fd, int level, uint64_t src_size, uint64_t shard_key, uint64_t* out_size)
+{
+    int rc = ensure_init(); if (rc) return rc;
+    FzCtx* c = ctx_for_key(shard_key);
+    if (!c) return -ENODEV;
+    std::vector<uint8_t> in;
+    if ((rc = read_all(src_fd, in, src_size))) return rc;
+    if (src_size && in.size() != src_size) return -EIO;
+    size_t cap = fzg_encode_bound(in.size(), 0);
+    std::vector<uint8_t> out(cap);
+    const void* sp = in.data(); size_t sl = in.size(); void* dp = out.data(); size_t dl = 0; int ist = 0;
+    rc = fzg_encode_batch(c->dev, 1, &sp, &sl, &dp, &cap, &dl, &ist, level, 0, 0);
+    if (rc) return rc;
+    if (ist) return -EIO;
+    if ((rc = write_all(dst_fd, out.data(), dl))) return rc;
+    if (out_size) *out_size = dl;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------- misc
+extern "C" const char* fzg_strerror(int code)
+{
+    switch (code) {
+    case FZG_OK: return "ok";
+    case FZG_E_MAGIC: return "unknown frame descriptor";
+    case FZG_E_TRUNCATED: return "input ends inside a frame";
+    case FZG_E_UNSUPPORTED: return "unsupported frame parameter (reserved bit, dictionary, window > 2^27)";
+    case FZG_E_CORRUPT: return "corrupted block";
+    case FZG_E_DSTSIZE: return "destination buffer too small";
+    case FZG_E_CHECKSUM: return "content checksum mismatch";
+    case FZG_E_FCS: return "decoded size differs from Frame_Content_Size";
+    default: return code < 0 ? strerror(-code) : "unknown status";
+    }
+}
+
+extern "C" int fzg_last_timing(int device, fzg_timing_t* out)
+{
+    FzCtx* c = ctx_for(device);
+    if (!c || !out) return -EINVAL;
+    std::lock_guard<std::mutex> lk(c->mu);
+    *out = c->timing;
+    return 0;
+}
+
+extern "C" const char* fzg_stage_name(int stage) { return stage < 16 ? fzh_decode_stage_name(stage) : fzh_encode_stage_name(stage - 16); }
+
+extern "C" void* fzg_stream(int device)
+{
+    FzCtx* c = ctx_for(device);
+    return c ? (void*)c->stream : nullptr;
+}

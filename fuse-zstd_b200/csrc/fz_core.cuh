@@ -1,0 +1,683 @@
+/*
+ * fz_core.cuh -- per-thread building blocks of the sm_100a zstd decoder.
+ *
+ * Everything here is written from the Zstandard format description (RFC 8878); it replaces the
+ * libzstd arithmetic that fuse-zstd reaches through zstd::stream::copy_decode
+ * (/root/reference/src/main.rs:463-467).  Functions are FZ_HD so the same source compiles
+ *   - under nvcc into the kernels of fz_decode.cu (the product path), and
+ *   - under g++ into tests/emul (TEST ONLY), which replays the launch sequence thread by thread
+ *     so pipeline logic can be checked against the oracle without a GPU.
+ */
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __CUDACC__
+#define FZ_HD __host__ __device__ __forceinline__
+#define FZ_D __device__ __forceinline__
+#else
+#define FZ_HD inline
+#define FZ_D inline
+#endif
+
+#include "../../include/fzgpu.h"
+
+namespace fz {
+
+constexpr uint32_t kMagic = 0xFD2FB528u;
+constexpr uint32_t kBlockMax = 128u * 1024u;
+constexpr uint64_t kWindowMax = 1ull << 27;   // zstd-rs streaming decoder default (windowLogMax = 27)
+constexpr int kMaxLL = 35, kMaxOF = 31, kMaxML = 52;
+constexpr int kLLLog = 9, kOFLog = 8, kMLLog = 9, kHufLogMax = 12, kHufLogFast = 11;
+
+// ------------------------------------------------------------------ descriptors (HBM)
+struct Item {            // one .zst file of the batch
+    const uint8_t* src; uint64_t src_len;
+    uint8_t* dst; uint64_t dst_cap;
+};
+
+struct ItemInfo {        // written by the count pass, consumed by the scan
+    uint32_t n_frames, n_blocks, n_seq_jobs, n_huf_jobs;
+    uint64_t lit_bytes, n_seq;
+    int32_t walk_status; uint32_t pad;
+};
+
+struct ItemBase {        // exclusive prefix sums over items
+    uint32_t frame, block, seq_job, huf_job;
+    uint64_t lit, seq;
+};
+
+struct Frame {
+    uint32_t item, first_block, n_blocks, block_max;
+    uint64_t fcs;            // Frame_Content_Size (valid when has_fcs)
+    uint64_t out_off;        // offset of the frame's first byte in the item's dst
+    uint64_t out_size;       // regenerated size (sum of block rsize)
+    uint32_t checksum;       // stored XXH64 low 32 bits
+    uint8_t has_fcs, has_checksum; uint16_t pad;
+    int32_t status; uint32_t pad2;
+};
+
+enum : uint8_t { BT_RAW = 0, BT_RLE = 1, BT_COMPRESSED = 2 };
+enum : uint8_t { LT_RAW = 0, LT_RLE = 1, LT_HUF = 2, LT_TREELESS = 3 };
+
+struct Block {
+    const uint8_t* src;      // block content (after the 3-byte header)
+    const uint8_t* lit;      // regenerated literals: into src (Raw) or into literal scratch
+    uint64_t seq_base;       // first record in the sequence scratch
+    uint64_t out_off;        // offset in item dst (filled by the offsets pass)
+    uint32_t csize;          // Block_Size field
+    uint32_t rsize;          // regenerated size (Raw/RLE: known; Compressed: filled by the sequence pass)
+    uint32_t lit_hdr, lit_regen, lit_csize;
+    uint32_t nseq, seq_hdr;  // seq_hdr: offset of the byte after nbSeq(+modes) inside the block
+    uint32_t frame;
+    int32_t huf_src, ll_src, of_src, ml_src;   // global block index that carries the table description
+    uint8_t type, last, lit_type, lit_streams, modes, pad[3];
+    int32_t status;
+};
+
+// 8-byte sequence record in HBM: ll:17 | ml:18 | offset_value:29
+FZ_HD uint64_t seq_pack(uint32_t ll, uint32_t ml, uint32_t ofv) { return (uint64_t)ll | ((uint64_t)ml << 17) | ((uint64_t)ofv << 35); }
+FZ_HD uint32_t seq_ll(uint64_t r) { return (uint32_t)r & 0x1FFFFu; }
+FZ_HD uint32_t seq_ml(uint64_t r) { return (uint32_t)(r >> 17) & 0x3FFFFu; }
+FZ_HD uint32_t seq_ofv(uint64_t r) { return (uint32_t)(r >> 35); }
+constexpr uint32_t kOfvCap = (1u << 29) - 1;
+
+// ------------------------------------------------------------------ small helpers
+FZ_HD int highbit(uint32_t v)
+{
+#ifdef __CUDA_ARCH__
+    return 31 - __clz((int)v);
+#else
+    return 31 - __builtin_clz(v);
+#endif
+}
+FZ_HD uint32_t shl_c(uint32_t v, uint32_t n) { return n >= 32 ? 0u : v << n; }   // clamped shifts
+FZ_HD uint32_t shr_c(uint32_t v, uint32_t n) { return n >= 32 ? 0u : v >> n; }
+FZ_HD uint32_t fsl_c(uint32_t lo, uint32_t hi, uint32_t n)                        // high word of (hi:lo << n), n clamped to 32
+{
+#ifdef __CUDA_ARCH__
+    return __funnelshift_lc(lo, hi, n);
+#else
+    return n >= 32 ? lo : (n == 0 ? hi : (hi << n) | (lo >> (32 - n)));
+#endif
+}
+FZ_HD uint32_t rd24(const uint8_t* p) { return p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16); }
+FZ_HD uint32_t rd32u(const uint8_t* p) { return p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+// ------------------------------------------------------------------ frame header
+struct FrameHdr { uint64_t fcs, window; uint32_t hsize; uint8_t has_fcs, checksum; };
+
+// RFC 8878 3.1.1.1.  p points at the magic; n = bytes available.  Returns FZG_* status.
+FZ_HD int parse_frame_header(const uint8_t* p, uint64_t n, FrameHdr& h)
+{
+    if (n < 5) return FZG_E_TRUNCATED;
+    uint32_t fhd = p[4];
+    uint32_t fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, did_flag = fhd & 3;
+    if (fhd & 8) return FZG_E_UNSUPPORTED;
+    h.checksum = (fhd >> 2) & 1;
+    uint32_t pos = 5;
+    h.window = 0;
+    if (!single) {
+        if (n < pos + 1) return FZG_E_TRUNCATED;
+        uint32_t b = p[pos++];
+        uint64_t base = 1ull << (10 + (b >> 3));
+        h.window = base + (base >> 3) * (b & 7);
+    }
+    uint32_t db = did_flag == 3 ? 4 : did_flag;
+    if (n < pos + db) return FZG_E_TRUNCATED;
+    uint32_t did = 0;
+    for (uint32_t i = 0; i < db; i++) did |= (uint32_t)p[pos + i] << (8 * i);
+    pos += db;
+    if (did != 0) return FZG_E_UNSUPPORTED;
+    uint32_t fb = fcs_flag == 0 ? single : (fcs_flag == 1 ? 2 : (fcs_flag == 2 ? 4 : 8));
+    if (n < pos + fb) return FZG_E_TRUNCATED;
+    h.has_fcs = fb != 0; h.fcs = 0;
+    for (uint32_t i = 0; i < fb; i++) h.fcs |= (uint64_t)p[pos + i] << (8 * i);
+    if (fb == 2) h.fcs += 256;
+    pos += fb;
+    if (single) h.window = h.fcs;
+    if (h.window > kWindowMax) return FZG_E_UNSUPPORTED;
+    h.hsize = pos;
+    return FZG_OK;
+}
+
+// ------------------------------------------------------------------ literals / sequences section headers
+struct LitHdr { uint32_t type, streams, hsize, regen, csize; };
+
+// RFC 8878 3.1.1.3.1.1.  Returns 0 or FZG_E_CORRUPT.
+FZ_HD int parse_lit_header(const uint8_t* p, uint32_t n, uint32_t block_max, LitHdr& h)
+{
+    if (n < 1) return FZG_E_CORRUPT;
+    uint32_t b0 = p[0];
+    h.type = b0 & 3; uint32_t sf = (b0 >> 2) & 3;
+    h.streams = 1; h.csize = 0;
+    if (h.type < 2) {
+        if (sf == 0 || sf == 2) { h.hsize = 1; h.regen = b0 >> 3; }
+        else if (sf == 1) { if (n < 2) return FZG_E_CORRUPT; h.hsize = 2; h.regen = (b0 >> 4) | ((uint32_t)p[1] << 4); }
+        else { if (n < 3) return FZG_E_CORRUPT; h.hsize = 3; h.regen = (b0 >> 4) | ((uint32_t)p[1] << 4) | ((uint32_t)p[2] << 12); }
+        if (h.regen > block_max) return FZG_E_CORRUPT;
+        h.csize = h.type == LT_RAW ? h.regen : 1;
+        if (h.hsize + h.csize > n) return FZG_E_CORRUPT;
+        return 0;
+    }
+    if (sf < 2) {
+        if (n < 3) return FZG_E_CORRUPT;
+        uint32_t v = rd24(p);
+        h.hsize = 3; h.regen = (v >> 4) & 0x3FF; h.csize = (v >> 14) & 0x3FF; h.streams = sf ? 4 : 1;
+    } else if (sf == 2) {
+        if (n < 4) return FZG_E_CORRUPT;
+        uint32_t v = rd32u(p);
+        h.hsize = 4; h.regen = (v >> 4) & 0x3FFF; h.csize = (v >> 18) & 0x3FFF; h.streams = 4;
+    } else {
+        if (n < 5) return FZG_E_CORRUPT;
+        uint64_t v = (uint64_t)rd32u(p) | ((uint64_t)p[4] << 32);
+        h.hsize = 5; h.regen = (uint32_t)((v >> 4) & 0x3FFFF); h.csize = (uint32_t)((v >> 22) & 0x3FFFF); h.streams = 4;
+    }
+    if (h.regen > block_max || h.regen == 0) return FZG_E_CORRUPT;
+    if (h.streams == 4 && h.regen < 6) return FZG_E_CORRUPT;
+    if (h.hsize + h.csize > n) return FZG_E_CORRUPT;
+    return 0;
+}
+
+// Sequences_Section_Header: nbSeq and the modes byte.  p = start of the section, n = bytes left
+// in the block.  hsize = bytes up to and including the modes byte (1 when nseq == 0).
+FZ_HD int parse_seq_header(const uint8_t* p, uint32_t n, uint32_t& nseq, uint32_t& hsize, uint32_t& modes)
+{
+    if (n < 1) return FZG_E_CORRUPT;
+    nseq = p[0]; hsize = 1; modes = 0;
+    if (nseq >= 128) {
+        if (nseq == 255) { if (n < 3) return FZG_E_CORRUPT; nseq = p[1] + ((uint32_t)p[2] << 8) + 0x7F00; hsize = 3; }
+        else { if (n < 2) return FZG_E_CORRUPT; nseq = ((nseq - 128) << 8) + p[1]; hsize = 2; }
+    }
+    if (nseq == 0) return hsize == n ? 0 : FZG_E_CORRUPT;
+    if (n < hsize + 1) return FZG_E_CORRUPT;
+    modes = p[hsize]; hsize += 1;
+    if (modes & 3) return FZG_E_CORRUPT;
+    return 0;
+}
+
+// ------------------------------------------------------------------ item walk (count pass and fill pass)
+// One thread walks one item: frames, skippable frames, block headers, literals / sequences section
+// headers.  FILL=false only counts; FILL=true writes Frame / Block descriptors and job lists at
+// the bases the scan produced.  Both passes take identical decisions.
+template <bool FILL>
+FZ_HD void walk_item(uint32_t item_idx, const Item& it, ItemInfo& info, const ItemBase* base,
+                     Frame* frames, Block* blocks, uint32_t* seq_jobs, uint32_t* huf_jobs,
+                     uint8_t* lit_scratch)
+{
+    const uint8_t* src = it.src; const uint64_t n = it.src_len;
+    uint64_t ip = 0;
+    uint32_t nf = 0, nb = 0, nsj = 0, nhj = 0; uint64_t lit_bytes = 0, n_seq = 0;
+    int status = FZG_OK;
+    while (ip < n) {
+        if (n - ip < 4) { status = FZG_E_TRUNCATED; break; }
+        uint32_t magic = rd32u(src + ip);
+        if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {
+            if (n - ip < 8) { status = FZG_E_TRUNCATED; break; }
+            uint64_t sz = rd32u(src + ip + 4);
+            if (n - ip - 8 < sz) { status = FZG_E_TRUNCATED; break; }
+            ip += 8 + sz; continue;
+        }
+        if (magic != kMagic) { status = FZG_E_MAGIC; break; }
+        FrameHdr fh;
+        status = parse_frame_header(src + ip, n - ip, fh);
+        if (status) break;
+        ip += fh.hsize;
+        uint32_t block_max = fh.window < kBlockMax ? (uint32_t)fh.window : kBlockMax;
+        uint32_t frame_gidx = 0, first_block = 0;
+        if (FILL) { frame_gidx = base->frame + nf; first_block = base->block + nb; }
+        int32_t huf_src = -1, ll_src = -1, of_src = -1, ml_src = -1;
+        uint32_t frame_blocks = 0;
+        for (;;) {
+            if (n - ip < 3) { status = FZG_E_TRUNCATED; break; }
+            uint32_t bh = rd24(src + ip); ip += 3;
+            uint32_t last = bh & 1, type = (bh >> 1) & 3, bsize = bh >> 3;
+            if (type == 3) { status = FZG_E_CORRUPT; break; }
+            if (bsize > block_max) { status = FZG_E_CORRUPT; break; }
+            uint32_t csize = type == BT_RLE ? 1 : bsize;
+            if (n - ip < csize) { status = FZG_E_TRUNCATED; break; }
+            Block b;
+            b.src = src + ip; b.lit = nullptr; b.seq_base = 0; b.out_off = 0;
+            b.csize = bsize; b.rsize = type == BT_COMPRESSED ? 0 : bsize;
+            b.lit_hdr = b.lit_regen = b.lit_csize = b.nseq = b.seq_hdr = 0;
+            b.frame = frame_gidx; b.huf_src = b.ll_src = b.of_src = b.ml_src = -1;
+            b.type = (uint8_t)type; b.last = (uint8_t)last; b.lit_type = 0; b.lit_streams = 0; b.modes = 0;
+            b.pad[0] = b.pad[1] = b.pad[2] = 0; b.status = 0;
+            uint32_t gb = FILL ? base->block + nb : 0;
+            if (type == BT_COMPRESSED) {
+                if (bsize < 2) { status = FZG_E_CORRUPT; break; }
+                LitHdr lh;
+                status = parse_lit_header(src + ip, bsize, block_max, lh);
+                if (status) break;
+                uint32_t litsec = lh.hsize + lh.csize;
+                uint32_t nseq, shs, modes;
+                status = parse_seq_header(src + ip + litsec, bsize - litsec, nseq, shs, modes);
+                if (status) break;
+                b.lit_hdr = lh.hsize; b.lit_regen = lh.regen; b.lit_csize = lh.csize;
+                b.lit_type = (uint8_t)lh.type; b.lit_streams = (uint8_t)lh.streams;
+                b.nseq = nseq; b.seq_hdr = litsec + shs; b.modes = (uint8_t)modes;
+                // table provenance is tracked with item-local block numbers (identical in both passes)
+                if (lh.type == LT_HUF) huf_src = (int32_t)nb;
+                else if (lh.type == LT_TREELESS && huf_src < 0) { status = FZG_E_CORRUPT; break; }
+                if (nseq) {
+                    uint32_t mll = (modes >> 6) & 3, mof = (modes >> 4) & 3, mml = (modes >> 2) & 3;
+                    if (mll != 3) ll_src = (int32_t)nb; else if (ll_src < 0) { status = FZG_E_CORRUPT; break; }
+                    if (mof != 3) of_src = (int32_t)nb; else if (of_src < 0) { status = FZG_E_CORRUPT; break; }
+                    if (mml != 3) ml_src = (int32_t)nb; else if (ml_src < 0) { status = FZG_E_CORRUPT; break; }
+                }
+                if (FILL) {
+                    const int32_t g0 = (int32_t)base->block;
+                    b.huf_src = lh.type >= LT_HUF ? g0 + huf_src : -1;
+                    if (nseq) { b.ll_src = g0 + ll_src; b.of_src = g0 + of_src; b.ml_src = g0 + ml_src; }
+                }
+                if (lh.type == LT_RAW) b.lit = src + ip + lh.hsize;
+                else {
+                    if (FILL) b.lit = lit_scratch + base->lit + lit_bytes;
+                    lit_bytes += (lh.regen + 15u) & ~15u;
+                }
+                if (nseq) { if (FILL) { b.seq_base = base->seq + n_seq; seq_jobs[base->seq_job + nsj] = gb; } n_seq += nseq; nsj++; }
+                if (lh.type != LT_RAW) { if (FILL) huf_jobs[base->huf_job + nhj] = gb; nhj++; }
+            }
+            if (FILL) blocks[gb] = b;
+            ip += csize; nb++; frame_blocks++;
+            if (last) break;
+        }
+        if (status) break;
+        uint32_t stored = 0;
+        if (fh.checksum) {
+            if (n - ip < 4) { status = FZG_E_TRUNCATED; break; }
+            stored = rd32u(src + ip); ip += 4;
+        }
+        if (FILL) {
+            Frame f;
+            f.item = item_idx; f.first_block = first_block; f.n_blocks = frame_blocks; f.block_max = block_max;
+            f.fcs = fh.fcs; f.out_off = 0; f.out_size = 0; f.checksum = stored;
+            f.has_fcs = fh.has_fcs; f.has_checksum = fh.checksum; f.pad = 0; f.status = 0; f.pad2 = 0;
+            frames[frame_gidx] = f;
+        }
+        nf++;
+    }
+    info.n_frames = nf; info.n_blocks = nb; info.n_seq_jobs = nsj; info.n_huf_jobs = nhj;
+    info.lit_bytes = lit_bytes; info.n_seq = n_seq; info.walk_status = status; info.pad = 0;
+}
+
+// ------------------------------------------------------------------ forward bit reader (FSE table descriptions)
+struct FwdBits {
+    const uint8_t* p; uint32_t n; uint32_t bitpos;
+    FZ_HD uint32_t peek(uint32_t nb) const   // nb <= 24; zero padded past the end
+    {
+        uint32_t byte = bitpos >> 3, sh = bitpos & 7; uint32_t w = 0;
+        for (uint32_t i = 0; i < 4; i++) if (byte + i < n) w |= (uint32_t)p[byte + i] << (8 * i);
+        return (w >> sh) & ((1u << nb) - 1);
+    }
+};
+
+// RFC 8878 4.1.1.  norm[] receives probabilities (-1 = "less than one").  Returns bytes used or -1.
+FZ_HD int read_ncount(const uint8_t* p, uint32_t n, int max_sym, int max_log, int16_t* norm, int& n_sym, int& log)
+{
+    if (n == 0) return -1;
+    FwdBits br{ p, n, 0 };
+    log = (int)br.peek(4) + 5; br.bitpos = 4;
+    if (log > max_log) return -1;
+    int remaining = 1 << log, sym = 0;
+    while (remaining > 0 && sym <= max_sym) {
+        int bits = highbit((uint32_t)remaining + 1) + 1;
+        uint32_t v = br.peek((uint32_t)bits);
+        uint32_t lower = (1u << (bits - 1)) - 1;
+        uint32_t thr = (1u << bits) - 1 - ((uint32_t)remaining + 1);
+        if ((v & lower) < thr) { v &= lower; br.bitpos += (uint32_t)bits - 1; }
+        else { if (v > lower) v -= thr; br.bitpos += (uint32_t)bits; }
+        int prob = (int)v - 1;
+        remaining -= prob < 0 ? 1 : prob;
+        norm[sym++] = (int16_t)prob;
+        if (prob == 0) {
+            for (;;) {
+                uint32_t rep = br.peek(2); br.bitpos += 2;
+                for (uint32_t i = 0; i < rep; i++) { if (sym > max_sym) return -1; norm[sym++] = 0; }
+                if (rep != 3) break;
+            }
+        }
+        if (br.bitpos > n * 8) return -1;
+    }
+    if (remaining != 0 || br.bitpos > n * 8) return -1;
+    n_sym = sym;
+    return (int)((br.bitpos + 7) >> 3);
+}
+
+// FSE decode cell, 32 bits: baseline[0:16) | nbBits[16:20) | nbExtra[20:25) | symbol[25:32)
+FZ_HD uint32_t cell_pack(uint32_t base, uint32_t nb, uint32_t extra, uint32_t sym) { return base | (nb << 16) | (extra << 20) | (sym << 25); }
+FZ_HD uint32_t cell_base(uint32_t c) { return c & 0xFFFFu; }
+FZ_HD uint32_t cell_nb(uint32_t c) { return (c >> 16) & 15u; }
+FZ_HD uint32_t cell_extra(uint32_t c) { return (c >> 20) & 31u; }
+FZ_HD uint32_t cell_sym(uint32_t c) { return c >> 25; }
+
+// Builds the decode table (RFC 8878 4.1.1).  extra_bits[sym] is folded into each cell so the
+// sequence loop needs one lookup per state.  `cnt` is per-thread scratch of >= 64 uint16.
+// Returns 0 or -1.  table has 1<<log cells.
+FZ_HD int build_fse_table(uint32_t* table, const int16_t* norm, int n_sym, int log, const uint8_t* extra_bits, uint16_t* cnt)
+{
+    const int size = 1 << log; int high = size - 1;
+    for (int s = 0; s < n_sym; s++) {
+        if (norm[s] == -1) { table[high--] = (uint32_t)s; cnt[s] = 1; }
+        else cnt[s] = (uint16_t)norm[s];
+    }
+    const int step = (size >> 1) + (size >> 3) + 3, mask = size - 1; int pos = 0;
+    for (int s = 0; s < n_sym; s++) {
+        for (int i = 0; i < norm[s]; i++) {
+            table[pos] = (uint32_t)s;
+            do { pos = (pos + step) & mask; } while (pos > high);
+        }
+    }
+    if (pos != 0) return -1;
+    for (int u = 0; u < size; u++) {
+        uint32_t s = table[u];
+        uint32_t nx = cnt[s]++;
+        uint32_t nb = (uint32_t)(log - highbit(nx));
+        table[u] = cell_pack((nx << nb) - (uint32_t)size, nb, extra_bits ? extra_bits[s] : s, s);
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------ backward bit reader (Huffman + sequences)
+// Top-aligned 64-bit container in two 32-bit registers, refilled 32 bits at a time from
+// 4-byte-aligned words (coalescing-friendly and legal for any stream alignment).  Words wholly
+// below the stream start are never loaded (zeros are supplied); `left` tracks the unread bits
+// of the real stream, so a stream that over-reads ends with left < 0 and is reported corrupt.
+struct BackBits {
+    uint32_t hi, lo; int avail; int left;
+    const uint32_t* wp; const uint32_t* wmin;
+
+    FZ_HD int init(const uint8_t* p, uint32_t n)
+    {
+        if (n == 0) return -1;
+        const uint8_t* lastp = p + n - 1;
+        uint32_t lastb = *lastp;
+        if (lastb == 0) return -1;
+        uintptr_t a = (uintptr_t)lastp & ~(uintptr_t)3;
+        uint32_t keep = (uint32_t)((uintptr_t)lastp & 3) + 1;
+        uint32_t w = *(const uint32_t*)a;
+        if (keep < 4) w &= (1u << (8 * keep)) - 1;
+        int hb = highbit(w);                        // sentinel position inside the word
+        hi = shl_c(w, 32 - hb); lo = 0; avail = hb;
+        left = (int)(n - 1) * 8 + highbit(lastb);
+        wp = (const uint32_t*)a - 1;
+        wmin = (const uint32_t*)((uintptr_t)p & ~(uintptr_t)3);
+        return 0;
+    }
+    FZ_HD void refill()                             // precondition: avail <= 32
+    {
+        uint32_t w = wp >= wmin ? *wp : 0u;
+        wp--;
+        hi |= shr_c(w, (uint32_t)avail);
+        lo = shl_c(w, 32 - (uint32_t)avail);
+        avail += 32;
+    }
+    FZ_HD uint32_t peek(uint32_t nb) const { return shr_c(hi, 32 - nb); }   // nb <= 32, nb <= avail
+    FZ_HD void skip(uint32_t nb)
+    {
+        hi = fsl_c(lo, hi, nb); lo = shl_c(lo, nb);
+        avail -= (int)nb; left -= (int)nb;
+    }
+    FZ_HD uint32_t read(uint32_t nb) { uint32_t v = peek(nb); skip(nb); return v; }
+};
+
+// ------------------------------------------------------------------ Huffman literals
+struct HufInfo { int log; uint32_t used; };   // used = bytes of the tree description
+
+// RFC 8878 4.2.1.  Decodes the tree description at p into weights w[0..n_w) (incl. the implicit
+// last weight).  Returns 0 or -1.  `ft` is scratch for the 64-cell FSE table, cnt >= 64 uint16.
+FZ_HD int huf_read_weights(const uint8_t* p, uint32_t n, uint8_t* w, int& n_w, HufInfo& info, uint32_t* ft, uint16_t* cnt)
+{
+    if (n < 1) return -1;
+    uint32_t h = p[0]; int nw = 0;
+    if (h >= 128) {
+        nw = (int)h - 127;
+        uint32_t bytes = (uint32_t)(nw + 1) / 2;
+        if (1 + bytes > n) return -1;
+        for (int i = 0; i < nw; i++) w[i] = (i & 1) ? (p[1 + i / 2] & 15) : (p[1 + i / 2] >> 4);
+        info.used = 1 + bytes;
+    } else {
+        if (h == 0 || h + 1 > n) return -1;
+        int16_t norm[16]; int ns, log;
+        int hb = read_ncount(p + 1, h, 12, 6, norm, ns, log);
+        if (hb < 0 || (uint32_t)hb >= h) return -1;
+        if (build_fse_table(ft, norm, ns, log, nullptr, cnt) != 0) return -1;
+        BackBits br;
+        if (br.init(p + 1 + hb, h - (uint32_t)hb) != 0) return -1;
+        br.refill(); if (br.avail <= 32) br.refill();
+        uint32_t s1 = br.read((uint32_t)log), s2 = br.read((uint32_t)log);
+        if (br.left < 0) return -1;
+        for (;;) {
+            if (br.avail <= 32) br.refill();
+            if (nw > 253) return -1;
+            uint32_t c1 = ft[s1];
+            w[nw++] = (uint8_t)cell_sym(c1);
+            s1 = cell_base(c1) + br.read(cell_nb(c1));
+            if (br.left < 0) { w[nw++] = (uint8_t)cell_sym(ft[s2]); break; }
+            if (nw > 253) return -1;
+            uint32_t c2 = ft[s2];
+            w[nw++] = (uint8_t)cell_sym(c2);
+            s2 = cell_base(c2) + br.read(cell_nb(c2));
+            if (br.left < 0) { w[nw++] = (uint8_t)cell_sym(ft[s1]); break; }
+        }
+        info.used = 1 + h;
+    }
+    uint32_t sum = 0; int rank1 = 0;
+    for (int i = 0; i < nw; i++) {
+        if (w[i] > kHufLogMax) return -1;
+        if (w[i]) sum += 1u << (w[i] - 1);
+        rank1 += w[i] == 1;
+    }
+    if (sum == 0) return -1;
+    int log = highbit(sum) + 1;
+    if (log > kHufLogMax) return -1;
+    uint32_t left = (1u << log) - sum;
+    if (left & (left - 1)) return -1;
+    int last = highbit(left) + 1;
+    w[nw++] = (uint8_t)last; rank1 += last == 1;
+    if (rank1 < 2 || (rank1 & 1)) return -1;
+    n_w = nw; info.log = log;
+    return 0;
+}
+
+// Canonical table fill: cells are (symbol | nbBits << 8), 1 << log of them.  Weight 1 (longest
+// codes) first, ascending symbol inside a weight.
+FZ_HD void huf_fill_table(uint16_t* table, const uint8_t* w, int n_w, int log)
+{
+    uint32_t start[kHufLogMax + 2];
+    uint32_t rank[kHufLogMax + 2];
+    for (int k = 0; k <= kHufLogMax + 1; k++) rank[k] = 0;
+    for (int s = 0; s < n_w; s++) rank[w[s]]++;
+    uint32_t cur = 0;
+    for (int k = 1; k <= log; k++) { start[k] = cur; cur += rank[k] << (k - 1); }
+    for (int s = 0; s < n_w; s++) {
+        uint32_t wt = w[s]; if (!wt) continue;
+        uint32_t len = 1u << (wt - 1), at = start[wt];
+        uint16_t cell = (uint16_t)((uint32_t)s | ((uint32_t)(log + 1 - (int)wt) << 8));
+        for (uint32_t i = 0; i < len; i++) table[at + i] = cell;
+        start[wt] = at + len;
+    }
+}
+
+// One Huffman stream: regenerates n_out bytes at `out`.  Returns 0 or -1.
+FZ_HD int huf_decode_stream(const uint16_t* table, int log, const uint8_t* p, uint32_t n, uint8_t* out, uint32_t n_out)
+{
+    BackBits br;
+    if (br.init(p, n) != 0) return -1;
+    br.refill();
+    uint32_t i = 0;
+    const uint32_t ulog = (uint32_t)log;
+    for (; i + 2 <= n_out; i += 2) {               // two symbols (<= 24 bits) per refill check
+        if (br.avail <= 32) br.refill();
+        uint32_t c0 = table[br.peek(ulog)]; br.skip(c0 >> 8);
+        uint32_t c1 = table[br.peek(ulog)]; br.skip(c1 >> 8);
+        out[i] = (uint8_t)c0; out[i + 1] = (uint8_t)c1;
+    }
+    if (i < n_out) {
+        if (br.avail <= 32) br.refill();
+        uint32_t c0 = table[br.peek(ulog)]; br.skip(c0 >> 8);
+        out[i] = (uint8_t)c0;
+    }
+    return br.left == 0 ? 0 : -1;
+}
+
+// ------------------------------------------------------------------ sequence tables
+struct SeqConsts {       // small read-only tables, staged in shared memory by the kernels
+    uint32_t ll_base[36]; uint32_t ml_base[53];
+    uint8_t ll_bits[36]; uint8_t ml_bits[53];
+    int16_t ll_def[36]; int16_t of_def[29]; int16_t ml_def[53];
+};
+
+#define FZ_LL_BASE { 0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,18,20,22,24,28,32,40,48,64,128,256,512,1024,2048,4096,8192,16384,32768,65536 }
+#define FZ_ML_BASE { 3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,30,31,32,33,34,35,37,39,41,43,47,51,59,67,83,99,131,259,515,1027,2051,4099,8195,16387,32771,65539 }
+#define FZ_LL_BITS { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,2,2,3,3,4,6,7,8,9,10,11,12,13,14,15,16 }
+#define FZ_ML_BITS { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,2,2,3,3,4,4,5,7,8,9,10,11,12,13,14,15,16 }
+#define FZ_LL_DEF { 4,3,2,2,2,2,2,2,2,2,2,2,2,1,1,1,2,2,2,2,2,2,2,2,2,3,2,1,1,1,1,1,-1,-1,-1,-1 }
+#define FZ_OF_DEF { 1,1,1,1,1,1,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1 }
+#define FZ_ML_DEF { 1,4,3,2,2,2,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1,-1,-1 }
+
+// Position and mode of table `which` (0 LL, 1 OF, 2 ML) inside block b's sequences section.
+// Returns the mode (0 predefined, 1 rle, 2 fse); sets p/n to the description bytes.  -1 on error.
+FZ_HD int locate_table(const Block& b, int which, const uint8_t*& p, uint32_t& n)
+{
+    uint32_t pos = b.seq_hdr;
+    for (int t = 0; t < 3; t++) {
+        int mode = (b.modes >> (6 - 2 * t)) & 3;
+        if (pos > b.csize) return -1;
+        if (t == which) { p = b.src + pos; n = b.csize - pos; return mode; }
+        if (mode == 1) pos += 1;
+        else if (mode == 2) {
+            int16_t norm[64]; int ns, log;
+            int used = read_ncount(b.src + pos, b.csize - pos, t == 0 ? kMaxLL : (t == 1 ? kMaxOF : kMaxML),
+                                   t == 0 ? kLLLog : (t == 1 ? kOFLog : kMLLog), norm, ns, log);
+            if (used < 0) return -1;
+            pos += (uint32_t)used;
+        }
+    }
+    return -1;
+}
+
+// Builds table `which` for block b (resolving Repeat through b.*_src).  used = description bytes
+// consumed in b itself (0 for Predefined / Repeat).  Returns 0 or -1.
+FZ_HD int build_seq_table(const Block* blocks, const Block& b, int which, const uint8_t* p, uint32_t n,
+                          const SeqConsts& K, uint32_t* table, int& log, uint32_t& used, uint16_t* cnt)
+{
+    int mode = (b.modes >> (6 - 2 * which)) & 3;
+    const int max_sym = which == 0 ? kMaxLL : (which == 1 ? kMaxOF : kMaxML);
+    const int max_log = which == 0 ? kLLLog : (which == 1 ? kOFLog : kMLLog);
+    const uint8_t* extra = which == 0 ? K.ll_bits : (which == 2 ? K.ml_bits : nullptr);
+    const bool own = mode != 3;          // description bytes live in this block
+    used = 0;
+    if (!own) {
+        int32_t src = which == 0 ? b.ll_src : (which == 1 ? b.of_src : b.ml_src);
+        if (src < 0) return -1;
+        mode = locate_table(blocks[src], which, p, n);
+        if (mode < 0 || mode == 3) return -1;
+    }
+    if (mode == 0) {
+        const int16_t* def = which == 0 ? K.ll_def : (which == 1 ? K.of_def : K.ml_def);
+        log = which == 1 ? 5 : 6;
+        return build_fse_table(table, def, which == 0 ? 36 : (which == 1 ? 29 : 53), log, extra, cnt);
+    }
+    if (mode == 1) {
+        if (n < 1 || p[0] > max_sym) return -1;
+        uint32_t s = p[0];
+        table[0] = cell_pack(0, 0, extra ? extra[s] : s, s); log = 0;
+        if (own) used = 1;
+        return 0;
+    }
+    int16_t norm[64]; int ns;
+    int u = read_ncount(p, n, max_sym, max_log, norm, ns, log);
+    if (u < 0) return -1;
+    if (own) used = (uint32_t)u;
+    return build_fse_table(table, norm, ns, log, extra, cnt);
+}
+
+// ------------------------------------------------------------------ sequence decode (one thread per block)
+// tables: tLL (512 cells), tOF (256), tML (512), normally in shared memory.  Writes nseq packed
+// records at `out` and the block totals.  Returns 0 or FZG_E_CORRUPT.
+FZ_HD int decode_sequences(const Block* blocks, const Block& b, const SeqConsts& K,
+                           uint32_t* tLL, uint32_t* tOF, uint32_t* tML, uint16_t* cnt,
+                           uint64_t* out, uint32_t& sum_ll, uint32_t& sum_ml)
+{
+    const uint8_t* p = b.src + b.seq_hdr; uint32_t n = b.csize - b.seq_hdr;
+    int logLL, logOF, logML; uint32_t used;
+    if (build_seq_table(blocks, b, 0, p, n, K, tLL, logLL, used, cnt) != 0) return FZG_E_CORRUPT;
+    p += used; n -= used;
+    if (build_seq_table(blocks, b, 1, p, n, K, tOF, logOF, used, cnt) != 0) return FZG_E_CORRUPT;
+    p += used; n -= used;
+    if (build_seq_table(blocks, b, 2, p, n, K, tML, logML, used, cnt) != 0) return FZG_E_CORRUPT;
+    p += used; n -= used;
+
+    BackBits br;
+    if (br.init(p, n) != 0) return FZG_E_CORRUPT;
+    br.refill(); if (br.avail <= 32) br.refill();
+    uint32_t sLL = br.read((uint32_t)logLL);
+    uint32_t sOF = br.read((uint32_t)logOF);
+    uint32_t sML = br.read((uint32_t)logML);
+    if (br.left < 0) return FZG_E_CORRUPT;
+
+    const uint32_t nseq = b.nseq;
+    uint32_t tot_ll = 0, tot_ml = 0; int bad = 0;
+    for (uint32_t i = 0; i < nseq; i++) {
+        const uint32_t cLL = tLL[sLL], cOF = tOF[sOF], cML = tML[sML];
+        const uint32_t ofb = cell_extra(cOF), mlb = cell_extra(cML), llb = cell_extra(cLL);
+        const bool more = i + 1 < nseq;
+        const uint32_t nLL = more ? cell_nb(cLL) : 0, nML = more ? cell_nb(cML) : 0, nOF = more ? cell_nb(cOF) : 0;
+        const uint32_t a1 = ofb, a2 = a1 + mlb, a3 = a2 + llb, a4 = a3 + nLL, a5 = a4 + nML, need = a5 + nOF;
+        if (br.avail <= 32) br.refill();
+        uint32_t ofx, mlx, llx;
+        if (need <= 32) {                     // common case: every field of this sequence sits in `hi`
+            const uint32_t x = br.hi;
+            ofx = shr_c(x, 32 - ofb);
+            mlx = shr_c(shl_c(x, a1), 32 - mlb);
+            llx = shr_c(shl_c(x, a2), 32 - llb);
+            sLL = cell_base(cLL) + shr_c(shl_c(x, a3), 32 - nLL);
+            sML = cell_base(cML) + shr_c(shl_c(x, a4), 32 - nML);
+            sOF = cell_base(cOF) + shr_c(shl_c(x, a5), 32 - nOF);
+            br.skip(need);
+        } else {                              // long offsets / lengths: field by field
+            ofx = br.read(ofb);
+            if (br.avail <= 32) br.refill();
+            mlx = br.read(mlb); llx = br.read(llb);
+            if (br.avail <= 32) br.refill();
+            sLL = cell_base(cLL) + br.read(nLL);
+            sML = cell_base(cML) + br.read(nML);
+            sOF = cell_base(cOF) + br.read(nOF);
+        }
+        const uint32_t ofc = cell_sym(cOF);
+        uint32_t ofv = (1u << ofc) + ofx;
+        if (ofc > 28) { bad = 1; ofv = kOfvCap; }            // offset beyond any legal window (2^27)
+        const uint32_t ml = K.ml_base[cell_sym(cML)] + mlx;
+        const uint32_t ll = K.ll_base[cell_sym(cLL)] + llx;
+        tot_ll += ll; tot_ml += ml;
+        out[i] = seq_pack(ll, ml, ofv);
+    }
+    sum_ll = tot_ll; sum_ml = tot_ml;
+    if (bad || br.left != 0) return FZG_E_CORRUPT;
+    return 0;
+}
+
+// ------------------------------------------------------------------ XXH64 (RFC 8878 3.1.1: Content_Checksum)
+constexpr uint64_t XP1 = 0x9E3779B185EBCA87ull, XP2 = 0xC2B2AE3D27D4EB4Full, XP3 = 0x165667B19E3779F9ull,
+                   XP4 = 0x85EBCA77C2B2AE63ull, XP5 = 0x27D4EB2F165667C5ull;
+FZ_HD uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+FZ_HD uint64_t xx_round(uint64_t acc, uint64_t in) { return rotl64(acc + in * XP2, 31) * XP1; }
+FZ_HD uint64_t xx_merge(uint64_t h, uint64_t v) { return (h ^ xx_round(0, v)) * XP1 + XP4; }
+FZ_HD uint64_t rd64u(const uint8_t* p)
+{
+    if (((uintptr_t)p & 7) == 0) return *(const uint64_t*)p;
+    uint64_t v = 0; for (int i = 0; i < 8; i++) v |= (uint64_t)p[i] << (8 * i); return v;
+}
+// tail: everything after the 32-byte stripes; h already merged (or seed + P5 for short inputs)
+FZ_HD uint64_t xx_finish(uint64_t h, const uint8_t* p, uint64_t rem, uint64_t total)
+{
+    h += total;
+    while (rem >= 8) { h ^= xx_round(0, rd64u(p)); h = rotl64(h, 27) * XP1 + XP4; p += 8; rem -= 8; }
+    if (rem >= 4) { h ^= (uint64_t)rd32u(p) * XP1; h = rotl64(h, 23) * XP2 + XP3; p += 4; rem -= 4; }
+    while (rem) { h ^= (uint64_t)(*p) * XP5; h = rotl64(h, 11) * XP1; p++; rem--; }
+    h ^= h >> 33; h *= XP2; h ^= h >> 29; h *= XP3; h ^= h >> 32;
+    return h;
+}
+
+}  // namespace fz

@@ -1,0 +1,61 @@
+/*
+ * fz_host.h -- per-device context of libfzgpu.so: stream, events, grow-only HBM scratch and
+ * pinned host staging.  One FzCtx per GPU; a call holds the context mutex for its duration, so
+ * several host threads (one per GPU, or several per GPU) may call the C ABI concurrently.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <mutex>
+
+#include "../../include/fzgpu.h"
+
+struct FzDevBuf {
+    void* p = nullptr; size_t cap = 0;
+    int reserve(size_t n)   // grow-only; contents are NOT preserved
+    {
+        if (n <= cap) return 0;
+        size_t want = n + n / 4 + 4096;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); p = nullptr; return -12; /* -ENOMEM */ }
+        cap = want; return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct FzPinBuf {
+    void* p = nullptr; size_t cap = 0;
+    int reserve(size_t n)
+    {
+        if (n <= cap) return 0;
+        size_t want = n + n / 4 + 4096;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        if (cudaMallocHost(&p, want) != cudaSuccess) { cudaGetLastError(); p = nullptr; return -12; }
+        cap = want; return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct FzCtx {
+    int dev = -1;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev[16] = {};
+    std::mutex mu;
+    // descriptors + scratch (HBM)
+    FzDevBuf d_items, d_infos, d_bases, d_outs, d_totals, d_frames, d_blocks, d_seq_jobs, d_huf_jobs, d_lit, d_seq;
+    // staging for host-resident batches
+    FzDevBuf d_stage_src, d_stage_dst;
+    FzPinBuf h_items, h_outs, h_totals, h_stage_src, h_stage_dst;
+    // encoder scratch
+    FzDevBuf e_items, e_outs, e_work;
+    fzg_timing_t timing = {};
+};
+
+// fz_decode.cu
+int fzh_decode_setup(void);
+int fzh_decode_run(FzCtx* c, uint32_t n, int flags);
+const char* fzh_decode_stage_name(int s);

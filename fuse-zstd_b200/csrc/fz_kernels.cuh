@@ -1,0 +1,191 @@
+/*
+ * fz_kernels.cuh -- warp-level stages of the decoder that are shared between the CUDA kernels
+ * (fz_decode.cu) and the test-only host emulation (tests/emul).  The warp is abstracted by a
+ * policy type W { kLanes; lane(); shfl64(v, src); sync(); } so the very same code runs with
+ * 32 lanes on the GPU and with one lane on the host.
+ */
+#pragma once
+#include "fz_core.cuh"
+
+namespace fz {
+
+struct ItemOut { uint64_t dst_len; int32_t status; int32_t fail; };
+
+// ------------------------------------------------------------------ literals pass (four threads per block)
+// thread 0 of the group: tree description (possibly from an earlier block: Treeless) -> table.
+// log < 0 reports a malformed description.
+FZ_HD void lit_build(const Block* blocks, const Block& b, uint16_t* table, int& log, uint32_t& used)
+{
+    const Block& sb = blocks[b.huf_src];
+    uint8_t w[256]; uint32_t ft[64]; uint16_t cnt[64];
+    int nw; HufInfo hi; hi.log = 0; hi.used = 0;
+    if (huf_read_weights(sb.src + sb.lit_hdr, sb.lit_csize, w, nw, hi, ft, cnt) != 0) { log = -1; used = 0; return; }
+    huf_fill_table(table, w, nw, hi.log);
+    log = hi.log; used = hi.used;
+}
+
+// thread `sub` (0..3) of the group: RLE fill or one Huffman stream.  Returns 0 or 1 (corrupt).
+FZ_HD int lit_decode_sub(const Block& b, uint32_t sub, const uint16_t* table, int log, uint32_t used)
+{
+    uint8_t* out = const_cast<uint8_t*>(b.lit);
+    if (b.lit_type == LT_RLE) {
+        const uint8_t v = b.src[b.lit_hdr];
+        for (uint32_t i = sub; i < b.lit_regen; i += 4) out[i] = v;
+        return 0;
+    }
+    if (log < 0) return 1;
+    const uint32_t skip = b.lit_type == LT_HUF ? used : 0;
+    if (skip > b.lit_csize) return 1;
+    const uint8_t* p = b.src + b.lit_hdr + skip;
+    const uint32_t n = b.lit_csize - skip, regen = b.lit_regen;
+    if (b.lit_streams == 1) return sub == 0 ? (huf_decode_stream(table, log, p, n, out, regen) != 0) : 0;
+    if (n < 10) return 1;
+    const uint32_t l1 = p[0] | ((uint32_t)p[1] << 8), l2 = p[2] | ((uint32_t)p[3] << 8), l3 = p[4] | ((uint32_t)p[5] << 8);
+    const uint32_t seg = (regen + 3) / 4;
+    if (6 + l1 + l2 + l3 > n || seg * 3 > regen) return 1;
+    const uint32_t l4 = n - 6 - l1 - l2 - l3;
+    const uint32_t start = sub == 0 ? 0 : (sub == 1 ? l1 : (sub == 2 ? l1 + l2 : l1 + l2 + l3));
+    const uint32_t len = sub == 0 ? l1 : (sub == 1 ? l2 : (sub == 2 ? l3 : l4));
+    const uint32_t cnt_out = sub == 3 ? regen - 3 * seg : seg;
+    return huf_decode_stream(table, log, p + 6 + start, len, out + sub * seg, cnt_out) != 0;
+}
+
+// ------------------------------------------------------------------ sequences pass (one thread per block)
+FZ_HD void seq_thread(Block* blocks, const Frame* frames, Block& b, const SeqConsts& K, uint32_t* tables, uint16_t* cnt,
+                      uint64_t* seqs)
+{
+    uint32_t sum_ll = 0, sum_ml = 0;
+    int st = decode_sequences(blocks, b, K, tables, tables + 512, tables + 768, cnt, seqs + b.seq_base, sum_ll, sum_ml);
+    if (!st && (sum_ll > b.lit_regen || b.lit_regen + sum_ml > frames[b.frame].block_max)) st = FZG_E_CORRUPT;
+    b.rsize = b.lit_regen + sum_ml;
+    if (st && !b.status) b.status = st;
+}
+
+// ------------------------------------------------------------------ checksum pass (four threads per frame)
+FZ_HD uint64_t xx_lane(const uint8_t* p, uint64_t len, uint32_t j)   // accumulator j over all 32-byte stripes
+{
+    uint64_t acc = j == 0 ? XP1 + XP2 : (j == 1 ? XP2 : (j == 2 ? 0 : 0 - XP1));
+    const uint64_t stripes = len >> 5;
+    const uint8_t* q = p + 8 * j;
+    if (((uintptr_t)p & 7) == 0) {
+        uint64_t s = 0;
+        for (; s + 4 <= stripes; s += 4) {               // four loads in flight per thread
+            const uint64_t a = *(const uint64_t*)(q + 32 * s), b = *(const uint64_t*)(q + 32 * s + 32),
+                           c = *(const uint64_t*)(q + 32 * s + 64), d = *(const uint64_t*)(q + 32 * s + 96);
+            acc = xx_round(acc, a); acc = xx_round(acc, b); acc = xx_round(acc, c); acc = xx_round(acc, d);
+        }
+        for (; s < stripes; s++) acc = xx_round(acc, *(const uint64_t*)(q + 32 * s));
+    } else {
+        for (uint64_t s = 0; s < stripes; s++) acc = xx_round(acc, rd64u(q + 32 * s));
+    }
+    return acc;
+}
+FZ_HD uint64_t xx_combine(uint64_t v1, uint64_t v2, uint64_t v3, uint64_t v4, const uint8_t* p, uint64_t len)
+{
+    uint64_t h;
+    if (len >= 32) {
+        h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
+        h = xx_merge(h, v1); h = xx_merge(h, v2); h = xx_merge(h, v3); h = xx_merge(h, v4);
+    } else h = XP5;
+    const uint64_t tail = len & 31;
+    return xx_finish(h, p + (len - tail), tail, len);
+}
+
+// ------------------------------------------------------------------ offsets pass (one thread per item)
+// After the literal and sequence passes every block knows its regenerated size.  Assigns each
+// block / frame its position in the item's dst, folds the first error (in stream order) into the
+// item status and checks Frame_Content_Size and the destination capacity.
+FZ_HD void offsets_item(const Item& it, const ItemInfo& info, const ItemBase& base, Frame* frames, Block* blocks,
+                        ItemOut& out)
+{
+    uint64_t pos = 0; int status = 0;
+    for (uint32_t f = 0; f < info.n_frames && !status; f++) {
+        Frame& fr = frames[base.frame + f];
+        fr.out_off = pos;
+        uint64_t fsize = 0;
+        for (uint32_t k = 0; k < fr.n_blocks; k++) {
+            Block& b = blocks[fr.first_block + k];
+            if (b.status) { status = b.status; break; }
+            if (b.rsize > fr.block_max) { status = FZG_E_CORRUPT; break; }
+            if (it.dst_cap - pos < b.rsize) { status = FZG_E_DSTSIZE; break; }
+            b.out_off = pos; pos += b.rsize; fsize += b.rsize;
+        }
+        if (status) break;
+        fr.out_size = fsize;
+        if (fr.has_fcs && fr.fcs != fsize) { status = FZG_E_FCS; break; }
+    }
+    if (!status) status = info.walk_status;
+    out.dst_len = status ? 0 : pos; out.status = status; out.fail = status != 0;
+}
+
+// finish pass (one thread per item): errors found while executing / checksumming, in frame order
+FZ_HD void finish_item(const ItemInfo& info, const ItemBase& base, const Frame* frames, ItemOut& o)
+{
+    if (o.fail) return;
+    for (uint32_t f = 0; f < info.n_frames; f++) {
+        int st = frames[base.frame + f].status;
+        if (st) { o.status = st; o.fail = 1; o.dst_len = 0; return; }
+    }
+}
+
+// ------------------------------------------------------------------ LZ77 execution (one warp per frame)
+// Sequences are executed in order; each copy is spread over the lanes of the warp.  Overlapping
+// matches (offset < length) are periodic with period `offset`, so byte k of the match equals
+// source byte k % offset and all lanes can proceed independently.
+template <class W>
+FZ_HD void exec_frame(const W& w, Frame& fr, const Block* blocks, const Item& it, const uint64_t* seqs)
+{
+    const uint32_t lane = w.lane();
+    uint8_t* const fbase = it.dst + fr.out_off;
+    uint32_t rep0 = 1, rep1 = 4, rep2 = 8;
+    uint64_t done = 0;                       // bytes of this frame already produced
+    int status = 0;
+    for (uint32_t k = 0; k < fr.n_blocks && !status; k++) {
+        const Block& b = blocks[fr.first_block + k];
+        uint8_t* out = fbase + done;
+        if (b.type == BT_RAW) {
+            for (uint32_t i = lane; i < b.rsize; i += W::kLanes) out[i] = b.src[i];
+        } else if (b.type == BT_RLE) {
+            const uint8_t v = b.src[0];
+            for (uint32_t i = lane; i < b.rsize; i += W::kLanes) out[i] = v;
+        } else {
+            const uint8_t* lit = b.lit;
+            const uint64_t* sq = seqs + b.seq_base;
+            uint32_t o = 0, lp = 0;
+            for (uint32_t g = 0; g < b.nseq && !status; g += W::kLanes) {
+                const uint32_t cnt = b.nseq - g < (uint32_t)W::kLanes ? b.nseq - g : (uint32_t)W::kLanes;
+                uint64_t mine = lane < cnt ? sq[g + lane] : 0;
+                for (uint32_t j = 0; j < cnt; j++) {
+                    const uint64_t r = w.shfl64(mine, j);
+                    const uint32_t ll = seq_ll(r), ml = seq_ml(r), ofv = seq_ofv(r);
+                    uint32_t off;                                   // RFC 8878 3.1.1.5 repeat offsets
+                    if (ofv > 3) { off = ofv - 3; rep2 = rep1; rep1 = rep0; rep0 = off; }
+                    else {
+                        const uint32_t idx = ofv - 1 + (ll == 0);
+                        if (idx == 0) off = rep0;
+                        else {
+                            off = idx == 3 ? rep0 - 1 : (idx == 1 ? rep1 : rep2);
+                            if (off == 0) off = 1;
+                            if (idx != 1) rep2 = rep1;
+                            rep1 = rep0; rep0 = off;
+                        }
+                    }
+                    for (uint32_t i = lane; i < ll; i += W::kLanes) out[o + i] = lit[lp + i];
+                    o += ll; lp += ll;
+                    if ((uint64_t)off > done + o) { status = FZG_E_CORRUPT; break; }
+                    w.sync();
+                    const uint8_t* s = out + o - off;
+                    if (off >= ml) { for (uint32_t i = lane; i < ml; i += W::kLanes) out[o + i] = s[i]; }
+                    else { for (uint32_t i = lane; i < ml; i += W::kLanes) out[o + i] = s[i % off]; }
+                    o += ml;   // the next match is fenced by the sync above; literal stores never alias a pending read
+                }
+            }
+            if (!status) for (uint32_t i = lane; i < b.lit_regen - lp; i += W::kLanes) out[o + i] = lit[lp + i];
+        }
+        done += b.rsize;
+        w.sync();
+    }
+    if (status && lane == 0) fr.status = status;
+}
+
+}  // namespace fz

@@ -1,0 +1,109 @@
+/*
+ * fzgpu.h -- C ABI of libfzgpu.so, the B200-native zstd codec behind fuse-zstd's codec boundary.
+ *
+ * Plain pointers and sizes only; no torch / C++ types.  Every entry point names the reference
+ * interface it replaces (paths relative to /root/reference).  INTEGRATION.md shows the ~30-line
+ * Rust `extern "C"` shim a fuse-zstd maintainer would add.
+ *
+ * Error convention (mirrors src/errors.rs:4-10 and src/main.rs:467): functions return 0 on
+ * success or a NEGATIVE errno-style code for call-level failures (-EINVAL, -ENOMEM, -ENODEV,
+ * -EIO); per-item codec results are reported as non-negative FZG_E_* status codes.  The Rust
+ * shim maps any non-zero decode result to libc::EFAULT (src/main.rs:467) and any encode failure
+ * to EIO (src/errors.rs:9).
+ *
+ * There is no CPU fallback anywhere in this library: without a CUDA device every compute entry
+ * point fails with -ENODEV.
+ */
+#ifndef FZGPU_H
+#define FZGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* per-item codec status (same numbering as oracle/zstd_oracle.h FZO_*) */
+enum {
+    FZG_OK = 0,
+    FZG_E_MAGIC = 1,       /* unknown frame descriptor / trailing garbage          */
+    FZG_E_TRUNCATED = 2,   /* input ends inside a frame (zstd-rs: UnexpectedEof)    */
+    FZG_E_UNSUPPORTED = 3, /* reserved FHD bit, dictionary id, window > 2^27        */
+    FZG_E_CORRUPT = 4,     /* entropy / sequence / block inconsistency              */
+    FZG_E_DSTSIZE = 5,     /* destination capacity too small                        */
+    FZG_E_CHECKSUM = 6,    /* XXH64 content checksum mismatch                       */
+    FZG_E_FCS = 7          /* produced size != Frame_Content_Size                   */
+};
+
+/* flags for the *_batch entry points */
+enum {
+    FZG_SRC_DEVICE = 1,         /* src[i] are device pointers (batch already resident in HBM)   */
+    FZG_DST_DEVICE = 2,         /* dst[i] are device pointers                                   */
+    FZG_NO_VERIFY_CHECKSUM = 4, /* skip XXH64 verification (default: verify, as libzstd does)   */
+    FZG_PROFILE = 8             /* record CUDA-event time per kernel (see fzg_last_timing)      */
+};
+
+/* Creates one context (stream, pinned staging, scratch) per listed CUDA device.  devices == NULL
+ * means "device 0 .. n_devices-1"; n_devices == 0 means all visible devices.  Idempotent. */
+int fzg_init(const int* devices, int n_devices);
+void fzg_shutdown(void);
+int fzg_device_count(void); /* devices with a context */
+
+/*
+ * Replaces  zstd::stream::copy_decode(source_file, target_file)      src/main.rs:463-467
+ * Reads src_fd from its current offset to EOF (all concatenated / skippable frames), writes the
+ * plain bytes to dst_fd at its current offset and leaves both offsets at the end, exactly as
+ * copy_decode's io::copy does.  shard_key = the fuse-zstd inode (src/main.rs:744-753); the GPU is
+ * shard_key % n_devices.  Returns 0, a positive FZG_E_* status, or -errno for I/O failures.
+ */
+int fzg_decode_fd(int src_fd, int dst_fd, uint64_t shard_key, uint64_t* out_size);
+
+/*
+ * Replaces  Encoder::new(w, level) + set_pledged_src_size(Some(n)) + include_checksum(true) +
+ *           io::copy + finish()                                       src/main.rs:781-791
+ * Reads src_size bytes from src_fd (current offset), writes zstd frames to dst_fd.  level follows
+ * src/main.rs:1233-1241 (0 => default 3).  Every frame carries Frame_Content_Size and the XXH64
+ * content checksum; the output is a concatenation of independent frames that stock libzstd
+ * (>= 1.0) decodes to the input.
+ */
+int fzg_encode_fd(int src_fd, int dst_fd, int level, uint64_t src_size, uint64_t shard_key,
+                  uint64_t* out_size);
+
+/*
+ * Batched decode -- the entry point configs 2-4 time.  n independent .zst files; src/dst are
+ * host arrays of n pointers (host or device memory, see flags).  dst_len[i] receives the plain
+ * size, status[i] an FZG_E_* code.  One launch sequence for all n items.  Blocking.
+ */
+int fzg_decode_batch(int device, size_t n, const void* const* src, const size_t* src_len,
+                     void* const* dst, const size_t* dst_cap, size_t* dst_len, int* status, int flags);
+
+/* Batched encode (config 5).  chunk_size = bytes per independent frame (0 => default). */
+int fzg_encode_batch(int device, size_t n, const void* const* src, const size_t* src_len,
+                     void* const* dst, const size_t* dst_cap, size_t* dst_len, int* status,
+                     int level, size_t chunk_size, int flags);
+size_t fzg_encode_bound(size_t src_len, size_t chunk_size);
+
+/*
+ * Host-side header walk (no GPU): sum of Frame_Content_Size over all frames and the number of
+ * compressed bytes the frames occupy.  Lets `lookup`/`getattr` (src/main.rs:40-47) size a file
+ * without decoding it.  *content_size = UINT64_MAX when some frame omits the field.
+ */
+int fzg_frame_info(const void* src, size_t len, uint64_t* content_size, uint64_t* compressed_size);
+
+const char* fzg_strerror(int code);
+
+/* ---- measurement hooks (bench.py); not part of the reference surface ---- */
+typedef struct {
+    float total_ms;        /* first kernel launch -> last kernel end, CUDA events on the ctx stream */
+    float kernel_ms[16];   /* per pipeline stage, FZG_PROFILE only (see fzg_stage_name)             */
+    int   launches;        /* kernels launched by the last *_batch call                              */
+    uint64_t bytes_in, bytes_out;
+} fzg_timing_t;
+int fzg_last_timing(int device, fzg_timing_t* out);
+const char* fzg_stage_name(int stage);
+void* fzg_stream(int device); /* cudaStream_t of the context (for external event timing) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,127 @@
+/*
+ * emul.cpp -- TEST ONLY.  Compiles the decoder's per-thread device code (fz_core.cuh,
+ * fz_kernels.cuh) with g++ and replays fz_decode.cu's launch sequence thread by thread on the
+ * host, so that descriptor/pipeline logic can be checked against the oracle on a machine with
+ * no GPU.  It is never linked into libfzgpu.so and is not a fallback: the product path is CUDA
+ * only.  Warp-level stages run with a one-lane "warp" policy.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../fuse-zstd_b200/csrc/fz_kernels.cuh"
+
+using namespace fz;
+
+static const SeqConsts kConsts = { FZ_LL_BASE, FZ_ML_BASE, FZ_LL_BITS, FZ_ML_BITS, FZ_LL_DEF, FZ_OF_DEF, FZ_ML_DEF };
+
+struct HostWarp {
+    static constexpr int kLanes = 1;
+    uint32_t lane() const { return 0; }
+    uint64_t shfl64(uint64_t v, uint32_t) const { return v; }
+    void sync() const {}
+};
+
+extern "C" int fze_decode_batch(size_t n, const void* const* src, const size_t* src_len, void* const* dst,
+                                const size_t* dst_cap, size_t* dst_len, int* status, int flags)
+{
+    std::vector<Item> items(n);
+    for (size_t i = 0; i < n; i++) items[i] = Item{ (const uint8_t*)src[i], src_len[i], (uint8_t*)dst[i], dst_cap[i] };
+    // count
+    std::vector<ItemInfo> infos(n);
+    for (size_t i = 0; i < n; i++) walk_item<false>((uint32_t)i, items[i], infos[i], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    // scan
+    std::vector<ItemBase> bases(n);
+    ItemBase run{ 0, 0, 0, 0, 0, 0 };
+    for (size_t i = 0; i < n; i++) {
+        bases[i] = run;
+        run.frame += infos[i].n_frames; run.block += infos[i].n_blocks; run.seq_job += infos[i].n_seq_jobs;
+        run.huf_job += infos[i].n_huf_jobs; run.lit += infos[i].lit_bytes; run.seq += infos[i].n_seq;
+    }
+    std::vector<Frame> frames(run.frame + 1);
+    std::vector<Block> blocks(run.block + 1);
+    std::vector<uint32_t> seq_jobs(run.seq_job + 1), huf_jobs(run.huf_job + 1);
+    std::vector<uint8_t> lit(run.lit + 64);
+    std::vector<uint64_t> seqs(run.seq + 8);
+    // fill
+    for (size_t i = 0; i < n; i++) {
+        ItemInfo tmp;
+        walk_item<true>((uint32_t)i, items[i], tmp, &bases[i], frames.data(), blocks.data(), seq_jobs.data(), huf_jobs.data(), lit.data());
+        if (memcmp(&tmp, &infos[i], sizeof tmp) != 0) return -1000;   // the two passes must agree
+    }
+    // literals: group of four threads per job
+    std::vector<uint16_t> table(1 << kHufLogMax);
+    for (uint32_t j = 0; j < run.huf_job; j++) {
+        Block& b = blocks[huf_jobs[j]];
+        int log = 0; uint32_t used = 0;
+        if (b.lit_type >= LT_HUF) lit_build(blocks.data(), b, table.data(), log, used);
+        for (uint32_t sub = 0; sub < 4; sub++)
+            if (lit_decode_sub(b, sub, table.data(), log, used)) b.status = FZG_E_CORRUPT;
+    }
+    // rsize of sequence-less blocks, then sequences
+    for (uint32_t k = 0; k < run.block; k++) if (blocks[k].type == BT_COMPRESSED && blocks[k].nseq == 0) blocks[k].rsize = blocks[k].lit_regen;
+    std::vector<uint32_t> tables(512 + 256 + 512);
+    uint16_t cnt[64];
+    for (uint32_t j = 0; j < run.seq_job; j++)
+        seq_thread(blocks.data(), frames.data(), blocks[seq_jobs[j]], kConsts, tables.data(), cnt, seqs.data());
+    // offsets
+    std::vector<ItemOut> outs(n);
+    for (size_t i = 0; i < n; i++) offsets_item(items[i], infos[i], bases[i], frames.data(), blocks.data(), outs[i]);
+    // execute
+    for (uint32_t f = 0; f < run.frame; f++) {
+        if (outs[frames[f].item].fail) continue;
+        exec_frame(HostWarp(), frames[f], blocks.data(), items[frames[f].item], seqs.data());
+    }
+    // checksum
+    if (!(flags & FZG_NO_VERIFY_CHECKSUM))
+        for (uint32_t f = 0; f < run.frame; f++) {
+            Frame& fr = frames[f];
+            if (!fr.has_checksum || fr.status || outs[fr.item].fail) continue;
+            const uint8_t* p = items[fr.item].dst + fr.out_off;
+            uint64_t v[4];
+            for (uint32_t j = 0; j < 4; j++) v[j] = xx_lane(p, fr.out_size, j);
+            if ((uint32_t)xx_combine(v[0], v[1], v[2], v[3], p, fr.out_size) != fr.checksum) fr.status = FZG_E_CHECKSUM;
+        }
+    // finish
+    for (size_t i = 0; i < n; i++) {
+        finish_item(infos[i], bases[i], frames.data(), outs[i]);
+        dst_len[i] = outs[i].dst_len; status[i] = outs[i].status;
+    }
+    return 0;
+}
+
+/* intermediate stages for one single-frame item: records + literals, for stage-level comparison with
+ * the oracle trace */
+extern "C" int fze_trace(const void* src, size_t src_len, uint64_t* seq_out, size_t seq_cap, size_t* n_seq,
+                         uint8_t* lit_out, size_t lit_cap, size_t* n_lit)
+{
+    Item it{ (const uint8_t*)src, src_len, nullptr, 0 };
+    ItemInfo info; ItemBase base{ 0, 0, 0, 0, 0, 0 };
+    walk_item<false>(0, it, info, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (info.walk_status) return info.walk_status;
+    std::vector<Frame> frames(info.n_frames + 1); std::vector<Block> blocks(info.n_blocks + 1);
+    std::vector<uint32_t> sj(info.n_seq_jobs + 1), hj(info.n_huf_jobs + 1);
+    std::vector<uint8_t> lit(info.lit_bytes + 64); std::vector<uint64_t> seqs(info.n_seq + 8);
+    ItemInfo tmp;
+    walk_item<true>(0, it, tmp, &base, frames.data(), blocks.data(), sj.data(), hj.data(), lit.data());
+    std::vector<uint16_t> table(1 << kHufLogMax);
+    for (uint32_t j = 0; j < info.n_huf_jobs; j++) {
+        Block& b = blocks[hj[j]]; int log = 0; uint32_t used = 0;
+        if (b.lit_type >= LT_HUF) lit_build(blocks.data(), b, table.data(), log, used);
+        for (uint32_t sub = 0; sub < 4; sub++) if (lit_decode_sub(b, sub, table.data(), log, used)) return FZG_E_CORRUPT;
+    }
+    std::vector<uint32_t> tables(1280); uint16_t cnt[64];
+    for (uint32_t j = 0; j < info.n_seq_jobs; j++) seq_thread(blocks.data(), frames.data(), blocks[sj[j]], kConsts, tables.data(), cnt, seqs.data());
+    size_t ns = 0, nl = 0;
+    for (uint32_t k = 0; k < info.n_blocks; k++) {
+        const Block& b = blocks[k];
+        if (b.status) return b.status;
+        if (b.type != BT_COMPRESSED) continue;
+        for (uint32_t i = 0; i < b.nseq; i++, ns++) if (ns < seq_cap) seq_out[ns] = seqs[b.seq_base + i];
+        for (uint32_t i = 0; i < b.lit_regen; i++, nl++) if (nl < lit_cap) lit_out[nl] = b.lit[i];
+    }
+    *n_seq = ns; *n_lit = nl;
+    return 0;
+}

@@ -1,0 +1,59 @@
+"""The C-ABI shared library loads and exports every symbol include/fzgpu.h declares (CPU, no GPU)."""
+import ctypes as C
+import importlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def codec():
+    m = importlib.import_module("fuse-zstd_b200.codec")
+    m.build()
+    return m
+
+
+def test_every_declared_symbol_is_exported(codec):
+    hdr = open(os.path.join(ROOT, "include", "fzgpu.h")).read()
+    declared = set(re.findall(r"\b(fzg_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(codec.EXPORTS), declared ^ set(codec.EXPORTS)
+    L = C.CDLL(codec.SO)
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_no_oracle_linkage(codec):
+    """the product library must not link, load or reference anything under oracle/"""
+    blob = open(codec.SO, "rb").read()
+    for needle in (b"fzo_", b"fzr_", b"libfzoracle", b"libfzref", b"libzstd"):
+        assert needle not in blob, needle
+
+
+def test_frame_info_host_walk(codec, golden):
+    for name, (comp, meta) in golden.items():
+        st, size, csize = codec.frame_info(comp)
+        assert st == 0, name
+        if "nopledge" in name:
+            assert size is None
+        else:
+            assert size == meta["plain_len"], name
+        assert csize == len(comp)
+    assert codec.frame_info(b"junkjunk")[0] == codec.E_MAGIC
+    assert codec.frame_info(golden["json_2000_L3_writer"][0][:100])[0] == codec.E_TRUNCATED
+
+
+def test_strerror(codec):
+    assert b"checksum" in codec.lib().fzg_strerror(codec.E_CHECKSUM)
+
+
+def test_compute_fails_loudly_without_gpu(codec, golden):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(OSError) as e:
+        codec.decode_batch([golden["json_2000_L3_writer"][0]])
+    assert e.value.errno == 19   # ENODEV: no CPU fallback
