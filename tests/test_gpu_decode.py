@@ -1,0 +1,203 @@
+"""Parity tests proper (B200): the CUDA decoder, called through the C ABI (include/fzgpu.h), against
+
+  * the committed golden fixtures (tests/golden: frames libzstd 1.5.5 produced for every block /
+    literals / sequence mode + the byte strings the reference's own tests pin,
+    /root/reference/tests/cmdline.rs:34-43,160-178, tests/convert.rs:16-43,54-98),
+  * the plain-C oracle (oracle/zstd_oracle.c) on seeded inputs, bit-exact, including error statuses,
+  * size-independent properties at larger sizes (stored XXH64 verified on device, FCS == produced).
+
+Nothing here reads /root/reference.  Every test needs a GPU.
+"""
+import hashlib
+import importlib
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+codec = importlib.import_module("fuse-zstd_b200.codec")
+stream = importlib.import_module("fuse-zstd_b200.stream")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    codec.build()
+    codec.init([0])
+    yield
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+def test_golden_vectors_bit_exact(golden, oracle):
+    names = sorted(golden)
+    res = codec.decode_batch([golden[n][0] for n in names], [golden[n][1]["plain_len"] for n in names])
+    for n, (st, out) in zip(names, res):
+        meta = golden[n][1]
+        assert st == 0, (n, codec.strerror(st))
+        assert len(out) == meta["plain_len"] and sha(out) == meta["plain_sha256"], n
+        st_o, out_o = oracle.decode(golden[n][0], cap=meta["plain_len"])
+        assert st_o == 0 and out_o == out, n
+    t = codec.last_timing(0)
+    assert t["launches"] >= 5          # the CUDA pipeline ran (no fallback exists)
+
+
+def test_golden_one_item_per_call(golden):
+    """the open() flow: one file per call (src/main.rs:463), incl. the 13-byte empty frame"""
+    for n in sorted(golden):
+        comp, meta = golden[n]
+        (st, out), = codec.decode_batch([comp], [meta["plain_len"]])
+        assert st == 0 and sha(out) == meta["plain_sha256"], n
+
+
+def test_error_statuses_match_oracle(golden, oracle):
+    comp, meta = golden["json_20000_L3_writer"]
+    n = meta["plain_len"]
+    cases = [b"", b"not a zstd file at all", comp[:-1], comp[: len(comp) // 2], comp + b"\x00", comp + b"garbage!",
+             bytes.fromhex("28b52ffd2000") + bytes([0x07, 0, 0]), bytes.fromhex("28b52ffd21") + b"\x05\x00" + bytes([1, 0, 0]),
+             bytes.fromhex("28b52ffd00") + bytes([18 << 3]) + bytes([1, 0, 0])]
+    for pos, mask in ((len(comp) - 1, 0x55), (4, 0x08), (len(comp) // 2, 0xFF), (40, 0x01), (300, 0x80)):
+        bad = bytearray(comp); bad[pos] ^= mask; cases.append(bytes(bad))
+    frame = bytearray(golden["ref_compressed_data_bulk"][0]); frame[5] = 16; cases.append(bytes(frame))
+    res = codec.decode_batch(cases, [n] * len(cases))
+    for c, (st, out) in zip(cases, res):
+        st_o, out_o = oracle.decode(c, cap=n)
+        assert (st == 0) == (st_o == 0), (st, st_o, c[:16])
+        if st_o == 0:
+            assert out == out_o
+        else:
+            assert st == st_o, (st, st_o, c[:16].hex())
+    (st, _), = codec.decode_batch([comp], [n - 1])
+    assert st in (codec.E_DSTSIZE, codec.E_CORRUPT)
+
+
+def test_mutation_fuzz_matches_oracle(golden, oracle):
+    rs = np.random.RandomState(1234)
+    for name in ("json_20000_L3_writer", "json_200k_L3_nopledge_nochk", "json_120k_L19_wlog11_repeat", "rle_mode_of_ml",
+                 "direct_weights_huffman"):
+        comp, meta = golden[name]
+        cases = []
+        for _ in range(150):
+            bad = bytearray(comp)
+            for _ in range(rs.randint(1, 4)):
+                bad[rs.randint(0, len(bad))] ^= 1 << rs.randint(0, 8)
+            cases.append(bytes(bad))
+        cap = meta["plain_len"] + 64
+        res = codec.decode_batch(cases, [cap] * len(cases))
+        for c, (st, out) in zip(cases, res):
+            st_o, out_o = oracle.decode(c, cap=cap)
+            assert (st == 0) == (st_o == 0), (name, st, st_o)
+            if st == 0:
+                assert out == out_o, name
+
+
+def _mixed_plain(rs, corpus, idx, size):
+    kind = idx % 6
+    if kind == 0:
+        return corpus.json_file(1000 + idx, size).tobytes()
+    if kind == 1:
+        return rs.randint(0, 256, size, dtype=np.uint8).tobytes()                     # incompressible -> Raw blocks
+    if kind == 2:
+        return bytes(rs.randint(0, 16, size, dtype=np.uint8))                         # low entropy
+    if kind == 3:
+        pat = rs.randint(0, 256, 23, dtype=np.uint8).tobytes()
+        return (pat * (size // 23 + 1))[:size]                                        # long repeats / RLE-ish
+    if kind == 4:
+        return (b"a" * size)                                                          # RLE blocks
+    j = corpus.json_file(2000 + idx, size).tobytes()
+    return j[: size // 2] + j[: size - size // 2]                                     # long-distance match
+
+
+def test_seeded_corpus_vs_oracle(ref, oracle, corpus):
+    """levels 1/3/19 x sizes 0..600k x 6 input kinds; reference-writer and bulk framing"""
+    if not ref.available:
+        pytest.skip("system libzstd absent: cannot produce fresh frames")
+    rs = np.random.RandomState(7)
+    blobs, plains = [], []
+    sizes = [0, 1, 7, 100, 1000, 4096, 65536, 131072, 131073, 200000, 600000]
+    for i, size in enumerate(sizes * 3):
+        level = (1, 3, 19)[i % 3] if size <= 200000 else (1, 3)[i % 2]
+        plain = _mixed_plain(rs, corpus, i, size)
+        comp = ref.writer_encode(plain, level) if i % 2 == 0 else ref.bulk_compress(plain, level)
+        blobs.append(comp); plains.append(plain)
+    res = codec.decode_batch(blobs, [len(p) for p in plains])
+    for i, ((st, out), plain, comp) in enumerate(zip(res, plains, blobs)):
+        assert st == 0, (i, codec.strerror(st))
+        assert out == plain, i
+        st_o, out_o = oracle.decode(comp, cap=len(plain))
+        assert st_o == 0 and out_o == out
+
+
+def test_window_and_multiframe(ref, corpus):
+    if not ref.available:
+        pytest.skip("system libzstd absent")
+    plain = corpus.json_file(77, 3 << 20).tobytes()
+    blobs = [ref.writer_encode(plain, 3, window_log=wl) for wl in (10, 14, 17, 20, 22)]
+    blobs.append(ref.writer_encode(plain, 5, pledge=False, checksum=False))
+    multi = b"".join(ref.writer_encode(plain[o:o + 300000], 3) for o in range(0, len(plain), 300000))
+    skippable = bytes.fromhex("502a4d18") + (5).to_bytes(4, "little") + b"hello"
+    blobs.append(skippable + multi + skippable)
+    res = codec.decode_batch(blobs, [len(plain)] * len(blobs))
+    for i, (st, out) in enumerate(res):
+        assert st == 0 and out == plain, i
+
+
+def test_device_resident_batch(golden):
+    """FZG_SRC_DEVICE | FZG_DST_DEVICE: what bench.py's `value` times"""
+    import torch
+    names = [n for n in sorted(golden) if golden[n][1]["plain_len"] > 0]
+    srcs = [torch.frombuffer(bytearray(golden[n][0]), dtype=torch.uint8).cuda() for n in names]
+    dsts = [torch.zeros(golden[n][1]["plain_len"] + 32, dtype=torch.uint8, device="cuda") for n in names]
+    torch.cuda.synchronize()
+    dl, st = codec.decode_batch_ptrs(0, [s.data_ptr() for s in srcs], [s.numel() for s in srcs],
+                                     [d.data_ptr() for d in dsts], [golden[n][1]["plain_len"] for n in names],
+                                     codec.SRC_DEVICE | codec.DST_DEVICE)
+    for n, d, l, s in zip(names, dsts, dl, st):
+        assert s == 0 and l == golden[n][1]["plain_len"], n
+        host = d.cpu().numpy()
+        assert sha(host[:int(l)].tobytes()) == golden[n][1]["plain_sha256"], n
+        assert not host[int(l):].any(), "wrote past dst_len: " + n
+
+
+def test_large_batch_properties(ref, corpus):
+    """1024 x 1 MiB level-3 reference-writer files: FCS == produced, stored XXH64 verified on device,
+    and a checksum of checksums over the outputs equals the one over the plain inputs."""
+    if not ref.available:
+        pytest.skip("system libzstd absent")
+    n, size = 1024, 1 << 20
+    plain = corpus.json_files(500000, n, size)
+    cap = ref.bound(size) + 64
+    comp = np.empty((n, cap), dtype=np.uint8)
+    sp = np.array([plain[i].ctypes.data for i in range(n)], dtype=np.uint64); sl = np.full(n, size, dtype=np.uint64)
+    dp = np.array([comp[i].ctypes.data for i in range(n)], dtype=np.uint64); dc = np.full(n, cap, dtype=np.uint64)
+    _, ol, st = ref.batch(2, os.cpu_count() or 1, sp, sl, dp, dc, 3)
+    assert not st.any()
+    out = np.zeros((n, size), dtype=np.uint8)
+    dl, st = codec.decode_batch_ptrs(0, dp, ol, [out[i].ctypes.data for i in range(n)], [size] * n, 0)
+    assert not st.any() and (dl == size).all()
+    assert hashlib.sha256(out.tobytes()).digest() == hashlib.sha256(plain.tobytes()).digest()
+
+
+def test_fd_entry_points_follow_the_reference_flow(golden):
+    """copy_decode(src_file, tmp_file) as open_wrapper drives it (src/main.rs:461-470)"""
+    comp, meta = golden["json_300000_L3_writer"]
+    with tempfile.TemporaryFile() as src, tempfile.TemporaryFile() as dst:
+        src.write(comp); src.flush(); src.seek(0)
+        n = stream.copy_decode(src, dst, inode=2**64 - 5)
+        assert n == meta["plain_len"]
+        assert os.lseek(dst.fileno(), 0, os.SEEK_CUR) == n        # offset left at the end, like io::copy
+        dst.seek(0)
+        assert sha(dst.read()) == meta["plain_sha256"]
+    with tempfile.TemporaryFile() as src:                          # any failure -> EFAULT (src/main.rs:467)
+        src.write(b"this is not zstd"); src.flush(); src.seek(0)
+        with pytest.raises(OSError) as e:
+            stream.decode_all(src)
+        assert e.value.errno == 14
+    with tempfile.TemporaryFile() as src:                          # empty input decodes to empty output
+        assert stream.decode_all(src) == b""
