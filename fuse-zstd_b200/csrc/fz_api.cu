@@ -61,7 +61,7 @@ extern "C" void fzg_shutdown(void)
         cudaSetDevice(c->dev);
         cudaStreamSynchronize(c->stream);
         FzDevBuf* db[] = { &c->d_items, &c->d_infos, &c->d_bases, &c->d_outs, &c->d_totals, &c->d_frames, &c->d_blocks,
-                           &c->d_seq_jobs, &c->d_huf_jobs, &c->d_lit, &c->d_seq, &c->d_stage_src, &c->d_stage_dst,
+                           &c->d_seq_jobs, &c->d_huf_jobs, &c->d_lit, &c->d_seq, &c->d_spans, &c->d_stage_src, &c->d_stage_dst,
                            &c->e_items, &c->e_outs, &c->e_work };
         for (auto* b : db) b->release();
         FzPinBuf* pb[] = { &c->h_items, &c->h_outs, &c->h_totals, &c->h_stage_src, &c->h_stage_dst };

@@ -38,13 +38,13 @@ struct Item {            // one .zst file of the batch
 
 struct ItemInfo {        // written by the count pass, consumed by the scan
     uint32_t n_frames, n_blocks, n_seq_jobs, n_huf_jobs;
-    uint64_t lit_bytes, n_seq;
+    uint64_t lit_bytes, n_seq, n_spans;
     int32_t walk_status; uint32_t pad;
 };
 
 struct ItemBase {        // exclusive prefix sums over items
     uint32_t frame, block, seq_job, huf_job;
-    uint64_t lit, seq;
+    uint64_t lit, seq, span;
 };
 
 struct Frame {
@@ -63,7 +63,8 @@ enum : uint8_t { LT_RAW = 0, LT_RLE = 1, LT_HUF = 2, LT_TREELESS = 3 };
 struct Block {
     const uint8_t* src;      // block content (after the 3-byte header)
     const uint8_t* lit;      // regenerated literals: into src (Raw) or into literal scratch
-    uint64_t seq_base;       // first record in the sequence scratch
+    uint64_t seq_base;       // first record in the sequence scratch (even, so records can be stored in pairs)
+    uint64_t span_base;      // first entry of this block's span index (one uint16 per kSpan output bytes)
     uint64_t out_off;        // offset in item dst (filled by the offsets pass)
     uint32_t csize;          // Block_Size field
     uint32_t rsize;          // regenerated size (Raw/RLE: known; Compressed: filled by the sequence pass)
@@ -71,16 +72,41 @@ struct Block {
     uint32_t nseq, seq_hdr;  // seq_hdr: offset of the byte after nbSeq(+modes) inside the block
     uint32_t frame;
     int32_t huf_src, ll_src, of_src, ml_src;   // global block index that carries the table description
+    uint32_t rep_out[3];     // repeat-offset history after the block, possibly symbolic (sequence pass)
+    uint32_t rep_in[3];      // resolved history at the start of the block (offsets pass)
     uint8_t type, last, lit_type, lit_streams, modes, pad[3];
     int32_t status;
 };
 
-// 8-byte sequence record in HBM: ll:17 | ml:18 | offset_value:29
-FZ_HD uint64_t seq_pack(uint32_t ll, uint32_t ml, uint32_t ofv) { return (uint64_t)ll | ((uint64_t)ml << 17) | ((uint64_t)ofv << 35); }
-FZ_HD uint32_t seq_ll(uint64_t r) { return (uint32_t)r & 0x1FFFFu; }
-FZ_HD uint32_t seq_ml(uint64_t r) { return (uint32_t)(r >> 17) & 0x3FFFFu; }
-FZ_HD uint32_t seq_ofv(uint64_t r) { return (uint32_t)(r >> 35); }
-constexpr uint32_t kOfvCap = (1u << 29) - 1;
+// 8-byte sequence record in HBM, produced by the sequence pass and consumed by the execute pass:
+//   E  [0:18)   output position (inside the block) just after this sequence's match
+//   LE [18:36)  literals consumed (inside the block) after this sequence's literal run
+//   off[36:64)  match distance: concrete (<= 2^27) or a symbolic reference to the repeat-offset
+//               history the block started with (see off_sym)
+// Sequence i therefore writes literals lit[LE(i-1) .. LE(i)) at E(i-1), then its match up to E(i):
+// every copy's source and destination are known without a serial scan.
+constexpr uint32_t kSpan = 256;                // bytes of output per span-index entry
+FZ_HD uint64_t rec_pack(uint32_t e, uint32_t le, uint32_t off) { return (uint64_t)e | ((uint64_t)le << 18) | ((uint64_t)off << 36); }
+FZ_HD uint32_t rec_e(uint64_t r) { return (uint32_t)r & 0x3FFFFu; }
+FZ_HD uint32_t rec_le(uint64_t r) { return (uint32_t)(r >> 18) & 0x3FFFFu; }
+FZ_HD uint32_t rec_off(uint64_t r) { return (uint32_t)(r >> 36); }
+
+// Repeat offsets across blocks (RFC 8878 3.1.1.5).  Blocks are entropy-decoded in parallel, so a
+// block does not know the three-entry history it starts with.  The sequence pass therefore starts
+// from three symbols in_0..in_2; a history slot is either a concrete distance (<= kOffMax) or
+// "max(in_k - d, 1)" (the `rep0 - 1` rule applied d times), encoded kOffMax | k << 24 | (d + 1).
+// The offsets pass resolves each block's starting history serially (a few values per block) and the
+// execute pass resolves the few records that still carry a symbol, in parallel.
+constexpr uint32_t kOffMax = 1u << 27;         // largest window the reference's streaming decoder accepts
+FZ_HD uint32_t off_sym(uint32_t k) { return kOffMax | (k << 24) | 1u; }
+FZ_HD uint32_t off_dec(uint32_t v) { return v > kOffMax ? v + 1 : (v > 1 ? v - 1 : 1u); }   // rep0 - 1, 0 -> 1
+FZ_HD uint32_t off_resolve(uint32_t v, uint32_t in0, uint32_t in1, uint32_t in2)
+{
+    if (v <= kOffMax) return v;
+    const uint32_t k = (v >> 24) & 3u, d = (v & 0xFFFFFFu) - 1u;
+    const uint32_t x = k == 0 ? in0 : (k == 1 ? in1 : in2);
+    return x > d ? x - d : 1u;
+}
 
 // ------------------------------------------------------------------ small helpers
 FZ_HD int highbit(uint32_t v)
@@ -207,7 +233,7 @@ FZ_HD void walk_item(uint32_t item_idx, const Item& it, ItemInfo& info, const It
 {
     const uint8_t* src = it.src; const uint64_t n = it.src_len;
     uint64_t ip = 0;
-    uint32_t nf = 0, nb = 0, nsj = 0, nhj = 0; uint64_t lit_bytes = 0, n_seq = 0;
+    uint32_t nf = 0, nb = 0, nsj = 0, nhj = 0; uint64_t lit_bytes = 0, n_seq = 0, n_spans = 0;
     int status = FZG_OK;
     while (ip < n) {
         if (n - ip < 4) { status = FZG_E_TRUNCATED; break; }
@@ -237,12 +263,13 @@ FZ_HD void walk_item(uint32_t item_idx, const Item& it, ItemInfo& info, const It
             uint32_t csize = type == BT_RLE ? 1 : bsize;
             if (n - ip < csize) { status = FZG_E_TRUNCATED; break; }
             Block b;
-            b.src = src + ip; b.lit = nullptr; b.seq_base = 0; b.out_off = 0;
+            b.src = src + ip; b.lit = nullptr; b.seq_base = 0; b.span_base = 0; b.out_off = 0;
             b.csize = bsize; b.rsize = type == BT_COMPRESSED ? 0 : bsize;
             b.lit_hdr = b.lit_regen = b.lit_csize = b.nseq = b.seq_hdr = 0;
             b.frame = frame_gidx; b.huf_src = b.ll_src = b.of_src = b.ml_src = -1;
             b.type = (uint8_t)type; b.last = (uint8_t)last; b.lit_type = 0; b.lit_streams = 0; b.modes = 0;
             b.pad[0] = b.pad[1] = b.pad[2] = 0; b.status = 0;
+            for (int r = 0; r < 3; r++) { b.rep_out[r] = off_sym((uint32_t)r); b.rep_in[r] = 0; }
             uint32_t gb = FILL ? base->block + nb : 0;
             if (type == BT_COMPRESSED) {
                 if (bsize < 2) { status = FZG_E_CORRUPT; break; }
@@ -256,6 +283,7 @@ FZ_HD void walk_item(uint32_t item_idx, const Item& it, ItemInfo& info, const It
                 b.lit_hdr = lh.hsize; b.lit_regen = lh.regen; b.lit_csize = lh.csize;
                 b.lit_type = (uint8_t)lh.type; b.lit_streams = (uint8_t)lh.streams;
                 b.nseq = nseq; b.seq_hdr = litsec + shs; b.modes = (uint8_t)modes;
+                if (nseq == 0) b.rsize = lh.regen;         // no sequences: the block regenerates exactly its literals
                 // table provenance is tracked with item-local block numbers (identical in both passes)
                 if (lh.type == LT_HUF) huf_src = (int32_t)nb;
                 else if (lh.type == LT_TREELESS && huf_src < 0) { status = FZG_E_CORRUPT; break; }
@@ -275,7 +303,10 @@ FZ_HD void walk_item(uint32_t item_idx, const Item& it, ItemInfo& info, const It
                     if (FILL) b.lit = lit_scratch + base->lit + lit_bytes;
                     lit_bytes += (lh.regen + 15u) & ~15u;
                 }
-                if (nseq) { if (FILL) { b.seq_base = base->seq + n_seq; seq_jobs[base->seq_job + nsj] = gb; } n_seq += nseq; nsj++; }
+                if (nseq) {
+                    if (FILL) { b.seq_base = base->seq + n_seq; b.span_base = base->span + n_spans; seq_jobs[base->seq_job + nsj] = gb; }
+                    n_seq += (nseq + 1u) & ~1u; n_spans += block_max / kSpan + 2; nsj++;
+                }
                 if (lh.type != LT_RAW) { if (FILL) huf_jobs[base->huf_job + nhj] = gb; nhj++; }
             }
             if (FILL) blocks[gb] = b;
@@ -298,7 +329,7 @@ FZ_HD void walk_item(uint32_t item_idx, const Item& it, ItemInfo& info, const It
         nf++;
     }
     info.n_frames = nf; info.n_blocks = nb; info.n_seq_jobs = nsj; info.n_huf_jobs = nhj;
-    info.lit_bytes = lit_bytes; info.n_seq = n_seq; info.walk_status = status; info.pad = 0;
+    info.lit_bytes = lit_bytes; info.n_seq = n_seq; info.n_spans = n_spans; info.walk_status = status; info.pad = 0;
 }
 
 // ------------------------------------------------------------------ forward bit reader (FSE table descriptions)
@@ -558,10 +589,12 @@ FZ_HD int locate_table(const Block& b, int which, const uint8_t*& p, uint32_t& n
 }
 
 // Builds table `which` for block b (resolving Repeat through b.*_src).  used = description bytes
-// consumed in b itself (0 for Predefined / Repeat).  Returns 0 or -1.
+// consumed in b itself (0 for Predefined / Repeat).  `scratch` = 128 uint16 (normalised counts, then
+// per-symbol counters) in shared memory: nothing on this path touches local memory.  Returns 0 or -1.
 FZ_HD int build_seq_table(const Block* blocks, const Block& b, int which, const uint8_t* p, uint32_t n,
-                          const SeqConsts& K, uint32_t* table, int& log, uint32_t& used, uint16_t* cnt)
+                          const SeqConsts& K, uint32_t* table, int& log, uint32_t& used, uint16_t* scratch)
 {
+    int16_t* norm = (int16_t*)scratch; uint16_t* cnt = scratch + 64;
     int mode = (b.modes >> (6 - 2 * which)) & 3;
     const int max_sym = which == 0 ? kMaxLL : (which == 1 ? kMaxOF : kMaxML);
     const int max_log = which == 0 ? kLLLog : (which == 1 ? kOFLog : kMLLog);
@@ -586,76 +619,215 @@ FZ_HD int build_seq_table(const Block* blocks, const Block& b, int which, const 
         if (own) used = 1;
         return 0;
     }
-    int16_t norm[64]; int ns;
+    int ns;
     int u = read_ncount(p, n, max_sym, max_log, norm, ns, log);
     if (u < 0) return -1;
     if (own) used = (uint32_t)u;
     return build_fse_table(table, norm, ns, log, extra, cnt);
 }
 
-// ------------------------------------------------------------------ sequence decode (one thread per block)
-// tables: tLL (512 cells), tOF (256), tML (512), normally in shared memory.  Writes nseq packed
-// records at `out` and the block totals.  Returns 0 or FZG_E_CORRUPT.
-FZ_HD int decode_sequences(const Block* blocks, const Block& b, const SeqConsts& K,
-                           uint32_t* tLL, uint32_t* tOF, uint32_t* tML, uint16_t* cnt,
-                           uint64_t* out, uint32_t& sum_ll, uint32_t& sum_ml)
+// ------------------------------------------------------------------ sequence bitstream reader
+// The sequence pass is one serial dependency chain per block, so nothing on that chain may wait
+// for HBM: the backward bitstream is pulled in aligned 16-byte chunks, one chunk ahead of use,
+// into registers (q = chunk being consumed, nq = next chunk), with an L2 prefetch further ahead.
+// Bits are served from a top-aligned 64-bit container (hi:lo), refilled 32 bits at a time.
+struct U4 { uint32_t x, y, z, w; };
+
+FZ_HD U4 ld_chunk(const uint8_t* p)             // 16-byte aligned; the chunk always holds >= 1 byte of the stream
 {
-    const uint8_t* p = b.src + b.seq_hdr; uint32_t n = b.csize - b.seq_hdr;
-    int logLL, logOF, logML; uint32_t used;
-    if (build_seq_table(blocks, b, 0, p, n, K, tLL, logLL, used, cnt) != 0) return FZG_E_CORRUPT;
-    p += used; n -= used;
-    if (build_seq_table(blocks, b, 1, p, n, K, tOF, logOF, used, cnt) != 0) return FZG_E_CORRUPT;
-    p += used; n -= used;
-    if (build_seq_table(blocks, b, 2, p, n, K, tML, logML, used, cnt) != 0) return FZG_E_CORRUPT;
-    p += used; n -= used;
+#ifdef __CUDA_ARCH__
+    const uint4 v = __ldg((const uint4*)p);
+    return U4{ v.x, v.y, v.z, v.w };
+#else
+    const uint32_t* w = (const uint32_t*)p;
+    return U4{ w[0], w[1], w[2], w[3] };
+#endif
+}
+FZ_HD void prefetch_l2(const uint8_t* p)
+{
+#ifdef __CUDA_ARCH__
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
 
-    BackBits br;
-    if (br.init(p, n) != 0) return FZG_E_CORRUPT;
-    br.refill(); if (br.avail <= 32) br.refill();
-    uint32_t sLL = br.read((uint32_t)logLL);
-    uint32_t sOF = br.read((uint32_t)logOF);
-    uint32_t sML = br.read((uint32_t)logML);
-    if (br.left < 0) return FZG_E_CORRUPT;
+struct SeqBits {
+    uint32_t hi, lo; int avail, left;
+    const uint8_t* cp;       // address of the chunk held in q
+    const uint8_t* cmin;     // lowest chunk that may be loaded
+    const uint8_t* wmin;     // lowest 4-byte word holding stream bytes
+    U4 q, nq; int qi;        // next word of q to hand out (3 .. 0)
 
-    const uint32_t nseq = b.nseq;
-    uint32_t tot_ll = 0, tot_ml = 0; int bad = 0;
-    for (uint32_t i = 0; i < nseq; i++) {
-        const uint32_t cLL = tLL[sLL], cOF = tOF[sOF], cML = tML[sML];
-        const uint32_t ofb = cell_extra(cOF), mlb = cell_extra(cML), llb = cell_extra(cLL);
-        const bool more = i + 1 < nseq;
-        const uint32_t nLL = more ? cell_nb(cLL) : 0, nML = more ? cell_nb(cML) : 0, nOF = more ? cell_nb(cOF) : 0;
-        const uint32_t a1 = ofb, a2 = a1 + mlb, a3 = a2 + llb, a4 = a3 + nLL, a5 = a4 + nML, need = a5 + nOF;
-        if (br.avail <= 32) br.refill();
-        uint32_t ofx, mlx, llx;
-        if (need <= 32) {                     // common case: every field of this sequence sits in `hi`
-            const uint32_t x = br.hi;
-            ofx = shr_c(x, 32 - ofb);
-            mlx = shr_c(shl_c(x, a1), 32 - mlb);
-            llx = shr_c(shl_c(x, a2), 32 - llb);
-            sLL = cell_base(cLL) + shr_c(shl_c(x, a3), 32 - nLL);
-            sML = cell_base(cML) + shr_c(shl_c(x, a4), 32 - nML);
-            sOF = cell_base(cOF) + shr_c(shl_c(x, a5), 32 - nOF);
-            br.skip(need);
-        } else {                              // long offsets / lengths: field by field
-            ofx = br.read(ofb);
-            if (br.avail <= 32) br.refill();
-            mlx = br.read(mlb); llx = br.read(llb);
-            if (br.avail <= 32) br.refill();
-            sLL = cell_base(cLL) + br.read(nLL);
-            sML = cell_base(cML) + br.read(nML);
-            sOF = cell_base(cOF) + br.read(nOF);
-        }
-        const uint32_t ofc = cell_sym(cOF);
-        uint32_t ofv = (1u << ofc) + ofx;
-        if (ofc > 28) { bad = 1; ofv = kOfvCap; }            // offset beyond any legal window (2^27)
-        const uint32_t ml = K.ml_base[cell_sym(cML)] + mlx;
-        const uint32_t ll = K.ll_base[cell_sym(cLL)] + llx;
-        tot_ll += ll; tot_ml += ml;
-        out[i] = seq_pack(ll, ml, ofv);
+    FZ_HD uint32_t word(int i) const { return i == 3 ? q.w : (i == 2 ? q.z : (i == 1 ? q.y : q.x)); }
+    FZ_HD void rotate()
+    {
+        q = nq; qi = 3; cp -= 16;
+        if (cp - 16 >= cmin) { nq = ld_chunk(cp - 16); if (cp - 256 >= cmin) prefetch_l2(cp - 256); }
+        else nq = U4{ 0, 0, 0, 0 };
     }
-    sum_ll = tot_ll; sum_ml = tot_ml;
-    if (bad || br.left != 0) return FZG_E_CORRUPT;
-    return 0;
+    FZ_HD uint32_t pop()
+    {
+        uint32_t w = word(qi);
+        if (cp + 4 * qi < wmin) w = 0;            // below the first byte of the stream: zero bits
+        if (--qi < 0) rotate();
+        return w;
+    }
+    FZ_HD int init(const uint8_t* p, uint32_t n)
+    {
+        if (n == 0) return -1;
+        const uint8_t* lastp = p + n - 1;
+        const uint32_t lastb = *lastp;
+        if (lastb == 0) return -1;
+        cp = (const uint8_t*)((uintptr_t)lastp & ~(uintptr_t)15);
+        cmin = (const uint8_t*)((uintptr_t)p & ~(uintptr_t)15);
+        wmin = (const uint8_t*)((uintptr_t)p & ~(uintptr_t)3);
+        q = ld_chunk(cp);
+        nq = cp - 16 >= cmin ? ld_chunk(cp - 16) : U4{ 0, 0, 0, 0 };
+        qi = (int)(((uintptr_t)lastp & 15) >> 2);
+        uint32_t w = word(qi);
+        const uint32_t keep = (uint32_t)((uintptr_t)lastp & 3) + 1;
+        if (keep < 4) w &= (1u << (8 * keep)) - 1;
+        if (cp + 4 * qi < wmin) return -1;        // cannot happen: the last byte is inside the stream
+        const int hb = highbit(w);                // sentinel bit
+        hi = shl_c(w, 32 - (uint32_t)hb); lo = 0; avail = hb;
+        left = (int)(n - 1) * 8 + highbit(lastb);
+        if (--qi < 0) rotate();
+        return 0;
+    }
+    FZ_HD void refill()                           // precondition: avail <= 32
+    {
+        const uint32_t w = pop();
+        hi |= shr_c(w, (uint32_t)avail);
+        lo = shl_c(w, 32 - (uint32_t)avail);
+        avail += 32;
+    }
+    FZ_HD uint32_t peek(uint32_t nb) const { return shr_c(hi, 32 - nb); }
+    FZ_HD void skip(uint32_t nb)
+    {
+        hi = fsl_c(lo, hi, nb); lo = shl_c(lo, nb);
+        avail -= (int)nb; left -= (int)nb;
+    }
+    FZ_HD uint32_t read(uint32_t nb) { const uint32_t v = peek(nb); skip(nb); return v; }
+};
+
+FZ_HD void store_rec_pair(uint64_t* at, uint64_t a, uint64_t b)   // `at` is 16-byte aligned
+{
+#ifdef __CUDA_ARCH__
+    *(ulonglong2*)at = make_ulonglong2(a, b);
+#else
+    at[0] = a; at[1] = b;
+#endif
+}
+
+// ------------------------------------------------------------------ sequence decode (one thread per block)
+// tables: tLL (512 cells), tOF (256), tML (512) and `scratch` (64 int16 + 64 uint16) in shared memory.
+// Writes nseq records at `out`, the span index at `span` and b.rsize / b.rep_out.  Returns 0 or
+// FZG_E_CORRUPT.
+//
+// SIMT shape: the lanes of a warp decode different blocks, so the sequence loop must run in lockstep
+// or the warp degenerates into 32 serial threads.  The function therefore has a single exit, the
+// table build (data-dependent control flow) is fenced off with a warp barrier, and the loop runs a
+// warp-uniform number of iterations (`bound` = the largest nseq among the lanes in `mask`), each lane
+// masking itself out once its own block is done or found corrupt.
+#ifdef __CUDA_ARCH__
+#define FZ_SYNCWARP(mask) __syncwarp(mask)
+#else
+#define FZ_SYNCWARP(mask) ((void)(mask))
+#endif
+
+FZ_HD int decode_sequences(const Block* blocks, Block& b, uint32_t block_max, const SeqConsts& K,
+                           uint32_t* tLL, uint32_t* tOF, uint32_t* tML, uint16_t* scratch,
+                           uint64_t* out, uint16_t* span, uint32_t bound, uint32_t mask)
+{
+    int st = 0;
+    int logLL = 0, logOF = 0, logML = 0;
+    SeqBits br;
+    uint32_t sLL = 0, sOF = 0, sML = 0;
+    {
+        const uint8_t* p = b.src + b.seq_hdr; uint32_t n = b.csize - b.seq_hdr; uint32_t used = 0;
+        if (build_seq_table(blocks, b, 0, p, n, K, tLL, logLL, used, scratch) != 0) st = FZG_E_CORRUPT;
+        if (!st) { p += used; n -= used; if (build_seq_table(blocks, b, 1, p, n, K, tOF, logOF, used, scratch) != 0) st = FZG_E_CORRUPT; }
+        if (!st) { p += used; n -= used; if (build_seq_table(blocks, b, 2, p, n, K, tML, logML, used, scratch) != 0) st = FZG_E_CORRUPT; }
+        if (!st) { p += used; n -= used; if (br.init(p, n) != 0) st = FZG_E_CORRUPT; }
+        if (!st) {
+            br.refill(); if (br.avail <= 32) br.refill();
+            sLL = br.read((uint32_t)logLL);
+            sOF = br.read((uint32_t)logOF);
+            sML = br.read((uint32_t)logML);
+            if (br.left < 0) st = FZG_E_CORRUPT;
+        }
+    }
+    const uint32_t nseq = b.nseq, lit_regen = b.lit_regen;
+    uint32_t live = st ? 0 : nseq;                      // this lane's remaining trip count
+    uint32_t rep0 = off_sym(0), rep1 = off_sym(1), rep2 = off_sym(2);
+    uint32_t E = 0, LE = 0;
+    uint64_t held = 0;
+    FZ_SYNCWARP(mask);
+    for (uint32_t i = 0; i < bound; i++) {
+        if (i < live) {
+            const uint32_t cLL = tLL[sLL], cOF = tOF[sOF], cML = tML[sML];
+            const uint32_t ofb = cell_extra(cOF), mlb = cell_extra(cML), llb = cell_extra(cLL);
+            const bool more = i + 1 < nseq;
+            const uint32_t nLL = more ? cell_nb(cLL) : 0, nML = more ? cell_nb(cML) : 0, nOF = more ? cell_nb(cOF) : 0;
+            const uint32_t a1 = ofb, a2 = a1 + mlb, a3 = a2 + llb, a4 = a3 + nLL, a5 = a4 + nML, need = a5 + nOF;
+            if (br.avail <= 32) br.refill();
+            uint32_t ofx, mlx, llx;
+            if (need <= 32) {                     // common case: every field of this sequence sits in `hi`
+                const uint32_t x = br.hi;
+                ofx = shr_c(x, 32 - ofb);
+                mlx = shr_c(shl_c(x, a1), 32 - mlb);
+                llx = shr_c(shl_c(x, a2), 32 - llb);
+                sLL = cell_base(cLL) + shr_c(shl_c(x, a3), 32 - nLL);
+                sML = cell_base(cML) + shr_c(shl_c(x, a4), 32 - nML);
+                sOF = cell_base(cOF) + shr_c(shl_c(x, a5), 32 - nOF);
+                br.skip(need);
+            } else {                              // long offsets / lengths: field by field
+                ofx = br.read(ofb);
+                if (br.avail <= 32) br.refill();
+                mlx = br.read(mlb); llx = br.read(llb);
+                if (br.avail <= 32) br.refill();
+                sLL = cell_base(cLL) + br.read(nLL);
+                sML = cell_base(cML) + br.read(nML);
+                sOF = cell_base(cOF) + br.read(nOF);
+            }
+            const uint32_t ofc = cell_sym(cOF);
+            const uint32_t ofv = (1u << (ofc & 31)) + ofx;
+            const uint32_t ml = K.ml_base[cell_sym(cML)] + mlx;
+            const uint32_t ll = K.ll_base[cell_sym(cLL)] + llx;
+            uint32_t off;                                       // RFC 8878 3.1.1.5 on (possibly symbolic) history
+            if (ofv > 3) { off = ofv - 3; rep2 = rep1; rep1 = rep0; rep0 = off; }
+            else {
+                const uint32_t idx = ofv - 1 + (ll == 0);
+                if (idx == 0) off = rep0;
+                else {
+                    off = idx == 3 ? off_dec(rep0) : (idx == 1 ? rep1 : rep2);
+                    if (idx != 1) rep2 = rep1;
+                    rep1 = rep0; rep0 = off;
+                }
+            }
+            const uint32_t Ep = E;
+            LE += ll; E += ll + ml;
+            if (ofc > 27 || (ofv > 3 && off > kOffMax) || LE > lit_regen || E > block_max) { st = FZG_E_CORRUPT; live = 0; }
+            else {
+                for (uint32_t s = (Ep + kSpan - 1) / kSpan; s <= (E - 1) / kSpan; s++) span[s] = (uint16_t)i;
+                const uint64_t rec = rec_pack(E, LE, off);
+                if (i & 1) store_rec_pair(out + i - 1, held, rec); else held = rec;
+            }
+        }
+    }
+    if (!st && br.left != 0) st = FZG_E_CORRUPT;
+    if (!st) {
+        if (nseq & 1) out[nseq - 1] = held;
+        const uint32_t rsize = E + (lit_regen - LE);
+        if (rsize > block_max) st = FZG_E_CORRUPT;
+        else {
+            for (uint32_t s = (E + kSpan - 1) / kSpan; s * kSpan < rsize; s++) span[s] = (uint16_t)nseq;     // trailing literals
+            b.rsize = rsize;
+            b.rep_out[0] = rep0; b.rep_out[1] = rep1; b.rep_out[2] = rep2;
+        }
+    }
+    return st;
 }
 
 // ------------------------------------------------------------------ XXH64 (RFC 8878 3.1.1: Content_Checksum)

@@ -17,6 +17,8 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 
+#include <algorithm>
+
 #include "fz_host.h"
 #include "fz_kernels.cuh"
 
@@ -34,38 +36,38 @@ __global__ void k_count(const Item* items, ItemInfo* infos, uint32_t n)
     infos[i] = info;
 }
 
-// single CTA; exclusive scan of six counters over the items.  totals[0..5] = frames, blocks,
-// seq jobs, huf jobs, literal bytes, sequences.
+// single CTA; exclusive scan of seven counters over the items.  totals[0..6] = frames, blocks,
+// seq jobs, huf jobs, literal bytes, sequence records, span-index entries.
 __global__ void k_scan(const ItemInfo* infos, ItemBase* bases, uint64_t* totals, uint32_t n)
 {
-    __shared__ uint64_t part[1024][6];
+    __shared__ uint64_t part[512][7];
     const uint32_t t = threadIdx.x, T = blockDim.x;
     const uint32_t per = (n + T - 1) / T;
     const uint32_t lo = t * per < n ? t * per : n, hi = lo + per < n ? lo + per : n;
-    uint64_t acc[6] = { 0, 0, 0, 0, 0, 0 };
+    uint64_t acc[7] = { 0, 0, 0, 0, 0, 0, 0 };
     for (uint32_t i = lo; i < hi; i++) {
         const ItemInfo& f = infos[i];
         acc[0] += f.n_frames; acc[1] += f.n_blocks; acc[2] += f.n_seq_jobs; acc[3] += f.n_huf_jobs;
-        acc[4] += f.lit_bytes; acc[5] += f.n_seq;
+        acc[4] += f.lit_bytes; acc[5] += f.n_seq; acc[6] += f.n_spans;
     }
-    for (int c = 0; c < 6; c++) part[t][c] = acc[c];
+    for (int c = 0; c < 7; c++) part[t][c] = acc[c];
     __syncthreads();
     if (t == 0) {
-        uint64_t run[6] = { 0, 0, 0, 0, 0, 0 };
+        uint64_t run[7] = { 0, 0, 0, 0, 0, 0, 0 };
         for (uint32_t k = 0; k < T; k++)
-            for (int c = 0; c < 6; c++) { uint64_t v = part[k][c]; part[k][c] = run[c]; run[c] += v; }
-        for (int c = 0; c < 6; c++) totals[c] = run[c];
+            for (int c = 0; c < 7; c++) { uint64_t v = part[k][c]; part[k][c] = run[c]; run[c] += v; }
+        for (int c = 0; c < 7; c++) totals[c] = run[c];
     }
     __syncthreads();
-    for (int c = 0; c < 6; c++) acc[c] = part[t][c];
+    for (int c = 0; c < 7; c++) acc[c] = part[t][c];
     for (uint32_t i = lo; i < hi; i++) {
         const ItemInfo& f = infos[i];
         ItemBase b;
         b.frame = (uint32_t)acc[0]; b.block = (uint32_t)acc[1]; b.seq_job = (uint32_t)acc[2]; b.huf_job = (uint32_t)acc[3];
-        b.lit = acc[4]; b.seq = acc[5];
+        b.lit = acc[4]; b.seq = acc[5]; b.span = acc[6];
         bases[i] = b;
         acc[0] += f.n_frames; acc[1] += f.n_blocks; acc[2] += f.n_seq_jobs; acc[3] += f.n_huf_jobs;
-        acc[4] += f.lit_bytes; acc[5] += f.n_seq;
+        acc[4] += f.lit_bytes; acc[5] += f.n_seq; acc[6] += f.n_spans;
     }
 }
 
@@ -102,30 +104,42 @@ __global__ void __launch_bounds__(kLitThreads) k_literals(Block* blocks, const u
 }
 
 // ------------------------------------------------------------------ sequences
-constexpr int kSeqLanes = 22;                    // blocks per CTA (one thread each); 2 CTAs per SM
-constexpr int kSeqTableCells = 512 + 256 + 512;  // LL, OF, ML cells (4 B each) per thread
+// One thread per block (the FSE state chain is serial), one CTA per SM.  What bounds this stage is
+// shared memory: a stream needs its three decode tables (LL 512 + OF 256 + ML 512 cells of 4 bytes)
+// plus 256 bytes of table-build scratch, so 43 streams fit in the 227 KB of an SM.  Each warp draws
+// its next batch of blocks from a global ticket.
+constexpr int kSeqStreams = 43;
+constexpr int kSeqThreads = 64;
+constexpr int kSeqTableCells = 512 + 256 + 512;
+constexpr int kSeqStreamBytes = kSeqTableCells * 4 + 256;
+constexpr int kSeqSmem = kSeqStreams * kSeqStreamBytes;
 
-__global__ void __launch_bounds__(32) k_sequences(Block* blocks, const Frame* frames, const uint32_t* jobs, uint32_t n_jobs,
-                                                  uint64_t* seqs)
+__global__ void __launch_bounds__(kSeqThreads, 1) k_sequences(Block* blocks, const Frame* frames, const uint32_t* jobs,
+                                                                uint32_t n_jobs, uint64_t* seqs, uint16_t* spans, uint32_t* ticket)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ SeqConsts K;
     for (uint32_t i = threadIdx.x; i < sizeof(SeqConsts) / 4; i += blockDim.x) ((uint32_t*)&K)[i] = ((const uint32_t*)&c_seq_consts)[i];
     __syncthreads();
-    const uint32_t job = blockIdx.x * kSeqLanes + threadIdx.x;
-    if (threadIdx.x >= kSeqLanes || job >= n_jobs) return;
-    uint16_t cnt[64];
-    seq_thread(blocks, frames, blocks[jobs[job]], K, (uint32_t*)smem + threadIdx.x * kSeqTableCells, cnt, seqs);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t first = warp == 0 ? 0 : (kSeqStreams + 1) / 2, lanes = warp == 0 ? (kSeqStreams + 1) / 2 : kSeqStreams / 2;
+    uint8_t* mine = smem + (first + lane) * kSeqStreamBytes;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(ticket, lanes);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n_jobs) return;
+        const uint32_t job = base + lane;
+        const bool on = lane < lanes && job < n_jobs;
+        Block* b = on ? &blocks[jobs[job]] : nullptr;
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, on);
+        const uint32_t bound = __reduce_max_sync(0xFFFFFFFFu, on ? b->nseq : 0u);
+        if (on) seq_thread(blocks, frames, *b, K, (uint32_t*)mine, (uint16_t*)(mine + kSeqTableCells * 4), seqs, spans, bound, mask);
+        __syncwarp();
+    }
 }
 
-// blocks without sequences regenerate exactly their literals
-__global__ void k_rsize_nseq0(Block* blocks, uint32_t n_blocks)
-{
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_blocks && blocks[i].type == BT_COMPRESSED && blocks[i].nseq == 0) blocks[i].rsize = blocks[i].lit_regen;
-}
-
-// ------------------------------------------------------------------ offsets / execute / checksum / finish
+// ------------------------------------------------------------------ offsets
 __global__ void k_offsets(const Item* items, const ItemInfo* infos, const ItemBase* bases, Frame* frames, Block* blocks,
                           ItemOut* outs, uint32_t n)
 {
@@ -136,22 +150,230 @@ __global__ void k_offsets(const Item* items, const ItemInfo* infos, const ItemBa
     outs[i] = o;
 }
 
-struct GpuWarp {
-    static constexpr int kLanes = 32;
-    __device__ __forceinline__ uint32_t lane() const { return threadIdx.x & 31; }
-    __device__ __forceinline__ uint64_t shfl64(uint64_t v, uint32_t src) const { return __shfl_sync(0xFFFFFFFFu, v, src); }
-    __device__ __forceinline__ void sync() const { __syncwarp(); }
-};
+// ------------------------------------------------------------------ execute (LZ77)
+// One CTA per frame at a time (frames are drawn from a ticket); the frame's blocks are executed in
+// order, each assembled in a 128 KiB shared-memory tile and then streamed to HBM with 16-byte
+// stores, so match sources inside the block are shared-memory reads and only window references to
+// earlier blocks go to L2/HBM.
+//
+// Inside a block the work is split by OUTPUT position, not by sequence: the block is cut into spans
+// of 256 bytes, spans go round-robin to the warps, and each lane owns one aligned 8-byte chunk of
+// its warp's span.  Because a sequence record carries cumulative positions (rec_e / rec_le), a lane
+// finds the sequence covering its chunk with a five-step search over 32 records (the span index
+// gives the first one) and then walks the pieces of its chunk -- literal run, match, next sequence
+// -- pulling up to 8 source bytes per piece with two aligned loads and a funnel shift.  A chunk is
+// written once, with one conflict-free 8-byte shared store.
+//
+// Ordering: s_front is the block-wide frontier (every byte below it is final).  Spans retire in
+// order; a piece whose source is not yet final waits for the next pass of the span loop, and inside
+// a span the frontier is the position reached by the first unfinished lane, so at least one lane
+// advances every pass.  Overlapping matches (offset < length) are periodic with period `offset` and
+// are redirected to the period that precedes the match.
+constexpr int kExecWarps = 16;
+constexpr uint32_t kTilePad = 48;
+constexpr uint32_t kExecSmem = kBlockMax + kTilePad;
+constexpr uint32_t kFull = 0xFFFFFFFFu;
 
-constexpr int kExecWarps = 4;
-__global__ void __launch_bounds__(kExecWarps * 32) k_execute(Frame* frames, const Block* blocks, const Item* items,
-                                                              const ItemOut* outs, const uint64_t* seqs, uint32_t n_frames)
+__device__ __forceinline__ uint64_t funnel8(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t byte_shift)
 {
-    const uint32_t f = blockIdx.x * kExecWarps + (threadIdx.x >> 5);
-    if (f >= n_frames) return;
-    Frame& fr = frames[f];
-    if (outs[fr.item].fail) return;
-    exec_frame(GpuWarp(), fr, blocks, items[fr.item], seqs);
+    if (byte_shift >= 4) { x0 = x1; x1 = x2; x2 = x3; }
+    const uint32_t r = (byte_shift & 3) * 8;
+    const uint32_t lo = __funnelshift_r(x0, x1, r), hi = __funnelshift_r(x1, x2, r);
+    return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+// 8 bytes starting at tile[s]; the tile is 8-byte aligned and padded
+__device__ __forceinline__ uint64_t ld8_tile(const uint8_t* tile, uint32_t s)
+{
+    const uint32_t a = s & ~7u;
+    const uint2 w0 = *(const uint2*)(tile + a), w1 = *(const uint2*)(tile + a + 8);
+    return funnel8(w0.x, w0.y, w1.x, w1.y, s & 7u);
+}
+// nb (1..8) bytes starting at g in global memory; never touches an 8-byte word that holds no wanted byte
+__device__ __forceinline__ uint64_t ld8_global(const uint8_t* g, uint32_t nb)
+{
+    const uintptr_t a = (uintptr_t)g & ~(uintptr_t)7;
+    const uint32_t sh = (uint32_t)((uintptr_t)g & 7);
+    const uint2 w0 = *(const uint2*)a;
+    uint2 w1 = make_uint2(0, 0);
+    if (sh + nb > 8) w1 = *(const uint2*)(a + 8);
+    return funnel8(w0.x, w0.y, w1.x, w1.y, sh);
+}
+
+__device__ __forceinline__ void cta_copy(uint8_t* dst, const uint8_t* src, uint32_t n)
+{
+    if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) {
+        const uint32_t nv = n >> 4;
+        for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x) ((uint4*)dst)[i] = ((const uint4*)src)[i];
+        for (uint32_t i = (nv << 4) + threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    } else {
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
+// tile[0 .. n) -> g (any alignment), 16-byte global stores
+__device__ __forceinline__ void cta_flush(uint8_t* g, const uint8_t* tile, uint32_t n)
+{
+    const uint32_t head = min(n, (uint32_t)((16 - ((uintptr_t)g & 15)) & 15));
+    for (uint32_t i = threadIdx.x; i < head; i += blockDim.x) g[i] = tile[i];
+    const uint32_t nv = (n - head) >> 4;
+    uint4* gv = (uint4*)(g + head);
+    const uint32_t ws = head >> 2, bs = (head & 3) * 8;      // uniform for the whole block
+    if (head == 0) {
+        for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x) gv[i] = ((const uint4*)tile)[i];
+    } else {
+        for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x) {
+            const uint4 a = ((const uint4*)tile)[i], b = ((const uint4*)tile)[i + 1];
+            uint32_t w0, w1, w2, w3, w4;
+            switch (ws) {
+            case 0: w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; break;
+            case 1: w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; break;
+            case 2: w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; break;
+            default: w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; break;
+            }
+            gv[i] = make_uint4(__funnelshift_r(w0, w1, bs), __funnelshift_r(w1, w2, bs), __funnelshift_r(w2, w3, bs),
+                               __funnelshift_r(w3, w4, bs));
+        }
+    }
+    for (uint32_t i = head + (nv << 4) + threadIdx.x; i < n; i += blockDim.x) g[i] = tile[i];
+}
+
+__device__ __forceinline__ void exec_block(uint8_t* tile, const Block& b, const uint64_t* __restrict__ sq,
+                                           const uint16_t* __restrict__ sp, const uint8_t* g0, uint64_t done,
+                                           volatile uint32_t* s_front, int* s_status)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nseq = b.nseq, rsize = b.rsize, lit_regen = b.lit_regen;
+    const uint8_t* __restrict__ lit = b.lit;
+    const uint32_t in0 = b.rep_in[0], in1 = b.rep_in[1], in2 = b.rep_in[2];
+    const uint32_t n_spans = (rsize + kSpan - 1) / kSpan;
+
+    for (uint32_t n = warp; n < n_spans; n += kExecWarps) {
+        const uint32_t ss = n * kSpan, P = ss + 8 * lane;
+        const bool active = P < rsize;
+        const uint32_t Pend = active ? min(P + 8, rsize) : P;
+
+        // ---- the sequence that covers byte P: first record with E > P
+        uint32_t k = 0xFFFFFFFFu;
+        for (uint32_t kb = sp[n];; kb += 32) {
+            const uint32_t j = kb + lane;
+            const uint32_t Ej = j < nseq ? rec_e(__ldg(sq + j)) : rsize;     // past the last sequence: trailing literals
+            uint32_t c = 0;
+#pragma unroll
+            for (int st = 16; st >= 1; st >>= 1) {
+                const uint32_t e = __shfl_sync(kFull, Ej, (c + st - 1) & 31);
+                if (e <= P) c += st;
+            }
+            const uint32_t e31 = __shfl_sync(kFull, Ej, 31);
+            if (c == 31 && e31 <= P) c = 32;
+            if (active && k == 0xFFFFFFFFu && c < 32) k = kb + c;
+            if (!__any_sync(kFull, active && k == 0xFFFFFFFFu)) break;
+        }
+
+        uint32_t S = 0, LEp = 0, M = 0, E = 0, LE = 0, off = 1;
+        auto fetch = [&](uint32_t kk) {          // sequence kk becomes current; (S, LEp) must hold its predecessor's ends
+            if (kk < nseq) {
+                const uint64_t r = __ldg(sq + kk);
+                E = rec_e(r); LE = rec_le(r); off = off_resolve(rec_off(r), in0, in1, in2);
+                M = S + (LE - LEp);
+                if ((uint64_t)off > done + M) { off = 0; atomicMax(s_status, FZG_E_CORRUPT); }   // before the frame start
+            } else { E = rsize; LE = lit_regen; off = 1; M = E; }
+        };
+        if (active) {
+            if (k > 0) { const uint64_t r = __ldg(sq + (k - 1 < nseq ? k - 1 : nseq - 1)); S = rec_e(r); LEp = rec_le(r); }
+            fetch(k);
+        }
+
+        uint32_t pos = P, filled = 0, myfront = ss;
+        uint64_t acc = 0;
+        for (;;) {                                  // passes over the span: at least one lane advances in every pass
+            const uint32_t Fv = *s_front;
+            __threadfence_block();
+            const uint32_t Fs = Fv >= ss ? myfront : Fv;
+            bool go = active && pos < Pend, wrote = false;
+            // lockstep piece loop: one vote per step keeps the lanes converged
+            while (__any_sync(kFull, go)) {
+                if (go) {
+                    if (pos >= E) { k++; S = E; LEp = LE; fetch(k); }
+                    uint64_t v = 0; uint32_t nb;
+                    if (pos < M) {                                         // literal run
+                        nb = min(M, Pend) - pos;
+                        v = ld8_global(lit + LEp + (pos - S), nb);
+                    } else {                                               // match
+                        nb = min(E, Pend) - pos;
+                        if (off != 0) {
+                            int32_t s = (int32_t)pos - (int32_t)off;
+                            if (s >= (int32_t)M) {                         // overlapping match: periodic, read the first period
+                                const uint32_t r = (pos - M) % off;
+                                s = (int32_t)(M - off + r); nb = min(nb, off - r);
+                            }
+                            if (s < 0) { nb = min(nb, (uint32_t)(-s)); v = ld8_global(g0 + s, nb); }    // window: earlier blocks, in HBM
+                            else if ((uint32_t)s + nb <= Fs) v = ld8_tile(tile, (uint32_t)s);
+                            else if ((uint32_t)s < Fs) { nb = Fs - (uint32_t)s; v = ld8_tile(tile, (uint32_t)s); }
+                            else if ((uint32_t)s >= P) { nb = 1; v = (acc >> (64 - 8 * filled + 8 * ((uint32_t)s - P))) & 0xFF; }   // own chunk
+                            else { nb = 0; go = false; }                   // produced by a lane / warp that has not got there yet
+                        }
+                    }
+                    if (nb) {
+                        acc = nb == 8 ? v : ((acc >> (8 * nb)) | (v << (64 - 8 * nb)));
+                        filled += nb; pos += nb; wrote = true;
+                        go = pos < Pend;
+                    }
+                }
+            }
+            if (wrote) *(uint64_t*)(tile + P) = filled == 8 ? acc : (acc >> (64 - 8 * filled));
+            __syncwarp();
+            const uint32_t m = __ballot_sync(kFull, active && pos < Pend);
+            if (!m) break;
+            myfront = __shfl_sync(kFull, pos, __ffs(m) - 1);
+        }
+        if (lane == 0) {                       // retire the span in order
+            __threadfence_block();
+            while (*s_front != ss) { }
+            *s_front = min(ss + kSpan, rsize);
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(kExecWarps * 32, 1) k_execute(Frame* frames, const Block* blocks, const Item* items,
+                                                                 const ItemOut* outs, const uint64_t* seqs, const uint16_t* spans,
+                                                                 uint32_t n_frames, uint32_t* ticket)
+{
+    extern __shared__ __align__(16) uint8_t tile[];
+    __shared__ volatile uint32_t s_front;
+    __shared__ uint32_t s_next;
+    __shared__ int s_status;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) { s_next = atomicAdd(ticket, 1); s_status = 0; }
+        __syncthreads();
+        const uint32_t f = s_next;
+        if (f >= n_frames) return;
+        Frame& fr = frames[f];
+        if (outs[fr.item].fail) continue;
+        uint8_t* const fbase = items[fr.item].dst + fr.out_off;
+        uint64_t done = 0;
+        for (uint32_t kb = 0; kb < fr.n_blocks; kb++) {
+            const Block& b = blocks[fr.first_block + kb];
+            uint8_t* const g0 = fbase + done;
+            const uint32_t rsize = b.rsize;
+            if (b.type == BT_RAW) cta_copy(g0, b.src, rsize);
+            else if (b.type == BT_RLE) {
+                const uint8_t v = b.src[0];
+                for (uint32_t i = threadIdx.x; i < rsize; i += blockDim.x) g0[i] = v;
+            } else if (b.nseq == 0) cta_copy(g0, b.lit, rsize);
+            else {
+                if (threadIdx.x == 0) s_front = 0;
+                __syncthreads();
+                exec_block(tile, b, seqs + b.seq_base, spans + b.span_base, g0, done, &s_front, &s_status);
+                __syncthreads();
+                cta_flush(g0, tile, rsize);
+            }
+            __syncthreads();                   // the tile is reused, and later blocks read this one from HBM
+            done += rsize;
+        }
+        if (threadIdx.x == 0 && s_status) fr.status = s_status;
+    }
 }
 
 // Four threads per frame, one XXH64 accumulator each (stripe = 32 bytes, lane j owns bytes 8j..8j+7).
@@ -188,10 +410,15 @@ const char* fzh_decode_stage_name(int s) { return s >= 0 && s < 9 ? kStageNames[
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "fzgpu: %s failed: %s (%s:%d)\n", #x, cudaGetErrorString(e_), __FILE__, __LINE__); return -5 /*-EIO*/; } } while (0)
 
+static int g_sm_count = 148;
+
 int fzh_decode_setup(void)
 {
     CK(cudaFuncSetAttribute(k_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, kLitGroups * kHufTableCells * 2));
-    CK(cudaFuncSetAttribute(k_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqLanes * kSeqTableCells * 4));
+    CK(cudaFuncSetAttribute(k_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqSmem));
+    CK(cudaFuncSetAttribute(k_execute, cudaFuncAttributeMaxDynamicSharedMemorySize, kExecSmem));
+    int dev = 0; CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
     return 0;
 }
 
@@ -208,21 +435,23 @@ int fzh_decode_run(FzCtx* c, uint32_t n, int flags)
     if ((rc = c->d_infos.reserve(n * sizeof(ItemInfo)))) return rc;
     if ((rc = c->d_bases.reserve(n * sizeof(ItemBase)))) return rc;
     if ((rc = c->d_outs.reserve(n * sizeof(ItemOut)))) return rc;
-    if ((rc = c->d_totals.reserve(64))) return rc;
+    if ((rc = c->d_totals.reserve(128))) return rc;
     Item* d_items = (Item*)c->d_items.p; ItemInfo* d_infos = (ItemInfo*)c->d_infos.p; ItemBase* d_bases = (ItemBase*)c->d_bases.p;
     ItemOut* d_outs = (ItemOut*)c->d_outs.p; uint64_t* d_totals = (uint64_t*)c->d_totals.p;
+    uint32_t* d_tickets = (uint32_t*)(d_totals + 8);               // [0] sequences, [1] execute
 
     CK(cudaMemcpyAsync(d_items, c->h_items.p, n * sizeof(Item), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(d_tickets, 0, 16, s));
     int ev = 0;
     auto mark = [&]() { if (prof || ev == 0) cudaEventRecord(c->ev[ev], s); ev++; };
     mark();                                                         // ev0: start
     const uint32_t tb = 128, gi = (n + tb - 1) / tb;
     k_count<<<gi, tb, 0, s>>>(d_items, d_infos, n); mark();
-    k_scan<<<1, 1024, 0, s>>>(d_infos, d_bases, d_totals, n); mark();
-    CK(cudaMemcpyAsync(c->h_totals.p, d_totals, 48, cudaMemcpyDeviceToHost, s));
+    k_scan<<<1, 512, 0, s>>>(d_infos, d_bases, d_totals, n); mark();
+    CK(cudaMemcpyAsync(c->h_totals.p, d_totals, 56, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     const uint64_t* tot = (const uint64_t*)c->h_totals.p;
-    const uint64_t n_frames = tot[0], n_blocks = tot[1], n_sj = tot[2], n_hj = tot[3], lit_bytes = tot[4], n_seq = tot[5];
+    const uint64_t n_frames = tot[0], n_blocks = tot[1], n_sj = tot[2], n_hj = tot[3], lit_bytes = tot[4], n_seq = tot[5], n_spans = tot[6];
     if (n_blocks >= (1ull << 31) || n_frames >= (1ull << 31)) return -22;
     if ((rc = c->d_frames.reserve((n_frames + 1) * sizeof(Frame)))) return rc;
     if ((rc = c->d_blocks.reserve((n_blocks + 1) * sizeof(Block)))) return rc;
@@ -230,18 +459,25 @@ int fzh_decode_run(FzCtx* c, uint32_t n, int flags)
     if ((rc = c->d_huf_jobs.reserve((n_hj + 1) * 4))) return rc;
     if ((rc = c->d_lit.reserve(lit_bytes + 64))) return rc;
     if ((rc = c->d_seq.reserve((n_seq + 8) * 8))) return rc;
+    if ((rc = c->d_spans.reserve((n_spans + 8) * 2))) return rc;
     Frame* d_frames = (Frame*)c->d_frames.p; Block* d_blocks = (Block*)c->d_blocks.p;
     uint32_t* d_sj = (uint32_t*)c->d_seq_jobs.p; uint32_t* d_hj = (uint32_t*)c->d_huf_jobs.p;
+    uint64_t* d_seq = (uint64_t*)c->d_seq.p; uint16_t* d_spans = (uint16_t*)c->d_spans.p;
 
     k_fill<<<gi, tb, 0, s>>>(d_items, d_infos, d_bases, d_frames, d_blocks, d_sj, d_hj, (uint8_t*)c->d_lit.p, n); mark();
     int launches = 3;
     if (n_hj) { k_literals<<<(uint32_t)((n_hj + kLitGroups - 1) / kLitGroups), kLitThreads, kLitGroups * kHufTableCells * 2, s>>>(d_blocks, d_hj, (uint32_t)n_hj); launches++; }
     mark();
-    if (n_blocks) { k_rsize_nseq0<<<(uint32_t)((n_blocks + 255) / 256), 256, 0, s>>>(d_blocks, (uint32_t)n_blocks); launches++; }
-    if (n_sj) { k_sequences<<<(uint32_t)((n_sj + kSeqLanes - 1) / kSeqLanes), 32, kSeqLanes * kSeqTableCells * 4, s>>>(d_blocks, d_frames, d_sj, (uint32_t)n_sj, (uint64_t*)c->d_seq.p); launches++; }
+    if (n_sj) {
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((n_sj + kSeqStreams - 1) / kSeqStreams, (uint64_t)g_sm_count);
+        k_sequences<<<grid, kSeqThreads, kSeqSmem, s>>>(d_blocks, d_frames, d_sj, (uint32_t)n_sj, d_seq, d_spans, d_tickets); launches++;
+    }
     mark();
     k_offsets<<<gi, tb, 0, s>>>(d_items, d_infos, d_bases, d_frames, d_blocks, d_outs, n); mark(); launches++;
-    if (n_frames) { k_execute<<<(uint32_t)((n_frames + kExecWarps - 1) / kExecWarps), kExecWarps * 32, 0, s>>>(d_frames, d_blocks, d_items, d_outs, (const uint64_t*)c->d_seq.p, (uint32_t)n_frames); launches++; }
+    if (n_frames) {
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(n_frames, (uint64_t)g_sm_count);
+        k_execute<<<grid, kExecWarps * 32, kExecSmem, s>>>(d_frames, d_blocks, d_items, d_outs, d_seq, d_spans, (uint32_t)n_frames, d_tickets + 1); launches++;
+    }
     mark();
     if (n_frames && !(flags & FZG_NO_VERIFY_CHECKSUM)) { k_checksum<<<(uint32_t)((n_frames * 4 + 127) / 128), 128, 0, s>>>(d_frames, d_items, d_outs, (uint32_t)n_frames); launches++; }
     mark();

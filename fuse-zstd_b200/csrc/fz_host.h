@@ -46,7 +46,7 @@ struct FzCtx {
     cudaEvent_t ev[16] = {};
     std::mutex mu;
     // descriptors + scratch (HBM)
-    FzDevBuf d_items, d_infos, d_bases, d_outs, d_totals, d_frames, d_blocks, d_seq_jobs, d_huf_jobs, d_lit, d_seq;
+    FzDevBuf d_items, d_infos, d_bases, d_outs, d_totals, d_frames, d_blocks, d_seq_jobs, d_huf_jobs, d_lit, d_seq, d_spans;
     // staging for host-resident batches
     FzDevBuf d_stage_src, d_stage_dst;
     FzPinBuf h_items, h_outs, h_totals, h_stage_src, h_stage_dst;

@@ -1,8 +1,7 @@
 /*
  * fz_kernels.cuh -- warp-level stages of the decoder that are shared between the CUDA kernels
- * (fz_decode.cu) and the test-only host emulation (tests/emul).  The warp is abstracted by a
- * policy type W { kLanes; lane(); shfl64(v, src); sync(); } so the very same code runs with
- * 32 lanes on the GPU and with one lane on the host.
+ * (fz_decode.cu) and the test-only host emulation (tests/emul), which replays them thread by thread.
+ * The LZ77 execute pass is warp-cooperative CUDA and lives in fz_decode.cu only.
  */
 #pragma once
 #include "fz_core.cuh"
@@ -51,13 +50,13 @@ FZ_HD int lit_decode_sub(const Block& b, uint32_t sub, const uint16_t* table, in
 }
 
 // ------------------------------------------------------------------ sequences pass (one thread per block)
-FZ_HD void seq_thread(Block* blocks, const Frame* frames, Block& b, const SeqConsts& K, uint32_t* tables, uint16_t* cnt,
-                      uint64_t* seqs)
+// tables = 1280 cells (LL 512 | OF 256 | ML 512), scratch = 128 uint16, both in shared memory.
+// bound / mask: see decode_sequences (warp-uniform trip count and the lanes that take part).
+FZ_HD void seq_thread(Block* blocks, const Frame* frames, Block& b, const SeqConsts& K, uint32_t* tables, uint16_t* scratch,
+                      uint64_t* seqs, uint16_t* spans, uint32_t bound, uint32_t mask)
 {
-    uint32_t sum_ll = 0, sum_ml = 0;
-    int st = decode_sequences(blocks, b, K, tables, tables + 512, tables + 768, cnt, seqs + b.seq_base, sum_ll, sum_ml);
-    if (!st && (sum_ll > b.lit_regen || b.lit_regen + sum_ml > frames[b.frame].block_max)) st = FZG_E_CORRUPT;
-    b.rsize = b.lit_regen + sum_ml;
+    const int st = decode_sequences(blocks, b, frames[b.frame].block_max, K, tables, tables + 512, tables + 768, scratch,
+                                    seqs + b.seq_base, spans + b.span_base, bound, mask);
     if (st && !b.status) b.status = st;
 }
 
@@ -103,12 +102,19 @@ FZ_HD void offsets_item(const Item& it, const ItemInfo& info, const ItemBase& ba
         Frame& fr = frames[base.frame + f];
         fr.out_off = pos;
         uint64_t fsize = 0;
+        uint32_t r0 = 1, r1 = 4, r2 = 8;              // RFC 8878 3.1.1.5: history at the start of a frame
         for (uint32_t k = 0; k < fr.n_blocks; k++) {
             Block& b = blocks[fr.first_block + k];
             if (b.status) { status = b.status; break; }
             if (b.rsize > fr.block_max) { status = FZG_E_CORRUPT; break; }
             if (it.dst_cap - pos < b.rsize) { status = FZG_E_DSTSIZE; break; }
             b.out_off = pos; pos += b.rsize; fsize += b.rsize;
+            if (b.type == BT_COMPRESSED && b.nseq) {
+                b.rep_in[0] = r0; b.rep_in[1] = r1; b.rep_in[2] = r2;
+                const uint32_t n0 = off_resolve(b.rep_out[0], r0, r1, r2), n1 = off_resolve(b.rep_out[1], r0, r1, r2),
+                               n2 = off_resolve(b.rep_out[2], r0, r1, r2);
+                r0 = n0; r1 = n1; r2 = n2;
+            }
         }
         if (status) break;
         fr.out_size = fsize;
@@ -126,66 +132,6 @@ FZ_HD void finish_item(const ItemInfo& info, const ItemBase& base, const Frame* 
         int st = frames[base.frame + f].status;
         if (st) { o.status = st; o.fail = 1; o.dst_len = 0; return; }
     }
-}
-
-// ------------------------------------------------------------------ LZ77 execution (one warp per frame)
-// Sequences are executed in order; each copy is spread over the lanes of the warp.  Overlapping
-// matches (offset < length) are periodic with period `offset`, so byte k of the match equals
-// source byte k % offset and all lanes can proceed independently.
-template <class W>
-FZ_HD void exec_frame(const W& w, Frame& fr, const Block* blocks, const Item& it, const uint64_t* seqs)
-{
-    const uint32_t lane = w.lane();
-    uint8_t* const fbase = it.dst + fr.out_off;
-    uint32_t rep0 = 1, rep1 = 4, rep2 = 8;
-    uint64_t done = 0;                       // bytes of this frame already produced
-    int status = 0;
-    for (uint32_t k = 0; k < fr.n_blocks && !status; k++) {
-        const Block& b = blocks[fr.first_block + k];
-        uint8_t* out = fbase + done;
-        if (b.type == BT_RAW) {
-            for (uint32_t i = lane; i < b.rsize; i += W::kLanes) out[i] = b.src[i];
-        } else if (b.type == BT_RLE) {
-            const uint8_t v = b.src[0];
-            for (uint32_t i = lane; i < b.rsize; i += W::kLanes) out[i] = v;
-        } else {
-            const uint8_t* lit = b.lit;
-            const uint64_t* sq = seqs + b.seq_base;
-            uint32_t o = 0, lp = 0;
-            for (uint32_t g = 0; g < b.nseq && !status; g += W::kLanes) {
-                const uint32_t cnt = b.nseq - g < (uint32_t)W::kLanes ? b.nseq - g : (uint32_t)W::kLanes;
-                uint64_t mine = lane < cnt ? sq[g + lane] : 0;
-                for (uint32_t j = 0; j < cnt; j++) {
-                    const uint64_t r = w.shfl64(mine, j);
-                    const uint32_t ll = seq_ll(r), ml = seq_ml(r), ofv = seq_ofv(r);
-                    uint32_t off;                                   // RFC 8878 3.1.1.5 repeat offsets
-                    if (ofv > 3) { off = ofv - 3; rep2 = rep1; rep1 = rep0; rep0 = off; }
-                    else {
-                        const uint32_t idx = ofv - 1 + (ll == 0);
-                        if (idx == 0) off = rep0;
-                        else {
-                            off = idx == 3 ? rep0 - 1 : (idx == 1 ? rep1 : rep2);
-                            if (off == 0) off = 1;
-                            if (idx != 1) rep2 = rep1;
-                            rep1 = rep0; rep0 = off;
-                        }
-                    }
-                    for (uint32_t i = lane; i < ll; i += W::kLanes) out[o + i] = lit[lp + i];
-                    o += ll; lp += ll;
-                    if ((uint64_t)off > done + o) { status = FZG_E_CORRUPT; break; }
-                    w.sync();
-                    const uint8_t* s = out + o - off;
-                    if (off >= ml) { for (uint32_t i = lane; i < ml; i += W::kLanes) out[o + i] = s[i]; }
-                    else { for (uint32_t i = lane; i < ml; i += W::kLanes) out[o + i] = s[i % off]; }
-                    o += ml;   // the next match is fenced by the sync above; literal stores never alias a pending read
-                }
-            }
-            if (!status) for (uint32_t i = lane; i < b.lit_regen - lp; i += W::kLanes) out[o + i] = lit[lp + i];
-        }
-        done += b.rsize;
-        w.sync();
-    }
-    if (status && lane == 0) fr.status = status;
 }
 
 }  // namespace fz

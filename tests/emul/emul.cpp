@@ -17,12 +17,39 @@ using namespace fz;
 
 static const SeqConsts kConsts = { FZ_LL_BASE, FZ_ML_BASE, FZ_LL_BITS, FZ_ML_BITS, FZ_LL_DEF, FZ_OF_DEF, FZ_ML_DEF };
 
-struct HostWarp {
-    static constexpr int kLanes = 1;
-    uint32_t lane() const { return 0; }
-    uint64_t shfl64(uint64_t v, uint32_t) const { return v; }
-    void sync() const {}
-};
+// TEST-ONLY serial executor over the records the sequence pass emits (the product's execute pass is the
+// warp-cooperative CUDA kernel k_execute; this checks the record / span / repeat-offset logic on the CPU).
+static void exec_frame_serial(Frame& fr, const Block* blocks, const Item& it, const uint64_t* seqs, const uint16_t* spans)
+{
+    uint8_t* const fbase = it.dst + fr.out_off;
+    uint64_t done = 0;
+    for (uint32_t k = 0; k < fr.n_blocks; k++) {
+        const Block& b = blocks[fr.first_block + k];
+        uint8_t* out = fbase + done;
+        if (b.type == BT_RAW) memcpy(out, b.src, b.rsize);
+        else if (b.type == BT_RLE) memset(out, b.src[0], b.rsize);
+        else {
+            const uint64_t* sq = seqs + b.seq_base;
+            uint32_t S = 0, LEp = 0;
+            for (uint32_t i = 0; i < b.nseq; i++) {
+                const uint32_t E = rec_e(sq[i]), LE = rec_le(sq[i]);
+                const uint32_t off = off_resolve(rec_off(sq[i]), b.rep_in[0], b.rep_in[1], b.rep_in[2]);
+                const uint32_t ll = LE - LEp, M = S + ll;
+                // span index: entry s names the sequence covering output byte s * kSpan
+                for (uint32_t sp = (S + kSpan - 1) / kSpan; sp * kSpan < E; sp++)
+                    if (spans[b.span_base + sp] != i) { fr.status = FZG_E_CORRUPT; return; }
+                memcpy(out + S, b.lit + LEp, ll);
+                if ((uint64_t)off > done + M) { fr.status = FZG_E_CORRUPT; return; }
+                for (uint32_t q = M; q < E; q++) out[q] = out[(int64_t)q - off];
+                S = E; LEp = LE;
+            }
+            for (uint32_t sp = (S + kSpan - 1) / kSpan; sp * kSpan < b.rsize; sp++)
+                if (b.nseq && spans[b.span_base + sp] != b.nseq) { fr.status = FZG_E_CORRUPT; return; }
+            memcpy(out + S, b.lit + LEp, b.lit_regen - LEp);
+        }
+        done += b.rsize;
+    }
+}
 
 extern "C" int fze_decode_batch(size_t n, const void* const* src, const size_t* src_len, void* const* dst,
                                 const size_t* dst_cap, size_t* dst_len, int* status, int flags)
@@ -34,17 +61,18 @@ extern "C" int fze_decode_batch(size_t n, const void* const* src, const size_t* 
     for (size_t i = 0; i < n; i++) walk_item<false>((uint32_t)i, items[i], infos[i], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     // scan
     std::vector<ItemBase> bases(n);
-    ItemBase run{ 0, 0, 0, 0, 0, 0 };
+    ItemBase run{ 0, 0, 0, 0, 0, 0, 0 };
     for (size_t i = 0; i < n; i++) {
         bases[i] = run;
         run.frame += infos[i].n_frames; run.block += infos[i].n_blocks; run.seq_job += infos[i].n_seq_jobs;
-        run.huf_job += infos[i].n_huf_jobs; run.lit += infos[i].lit_bytes; run.seq += infos[i].n_seq;
+        run.huf_job += infos[i].n_huf_jobs; run.lit += infos[i].lit_bytes; run.seq += infos[i].n_seq; run.span += infos[i].n_spans;
     }
     std::vector<Frame> frames(run.frame + 1);
     std::vector<Block> blocks(run.block + 1);
     std::vector<uint32_t> seq_jobs(run.seq_job + 1), huf_jobs(run.huf_job + 1);
     std::vector<uint8_t> lit(run.lit + 64);
     std::vector<uint64_t> seqs(run.seq + 8);
+    std::vector<uint16_t> spans(run.span + 8);
     // fill
     for (size_t i = 0; i < n; i++) {
         ItemInfo tmp;
@@ -60,19 +88,18 @@ extern "C" int fze_decode_batch(size_t n, const void* const* src, const size_t* 
         for (uint32_t sub = 0; sub < 4; sub++)
             if (lit_decode_sub(b, sub, table.data(), log, used)) b.status = FZG_E_CORRUPT;
     }
-    // rsize of sequence-less blocks, then sequences
-    for (uint32_t k = 0; k < run.block; k++) if (blocks[k].type == BT_COMPRESSED && blocks[k].nseq == 0) blocks[k].rsize = blocks[k].lit_regen;
+    // sequences
     std::vector<uint32_t> tables(512 + 256 + 512);
-    uint16_t cnt[64];
+    uint16_t scratch[128];
     for (uint32_t j = 0; j < run.seq_job; j++)
-        seq_thread(blocks.data(), frames.data(), blocks[seq_jobs[j]], kConsts, tables.data(), cnt, seqs.data());
+        seq_thread(blocks.data(), frames.data(), blocks[seq_jobs[j]], kConsts, tables.data(), scratch, seqs.data(), spans.data(), blocks[seq_jobs[j]].nseq, 1);
     // offsets
     std::vector<ItemOut> outs(n);
     for (size_t i = 0; i < n; i++) offsets_item(items[i], infos[i], bases[i], frames.data(), blocks.data(), outs[i]);
     // execute
     for (uint32_t f = 0; f < run.frame; f++) {
         if (outs[frames[f].item].fail) continue;
-        exec_frame(HostWarp(), frames[f], blocks.data(), items[frames[f].item], seqs.data());
+        exec_frame_serial(frames[f], blocks.data(), items[frames[f].item], seqs.data(), spans.data());
     }
     // checksum
     if (!(flags & FZG_NO_VERIFY_CHECKSUM))
@@ -98,12 +125,12 @@ extern "C" int fze_trace(const void* src, size_t src_len, uint64_t* seq_out, siz
                          uint8_t* lit_out, size_t lit_cap, size_t* n_lit)
 {
     Item it{ (const uint8_t*)src, src_len, nullptr, 0 };
-    ItemInfo info; ItemBase base{ 0, 0, 0, 0, 0, 0 };
+    ItemInfo info; ItemBase base{ 0, 0, 0, 0, 0, 0, 0 };
     walk_item<false>(0, it, info, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     if (info.walk_status) return info.walk_status;
     std::vector<Frame> frames(info.n_frames + 1); std::vector<Block> blocks(info.n_blocks + 1);
     std::vector<uint32_t> sj(info.n_seq_jobs + 1), hj(info.n_huf_jobs + 1);
-    std::vector<uint8_t> lit(info.lit_bytes + 64); std::vector<uint64_t> seqs(info.n_seq + 8);
+    std::vector<uint8_t> lit(info.lit_bytes + 64); std::vector<uint64_t> seqs(info.n_seq + 8); std::vector<uint16_t> spans(info.n_spans + 8);
     ItemInfo tmp;
     walk_item<true>(0, it, tmp, &base, frames.data(), blocks.data(), sj.data(), hj.data(), lit.data());
     std::vector<uint16_t> table(1 << kHufLogMax);
@@ -112,14 +139,23 @@ extern "C" int fze_trace(const void* src, size_t src_len, uint64_t* seq_out, siz
         if (b.lit_type >= LT_HUF) lit_build(blocks.data(), b, table.data(), log, used);
         for (uint32_t sub = 0; sub < 4; sub++) if (lit_decode_sub(b, sub, table.data(), log, used)) return FZG_E_CORRUPT;
     }
-    std::vector<uint32_t> tables(1280); uint16_t cnt[64];
-    for (uint32_t j = 0; j < info.n_seq_jobs; j++) seq_thread(blocks.data(), frames.data(), blocks[sj[j]], kConsts, tables.data(), cnt, seqs.data());
+    std::vector<uint32_t> tables(1280); uint16_t scratch[128];
+    for (uint32_t j = 0; j < info.n_seq_jobs; j++) seq_thread(blocks.data(), frames.data(), blocks[sj[j]], kConsts, tables.data(), scratch, seqs.data(), spans.data(), blocks[sj[j]].nseq, 1);
+    it.dst_cap = ~0ull;
+    ItemOut io; offsets_item(it, info, base, frames.data(), blocks.data(), io);      // resolves every block's starting history
     size_t ns = 0, nl = 0;
     for (uint32_t k = 0; k < info.n_blocks; k++) {
         const Block& b = blocks[k];
         if (b.status) return b.status;
         if (b.type != BT_COMPRESSED) continue;
-        for (uint32_t i = 0; i < b.nseq; i++, ns++) if (ns < seq_cap) seq_out[ns] = seqs[b.seq_base + i];
+        uint32_t S = 0, LEp = 0;
+        for (uint32_t i = 0; i < b.nseq; i++, ns++) {           // (ll : 17 | ml : 18 | resolved distance : 29)
+            const uint64_t r = seqs[b.seq_base + i];
+            const uint32_t ll = rec_le(r) - LEp, ml = rec_e(r) - S - ll;
+            const uint32_t off = off_resolve(rec_off(r), b.rep_in[0], b.rep_in[1], b.rep_in[2]);
+            if (ns < seq_cap) seq_out[ns] = (uint64_t)ll | ((uint64_t)ml << 17) | ((uint64_t)off << 35);
+            S = rec_e(r); LEp = rec_le(r);
+        }
         for (uint32_t i = 0; i < b.lit_regen; i++, nl++) if (nl < lit_cap) lit_out[nl] = b.lit[i];
     }
     *n_seq = ns; *n_lit = nl;
