@@ -117,8 +117,22 @@ FZ_HD int highbit(uint32_t v)
     return 31 - __builtin_clz(v);
 #endif
 }
-FZ_HD uint32_t shl_c(uint32_t v, uint32_t n) { return n >= 32 ? 0u : v << n; }   // clamped shifts
-FZ_HD uint32_t shr_c(uint32_t v, uint32_t n) { return n >= 32 ? 0u : v >> n; }
+FZ_HD uint32_t shl_c(uint32_t v, uint32_t n)   // clamped shifts: a count >= 32 gives 0 (PTX shl/shr semantics)
+{
+#ifdef __CUDA_ARCH__
+    uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r;
+#else
+    return n >= 32 ? 0u : v << n;
+#endif
+}
+FZ_HD uint32_t shr_c(uint32_t v, uint32_t n)
+{
+#ifdef __CUDA_ARCH__
+    uint32_t r; asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r;
+#else
+    return n >= 32 ? 0u : v >> n;
+#endif
+}
 FZ_HD uint32_t fsl_c(uint32_t lo, uint32_t hi, uint32_t n)                        // high word of (hi:lo << n), n clamped to 32
 {
 #ifdef __CUDA_ARCH__
@@ -627,80 +641,83 @@ FZ_HD int build_seq_table(const Block* blocks, const Block& b, int which, const 
 }
 
 // ------------------------------------------------------------------ sequence bitstream reader
-// The sequence pass is one serial dependency chain per block, so nothing on that chain may wait
-// for HBM: the backward bitstream is pulled in aligned 16-byte chunks, one chunk ahead of use,
-// into registers (q = chunk being consumed, nq = next chunk), with an L2 prefetch further ahead.
-// Bits are served from a top-aligned 64-bit container (hi:lo), refilled 32 bits at a time.
-struct U4 { uint32_t x, y, z, w; };
-
-FZ_HD U4 ld_chunk(const uint8_t* p)             // 16-byte aligned; the chunk always holds >= 1 byte of the stream
+// The sequence pass is one serial dependency chain per block and the lanes of a warp run different
+// blocks in lockstep, so the reader must neither wait for HBM nor branch.  The backward bitstream is
+// mirrored into a 256-byte shared-memory ring (ring byte = global address & 255) by cp.async, 16 bytes
+// at a time and ~240 bytes ahead of use; the consumer takes 32-bit words from the ring with one LDS
+// and serves bits from a top-aligned 64-bit container (hi:lo).
+FZ_HD void ring_fetch(uint8_t* ring_slot, const uint8_t* gsrc)        // one aligned 16-byte chunk -> ring
 {
 #ifdef __CUDA_ARCH__
-    const uint4 v = __ldg((const uint4*)p);
-    return U4{ v.x, v.y, v.z, v.w };
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(ring_slot)), "l"(gsrc) : "memory");
 #else
-    const uint32_t* w = (const uint32_t*)p;
-    return U4{ w[0], w[1], w[2], w[3] };
+    for (int i = 0; i < 16; i++) ring_slot[i] = gsrc[i];
 #endif
 }
-FZ_HD void prefetch_l2(const uint8_t* p)
+FZ_HD void ring_commit()
 {
 #ifdef __CUDA_ARCH__
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-    (void)p;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N> FZ_HD void ring_wait()
+{
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 #endif
 }
 
 struct SeqBits {
     uint32_t hi, lo; int avail, left;
-    const uint8_t* cp;       // address of the chunk held in q
-    const uint8_t* cmin;     // lowest chunk that may be loaded
-    const uint8_t* wmin;     // lowest 4-byte word holding stream bytes
-    U4 q, nq; int qi;        // next word of q to hand out (3 .. 0)
+    const uint8_t* cmin;     // 16-byte aligned address at or below the first byte of the stream
+    uint8_t* ring;           // 256 bytes of shared memory, 16-byte aligned
+    uint32_t rb;             // (uint32_t)cmin & 255
+    int32_t wa;              // offset from cmin of the next word to hand out (going down)
+    int32_t fa;              // offset from cmin of the next chunk to fetch (going down)
+    int32_t wmin;            // offset of the lowest word holding stream bytes
 
-    FZ_HD uint32_t word(int i) const { return i == 3 ? q.w : (i == 2 ? q.z : (i == 1 ? q.y : q.x)); }
-    FZ_HD void rotate()
+    FZ_HD void top_up()                          // at most one chunk per call; a slot is free once the consumer is below it
     {
-        q = nq; qi = 3; cp -= 16;
-        if (cp - 16 >= cmin) { nq = ld_chunk(cp - 16); if (cp - 256 >= cmin) prefetch_l2(cp - 256); }
-        else nq = U4{ 0, 0, 0, 0 };
+        if (fa >= 0 && fa + 256 > wa) { ring_fetch(ring + ((rb + (uint32_t)fa) & 255u), cmin + fa); fa -= 16; }
+        ring_commit();
     }
     FZ_HD uint32_t pop()
     {
-        uint32_t w = word(qi);
-        if (cp + 4 * qi < wmin) w = 0;            // below the first byte of the stream: zero bits
-        if (--qi < 0) rotate();
+        uint32_t w = *(const uint32_t*)(ring + ((rb + (uint32_t)wa) & 255u));
+        if (wa < wmin) w = 0;                     // below the first byte of the stream: zero bits
+        wa -= 4;
         return w;
     }
-    FZ_HD int init(const uint8_t* p, uint32_t n)
+    FZ_HD int init(const uint8_t* p, uint32_t n, uint8_t* ring_)
     {
         if (n == 0) return -1;
         const uint8_t* lastp = p + n - 1;
         const uint32_t lastb = *lastp;
         if (lastb == 0) return -1;
-        cp = (const uint8_t*)((uintptr_t)lastp & ~(uintptr_t)15);
+        ring = ring_;
         cmin = (const uint8_t*)((uintptr_t)p & ~(uintptr_t)15);
-        wmin = (const uint8_t*)((uintptr_t)p & ~(uintptr_t)3);
-        q = ld_chunk(cp);
-        nq = cp - 16 >= cmin ? ld_chunk(cp - 16) : U4{ 0, 0, 0, 0 };
-        qi = (int)(((uintptr_t)lastp & 15) >> 2);
-        uint32_t w = word(qi);
+        rb = (uint32_t)(uintptr_t)cmin & 255u;
+        wmin = (int32_t)((p - cmin) & ~(ptrdiff_t)3);
+        wa = (int32_t)((lastp - cmin) & ~(ptrdiff_t)3);
+        fa = wa & ~15;
+        for (int i = 0; i < 16; i++) top_up();    // fill the ring
+        ring_wait<0>();
+        uint32_t w = pop();
         const uint32_t keep = (uint32_t)((uintptr_t)lastp & 3) + 1;
         if (keep < 4) w &= (1u << (8 * keep)) - 1;
-        if (cp + 4 * qi < wmin) return -1;        // cannot happen: the last byte is inside the stream
-        const int hb = highbit(w);                // sentinel bit
+        const int hb = highbit(w);                // sentinel bit (w != 0: the last byte is non-zero)
         hi = shl_c(w, 32 - (uint32_t)hb); lo = 0; avail = hb;
         left = (int)(n - 1) * 8 + highbit(lastb);
-        if (--qi < 0) rotate();
         return 0;
     }
-    FZ_HD void refill()                           // precondition: avail <= 32
+    FZ_HD void refill()                           // no-op unless avail <= 32
     {
-        const uint32_t w = pop();
-        hi |= shr_c(w, (uint32_t)avail);
-        lo = shl_c(w, 32 - (uint32_t)avail);
-        avail += 32;
+        if (avail <= 32) {
+            const uint32_t w = pop();
+            hi |= shr_c(w, (uint32_t)avail);
+            lo = shl_c(w, 32 - (uint32_t)avail);
+            avail += 32;
+        }
     }
     FZ_HD uint32_t peek(uint32_t nb) const { return shr_c(hi, 32 - nb); }
     FZ_HD void skip(uint32_t nb)
@@ -749,9 +766,9 @@ FZ_HD int decode_sequences(const Block* blocks, Block& b, uint32_t block_max, co
         if (build_seq_table(blocks, b, 0, p, n, K, tLL, logLL, used, scratch) != 0) st = FZG_E_CORRUPT;
         if (!st) { p += used; n -= used; if (build_seq_table(blocks, b, 1, p, n, K, tOF, logOF, used, scratch) != 0) st = FZG_E_CORRUPT; }
         if (!st) { p += used; n -= used; if (build_seq_table(blocks, b, 2, p, n, K, tML, logML, used, scratch) != 0) st = FZG_E_CORRUPT; }
-        if (!st) { p += used; n -= used; if (br.init(p, n) != 0) st = FZG_E_CORRUPT; }
+        if (!st) { p += used; n -= used; if (br.init(p, n, (uint8_t*)scratch) != 0) st = FZG_E_CORRUPT; }   // scratch becomes the ring
         if (!st) {
-            br.refill(); if (br.avail <= 32) br.refill();
+            br.refill(); br.refill();
             sLL = br.read((uint32_t)logLL);
             sOF = br.read((uint32_t)logOF);
             sML = br.read((uint32_t)logML);
@@ -771,7 +788,8 @@ FZ_HD int decode_sequences(const Block* blocks, Block& b, uint32_t block_max, co
             const bool more = i + 1 < nseq;
             const uint32_t nLL = more ? cell_nb(cLL) : 0, nML = more ? cell_nb(cML) : 0, nOF = more ? cell_nb(cOF) : 0;
             const uint32_t a1 = ofb, a2 = a1 + mlb, a3 = a2 + llb, a4 = a3 + nLL, a5 = a4 + nML, need = a5 + nOF;
-            if (br.avail <= 32) br.refill();
+            br.top_up(); ring_wait<8>();          // the word consumed now was fetched >= 20 iterations ago
+            br.refill();
             uint32_t ofx, mlx, llx;
             if (need <= 32) {                     // common case: every field of this sequence sits in `hi`
                 const uint32_t x = br.hi;
@@ -784,9 +802,9 @@ FZ_HD int decode_sequences(const Block* blocks, Block& b, uint32_t block_max, co
                 br.skip(need);
             } else {                              // long offsets / lengths: field by field
                 ofx = br.read(ofb);
-                if (br.avail <= 32) br.refill();
+                br.refill();
                 mlx = br.read(mlb); llx = br.read(llb);
-                if (br.avail <= 32) br.refill();
+                br.refill();
                 sLL = cell_base(cLL) + br.read(nLL);
                 sML = cell_base(cML) + br.read(nML);
                 sOF = cell_base(cOF) + br.read(nOF);
@@ -810,7 +828,9 @@ FZ_HD int decode_sequences(const Block* blocks, Block& b, uint32_t block_max, co
             LE += ll; E += ll + ml;
             if (ofc > 27 || (ofv > 3 && off > kOffMax) || LE > lit_regen || E > block_max) { st = FZG_E_CORRUPT; live = 0; }
             else {
-                for (uint32_t s = (Ep + kSpan - 1) / kSpan; s <= (E - 1) / kSpan; s++) span[s] = (uint16_t)i;
+                const uint32_t s1 = (E - 1) / kSpan;              // span boundaries kSpan * s inside [Ep, E): almost always 0 or 1
+                if (s1 * kSpan >= Ep) span[s1] = (uint16_t)i;
+                if (E - Ep > kSpan) for (uint32_t s = (Ep + kSpan - 1) / kSpan; s < s1; s++) span[s] = (uint16_t)i;
                 const uint64_t rec = rec_pack(E, LE, off);
                 if (i & 1) store_rec_pair(out + i - 1, held, rec); else held = rec;
             }

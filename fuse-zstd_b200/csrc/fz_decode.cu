@@ -109,7 +109,12 @@ __global__ void __launch_bounds__(kLitThreads) k_literals(Block* blocks, const u
 // plus 256 bytes of table-build scratch, so 43 streams fit in the 227 KB of an SM.  Each warp draws
 // its next batch of blocks from a global ticket.
 constexpr int kSeqStreams = 43;
-constexpr int kSeqThreads = 64;
+#ifndef FZ_SEQ_LANES
+#define FZ_SEQ_LANES 8
+#endif
+constexpr int kSeqLanes = FZ_SEQ_LANES;                      // streams per warp: few, so that data-dependent branches cost little
+constexpr int kSeqWarps = (kSeqStreams + kSeqLanes - 1) / kSeqLanes;
+constexpr int kSeqThreads = kSeqWarps * 32;
 constexpr int kSeqTableCells = 512 + 256 + 512;
 constexpr int kSeqStreamBytes = kSeqTableCells * 4 + 256;
 constexpr int kSeqSmem = kSeqStreams * kSeqStreamBytes;
@@ -122,8 +127,8 @@ __global__ void __launch_bounds__(kSeqThreads, 1) k_sequences(Block* blocks, con
     for (uint32_t i = threadIdx.x; i < sizeof(SeqConsts) / 4; i += blockDim.x) ((uint32_t*)&K)[i] = ((const uint32_t*)&c_seq_consts)[i];
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t first = warp == 0 ? 0 : (kSeqStreams + 1) / 2, lanes = warp == 0 ? (kSeqStreams + 1) / 2 : kSeqStreams / 2;
-    uint8_t* mine = smem + (first + lane) * kSeqStreamBytes;
+    const uint32_t first = warp * kSeqLanes, lanes = min((uint32_t)kSeqLanes, kSeqStreams - first);
+    uint8_t* mine = smem + (first + (lane < lanes ? lane : 0)) * kSeqStreamBytes;
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(ticket, lanes);
@@ -164,13 +169,16 @@ __global__ void k_offsets(const Item* items, const ItemInfo* infos, const ItemBa
 // -- pulling up to 8 source bytes per piece with two aligned loads and a funnel shift.  A chunk is
 // written once, with one conflict-free 8-byte shared store.
 //
-// Ordering: s_front is the block-wide frontier (every byte below it is final).  Spans retire in
-// order; a piece whose source is not yet final waits for the next pass of the span loop, and inside
-// a span the frontier is the position reached by the first unfinished lane, so at least one lane
-// advances every pass.  Overlapping matches (offset < length) are periodic with period `offset` and
-// are redirected to the period that precedes the match.
-constexpr int kExecWarps = 16;
+// Ordering: s_ready holds one bit per 8-byte chunk of the tile (one 32-bit word per span, written only
+// by the warp that owns the span).  A piece is copied as soon as the chunk holding its source is
+// marked; until then its lane sits out and retries in the next pass of the span loop.  Spans finish
+// out of order, so a span waits only for the data it actually reads.  Progress: the lowest unfinished
+// chunk of the block only reads lower -- finished -- chunks, and its owner is working on it, since
+// every warp takes its spans in increasing order.  Overlapping matches (offset < length) are periodic
+// with period `offset` and are redirected to the period that precedes the match.
+constexpr int kExecWarps = 32;
 constexpr uint32_t kTilePad = 48;
+constexpr uint32_t kReadyWords = kBlockMax / kSpan;          // 512
 constexpr uint32_t kExecSmem = kBlockMax + kTilePad;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 
@@ -181,15 +189,9 @@ __device__ __forceinline__ uint64_t funnel8(uint32_t x0, uint32_t x1, uint32_t x
     const uint32_t lo = __funnelshift_r(x0, x1, r), hi = __funnelshift_r(x1, x2, r);
     return (uint64_t)lo | ((uint64_t)hi << 32);
 }
-// 8 bytes starting at tile[s]; the tile is 8-byte aligned and padded
-__device__ __forceinline__ uint64_t ld8_tile(const uint8_t* tile, uint32_t s)
-{
-    const uint32_t a = s & ~7u;
-    const uint2 w0 = *(const uint2*)(tile + a), w1 = *(const uint2*)(tile + a + 8);
-    return funnel8(w0.x, w0.y, w1.x, w1.y, s & 7u);
-}
-// nb (1..8) bytes starting at g in global memory; never touches an 8-byte word that holds no wanted byte
-__device__ __forceinline__ uint64_t ld8_global(const uint8_t* g, uint32_t nb)
+// nb (1..8) bytes starting at generic address g (global memory or the shared tile); never touches an
+// 8-byte word that holds no wanted byte
+__device__ __forceinline__ uint64_t ld8_any(const uint8_t* g, uint32_t nb)
 {
     const uintptr_t a = (uintptr_t)g & ~(uintptr_t)7;
     const uint32_t sh = (uint32_t)((uintptr_t)g & 7);
@@ -239,7 +241,7 @@ __device__ __forceinline__ void cta_flush(uint8_t* g, const uint8_t* tile, uint3
 
 __device__ __forceinline__ void exec_block(uint8_t* tile, const Block& b, const uint64_t* __restrict__ sq,
                                            const uint16_t* __restrict__ sp, const uint8_t* g0, uint64_t done,
-                                           volatile uint32_t* s_front, int* s_status)
+                                           volatile uint32_t* s_ready, int* s_status)
 {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nseq = b.nseq, rsize = b.rsize, lit_regen = b.lit_regen;
@@ -283,21 +285,19 @@ __device__ __forceinline__ void exec_block(uint8_t* tile, const Block& b, const 
             fetch(k);
         }
 
-        uint32_t pos = P, filled = 0, myfront = ss;
+        uint32_t pos = P, filled = 0, donemask = 0;
         uint64_t acc = 0;
-        for (;;) {                                  // passes over the span: at least one lane advances in every pass
-            const uint32_t Fv = *s_front;
-            __threadfence_block();
-            const uint32_t Fs = Fv >= ss ? myfront : Fv;
-            bool go = active && pos < Pend, wrote = false;
+        bool go = active;
+        for (uint32_t idle = 0;;) {                 // passes over the span
+            bool wrote = false;
             // lockstep piece loop: one vote per step keeps the lanes converged
             while (__any_sync(kFull, go)) {
                 if (go) {
                     if (pos >= E) { k++; S = E; LEp = LE; fetch(k); }
-                    uint64_t v = 0; uint32_t nb;
+                    uint32_t nb; const uint8_t* src = nullptr; bool fromacc = false;
                     if (pos < M) {                                         // literal run
                         nb = min(M, Pend) - pos;
-                        v = ld8_global(lit + LEp + (pos - S), nb);
+                        src = lit + LEp + (pos - S);
                     } else {                                               // match
                         nb = min(E, Pend) - pos;
                         if (off != 0) {
@@ -306,32 +306,38 @@ __device__ __forceinline__ void exec_block(uint8_t* tile, const Block& b, const 
                                 const uint32_t r = (pos - M) % off;
                                 s = (int32_t)(M - off + r); nb = min(nb, off - r);
                             }
-                            if (s < 0) { nb = min(nb, (uint32_t)(-s)); v = ld8_global(g0 + s, nb); }    // window: earlier blocks, in HBM
-                            else if ((uint32_t)s + nb <= Fs) v = ld8_tile(tile, (uint32_t)s);
-                            else if ((uint32_t)s < Fs) { nb = Fs - (uint32_t)s; v = ld8_tile(tile, (uint32_t)s); }
-                            else if ((uint32_t)s >= P) { nb = 1; v = (acc >> (64 - 8 * filled + 8 * ((uint32_t)s - P))) & 0xFF; }   // own chunk
-                            else { nb = 0; go = false; }                   // produced by a lane / warp that has not got there yet
+                            if (s < 0) { nb = min(nb, (uint32_t)(-s)); src = g0 + s; }           // window: earlier blocks, in HBM / L2
+                            else if ((uint32_t)s >= P) { nb = 1; fromacc = true; src = tile + s; }   // own chunk: still in registers
+                            else {
+                                nb = min(nb, 8 - ((uint32_t)s & 7));       // stay inside one source chunk
+                                const uint32_t word = s_ready[(uint32_t)s / kSpan];
+                                asm volatile("" ::: "memory");     // the tile is read only after its flag
+                                if ((word >> (((uint32_t)s >> 3) & 31)) & 1) src = tile + s;
+                                else { nb = 0; go = false; }               // its producer has not got there yet
+                            }
                         }
                     }
                     if (nb) {
+                        uint64_t v = 0;
+                        if (fromacc) v = (acc >> (64 - 8 * filled + 8 * ((uint32_t)(src - tile) - P))) & 0xFF;
+                        else if (src) v = ld8_any(src, nb);
                         acc = nb == 8 ? v : ((acc >> (8 * nb)) | (v << (64 - 8 * nb)));
                         filled += nb; pos += nb; wrote = true;
                         go = pos < Pend;
                     }
                 }
             }
-            if (wrote) *(uint64_t*)(tile + P) = filled == 8 ? acc : (acc >> (64 - 8 * filled));
+            const bool fin = active && pos >= Pend;
+            if (fin && wrote) *(uint64_t*)(tile + P) = filled == 8 ? acc : (acc >> (64 - 8 * filled));
             __syncwarp();
-            const uint32_t m = __ballot_sync(kFull, active && pos < Pend);
-            if (!m) break;
-            myfront = __shfl_sync(kFull, pos, __ffs(m) - 1);
+            const uint32_t finmask = __ballot_sync(kFull, fin || !active);
+            if (finmask != donemask) {              // publish the chunks finished in this pass
+                if (lane == 0) { __threadfence_block(); s_ready[n] = finmask; }
+                donemask = finmask; idle = 0;
+            } else if (++idle > 2) __nanosleep(64);
+            if (finmask == kFull) break;
+            go = active && pos < Pend;
         }
-        if (lane == 0) {                       // retire the span in order
-            __threadfence_block();
-            while (*s_front != ss) { }
-            *s_front = min(ss + kSpan, rsize);
-        }
-        __syncwarp();
     }
 }
 
@@ -340,7 +346,7 @@ __global__ void __launch_bounds__(kExecWarps * 32, 1) k_execute(Frame* frames, c
                                                                  uint32_t n_frames, uint32_t* ticket)
 {
     extern __shared__ __align__(16) uint8_t tile[];
-    __shared__ volatile uint32_t s_front;
+    __shared__ volatile uint32_t s_ready[kReadyWords];
     __shared__ uint32_t s_next;
     __shared__ int s_status;
     for (;;) {
@@ -363,9 +369,9 @@ __global__ void __launch_bounds__(kExecWarps * 32, 1) k_execute(Frame* frames, c
                 for (uint32_t i = threadIdx.x; i < rsize; i += blockDim.x) g0[i] = v;
             } else if (b.nseq == 0) cta_copy(g0, b.lit, rsize);
             else {
-                if (threadIdx.x == 0) s_front = 0;
+                for (uint32_t i = threadIdx.x; i < kReadyWords; i += blockDim.x) s_ready[i] = 0;
                 __syncthreads();
-                exec_block(tile, b, seqs + b.seq_base, spans + b.span_base, g0, done, &s_front, &s_status);
+                exec_block(tile, b, seqs + b.seq_base, spans + b.span_base, g0, done, s_ready, &s_status);
                 __syncthreads();
                 cta_flush(g0, tile, rsize);
             }

@@ -90,7 +90,7 @@ extern "C" int fze_decode_batch(size_t n, const void* const* src, const size_t* 
     }
     // sequences
     std::vector<uint32_t> tables(512 + 256 + 512);
-    uint16_t scratch[128];
+    alignas(16) uint16_t scratch[128];
     for (uint32_t j = 0; j < run.seq_job; j++)
         seq_thread(blocks.data(), frames.data(), blocks[seq_jobs[j]], kConsts, tables.data(), scratch, seqs.data(), spans.data(), blocks[seq_jobs[j]].nseq, 1);
     // offsets
@@ -139,7 +139,7 @@ extern "C" int fze_trace(const void* src, size_t src_len, uint64_t* seq_out, siz
         if (b.lit_type >= LT_HUF) lit_build(blocks.data(), b, table.data(), log, used);
         for (uint32_t sub = 0; sub < 4; sub++) if (lit_decode_sub(b, sub, table.data(), log, used)) return FZG_E_CORRUPT;
     }
-    std::vector<uint32_t> tables(1280); uint16_t scratch[128];
+    std::vector<uint32_t> tables(1280); alignas(16) uint16_t scratch[128];
     for (uint32_t j = 0; j < info.n_seq_jobs; j++) seq_thread(blocks.data(), frames.data(), blocks[sj[j]], kConsts, tables.data(), scratch, seqs.data(), spans.data(), blocks[sj[j]].nseq, 1);
     it.dst_cap = ~0ull;
     ItemOut io; offsets_item(it, info, base, frames.data(), blocks.data(), io);      // resolves every block's starting history
