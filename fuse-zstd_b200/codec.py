@@ -7,7 +7,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "libfzgpu.so")
+SO = os.environ.get("FZG_LIB") or os.path.join(HERE, "libfzgpu.so")   # FZG_LIB: a differently tuned build (kernel experiments)
 
 OK, E_MAGIC, E_TRUNCATED, E_UNSUPPORTED, E_CORRUPT, E_DSTSIZE, E_CHECKSUM, E_FCS = range(8)
 SRC_DEVICE, DST_DEVICE, NO_VERIFY_CHECKSUM, PROFILE = 1, 2, 4, 8

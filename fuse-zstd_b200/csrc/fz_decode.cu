@@ -156,31 +156,51 @@ __global__ void k_offsets(const Item* items, const ItemInfo* infos, const ItemBa
 }
 
 // ------------------------------------------------------------------ execute (LZ77)
-// One CTA per frame at a time (frames are drawn from a ticket); the frame's blocks are executed in
-// order, each assembled in a 128 KiB shared-memory tile and then streamed to HBM with 16-byte
-// stores, so match sources inside the block are shared-memory reads and only window references to
-// earlier blocks go to L2/HBM.
+// What bounds this stage is the dependency chain inside a frame: on text-like data almost every
+// 256-byte stretch of output copies something from the stretch just before it, so one frame cannot
+// be spread over many warps -- they would wait on one another.  The parallelism therefore comes from
+// running MANY frames per SM: a small CTA (a few warps) owns one frame at a time (frames are drawn
+// from a ticket) and executes its blocks in order, straight into the destination in HBM; a dozen
+// such CTAs share an SM and overlap each other's chain latency.  Match sources are read back through
+// L1/L2 (the same SM wrote them).
 //
 // Inside a block the work is split by OUTPUT position, not by sequence: the block is cut into spans
-// of 256 bytes, spans go round-robin to the warps, and each lane owns one aligned 8-byte chunk of
-// its warp's span.  Because a sequence record carries cumulative positions (rec_e / rec_le), a lane
+// of 256 bytes, spans go round-robin to the CTA's warps, and each lane owns one 8-byte chunk of its
+// warp's span.  Because a sequence record carries cumulative positions (rec_e / rec_le), a lane
 // finds the sequence covering its chunk with a five-step search over 32 records (the span index
 // gives the first one) and then walks the pieces of its chunk -- literal run, match, next sequence
 // -- pulling up to 8 source bytes per piece with two aligned loads and a funnel shift.  A chunk is
-// written once, with one conflict-free 8-byte shared store.
+// written once, with one 8-byte store (256 contiguous bytes per warp).
 //
-// Ordering: s_ready holds one bit per 8-byte chunk of the tile (one 32-bit word per span, written only
-// by the warp that owns the span).  A piece is copied as soon as the chunk holding its source is
-// marked; until then its lane sits out and retries in the next pass of the span loop.  Spans finish
-// out of order, so a span waits only for the data it actually reads.  Progress: the lowest unfinished
-// chunk of the block only reads lower -- finished -- chunks, and its owner is working on it, since
-// every warp takes its spans in increasing order.  Overlapping matches (offset < length) are periodic
-// with period `offset` and are redirected to the period that precedes the match.
-constexpr int kExecWarps = 32;
-constexpr uint32_t kTilePad = 48;
+// Ordering: s_ready holds one bit per 8-byte chunk of the block (one 32-bit word per span, written only
+// by the warp that owns the span, release/acquire at CTA scope).  A piece is copied as soon as the
+// chunks holding its source are marked; until then its lane sits out and retries in the next pass of
+// the span loop.  Spans finish out of order, so a span waits only for the data it actually reads.
+// Progress: the lowest unfinished chunk of the block only reads lower -- finished -- chunks, and its
+// owner is working on it, since every warp takes its spans in increasing order.  Overlapping matches
+// (offset < length) are periodic with period `offset` and are redirected to the period that precedes
+// the match.  Earlier blocks of the frame (the window) are complete before a block starts.
+#ifndef FZ_EXEC_WARPS
+#define FZ_EXEC_WARPS 4
+#endif
+#ifndef FZ_EXEC_CTAS
+#define FZ_EXEC_CTAS 8
+#endif
+constexpr int kExecWarps = FZ_EXEC_WARPS;                    // warps per frame in flight
+constexpr int kExecCtasPerSm = FZ_EXEC_CTAS;
 constexpr uint32_t kReadyWords = kBlockMax / kSpan;          // 512
-constexpr uint32_t kExecSmem = kBlockMax + kTilePad;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t ld_acquire_shared(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_shared(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ uint64_t funnel8(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t byte_shift)
 {
@@ -189,8 +209,7 @@ __device__ __forceinline__ uint64_t funnel8(uint32_t x0, uint32_t x1, uint32_t x
     const uint32_t lo = __funnelshift_r(x0, x1, r), hi = __funnelshift_r(x1, x2, r);
     return (uint64_t)lo | ((uint64_t)hi << 32);
 }
-// nb (1..8) bytes starting at generic address g (global memory or the shared tile); never touches an
-// 8-byte word that holds no wanted byte
+// nb (1..8) bytes starting at g; never touches an 8-byte word that holds no wanted byte
 __device__ __forceinline__ uint64_t ld8_any(const uint8_t* g, uint32_t nb)
 {
     const uintptr_t a = (uintptr_t)g & ~(uintptr_t)7;
@@ -199,6 +218,14 @@ __device__ __forceinline__ uint64_t ld8_any(const uint8_t* g, uint32_t nb)
     uint2 w1 = make_uint2(0, 0);
     if (sh + nb > 8) w1 = *(const uint2*)(a + 8);
     return funnel8(w0.x, w0.y, w1.x, w1.y, sh);
+}
+// nb (1..8) low bytes of v -> g, any alignment
+__device__ __forceinline__ void st8_any(uint8_t* g, uint64_t v, uint32_t nb)
+{
+    const uint32_t a = (uint32_t)(uintptr_t)g & 7;
+    if (nb == 8 && a == 0) *(uint64_t*)g = v;
+    else if (nb == 8 && (a & 3) == 0) { ((uint32_t*)g)[0] = (uint32_t)v; ((uint32_t*)g)[1] = (uint32_t)(v >> 32); }
+    else for (uint32_t i = 0; i < nb; i++) g[i] = (uint8_t)(v >> (8 * i));
 }
 
 __device__ __forceinline__ void cta_copy(uint8_t* dst, const uint8_t* src, uint32_t n)
@@ -212,36 +239,8 @@ __device__ __forceinline__ void cta_copy(uint8_t* dst, const uint8_t* src, uint3
     }
 }
 
-// tile[0 .. n) -> g (any alignment), 16-byte global stores
-__device__ __forceinline__ void cta_flush(uint8_t* g, const uint8_t* tile, uint32_t n)
-{
-    const uint32_t head = min(n, (uint32_t)((16 - ((uintptr_t)g & 15)) & 15));
-    for (uint32_t i = threadIdx.x; i < head; i += blockDim.x) g[i] = tile[i];
-    const uint32_t nv = (n - head) >> 4;
-    uint4* gv = (uint4*)(g + head);
-    const uint32_t ws = head >> 2, bs = (head & 3) * 8;      // uniform for the whole block
-    if (head == 0) {
-        for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x) gv[i] = ((const uint4*)tile)[i];
-    } else {
-        for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x) {
-            const uint4 a = ((const uint4*)tile)[i], b = ((const uint4*)tile)[i + 1];
-            uint32_t w0, w1, w2, w3, w4;
-            switch (ws) {
-            case 0: w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; break;
-            case 1: w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; break;
-            case 2: w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; break;
-            default: w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; break;
-            }
-            gv[i] = make_uint4(__funnelshift_r(w0, w1, bs), __funnelshift_r(w1, w2, bs), __funnelshift_r(w2, w3, bs),
-                               __funnelshift_r(w3, w4, bs));
-        }
-    }
-    for (uint32_t i = head + (nv << 4) + threadIdx.x; i < n; i += blockDim.x) g[i] = tile[i];
-}
-
-__device__ __forceinline__ void exec_block(uint8_t* tile, const Block& b, const uint64_t* __restrict__ sq,
-                                           const uint16_t* __restrict__ sp, const uint8_t* g0, uint64_t done,
-                                           volatile uint32_t* s_ready, int* s_status)
+__device__ __forceinline__ void exec_block(const Block& b, const uint64_t* __restrict__ sq, const uint16_t* __restrict__ sp,
+                                           uint8_t* g0, uint64_t done, uint32_t* s_ready, int* s_status)
 {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nseq = b.nseq, rsize = b.rsize, lit_regen = b.lit_regen;
@@ -285,10 +284,10 @@ __device__ __forceinline__ void exec_block(uint8_t* tile, const Block& b, const 
             fetch(k);
         }
 
-        uint32_t pos = P, filled = 0, donemask = 0;
+        uint32_t pos = P, filled = 0, donemask = 0, waitc = 0;
         uint64_t acc = 0;
         bool go = active;
-        for (uint32_t idle = 0;;) {                 // passes over the span
+        for (;;) {                                  // passes over the span
             bool wrote = false;
             // lockstep piece loop: one vote per step keeps the lanes converged
             while (__any_sync(kFull, go)) {
@@ -306,20 +305,22 @@ __device__ __forceinline__ void exec_block(uint8_t* tile, const Block& b, const 
                                 const uint32_t r = (pos - M) % off;
                                 s = (int32_t)(M - off + r); nb = min(nb, off - r);
                             }
-                            if (s < 0) { nb = min(nb, (uint32_t)(-s)); src = g0 + s; }           // window: earlier blocks, in HBM / L2
-                            else if ((uint32_t)s >= P) { nb = 1; fromacc = true; src = tile + s; }   // own chunk: still in registers
-                            else {
-                                nb = min(nb, 8 - ((uint32_t)s & 7));       // stay inside one source chunk
-                                const uint32_t word = s_ready[(uint32_t)s / kSpan];
-                                asm volatile("" ::: "memory");     // the tile is read only after its flag
-                                if ((word >> (((uint32_t)s >> 3) & 31)) & 1) src = tile + s;
-                                else { nb = 0; go = false; }               // its producer has not got there yet
+                            if (s < 0) { nb = min(nb, (uint32_t)(-s)); src = g0 + s; }              // window: earlier blocks
+                            else if ((uint32_t)s >= P) { nb = 1; fromacc = true; src = g0 + s; }    // own chunk: still in registers
+                            else {                                         // the source spans one or two 8-byte chunks of the block
+                                const uint32_t c0 = (uint32_t)s >> 3, c1 = ((uint32_t)s + nb - 1) >> 3;
+                                const uint32_t w0 = ld_acquire_shared(s_ready + (c0 >> 5));
+                                const uint32_t w1 = (c1 >> 5) == (c0 >> 5) ? w0 : ld_acquire_shared(s_ready + (c1 >> 5));
+                                if ((w0 >> (c0 & 31)) & 1) {
+                                    if (!((w1 >> (c1 & 31)) & 1)) nb = 8 - ((uint32_t)s & 7);   // only the first chunk is final
+                                    src = g0 + s;
+                                } else { nb = 0; go = false; waitc = c0; } // its producer has not got there yet
                             }
                         }
                     }
                     if (nb) {
                         uint64_t v = 0;
-                        if (fromacc) v = (acc >> (64 - 8 * filled + 8 * ((uint32_t)(src - tile) - P))) & 0xFF;
+                        if (fromacc) v = (acc >> (64 - 8 * filled + 8 * ((uint32_t)(src - g0) - P))) & 0xFF;
                         else if (src) v = ld8_any(src, nb);
                         acc = nb == 8 ? v : ((acc >> (8 * nb)) | (v << (64 - 8 * nb)));
                         filled += nb; pos += nb; wrote = true;
@@ -328,25 +329,31 @@ __device__ __forceinline__ void exec_block(uint8_t* tile, const Block& b, const 
                 }
             }
             const bool fin = active && pos >= Pend;
-            if (fin && wrote) *(uint64_t*)(tile + P) = filled == 8 ? acc : (acc >> (64 - 8 * filled));
+            if (fin && wrote) st8_any(g0 + P, filled == 8 ? acc : (acc >> (64 - 8 * filled)), filled);
             __syncwarp();
             const uint32_t finmask = __ballot_sync(kFull, fin || !active);
             if (finmask != donemask) {              // publish the chunks finished in this pass
-                if (lane == 0) { __threadfence_block(); s_ready[n] = finmask; }
-                donemask = finmask; idle = 0;
-            } else if (++idle > 2) __nanosleep(64);
+                if (lane == 0) st_release_shared(s_ready + n, finmask);
+                donemask = finmask;
+            }
             if (finmask == kFull) break;
             go = active && pos < Pend;
+            // Every unfinished lane is blocked on a lower chunk: poll just those flags (cheap, with back-off) until one
+            // of them is set, instead of re-running the piece logic.  A chunk of this very span counts as published.
+            for (uint32_t spin = 0;; spin++) {
+                const bool ok = go && (((waitc >> 5) == n ? finmask : ld_acquire_shared(s_ready + (waitc >> 5))) >> (waitc & 31) & 1);
+                if (__any_sync(kFull, ok)) break;
+                __nanosleep(spin < 8 ? 32u * (spin + 1) : 256u);
+            }
         }
     }
 }
 
-__global__ void __launch_bounds__(kExecWarps * 32, 1) k_execute(Frame* frames, const Block* blocks, const Item* items,
-                                                                 const ItemOut* outs, const uint64_t* seqs, const uint16_t* spans,
-                                                                 uint32_t n_frames, uint32_t* ticket)
+__global__ void __launch_bounds__(kExecWarps * 32, kExecCtasPerSm) k_execute(Frame* frames, const Block* blocks, const Item* items,
+                                                                              const ItemOut* outs, const uint64_t* seqs,
+                                                                              const uint16_t* spans, uint32_t n_frames, uint32_t* ticket)
 {
-    extern __shared__ __align__(16) uint8_t tile[];
-    __shared__ volatile uint32_t s_ready[kReadyWords];
+    __shared__ uint32_t s_ready[kReadyWords];
     __shared__ uint32_t s_next;
     __shared__ int s_status;
     for (;;) {
@@ -371,11 +378,10 @@ __global__ void __launch_bounds__(kExecWarps * 32, 1) k_execute(Frame* frames, c
             else {
                 for (uint32_t i = threadIdx.x; i < kReadyWords; i += blockDim.x) s_ready[i] = 0;
                 __syncthreads();
-                exec_block(tile, b, seqs + b.seq_base, spans + b.span_base, g0, done, s_ready, &s_status);
-                __syncthreads();
-                cta_flush(g0, tile, rsize);
+                exec_block(b, seqs + b.seq_base, spans + b.span_base, g0, done, s_ready, &s_status);
             }
-            __syncthreads();                   // the tile is reused, and later blocks read this one from HBM
+            __threadfence_block();
+            __syncthreads();                   // later blocks read this one back (the window), and s_ready is reused
             done += rsize;
         }
         if (threadIdx.x == 0 && s_status) fr.status = s_status;
@@ -422,7 +428,6 @@ int fzh_decode_setup(void)
 {
     CK(cudaFuncSetAttribute(k_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, kLitGroups * kHufTableCells * 2));
     CK(cudaFuncSetAttribute(k_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqSmem));
-    CK(cudaFuncSetAttribute(k_execute, cudaFuncAttributeMaxDynamicSharedMemorySize, kExecSmem));
     int dev = 0; CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
     return 0;
@@ -481,8 +486,8 @@ int fzh_decode_run(FzCtx* c, uint32_t n, int flags)
     mark();
     k_offsets<<<gi, tb, 0, s>>>(d_items, d_infos, d_bases, d_frames, d_blocks, d_outs, n); mark(); launches++;
     if (n_frames) {
-        const uint32_t grid = (uint32_t)std::min<uint64_t>(n_frames, (uint64_t)g_sm_count);
-        k_execute<<<grid, kExecWarps * 32, kExecSmem, s>>>(d_frames, d_blocks, d_items, d_outs, d_seq, d_spans, (uint32_t)n_frames, d_tickets + 1); launches++;
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(n_frames, (uint64_t)g_sm_count * kExecCtasPerSm);
+        k_execute<<<grid, kExecWarps * 32, 0, s>>>(d_frames, d_blocks, d_items, d_outs, d_seq, d_spans, (uint32_t)n_frames, d_tickets + 1); launches++;
     }
     mark();
     if (n_frames && !(flags & FZG_NO_VERIFY_CHECKSUM)) { k_checksum<<<(uint32_t)((n_frames * 4 + 127) / 128), 128, 0, s>>>(d_frames, d_items, d_outs, (uint32_t)n_frames); launches++; }
