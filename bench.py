@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--files", type=int, default=10000, help="files per GPU (config 2: 10 000)")
     ap.add_argument("--file-size", type=int, default=1 << 20)
     ap.add_argument("--level", type=int, default=3)
-    ap.add_argument("--e2e-files", type=int, default=2560, help="files per GPU in the host-buffer (e2e) leg")
+    ap.add_argument("--e2e-files", type=int, default=5000, help="files per GPU in the host-buffer (e2e) leg")
     ap.add_argument("--cpu-files", type=int, default=4096, help="bounded sample for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -292,8 +292,6 @@ def run_b200(args, rank, local_rank, world):
         h_dst = torch.empty(E * S, dtype=torch.uint8, pin_memory=True)
         hsp = (h_src.data_ptr() + w.comp_off[:E]).astype(np.uint64)
         hdp = (h_dst.data_ptr() + np.arange(E, dtype=np.uint64) * np.uint64(S)).astype(np.uint64)
-        # the items must tile the pinned buffer contiguously for the one-copy path: lengths = slot sizes
-        slot = np.diff(np.append(w.comp_off[:E], np.uint64(src_bytes))).astype(np.uint64)
         for _ in range(2):
             dl, st = codec.decode_batch_ptrs(dev, hsp, w.comp_len[:E], hdp, dc[:E], 0)
         assert not st.any() and (dl == S).all()

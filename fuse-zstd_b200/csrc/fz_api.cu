@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <vector>
@@ -20,7 +21,7 @@
 using namespace fz;
 
 int fzh_encode_setup(void);
-int fzh_encode_run(FzCtx* c, uint32_t n, int level, size_t chunk, int flags);
+int fzh_encode_run(FzCtx* c, uint32_t first, uint32_t n, int level, size_t chunk, int flags);
 size_t fzh_encode_bound(size_t src_len, size_t chunk);
 const char* fzh_encode_stage_name(int s);
 
@@ -46,6 +47,7 @@ extern "C" int fzg_init(const int* devices, int n_devices)
         c->dev = d;
         CKR(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CKR(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CKR(cudaStreamCreateWithFlags(&c->copy_stream2, cudaStreamNonBlocking));
         for (auto& e : c->ev) CKR(cudaEventCreate(&e));
         int rc = fzh_decode_setup(); if (rc) return rc;
         rc = fzh_encode_setup(); if (rc) return rc;
@@ -67,7 +69,7 @@ extern "C" void fzg_shutdown(void)
         FzPinBuf* pb[] = { &c->h_items, &c->h_outs, &c->h_totals, &c->h_stage_src, &c->h_stage_dst };
         for (auto* b : pb) b->release();
         for (auto& e : c->ev) cudaEventDestroy(e);
-        cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copy_stream);
+        cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copy_stream); cudaStreamDestroy(c->copy_stream2);
         delete c;
     }
     g_ctx.clear(); g_dev.clear();
@@ -102,7 +104,11 @@ static bool is_pinned(const void* p)
 static inline size_t al16(size_t v) { return (v + 15) & ~(size_t)15; }
 
 // ---------------------------------------------------------------------------------- batched decode / encode
-// Shared staging logic: direction-agnostic.  `encode` selects the pipeline.
+// Device-resident batches run as one launch sequence.  Host-resident batches are cut into chunks of
+// ~1 GiB of output and pipelined on three streams: while chunk c is decoded, chunk c+1 crosses PCIe
+// host->device and chunk c-1 device->host, so the call costs about max(PCIe, kernels) instead of their sum.
+static constexpr size_t kChunkOutBytes = 1ull << 30;
+
 static int run_batch(bool encode, int device, size_t n, const void* const* src, const size_t* src_len, void* const* dst,
                      const size_t* dst_cap, size_t* dst_len, int* status, int flags, int level, size_t chunk)
 {
@@ -120,66 +126,111 @@ static int run_batch(bool encode, int device, size_t n, const void* const* src, 
     if ((rc = c->h_outs.reserve(n * sizeof(ItemOut)))) return rc;
     if ((rc = c->h_totals.reserve(64))) return rc;
     Item* items = (Item*)c->h_items.p;
+    const ItemOut* outs = (const ItemOut*)c->h_outs.p;
+    for (size_t i = 0; i < n; i++) { items[i].src_len = src_len[i]; items[i].dst_cap = dst_cap[i]; }
+    fzg_timing_t acc = {};
 
-    // ---- sources
-    size_t src_total = 0, dst_total = 0;
-    for (size_t i = 0; i < n; i++) { src_total += al16(src_len[i]) + 16; dst_total += al16(dst_cap[i]) + 16; }
+    // ---- device layout of the sources
+    const uint8_t* h2d_base = nullptr;            // pinned host region mirrored at d_stage_src
     if (!src_dev) {
-        if ((rc = c->d_stage_src.reserve(src_total + 64))) return rc;
-        uint8_t* dbase = (uint8_t*)c->d_stage_src.p;
-        bool contiguous = true;
-        for (size_t i = 0; i + 1 < n && contiguous; i++) contiguous = (const uint8_t*)src[i] + src_len[i] == (const uint8_t*)src[i + 1];
-        const bool pinned = n && src_len[0] && is_pinned(src[0]) && is_pinned((const uint8_t*)src[n - 1] + (src_len[n - 1] ? src_len[n - 1] - 1 : 0));
-        if (contiguous && pinned) {               // one bulk copy straight from the caller's pinned buffer
-            size_t total = (const uint8_t*)src[n - 1] + src_len[n - 1] - (const uint8_t*)src[0];
+        // a caller's pinned buffer whose items lie in increasing order is copied as it is (gaps included)
+        bool span_ok = src_len[0] && is_pinned(src[0]) && is_pinned((const uint8_t*)src[n - 1] + (src_len[n - 1] ? src_len[n - 1] - 1 : 0));
+        size_t sum = 0;
+        for (size_t i = 0; i < n && span_ok; i++) {
+            sum += src_len[i];
+            if (i + 1 < n && (const uint8_t*)src[i] + src_len[i] > (const uint8_t*)src[i + 1]) span_ok = false;
+        }
+        const size_t span = span_ok ? (size_t)((const uint8_t*)src[n - 1] + src_len[n - 1] - (const uint8_t*)src[0]) : 0;
+        if (span_ok && span <= 2 * sum + (64u << 10) * n) {
+            if ((rc = c->d_stage_src.reserve(span + 64))) return rc;
+            h2d_base = (const uint8_t*)src[0];
+            for (size_t i = 0; i < n; i++) items[i].src = (uint8_t*)c->d_stage_src.p + ((const uint8_t*)src[i] - h2d_base);
+        } else {                                  // pack into pinned staging
+            size_t total = 0;
+            for (size_t i = 0; i < n; i++) total += al16(src_len[i]) + 16;
             if ((rc = c->d_stage_src.reserve(total + 64))) return rc;
-            dbase = (uint8_t*)c->d_stage_src.p;
-            CKR(cudaMemcpyAsync(dbase, src[0], total, cudaMemcpyHostToDevice, s));
-            for (size_t i = 0; i < n; i++) items[i].src = dbase + ((const uint8_t*)src[i] - (const uint8_t*)src[0]);
-        } else {                                  // pack into pinned staging, then one bulk copy
-            if ((rc = c->h_stage_src.reserve(src_total))) return rc;
+            if ((rc = c->h_stage_src.reserve(total + 64))) return rc;
             uint8_t* hbase = (uint8_t*)c->h_stage_src.p; size_t off = 0;
             for (size_t i = 0; i < n; i++) {
                 if (src_len[i]) memcpy(hbase + off, src[i], src_len[i]);
-                items[i].src = dbase + off; off += al16(src_len[i]) + 16;
+                items[i].src = (uint8_t*)c->d_stage_src.p + off; off += al16(src_len[i]) + 16;
             }
-            CKR(cudaMemcpyAsync(dbase, hbase, off, cudaMemcpyHostToDevice, s));
+            h2d_base = hbase;
         }
     } else for (size_t i = 0; i < n; i++) items[i].src = (const uint8_t*)src[i];
-    // ---- destinations
-    bool dst_contig = true;
-    if (!dst_dev) {
-        for (size_t i = 0; i + 1 < n && dst_contig; i++) dst_contig = (uint8_t*)dst[i] + dst_cap[i] == (uint8_t*)dst[i + 1];
-        if ((rc = c->d_stage_dst.reserve(dst_total + 64))) return rc;
-        uint8_t* dbase = (uint8_t*)c->d_stage_dst.p; size_t off = 0;
-        for (size_t i = 0; i < n; i++) {
-            if (dst_contig) { items[i].dst = dbase + ((uint8_t*)dst[i] - (uint8_t*)dst[0]); }
-            else { items[i].dst = dbase + off; off += al16(dst_cap[i]) + 16; }
-        }
-    } else for (size_t i = 0; i < n; i++) items[i].dst = (uint8_t*)dst[i];
-    for (size_t i = 0; i < n; i++) { items[i].src_len = src_len[i]; items[i].dst_cap = dst_cap[i]; }
 
-    rc = encode ? fzh_encode_run(c, (uint32_t)n, level, chunk, flags) : fzh_decode_run(c, (uint32_t)n, flags);
-    if (rc) return rc;
-    const ItemOut* outs = (const ItemOut*)c->h_outs.p;
+    // ---- device layout of the destinations
+    bool dst_contig = false;
+    if (!dst_dev) {
+        dst_contig = is_pinned(dst[0]);
+        for (size_t i = 0; i + 1 < n && dst_contig; i++) dst_contig = (uint8_t*)dst[i] + dst_cap[i] == (uint8_t*)dst[i + 1];
+        size_t total = 0;
+        for (size_t i = 0; i < n; i++) total += dst_contig ? dst_cap[i] : al16(dst_cap[i]) + 16;
+        if ((rc = c->d_stage_dst.reserve(total + 64))) return rc;
+        uint8_t* dbase = (uint8_t*)c->d_stage_dst.p; size_t off = 0;
+        for (size_t i = 0; i < n; i++) { items[i].dst = dbase + off; off += dst_contig ? dst_cap[i] : al16(dst_cap[i]) + 16; }
+    } else for (size_t i = 0; i < n; i++) items[i].dst = (uint8_t*)dst[i];
+
+    auto run = [&](size_t first, size_t cnt) -> int {
+        int r = encode ? fzh_encode_run(c, (uint32_t)first, (uint32_t)cnt, level, chunk, flags) : fzh_decode_run(c, (uint32_t)first, (uint32_t)cnt, flags);
+        if (r) return r;
+        acc.total_ms += c->timing.total_ms; acc.launches += c->timing.launches;
+        for (int k = 0; k < 16; k++) acc.kernel_ms[k] += c->timing.kernel_ms[k];
+        return 0;
+    };
+
+    if (src_dev && dst_dev) {
+        if ((rc = run(0, n))) return rc;
+    } else {
+        std::vector<size_t> cuts{ 0 };            // chunk boundaries
+        for (size_t i = 0, bytes = 0; i < n; i++) {
+            bytes += dst_cap[i] + src_len[i];
+            if (bytes >= kChunkOutBytes && i + 1 < n) { cuts.push_back(i + 1); bytes = 0; }
+        }
+        cuts.push_back(n);
+        const size_t nchunks = cuts.size() - 1;
+        cudaStream_t s_in = c->copy_stream, s_out = c->copy_stream2;
+        auto h2d = [&](size_t k) -> int {         // chunk k: host -> device on the copy-in stream
+            if (src_dev) return 0;
+            const size_t lo = cuts[k], hi = cuts[k + 1];
+            const uint8_t* d_lo = items[lo].src; const uint8_t* d_hi = items[hi - 1].src + src_len[hi - 1];
+            const size_t off = (size_t)(d_lo - (const uint8_t*)c->d_stage_src.p);
+            if (d_hi > d_lo) CKR(cudaMemcpyAsync((void*)d_lo, h2d_base + off, (size_t)(d_hi - d_lo), cudaMemcpyHostToDevice, s_in));
+            CKR(cudaEventRecord(c->ev[12 + (k & 1)], s_in));
+            return 0;
+        };
+        static const bool trace = getenv("FZG_TRACE") != nullptr;
+        struct timespec t0; clock_gettime(CLOCK_MONOTONIC, &t0);
+        auto now_ms = [&]() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (t.tv_sec - t0.tv_sec) * 1e3 + (t.tv_nsec - t0.tv_nsec) * 1e-6; };
+        if ((rc = h2d(0))) return rc;
+        for (size_t k = 0; k < nchunks; k++) {
+            const size_t lo = cuts[k], hi = cuts[k + 1];
+            if (k + 1 < nchunks && (rc = h2d(k + 1))) return rc;
+            if (!src_dev) CKR(cudaStreamWaitEvent(s, c->ev[12 + (k & 1)], 0));
+            const double ta = now_ms();
+            if ((rc = run(lo, hi - lo))) return rc;                     // returns once chunk k is decoded
+            if (trace) fprintf(stderr, "fzgpu: chunk %zu/%zu items %zu: run %.2f -> %.2f ms (gpu %.2f ms)\n", k, nchunks, hi - lo, ta, now_ms(), c->timing.total_ms);
+            if (!dst_dev) {
+                bool all_full = dst_contig;
+                for (size_t i = lo; i < hi && all_full; i++) all_full = !outs[i].status && outs[i].dst_len == dst_cap[i];
+                if (all_full) {
+                    CKR(cudaMemcpyAsync(dst[lo], items[lo].dst, (size_t)((uint8_t*)dst[hi - 1] + dst_cap[hi - 1] - (uint8_t*)dst[lo]), cudaMemcpyDeviceToHost, s_out));
+                } else {
+                    for (size_t i = lo; i < hi; i++)
+                        if (!outs[i].status && outs[i].dst_len) CKR(cudaMemcpyAsync(dst[i], items[i].dst, outs[i].dst_len, cudaMemcpyDeviceToHost, s_out));
+                }
+            }
+        }
+        if (!dst_dev) CKR(cudaStreamSynchronize(s_out));
+        if (trace) fprintf(stderr, "fzgpu: all chunks back on the host at %.2f ms\n", now_ms());
+    }
     uint64_t bytes_in = 0, bytes_out = 0;
-    bool all_full = true;
     for (size_t i = 0; i < n; i++) {
         dst_len[i] = (size_t)outs[i].dst_len; status[i] = outs[i].status;
         bytes_in += src_len[i]; bytes_out += outs[i].dst_len;
-        if (outs[i].status || outs[i].dst_len != dst_cap[i]) all_full = false;
     }
+    c->timing = acc;
     c->timing.bytes_in = bytes_in; c->timing.bytes_out = bytes_out;
-    // ---- results back to the host
-    if (!dst_dev) {
-        if (dst_contig && all_full && is_pinned(dst[0])) {
-            CKR(cudaMemcpyAsync(dst[0], items[0].dst, (uint8_t*)dst[n - 1] + dst_cap[n - 1] - (uint8_t*)dst[0], cudaMemcpyDeviceToHost, s));
-        } else {
-            for (size_t i = 0; i < n; i++)
-                if (!outs[i].status && outs[i].dst_len) CKR(cudaMemcpyAsync(dst[i], items[i].dst, outs[i].dst_len, cudaMemcpyDeviceToHost, s));
-        }
-        CKR(cudaStreamSynchronize(s));
-    }
     return 0;
 }
 

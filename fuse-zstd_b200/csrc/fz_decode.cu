@@ -27,9 +27,10 @@ namespace fz {
 __constant__ SeqConsts c_seq_consts = { FZ_LL_BASE, FZ_ML_BASE, FZ_LL_BITS, FZ_ML_BITS, FZ_LL_DEF, FZ_OF_DEF, FZ_ML_DEF };
 
 // ------------------------------------------------------------------ count / scan / fill
-__global__ void k_count(const Item* items, ItemInfo* infos, uint32_t n)
+__global__ void k_count(const Item* items, ItemInfo* infos, uint32_t n, uint32_t* tickets)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 4) tickets[i] = 0;
     if (i >= n) return;
     ItemInfo info;
     walk_item<false>(i, items[i], info, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
@@ -38,7 +39,7 @@ __global__ void k_count(const Item* items, ItemInfo* infos, uint32_t n)
 
 // single CTA; exclusive scan of seven counters over the items.  totals[0..6] = frames, blocks,
 // seq jobs, huf jobs, literal bytes, sequence records, span-index entries.
-__global__ void k_scan(const ItemInfo* infos, ItemBase* bases, uint64_t* totals, uint32_t n)
+__global__ void k_scan(const ItemInfo* infos, ItemBase* bases, uint64_t* totals, uint32_t n)   // totals: pinned host memory (zero-copy)
 {
     __shared__ uint64_t part[512][7];
     const uint32_t t = threadIdx.x, T = blockDim.x;
@@ -402,13 +403,14 @@ __global__ void k_checksum(Frame* frames, const Item* items, const ItemOut* outs
     if (active && j == 0 && (uint32_t)xx_combine(v1, v2, v3, v4, p, len) != frames[f].checksum) frames[f].status = FZG_E_CHECKSUM;
 }
 
-__global__ void k_finish(const ItemInfo* infos, const ItemBase* bases, const Frame* frames, ItemOut* outs, uint32_t n)
+__global__ void k_finish(const ItemInfo* infos, const ItemBase* bases, const Frame* frames, const ItemOut* outs, ItemOut* host_outs,
+                         uint32_t n)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     ItemOut o = outs[i];
     finish_item(infos[i], bases[i], frames, o);
-    outs[i] = o;
+    host_outs[i] = o;                          // pinned host memory (zero-copy)
 }
 
 }  // namespace fz
@@ -433,35 +435,37 @@ int fzh_decode_setup(void)
     return 0;
 }
 
-// Runs the whole pipeline for n items whose Item records (device pointers) are in c->h_items.
-// Results land in c->h_outs (pinned).  Blocking.
-int fzh_decode_run(FzCtx* c, uint32_t n, int flags)
+// Runs the whole pipeline for items [first, first + n) of c->h_items (Item records holding device
+// pointers).  Results land in c->h_outs[first ..] (pinned).  Blocking on the context's stream.
+int fzh_decode_run(FzCtx* c, uint32_t first, uint32_t n, int flags)
 {
     cudaStream_t s = c->stream;
     const bool prof = flags & FZG_PROFILE;
     c->timing = fzg_timing_t{};
     if (n == 0) return 0;
     int rc;
-    if ((rc = c->d_items.reserve(n * sizeof(Item)))) return rc;
     if ((rc = c->d_infos.reserve(n * sizeof(ItemInfo)))) return rc;
     if ((rc = c->d_bases.reserve(n * sizeof(ItemBase)))) return rc;
     if ((rc = c->d_outs.reserve(n * sizeof(ItemOut)))) return rc;
     if ((rc = c->d_totals.reserve(128))) return rc;
-    Item* d_items = (Item*)c->d_items.p; ItemInfo* d_infos = (ItemInfo*)c->d_infos.p; ItemBase* d_bases = (ItemBase*)c->d_bases.p;
+    // The per-call control data (item records in, totals and per-item results out) lives in pinned host memory that
+    // the kernels access directly (UVA zero-copy).  A cudaMemcpyAsync would queue on the copy engines behind the
+    // gigabyte-sized batch transfers of the neighbouring chunks (see run_batch) and stall the pipeline.
+    const Item* d_items = (const Item*)c->h_items.p + first;
+    ItemInfo* d_infos = (ItemInfo*)c->d_infos.p; ItemBase* d_bases = (ItemBase*)c->d_bases.p;
     ItemOut* d_outs = (ItemOut*)c->d_outs.p; uint64_t* d_totals = (uint64_t*)c->d_totals.p;
     uint32_t* d_tickets = (uint32_t*)(d_totals + 8);               // [0] sequences, [1] execute
+    uint64_t* h_totals = (uint64_t*)c->h_totals.p;
+    ItemOut* h_outs = (ItemOut*)c->h_outs.p + first;
 
-    CK(cudaMemcpyAsync(d_items, c->h_items.p, n * sizeof(Item), cudaMemcpyHostToDevice, s));
-    CK(cudaMemsetAsync(d_tickets, 0, 16, s));
     int ev = 0;
     auto mark = [&]() { if (prof || ev == 0) cudaEventRecord(c->ev[ev], s); ev++; };
     mark();                                                         // ev0: start
     const uint32_t tb = 128, gi = (n + tb - 1) / tb;
-    k_count<<<gi, tb, 0, s>>>(d_items, d_infos, n); mark();
-    k_scan<<<1, 512, 0, s>>>(d_infos, d_bases, d_totals, n); mark();
-    CK(cudaMemcpyAsync(c->h_totals.p, d_totals, 56, cudaMemcpyDeviceToHost, s));
+    k_count<<<gi, tb, 0, s>>>(d_items, d_infos, n, d_tickets); mark();
+    k_scan<<<1, 512, 0, s>>>(d_infos, d_bases, h_totals, n); mark();
     CK(cudaStreamSynchronize(s));
-    const uint64_t* tot = (const uint64_t*)c->h_totals.p;
+    const uint64_t* tot = h_totals;
     const uint64_t n_frames = tot[0], n_blocks = tot[1], n_sj = tot[2], n_hj = tot[3], lit_bytes = tot[4], n_seq = tot[5], n_spans = tot[6];
     if (n_blocks >= (1ull << 31) || n_frames >= (1ull << 31)) return -22;
     if ((rc = c->d_frames.reserve((n_frames + 1) * sizeof(Frame)))) return rc;
@@ -492,10 +496,9 @@ int fzh_decode_run(FzCtx* c, uint32_t n, int flags)
     mark();
     if (n_frames && !(flags & FZG_NO_VERIFY_CHECKSUM)) { k_checksum<<<(uint32_t)((n_frames * 4 + 127) / 128), 128, 0, s>>>(d_frames, d_items, d_outs, (uint32_t)n_frames); launches++; }
     mark();
-    k_finish<<<gi, tb, 0, s>>>(d_infos, d_bases, d_frames, d_outs, n); launches++;
+    k_finish<<<gi, tb, 0, s>>>(d_infos, d_bases, d_frames, d_outs, h_outs, n); launches++;
     if (!prof) ev = 9;
     cudaEventRecord(c->ev[ev], s);                                   // last event
-    CK(cudaMemcpyAsync(c->h_outs.p, d_outs, n * sizeof(ItemOut), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     c->timing.launches = launches;

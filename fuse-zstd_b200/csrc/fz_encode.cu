@@ -6,7 +6,7 @@
 #include "fz_host.h"
 
 int fzh_encode_setup(void) { return 0; }
-int fzh_encode_run(FzCtx*, uint32_t, int, size_t, int) { return -38; /* -ENOSYS */ }
+int fzh_encode_run(FzCtx*, uint32_t, uint32_t, int, size_t, int) { return -38; /* -ENOSYS */ }
 size_t fzh_encode_bound(size_t src_len, size_t chunk)
 {
     if (chunk == 0) chunk = 1u << 20;

@@ -42,7 +42,8 @@ struct FzPinBuf {
 struct FzCtx {
     int dev = -1;
     cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;    // host -> device
+    cudaStream_t copy_stream2 = nullptr;   // device -> host
     cudaEvent_t ev[16] = {};
     std::mutex mu;
     // descriptors + scratch (HBM)
@@ -57,5 +58,5 @@ struct FzCtx {
 
 // fz_decode.cu
 int fzh_decode_setup(void);
-int fzh_decode_run(FzCtx* c, uint32_t n, int flags);
+int fzh_decode_run(FzCtx* c, uint32_t first, uint32_t n, int flags);   // items [first, first + n) of c->h_items
 const char* fzh_decode_stage_name(int s);
