@@ -66,7 +66,7 @@ extern "C" void fzg_shutdown(void)
                            &c->d_seq_jobs, &c->d_huf_jobs, &c->d_lit, &c->d_seq, &c->d_spans, &c->d_stage_src, &c->d_stage_dst,
                            &c->e_items, &c->e_outs, &c->e_work };
         for (auto* b : db) b->release();
-        FzPinBuf* pb[] = { &c->h_items, &c->h_outs, &c->h_totals, &c->h_stage_src, &c->h_stage_dst };
+        FzPinBuf* pb[] = { &c->h_items, &c->h_outs, &c->h_totals, &c->h_stage_src, &c->h_stage_dst, &c->e_chunks_h, &c->e_first_h };
         for (auto* b : pb) b->release();
         for (auto& e : c->ev) cudaEventDestroy(e);
         cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copy_stream); cudaStreamDestroy(c->copy_stream2);

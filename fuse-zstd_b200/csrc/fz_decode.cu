@@ -24,7 +24,6 @@
 
 namespace fz {
 
-__constant__ SeqConsts c_seq_consts = { FZ_LL_BASE, FZ_ML_BASE, FZ_LL_BITS, FZ_ML_BITS, FZ_LL_DEF, FZ_OF_DEF, FZ_ML_DEF };
 
 // ------------------------------------------------------------------ count / scan / fill
 __global__ void k_count(const Item* items, ItemInfo* infos, uint32_t n, uint32_t* tickets)

@@ -1,16 +1,617 @@
 /*
- * fz_encode.cu -- sm_100a zstd encoder (replaces the Encoder flow of
- * /root/reference/src/main.rs:781-791).  Placeholder until the encoder stage lands: the entry
- * points exist so the ABI is complete, and report -ENOSYS.
+ * fz_encode.cu -- sm_100a zstd encoder: replaces the Encoder flow of
+ * /root/reference/src/main.rs:781-791 (Encoder::new(level) + set_pledged_src_size + include_checksum(true) +
+ * io::copy + finish) for a whole batch of files per call.
+ *
+ * Output format: every file becomes a concatenation of INDEPENDENT frames, one per chunk of <= 128 KiB of
+ * input, each with Frame_Content_Size, Single_Segment and the XXH64 content checksum (what the reference's
+ * writer sets), holding one block (Compressed, or Raw when that is not smaller).  The reference's decoder
+ * (zstd::stream::copy_decode, /root/reference/src/main.rs:463) reads concatenated frames as one file, and
+ * independent frames are what lets both this encoder and the decoder run one CTA / warp per frame.
+ * `level` is accepted as the reference passes it (0..19, 0 => default) and selects the one strategy
+ * implemented here, which sits below libzstd level 3 in ratio.
+ *
+ * Stages (one kernel each, all on the context's stream); unit = chunk = frame:
+ *   k_enc_match    warp/chunk    greedy LZ77: 32 positions per step, 4-byte hash, 16 KB shared-memory table
+ *                                per warp (+ __match_any_sync for candidates inside the step), matches verified
+ *                                and extended 8 bytes at a time; emits sequences + the literal run bytes
+ *   k_enc_lit      warp/chunk    literals: histogram -> length-limited (11 bit) code lengths with an exact
+ *                                Kraft sum -> canonical codes in the decoder's order -> direct-weight tree
+ *                                description -> 4 Huffman streams (sizes computed first, written in place)
+ *   k_enc_seq      thread/chunk  sequences: FSE with the Predefined LL/OF/ML tables (RFC 8878 3.1.1.3.2.2),
+ *                                encoding tables built once per CTA in shared memory
+ *   k_enc_place    thread/item   frame sizes -> offsets inside the item's dst, capacity check
+ *   k_enc_write    warp/chunk    frame header + block header + sections (or the raw bytes) + XXH64 trailer
  */
-#include "fz_host.h"
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
 
-int fzh_encode_setup(void) { return 0; }
-int fzh_encode_run(FzCtx*, uint32_t, uint32_t, int, size_t, int) { return -38; /* -ENOSYS */ }
+#include <algorithm>
+#include <vector>
+
+#include "fz_host.h"
+#include "fz_kernels.cuh"
+
+namespace fz {
+
+constexpr uint32_t kEncChunkMax = 128u * 1024u;
+constexpr uint32_t kEncMinMatch = 4;
+constexpr uint32_t kEncHashLog = 13;
+constexpr uint32_t kEncMaxOff = 65535;                       // the table keeps the low 16 bits of a position
+constexpr uint32_t kEncMatchWarps = 4;                       // warps (= chunks in flight) per CTA in k_enc_match
+constexpr uint32_t kHufMaxLen = 11;
+
+struct EncChunk {
+    const uint8_t* src;      // chunk input
+    uint8_t* scratch;        // per-chunk scratch: literals | sequences | literals section | sequences section
+    uint32_t size;           // input bytes (<= 128 KiB)
+    uint32_t item;           // index of the owning item in this launch
+    uint32_t nseq, nlit;     // from k_enc_match
+    uint32_t lit_sec, seq_sec;   // section sizes in bytes (0 lit_sec = not compressible -> raw block)
+    uint32_t frame_size;     // bytes this chunk occupies in the output
+    uint32_t raw;            // 1: the block is stored Raw (set by k_enc_place)
+    uint64_t out_off;        // offset of the frame inside the item's dst
+};
+
+// scratch layout per chunk (offsets from EncChunk::scratch); sized for the worst case
+constexpr uint32_t kScrLit = 0;                                          // literal bytes, <= 128 KiB
+constexpr uint32_t kScrSeq = kEncChunkMax + 64;                          // 8-byte sequence records, <= size/4 + 1
+constexpr uint32_t kScrLitSec = kScrSeq + (kEncChunkMax / kEncMinMatch + 8) * 8;      // literals section
+constexpr uint32_t kScrSeqSec = kScrLitSec + kEncChunkMax + kEncChunkMax / 2 + 1024;  // sequences section
+constexpr uint32_t kScrBytes = kScrSeqSec + kEncChunkMax + kEncChunkMax / 2 + 1024;
+
+FZ_HD uint64_t eseq_pack(uint32_t ll, uint32_t ml, uint32_t off) { return (uint64_t)ll | ((uint64_t)ml << 18) | ((uint64_t)off << 36); }
+FZ_HD uint32_t eseq_ll(uint64_t r) { return (uint32_t)r & 0x3FFFFu; }
+FZ_HD uint32_t eseq_ml(uint64_t r) { return (uint32_t)(r >> 18) & 0x3FFFFu; }
+FZ_HD uint32_t eseq_off(uint64_t r) { return (uint32_t)(r >> 36); }
+
+__device__ __forceinline__ uint64_t ld8u(const uint8_t* g)   // 8 bytes at any alignment (may read up to 15 bytes past g)
+{
+    const uintptr_t a = (uintptr_t)g & ~(uintptr_t)7;
+    const uint32_t sh = (uint32_t)((uintptr_t)g & 7) * 8;
+    const uint64_t w0 = *(const uint64_t*)a;
+    if (sh == 0) return w0;
+    const uint64_t w1 = *(const uint64_t*)(a + 8);
+    return (w0 >> sh) | (w1 << (64 - sh));
+}
+
+// ------------------------------------------------------------------ LZ77 matching
+__global__ void __launch_bounds__(kEncMatchWarps * 32) k_enc_match(EncChunk* chunks, uint32_t n_chunks, uint32_t* ticket)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint16_t* table = (uint16_t*)smem + warp * (1u << kEncHashLog);
+    for (;;) {
+        uint32_t ci = 0;
+        if (lane == 0) ci = atomicAdd(ticket, 1);
+        ci = __shfl_sync(0xFFFFFFFFu, ci, 0);
+        if (ci >= n_chunks) return;
+        EncChunk& ch = chunks[ci];
+        const uint8_t* __restrict__ src = ch.src;
+        const uint32_t size = ch.size;
+        uint8_t* lit = ch.scratch + kScrLit;
+        uint64_t* seq = (uint64_t*)(ch.scratch + kScrSeq);
+        for (uint32_t i = lane; i < (1u << kEncHashLog); i += 32) table[i] = 0;
+        __syncwarp();
+        uint32_t anchor = 0, cur = 0, nseq = 0, nlit = 0;
+        // positions whose 8-byte probe would run past the chunk are left to the trailing literals
+        const uint32_t limit = size >= 16 ? size - 12 : 0;
+        for (uint32_t base = 0; base < limit; base += 32) {
+            const uint32_t p = base + lane;
+            const bool in = p < limit;
+            uint64_t v = 0; uint32_t h = 0;
+            if (in) { v = ld8u(src + p); h = ((uint32_t)v * 2654435761u) >> (32 - kEncHashLog); }
+            // candidates: the nearest earlier lane of this step with the same hash, else the table
+            const uint32_t same = __match_any_sync(0xFFFFFFFFu, in ? h : (0x80000000u | lane));
+            const uint32_t below = same & ((1u << lane) - 1);
+            int32_t cand = -1;
+            if (in) {
+                if (below) cand = (int32_t)(base + (31 - __clz(below)));
+                else {
+                    const uint32_t e = table[h];
+                    int32_t c = (int32_t)((p & ~0xFFFFu) | e);
+                    if (c >= (int32_t)p) c -= 65536;
+                    cand = c;
+                }
+            }
+            __syncwarp();
+            if (in && (same >> lane) == 1) table[h] = (uint16_t)p;          // the highest lane of a group records it
+            // verify + extend (8 bytes per probe)
+            uint32_t len = 0;
+            if (in && p >= cur && cand >= 0 && p - (uint32_t)cand <= kEncMaxOff) {
+                const uint8_t* a = src + cand; const uint8_t* b = src + p;
+                const uint32_t maxlen = size - p;
+                uint64_t x = ld8u(a) ^ v;
+                if ((uint32_t)x == 0) {                                     // at least 4 bytes
+                    while (x == 0 && len + 8 < maxlen) { len += 8; x = ld8u(a + len) ^ ld8u(b + len); }
+                    len += x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8;
+                    if (len > maxlen) len = maxlen;
+                }
+            }
+            // greedy selection, left to right
+            uint32_t avail = __ballot_sync(0xFFFFFFFFu, len >= kEncMinMatch);
+            while (avail) {
+                const uint32_t l = __ffs(avail) - 1;
+                const uint32_t pl = base + l;
+                const uint32_t ml = __shfl_sync(0xFFFFFFFFu, len, l);
+                const uint32_t off = pl - (uint32_t)__shfl_sync(0xFFFFFFFFu, cand, l);
+                if (pl >= cur) {
+                    const uint32_t ll = pl - anchor;
+                    for (uint32_t i = lane; i < ll; i += 32) lit[nlit + i] = src[anchor + i];
+                    if (lane == 0) seq[nseq] = eseq_pack(ll, ml, off);
+                    nseq++; nlit += ll;
+                    anchor = cur = pl + ml;
+                }
+                const uint32_t covered = cur - base;                        // lanes below `cur` are inside the match
+                avail = covered >= 32 ? 0 : avail & ~((1u << covered) - 1) & ~((2u << l) - 1);
+            }
+        }
+        const uint32_t rest = size - anchor;                                // trailing literals
+        for (uint32_t i = lane; i < rest; i += 32) lit[nlit + i] = src[anchor + i];
+        nlit += rest;
+        if (lane == 0) { ch.nseq = nseq; ch.nlit = nlit; }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ literals section
+struct BitOut {             // forward bitstream (LSB first), flushed by bytes
+    uint8_t* p; uint64_t acc; uint32_t n;
+    __device__ __forceinline__ void init(uint8_t* dst) { p = dst; acc = 0; n = 0; }
+    __device__ __forceinline__ void add(uint32_t v, uint32_t nb) { acc |= (uint64_t)v << n; n += nb; }   // caller keeps n <= 56
+    __device__ __forceinline__ void flush() { while (n >= 8) { *p++ = (uint8_t)acc; acc >>= 8; n -= 8; } }
+    __device__ __forceinline__ uint8_t* close() { add(1, 1); flush(); if (n) { *p++ = (uint8_t)acc; } return p; }   // sentinel bit
+};
+
+__device__ __forceinline__ uint32_t lit_header(uint8_t* dst, uint32_t type, uint32_t regen, uint32_t comp, bool four)
+{
+    if (type < 2) {                                   // Raw / RLE: 1, 2 or 3 bytes
+        if (regen < 32) { dst[0] = (uint8_t)(type | (regen << 3)); return 1; }
+        if (regen < 4096) { dst[0] = (uint8_t)(type | (1 << 2) | (regen << 4)); dst[1] = (uint8_t)(regen >> 4); return 2; }
+        dst[0] = (uint8_t)(type | (3 << 2) | (regen << 4)); dst[1] = (uint8_t)(regen >> 4); dst[2] = (uint8_t)(regen >> 12); return 3;
+    }
+    if (regen < 1024 && comp < 1024) {
+        const uint32_t v = type | ((four ? 1u : 0u) << 2) | (regen << 4) | (comp << 14);
+        dst[0] = (uint8_t)v; dst[1] = (uint8_t)(v >> 8); dst[2] = (uint8_t)(v >> 16); return 3;
+    }
+    if (regen < 16384 && comp < 16384) {
+        const uint32_t v = type | (2u << 2) | (regen << 4) | (comp << 18);
+        dst[0] = (uint8_t)v; dst[1] = (uint8_t)(v >> 8); dst[2] = (uint8_t)(v >> 16); dst[3] = (uint8_t)(v >> 24); return 4;
+    }
+    const uint64_t v = type | (3u << 2) | ((uint64_t)regen << 4) | ((uint64_t)comp << 22);
+    for (int i = 0; i < 5; i++) dst[i] = (uint8_t)(v >> (8 * i));
+    return 5;
+}
+__device__ __forceinline__ uint32_t lit_header_size(uint32_t regen, uint32_t comp)
+{
+    return (regen < 1024 && comp < 1024) ? 3 : ((regen < 16384 && comp < 16384) ? 4 : 5);
+}
+
+constexpr int kLitWarps = 4;
+__global__ void __launch_bounds__(kLitWarps * 32) k_enc_lit(EncChunk* chunks, uint32_t n_chunks, uint32_t* ticket)
+{
+    __shared__ uint32_t s_hist[kLitWarps][256];
+    __shared__ uint16_t s_code[kLitWarps][256];
+    __shared__ uint8_t s_len[kLitWarps][256];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* hist = s_hist[warp]; uint16_t* code = s_code[warp]; uint8_t* len = s_len[warp];
+    for (;;) {
+        uint32_t ci = 0;
+        if (lane == 0) ci = atomicAdd(ticket, 1);
+        ci = __shfl_sync(0xFFFFFFFFu, ci, 0);
+        if (ci >= n_chunks) return;
+        EncChunk& ch = chunks[ci];
+        const uint8_t* __restrict__ lit = ch.scratch + kScrLit;
+        uint8_t* out = ch.scratch + kScrLitSec;
+        const uint32_t nlit = ch.nlit;
+        for (uint32_t i = lane; i < 256; i += 32) hist[i] = 0;
+        __syncwarp();
+        for (uint32_t i = lane; i < nlit; i += 32) atomicAdd(&hist[lit[i]], 1u);
+        __syncwarp();
+        // per lane: symbols 8*lane .. 8*lane+7
+        uint32_t cnt[8], nsym = 0, maxsym = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { cnt[j] = hist[8 * lane + j]; if (cnt[j]) { nsym++; maxsym = 8 * lane + j; } }
+        nsym = __reduce_add_sync(0xFFFFFFFFu, nsym);
+        maxsym = __reduce_max_sync(0xFFFFFFFFu, maxsym);
+        uint32_t sec = 0;
+        bool huf = nlit >= 256 && nsym >= 2 && maxsym <= 128;
+        if (huf) {
+            // ---- code lengths: ceil(log2(total / count)) capped at 11, then make the Kraft sum exactly 2^11
+            uint32_t L[8]; uint32_t kraft = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                L[j] = 0;
+                if (cnt[j]) { uint32_t l = 1; while (l < kHufMaxLen && ((uint64_t)cnt[j] << l) < nlit) l++; L[j] = l; kraft += 1u << (kHufMaxLen - l); }
+            }
+            kraft = __reduce_add_sync(0xFFFFFFFFu, kraft);
+            while (kraft > (1u << kHufMaxLen)) {       // too many rare symbols at the cap: lengthen the rarest code that is below the cap
+                uint32_t best = 0xFFFFFFFFu;           // key = count : 18 | length : 4 | symbol : 8
+#pragma unroll
+                for (int j = 0; j < 8; j++) if (cnt[j] && L[j] < kHufMaxLen) best = min(best, (cnt[j] << 12) | (L[j] << 8) | (8 * lane + j));
+                best = __reduce_min_sync(0xFFFFFFFFu, best);
+                const uint32_t s = best & 255, lold = (best >> 8) & 15;
+#pragma unroll
+                for (int j = 0; j < 8; j++) if (8 * lane + j == (int)s) L[j]++;
+                kraft -= 1u << (kHufMaxLen - lold - 1);
+            }
+            while (kraft < (1u << kHufMaxLen)) {       // slack: shorten a longest code (its unit always fits), the most frequent one
+                uint32_t lmax = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) lmax = max(lmax, L[j]);
+                lmax = __reduce_max_sync(0xFFFFFFFFu, lmax);
+                uint32_t best = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) if (L[j] == lmax) best = max(best, (cnt[j] << 8) | (8 * lane + j));
+                best = __reduce_max_sync(0xFFFFFFFFu, best);
+                const uint32_t s = best & 255;
+#pragma unroll
+                for (int j = 0; j < 8; j++) if (8 * lane + j == (int)s) L[j]--;
+                kraft += 1u << (kHufMaxLen - lmax);
+            }
+            uint32_t lmax = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) lmax = max(lmax, L[j]);
+            lmax = __reduce_max_sync(0xFFFFFFFFu, lmax);
+#pragma unroll
+            for (int j = 0; j < 8; j++) len[8 * lane + j] = (uint8_t)L[j];
+            __syncwarp();
+            // ---- canonical codes in the decoder's order: weight ascending (longest codes first), symbol ascending
+            if (lane == 0) {
+                uint32_t rank[kHufMaxLen + 2], next[kHufMaxLen + 2];
+                for (uint32_t w = 0; w <= kHufMaxLen + 1; w++) rank[w] = 0;
+                for (uint32_t s = 0; s <= maxsym; s++) if (len[s]) rank[lmax + 1 - len[s]]++;
+                uint32_t cells = 0;
+                for (uint32_t w = 1; w <= lmax; w++) { next[w] = cells >> (w - 1); cells += rank[w] << (w - 1); }
+                for (uint32_t s = 0; s <= maxsym; s++) if (len[s]) { const uint32_t w = lmax + 1 - len[s]; code[s] = (uint16_t)next[w]++; }
+            }
+            __syncwarp();
+            // ---- stream sizes first, so that the four streams can be written in place
+            const uint32_t seg = (nlit + 3) / 4;
+            uint32_t bits[4] = { 0, 0, 0, 0 };
+            for (uint32_t i = lane; i < nlit; i += 32) {
+                const uint32_t l = len[lit[i]];
+                const uint32_t q = i / seg;
+                bits[0] += q == 0 ? l : 0; bits[1] += q == 1 ? l : 0; bits[2] += q == 2 ? l : 0; bits[3] += q == 3 ? l : 0;
+            }
+            uint32_t bytes[4], total = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) { bytes[q] = (__reduce_add_sync(0xFFFFFFFFu, bits[q]) + 1 + 7) / 8; total += bytes[q]; }
+            const uint32_t tree = 1 + (maxsym + 1) / 2;          // header byte + maxsym direct weights (last one implicit)
+            const uint32_t comp = tree + 6 + total;
+            if (seg * 3 < nlit && comp + 8 < nlit && bytes[0] < 65536 && bytes[1] < 65536 && bytes[2] < 65536) {
+                const uint32_t hs = lit_header_size(nlit, comp);
+                if (lane == 0) {
+                    lit_header(out, 2, nlit, comp, true);
+                    uint8_t* t = out + hs;
+                    t[0] = (uint8_t)(127 + maxsym);
+                    for (uint32_t i = 0; i < maxsym; i += 2) {
+                        const uint32_t w0 = len[i] ? lmax + 1 - len[i] : 0, w1 = (i + 1 < maxsym && len[i + 1]) ? lmax + 1 - len[i + 1] : 0;
+                        t[1 + i / 2] = (uint8_t)((w0 << 4) | w1);
+                    }
+                    uint8_t* j = t + tree;
+                    j[0] = (uint8_t)bytes[0]; j[1] = (uint8_t)(bytes[0] >> 8); j[2] = (uint8_t)bytes[1]; j[3] = (uint8_t)(bytes[1] >> 8);
+                    j[4] = (uint8_t)bytes[2]; j[5] = (uint8_t)(bytes[2] >> 8);
+                }
+                if (lane < 4) {                                    // one Huffman stream per lane, symbols last to first
+                    const uint32_t lo = lane * seg, hi = min(nlit, lo + seg);
+                    uint32_t start = 0;
+                    for (uint32_t q = 0; q < lane; q++) start += bytes[q];
+                    BitOut bo; bo.init(out + hs + tree + 6 + start);
+                    for (uint32_t i = hi; i > lo; i--) {
+                        const uint32_t s = lit[i - 1];
+                        bo.add(code[s], len[s]);
+                        if (bo.n >= 40) bo.flush();
+                    }
+                    bo.close();
+                }
+                sec = hs + comp;
+            } else huf = false;
+        }
+        if (!huf) {
+            if (nsym == 1 && nlit > 1) {                           // RLE literals
+                if (lane == 0) { const uint32_t hs = lit_header(out, 1, nlit, 0, false); out[hs] = lit[0]; sec = hs + 1; }
+                sec = __shfl_sync(0xFFFFFFFFu, sec, 0);
+            } else {                                               // Raw literals
+                uint32_t hs = 0;
+                if (lane == 0) hs = lit_header(out, 0, nlit, 0, false);
+                hs = __shfl_sync(0xFFFFFFFFu, hs, 0);
+                for (uint32_t i = lane; i < nlit; i += 32) out[hs + i] = lit[i];
+                sec = hs + nlit;
+            }
+        }
+        if (lane == 0) ch.lit_sec = sec;
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ sequences section (FSE, predefined tables)
+struct FseCTable {          // encoding table of one predefined distribution (FSE_buildCTable)
+    uint16_t state[64];     // next-state table, tableSize entries
+    int32_t dfs[56];        // deltaFindState per symbol
+    uint32_t dnb[56];       // deltaNbBits per symbol
+    uint32_t log;
+};
+
+__device__ void build_ctable(FseCTable& t, const int16_t* norm, int nsym, int log)
+{
+    const int size = 1 << log; int high = size - 1;
+    uint8_t sym[64]; uint16_t cumul[58];
+    cumul[0] = 0;
+    for (int s = 0; s < nsym; s++) {
+        if (norm[s] == -1) { cumul[s + 1] = cumul[s] + 1; sym[high--] = (uint8_t)s; }
+        else cumul[s + 1] = cumul[s] + (uint16_t)norm[s];
+    }
+    const int step = (size >> 1) + (size >> 3) + 3, mask = size - 1; int pos = 0;
+    for (int s = 0; s < nsym; s++)
+        for (int i = 0; i < norm[s]; i++) { sym[pos] = (uint8_t)s; do { pos = (pos + step) & mask; } while (pos > high); }
+    for (int u = 0; u < size; u++) { const int s = sym[u]; t.state[cumul[s]++] = (uint16_t)(size + u); }
+    int total = 0;
+    for (int s = 0; s < nsym; s++) {
+        const int n = norm[s];
+        if (n == 0) { t.dnb[s] = ((uint32_t)(log + 1) << 16) - (1u << log); t.dfs[s] = 0; }
+        else if (n == -1 || n == 1) { t.dnb[s] = ((uint32_t)log << 16) - (1u << log); t.dfs[s] = total - 1; total++; }
+        else {
+            const uint32_t maxBits = (uint32_t)log - (uint32_t)highbit((uint32_t)n - 1);
+            const uint32_t minStatePlus = (uint32_t)n << maxBits;
+            t.dnb[s] = (maxBits << 16) - minStatePlus; t.dfs[s] = total - n; total += n;
+        }
+    }
+    t.log = (uint32_t)log;
+}
+
+__device__ __forceinline__ uint32_t ll_code(uint32_t ll)
+{
+    if (ll < 16) return ll;
+    if (ll < 64) { const uint32_t t[] = { 16, 16, 17, 17, 18, 18, 19, 19, 20, 20, 20, 20, 21, 21, 21, 21 }; return ll < 32 ? t[ll - 16] : (ll < 40 ? 22 : (ll < 48 ? 23 : 24)); }
+    return (uint32_t)highbit(ll) + 19;
+}
+__device__ __forceinline__ uint32_t ml_code(uint32_t mlb)      // mlb = match length - 3
+{
+    if (mlb < 32) return mlb;
+    if (mlb < 128) {
+        if (mlb < 40) return 32 + ((mlb - 32) >> 1);                    // 32,32,33,33,34,34,35,35
+        if (mlb < 48) return 36 + ((mlb - 40) >> 2);                    // 36 x4, 37 x4
+        if (mlb < 64) return 38 + ((mlb - 48) >> 3);                    // 38 x8, 39 x8
+        if (mlb < 96) return 40 + ((mlb - 64) >> 4);                    // 40 x16, 41 x16
+        return 42;                                                      // 96 .. 127
+    }
+    return (uint32_t)highbit(mlb) + 36;
+}
+
+constexpr int kSeqEncThreads = 128;
+__global__ void __launch_bounds__(kSeqEncThreads) k_enc_seq(EncChunk* chunks, uint32_t n_chunks)
+{
+    __shared__ FseCTable tLL, tOF, tML;
+    __shared__ SeqConsts K;
+    for (uint32_t i = threadIdx.x; i < sizeof(SeqConsts) / 4; i += blockDim.x) ((uint32_t*)&K)[i] = ((const uint32_t*)&c_seq_consts)[i];
+    __syncthreads();
+    if (threadIdx.x == 0) build_ctable(tLL, K.ll_def, 36, 6);
+    if (threadIdx.x == 32) build_ctable(tOF, K.of_def, 29, 5);
+    if (threadIdx.x == 64) build_ctable(tML, K.ml_def, 53, 6);
+    __syncthreads();
+    const uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= n_chunks) return;
+    EncChunk& ch = chunks[ci];
+    const uint64_t* __restrict__ seq = (const uint64_t*)(ch.scratch + kScrSeq);
+    uint8_t* out = ch.scratch + kScrSeqSec;
+    const uint32_t nseq = ch.nseq;
+    uint32_t hs;
+    if (nseq < 128) { out[0] = (uint8_t)nseq; hs = 1; }
+    else if (nseq < 0x7F00) { out[0] = (uint8_t)((nseq >> 8) + 128); out[1] = (uint8_t)nseq; hs = 2; }
+    else { out[0] = 255; out[1] = (uint8_t)(nseq - 0x7F00); out[2] = (uint8_t)((nseq - 0x7F00) >> 8); hs = 3; }
+    if (nseq == 0) { ch.seq_sec = hs; return; }
+    out[hs++] = 0;                                   // Symbol_Compression_Modes: LL, OF, ML all Predefined
+    BitOut bo; bo.init(out + hs);
+    auto init_state = [](const FseCTable& t, uint32_t s) -> uint32_t {      // FSE_initCState2
+        const uint32_t nb = (t.dnb[s] + (1u << 15)) >> 16;
+        const uint32_t value = (nb << 16) - t.dnb[s];
+        return t.state[(value >> nb) + t.dfs[s]];
+    };
+    auto encode = [&bo](const FseCTable& t, uint32_t& state, uint32_t s) {  // FSE_encodeSymbol
+        const uint32_t nb = (state + t.dnb[s]) >> 16;
+        bo.add(state & ((1u << nb) - 1), nb);
+        state = t.state[(state >> nb) + t.dfs[s]];
+    };
+    uint32_t sLL, sOF, sML;
+    {
+        const uint64_t r = seq[nseq - 1];
+        const uint32_t ll = eseq_ll(r), mlb = eseq_ml(r) - 3, ofv = eseq_off(r) + 3;
+        const uint32_t lc = ll_code(ll), mc = ml_code(mlb), oc = (uint32_t)highbit(ofv);
+        sML = init_state(tML, mc); sOF = init_state(tOF, oc); sLL = init_state(tLL, lc);
+        bo.add(ll - K.ll_base[lc], K.ll_bits[lc]); bo.flush();
+        bo.add(mlb + 3 - K.ml_base[mc], K.ml_bits[mc]); bo.flush();
+        bo.add(ofv - (1u << oc), oc); bo.flush();
+    }
+    const uint8_t* const limit = out + kEncChunkMax + kEncChunkMax / 2;     // a section this large means a Raw block anyway
+    for (uint32_t i = nseq - 1; i-- > 0;) {
+        if (bo.p > limit) break;
+        const uint64_t r = seq[i];
+        const uint32_t ll = eseq_ll(r), mlb = eseq_ml(r) - 3, ofv = eseq_off(r) + 3;
+        const uint32_t lc = ll_code(ll), mc = ml_code(mlb), oc = (uint32_t)highbit(ofv);
+        encode(tOF, sOF, oc); encode(tML, sML, mc); encode(tLL, sLL, lc); bo.flush();     // <= 5 + 6 + 6 bits
+        bo.add(ll - K.ll_base[lc], K.ll_bits[lc]); bo.flush();
+        bo.add(mlb + 3 - K.ml_base[mc], K.ml_bits[mc]); bo.flush();
+        bo.add(ofv - (1u << oc), oc); bo.flush();
+    }
+    bo.add(sML - 64, 6); bo.flush();                 // FSE_flushCState: the final states, ML, OF, LL
+    bo.add(sOF - 32, 5); bo.flush();
+    bo.add(sLL - 64, 6); bo.flush();
+    uint8_t* end = bo.close();
+    ch.seq_sec = bo.p > limit ? kEncChunkMax : (uint32_t)(end - out);
+}
+
+// ------------------------------------------------------------------ placement + final write
+__device__ __forceinline__ uint32_t frame_header_size(uint32_t size) { return 4 + 1 + (size < 256 ? 1 : (size < 65536 + 256 ? 2 : 4)); }
+
+__global__ void k_enc_place(const Item* items, EncChunk* chunks, const uint32_t* first_chunk, ItemOut* outs, uint32_t n_items)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    uint64_t pos = 0; int status = 0;
+    for (uint32_t c = first_chunk[i]; c < first_chunk[i + 1]; c++) {
+        EncChunk& ch = chunks[c];
+        const uint32_t body = ch.lit_sec + ch.seq_sec;
+        const bool compressed = ch.size >= 32 && body + 8 < ch.size && body < kEncChunkMax;
+        ch.raw = compressed ? 0 : 1;
+        ch.frame_size = frame_header_size(ch.size) + 3 + (compressed ? body : ch.size) + 4;
+        ch.out_off = pos; pos += ch.frame_size;
+    }
+    if (pos > items[i].dst_cap) status = FZG_E_DSTSIZE;
+    outs[i].dst_len = status ? 0 : pos; outs[i].status = status; outs[i].fail = status != 0;
+}
+
+__global__ void __launch_bounds__(128) k_enc_write(const Item* items, const EncChunk* chunks, const ItemOut* outs, uint32_t n_chunks)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (ci >= n_chunks) return;
+    const EncChunk& ch = chunks[ci];
+    if (outs[ch.item].fail) return;
+    uint8_t* o = items[ch.item].dst + ch.out_off;
+    const uint32_t size = ch.size;
+    const bool compressed = ch.raw == 0;
+    const uint32_t body = compressed ? ch.lit_sec + ch.seq_sec : size;
+    const uint32_t fh = frame_header_size(size);
+    // XXH64 of the chunk: lanes 0..3 own one accumulator each
+    uint64_t acc = lane < 4 ? xx_lane(ch.src, size, lane) : 0;
+    const uint64_t v1 = __shfl_sync(0xFFFFFFFFu, acc, 0), v2 = __shfl_sync(0xFFFFFFFFu, acc, 1), v3 = __shfl_sync(0xFFFFFFFFu, acc, 2),
+                   v4 = __shfl_sync(0xFFFFFFFFu, acc, 3);
+    if (lane == 0) {
+        o[0] = 0x28; o[1] = 0xB5; o[2] = 0x2F; o[3] = 0xFD;
+        // Frame_Header_Descriptor: FCS flag | Single_Segment | Content_Checksum (what the reference's writer sets)
+        if (size < 256) { o[4] = 0x24; o[5] = (uint8_t)size; }
+        else if (size < 65536 + 256) { o[4] = 0x64; o[5] = (uint8_t)(size - 256); o[6] = (uint8_t)((size - 256) >> 8); }
+        else { o[4] = 0xA4; o[5] = (uint8_t)size; o[6] = (uint8_t)(size >> 8); o[7] = (uint8_t)(size >> 16); o[8] = (uint8_t)(size >> 24); }
+        const uint32_t bh = 1u | ((compressed ? 2u : 0u) << 1) | (body << 3);          // Last_Block | type | size
+        o[fh] = (uint8_t)bh; o[fh + 1] = (uint8_t)(bh >> 8); o[fh + 2] = (uint8_t)(bh >> 16);
+        const uint32_t x = (uint32_t)xx_combine(v1, v2, v3, v4, ch.src, size);
+        uint8_t* t = o + fh + 3 + body;
+        t[0] = (uint8_t)x; t[1] = (uint8_t)(x >> 8); t[2] = (uint8_t)(x >> 16); t[3] = (uint8_t)(x >> 24);
+    }
+    uint8_t* b = o + fh + 3;
+    if (compressed) {
+        const uint8_t* ls = ch.scratch + kScrLitSec; const uint8_t* ss = ch.scratch + kScrSeqSec;
+        for (uint32_t i = lane; i < ch.lit_sec; i += 32) b[i] = ls[i];
+        for (uint32_t i = lane; i < ch.seq_sec; i += 32) b[ch.lit_sec + i] = ss[i];
+    } else {
+        for (uint32_t i = lane; i < size; i += 32) b[i] = ch.src[i];
+    }
+}
+
+}  // namespace fz
+
+// ====================================================================== host side
+using namespace fz;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "fzgpu: %s failed: %s (%s:%d)\n", #x, cudaGetErrorString(e_), __FILE__, __LINE__); return -5 /*-EIO*/; } } while (0)
+
+static const char* kEncStageNames[] = { "enc_match", "enc_lit", "enc_seq", "enc_place", "enc_write" };
+const char* fzh_encode_stage_name(int s) { return s >= 0 && s < 5 ? kEncStageNames[s] : ""; }
+
+static size_t enc_chunk_size(size_t chunk) { return chunk == 0 || chunk > kEncChunkMax ? kEncChunkMax : std::max<size_t>(chunk, 1024); }
+
 size_t fzh_encode_bound(size_t src_len, size_t chunk)
 {
-    if (chunk == 0) chunk = 1u << 20;
-    size_t frames = src_len / chunk + 1;
-    return src_len + src_len / 128 + frames * 32 + 64;
+    const size_t cs = enc_chunk_size(chunk);
+    const size_t frames = src_len ? (src_len + cs - 1) / cs : 1;
+    return src_len + frames * 16 + 16;
 }
-const char* fzh_encode_stage_name(int) { return ""; }
+
+int fzh_encode_setup(void)
+{
+    CK(cudaFuncSetAttribute(k_enc_match, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncMatchWarps * (2 << kEncHashLog)));
+    return 0;
+}
+
+// Encodes items [first, first + n) of c->h_items (device pointers).  Results -> c->h_outs[first ..].  Blocking.
+// The per-chunk scratch is large (5.5 bytes per input byte in the worst case), so the chunks are processed in waves.
+int fzh_encode_run(FzCtx* c, uint32_t first, uint32_t n, int level, size_t chunk, int flags)
+{
+    (void)level;
+    cudaStream_t s = c->stream;
+    const bool prof = flags & FZG_PROFILE;
+    c->timing = fzg_timing_t{};
+    if (n == 0) return 0;
+    const Item* h_items = (const Item*)c->h_items.p + first;
+    ItemOut* h_outs = (ItemOut*)c->h_outs.p + first;
+    const size_t cs = enc_chunk_size(chunk);
+    // ---- chunk descriptors, built on the host (sizes are known up front: src/main.rs:773 reads st_size)
+    std::vector<uint32_t> first_chunk(n + 1);
+    uint64_t n_chunks = 0;
+    for (uint32_t i = 0; i < n; i++) { first_chunk[i] = (uint32_t)n_chunks; n_chunks += h_items[i].src_len ? (h_items[i].src_len + cs - 1) / cs : 1; }
+    first_chunk[n] = (uint32_t)n_chunks;
+    if (n_chunks >= (1ull << 31)) return -22;
+    int rc;
+    if ((rc = c->e_chunks_h.reserve(n_chunks * sizeof(EncChunk)))) return rc;
+    if ((rc = c->e_first_h.reserve((n + 1) * 4))) return rc;
+    if ((rc = c->e_items.reserve(n_chunks * sizeof(EncChunk)))) return rc;
+    if ((rc = c->d_outs.reserve(n * sizeof(ItemOut)))) return rc;
+    if ((rc = c->d_totals.reserve(128))) return rc;
+    const uint64_t wave = std::min<uint64_t>(n_chunks, 8192);
+    if ((rc = c->e_work.reserve(wave * (uint64_t)kScrBytes))) return rc;
+    EncChunk* hc = (EncChunk*)c->e_chunks_h.p;
+    memcpy(c->e_first_h.p, first_chunk.data(), (n + 1) * 4);
+    for (uint32_t i = 0; i < n; i++) {
+        uint64_t off = 0;
+        for (uint32_t k = first_chunk[i]; k < first_chunk[i + 1]; k++) {
+            EncChunk& ch = hc[k];
+            ch.src = h_items[i].src + off; ch.size = (uint32_t)std::min<uint64_t>(cs, h_items[i].src_len - off); off += ch.size;
+            ch.scratch = (uint8_t*)c->e_work.p + (uint64_t)(k % wave) * kScrBytes;
+            ch.item = i; ch.nseq = ch.nlit = ch.lit_sec = ch.seq_sec = ch.frame_size = ch.raw = 0; ch.out_off = 0;
+        }
+    }
+    EncChunk* d_chunks = (EncChunk*)c->e_items.p;
+    ItemOut* d_outs = (ItemOut*)c->d_outs.p;
+    uint32_t* d_tickets = (uint32_t*)c->d_totals.p;
+    CK(cudaMemcpyAsync(d_chunks, hc, n_chunks * sizeof(EncChunk), cudaMemcpyHostToDevice, s));
+    int ev = 0;
+    auto mark = [&]() { if (prof || ev == 0) cudaEventRecord(c->ev[ev], s); ev++; };
+    mark();
+    int launches = 0;
+    const uint64_t n_waves = (n_chunks + wave - 1) / wave;
+    uint32_t* d_first = (uint32_t*)c->e_first_h.p;                         // pinned host memory, read zero-copy
+    auto run_wave = [&](uint64_t w, bool marks) -> int {
+        const uint64_t lo = w * wave; const uint32_t cnt = (uint32_t)std::min<uint64_t>(wave, n_chunks - lo);
+        CK(cudaMemsetAsync(d_tickets, 0, 16, s));
+        k_enc_match<<<std::min<uint32_t>((cnt + kEncMatchWarps - 1) / kEncMatchWarps, 148 * 3), kEncMatchWarps * 32, kEncMatchWarps * (2 << kEncHashLog), s>>>(d_chunks + lo, cnt, d_tickets);
+        if (marks) mark();
+        k_enc_lit<<<std::min<uint32_t>((cnt + kLitWarps - 1) / kLitWarps, 148 * 8), kLitWarps * 32, 0, s>>>(d_chunks + lo, cnt, d_tickets + 1);
+        if (marks) mark();
+        k_enc_seq<<<(cnt + kSeqEncThreads - 1) / kSeqEncThreads, kSeqEncThreads, 0, s>>>(d_chunks + lo, cnt);
+        if (marks) mark();
+        launches += 3;
+        return 0;
+    };
+    // k_enc_write needs every frame's offset, i.e. every chunk's compressed size, while the per-chunk scratch only
+    // holds one wave (8192 chunks = 1 GiB of input).  One wave: match -> lit -> seq -> place -> write.  Several waves:
+    // pass 1 sizes all waves, then each wave is regenerated (the stages are deterministic) and written.
+    if (n_waves == 1) {
+        if ((rc = run_wave(0, true))) return rc;
+        k_enc_place<<<(n + 127) / 128, 128, 0, s>>>(h_items, d_chunks, d_first, d_outs, n); mark();
+        k_enc_write<<<(uint32_t)((n_chunks * 32 + 127) / 128), 128, 0, s>>>(h_items, d_chunks, d_outs, (uint32_t)n_chunks); mark();
+        launches += 2;
+    } else {
+        for (uint64_t w = 0; w < n_waves; w++) if ((rc = run_wave(w, false))) return rc;
+        mark(); mark(); mark();
+        k_enc_place<<<(n + 127) / 128, 128, 0, s>>>(h_items, d_chunks, d_first, d_outs, n); mark();
+        launches++;
+        for (uint64_t w = 0; w < n_waves; w++) {
+            const uint64_t lo = w * wave; const uint32_t cnt = (uint32_t)std::min<uint64_t>(wave, n_chunks - lo);
+            if ((rc = run_wave(w, false))) return rc;
+            k_enc_write<<<(cnt * 32 + 127) / 128, 128, 0, s>>>(h_items, d_chunks + lo, d_outs, cnt);
+            launches++;
+        }
+        mark();
+    }
+    if (!prof) ev = 5;
+    cudaEventRecord(c->ev[ev], s);
+    CK(cudaMemcpyAsync(h_outs, d_outs, n * sizeof(ItemOut), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    c->timing.launches = launches;
+    cudaEventElapsedTime(&c->timing.total_ms, c->ev[0], c->ev[ev]);
+    if (prof) for (int k = 0; k < 5; k++) cudaEventElapsedTime(&c->timing.kernel_ms[k], c->ev[k], c->ev[k + 1]);
+    return 0;
+}

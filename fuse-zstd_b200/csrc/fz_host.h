@@ -50,7 +50,7 @@ struct FzCtx {
     FzDevBuf d_items, d_infos, d_bases, d_outs, d_totals, d_frames, d_blocks, d_seq_jobs, d_huf_jobs, d_lit, d_seq, d_spans;
     // staging for host-resident batches
     FzDevBuf d_stage_src, d_stage_dst;
-    FzPinBuf h_items, h_outs, h_totals, h_stage_src, h_stage_dst;
+    FzPinBuf h_items, h_outs, h_totals, h_stage_src, h_stage_dst, e_chunks_h, e_first_h;
     // encoder scratch
     FzDevBuf e_items, e_outs, e_work;
     fzg_timing_t timing = {};

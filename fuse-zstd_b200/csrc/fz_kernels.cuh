@@ -10,6 +10,10 @@ namespace fz {
 
 struct ItemOut { uint64_t dst_len; int32_t status; int32_t fail; };
 
+#ifdef __CUDACC__
+static __constant__ SeqConsts c_seq_consts = { FZ_LL_BASE, FZ_ML_BASE, FZ_LL_BITS, FZ_ML_BITS, FZ_LL_DEF, FZ_OF_DEF, FZ_ML_DEF };
+#endif
+
 // ------------------------------------------------------------------ literals pass (four threads per block)
 // thread 0 of the group: tree description (possibly from an earlier block: Treeless) -> table.
 // log < 0 reports a malformed description.

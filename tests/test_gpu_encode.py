@@ -1,0 +1,148 @@
+"""Parity tests of the CUDA encoder (B200), called through the C ABI (fzg_encode_batch / fzg_encode_fd): every frame it
+emits must decode, bit-exactly, through
+
+  * stock libzstd driven exactly as the reference's reader drives it (zstd::stream::copy_decode,
+    /root/reference/src/main.rs:463-467 -> oracle/_ref),
+  * the plain-C oracle (oracle/zstd_oracle.c),
+  * this repo's CUDA decoder,
+
+and carry what the reference's writer sets (/root/reference/src/main.rs:781-791): Frame_Content_Size and the XXH64
+content checksum.  The compression ratio is reported against libzstd level 3 with a stated bound.
+"""
+import importlib
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+codec = importlib.import_module("fuse-zstd_b200.codec")
+stream = importlib.import_module("fuse-zstd_b200.stream")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    codec.build()
+    codec.init([0])
+    yield
+
+
+def _inputs(corpus):
+    rs = np.random.RandomState(11)
+    j = corpus.json_file(31337, 3 << 20).tobytes()
+    cases = {
+        "empty": b"",
+        "one_byte": b"x",
+        "ref_compressed_data": b"compressed data",                 # tests/convert.rs:16-25
+        "ref_truncated_and_appended": b"truncated and appended",   # tests/cmdline.rs:160-178
+        "json_1MiB": j[: 1 << 20],
+        "json_3MiB": j,
+        "json_131071": j[:131071], "json_131072": j[:131072], "json_131073": j[:131073],
+        "json_5000": j[:5000], "json_300": j[:300], "json_40": j[:40],
+        "random_200k": rs.randint(0, 256, 200000, dtype=np.uint8).tobytes(),
+        "lowentropy_300k": bytes(rs.randint(0, 16, 300000, dtype=np.uint8)),
+        "binary_highsyms_300k": bytes((rs.randint(0, 40, 300000) * 6 + 3).astype(np.uint8)),   # symbols > 128: Raw literals path
+        "aaaa_400k": b"a" * 400000,
+        "period23_300k": (rs.randint(0, 256, 23, dtype=np.uint8).tobytes() * 14000)[:300000],
+        "two_symbols": bytes(rs.randint(0, 2, 50000, dtype=np.uint8) + 65),
+        "long_distance": j[:60000] + rs.randint(0, 256, 30000, dtype=np.uint8).tobytes() + j[:60000],
+    }
+    return cases
+
+
+def test_empty_file_is_the_reference_frame():
+    """create() encodes an empty file (src/main.rs:527-531); tests/cmdline.rs:34-43 pins the 13 bytes"""
+    (st, comp), = codec.encode_batch([b""])
+    assert st == 0
+    assert comp.hex() == "28b52ffd2400010000" "99e9d851"
+
+
+def test_round_trip_through_libzstd_oracle_and_cuda_decoder(ref, oracle, corpus):
+    cases = _inputs(corpus)
+    names = sorted(cases)
+    res = codec.encode_batch([cases[n] for n in names])
+    comps = []
+    for n, (st, comp) in zip(names, res):
+        assert st == 0, n
+        assert len(comp) <= codec.encode_bound(len(cases[n])), n
+        comps.append(comp)
+        st_i, size, csize = codec.frame_info(comp)
+        assert st_i == 0 and size == len(cases[n]) and csize == len(comp), n     # every frame carries FCS
+        st_o, out_o = oracle.decode(comp, cap=len(cases[n]))
+        assert st_o == 0 and out_o == cases[n], (n, st_o)
+        if ref.available:
+            st_r, out_r = ref.copy_decode(comp, len(cases[n]))                 # the reference's reader on stock libzstd
+            assert st_r == 0 and out_r == cases[n], (n, st_r)
+    back = codec.decode_batch(comps, [len(cases[n]) for n in names])
+    for n, (st, out) in zip(names, back):
+        assert st == 0 and out == cases[n], n
+
+
+def test_checksum_is_present_and_checked(corpus, oracle):
+    plain = corpus.json_file(5, 200000).tobytes()
+    (st, comp), = codec.encode_batch([plain])
+    assert st == 0
+    assert comp[4] & 0x04, "Content_Checksum flag (include_checksum(true), src/main.rs:789)"
+    bad = bytearray(comp); bad[-1] ^= 0xFF
+    assert oracle.decode(bytes(bad), cap=len(plain))[0] == 6            # XXH64 mismatch
+
+
+def test_ratio_against_libzstd_level3(ref, corpus):
+    """the stated bound: total bytes <= 1.60 x libzstd level 3 (reference-writer framing) on the JSON corpus"""
+    if not ref.available:
+        pytest.skip("system libzstd absent")
+    n, size = 64, 1 << 20
+    plain = corpus.json_files(900000, n, size)
+    res = codec.encode_batch([plain[i] for i in range(n)])
+    ours = sum(len(c) for st, c in res)
+    assert all(st == 0 for st, _ in res)
+    theirs = sum(len(ref.writer_encode(plain[i].tobytes(), 3)) for i in range(n))
+    ratio = ours / theirs
+    print("\nencoder: %d bytes vs libzstd L3 %d bytes -> x%.3f ; ratio %.3f vs %.3f" % (ours, theirs, ratio, n * size / ours, n * size / theirs))
+    assert ratio <= 1.60
+
+
+def test_encoder_flow_through_fd_entry_points(ref, corpus):
+    """Encoder::new(w, level) + set_pledged_src_size + include_checksum(true) + io::copy + finish (src/main.rs:781-791)"""
+    plain = corpus.json_file(99, 700001).tobytes()
+    with tempfile.TemporaryFile() as out:
+        enc = stream.Encoder(out, level=0, inode=2**64 - 9)
+        enc.set_pledged_src_size(len(plain)); enc.include_checksum(True)
+        for o in range(0, len(plain), 8192):
+            enc.write(plain[o:o + 8192])
+        n = enc.finish()
+        out.seek(0); comp = out.read()
+        assert n == len(comp)
+    if ref.available:
+        st, back = ref.copy_decode(comp, len(plain))
+        assert st == 0 and back == plain
+    with tempfile.TemporaryFile() as src:                               # and back through copy_decode
+        src.write(comp); src.flush(); src.seek(0)
+        assert stream.decode_all(src) == plain
+    with tempfile.TemporaryFile() as out:                               # pledged size mismatch -> EIO-class failure
+        enc = stream.Encoder(out, level=3); enc.set_pledged_src_size(5); enc.write(b"123456")
+        with pytest.raises(OSError):
+            enc.finish()
+
+
+def test_device_resident_encode(corpus):
+    import torch
+    n, size = 16, 1 << 20
+    plain = corpus.json_files(910000, n, size)
+    d_src = torch.from_numpy(plain).cuda()
+    cap = codec.encode_bound(size)
+    d_dst = torch.zeros(n * cap, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    dl, st = codec.encode_batch_ptrs(0, [d_src.data_ptr() + i * size for i in range(n)], [size] * n,
+                                     [d_dst.data_ptr() + i * cap for i in range(n)], [cap] * n, 3, 0,
+                                     codec.SRC_DEVICE | codec.DST_DEVICE)
+    assert not st.any()
+    host = d_dst.cpu().numpy()
+    comps = [host[i * cap:i * cap + int(dl[i])].tobytes() for i in range(n)]
+    back = codec.decode_batch(comps, [size] * n)
+    for i, (s, out) in enumerate(back):
+        assert s == 0 and out == plain[i].tobytes(), i
