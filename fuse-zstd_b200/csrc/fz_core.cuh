@@ -737,36 +737,157 @@ FZ_HD void store_rec_pair(uint64_t* at, uint64_t a, uint64_t b)   // `at` is 16-
 #endif
 }
 
-// ------------------------------------------------------------------ sequence decode (one thread per block)
-// tables: tLL (512 cells), tOF (256), tML (512) and `scratch` (64 int16 + 64 uint16) in shared memory.
-// Writes nseq records at `out`, the span index at `span` and b.rsize / b.rep_out.  Returns 0 or
-// FZG_E_CORRUPT.
+// ------------------------------------------------------------------ sequence pass, stage A: the FSE chain
+// The three-state FSE chain is the only inherently serial part of a block, so stage A does nothing
+// else: one thread per block walks the backward bitstream and leaves one 8-byte RAW record per
+// sequence; everything that can be done for many sequences at once (extra bits -> values, running
+// positions, repeat offsets, span index) is stage B (warp per block, fz_decode.cu).
 //
-// SIMT shape: the lanes of a warp decode different blocks, so the sequence loop must run in lockstep
-// or the warp degenerates into 32 serial threads.  The function therefore has a single exit, the
-// table build (data-dependent control flow) is fenced off with a warp barrier, and the loop runs a
-// warp-uniform number of iterations (`bound` = the largest nseq among the lanes in `mask`), each lane
-// masking itself out once its own block is done or found corrupt.
+// Shared memory per stream (3840 bytes, 60 streams per SM):
+//   uint16 cLL[512] | uint16 cML[512] | uint16 cOF[256] | uint8 yLL[512] | uint8 yML[512] | ring[256]
+// A chain cell is 16 bits: J[0:10) | extra[10:15), where J encodes (baseline, nbBits) jointly as
+// ((baseline >> nb) << 1 | 1) << nb -- nb = ctz(J), baseline = (J & (J - 1)) >> 1 -- and `extra` is the
+// number of extra bits of the cell's symbol (for offsets that IS the symbol).  The LL / ML symbols
+// themselves are only needed by stage B and sit in the byte tables yLL / yML, off the chain.
+//
+// RAW record, fast form (every field of the sequence fits in the 32-bit window x):
+//   x[0:32) | symLL[32:38) | symML[38:44) | symOF[44:49) | 0
+// RAW record, slow form (long lengths / offsets, decoded field by field):
+//   ll[0:18) | (ml - 3)[18:35) | offset_value[35:63) | 1[63]
+constexpr uint32_t kChainCellsLL = 512, kChainCellsML = 512, kChainCellsOF = 256;
+constexpr uint32_t kChainBytes = (kChainCellsLL + kChainCellsML + kChainCellsOF) * 2 + kChainCellsLL + kChainCellsML + 256;
+
+FZ_HD uint32_t chain_pack(uint32_t base, uint32_t nb, uint32_t extra) { return ((((base >> nb) << 1) | 1u) << nb) | (extra << 10); }
+FZ_HD uint32_t ctz32(uint32_t v)
+{
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__ffs((int)v) - 1u;
+#else
+    return (uint32_t)__builtin_ctz(v);
+#endif
+}
+
+// Same construction as build_fse_table, chain-cell output.  ysym (1 << log bytes) receives the symbol of
+// every cell (used as the spread buffer first); it may be nullptr for offsets only if `spread` is given.
+FZ_HD int build_chain_table(uint16_t* cell, uint8_t* ysym, const int16_t* norm, int n_sym, int log, const uint8_t* extra_bits, uint16_t* cnt)
+{
+    const int size = 1 << log; int high = size - 1;
+    for (int s = 0; s < n_sym; s++) {
+        if (norm[s] == -1) { ysym[high--] = (uint8_t)s; cnt[s] = 1; }
+        else cnt[s] = (uint16_t)norm[s];
+    }
+    const int step = (size >> 1) + (size >> 3) + 3, mask = size - 1; int pos = 0;
+    for (int s = 0; s < n_sym; s++) {
+        for (int i = 0; i < norm[s]; i++) {
+            ysym[pos] = (uint8_t)s;
+            do { pos = (pos + step) & mask; } while (pos > high);
+        }
+    }
+    if (pos != 0) return -1;
+    for (int u = 0; u < size; u++) {
+        const uint32_t s = ysym[u];
+        const uint32_t nx = cnt[s]++;
+        const uint32_t nb = (uint32_t)(log - highbit(nx));
+        cell[u] = (uint16_t)chain_pack((nx << nb) - (uint32_t)size, nb, extra_bits ? extra_bits[s] : s);
+    }
+    return 0;
+}
+
+// Chain tables of block b for table `which` (0 LL, 1 OF, 2 ML), resolving Repeat through b.*_src.
+FZ_HD int build_chain_seq_table(const Block* blocks, const Block& b, int which, const uint8_t* p, uint32_t n,
+                                const SeqConsts& K, uint16_t* cell, uint8_t* ysym, int& log, uint32_t& used, uint16_t* scratch)
+{
+    int16_t* norm = (int16_t*)scratch; uint16_t* cnt = scratch + 64;
+    int mode = (b.modes >> (6 - 2 * which)) & 3;
+    const int max_sym = which == 0 ? kMaxLL : (which == 1 ? kMaxOF : kMaxML);
+    const int max_log = which == 0 ? kLLLog : (which == 1 ? kOFLog : kMLLog);
+    const uint8_t* extra = which == 0 ? K.ll_bits : (which == 2 ? K.ml_bits : nullptr);
+    const bool own = mode != 3;
+    used = 0;
+    if (!own) {
+        int32_t src = which == 0 ? b.ll_src : (which == 1 ? b.of_src : b.ml_src);
+        if (src < 0) return -1;
+        mode = locate_table(blocks[src], which, p, n);
+        if (mode < 0 || mode == 3) return -1;
+    }
+    if (mode == 0) {
+        const int16_t* def = which == 0 ? K.ll_def : (which == 1 ? K.of_def : K.ml_def);
+        log = which == 1 ? 5 : 6;
+        return build_chain_table(cell, ysym, def, which == 0 ? 36 : (which == 1 ? 29 : 53), log, extra, cnt);
+    }
+    if (mode == 1) {
+        if (n < 1 || p[0] > max_sym) return -1;
+        const uint32_t sy = p[0];
+        cell[0] = (uint16_t)chain_pack(0, 0, extra ? extra[sy] : sy); ysym[0] = (uint8_t)sy; log = 0;
+        if (own) used = 1;
+        return 0;
+    }
+    int ns;
+    const int u = read_ncount(p, n, max_sym, max_log, norm, ns, log);
+    if (u < 0) return -1;
+    if (own) used = (uint32_t)u;
+    return build_chain_table(cell, ysym, norm, ns, log, extra, cnt);
+}
+
+FZ_HD uint64_t raw_pack_fast(uint32_t x, uint32_t yll, uint32_t yml, uint32_t yof) { return (uint64_t)x | ((uint64_t)(yll | (yml << 6) | (yof << 12)) << 32); }
+FZ_HD uint64_t raw_pack_slow(uint32_t ll, uint32_t ml, uint32_t ofv) { return (uint64_t)(ll & 0x3FFFFu) | ((uint64_t)((ml - 3) & 0x1FFFFu) << 18) | ((uint64_t)(ofv & 0xFFFFFFFu) << 35) | (1ull << 63); }
+// RAW -> (literal length, match length, offset value).  Returns false when the offset code is beyond any legal window.
+FZ_HD bool raw_unpack(uint64_t r, const SeqConsts& K, uint32_t& ll, uint32_t& ml, uint32_t& ofv)
+{
+    if (r >> 63) { ll = (uint32_t)r & 0x3FFFFu; ml = ((uint32_t)(r >> 18) & 0x1FFFFu) + 3; ofv = (uint32_t)(r >> 35) & 0xFFFFFFFu; return true; }
+    const uint32_t x = (uint32_t)r, y = (uint32_t)(r >> 32);
+    const uint32_t yll = y & 63, yml = (y >> 6) & 63, yof = (y >> 12) & 31;
+    const uint32_t ofb = yof, mlb = K.ml_bits[yml], llb = K.ll_bits[yll];
+    ofv = (1u << yof) + shr_c(x, 32 - ofb);
+    ml = K.ml_base[yml] + shr_c(shl_c(x, ofb), 32 - mlb);
+    ll = K.ll_base[yll] + shr_c(shl_c(x, ofb + mlb), 32 - llb);
+    return yof <= 27;
+}
+// RFC 8878 3.1.1.5 on a (possibly symbolic) history; returns the match distance of this sequence.
+FZ_HD uint32_t rep_update(uint32_t ofv, bool ll0, uint32_t& rep0, uint32_t& rep1, uint32_t& rep2)
+{
+    uint32_t off;
+    if (ofv > 3) { off = ofv - 3; rep2 = rep1; rep1 = rep0; rep0 = off; }
+    else {
+        const uint32_t idx = ofv - 1 + (ll0 ? 1u : 0u);
+        if (idx == 0) off = rep0;
+        else {
+            off = idx == 3 ? off_dec(rep0) : (idx == 1 ? rep1 : rep2);
+            if (idx != 1) rep2 = rep1;
+            rep1 = rep0; rep0 = off;
+        }
+    }
+    return off;
+}
+
 #ifdef __CUDA_ARCH__
 #define FZ_SYNCWARP(mask) __syncwarp(mask)
 #else
 #define FZ_SYNCWARP(mask) ((void)(mask))
 #endif
 
-FZ_HD int decode_sequences(const Block* blocks, Block& b, uint32_t block_max, const SeqConsts& K,
-                           uint32_t* tLL, uint32_t* tOF, uint32_t* tML, uint16_t* scratch,
-                           uint64_t* out, uint16_t* span, uint32_t bound, uint32_t mask)
+// Stage A.  `mem` = this stream's kChainBytes of shared memory.  Writes nseq RAW records at `out`.
+// SIMT shape: the lanes of a warp run different blocks, so the loop must stay in lockstep or the warp
+// degenerates into serial threads: single exit, the table build (data-dependent control flow) is
+// fenced off with a warp barrier, and the loop runs a warp-uniform number of iterations (`bound` =
+// the largest nseq among the lanes in `mask`), each lane masking itself out when its block is done.
+FZ_HD int decode_sequences_chain(const Block* blocks, const Block& b, const SeqConsts& K, uint8_t* mem,
+                                 uint64_t* out, uint32_t bound, uint32_t mask)
 {
+    uint16_t* cLL = (uint16_t*)mem; uint16_t* cML = cLL + kChainCellsLL; uint16_t* cOF = cML + kChainCellsML;
+    uint8_t* yLL = (uint8_t*)(cOF + kChainCellsOF); uint8_t* yML = yLL + kChainCellsLL;
+    uint16_t* scratch = (uint16_t*)(yML + kChainCellsML);             // 256 bytes: table-build scratch, then the bitstream ring
     int st = 0;
     int logLL = 0, logOF = 0, logML = 0;
     SeqBits br;
     uint32_t sLL = 0, sOF = 0, sML = 0;
     {
         const uint8_t* p = b.src + b.seq_hdr; uint32_t n = b.csize - b.seq_hdr; uint32_t used = 0;
-        if (build_seq_table(blocks, b, 0, p, n, K, tLL, logLL, used, scratch) != 0) st = FZG_E_CORRUPT;
-        if (!st) { p += used; n -= used; if (build_seq_table(blocks, b, 1, p, n, K, tOF, logOF, used, scratch) != 0) st = FZG_E_CORRUPT; }
-        if (!st) { p += used; n -= used; if (build_seq_table(blocks, b, 2, p, n, K, tML, logML, used, scratch) != 0) st = FZG_E_CORRUPT; }
-        if (!st) { p += used; n -= used; if (br.init(p, n, (uint8_t*)scratch) != 0) st = FZG_E_CORRUPT; }   // scratch becomes the ring
+        if (build_chain_seq_table(blocks, b, 0, p, n, K, cLL, yLL, logLL, used, scratch) != 0) st = FZG_E_CORRUPT;
+        // the offset table's symbol bytes are not kept: yML (not built yet) serves as its spread buffer
+        if (!st) { p += used; n -= used; if (build_chain_seq_table(blocks, b, 1, p, n, K, cOF, yML, logOF, used, scratch) != 0) st = FZG_E_CORRUPT; }
+        if (!st) { p += used; n -= used; if (build_chain_seq_table(blocks, b, 2, p, n, K, cML, yML, logML, used, scratch) != 0) st = FZG_E_CORRUPT; }
+        if (!st) { p += used; n -= used; if (br.init(p, n, (uint8_t*)scratch) != 0) st = FZG_E_CORRUPT; }
         if (!st) {
             br.refill(); br.refill();
             sLL = br.read((uint32_t)logLL);
@@ -775,78 +896,45 @@ FZ_HD int decode_sequences(const Block* blocks, Block& b, uint32_t block_max, co
             if (br.left < 0) st = FZG_E_CORRUPT;
         }
     }
-    const uint32_t nseq = b.nseq, lit_regen = b.lit_regen;
-    uint32_t live = st ? 0 : nseq;                      // this lane's remaining trip count
-    uint32_t rep0 = off_sym(0), rep1 = off_sym(1), rep2 = off_sym(2);
-    uint32_t E = 0, LE = 0;
+    const uint32_t nseq = b.nseq;
+    const uint32_t live = st ? 0 : nseq;                // this lane's trip count
     uint64_t held = 0;
     FZ_SYNCWARP(mask);
     for (uint32_t i = 0; i < bound; i++) {
         if (i < live) {
-            const uint32_t cLL = tLL[sLL], cOF = tOF[sOF], cML = tML[sML];
-            const uint32_t ofb = cell_extra(cOF), mlb = cell_extra(cML), llb = cell_extra(cLL);
+            const uint32_t cl = cLL[sLL], co = cOF[sOF], cm = cML[sML];
+            const uint32_t yl = yLL[sLL], ym = yML[sML];              // off the chain: only stage B wants the symbols
+            const uint32_t jl = cl & 1023u, jo = co & 1023u, jm = cm & 1023u;
+            const uint32_t llb = cl >> 10, ofb = co >> 10, mlb = cm >> 10;
             const bool more = i + 1 < nseq;
-            const uint32_t nLL = more ? cell_nb(cLL) : 0, nML = more ? cell_nb(cML) : 0, nOF = more ? cell_nb(cOF) : 0;
-            const uint32_t a1 = ofb, a2 = a1 + mlb, a3 = a2 + llb, a4 = a3 + nLL, a5 = a4 + nML, need = a5 + nOF;
+            const uint32_t nLL = more ? ctz32(jl) : 0, nML = more ? ctz32(jm) : 0, nOF = more ? ctz32(jo) : 0;
+            const uint32_t a3 = ofb + mlb + llb, a4 = a3 + nLL, a5 = a4 + nML, need = a5 + nOF;
             br.top_up(); ring_wait<8>();          // the word consumed now was fetched >= 20 iterations ago
             br.refill();
-            uint32_t ofx, mlx, llx;
+            uint64_t raw;
             if (need <= 32) {                     // common case: every field of this sequence sits in `hi`
                 const uint32_t x = br.hi;
-                ofx = shr_c(x, 32 - ofb);
-                mlx = shr_c(shl_c(x, a1), 32 - mlb);
-                llx = shr_c(shl_c(x, a2), 32 - llb);
-                sLL = cell_base(cLL) + shr_c(shl_c(x, a3), 32 - nLL);
-                sML = cell_base(cML) + shr_c(shl_c(x, a4), 32 - nML);
-                sOF = cell_base(cOF) + shr_c(shl_c(x, a5), 32 - nOF);
+                sLL = ((jl & (jl - 1)) >> 1) + shr_c(shl_c(x, a3), 32 - nLL);
+                sML = ((jm & (jm - 1)) >> 1) + shr_c(shl_c(x, a4), 32 - nML);
+                sOF = ((jo & (jo - 1)) >> 1) + shr_c(shl_c(x, a5), 32 - nOF);
                 br.skip(need);
+                raw = raw_pack_fast(x, yl, ym, ofb);
             } else {                              // long offsets / lengths: field by field
-                ofx = br.read(ofb);
+                const uint32_t ofx = br.read(ofb);
                 br.refill();
-                mlx = br.read(mlb); llx = br.read(llb);
+                const uint32_t mlx = br.read(mlb), llx = br.read(llb);
                 br.refill();
-                sLL = cell_base(cLL) + br.read(nLL);
-                sML = cell_base(cML) + br.read(nML);
-                sOF = cell_base(cOF) + br.read(nOF);
+                sLL = ((jl & (jl - 1)) >> 1) + br.read(nLL);
+                sML = ((jm & (jm - 1)) >> 1) + br.read(nML);
+                sOF = ((jo & (jo - 1)) >> 1) + br.read(nOF);
+                // an offset code beyond any legal window is kept visible for stage B (it tests the value)
+                raw = raw_pack_slow(K.ll_base[yl] + llx, K.ml_base[ym] + mlx, ofb > 27 ? 0xFFFFFFFu : (1u << ofb) + ofx);
             }
-            const uint32_t ofc = cell_sym(cOF);
-            const uint32_t ofv = (1u << (ofc & 31)) + ofx;
-            const uint32_t ml = K.ml_base[cell_sym(cML)] + mlx;
-            const uint32_t ll = K.ll_base[cell_sym(cLL)] + llx;
-            uint32_t off;                                       // RFC 8878 3.1.1.5 on (possibly symbolic) history
-            if (ofv > 3) { off = ofv - 3; rep2 = rep1; rep1 = rep0; rep0 = off; }
-            else {
-                const uint32_t idx = ofv - 1 + (ll == 0);
-                if (idx == 0) off = rep0;
-                else {
-                    off = idx == 3 ? off_dec(rep0) : (idx == 1 ? rep1 : rep2);
-                    if (idx != 1) rep2 = rep1;
-                    rep1 = rep0; rep0 = off;
-                }
-            }
-            const uint32_t Ep = E;
-            LE += ll; E += ll + ml;
-            if (ofc > 27 || (ofv > 3 && off > kOffMax) || LE > lit_regen || E > block_max) { st = FZG_E_CORRUPT; live = 0; }
-            else {
-                const uint32_t s1 = (E - 1) / kSpan;              // span boundaries kSpan * s inside [Ep, E): almost always 0 or 1
-                if (s1 * kSpan >= Ep) span[s1] = (uint16_t)i;
-                if (E - Ep > kSpan) for (uint32_t s = (Ep + kSpan - 1) / kSpan; s < s1; s++) span[s] = (uint16_t)i;
-                const uint64_t rec = rec_pack(E, LE, off);
-                if (i & 1) store_rec_pair(out + i - 1, held, rec); else held = rec;
-            }
+            if (i & 1) store_rec_pair(out + i - 1, held, raw); else held = raw;
         }
     }
     if (!st && br.left != 0) st = FZG_E_CORRUPT;
-    if (!st) {
-        if (nseq & 1) out[nseq - 1] = held;
-        const uint32_t rsize = E + (lit_regen - LE);
-        if (rsize > block_max) st = FZG_E_CORRUPT;
-        else {
-            for (uint32_t s = (E + kSpan - 1) / kSpan; s * kSpan < rsize; s++) span[s] = (uint16_t)nseq;     // trailing literals
-            b.rsize = rsize;
-            b.rep_out[0] = rep0; b.rep_out[1] = rep1; b.rep_out[2] = rep2;
-        }
-    }
+    if (!st && (nseq & 1)) out[nseq - 1] = held;
     return st;
 }
 

@@ -103,24 +103,23 @@ __global__ void __launch_bounds__(kLitThreads) k_literals(Block* blocks, const u
     if (active && lit_decode_sub(*b, sub, table, huf ? s_log[grp] : 0, huf ? s_used[grp] : 0)) b->status = FZG_E_CORRUPT;
 }
 
-// ------------------------------------------------------------------ sequences
-// One thread per block (the FSE state chain is serial), one CTA per SM.  What bounds this stage is
-// shared memory: a stream needs its three decode tables (LL 512 + OF 256 + ML 512 cells of 4 bytes)
-// plus 256 bytes of table-build scratch, so 43 streams fit in the 227 KB of an SM.  Each warp draws
-// its next batch of blocks from a global ticket.
-constexpr int kSeqStreams = 43;
+// ------------------------------------------------------------------ sequences, stage A: the FSE chain
+// One thread per block (the FSE state chain is serial), one CTA per SM.  What bounds this stage is the
+// latency of that chain times the number of chains an SM can hold, and the latter is set by shared
+// memory: a stream needs 3840 bytes (16-bit chain cells + symbol bytes + bitstream ring), so 60 streams
+// fit in the 227 KB of an SM.  A warp carries only a few streams (data-dependent branches cost little
+// that way, and the SM has issue slots to spare); each warp draws its next batch of blocks from a ticket.
+constexpr int kSeqStreams = 60;
 #ifndef FZ_SEQ_LANES
 #define FZ_SEQ_LANES 8
 #endif
-constexpr int kSeqLanes = FZ_SEQ_LANES;                      // streams per warp: few, so that data-dependent branches cost little
+constexpr int kSeqLanes = FZ_SEQ_LANES;
 constexpr int kSeqWarps = (kSeqStreams + kSeqLanes - 1) / kSeqLanes;
 constexpr int kSeqThreads = kSeqWarps * 32;
-constexpr int kSeqTableCells = 512 + 256 + 512;
-constexpr int kSeqStreamBytes = kSeqTableCells * 4 + 256;
-constexpr int kSeqSmem = kSeqStreams * kSeqStreamBytes;
+constexpr int kSeqSmem = kSeqStreams * kChainBytes;
 
-__global__ void __launch_bounds__(kSeqThreads, 1) k_sequences(Block* blocks, const Frame* frames, const uint32_t* jobs,
-                                                                uint32_t n_jobs, uint64_t* seqs, uint16_t* spans, uint32_t* ticket)
+__global__ void __launch_bounds__(kSeqThreads, 1) k_sequences(Block* blocks, const uint32_t* jobs, uint32_t n_jobs, uint64_t* seqs,
+                                                                uint32_t* ticket)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ SeqConsts K;
@@ -128,7 +127,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) k_sequences(Block* blocks, con
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t first = warp * kSeqLanes, lanes = min((uint32_t)kSeqLanes, kSeqStreams - first);
-    uint8_t* mine = smem + (first + (lane < lanes ? lane : 0)) * kSeqStreamBytes;
+    uint8_t* mine = smem + (first + (lane < lanes ? lane : 0)) * kChainBytes;
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(ticket, lanes);
@@ -139,9 +138,83 @@ __global__ void __launch_bounds__(kSeqThreads, 1) k_sequences(Block* blocks, con
         Block* b = on ? &blocks[jobs[job]] : nullptr;
         const uint32_t mask = __ballot_sync(0xFFFFFFFFu, on);
         const uint32_t bound = __reduce_max_sync(0xFFFFFFFFu, on ? b->nseq : 0u);
-        if (on) seq_thread(blocks, frames, *b, K, (uint32_t*)mine, (uint16_t*)(mine + kSeqTableCells * 4), seqs, spans, bound, mask);
+        if (on) seq_chain_thread(blocks, *b, K, mine, seqs, bound, mask);
         __syncwarp();
     }
+}
+
+// ------------------------------------------------------------------ sequences, stage B: records
+// One warp per block, 32 sequences per step, in place over the RAW records of stage A: extra bits ->
+// (literal length, match length, offset value); warp scans -> cumulative positions E / LE; repeat
+// offsets; the positional record (rec_pack) and the span index.  Repeat offsets are the only serial
+// part: a step without repeat codes takes its history from the last three lanes, otherwise the history
+// hops from one repeat code to the next (a few per step), never lane by lane.
+__device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v, uint32_t lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= (uint32_t)d) v += t; }
+    return v;
+}
+
+constexpr int kRecWarps = 8;
+__global__ void __launch_bounds__(kRecWarps * 32) k_records(Block* blocks, const Frame* frames, const uint32_t* jobs, uint32_t n_jobs,
+                                                            uint64_t* seqs, uint16_t* spans)
+{
+    __shared__ SeqConsts K;
+    for (uint32_t i = threadIdx.x; i < sizeof(SeqConsts) / 4; i += blockDim.x) ((uint32_t*)&K)[i] = ((const uint32_t*)&c_seq_consts)[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t job = blockIdx.x * kRecWarps + (threadIdx.x >> 5);
+    if (job >= n_jobs) return;
+    Block& b = blocks[jobs[job]];
+    if (b.status) return;
+    const uint32_t nseq = b.nseq, lit_regen = b.lit_regen, block_max = frames[b.frame].block_max;
+    uint64_t* sq = seqs + b.seq_base; uint16_t* span = spans + b.span_base;
+    uint32_t rep0 = off_sym(0), rep1 = off_sym(1), rep2 = off_sym(2);      // history, warp-uniform
+    uint32_t Ebase = 0, LEbase = 0; bool bad = false;
+    for (uint32_t g = 0; g < nseq && !bad; g += 32) {
+        const uint32_t i = g + lane; const bool valid = i < nseq;
+        const uint32_t nv = min(32u, nseq - g);
+        uint32_t ll = 0, ml = 0, ofv = 4; bool ok = true;
+        if (valid) ok = raw_unpack(sq[i], K, ll, ml, ofv);
+        const uint32_t LE = LEbase + warp_scan_incl(ll, lane), E = Ebase + warp_scan_incl(ll + ml, lane);
+        // ---- repeat offsets
+        uint32_t off = ofv - 3;
+        uint32_t reps = __ballot_sync(0xFFFFFFFFu, valid && ofv <= 3);
+        uint32_t pos = 0;                                                  // history is valid as of lane `pos`
+        auto advance = [&](uint32_t upto) {                                // lanes [pos, upto) are plain offsets: push the last three
+            const uint32_t cnt = upto - pos;
+            const uint32_t o1 = __shfl_sync(0xFFFFFFFFu, off, (upto - 1) & 31), o2 = __shfl_sync(0xFFFFFFFFu, off, (upto - 2) & 31),
+                           o3 = __shfl_sync(0xFFFFFFFFu, off, (upto - 3) & 31);
+            const uint32_t n0 = cnt >= 1 ? o1 : rep0, n1 = cnt >= 2 ? o2 : (cnt == 1 ? rep0 : rep1),
+                           n2 = cnt >= 3 ? o3 : (cnt == 2 ? rep0 : (cnt == 1 ? rep1 : rep2));
+            rep0 = n0; rep1 = n1; rep2 = n2; pos = upto;
+        };
+        while (reps) {
+            const uint32_t r = __ffs(reps) - 1; reps &= reps - 1;
+            advance(r);
+            const uint32_t ofr = __shfl_sync(0xFFFFFFFFu, ofv, r); const bool ll0 = __shfl_sync(0xFFFFFFFFu, ll, r) == 0;
+            const uint32_t o = rep_update(ofr, ll0, rep0, rep1, rep2);
+            if (lane == r) off = o;
+            pos = r + 1;
+        }
+        advance(nv);
+        ok = ok && !(ofv > 3 && off > kOffMax) && LE <= lit_regen && E <= block_max;
+        bad = __any_sync(0xFFFFFFFFu, valid && !ok);
+        if (bad) break;
+        if (valid) {
+            sq[i] = rec_pack(E, LE, off);
+            const uint32_t Ep = E - ll - ml;
+            const uint32_t s1 = (E - 1) / kSpan;                           // span boundaries kSpan * s inside [Ep, E): almost always 0 or 1
+            if (s1 * kSpan >= Ep) span[s1] = (uint16_t)i;
+            if (E - Ep > kSpan) for (uint32_t sI = (Ep + kSpan - 1) / kSpan; sI < s1; sI++) span[sI] = (uint16_t)i;
+        }
+        Ebase = __shfl_sync(0xFFFFFFFFu, E, 31); LEbase = __shfl_sync(0xFFFFFFFFu, LE, 31);
+    }
+    const uint32_t rsize = Ebase + (lit_regen - LEbase);
+    if (bad || rsize > block_max) { if (lane == 0) b.status = FZG_E_CORRUPT; return; }
+    for (uint32_t sI = (Ebase + kSpan - 1) / kSpan + lane; sI * kSpan < rsize; sI += 32) span[sI] = (uint16_t)nseq;     // trailing literals
+    if (lane == 0) { b.rsize = rsize; b.rep_out[0] = rep0; b.rep_out[1] = rep1; b.rep_out[2] = rep2; }
 }
 
 // ------------------------------------------------------------------ offsets
@@ -417,9 +490,9 @@ __global__ void k_finish(const ItemInfo* infos, const ItemBase* bases, const Fra
 // ====================================================================== host side
 using namespace fz;
 
-static const char* kStageNames[] = { "count", "scan", "fill", "literals", "sequences", "offsets", "execute", "checksum",
+static const char* kStageNames[] = { "count", "scan", "fill", "literals", "sequences", "records", "offsets", "execute", "checksum",
                                      "finish" };
-const char* fzh_decode_stage_name(int s) { return s >= 0 && s < 9 ? kStageNames[s] : ""; }
+const char* fzh_decode_stage_name(int s) { return s >= 0 && s < 10 ? kStageNames[s] : ""; }
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "fzgpu: %s failed: %s (%s:%d)\n", #x, cudaGetErrorString(e_), __FILE__, __LINE__); return -5 /*-EIO*/; } } while (0)
 
@@ -484,8 +557,10 @@ int fzh_decode_run(FzCtx* c, uint32_t first, uint32_t n, int flags)
     mark();
     if (n_sj) {
         const uint32_t grid = (uint32_t)std::min<uint64_t>((n_sj + kSeqStreams - 1) / kSeqStreams, (uint64_t)g_sm_count);
-        k_sequences<<<grid, kSeqThreads, kSeqSmem, s>>>(d_blocks, d_frames, d_sj, (uint32_t)n_sj, d_seq, d_spans, d_tickets); launches++;
+        k_sequences<<<grid, kSeqThreads, kSeqSmem, s>>>(d_blocks, d_sj, (uint32_t)n_sj, d_seq, d_tickets); launches++;
     }
+    mark();
+    if (n_sj) { k_records<<<(uint32_t)((n_sj + kRecWarps - 1) / kRecWarps), kRecWarps * 32, 0, s>>>(d_blocks, d_frames, d_sj, (uint32_t)n_sj, d_seq, d_spans); launches++; }
     mark();
     k_offsets<<<gi, tb, 0, s>>>(d_items, d_infos, d_bases, d_frames, d_blocks, d_outs, n); mark(); launches++;
     if (n_frames) {
@@ -496,12 +571,12 @@ int fzh_decode_run(FzCtx* c, uint32_t first, uint32_t n, int flags)
     if (n_frames && !(flags & FZG_NO_VERIFY_CHECKSUM)) { k_checksum<<<(uint32_t)((n_frames * 4 + 127) / 128), 128, 0, s>>>(d_frames, d_items, d_outs, (uint32_t)n_frames); launches++; }
     mark();
     k_finish<<<gi, tb, 0, s>>>(d_infos, d_bases, d_frames, d_outs, h_outs, n); launches++;
-    if (!prof) ev = 9;
+    if (!prof) ev = 10;
     cudaEventRecord(c->ev[ev], s);                                   // last event
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     c->timing.launches = launches;
     cudaEventElapsedTime(&c->timing.total_ms, c->ev[0], c->ev[ev]);
-    if (prof) for (int k = 0; k < 9; k++) cudaEventElapsedTime(&c->timing.kernel_ms[k], c->ev[k], c->ev[k + 1]);
+    if (prof) for (int k = 0; k < 10; k++) cudaEventElapsedTime(&c->timing.kernel_ms[k], c->ev[k], c->ev[k + 1]);
     return 0;
 }

@@ -53,14 +53,11 @@ FZ_HD int lit_decode_sub(const Block& b, uint32_t sub, const uint16_t* table, in
     return huf_decode_stream(table, log, p + 6 + start, len, out + sub * seg, cnt_out) != 0;
 }
 
-// ------------------------------------------------------------------ sequences pass (one thread per block)
-// tables = 1280 cells (LL 512 | OF 256 | ML 512), scratch = 128 uint16, both in shared memory.
-// bound / mask: see decode_sequences (warp-uniform trip count and the lanes that take part).
-FZ_HD void seq_thread(Block* blocks, const Frame* frames, Block& b, const SeqConsts& K, uint32_t* tables, uint16_t* scratch,
-                      uint64_t* seqs, uint16_t* spans, uint32_t bound, uint32_t mask)
+// ------------------------------------------------------------------ sequences pass, stage A (one thread per block)
+// mem = kChainBytes of shared memory for this stream; bound / mask: see decode_sequences_chain.
+FZ_HD void seq_chain_thread(Block* blocks, Block& b, const SeqConsts& K, uint8_t* mem, uint64_t* seqs, uint32_t bound, uint32_t mask)
 {
-    const int st = decode_sequences(blocks, b, frames[b.frame].block_max, K, tables, tables + 512, tables + 768, scratch,
-                                    seqs + b.seq_base, spans + b.span_base, bound, mask);
+    const int st = decode_sequences_chain(blocks, b, K, mem, seqs + b.seq_base, bound, mask);
     if (st && !b.status) b.status = st;
 }
 

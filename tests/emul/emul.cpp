@@ -17,6 +17,29 @@ using namespace fz;
 
 static const SeqConsts kConsts = { FZ_LL_BASE, FZ_ML_BASE, FZ_LL_BITS, FZ_ML_BITS, FZ_LL_DEF, FZ_OF_DEF, FZ_ML_DEF };
 
+// TEST-ONLY serial restatement of stage B (k_records in fz_decode.cu is warp-parallel CUDA): RAW records ->
+// positional records + span index + block totals, through the same helpers (raw_unpack, rep_update, rec_pack).
+static void records_serial(Block& b, uint32_t block_max, uint64_t* seqs, uint16_t* spans)
+{
+    if (b.status) return;
+    uint64_t* sq = seqs + b.seq_base; uint16_t* span = spans + b.span_base;
+    uint32_t rep0 = off_sym(0), rep1 = off_sym(1), rep2 = off_sym(2), E = 0, LE = 0;
+    for (uint32_t i = 0; i < b.nseq; i++) {
+        uint32_t ll, ml, ofv;
+        bool ok = raw_unpack(sq[i], kConsts, ll, ml, ofv);
+        const uint32_t off = rep_update(ofv, ll == 0, rep0, rep1, rep2);
+        const uint32_t Ep = E;
+        LE += ll; E += ll + ml;
+        if (!ok || (ofv > 3 && off > kOffMax) || LE > b.lit_regen || E > block_max) { b.status = FZG_E_CORRUPT; return; }
+        sq[i] = rec_pack(E, LE, off);
+        for (uint32_t s = (Ep + kSpan - 1) / kSpan; s * kSpan < E; s++) span[s] = (uint16_t)i;
+    }
+    const uint32_t rsize = E + (b.lit_regen - LE);
+    if (rsize > block_max) { b.status = FZG_E_CORRUPT; return; }
+    for (uint32_t s = (E + kSpan - 1) / kSpan; s * kSpan < rsize; s++) span[s] = (uint16_t)b.nseq;
+    b.rsize = rsize; b.rep_out[0] = rep0; b.rep_out[1] = rep1; b.rep_out[2] = rep2;
+}
+
 // TEST-ONLY serial executor over the records the sequence pass emits (the product's execute pass is the
 // warp-cooperative CUDA kernel k_execute; this checks the record / span / repeat-offset logic on the CPU).
 static void exec_frame_serial(Frame& fr, const Block* blocks, const Item& it, const uint64_t* seqs, const uint16_t* spans)
@@ -89,10 +112,12 @@ extern "C" int fze_decode_batch(size_t n, const void* const* src, const size_t* 
             if (lit_decode_sub(b, sub, table.data(), log, used)) b.status = FZG_E_CORRUPT;
     }
     // sequences
-    std::vector<uint32_t> tables(512 + 256 + 512);
-    alignas(16) uint16_t scratch[128];
-    for (uint32_t j = 0; j < run.seq_job; j++)
-        seq_thread(blocks.data(), frames.data(), blocks[seq_jobs[j]], kConsts, tables.data(), scratch, seqs.data(), spans.data(), blocks[seq_jobs[j]].nseq, 1);
+    alignas(16) static uint8_t chain_mem[kChainBytes];
+    for (uint32_t j = 0; j < run.seq_job; j++) {
+        Block& b = blocks[seq_jobs[j]];
+        seq_chain_thread(blocks.data(), b, kConsts, chain_mem, seqs.data(), b.nseq, 1);
+        records_serial(b, frames[b.frame].block_max, seqs.data(), spans.data());
+    }
     // offsets
     std::vector<ItemOut> outs(n);
     for (size_t i = 0; i < n; i++) offsets_item(items[i], infos[i], bases[i], frames.data(), blocks.data(), outs[i]);
@@ -139,8 +164,12 @@ extern "C" int fze_trace(const void* src, size_t src_len, uint64_t* seq_out, siz
         if (b.lit_type >= LT_HUF) lit_build(blocks.data(), b, table.data(), log, used);
         for (uint32_t sub = 0; sub < 4; sub++) if (lit_decode_sub(b, sub, table.data(), log, used)) return FZG_E_CORRUPT;
     }
-    std::vector<uint32_t> tables(1280); alignas(16) uint16_t scratch[128];
-    for (uint32_t j = 0; j < info.n_seq_jobs; j++) seq_thread(blocks.data(), frames.data(), blocks[sj[j]], kConsts, tables.data(), scratch, seqs.data(), spans.data(), blocks[sj[j]].nseq, 1);
+    alignas(16) static uint8_t chain_mem[kChainBytes];
+    for (uint32_t j = 0; j < info.n_seq_jobs; j++) {
+        Block& b = blocks[sj[j]];
+        seq_chain_thread(blocks.data(), b, kConsts, chain_mem, seqs.data(), b.nseq, 1);
+        records_serial(b, frames[b.frame].block_max, seqs.data(), spans.data());
+    }
     it.dst_cap = ~0ull;
     ItemOut io; offsets_item(it, info, base, frames.data(), blocks.data(), io);      // resolves every block's starting history
     size_t ns = 0, nl = 0;
