@@ -22,6 +22,12 @@
 
 #include "../../include/fzgpu.h"
 
+#ifdef __CUDA_ARCH__
+#define FZ_SYNCWARP(mask) __syncwarp(mask)
+#else
+#define FZ_SYNCWARP(mask) ((void)(mask))
+#endif
+
 namespace fz {
 
 constexpr uint32_t kMagic = 0xFD2FB528u;
@@ -527,10 +533,8 @@ FZ_HD int huf_read_weights(const uint8_t* p, uint32_t n, uint8_t* w, int& n_w, H
 
 // Canonical table fill: cells are (symbol | nbBits << 8), 1 << log of them.  Weight 1 (longest
 // codes) first, ascending symbol inside a weight.
-FZ_HD void huf_fill_table(uint16_t* table, const uint8_t* w, int n_w, int log)
+FZ_HD void huf_fill_table(uint16_t* table, const uint8_t* w, int n_w, int log, uint32_t* start /*[kHufLogMax + 2]*/, uint32_t* rank /*[kHufLogMax + 2]*/)
 {
-    uint32_t start[kHufLogMax + 2];
-    uint32_t rank[kHufLogMax + 2];
     for (int k = 0; k <= kHufLogMax + 1; k++) rank[k] = 0;
     for (int s = 0; s < n_w; s++) rank[w[s]]++;
     uint32_t cur = 0;
@@ -542,28 +546,6 @@ FZ_HD void huf_fill_table(uint16_t* table, const uint8_t* w, int n_w, int log)
         for (uint32_t i = 0; i < len; i++) table[at + i] = cell;
         start[wt] = at + len;
     }
-}
-
-// One Huffman stream: regenerates n_out bytes at `out`.  Returns 0 or -1.
-FZ_HD int huf_decode_stream(const uint16_t* table, int log, const uint8_t* p, uint32_t n, uint8_t* out, uint32_t n_out)
-{
-    BackBits br;
-    if (br.init(p, n) != 0) return -1;
-    br.refill();
-    uint32_t i = 0;
-    const uint32_t ulog = (uint32_t)log;
-    for (; i + 2 <= n_out; i += 2) {               // two symbols (<= 24 bits) per refill check
-        if (br.avail <= 32) br.refill();
-        uint32_t c0 = table[br.peek(ulog)]; br.skip(c0 >> 8);
-        uint32_t c1 = table[br.peek(ulog)]; br.skip(c1 >> 8);
-        out[i] = (uint8_t)c0; out[i + 1] = (uint8_t)c1;
-    }
-    if (i < n_out) {
-        if (br.avail <= 32) br.refill();
-        uint32_t c0 = table[br.peek(ulog)]; br.skip(c0 >> 8);
-        out[i] = (uint8_t)c0;
-    }
-    return br.left == 0 ? 0 : -1;
 }
 
 // ------------------------------------------------------------------ sequence tables
@@ -728,6 +710,42 @@ struct SeqBits {
     FZ_HD uint32_t read(uint32_t nb) { const uint32_t v = peek(nb); skip(nb); return v; }
 };
 
+// One Huffman stream (RFC 8878 4.2.2): regenerates n_out bytes at `out` from the n bytes at p, through the
+// ring-fed reader.  Lanes of a warp decode different streams in lockstep: `bound` is the warp-uniform number
+// of 4-symbol iterations (>= n_out / 4 of every lane in `mask`), `ok` false masks the lane out.  Symbols are
+// stored four at a time once the output is 4-byte aligned.  Returns 0 or -1.
+FZ_HD int huf_decode_stream(const uint16_t* table, int log, const uint8_t* p, uint32_t n, uint8_t* out, uint32_t n_out,
+                            uint8_t* ring, uint32_t bound, uint32_t mask, bool ok)
+{
+    SeqBits br;
+    if (ok && br.init(p, n, ring) != 0) ok = false;
+    const uint32_t ulog = (uint32_t)log;
+    uint32_t i = 0;
+    if (ok) {
+        uint32_t head = (uint32_t)((4 - ((uintptr_t)out & 3)) & 3);                        // <= 3 symbols up to alignment
+        if (head > n_out) head = n_out;
+        for (; i < head; i++) { br.refill(); const uint32_t c = table[br.peek(ulog)]; br.skip(c >> 8); out[i] = (uint8_t)c; }
+    }
+    const uint32_t quads = ok ? (n_out - i) / 4 : 0;
+    FZ_SYNCWARP(mask);
+    for (uint32_t q = 0; q < bound; q++) {
+        if (q < quads) {
+            br.top_up(); ring_wait<8>();
+            br.refill();
+            const uint32_t c0 = table[br.peek(ulog)]; br.skip(c0 >> 8);
+            const uint32_t c1 = table[br.peek(ulog)]; br.skip(c1 >> 8);
+            br.refill();
+            const uint32_t c2 = table[br.peek(ulog)]; br.skip(c2 >> 8);
+            const uint32_t c3 = table[br.peek(ulog)]; br.skip(c3 >> 8);
+            *(uint32_t*)(out + i) = (c0 & 255u) | ((c1 & 255u) << 8) | ((c2 & 255u) << 16) | (c3 << 24);
+            i += 4;
+        }
+    }
+    if (!ok) return -1;
+    for (; i < n_out; i++) { br.top_up(); ring_wait<0>(); br.refill(); const uint32_t c = table[br.peek(ulog)]; br.skip(c >> 8); out[i] = (uint8_t)c; }
+    return br.left == 0 ? 0 : -1;
+}
+
 FZ_HD void store_rec_pair(uint64_t* at, uint64_t a, uint64_t b)   // `at` is 16-byte aligned
 {
 #ifdef __CUDA_ARCH__
@@ -859,12 +877,6 @@ FZ_HD uint32_t rep_update(uint32_t ofv, bool ll0, uint32_t& rep0, uint32_t& rep1
     }
     return off;
 }
-
-#ifdef __CUDA_ARCH__
-#define FZ_SYNCWARP(mask) __syncwarp(mask)
-#else
-#define FZ_SYNCWARP(mask) ((void)(mask))
-#endif
 
 // Stage A.  `mem` = this stream's kChainBytes of shared memory.  Writes nseq RAW records at `out`.
 // SIMT shape: the lanes of a warp run different blocks, so the loop must stay in lockstep or the warp

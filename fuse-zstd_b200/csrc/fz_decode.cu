@@ -81,26 +81,43 @@ __global__ void k_fill(const Item* items, ItemInfo* infos, const ItemBase* bases
 }
 
 // ------------------------------------------------------------------ literals
-// Four threads per block: thread 0 of the group parses the tree description and fills the
-// group's table in shared memory, then each thread decodes one of the (up to) four streams.
-constexpr int kLitGroups = 16;                  // blocks per CTA
+// Four threads per block: thread 0 of the group parses the tree description (direct or FSE-compressed
+// weights, or the tree of an earlier block for Treeless literals) and fills the group's table in shared
+// memory, then each thread decodes one of the (up to) four Huffman streams, pulling its bitstream
+// through a cp.async ring.  24 groups (9 KB each) per CTA, one CTA per SM, blocks drawn from a ticket.
+constexpr int kLitGroups = 24;                  // blocks in flight per CTA
 constexpr int kLitThreads = kLitGroups * 4;
-constexpr int kHufTableCells = 1 << kHufLogMax; // 8 KB per group
+constexpr int kLitSmem = kLitGroups * kLitGroupBytes;
 
-__global__ void __launch_bounds__(kLitThreads) k_literals(Block* blocks, const uint32_t* jobs, uint32_t n_jobs)
+__global__ void __launch_bounds__(kLitThreads, 1) k_literals(Block* blocks, const uint32_t* jobs, uint32_t n_jobs, uint32_t* ticket)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint16_t* table = (uint16_t*)smem + (threadIdx.x >> 2) * kHufTableCells;
     __shared__ int s_log[kLitGroups];
     __shared__ uint32_t s_used[kLitGroups];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t grp = threadIdx.x >> 2, sub = threadIdx.x & 3;
-    const uint32_t job = blockIdx.x * kLitGroups + grp;
-    const bool active = job < n_jobs;
-    Block* b = active ? &blocks[jobs[job]] : nullptr;
-    const bool huf = active && b->lit_type >= LT_HUF;
-    if (huf && sub == 0) { int log; uint32_t used; lit_build(blocks, *b, table, log, used); s_log[grp] = log; s_used[grp] = used; }
-    __syncwarp();
-    if (active && lit_decode_sub(*b, sub, table, huf ? s_log[grp] : 0, huf ? s_used[grp] : 0)) b->status = FZG_E_CORRUPT;
+    uint8_t* gmem = smem + grp * kLitGroupBytes;
+    uint16_t* table = (uint16_t*)gmem;
+    uint8_t* rings = gmem + (1u << kHufLogMax) * 2;
+    (void)warp;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(ticket, 8);            // eight blocks per warp and round
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n_jobs) return;
+        const uint32_t job = base + (lane >> 2);
+        const bool active = job < n_jobs;
+        Block* b = active ? &blocks[jobs[job]] : nullptr;
+        const bool huf = active && b->lit_type >= LT_HUF;
+        if (huf && sub == 0) { int log; uint32_t used; lit_build(blocks, *b, table, *(LitScratch*)rings, log, used); s_log[grp] = log; s_used[grp] = used; }
+        __syncwarp();
+        LitWork wk{ nullptr, nullptr, 0, 0, 0 };
+        if (active) wk = lit_plan(*b, sub, huf ? s_log[grp] : 0, huf ? s_used[grp] : 0);
+        const uint32_t bound = __reduce_max_sync(0xFFFFFFFFu, wk.kind == 2 ? wk.n_out / 4 : 0u);
+        const int bad = lit_run(wk, sub, table, huf ? s_log[grp] : 0, rings + sub * 256, bound, 0xFFFFFFFFu);
+        if (active && bad) b->status = FZG_E_CORRUPT;
+        __syncwarp();
+    }
 }
 
 // ------------------------------------------------------------------ sequences, stage A: the FSE chain
@@ -500,7 +517,7 @@ static int g_sm_count = 148;
 
 int fzh_decode_setup(void)
 {
-    CK(cudaFuncSetAttribute(k_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, kLitGroups * kHufTableCells * 2));
+    CK(cudaFuncSetAttribute(k_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, kLitSmem));
     CK(cudaFuncSetAttribute(k_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqSmem));
     int dev = 0; CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
@@ -553,7 +570,7 @@ int fzh_decode_run(FzCtx* c, uint32_t first, uint32_t n, int flags)
 
     k_fill<<<gi, tb, 0, s>>>(d_items, d_infos, d_bases, d_frames, d_blocks, d_sj, d_hj, (uint8_t*)c->d_lit.p, n); mark();
     int launches = 3;
-    if (n_hj) { k_literals<<<(uint32_t)((n_hj + kLitGroups - 1) / kLitGroups), kLitThreads, kLitGroups * kHufTableCells * 2, s>>>(d_blocks, d_hj, (uint32_t)n_hj); launches++; }
+    if (n_hj) { k_literals<<<(uint32_t)std::min<uint64_t>((n_hj + kLitGroups - 1) / kLitGroups, (uint64_t)g_sm_count), kLitThreads, kLitSmem, s>>>(d_blocks, d_hj, (uint32_t)n_hj, d_tickets + 2); launches++; }
     mark();
     if (n_sj) {
         const uint32_t grid = (uint32_t)std::min<uint64_t>((n_sj + kSeqStreams - 1) / kSeqStreams, (uint64_t)g_sm_count);

@@ -15,42 +15,53 @@ static __constant__ SeqConsts c_seq_consts = { FZ_LL_BASE, FZ_ML_BASE, FZ_LL_BIT
 #endif
 
 // ------------------------------------------------------------------ literals pass (four threads per block)
+// Per block (group of four threads) in shared memory: the decode table (8 KB) and 1 KB that serves first as
+// table-build scratch and then as the four bitstream rings.
+constexpr uint32_t kLitGroupBytes = (1u << kHufLogMax) * 2 + 1024;
+struct LitScratch {          // overlays the 1 KB ring area while the table is being built
+    uint8_t w[256]; uint32_t ft[64]; uint16_t cnt[64]; uint32_t start[kHufLogMax + 2], rank[kHufLogMax + 2];
+};
+
 // thread 0 of the group: tree description (possibly from an earlier block: Treeless) -> table.
 // log < 0 reports a malformed description.
-FZ_HD void lit_build(const Block* blocks, const Block& b, uint16_t* table, int& log, uint32_t& used)
+FZ_HD void lit_build(const Block* blocks, const Block& b, uint16_t* table, LitScratch& sc, int& log, uint32_t& used)
 {
     const Block& sb = blocks[b.huf_src];
-    uint8_t w[256]; uint32_t ft[64]; uint16_t cnt[64];
     int nw; HufInfo hi; hi.log = 0; hi.used = 0;
-    if (huf_read_weights(sb.src + sb.lit_hdr, sb.lit_csize, w, nw, hi, ft, cnt) != 0) { log = -1; used = 0; return; }
-    huf_fill_table(table, w, nw, hi.log);
+    if (huf_read_weights(sb.src + sb.lit_hdr, sb.lit_csize, sc.w, nw, hi, sc.ft, sc.cnt) != 0) { log = -1; used = 0; return; }
+    huf_fill_table(table, sc.w, nw, hi.log, sc.start, sc.rank);
     log = hi.log; used = hi.used;
 }
 
-// thread `sub` (0..3) of the group: RLE fill or one Huffman stream.  Returns 0 or 1 (corrupt).
-FZ_HD int lit_decode_sub(const Block& b, uint32_t sub, const uint16_t* table, int log, uint32_t used)
+// What thread `sub` (0..3) of the group has to do for block b: nothing, an RLE fill, or one Huffman stream.
+struct LitWork { const uint8_t* p; uint8_t* out; uint32_t n, n_out; int kind; };   // kind: 0 none, 1 rle, 2 huffman stream, -1 corrupt
+FZ_HD LitWork lit_plan(const Block& b, uint32_t sub, int log, uint32_t used)
 {
-    uint8_t* out = const_cast<uint8_t*>(b.lit);
-    if (b.lit_type == LT_RLE) {
-        const uint8_t v = b.src[b.lit_hdr];
-        for (uint32_t i = sub; i < b.lit_regen; i += 4) out[i] = v;
-        return 0;
-    }
-    if (log < 0) return 1;
+    LitWork wk{ nullptr, const_cast<uint8_t*>(b.lit), 0, 0, 0 };
+    if (b.lit_type == LT_RLE) { wk.kind = 1; wk.p = b.src + b.lit_hdr; wk.n_out = b.lit_regen; return wk; }
+    if (log < 0) { wk.kind = -1; return wk; }
     const uint32_t skip = b.lit_type == LT_HUF ? used : 0;
-    if (skip > b.lit_csize) return 1;
+    if (skip > b.lit_csize) { wk.kind = -1; return wk; }
     const uint8_t* p = b.src + b.lit_hdr + skip;
     const uint32_t n = b.lit_csize - skip, regen = b.lit_regen;
-    if (b.lit_streams == 1) return sub == 0 ? (huf_decode_stream(table, log, p, n, out, regen) != 0) : 0;
-    if (n < 10) return 1;
+    if (b.lit_streams == 1) { if (sub == 0) { wk.kind = 2; wk.p = p; wk.n = n; wk.n_out = regen; } return wk; }
+    if (n < 10) { wk.kind = -1; return wk; }
     const uint32_t l1 = p[0] | ((uint32_t)p[1] << 8), l2 = p[2] | ((uint32_t)p[3] << 8), l3 = p[4] | ((uint32_t)p[5] << 8);
     const uint32_t seg = (regen + 3) / 4;
-    if (6 + l1 + l2 + l3 > n || seg * 3 > regen) return 1;
+    if (6 + l1 + l2 + l3 > n || seg * 3 > regen) { wk.kind = -1; return wk; }
     const uint32_t l4 = n - 6 - l1 - l2 - l3;
     const uint32_t start = sub == 0 ? 0 : (sub == 1 ? l1 : (sub == 2 ? l1 + l2 : l1 + l2 + l3));
-    const uint32_t len = sub == 0 ? l1 : (sub == 1 ? l2 : (sub == 2 ? l3 : l4));
-    const uint32_t cnt_out = sub == 3 ? regen - 3 * seg : seg;
-    return huf_decode_stream(table, log, p + 6 + start, len, out + sub * seg, cnt_out) != 0;
+    wk.kind = 2; wk.p = p + 6 + start; wk.n = sub == 0 ? l1 : (sub == 1 ? l2 : (sub == 2 ? l3 : l4));
+    wk.out += sub * seg; wk.n_out = sub == 3 ? regen - 3 * seg : seg;
+    return wk;
+}
+
+// Executes the plan; ring = this thread's 256 bytes; bound / mask as in huf_decode_stream.  Returns 0 or 1 (corrupt).
+FZ_HD int lit_run(const LitWork& wk, uint32_t sub, const uint16_t* table, int log, uint8_t* ring, uint32_t bound, uint32_t mask)
+{
+    if (wk.kind == 1) { const uint8_t v = wk.p[0]; for (uint32_t i = sub; i < wk.n_out; i += 4) wk.out[i] = v; }
+    const int r = huf_decode_stream(table, log, wk.p, wk.n, wk.out, wk.n_out, ring, bound, mask, wk.kind == 2);
+    return wk.kind == 2 ? (r != 0) : (wk.kind < 0);
 }
 
 // ------------------------------------------------------------------ sequences pass, stage A (one thread per block)

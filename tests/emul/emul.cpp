@@ -104,12 +104,15 @@ extern "C" int fze_decode_batch(size_t n, const void* const* src, const size_t* 
     }
     // literals: group of four threads per job
     std::vector<uint16_t> table(1 << kHufLogMax);
+    alignas(16) static uint8_t ring[256]; static LitScratch sc;
     for (uint32_t j = 0; j < run.huf_job; j++) {
         Block& b = blocks[huf_jobs[j]];
         int log = 0; uint32_t used = 0;
-        if (b.lit_type >= LT_HUF) lit_build(blocks.data(), b, table.data(), log, used);
-        for (uint32_t sub = 0; sub < 4; sub++)
-            if (lit_decode_sub(b, sub, table.data(), log, used)) b.status = FZG_E_CORRUPT;
+        if (b.lit_type >= LT_HUF) lit_build(blocks.data(), b, table.data(), sc, log, used);
+        for (uint32_t sub = 0; sub < 4; sub++) {
+            const LitWork wk = lit_plan(b, sub, log, used);
+            if (lit_run(wk, sub, table.data(), log, ring, wk.n_out / 4, 1)) b.status = FZG_E_CORRUPT;
+        }
     }
     // sequences
     alignas(16) static uint8_t chain_mem[kChainBytes];
@@ -159,10 +162,14 @@ extern "C" int fze_trace(const void* src, size_t src_len, uint64_t* seq_out, siz
     ItemInfo tmp;
     walk_item<true>(0, it, tmp, &base, frames.data(), blocks.data(), sj.data(), hj.data(), lit.data());
     std::vector<uint16_t> table(1 << kHufLogMax);
+    alignas(16) static uint8_t ring[256]; static LitScratch sc;
     for (uint32_t j = 0; j < info.n_huf_jobs; j++) {
         Block& b = blocks[hj[j]]; int log = 0; uint32_t used = 0;
-        if (b.lit_type >= LT_HUF) lit_build(blocks.data(), b, table.data(), log, used);
-        for (uint32_t sub = 0; sub < 4; sub++) if (lit_decode_sub(b, sub, table.data(), log, used)) return FZG_E_CORRUPT;
+        if (b.lit_type >= LT_HUF) lit_build(blocks.data(), b, table.data(), sc, log, used);
+        for (uint32_t sub = 0; sub < 4; sub++) {
+            const LitWork wk = lit_plan(b, sub, log, used);
+            if (lit_run(wk, sub, table.data(), log, ring, wk.n_out / 4, 1)) return FZG_E_CORRUPT;
+        }
     }
     alignas(16) static uint8_t chain_mem[kChainBytes];
     for (uint32_t j = 0; j < info.n_seq_jobs; j++) {
