@@ -12,6 +12,8 @@
 #include <time.h>
 #include <unistd.h>
 
+#include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "fz_core.cuh"
@@ -45,7 +47,14 @@ extern "C" int fzg_init(const int* devices, int n_devices)
         CKR(cudaSetDevice(d));
         FzCtx* c = new FzCtx();
         c->dev = d;
-        CKR(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        const char* nl = getenv("FZG_LANES");
+        c->n_lanes = nl ? std::max(1, std::min(kMaxLanes, atoi(nl))) : 1;   // measured: no gain from 2-4 lanes on B200 (profiles/r01_notes.md)
+        for (int l = 0; l < kMaxLanes; l++) {
+            CKR(cudaStreamCreateWithFlags(&c->lane[l].stream, cudaStreamNonBlocking));
+            for (auto& e : c->lane[l].ev) CKR(cudaEventCreate(&e));
+            CKR(cudaEventCreateWithFlags(&c->lane[l].ev_entropy, cudaEventDisableTiming));
+        }
+        c->stream = c->lane[0].stream;
         CKR(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         CKR(cudaStreamCreateWithFlags(&c->copy_stream2, cudaStreamNonBlocking));
         for (auto& e : c->ev) CKR(cudaEventCreate(&e));
@@ -62,14 +71,23 @@ extern "C" void fzg_shutdown(void)
     for (FzCtx* c : g_ctx) {
         cudaSetDevice(c->dev);
         cudaStreamSynchronize(c->stream);
-        FzDevBuf* db[] = { &c->d_items, &c->d_infos, &c->d_bases, &c->d_outs, &c->d_totals, &c->d_frames, &c->d_blocks,
-                           &c->d_seq_jobs, &c->d_huf_jobs, &c->d_lit, &c->d_seq, &c->d_spans, &c->d_stage_src, &c->d_stage_dst,
-                           &c->e_items, &c->e_outs, &c->e_work };
+        FzDevBuf* db[] = { &c->d_stage_src, &c->d_stage_dst, &c->e_items, &c->e_outs, &c->e_work, &c->d_outs, &c->d_totals };
         for (auto* b : db) b->release();
         FzPinBuf* pb[] = { &c->h_items, &c->h_outs, &c->h_totals, &c->h_stage_src, &c->h_stage_dst, &c->e_chunks_h, &c->e_first_h };
         for (auto* b : pb) b->release();
+        for (int l = 0; l < kMaxLanes; l++) {
+            FzLane& L = c->lane[l];
+            cudaStreamSynchronize(L.stream);
+            FzDevBuf* lb[] = { &L.d_infos, &L.d_bases, &L.d_outs, &L.d_totals, &L.d_frames, &L.d_blocks, &L.d_seq_jobs, &L.d_huf_jobs,
+                               &L.d_lit, &L.d_seq, &L.d_spans };
+            for (auto* b : lb) b->release();
+            L.h_totals.release();
+            for (auto& e : L.ev) cudaEventDestroy(e);
+            cudaEventDestroy(L.ev_entropy);
+            cudaStreamDestroy(L.stream);
+        }
         for (auto& e : c->ev) cudaEventDestroy(e);
-        cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copy_stream); cudaStreamDestroy(c->copy_stream2);
+        cudaStreamDestroy(c->copy_stream); cudaStreamDestroy(c->copy_stream2);
         delete c;
     }
     g_ctx.clear(); g_dev.clear();
@@ -171,16 +189,47 @@ static int run_batch(bool encode, int device, size_t n, const void* const* src, 
         for (size_t i = 0; i < n; i++) { items[i].dst = dbase + off; off += dst_contig ? dst_cap[i] : al16(dst_cap[i]) + 16; }
     } else for (size_t i = 0; i < n; i++) items[i].dst = (uint8_t*)dst[i];
 
-    auto run = [&](size_t first, size_t cnt) -> int {
-        int r = encode ? fzh_encode_run(c, (uint32_t)first, (uint32_t)cnt, level, chunk, flags) : fzh_decode_run(c, (uint32_t)first, (uint32_t)cnt, flags);
-        if (r) return r;
-        acc.total_ms += c->timing.total_ms; acc.launches += c->timing.launches;
-        for (int k = 0; k < 16; k++) acc.kernel_ms[k] += c->timing.kernel_ms[k];
+    auto add_timing = [&](const fzg_timing_t& t, bool concurrent) {
+        acc.total_ms = concurrent ? std::max(acc.total_ms, t.total_ms) : acc.total_ms + t.total_ms;
+        acc.launches += t.launches;
+        for (int k = 0; k < 16; k++) acc.kernel_ms[k] += t.kernel_ms[k];
+    };
+    // items [first, first + cnt): the encoder runs on the context's stream; the decoder splits the range over the
+    // context's lanes (by compressed bytes), one host thread per lane, so that different stages of different slices overlap
+    auto run = [&](size_t first, size_t cnt, cudaEvent_t after) -> int {     // `after`: the chunk's H2D copy (or null)
+        if (after) for (int l = 0; l < (encode ? 1 : kMaxLanes); l++) CKR(cudaStreamWaitEvent(c->lane[l].stream, after, 0));
+        if (encode) {
+            int r = fzh_encode_run(c, (uint32_t)first, (uint32_t)cnt, level, chunk, flags);
+            if (r) return r;
+            add_timing(c->timing, false);
+            return 0;
+        }
+        const int lanes = cnt >= 64 ? c->n_lanes : 1;
+        if (lanes == 1) {
+            int r = fzh_decode_run(c, 0, (uint32_t)first, (uint32_t)cnt, flags, false);
+            if (r) return r;
+            add_timing(c->lane[0].timing, false);
+            return 0;
+        }
+        uint64_t total = 0;
+        for (size_t i = first; i < first + cnt; i++) total += src_len[i] + 1;
+        size_t cut[kMaxLanes + 1]; cut[0] = first; cut[lanes] = first + cnt;
+        { uint64_t run_b = 0; int l = 1;
+          for (size_t i = first; i < first + cnt && l < lanes; i++) { run_b += src_len[i] + 1; if (run_b * lanes >= total * l) cut[l++] = i + 1; }
+          for (; l < lanes; l++) cut[l] = first + cnt; }
+        c->epoch++;
+        int rcs[kMaxLanes] = { 0, 0, 0, 0 };
+        std::vector<std::thread> th;
+        for (int l = 1; l < lanes; l++)
+            th.emplace_back([&, l]() { cudaSetDevice(c->dev); rcs[l] = fzh_decode_run(c, l, (uint32_t)cut[l], (uint32_t)(cut[l + 1] - cut[l]), flags, true); });
+        rcs[0] = fzh_decode_run(c, 0, (uint32_t)cut[0], (uint32_t)(cut[1] - cut[0]), flags, true);
+        for (auto& t : th) t.join();
+        for (int l = 0; l < lanes; l++) { if (rcs[l]) return rcs[l]; add_timing(c->lane[l].timing, l > 0); }
         return 0;
     };
 
     if (src_dev && dst_dev) {
-        if ((rc = run(0, n))) return rc;
+        if ((rc = run(0, n, nullptr))) return rc;
     } else {
         std::vector<size_t> cuts{ 0 };            // chunk boundaries
         for (size_t i = 0, bytes = 0; i < n; i++) {
@@ -206,9 +255,8 @@ static int run_batch(bool encode, int device, size_t n, const void* const* src, 
         for (size_t k = 0; k < nchunks; k++) {
             const size_t lo = cuts[k], hi = cuts[k + 1];
             if (k + 1 < nchunks && (rc = h2d(k + 1))) return rc;
-            if (!src_dev) CKR(cudaStreamWaitEvent(s, c->ev[12 + (k & 1)], 0));
             const double ta = now_ms();
-            if ((rc = run(lo, hi - lo))) return rc;                     // returns once chunk k is decoded
+            if ((rc = run(lo, hi - lo, src_dev ? nullptr : c->ev[12 + (k & 1)]))) return rc;   // returns once chunk k is decoded
             if (trace) fprintf(stderr, "fzgpu: chunk %zu/%zu items %zu: run %.2f -> %.2f ms (gpu %.2f ms)\n", k, nchunks, hi - lo, ta, now_ms(), c->timing.total_ms);
             if (!dst_dev) {
                 bool all_full = dst_contig;

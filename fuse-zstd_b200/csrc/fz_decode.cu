@@ -18,6 +18,7 @@
 #include <stdio.h>
 
 #include <algorithm>
+#include <thread>
 
 #include "fz_host.h"
 #include "fz_kernels.cuh"
@@ -85,7 +86,10 @@ __global__ void k_fill(const Item* items, ItemInfo* infos, const ItemBase* bases
 // weights, or the tree of an earlier block for Treeless literals) and fills the group's table in shared
 // memory, then each thread decodes one of the (up to) four Huffman streams, pulling its bitstream
 // through a cp.async ring.  24 groups (9 KB each) per CTA, one CTA per SM, blocks drawn from a ticket.
-constexpr int kLitGroups = 24;                  // blocks in flight per CTA
+#ifndef FZ_LIT_GROUPS
+#define FZ_LIT_GROUPS 24
+#endif
+constexpr int kLitGroups = FZ_LIT_GROUPS;       // blocks in flight per CTA
 constexpr int kLitThreads = kLitGroups * 4;
 constexpr int kLitSmem = kLitGroups * kLitGroupBytes;
 
@@ -126,7 +130,10 @@ __global__ void __launch_bounds__(kLitThreads, 1) k_literals(Block* blocks, cons
 // memory: a stream needs 3840 bytes (16-bit chain cells + symbol bytes + bitstream ring), so 60 streams
 // fit in the 227 KB of an SM.  A warp carries only a few streams (data-dependent branches cost little
 // that way, and the SM has issue slots to spare); each warp draws its next batch of blocks from a ticket.
-constexpr int kSeqStreams = 60;
+#ifndef FZ_SEQ_STREAMS
+#define FZ_SEQ_STREAMS 60
+#endif
+constexpr int kSeqStreams = FZ_SEQ_STREAMS;
 #ifndef FZ_SEQ_LANES
 #define FZ_SEQ_LANES 8
 #endif
@@ -274,7 +281,7 @@ __global__ void k_offsets(const Item* items, const ItemInfo* infos, const ItemBa
 #define FZ_EXEC_WARPS 4
 #endif
 #ifndef FZ_EXEC_CTAS
-#define FZ_EXEC_CTAS 8
+#define FZ_EXEC_CTAS 12
 #endif
 constexpr int kExecWarps = FZ_EXEC_WARPS;                    // warps per frame in flight
 constexpr int kExecCtasPerSm = FZ_EXEC_CTAS;
@@ -361,17 +368,18 @@ __device__ __forceinline__ void exec_block(const Block& b, const uint64_t* __res
         }
 
         uint32_t S = 0, LEp = 0, M = 0, E = 0, LE = 0, off = 1;
-        auto fetch = [&](uint32_t kk) {          // sequence kk becomes current; (S, LEp) must hold its predecessor's ends
+        uint64_t nxt = 0;                        // record k + 1, loaded one sequence ahead so that its L2 latency is off the piece loop
+        auto fetch = [&](uint32_t kk, uint64_t r) {   // sequence kk (record r) becomes current; (S, LEp) hold its predecessor's ends
             if (kk < nseq) {
-                const uint64_t r = __ldg(sq + kk);
                 E = rec_e(r); LE = rec_le(r); off = off_resolve(rec_off(r), in0, in1, in2);
                 M = S + (LE - LEp);
                 if ((uint64_t)off > done + M) { off = 0; atomicMax(s_status, FZG_E_CORRUPT); }   // before the frame start
             } else { E = rsize; LE = lit_regen; off = 1; M = E; }
+            nxt = kk + 1 < nseq ? __ldg(sq + kk + 1) : 0;
         };
         if (active) {
             if (k > 0) { const uint64_t r = __ldg(sq + (k - 1 < nseq ? k - 1 : nseq - 1)); S = rec_e(r); LEp = rec_le(r); }
-            fetch(k);
+            fetch(k, k < nseq ? __ldg(sq + k) : 0);
         }
 
         uint32_t pos = P, filled = 0, donemask = 0, waitc = 0;
@@ -382,7 +390,7 @@ __device__ __forceinline__ void exec_block(const Block& b, const uint64_t* __res
             // lockstep piece loop: one vote per step keeps the lanes converged
             while (__any_sync(kFull, go)) {
                 if (go) {
-                    if (pos >= E) { k++; S = E; LEp = LE; fetch(k); }
+                    if (pos >= E) { k++; S = E; LEp = LE; fetch(k, nxt); }
                     uint32_t nb; const uint8_t* src = nullptr; bool fromacc = false;
                     if (pos < M) {                                         // literal run
                         nb = min(M, Pend) - pos;
@@ -526,11 +534,17 @@ int fzh_decode_setup(void)
 
 // Runs the whole pipeline for items [first, first + n) of c->h_items (Item records holding device
 // pointers).  Results land in c->h_outs[first ..] (pinned).  Blocking on the context's stream.
-int fzh_decode_run(FzCtx* c, uint32_t first, uint32_t n, int flags)
+int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int flags, bool staggered)
 {
+    FzLane* c = &ctx->lane[lane_idx];
     cudaStream_t s = c->stream;
     const bool prof = flags & FZG_PROFILE;
     c->timing = fzg_timing_t{};
+    struct Signal {                              // the next lane waits for this one's entropy stages: never leave it hanging
+        FzCtx* ctx; FzLane* c; bool on;
+        void fire() { if (on) { cudaEventRecord(c->ev_entropy, c->stream); c->entropy_epoch.store(ctx->epoch, std::memory_order_release); on = false; } }
+        ~Signal() { fire(); }
+    } signal{ ctx, c, staggered };
     if (n == 0) return 0;
     int rc;
     if ((rc = c->d_infos.reserve(n * sizeof(ItemInfo)))) return rc;
@@ -540,12 +554,13 @@ int fzh_decode_run(FzCtx* c, uint32_t first, uint32_t n, int flags)
     // The per-call control data (item records in, totals and per-item results out) lives in pinned host memory that
     // the kernels access directly (UVA zero-copy).  A cudaMemcpyAsync would queue on the copy engines behind the
     // gigabyte-sized batch transfers of the neighbouring chunks (see run_batch) and stall the pipeline.
-    const Item* d_items = (const Item*)c->h_items.p + first;
+    const Item* d_items = (const Item*)ctx->h_items.p + first;
     ItemInfo* d_infos = (ItemInfo*)c->d_infos.p; ItemBase* d_bases = (ItemBase*)c->d_bases.p;
     ItemOut* d_outs = (ItemOut*)c->d_outs.p; uint64_t* d_totals = (uint64_t*)c->d_totals.p;
     uint32_t* d_tickets = (uint32_t*)(d_totals + 8);               // [0] sequences, [1] execute
+    if ((rc = c->h_totals.reserve(64))) return rc;
     uint64_t* h_totals = (uint64_t*)c->h_totals.p;
-    ItemOut* h_outs = (ItemOut*)c->h_outs.p + first;
+    ItemOut* h_outs = (ItemOut*)ctx->h_outs.p + first;
 
     int ev = 0;
     auto mark = [&]() { if (prof || ev == 0) cudaEventRecord(c->ev[ev], s); ev++; };
@@ -570,6 +585,14 @@ int fzh_decode_run(FzCtx* c, uint32_t first, uint32_t n, int flags)
 
     k_fill<<<gi, tb, 0, s>>>(d_items, d_infos, d_bases, d_frames, d_blocks, d_sj, d_hj, (uint8_t*)c->d_lit.p, n); mark();
     int launches = 3;
+    // Stagger the lanes: the entropy stages (bound by shared memory, few warps) of lane l start when lane l-1 has finished
+    // its own and moved on to the LZ77 stage (bound by instruction issue, no shared memory), so the two kinds of work share
+    // the SMs instead of two lanes fighting over the same resource.
+    if (lane_idx > 0 && staggered) {
+        FzLane& prev = ctx->lane[lane_idx - 1];
+        while (prev.entropy_epoch.load(std::memory_order_acquire) < ctx->epoch) std::this_thread::yield();
+        CK(cudaStreamWaitEvent(s, prev.ev_entropy, 0));
+    }
     if (n_hj) { k_literals<<<(uint32_t)std::min<uint64_t>((n_hj + kLitGroups - 1) / kLitGroups, (uint64_t)g_sm_count), kLitThreads, kLitSmem, s>>>(d_blocks, d_hj, (uint32_t)n_hj, d_tickets + 2); launches++; }
     mark();
     if (n_sj) {
@@ -579,6 +602,7 @@ int fzh_decode_run(FzCtx* c, uint32_t first, uint32_t n, int flags)
     mark();
     if (n_sj) { k_records<<<(uint32_t)((n_sj + kRecWarps - 1) / kRecWarps), kRecWarps * 32, 0, s>>>(d_blocks, d_frames, d_sj, (uint32_t)n_sj, d_seq, d_spans); launches++; }
     mark();
+    signal.fire();
     k_offsets<<<gi, tb, 0, s>>>(d_items, d_infos, d_bases, d_frames, d_blocks, d_outs, n); mark(); launches++;
     if (n_frames) {
         const uint32_t grid = (uint32_t)std::min<uint64_t>(n_frames, (uint64_t)g_sm_count * kExecCtasPerSm);

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <atomic>
 #include <mutex>
 
 #include "../../include/fzgpu.h"
@@ -39,24 +40,39 @@ struct FzPinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+// One decode pipeline in flight: its own stream, events and scratch.  A context runs several lanes side by side
+// (each on a slice of the batch, driven by its own host thread) so that the shared-memory-bound entropy stages of
+// one slice overlap the issue-bound LZ77 stage of another.
+struct FzLane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[16] = {};
+    FzDevBuf d_infos, d_bases, d_outs, d_totals, d_frames, d_blocks, d_seq_jobs, d_huf_jobs, d_lit, d_seq, d_spans;
+    FzPinBuf h_totals;
+    fzg_timing_t timing = {};
+    cudaEvent_t ev_entropy = nullptr;      // recorded after this lane's entropy stages (literals, sequences, records)
+    std::atomic<uint64_t> entropy_epoch{ 0 };   // call number whose ev_entropy has been enqueued
+};
+constexpr int kMaxLanes = 4;
+
 struct FzCtx {
     int dev = -1;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;         // = lane[0].stream
     cudaStream_t copy_stream = nullptr;    // host -> device
     cudaStream_t copy_stream2 = nullptr;   // device -> host
-    cudaEvent_t ev[16] = {};
+    cudaEvent_t ev[16] = {};               // [0..11] encoder stages, [12..13] chunk pipeline
     std::mutex mu;
-    // descriptors + scratch (HBM)
-    FzDevBuf d_items, d_infos, d_bases, d_outs, d_totals, d_frames, d_blocks, d_seq_jobs, d_huf_jobs, d_lit, d_seq, d_spans;
+    FzLane lane[kMaxLanes];
+    int n_lanes = 1;
+    uint64_t epoch = 0;                    // call counter (staggering of the lanes, see fzh_decode_run)
     // staging for host-resident batches
     FzDevBuf d_stage_src, d_stage_dst;
     FzPinBuf h_items, h_outs, h_totals, h_stage_src, h_stage_dst, e_chunks_h, e_first_h;
     // encoder scratch
-    FzDevBuf e_items, e_outs, e_work;
+    FzDevBuf e_items, e_outs, e_work, d_outs, d_totals;
     fzg_timing_t timing = {};
 };
 
 // fz_decode.cu
 int fzh_decode_setup(void);
-int fzh_decode_run(FzCtx* c, uint32_t first, uint32_t n, int flags);   // items [first, first + n) of c->h_items
+int fzh_decode_run(FzCtx* c, int lane, uint32_t first, uint32_t n, int flags, bool staggered);   // items [first, first + n) of c->h_items on lane `lane`
 const char* fzh_decode_stage_name(int s);
