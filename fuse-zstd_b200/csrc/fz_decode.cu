@@ -253,51 +253,36 @@ __global__ void k_offsets(const Item* items, const ItemInfo* infos, const ItemBa
 }
 
 // ------------------------------------------------------------------ execute (LZ77)
-// What bounds this stage is the dependency chain inside a frame: on text-like data almost every
-// 256-byte stretch of output copies something from the stretch just before it, so one frame cannot
-// be spread over many warps -- they would wait on one another.  The parallelism therefore comes from
-// running MANY frames per SM: a small CTA (a few warps) owns one frame at a time (frames are drawn
-// from a ticket) and executes its blocks in order, straight into the destination in HBM; a dozen
-// such CTAs share an SM and overlap each other's chain latency.  Match sources are read back through
-// L1/L2 (the same SM wrote them).
+// What bounds this stage is the dependency chain inside a frame (on text-like data almost every
+// stretch of output copies something from just before it), so a frame is not spread over warps: ONE
+// WARP owns a frame at a time (frames are drawn from a ticket) and executes its blocks and sequences
+// in order, and the parallelism comes from the ~48 frames an SM has in flight.  There is no
+// cross-warp synchronisation at all.
 //
-// Inside a block the work is split by OUTPUT position, not by sequence: the block is cut into spans
-// of 256 bytes, spans go round-robin to the CTA's warps, and each lane owns one 8-byte chunk of its
-// warp's span.  Because a sequence record carries cumulative positions (rec_e / rec_le), a lane
-// finds the sequence covering its chunk with a five-step search over 32 records (the span index
-// gives the first one) and then walks the pieces of its chunk -- literal run, match, next sequence
-// -- pulling up to 8 source bytes per piece with two aligned loads and a funnel shift.  A chunk is
-// written once, with one 8-byte store (256 contiguous bytes per warp).
-//
-// Ordering: s_ready holds one bit per 8-byte chunk of the block (one 32-bit word per span, written only
-// by the warp that owns the span, release/acquire at CTA scope).  A piece is copied as soon as the
-// chunks holding its source are marked; until then its lane sits out and retries in the next pass of
-// the span loop.  Spans finish out of order, so a span waits only for the data it actually reads.
-// Progress: the lowest unfinished chunk of the block only reads lower -- finished -- chunks, and its
-// owner is working on it, since every warp takes its spans in increasing order.  Overlapping matches
-// (offset < length) are periodic with period `offset` and are redirected to the period that precedes
-// the match.  Earlier blocks of the frame (the window) are complete before a block starts.
+// A warp takes 32 sequences per round, one per lane.  The positional records (rec_e / rec_le) give
+// every lane its literal run [S, M) and match [M, E) without a scan.  The round's output (a few
+// hundred bytes) is assembled in a per-warp shared-memory stage and then written to HBM with
+// 16-byte stores:
+//   1. literal runs: every lane copies its own run from the literal buffer, 8 bytes per step;
+//   2. matches: every lane copies its own match, 8 bytes per step (two aligned loads + funnel shift),
+//      from HBM/L2 when the source lies before the round (earlier rounds, earlier blocks = the window)
+//      or from the stage when it lies inside the round.  A lane whose source is not written yet
+//      sits out; the frontier is the position reached by the first unfinished lane, which can always
+//      advance (its sources lie below its own position), so the passes terminate;
+//   3. flush.
+// Offsets < 8 (the match overlaps its own 8-byte step) are expanded from the period; a sequence too
+// large for the stage (long literal run or long match) is copied by the whole warp straight to HBM.
 #ifndef FZ_EXEC_WARPS
 #define FZ_EXEC_WARPS 4
 #endif
 #ifndef FZ_EXEC_CTAS
 #define FZ_EXEC_CTAS 12
 #endif
-constexpr int kExecWarps = FZ_EXEC_WARPS;                    // warps per frame in flight
+constexpr int kExecWarps = FZ_EXEC_WARPS;                    // warps (= frames in flight) per CTA
 constexpr int kExecCtasPerSm = FZ_EXEC_CTAS;
-constexpr uint32_t kReadyWords = kBlockMax / kSpan;          // 512
+constexpr uint32_t kStage = 1024;                            // bytes of round output a warp assembles in shared memory
+constexpr uint32_t kStageBytes = kStage + 48;                // + alignment slack (the stage mirrors the low 4 address bits) + load slack
 constexpr uint32_t kFull = 0xFFFFFFFFu;
-
-__device__ __forceinline__ uint32_t ld_acquire_shared(const uint32_t* p)
-{
-    uint32_t v;
-    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_shared(uint32_t* p, uint32_t v)
-{
-    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
-}
 
 __device__ __forceinline__ uint64_t funnel8(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t byte_shift)
 {
@@ -306,7 +291,7 @@ __device__ __forceinline__ uint64_t funnel8(uint32_t x0, uint32_t x1, uint32_t x
     const uint32_t lo = __funnelshift_r(x0, x1, r), hi = __funnelshift_r(x1, x2, r);
     return (uint64_t)lo | ((uint64_t)hi << 32);
 }
-// nb (1..8) bytes starting at g; never touches an 8-byte word that holds no wanted byte
+// nb (1..8) bytes starting at generic address g (HBM or shared memory); never touches an 8-byte word that holds no wanted byte
 __device__ __forceinline__ uint64_t ld8_any(const uint8_t* g, uint32_t nb)
 {
     const uintptr_t a = (uintptr_t)g & ~(uintptr_t)7;
@@ -316,173 +301,191 @@ __device__ __forceinline__ uint64_t ld8_any(const uint8_t* g, uint32_t nb)
     if (sh + nb > 8) w1 = *(const uint2*)(a + 8);
     return funnel8(w0.x, w0.y, w1.x, w1.y, sh);
 }
-// nb (1..8) low bytes of v -> g, any alignment
-__device__ __forceinline__ void st8_any(uint8_t* g, uint64_t v, uint32_t nb)
+// nb (1..8) low bytes of v -> shared memory at any alignment
+__device__ __forceinline__ void st_stage(uint8_t* p, uint64_t v, uint32_t nb)
 {
-    const uint32_t a = (uint32_t)(uintptr_t)g & 7;
-    if (nb == 8 && a == 0) *(uint64_t*)g = v;
-    else if (nb == 8 && (a & 3) == 0) { ((uint32_t*)g)[0] = (uint32_t)v; ((uint32_t*)g)[1] = (uint32_t)(v >> 32); }
-    else for (uint32_t i = 0; i < nb; i++) g[i] = (uint8_t)(v >> (8 * i));
+#pragma unroll
+    for (uint32_t i = 0; i < 8; i++) if (i < nb) p[i] = (uint8_t)(v >> (8 * i));
 }
 
-__device__ __forceinline__ void cta_copy(uint8_t* dst, const uint8_t* src, uint32_t n)
+// warp-cooperative copy / fill, any alignment, any size
+__device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane)
 {
     if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) {
         const uint32_t nv = n >> 4;
-        for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x) ((uint4*)dst)[i] = ((const uint4*)src)[i];
-        for (uint32_t i = (nv << 4) + threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+        for (uint32_t i = lane; i < nv; i += 32) ((uint4*)dst)[i] = ((const uint4*)src)[i];
+        for (uint32_t i = (nv << 4) + lane; i < n; i += 32) dst[i] = src[i];
     } else {
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+        for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
     }
 }
 
-__device__ __forceinline__ void exec_block(const Block& b, const uint64_t* __restrict__ sq, const uint16_t* __restrict__ sp,
-                                           uint8_t* g0, uint64_t done, uint32_t* s_ready, int* s_status)
+// One sequence that does not fit the stage: literal run + match copied by the whole warp, straight to HBM.
+// dst = output position of the sequence start, all arguments warp-uniform.
+__device__ __forceinline__ void warp_big_sequence(uint8_t* dst, const uint8_t* lit, uint32_t ll, uint32_t ml, uint32_t off, uint32_t lane)
 {
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    warp_copy(dst, lit, ll, lane);
+    __syncwarp();
+    uint8_t* m = dst + ll;
+    if (off == 0) return;                                    // flagged corrupt by the caller
+    if (off >= 512) {                                        // source and destination of a 512-byte round never overlap
+        const uint8_t* s = m - off;
+        for (uint32_t i = 0; i < ml; i += 512) {
+            const uint32_t nb = min(16u, ml > i + 16 * lane ? ml - i - 16 * lane : 0u);
+            for (uint32_t k = 0; k < nb; k++) m[i + 16 * lane + k] = s[i + 16 * lane + k];
+            __syncwarp();
+        }
+    } else {                                                 // periodic with period `off`: byte i equals byte i % off of the period
+        const uint8_t* s = m - off;
+        for (uint32_t i = lane; i < ml; i += 32) m[i] = s[i % off];
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void exec_block_warp(uint8_t* stage, const Block& b, const uint64_t* __restrict__ sq, uint8_t* g0,
+                                                uint64_t done, int& status, uint32_t lane)
+{
     const uint32_t nseq = b.nseq, rsize = b.rsize, lit_regen = b.lit_regen;
     const uint8_t* __restrict__ lit = b.lit;
     const uint32_t in0 = b.rep_in[0], in1 = b.rep_in[1], in2 = b.rep_in[2];
-    const uint32_t n_spans = (rsize + kSpan - 1) / kSpan;
-
-    for (uint32_t n = warp; n < n_spans; n += kExecWarps) {
-        const uint32_t ss = n * kSpan, P = ss + 8 * lane;
-        const bool active = P < rsize;
-        const uint32_t Pend = active ? min(P + 8, rsize) : P;
-
-        // ---- the sequence that covers byte P: first record with E > P
-        uint32_t k = 0xFFFFFFFFu;
-        for (uint32_t kb = sp[n];; kb += 32) {
-            const uint32_t j = kb + lane;
-            const uint32_t Ej = j < nseq ? rec_e(__ldg(sq + j)) : rsize;     // past the last sequence: trailing literals
-            uint32_t c = 0;
-#pragma unroll
-            for (int st = 16; st >= 1; st >>= 1) {
-                const uint32_t e = __shfl_sync(kFull, Ej, (c + st - 1) & 31);
-                if (e <= P) c += st;
-            }
-            const uint32_t e31 = __shfl_sync(kFull, Ej, 31);
-            if (c == 31 && e31 <= P) c = 32;
-            if (active && k == 0xFFFFFFFFu && c < 32) k = kb + c;
-            if (!__any_sync(kFull, active && k == 0xFFFFFFFFu)) break;
+    uint32_t Ecarry = 0, LEcarry = 0;
+    for (uint32_t g = 0; g < nseq;) {
+        const uint32_t nv = min(32u, nseq - g);
+        const uint64_t r = lane < nv ? __ldg(sq + g + lane) : 0;
+        uint32_t E = rec_e(r), LE = rec_le(r);
+        const uint32_t Elast = __shfl_sync(kFull, E, nv - 1), LElast = __shfl_sync(kFull, LE, nv - 1);
+        if (lane >= nv) { E = Elast; LE = LElast; }
+        uint32_t S = __shfl_up_sync(kFull, E, 1), LEp = __shfl_up_sync(kFull, LE, 1);
+        if (lane == 0) { S = Ecarry; LEp = LEcarry; }
+        const uint32_t gS = Ecarry;                              // output position where this round starts
+        const uint32_t M = S + (LE - LEp);
+        uint32_t off = lane < nv ? off_resolve(rec_off(r), in0, in1, in2) : 1;
+        if (lane < nv && (uint64_t)off > done + M) { off = 0; status = FZG_E_CORRUPT; }     // reaches before the frame start
+        // sequences of this round: the leading ones whose output fits the stage
+        const uint32_t fit = __ballot_sync(kFull, lane < nv && E - gS <= kStage);
+        const uint32_t m = fit == kFull ? 32u : (uint32_t)__ffs((int)~fit) - 1u;
+        if (m == 0) {                                            // sequence g alone is larger than the stage
+            const uint32_t ll0 = __shfl_sync(kFull, LE - LEp, 0), ml0 = __shfl_sync(kFull, E - M, 0), off0 = __shfl_sync(kFull, off, 0);
+            warp_big_sequence(g0 + gS, lit + LEcarry, ll0, ml0, off0, lane);
+            Ecarry = __shfl_sync(kFull, E, 0); LEcarry = __shfl_sync(kFull, LE, 0);
+            g += 1;
+            continue;
         }
-
-        uint32_t S = 0, LEp = 0, M = 0, E = 0, LE = 0, off = 1;
-        uint64_t nxt = 0;                        // record k + 1, loaded one sequence ahead so that its L2 latency is off the piece loop
-        auto fetch = [&](uint32_t kk, uint64_t r) {   // sequence kk (record r) becomes current; (S, LEp) hold its predecessor's ends
-            if (kk < nseq) {
-                E = rec_e(r); LE = rec_le(r); off = off_resolve(rec_off(r), in0, in1, in2);
-                M = S + (LE - LEp);
-                if ((uint64_t)off > done + M) { off = 0; atomicMax(s_status, FZG_E_CORRUPT); }   // before the frame start
-            } else { E = rsize; LE = lit_regen; off = 1; M = E; }
-            nxt = kk + 1 < nseq ? __ldg(sq + kk + 1) : 0;
-        };
-        if (active) {
-            if (k > 0) { const uint64_t r = __ldg(sq + (k - 1 < nseq ? k - 1 : nseq - 1)); S = rec_e(r); LEp = rec_le(r); }
-            fetch(k, k < nseq ? __ldg(sq + k) : 0);
-        }
-
-        uint32_t pos = P, filled = 0, donemask = 0, waitc = 0;
-        uint64_t acc = 0;
-        bool go = active;
-        for (;;) {                                  // passes over the span
-            bool wrote = false;
-            // lockstep piece loop: one vote per step keeps the lanes converged
+        const bool mine = lane < m;
+        const uint32_t gE = __shfl_sync(kFull, E, m - 1);         // end of the round's output
+        const uint32_t a = (uint32_t)((uintptr_t)(g0 + gS) & 15); // stage[a + i] <-> g0[gS + i]: same low address bits as HBM
+        uint8_t* const st = stage + a - gS;                       // st[p] is the stage byte of output position p (gS <= p < gE)
+        // ---- 1. literal runs
+        {
+            uint32_t pos = S; const uint8_t* src = lit + LEp;
+            bool go = mine && pos < M;
             while (__any_sync(kFull, go)) {
                 if (go) {
-                    if (pos >= E) { k++; S = E; LEp = LE; fetch(k, nxt); }
-                    uint32_t nb; const uint8_t* src = nullptr; bool fromacc = false;
-                    if (pos < M) {                                         // literal run
-                        nb = min(M, Pend) - pos;
-                        src = lit + LEp + (pos - S);
-                    } else {                                               // match
-                        nb = min(E, Pend) - pos;
-                        if (off != 0) {
-                            int32_t s = (int32_t)pos - (int32_t)off;
-                            if (s >= (int32_t)M) {                         // overlapping match: periodic, read the first period
-                                const uint32_t r = (pos - M) % off;
-                                s = (int32_t)(M - off + r); nb = min(nb, off - r);
-                            }
-                            if (s < 0) { nb = min(nb, (uint32_t)(-s)); src = g0 + s; }              // window: earlier blocks
-                            else if ((uint32_t)s >= P) { nb = 1; fromacc = true; src = g0 + s; }    // own chunk: still in registers
-                            else {                                         // the source spans one or two 8-byte chunks of the block
-                                const uint32_t c0 = (uint32_t)s >> 3, c1 = ((uint32_t)s + nb - 1) >> 3;
-                                const uint32_t w0 = ld_acquire_shared(s_ready + (c0 >> 5));
-                                const uint32_t w1 = (c1 >> 5) == (c0 >> 5) ? w0 : ld_acquire_shared(s_ready + (c1 >> 5));
-                                if ((w0 >> (c0 & 31)) & 1) {
-                                    if (!((w1 >> (c1 & 31)) & 1)) nb = 8 - ((uint32_t)s & 7);   // only the first chunk is final
-                                    src = g0 + s;
-                                } else { nb = 0; go = false; waitc = c0; } // its producer has not got there yet
-                            }
-                        }
-                    }
-                    if (nb) {
-                        uint64_t v = 0;
-                        if (fromacc) v = (acc >> (64 - 8 * filled + 8 * ((uint32_t)(src - g0) - P))) & 0xFF;
-                        else if (src) v = ld8_any(src, nb);
-                        acc = nb == 8 ? v : ((acc >> (8 * nb)) | (v << (64 - 8 * nb)));
-                        filled += nb; pos += nb; wrote = true;
-                        go = pos < Pend;
-                    }
+                    const uint32_t nb = min(8u, M - pos);
+                    st_stage(st + pos, ld8_any(src, nb), nb);
+                    pos += nb; src += nb; go = pos < M;
                 }
             }
-            const bool fin = active && pos >= Pend;
-            if (fin && wrote) st8_any(g0 + P, filled == 8 ? acc : (acc >> (64 - 8 * filled)), filled);
-            __syncwarp();
-            const uint32_t finmask = __ballot_sync(kFull, fin || !active);
-            if (finmask != donemask) {              // publish the chunks finished in this pass
-                if (lane == 0) st_release_shared(s_ready + n, finmask);
-                donemask = finmask;
-            }
-            if (finmask == kFull) break;
-            go = active && pos < Pend;
-            // Every unfinished lane is blocked on a lower chunk: poll just those flags (cheap, with back-off) until one
-            // of them is set, instead of re-running the piece logic.  A chunk of this very span counts as published.
-            for (uint32_t spin = 0;; spin++) {
-                const bool ok = go && (((waitc >> 5) == n ? finmask : ld_acquire_shared(s_ready + (waitc >> 5))) >> (waitc & 31) & 1);
-                if (__any_sync(kFull, ok)) break;
-                __nanosleep(spin < 8 ? 32u * (spin + 1) : 256u);
+        }
+        __syncwarp();
+        // ---- 2. matches
+        {
+            uint32_t pos = M;
+            bool pending = mine && pos < E;
+            uint32_t front = gS;                                  // every output byte below `front` is written (HBM or stage)
+            while (__any_sync(kFull, pending)) {
+                const uint32_t pm = __ballot_sync(kFull, pending);
+                const uint32_t first = (uint32_t)__ffs((int)pm) - 1u;
+                front = __shfl_sync(kFull, pos, first);           // lanes below `first` are complete, `first` has written up to pos
+                bool go = pending;
+                while (__any_sync(kFull, go)) {
+                    if (go) {
+                        uint32_t nb = min(8u, E - pos);
+                        uint64_t v = 0;
+                        if (off == 0) { /* corrupt: zeros */ }
+                        else if (off < 8 && off < nb) {           // the step overlaps itself: expand the period byte by byte
+                            const int32_t s0 = (int32_t)pos - (int32_t)off;
+                            const bool ok = lane == first || (uint32_t)(s0 + (int32_t)off) <= front || s0 >= (int32_t)M;   // period written?
+                            if (ok) {
+                                const uint8_t* sp = s0 < (int32_t)gS ? (const uint8_t*)g0 + s0 : (const uint8_t*)st + s0;
+                                const uint32_t take = s0 < (int32_t)gS ? min(off, gS - (uint32_t)s0) : off;   // a period straddling the round start
+                                uint64_t pat = ld8_any(sp, take);
+                                if (take < off) pat = (pat & ((1ull << (8 * take)) - 1)) | (ld8_any((const uint8_t*)st + gS, off - take) << (8 * take));
+                                for (uint32_t i = 0; i < nb; i++) v |= ((pat >> (8 * (i % off))) & 0xFF) << (8 * i);
+                            } else nb = 0;
+                        } else {
+                            const int32_t s = (int32_t)pos - (int32_t)off;
+                            // available bytes: below `front`, or this lane's own match bytes written so far
+                            const uint32_t lim = lane == first ? pos : ((s >= (int32_t)M) ? pos : front);
+                            if (s < (int32_t)gS) {                 // before the round: HBM / L2 (earlier rounds, earlier blocks)
+                                nb = min(nb, gS - (uint32_t)s);    // a step straddling the round start is split
+                                v = ld8_any((const uint8_t*)g0 + s, nb);
+                            } else if ((uint32_t)s + nb <= lim) v = ld8_any((const uint8_t*)st + s, nb);
+                            else if ((uint32_t)s < lim) { nb = lim - (uint32_t)s; v = ld8_any((const uint8_t*)st + s, nb); }
+                            else nb = 0;
+                        }
+                        if (nb) { st_stage(st + pos, v, nb); pos += nb; go = pos < E; }
+                        else go = false;                          // its source is still being produced by a lower lane
+                    }
+                }
+                __syncwarp();
+                pending = mine && pos < E;
             }
         }
+        __syncwarp();
+        // ---- 3. flush stage[a .. a + (gE - gS)) -> g0 + gS: head bytes, aligned 16-byte body, tail bytes
+        {
+            const uint32_t n = gE - gS;
+            uint8_t* gd = g0 + gS;
+            const uint32_t head = min(n, (16 - a) & 15);
+            if (lane < head) gd[lane] = stage[a + lane];
+            const uint32_t nvec = (n - head) >> 4;
+            for (uint32_t i = lane; i < nvec; i += 32) *(uint4*)(gd + head + 16 * i) = *(const uint4*)(stage + a + head + 16 * i);
+            const uint32_t tail0 = head + (nvec << 4);
+            if (tail0 + lane < n) gd[tail0 + lane] = stage[a + tail0 + lane];
+        }
+        __syncwarp();
+        Ecarry = gE; LEcarry = __shfl_sync(kFull, LE, m - 1);
+        g += m;
     }
+    // literals after the last sequence
+    warp_copy(g0 + Ecarry, lit + LEcarry, rsize - Ecarry, lane);
+    (void)lit_regen;
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(kExecWarps * 32, kExecCtasPerSm) k_execute(Frame* frames, const Block* blocks, const Item* items,
                                                                               const ItemOut* outs, const uint64_t* seqs,
-                                                                              const uint16_t* spans, uint32_t n_frames, uint32_t* ticket)
+                                                                              uint32_t n_frames, uint32_t* ticket)
 {
-    __shared__ uint32_t s_ready[kReadyWords];
-    __shared__ uint32_t s_next;
-    __shared__ int s_status;
+    __shared__ __align__(16) uint8_t s_stage[kExecWarps][kStageBytes];
+    const uint32_t lane = threadIdx.x & 31;
+    uint8_t* stage = s_stage[threadIdx.x >> 5];
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) { s_next = atomicAdd(ticket, 1); s_status = 0; }
-        __syncthreads();
-        const uint32_t f = s_next;
+        uint32_t f = 0;
+        if (lane == 0) f = atomicAdd(ticket, 1);
+        f = __shfl_sync(kFull, f, 0);
         if (f >= n_frames) return;
         Frame& fr = frames[f];
         if (outs[fr.item].fail) continue;
         uint8_t* const fbase = items[fr.item].dst + fr.out_off;
         uint64_t done = 0;
+        int status = 0;
         for (uint32_t kb = 0; kb < fr.n_blocks; kb++) {
             const Block& b = blocks[fr.first_block + kb];
             uint8_t* const g0 = fbase + done;
             const uint32_t rsize = b.rsize;
-            if (b.type == BT_RAW) cta_copy(g0, b.src, rsize);
+            if (b.type == BT_RAW) warp_copy(g0, b.src, rsize, lane);
             else if (b.type == BT_RLE) {
                 const uint8_t v = b.src[0];
-                for (uint32_t i = threadIdx.x; i < rsize; i += blockDim.x) g0[i] = v;
-            } else if (b.nseq == 0) cta_copy(g0, b.lit, rsize);
-            else {
-                for (uint32_t i = threadIdx.x; i < kReadyWords; i += blockDim.x) s_ready[i] = 0;
-                __syncthreads();
-                exec_block(b, seqs + b.seq_base, spans + b.span_base, g0, done, s_ready, &s_status);
-            }
-            __threadfence_block();
-            __syncthreads();                   // later blocks read this one back (the window), and s_ready is reused
+                for (uint32_t i = lane; i < rsize; i += 32) g0[i] = v;
+            } else if (b.nseq == 0) warp_copy(g0, b.lit, rsize, lane);
+            else exec_block_warp(stage, b, seqs + b.seq_base, g0, done, status, lane);
+            __syncwarp();                      // later blocks read this one back (the window)
             done += rsize;
         }
-        if (threadIdx.x == 0 && s_status) fr.status = s_status;
+        status = __reduce_max_sync(kFull, status);
+        if (lane == 0 && status) fr.status = status;
     }
 }
 
@@ -605,8 +608,8 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
     signal.fire();
     k_offsets<<<gi, tb, 0, s>>>(d_items, d_infos, d_bases, d_frames, d_blocks, d_outs, n); mark(); launches++;
     if (n_frames) {
-        const uint32_t grid = (uint32_t)std::min<uint64_t>(n_frames, (uint64_t)g_sm_count * kExecCtasPerSm);
-        k_execute<<<grid, kExecWarps * 32, 0, s>>>(d_frames, d_blocks, d_items, d_outs, d_seq, d_spans, (uint32_t)n_frames, d_tickets + 1); launches++;
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((n_frames + kExecWarps - 1) / kExecWarps, (uint64_t)g_sm_count * kExecCtasPerSm);
+        k_execute<<<grid, kExecWarps * 32, 0, s>>>(d_frames, d_blocks, d_items, d_outs, d_seq, (uint32_t)n_frames, d_tickets + 1); launches++;
     }
     mark();
     if (n_frames && !(flags & FZG_NO_VERIFY_CHECKSUM)) { k_checksum<<<(uint32_t)((n_frames * 4 + 127) / 128), 128, 0, s>>>(d_frames, d_items, d_outs, (uint32_t)n_frames); launches++; }
