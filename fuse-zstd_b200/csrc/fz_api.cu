@@ -79,7 +79,7 @@ extern "C" void fzg_shutdown(void)
             FzLane& L = c->lane[l];
             cudaStreamSynchronize(L.stream);
             FzDevBuf* lb[] = { &L.d_infos, &L.d_bases, &L.d_outs, &L.d_totals, &L.d_frames, &L.d_blocks, &L.d_seq_jobs, &L.d_huf_jobs,
-                               &L.d_lit, &L.d_seq, &L.d_spans };
+                               &L.d_lit, &L.d_seq };
             for (auto* b : lb) b->release();
             L.h_totals.release();
             for (auto& e : L.ev) cudaEventDestroy(e);
@@ -138,7 +138,6 @@ static int run_batch(bool encode, int device, size_t n, const void* const* src, 
     if (!c) return -ENODEV;
     std::lock_guard<std::mutex> lk(c->mu);
     CKR(cudaSetDevice(c->dev));
-    cudaStream_t s = c->stream;
     const bool src_dev = flags & FZG_SRC_DEVICE, dst_dev = flags & FZG_DST_DEVICE;
     if ((rc = c->h_items.reserve(n * sizeof(Item)))) return rc;
     if ((rc = c->h_outs.reserve(n * sizeof(ItemOut)))) return rc;

@@ -44,13 +44,13 @@ struct Item {            // one .zst file of the batch
 
 struct ItemInfo {        // written by the count pass, consumed by the scan
     uint32_t n_frames, n_blocks, n_seq_jobs, n_huf_jobs;
-    uint64_t lit_bytes, n_seq, n_spans;
+    uint64_t lit_bytes, n_seq;
     int32_t walk_status; uint32_t pad;
 };
 
 struct ItemBase {        // exclusive prefix sums over items
     uint32_t frame, block, seq_job, huf_job;
-    uint64_t lit, seq, span;
+    uint64_t lit, seq;
 };
 
 struct Frame {
@@ -70,7 +70,6 @@ struct Block {
     const uint8_t* src;      // block content (after the 3-byte header)
     const uint8_t* lit;      // regenerated literals: into src (Raw) or into literal scratch
     uint64_t seq_base;       // first record in the sequence scratch (even, so records can be stored in pairs)
-    uint64_t span_base;      // first entry of this block's span index (one uint16 per kSpan output bytes)
     uint64_t out_off;        // offset in item dst (filled by the offsets pass)
     uint32_t csize;          // Block_Size field
     uint32_t rsize;          // regenerated size (Raw/RLE: known; Compressed: filled by the sequence pass)
@@ -253,7 +252,7 @@ FZ_HD void walk_item(uint32_t item_idx, const Item& it, ItemInfo& info, const It
 {
     const uint8_t* src = it.src; const uint64_t n = it.src_len;
     uint64_t ip = 0;
-    uint32_t nf = 0, nb = 0, nsj = 0, nhj = 0; uint64_t lit_bytes = 0, n_seq = 0, n_spans = 0;
+    uint32_t nf = 0, nb = 0, nsj = 0, nhj = 0; uint64_t lit_bytes = 0, n_seq = 0;
     int status = FZG_OK;
     while (ip < n) {
         if (n - ip < 4) { status = FZG_E_TRUNCATED; break; }
@@ -283,7 +282,7 @@ FZ_HD void walk_item(uint32_t item_idx, const Item& it, ItemInfo& info, const It
             uint32_t csize = type == BT_RLE ? 1 : bsize;
             if (n - ip < csize) { status = FZG_E_TRUNCATED; break; }
             Block b;
-            b.src = src + ip; b.lit = nullptr; b.seq_base = 0; b.span_base = 0; b.out_off = 0;
+            b.src = src + ip; b.lit = nullptr; b.seq_base = 0; b.out_off = 0;
             b.csize = bsize; b.rsize = type == BT_COMPRESSED ? 0 : bsize;
             b.lit_hdr = b.lit_regen = b.lit_csize = b.nseq = b.seq_hdr = 0;
             b.frame = frame_gidx; b.huf_src = b.ll_src = b.of_src = b.ml_src = -1;
@@ -324,8 +323,8 @@ FZ_HD void walk_item(uint32_t item_idx, const Item& it, ItemInfo& info, const It
                     lit_bytes += (lh.regen + 15u) & ~15u;
                 }
                 if (nseq) {
-                    if (FILL) { b.seq_base = base->seq + n_seq; b.span_base = base->span + n_spans; seq_jobs[base->seq_job + nsj] = gb; }
-                    n_seq += (nseq + 1u) & ~1u; n_spans += block_max / kSpan + 2; nsj++;
+                    if (FILL) { b.seq_base = base->seq + n_seq; seq_jobs[base->seq_job + nsj] = gb; }
+                    n_seq += (nseq + 1u) & ~1u; nsj++;
                 }
                 if (lh.type != LT_RAW) { if (FILL) huf_jobs[base->huf_job + nhj] = gb; nhj++; }
             }
@@ -349,7 +348,7 @@ FZ_HD void walk_item(uint32_t item_idx, const Item& it, ItemInfo& info, const It
         nf++;
     }
     info.n_frames = nf; info.n_blocks = nb; info.n_seq_jobs = nsj; info.n_huf_jobs = nhj;
-    info.lit_bytes = lit_bytes; info.n_seq = n_seq; info.n_spans = n_spans; info.walk_status = status; info.pad = 0;
+    info.lit_bytes = lit_bytes; info.n_seq = n_seq; info.walk_status = status; info.pad = 0;
 }
 
 // ------------------------------------------------------------------ forward bit reader (FSE table descriptions)

@@ -37,38 +37,38 @@ __global__ void k_count(const Item* items, ItemInfo* infos, uint32_t n, uint32_t
     infos[i] = info;
 }
 
-// single CTA; exclusive scan of seven counters over the items.  totals[0..6] = frames, blocks,
-// seq jobs, huf jobs, literal bytes, sequence records, span-index entries.
+// single CTA; exclusive scan of six counters over the items.  totals[0..5] = frames, blocks,
+// seq jobs, huf jobs, literal bytes, sequence records.
 __global__ void k_scan(const ItemInfo* infos, ItemBase* bases, uint64_t* totals, uint32_t n)   // totals: pinned host memory (zero-copy)
 {
-    __shared__ uint64_t part[512][7];
+    __shared__ uint64_t part[512][6];
     const uint32_t t = threadIdx.x, T = blockDim.x;
     const uint32_t per = (n + T - 1) / T;
     const uint32_t lo = t * per < n ? t * per : n, hi = lo + per < n ? lo + per : n;
-    uint64_t acc[7] = { 0, 0, 0, 0, 0, 0, 0 };
+    uint64_t acc[6] = { 0, 0, 0, 0, 0, 0 };
     for (uint32_t i = lo; i < hi; i++) {
         const ItemInfo& f = infos[i];
         acc[0] += f.n_frames; acc[1] += f.n_blocks; acc[2] += f.n_seq_jobs; acc[3] += f.n_huf_jobs;
-        acc[4] += f.lit_bytes; acc[5] += f.n_seq; acc[6] += f.n_spans;
+        acc[4] += f.lit_bytes; acc[5] += f.n_seq;
     }
-    for (int c = 0; c < 7; c++) part[t][c] = acc[c];
+    for (int c = 0; c < 6; c++) part[t][c] = acc[c];
     __syncthreads();
     if (t == 0) {
-        uint64_t run[7] = { 0, 0, 0, 0, 0, 0, 0 };
+        uint64_t run[6] = { 0, 0, 0, 0, 0, 0 };
         for (uint32_t k = 0; k < T; k++)
-            for (int c = 0; c < 7; c++) { uint64_t v = part[k][c]; part[k][c] = run[c]; run[c] += v; }
-        for (int c = 0; c < 7; c++) totals[c] = run[c];
+            for (int c = 0; c < 6; c++) { uint64_t v = part[k][c]; part[k][c] = run[c]; run[c] += v; }
+        for (int c = 0; c < 6; c++) totals[c] = run[c];
     }
     __syncthreads();
-    for (int c = 0; c < 7; c++) acc[c] = part[t][c];
+    for (int c = 0; c < 6; c++) acc[c] = part[t][c];
     for (uint32_t i = lo; i < hi; i++) {
         const ItemInfo& f = infos[i];
         ItemBase b;
         b.frame = (uint32_t)acc[0]; b.block = (uint32_t)acc[1]; b.seq_job = (uint32_t)acc[2]; b.huf_job = (uint32_t)acc[3];
-        b.lit = acc[4]; b.seq = acc[5]; b.span = acc[6];
+        b.lit = acc[4]; b.seq = acc[5];
         bases[i] = b;
         acc[0] += f.n_frames; acc[1] += f.n_blocks; acc[2] += f.n_seq_jobs; acc[3] += f.n_huf_jobs;
-        acc[4] += f.lit_bytes; acc[5] += f.n_seq; acc[6] += f.n_spans;
+        acc[4] += f.lit_bytes; acc[5] += f.n_seq;
     }
 }
 
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) k_sequences(Block* blocks, con
 // ------------------------------------------------------------------ sequences, stage B: records
 // One warp per block, 32 sequences per step, in place over the RAW records of stage A: extra bits ->
 // (literal length, match length, offset value); warp scans -> cumulative positions E / LE; repeat
-// offsets; the positional record (rec_pack) and the span index.  Repeat offsets are the only serial
+// offsets; the positional record (rec_pack).  Repeat offsets are the only serial
 // part: a step without repeat codes takes its history from the last three lanes, otherwise the history
 // hops from one repeat code to the next (a few per step), never lane by lane.
 __device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v, uint32_t lane)
@@ -182,7 +182,7 @@ __device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v, uint32_t lane)
 
 constexpr int kRecWarps = 8;
 __global__ void __launch_bounds__(kRecWarps * 32) k_records(Block* blocks, const Frame* frames, const uint32_t* jobs, uint32_t n_jobs,
-                                                            uint64_t* seqs, uint16_t* spans)
+                                                            uint64_t* seqs)
 {
     __shared__ SeqConsts K;
     for (uint32_t i = threadIdx.x; i < sizeof(SeqConsts) / 4; i += blockDim.x) ((uint32_t*)&K)[i] = ((const uint32_t*)&c_seq_consts)[i];
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kRecWarps * 32) k_records(Block* blocks, const
     Block& b = blocks[jobs[job]];
     if (b.status) return;
     const uint32_t nseq = b.nseq, lit_regen = b.lit_regen, block_max = frames[b.frame].block_max;
-    uint64_t* sq = seqs + b.seq_base; uint16_t* span = spans + b.span_base;
+    uint64_t* sq = seqs + b.seq_base;
     uint32_t rep0 = off_sym(0), rep1 = off_sym(1), rep2 = off_sym(2);      // history, warp-uniform
     uint32_t Ebase = 0, LEbase = 0; bool bad = false;
     for (uint32_t g = 0; g < nseq && !bad; g += 32) {
@@ -226,18 +226,11 @@ __global__ void __launch_bounds__(kRecWarps * 32) k_records(Block* blocks, const
         ok = ok && !(ofv > 3 && off > kOffMax) && LE <= lit_regen && E <= block_max;
         bad = __any_sync(0xFFFFFFFFu, valid && !ok);
         if (bad) break;
-        if (valid) {
-            sq[i] = rec_pack(E, LE, off);
-            const uint32_t Ep = E - ll - ml;
-            const uint32_t s1 = (E - 1) / kSpan;                           // span boundaries kSpan * s inside [Ep, E): almost always 0 or 1
-            if (s1 * kSpan >= Ep) span[s1] = (uint16_t)i;
-            if (E - Ep > kSpan) for (uint32_t sI = (Ep + kSpan - 1) / kSpan; sI < s1; sI++) span[sI] = (uint16_t)i;
-        }
+        if (valid) sq[i] = rec_pack(E, LE, off);
         Ebase = __shfl_sync(0xFFFFFFFFu, E, 31); LEbase = __shfl_sync(0xFFFFFFFFu, LE, 31);
     }
     const uint32_t rsize = Ebase + (lit_regen - LEbase);
     if (bad || rsize > block_max) { if (lane == 0) b.status = FZG_E_CORRUPT; return; }
-    for (uint32_t sI = (Ebase + kSpan - 1) / kSpan + lane; sI * kSpan < rsize; sI += 32) span[sI] = (uint16_t)nseq;     // trailing literals
     if (lane == 0) { b.rsize = rsize; b.rep_out[0] = rep0; b.rep_out[1] = rep1; b.rep_out[2] = rep2; }
 }
 
@@ -280,7 +273,10 @@ __global__ void k_offsets(const Item* items, const ItemInfo* infos, const ItemBa
 #endif
 constexpr int kExecWarps = FZ_EXEC_WARPS;                    // warps (= frames in flight) per CTA
 constexpr int kExecCtasPerSm = FZ_EXEC_CTAS;
-constexpr uint32_t kStage = 1024;                            // bytes of round output a warp assembles in shared memory
+#ifndef FZ_EXEC_STAGE
+#define FZ_EXEC_STAGE 1024
+#endif
+constexpr uint32_t kStage = FZ_EXEC_STAGE;                            // bytes of round output a warp assembles in shared memory
 constexpr uint32_t kStageBytes = kStage + 48;                // + alignment slack (the stage mirrors the low 4 address bits) + load slack
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 
@@ -573,7 +569,7 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
     k_scan<<<1, 512, 0, s>>>(d_infos, d_bases, h_totals, n); mark();
     CK(cudaStreamSynchronize(s));
     const uint64_t* tot = h_totals;
-    const uint64_t n_frames = tot[0], n_blocks = tot[1], n_sj = tot[2], n_hj = tot[3], lit_bytes = tot[4], n_seq = tot[5], n_spans = tot[6];
+    const uint64_t n_frames = tot[0], n_blocks = tot[1], n_sj = tot[2], n_hj = tot[3], lit_bytes = tot[4], n_seq = tot[5];
     if (n_blocks >= (1ull << 31) || n_frames >= (1ull << 31)) return -22;
     if ((rc = c->d_frames.reserve((n_frames + 1) * sizeof(Frame)))) return rc;
     if ((rc = c->d_blocks.reserve((n_blocks + 1) * sizeof(Block)))) return rc;
@@ -581,10 +577,9 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
     if ((rc = c->d_huf_jobs.reserve((n_hj + 1) * 4))) return rc;
     if ((rc = c->d_lit.reserve(lit_bytes + 64))) return rc;
     if ((rc = c->d_seq.reserve((n_seq + 8) * 8))) return rc;
-    if ((rc = c->d_spans.reserve((n_spans + 8) * 2))) return rc;
     Frame* d_frames = (Frame*)c->d_frames.p; Block* d_blocks = (Block*)c->d_blocks.p;
     uint32_t* d_sj = (uint32_t*)c->d_seq_jobs.p; uint32_t* d_hj = (uint32_t*)c->d_huf_jobs.p;
-    uint64_t* d_seq = (uint64_t*)c->d_seq.p; uint16_t* d_spans = (uint16_t*)c->d_spans.p;
+    uint64_t* d_seq = (uint64_t*)c->d_seq.p;
 
     k_fill<<<gi, tb, 0, s>>>(d_items, d_infos, d_bases, d_frames, d_blocks, d_sj, d_hj, (uint8_t*)c->d_lit.p, n); mark();
     int launches = 3;
@@ -603,7 +598,7 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
         k_sequences<<<grid, kSeqThreads, kSeqSmem, s>>>(d_blocks, d_sj, (uint32_t)n_sj, d_seq, d_tickets); launches++;
     }
     mark();
-    if (n_sj) { k_records<<<(uint32_t)((n_sj + kRecWarps - 1) / kRecWarps), kRecWarps * 32, 0, s>>>(d_blocks, d_frames, d_sj, (uint32_t)n_sj, d_seq, d_spans); launches++; }
+    if (n_sj) { k_records<<<(uint32_t)((n_sj + kRecWarps - 1) / kRecWarps), kRecWarps * 32, 0, s>>>(d_blocks, d_frames, d_sj, (uint32_t)n_sj, d_seq); launches++; }
     mark();
     signal.fire();
     k_offsets<<<gi, tb, 0, s>>>(d_items, d_infos, d_bases, d_frames, d_blocks, d_outs, n); mark(); launches++;

@@ -19,30 +19,27 @@ static const SeqConsts kConsts = { FZ_LL_BASE, FZ_ML_BASE, FZ_LL_BITS, FZ_ML_BIT
 
 // TEST-ONLY serial restatement of stage B (k_records in fz_decode.cu is warp-parallel CUDA): RAW records ->
 // positional records + span index + block totals, through the same helpers (raw_unpack, rep_update, rec_pack).
-static void records_serial(Block& b, uint32_t block_max, uint64_t* seqs, uint16_t* spans)
+static void records_serial(Block& b, uint32_t block_max, uint64_t* seqs)
 {
     if (b.status) return;
-    uint64_t* sq = seqs + b.seq_base; uint16_t* span = spans + b.span_base;
+    uint64_t* sq = seqs + b.seq_base;
     uint32_t rep0 = off_sym(0), rep1 = off_sym(1), rep2 = off_sym(2), E = 0, LE = 0;
     for (uint32_t i = 0; i < b.nseq; i++) {
         uint32_t ll, ml, ofv;
         bool ok = raw_unpack(sq[i], kConsts, ll, ml, ofv);
         const uint32_t off = rep_update(ofv, ll == 0, rep0, rep1, rep2);
-        const uint32_t Ep = E;
         LE += ll; E += ll + ml;
         if (!ok || (ofv > 3 && off > kOffMax) || LE > b.lit_regen || E > block_max) { b.status = FZG_E_CORRUPT; return; }
         sq[i] = rec_pack(E, LE, off);
-        for (uint32_t s = (Ep + kSpan - 1) / kSpan; s * kSpan < E; s++) span[s] = (uint16_t)i;
     }
     const uint32_t rsize = E + (b.lit_regen - LE);
     if (rsize > block_max) { b.status = FZG_E_CORRUPT; return; }
-    for (uint32_t s = (E + kSpan - 1) / kSpan; s * kSpan < rsize; s++) span[s] = (uint16_t)b.nseq;
     b.rsize = rsize; b.rep_out[0] = rep0; b.rep_out[1] = rep1; b.rep_out[2] = rep2;
 }
 
 // TEST-ONLY serial executor over the records the sequence pass emits (the product's execute pass is the
 // warp-cooperative CUDA kernel k_execute; this checks the record / span / repeat-offset logic on the CPU).
-static void exec_frame_serial(Frame& fr, const Block* blocks, const Item& it, const uint64_t* seqs, const uint16_t* spans)
+static void exec_frame_serial(Frame& fr, const Block* blocks, const Item& it, const uint64_t* seqs)
 {
     uint8_t* const fbase = it.dst + fr.out_off;
     uint64_t done = 0;
@@ -58,16 +55,11 @@ static void exec_frame_serial(Frame& fr, const Block* blocks, const Item& it, co
                 const uint32_t E = rec_e(sq[i]), LE = rec_le(sq[i]);
                 const uint32_t off = off_resolve(rec_off(sq[i]), b.rep_in[0], b.rep_in[1], b.rep_in[2]);
                 const uint32_t ll = LE - LEp, M = S + ll;
-                // span index: entry s names the sequence covering output byte s * kSpan
-                for (uint32_t sp = (S + kSpan - 1) / kSpan; sp * kSpan < E; sp++)
-                    if (spans[b.span_base + sp] != i) { fr.status = FZG_E_CORRUPT; return; }
                 memcpy(out + S, b.lit + LEp, ll);
                 if ((uint64_t)off > done + M) { fr.status = FZG_E_CORRUPT; return; }
                 for (uint32_t q = M; q < E; q++) out[q] = out[(int64_t)q - off];
                 S = E; LEp = LE;
             }
-            for (uint32_t sp = (S + kSpan - 1) / kSpan; sp * kSpan < b.rsize; sp++)
-                if (b.nseq && spans[b.span_base + sp] != b.nseq) { fr.status = FZG_E_CORRUPT; return; }
             memcpy(out + S, b.lit + LEp, b.lit_regen - LEp);
         }
         done += b.rsize;
@@ -84,18 +76,17 @@ extern "C" int fze_decode_batch(size_t n, const void* const* src, const size_t* 
     for (size_t i = 0; i < n; i++) walk_item<false>((uint32_t)i, items[i], infos[i], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     // scan
     std::vector<ItemBase> bases(n);
-    ItemBase run{ 0, 0, 0, 0, 0, 0, 0 };
+    ItemBase run{ 0, 0, 0, 0, 0, 0 };
     for (size_t i = 0; i < n; i++) {
         bases[i] = run;
         run.frame += infos[i].n_frames; run.block += infos[i].n_blocks; run.seq_job += infos[i].n_seq_jobs;
-        run.huf_job += infos[i].n_huf_jobs; run.lit += infos[i].lit_bytes; run.seq += infos[i].n_seq; run.span += infos[i].n_spans;
+        run.huf_job += infos[i].n_huf_jobs; run.lit += infos[i].lit_bytes; run.seq += infos[i].n_seq;
     }
     std::vector<Frame> frames(run.frame + 1);
     std::vector<Block> blocks(run.block + 1);
     std::vector<uint32_t> seq_jobs(run.seq_job + 1), huf_jobs(run.huf_job + 1);
     std::vector<uint8_t> lit(run.lit + 64);
     std::vector<uint64_t> seqs(run.seq + 8);
-    std::vector<uint16_t> spans(run.span + 8);
     // fill
     for (size_t i = 0; i < n; i++) {
         ItemInfo tmp;
@@ -119,7 +110,7 @@ extern "C" int fze_decode_batch(size_t n, const void* const* src, const size_t* 
     for (uint32_t j = 0; j < run.seq_job; j++) {
         Block& b = blocks[seq_jobs[j]];
         seq_chain_thread(blocks.data(), b, kConsts, chain_mem, seqs.data(), b.nseq, 1);
-        records_serial(b, frames[b.frame].block_max, seqs.data(), spans.data());
+        records_serial(b, frames[b.frame].block_max, seqs.data());
     }
     // offsets
     std::vector<ItemOut> outs(n);
@@ -127,7 +118,7 @@ extern "C" int fze_decode_batch(size_t n, const void* const* src, const size_t* 
     // execute
     for (uint32_t f = 0; f < run.frame; f++) {
         if (outs[frames[f].item].fail) continue;
-        exec_frame_serial(frames[f], blocks.data(), items[frames[f].item], seqs.data(), spans.data());
+        exec_frame_serial(frames[f], blocks.data(), items[frames[f].item], seqs.data());
     }
     // checksum
     if (!(flags & FZG_NO_VERIFY_CHECKSUM))
@@ -153,12 +144,12 @@ extern "C" int fze_trace(const void* src, size_t src_len, uint64_t* seq_out, siz
                          uint8_t* lit_out, size_t lit_cap, size_t* n_lit)
 {
     Item it{ (const uint8_t*)src, src_len, nullptr, 0 };
-    ItemInfo info; ItemBase base{ 0, 0, 0, 0, 0, 0, 0 };
+    ItemInfo info; ItemBase base{ 0, 0, 0, 0, 0, 0 };
     walk_item<false>(0, it, info, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     if (info.walk_status) return info.walk_status;
     std::vector<Frame> frames(info.n_frames + 1); std::vector<Block> blocks(info.n_blocks + 1);
     std::vector<uint32_t> sj(info.n_seq_jobs + 1), hj(info.n_huf_jobs + 1);
-    std::vector<uint8_t> lit(info.lit_bytes + 64); std::vector<uint64_t> seqs(info.n_seq + 8); std::vector<uint16_t> spans(info.n_spans + 8);
+    std::vector<uint8_t> lit(info.lit_bytes + 64); std::vector<uint64_t> seqs(info.n_seq + 8);
     ItemInfo tmp;
     walk_item<true>(0, it, tmp, &base, frames.data(), blocks.data(), sj.data(), hj.data(), lit.data());
     std::vector<uint16_t> table(1 << kHufLogMax);
@@ -175,7 +166,7 @@ extern "C" int fze_trace(const void* src, size_t src_len, uint64_t* seq_out, siz
     for (uint32_t j = 0; j < info.n_seq_jobs; j++) {
         Block& b = blocks[sj[j]];
         seq_chain_thread(blocks.data(), b, kConsts, chain_mem, seqs.data(), b.nseq, 1);
-        records_serial(b, frames[b.frame].block_max, seqs.data(), spans.data());
+        records_serial(b, frames[b.frame].block_max, seqs.data());
     }
     it.dst_cap = ~0ull;
     ItemOut io; offsets_item(it, info, base, frames.data(), blocks.data(), io);      // resolves every block's starting history
