@@ -123,9 +123,9 @@ static inline size_t al16(size_t v) { return (v + 15) & ~(size_t)15; }
 
 // ---------------------------------------------------------------------------------- batched decode / encode
 // Device-resident batches run as one launch sequence.  Host-resident batches are cut into chunks of
-// ~1 GiB of output and pipelined on three streams: while chunk c is decoded, chunk c+1 crosses PCIe
+// ~2 GiB of (input + output) and pipelined on three streams: while chunk c is decoded, chunk c+1 crosses PCIe
 // host->device and chunk c-1 device->host, so the call costs about max(PCIe, kernels) instead of their sum.
-static constexpr size_t kChunkOutBytes = 1ull << 30;
+static constexpr size_t kChunkOutBytes = 2ull << 30;     // large enough that a chunk's kernels are throughput- not latency-bound
 
 static int run_batch(bool encode, int device, size_t n, const void* const* src, const size_t* src_len, void* const* dst,
                      const size_t* dst_cap, size_t* dst_len, int* status, int flags, int level, size_t chunk)

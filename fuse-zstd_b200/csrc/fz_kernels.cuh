@@ -80,10 +80,12 @@ FZ_HD uint64_t xx_lane(const uint8_t* p, uint64_t len, uint32_t j)   // accumula
     const uint8_t* q = p + 8 * j;
     if (((uintptr_t)p & 7) == 0) {
         uint64_t s = 0;
-        for (; s + 4 <= stripes; s += 4) {               // four loads in flight per thread
-            const uint64_t a = *(const uint64_t*)(q + 32 * s), b = *(const uint64_t*)(q + 32 * s + 32),
-                           c = *(const uint64_t*)(q + 32 * s + 64), d = *(const uint64_t*)(q + 32 * s + 96);
-            acc = xx_round(acc, a); acc = xx_round(acc, b); acc = xx_round(acc, c); acc = xx_round(acc, d);
+        for (; s + 16 <= stripes; s += 16) {             // a serial multiply chain fed from HBM: sixteen loads in flight per thread
+            uint64_t in[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) in[k] = *(const uint64_t*)(q + 32 * (s + k));
+#pragma unroll
+            for (int k = 0; k < 16; k++) acc = xx_round(acc, in[k]);
         }
         for (; s < stripes; s++) acc = xx_round(acc, *(const uint64_t*)(q + 32 * s));
     } else {
