@@ -227,6 +227,7 @@ def run_b200(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     codec = importlib.import_module("fuse-zstd_b200.codec")
+    shard = importlib.import_module("fuse-zstd_b200.shard")
     if not os.path.exists(codec.SO):
         codec.build()
     codec.init([local_rank])
@@ -234,7 +235,7 @@ def run_b200(args, rank, local_rank, world):
     threads = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
     F, S = args.files, args.file_size
     t0 = time.time()
-    w = Workload(rank * F, F, S, args.level, threads)
+    w = Workload(shard.files_for_rank(rank, F)[0], F, S, args.level, threads)
     log("[rank %d] corpus: %d files, ratio %.3f, gen %.1fs compress %.1fs (%d threads)" % (
         rank, F, w.plain_bytes / w.comp_bytes, w.gen_s, w.cmp_s, threads))
 
@@ -279,8 +280,7 @@ def run_b200(args, rank, local_rank, world):
     barrier()
     clocks = sampler.result()
     ms = ev0.elapsed_time(ev1) / args.steps
-    if world > 1:
-        tt = torch.tensor([ms], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
+    ms = shard.max_over_ranks(ms, "cuda")
 
     # ---- e2e: pinned host buffers through the same C ABI call
     e2e = None
@@ -304,8 +304,7 @@ def run_b200(args, rank, local_rank, world):
             codec.decode_batch_ptrs(dev, hsp, w.comp_len[:E], hdp, dc[:E], 0)
         torch.cuda.synchronize()
         e_ms = (time.perf_counter() - t_0) * 1e3 / reps
-        if world > 1:
-            tt = torch.tensor([e_ms], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); e_ms = float(tt.item())
+        e_ms = shard.max_over_ranks(e_ms, "cuda")
         e2e = {"value": round(world * E * S / 1e9 / (e_ms / 1e3), 3), "unit": UNIT,
                "h2d_bytes_per_step": int(w.comp_len[:E].sum()), "d2h_bytes_per_step": E * S,
                "files_per_step_per_gpu": E, "ms_per_step": round(e_ms, 3), "timer": "host wall clock around the blocking C-ABI call"}
