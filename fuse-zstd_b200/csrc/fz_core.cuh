@@ -662,6 +662,10 @@ struct SeqBits {
         if (fa >= 0 && fa + 256 > wa) { ring_fetch(ring + ((rb + (uint32_t)fa) & 255u), cmin + fa); fa -= 16; }
         ring_commit();
     }
+    FZ_HD void fill()                            // every free slot of the ring
+    {
+        while (fa >= 0 && fa + 256 > wa) { ring_fetch(ring + ((rb + (uint32_t)fa) & 255u), cmin + fa); fa -= 16; }
+    }
     FZ_HD uint32_t pop()
     {
         uint32_t w = *(const uint32_t*)(ring + ((rb + (uint32_t)wa) & 255u));
@@ -757,22 +761,23 @@ FZ_HD void store_rec_pair(uint64_t* at, uint64_t a, uint64_t b)   // `at` is 16-
 // ------------------------------------------------------------------ sequence pass, stage A: the FSE chain
 // The three-state FSE chain is the only inherently serial part of a block, so stage A does nothing
 // else: one thread per block walks the backward bitstream and leaves one 8-byte RAW record per
-// sequence; everything that can be done for many sequences at once (extra bits -> values, running
-// positions, repeat offsets, span index) is stage B (warp per block, fz_decode.cu).
+// sequence; everything that can be done for many sequences at once (states -> symbols, extra bits ->
+// values, running positions, repeat offsets) is stage B (warp per block, fz_decode.cu).
 //
-// Shared memory per stream (3840 bytes, 60 streams per SM):
-//   uint16 cLL[512] | uint16 cML[512] | uint16 cOF[256] | uint8 yLL[512] | uint8 yML[512] | ring[256]
+// Shared memory per stream (2816 bytes, 82 streams per SM):
+//   uint16 cLL[512] | uint16 cML[512] | uint16 cOF[256] | ring[256]
 // A chain cell is 16 bits: J[0:10) | extra[10:15), where J encodes (baseline, nbBits) jointly as
 // ((baseline >> nb) << 1 | 1) << nb -- nb = ctz(J), baseline = (J & (J - 1)) >> 1 -- and `extra` is the
-// number of extra bits of the cell's symbol (for offsets that IS the symbol).  The LL / ML symbols
-// themselves are only needed by stage B and sit in the byte tables yLL / yML, off the chain.
+// number of extra bits of the cell's symbol (for offsets that IS the symbol).  The LL / ML symbols are
+// not kept here: the RAW record carries the STATES, and stage B maps state -> symbol with its own
+// copy of the (cheap) symbol spread.
 //
-// RAW record, fast form (every field of the sequence fits in the 32-bit window x):
-//   x[0:32) | symLL[32:38) | symML[38:44) | symOF[44:49) | 0
+// RAW record, fast form (the extra bits of the sequence are the top bits of the 32-bit window x):
+//   x[0:32) | stateLL[32:41) | stateML[41:50) | offset code[50:55) | 0
 // RAW record, slow form (long lengths / offsets, decoded field by field):
 //   ll[0:18) | (ml - 3)[18:35) | offset_value[35:63) | 1[63]
 constexpr uint32_t kChainCellsLL = 512, kChainCellsML = 512, kChainCellsOF = 256;
-constexpr uint32_t kChainBytes = (kChainCellsLL + kChainCellsML + kChainCellsOF) * 2 + kChainCellsLL + kChainCellsML + 256;
+constexpr uint32_t kChainBytes = (kChainCellsLL + kChainCellsML + kChainCellsOF) * 2 + 256;
 
 FZ_HD uint32_t chain_pack(uint32_t base, uint32_t nb, uint32_t extra) { return ((((base >> nb) << 1) | 1u) << nb) | (extra << 10); }
 FZ_HD uint32_t ctz32(uint32_t v)
@@ -784,76 +789,145 @@ FZ_HD uint32_t ctz32(uint32_t v)
 #endif
 }
 
-// Same construction as build_fse_table, chain-cell output.  ysym (1 << log bytes) receives the symbol of
-// every cell (used as the spread buffer first); it may be nullptr for offsets only if `spread` is given.
-FZ_HD int build_chain_table(uint16_t* cell, uint8_t* ysym, const int16_t* norm, int n_sym, int log, const uint8_t* extra_bits, uint16_t* cnt)
+// RFC 8878 4.1.1 symbol spread: tab[cell] = symbol for all 1 << log cells; cnt[s] = first `next` value of symbol s
+// (cnt may be nullptr).  Returns 0 or -1.
+template <class T>
+FZ_HD int fse_spread(T* tab, const int16_t* norm, int n_sym, int log, uint16_t* cnt)
 {
     const int size = 1 << log; int high = size - 1;
     for (int s = 0; s < n_sym; s++) {
-        if (norm[s] == -1) { ysym[high--] = (uint8_t)s; cnt[s] = 1; }
-        else cnt[s] = (uint16_t)norm[s];
+        if (norm[s] == -1) { tab[high--] = (T)s; if (cnt) cnt[s] = 1; }
+        else if (cnt) cnt[s] = (uint16_t)norm[s];
     }
     const int step = (size >> 1) + (size >> 3) + 3, mask = size - 1; int pos = 0;
     for (int s = 0; s < n_sym; s++) {
         for (int i = 0; i < norm[s]; i++) {
-            ysym[pos] = (uint8_t)s;
+            tab[pos] = (T)s;
             do { pos = (pos + step) & mask; } while (pos > high);
         }
     }
-    if (pos != 0) return -1;
-    for (int u = 0; u < size; u++) {
-        const uint32_t s = ysym[u];
-        const uint32_t nx = cnt[s]++;
+    return pos == 0 ? 0 : -1;
+}
+
+// Where table `which` (0 LL, 1 OF, 2 ML) of block b is described (its own sequences section, or -- Repeat mode --
+// the section of the block recorded in b.*_src) and how.  p / n on entry: the current position in b's section.
+struct TableSrc { int mode; const uint8_t* p; uint32_t n; bool own; };
+FZ_HD int resolve_table(const Block* blocks, const Block& b, int which, const uint8_t* p, uint32_t n, TableSrc& t)
+{
+    t.mode = (b.modes >> (6 - 2 * which)) & 3; t.p = p; t.n = n; t.own = t.mode != 3;
+    if (!t.own) {
+        const int32_t src = which == 0 ? b.ll_src : (which == 1 ? b.of_src : b.ml_src);
+        if (src < 0) return -1;
+        t.mode = locate_table(blocks[src], which, t.p, t.n);
+        if (t.mode < 0 || t.mode == 3) return -1;
+    }
+    return 0;
+}
+// Normalised counts of a Predefined / FSE_Compressed table.  norm_buf: 64 int16 of scratch.  used = description bytes.
+FZ_HD int table_norm(const TableSrc& t, int which, const SeqConsts& K, int16_t* norm_buf, const int16_t*& norm, int& ns, int& log, uint32_t& used)
+{
+    used = 0;
+    if (t.mode == 0) {
+        norm = which == 0 ? K.ll_def : (which == 1 ? K.of_def : K.ml_def);
+        ns = which == 0 ? 36 : (which == 1 ? 29 : 53); log = which == 1 ? 5 : 6;
+        return 0;
+    }
+    const int max_sym = which == 0 ? kMaxLL : (which == 1 ? kMaxOF : kMaxML);
+    const int max_log = which == 0 ? kLLLog : (which == 1 ? kOFLog : kMLLog);
+    const int u = read_ncount(t.p, t.n, max_sym, max_log, norm_buf, ns, log);
+    if (u < 0) return -1;
+    norm = norm_buf; used = (uint32_t)u;
+    return 0;
+}
+
+// Stage A: chain cells of table `which`.  scratch = 128 uint16 (normalised counts, then per-symbol counters).
+FZ_HD int build_chain_seq_table(const Block* blocks, const Block& b, int which, const uint8_t* p, uint32_t n,
+                                const SeqConsts& K, uint16_t* cell, int& log, uint32_t& used, uint16_t* scratch)
+{
+    const int max_sym = which == 0 ? kMaxLL : (which == 1 ? kMaxOF : kMaxML);
+    const uint8_t* extra = which == 0 ? K.ll_bits : (which == 2 ? K.ml_bits : nullptr);
+    TableSrc t; used = 0;
+    if (resolve_table(blocks, b, which, p, n, t) != 0) return -1;
+    if (t.mode == 1) {
+        if (t.n < 1 || t.p[0] > max_sym) return -1;
+        const uint32_t sy = t.p[0];
+        cell[0] = (uint16_t)chain_pack(0, 0, extra ? extra[sy] : sy); log = 0;
+        if (t.own) used = 1;
+        return 0;
+    }
+    const int16_t* norm; int ns; uint32_t u; uint16_t* cnt = scratch + 64;
+    if (table_norm(t, which, K, (int16_t*)scratch, norm, ns, log, u) != 0) return -1;
+    if (t.own) used = u;
+    if (fse_spread(cell, norm, ns, log, cnt) != 0) return -1;     // the cells hold the symbols first ...
+    const int size = 1 << log;
+    for (int c = 0; c < size; c++) {                               // ... and are converted in place
+        const uint32_t sy = cell[c];
+        const uint32_t nx = cnt[sy]++;
         const uint32_t nb = (uint32_t)(log - highbit(nx));
-        cell[u] = (uint16_t)chain_pack((nx << nb) - (uint32_t)size, nb, extra_bits ? extra_bits[s] : s);
+        cell[c] = (uint16_t)chain_pack((nx << nb) - (uint32_t)size, nb, extra ? extra[sy] : sy);
     }
     return 0;
 }
 
-// Chain tables of block b for table `which` (0 LL, 1 OF, 2 ML), resolving Repeat through b.*_src.
-FZ_HD int build_chain_seq_table(const Block* blocks, const Block& b, int which, const uint8_t* p, uint32_t n,
-                                const SeqConsts& K, uint16_t* cell, uint8_t* ysym, int& log, uint32_t& used, uint16_t* scratch)
+// Stage B: state -> symbol maps of the LL and ML tables of block b (yLL / yML: 512 bytes each; norm_buf: 64 int16).
+FZ_HD int build_symbol_maps(const Block* blocks, const Block& b, const SeqConsts& K, uint8_t* yLL, uint8_t* yML, int16_t* norm_buf)
 {
-    int16_t* norm = (int16_t*)scratch; uint16_t* cnt = scratch + 64;
-    int mode = (b.modes >> (6 - 2 * which)) & 3;
-    const int max_sym = which == 0 ? kMaxLL : (which == 1 ? kMaxOF : kMaxML);
-    const int max_log = which == 0 ? kLLLog : (which == 1 ? kOFLog : kMLLog);
-    const uint8_t* extra = which == 0 ? K.ll_bits : (which == 2 ? K.ml_bits : nullptr);
-    const bool own = mode != 3;
-    used = 0;
-    if (!own) {
-        int32_t src = which == 0 ? b.ll_src : (which == 1 ? b.of_src : b.ml_src);
-        if (src < 0) return -1;
-        mode = locate_table(blocks[src], which, p, n);
-        if (mode < 0 || mode == 3) return -1;
+    const uint8_t* p = b.src + b.seq_hdr; uint32_t n = b.csize - b.seq_hdr;
+    for (int which = 0; which < 3; which++) {                      // stream order: LL, OF, ML (OF only to find where ML starts)
+        uint8_t* y = which == 0 ? yLL : yML;
+        TableSrc t;
+        if (resolve_table(blocks, b, which, p, n, t) != 0) return -1;
+        uint32_t used = 0;
+        if (t.mode == 1) {
+            if (t.n < 1) return -1;
+            if (which != 1) y[0] = t.p[0];
+            used = 1;
+        } else {
+            const int16_t* norm; int ns, log;
+            if (table_norm(t, which, K, norm_buf, norm, ns, log, used) != 0) return -1;
+            if (which != 1 && fse_spread(y, norm, ns, log, (uint16_t*)nullptr) != 0) return -1;
+        }
+        if (t.own) { p += used; n -= used; }
     }
-    if (mode == 0) {
-        const int16_t* def = which == 0 ? K.ll_def : (which == 1 ? K.of_def : K.ml_def);
-        log = which == 1 ? 5 : 6;
-        return build_chain_table(cell, ysym, def, which == 0 ? 36 : (which == 1 ? 29 : 53), log, extra, cnt);
-    }
-    if (mode == 1) {
-        if (n < 1 || p[0] > max_sym) return -1;
-        const uint32_t sy = p[0];
-        cell[0] = (uint16_t)chain_pack(0, 0, extra ? extra[sy] : sy); ysym[0] = (uint8_t)sy; log = 0;
-        if (own) used = 1;
-        return 0;
-    }
-    int ns;
-    const int u = read_ncount(p, n, max_sym, max_log, norm, ns, log);
-    if (u < 0) return -1;
-    if (own) used = (uint32_t)u;
-    return build_chain_table(cell, ysym, norm, ns, log, extra, cnt);
+    return 0;
 }
 
-FZ_HD uint64_t raw_pack_fast(uint32_t x, uint32_t yll, uint32_t yml, uint32_t yof) { return (uint64_t)x | ((uint64_t)(yll | (yml << 6) | (yof << 12)) << 32); }
+// Symbol of cell `state` of table `which` of block b, recomputed from the table description (no table in memory).
+// Only for the rare sequence whose extra bits do not fit one 32-bit window (stage A keeps no symbols).  -1 on error.
+FZ_HD int symbol_of_state(const Block* blocks, const Block& b, int which, uint32_t state, const SeqConsts& K)
+{
+    const uint8_t* p = b.src + b.seq_hdr; uint32_t n = b.csize - b.seq_hdr;
+    int16_t norm_buf[64];
+    for (int w = 0; w <= which; w++) {
+        TableSrc t;
+        if (resolve_table(blocks, b, w, p, n, t) != 0) return -1;
+        uint32_t used = 0; const int16_t* norm = nullptr; int ns = 0, log = 0;
+        if (t.mode == 1) { if (t.n < 1) return -1; if (w == which) return t.p[0]; used = 1; }
+        else {
+            if (table_norm(t, w, K, norm_buf, norm, ns, log, used) != 0) return -1;
+            if (w == which) {
+                const int size = 1 << log; int high = size - 1;
+                for (int sy = 0; sy < ns; sy++) if (norm[sy] == -1) { if ((uint32_t)high == state) return sy; high--; }
+                const int step = (size >> 1) + (size >> 3) + 3, mask = size - 1; int pos = 0;
+                for (int sy = 0; sy < ns; sy++)
+                    for (int i = 0; i < norm[sy]; i++) { if ((uint32_t)pos == state) return sy; do { pos = (pos + step) & mask; } while (pos > high); }
+                return -1;
+            }
+        }
+        if (t.own) { p += used; n -= used; }
+    }
+    return -1;
+}
+
+FZ_HD uint64_t raw_pack_fast(uint32_t x, uint32_t sll, uint32_t sml, uint32_t ofc) { return (uint64_t)x | ((uint64_t)(sll | (sml << 9) | (ofc << 18)) << 32); }
 FZ_HD uint64_t raw_pack_slow(uint32_t ll, uint32_t ml, uint32_t ofv) { return (uint64_t)(ll & 0x3FFFFu) | ((uint64_t)((ml - 3) & 0x1FFFFu) << 18) | ((uint64_t)(ofv & 0xFFFFFFFu) << 35) | (1ull << 63); }
-// RAW -> (literal length, match length, offset value).  Returns false when the offset code is beyond any legal window.
-FZ_HD bool raw_unpack(uint64_t r, const SeqConsts& K, uint32_t& ll, uint32_t& ml, uint32_t& ofv)
+// RAW -> (literal length, match length, offset value), with the block's state -> symbol maps.  Returns false when
+// the offset code is beyond any legal window.
+FZ_HD bool raw_unpack(uint64_t r, const SeqConsts& K, const uint8_t* yLL, const uint8_t* yML, uint32_t& ll, uint32_t& ml, uint32_t& ofv)
 {
     if (r >> 63) { ll = (uint32_t)r & 0x3FFFFu; ml = ((uint32_t)(r >> 18) & 0x1FFFFu) + 3; ofv = (uint32_t)(r >> 35) & 0xFFFFFFFu; return true; }
     const uint32_t x = (uint32_t)r, y = (uint32_t)(r >> 32);
-    const uint32_t yll = y & 63, yml = (y >> 6) & 63, yof = (y >> 12) & 31;
+    const uint32_t yll = yLL[y & 511], yml = yML[(y >> 9) & 511], yof = (y >> 18) & 31;
     const uint32_t ofb = yof, mlb = K.ml_bits[yml], llb = K.ll_bits[yll];
     ofv = (1u << yof) + shr_c(x, 32 - ofb);
     ml = K.ml_base[yml] + shr_c(shl_c(x, ofb), 32 - mlb);
@@ -877,27 +951,36 @@ FZ_HD uint32_t rep_update(uint32_t ofv, bool ll0, uint32_t& rep0, uint32_t& rep1
     return off;
 }
 
+// RAW slow form for a sequence whose extra bits exceed one window: the symbols are recovered from the description.
+FZ_HD uint64_t raw_slow(const Block* blocks, const Block& b, const SeqConsts& K, uint32_t sLL, uint32_t sML, uint32_t ofb,
+                        uint32_t ofx, uint32_t mlx, uint32_t llx, int& st)
+{
+    const int yl = symbol_of_state(blocks, b, 0, sLL, K), ym = symbol_of_state(blocks, b, 2, sML, K);
+    if (yl < 0 || ym < 0 || yl > kMaxLL || ym > kMaxML) { st = FZG_E_CORRUPT; return 0; }
+    // an offset code beyond any legal window is kept visible for stage B (it tests the value)
+    return raw_pack_slow(K.ll_base[yl] + llx, K.ml_base[ym] + mlx, ofb > 27 ? 0xFFFFFFFu : (1u << ofb) + ofx);
+}
+
 // Stage A.  `mem` = this stream's kChainBytes of shared memory.  Writes nseq RAW records at `out`.
 // SIMT shape: the lanes of a warp run different blocks, so the loop must stay in lockstep or the warp
 // degenerates into serial threads: single exit, the table build (data-dependent control flow) is
 // fenced off with a warp barrier, and the loop runs a warp-uniform number of iterations (`bound` =
-// the largest nseq among the lanes in `mask`), each lane masking itself out when its block is done.
+// the largest nseq - 1 among the lanes in `mask`), each lane masking itself out when its block is
+// done.  The last sequence of a block updates no state; it is decoded after the loop, by all lanes at once.
 FZ_HD int decode_sequences_chain(const Block* blocks, const Block& b, const SeqConsts& K, uint8_t* mem,
                                  uint64_t* out, uint32_t bound, uint32_t mask)
 {
     uint16_t* cLL = (uint16_t*)mem; uint16_t* cML = cLL + kChainCellsLL; uint16_t* cOF = cML + kChainCellsML;
-    uint8_t* yLL = (uint8_t*)(cOF + kChainCellsOF); uint8_t* yML = yLL + kChainCellsLL;
-    uint16_t* scratch = (uint16_t*)(yML + kChainCellsML);             // 256 bytes: table-build scratch, then the bitstream ring
+    uint16_t* scratch = cOF + kChainCellsOF;                          // 256 bytes: table-build scratch, then the bitstream ring
     int st = 0;
     int logLL = 0, logOF = 0, logML = 0;
     SeqBits br;
     uint32_t sLL = 0, sOF = 0, sML = 0;
     {
         const uint8_t* p = b.src + b.seq_hdr; uint32_t n = b.csize - b.seq_hdr; uint32_t used = 0;
-        if (build_chain_seq_table(blocks, b, 0, p, n, K, cLL, yLL, logLL, used, scratch) != 0) st = FZG_E_CORRUPT;
-        // the offset table's symbol bytes are not kept: yML (not built yet) serves as its spread buffer
-        if (!st) { p += used; n -= used; if (build_chain_seq_table(blocks, b, 1, p, n, K, cOF, yML, logOF, used, scratch) != 0) st = FZG_E_CORRUPT; }
-        if (!st) { p += used; n -= used; if (build_chain_seq_table(blocks, b, 2, p, n, K, cML, yML, logML, used, scratch) != 0) st = FZG_E_CORRUPT; }
+        if (build_chain_seq_table(blocks, b, 0, p, n, K, cLL, logLL, used, scratch) != 0) st = FZG_E_CORRUPT;
+        if (!st) { p += used; n -= used; if (build_chain_seq_table(blocks, b, 1, p, n, K, cOF, logOF, used, scratch) != 0) st = FZG_E_CORRUPT; }
+        if (!st) { p += used; n -= used; if (build_chain_seq_table(blocks, b, 2, p, n, K, cML, logML, used, scratch) != 0) st = FZG_E_CORRUPT; }
         if (!st) { p += used; n -= used; if (br.init(p, n, (uint8_t*)scratch) != 0) st = FZG_E_CORRUPT; }
         if (!st) {
             br.refill(); br.refill();
@@ -908,44 +991,57 @@ FZ_HD int decode_sequences_chain(const Block* blocks, const Block& b, const SeqC
         }
     }
     const uint32_t nseq = b.nseq;
-    const uint32_t live = st ? 0 : nseq;                // this lane's trip count
-    uint64_t held = 0;
+    const uint32_t live = st ? 0 : nseq - 1;            // this lane's trip count (nseq >= 1 for a sequence job)
     FZ_SYNCWARP(mask);
     for (uint32_t i = 0; i < bound; i++) {
+        if ((i & 3) == 0) {                              // keep the ring full: <= 44 bytes are consumed between two visits
+            if (i < live) br.fill();
+            ring_commit(); ring_wait<2>();               // the words consumed now were fetched >= 5 visits ago
+        }
         if (i < live) {
             const uint32_t cl = cLL[sLL], co = cOF[sOF], cm = cML[sML];
-            const uint32_t yl = yLL[sLL], ym = yML[sML];              // off the chain: only stage B wants the symbols
             const uint32_t jl = cl & 1023u, jo = co & 1023u, jm = cm & 1023u;
             const uint32_t llb = cl >> 10, ofb = co >> 10, mlb = cm >> 10;
-            const bool more = i + 1 < nseq;
-            const uint32_t nLL = more ? ctz32(jl) : 0, nML = more ? ctz32(jm) : 0, nOF = more ? ctz32(jo) : 0;
+            const uint32_t nLL = ctz32(jl), nML = ctz32(jm), nOF = ctz32(jo);
             const uint32_t a3 = ofb + mlb + llb, a4 = a3 + nLL, a5 = a4 + nML, need = a5 + nOF;
-            br.top_up(); ring_wait<8>();          // the word consumed now was fetched >= 20 iterations ago
             br.refill();
             uint64_t raw;
             if (need <= 32) {                     // common case: every field of this sequence sits in `hi`
                 const uint32_t x = br.hi;
+                raw = raw_pack_fast(x, sLL, sML, ofb);
                 sLL = ((jl & (jl - 1)) >> 1) + shr_c(shl_c(x, a3), 32 - nLL);
                 sML = ((jm & (jm - 1)) >> 1) + shr_c(shl_c(x, a4), 32 - nML);
                 sOF = ((jo & (jo - 1)) >> 1) + shr_c(shl_c(x, a5), 32 - nOF);
                 br.skip(need);
-                raw = raw_pack_fast(x, yl, ym, ofb);
             } else {                              // long offsets / lengths: field by field
+                const uint32_t x = br.hi;
                 const uint32_t ofx = br.read(ofb);
                 br.refill();
                 const uint32_t mlx = br.read(mlb), llx = br.read(llb);
                 br.refill();
+                raw = a3 <= 32 ? raw_pack_fast(x, sLL, sML, ofb) : raw_slow(blocks, b, K, sLL, sML, ofb, ofx, mlx, llx, st);
                 sLL = ((jl & (jl - 1)) >> 1) + br.read(nLL);
                 sML = ((jm & (jm - 1)) >> 1) + br.read(nML);
                 sOF = ((jo & (jo - 1)) >> 1) + br.read(nOF);
-                // an offset code beyond any legal window is kept visible for stage B (it tests the value)
-                raw = raw_pack_slow(K.ll_base[yl] + llx, K.ml_base[ym] + mlx, ofb > 27 ? 0xFFFFFFFu : (1u << ofb) + ofx);
             }
-            if (i & 1) store_rec_pair(out + i - 1, held, raw); else held = raw;
+            out[i] = raw;
         }
     }
-    if (!st && br.left != 0) st = FZG_E_CORRUPT;
-    if (!st && (nseq & 1)) out[nseq - 1] = held;
+    ring_wait<0>();
+    if (!st) {                                    // the last sequence: its three fields, no state update
+        br.fill(); ring_commit(); ring_wait<0>();
+        const uint32_t cl = cLL[sLL], co = cOF[sOF], cm = cML[sML];
+        const uint32_t llb = cl >> 10, ofb = co >> 10, mlb = cm >> 10;
+        br.refill();
+        if (ofb + mlb + llb <= 32) { out[nseq - 1] = raw_pack_fast(br.hi, sLL, sML, ofb); br.skip(ofb + mlb + llb); }
+        else {
+            const uint32_t ofx = br.read(ofb);
+            br.refill();
+            const uint32_t mlx = br.read(mlb), llx = br.read(llb);
+            out[nseq - 1] = raw_slow(blocks, b, K, sLL, sML, ofb, ofx, mlx, llx, st);
+        }
+        if (br.left != 0) st = FZG_E_CORRUPT;
+    }
     return st;
 }
 

@@ -127,11 +127,11 @@ __global__ void __launch_bounds__(kLitThreads, 1) k_literals(Block* blocks, cons
 // ------------------------------------------------------------------ sequences, stage A: the FSE chain
 // One thread per block (the FSE state chain is serial), one CTA per SM.  What bounds this stage is the
 // latency of that chain times the number of chains an SM can hold, and the latter is set by shared
-// memory: a stream needs 3840 bytes (16-bit chain cells + symbol bytes + bitstream ring), so 60 streams
-// fit in the 227 KB of an SM.  A warp carries only a few streams (data-dependent branches cost little
+// memory: a stream needs 2816 bytes (16-bit chain cells + bitstream ring), so 82 streams fit in the
+// 227 KB of an SM.  A warp carries only a few streams (data-dependent branches cost little
 // that way, and the SM has issue slots to spare); each warp draws its next batch of blocks from a ticket.
 #ifndef FZ_SEQ_STREAMS
-#define FZ_SEQ_STREAMS 60
+#define FZ_SEQ_STREAMS 82
 #endif
 constexpr int kSeqStreams = FZ_SEQ_STREAMS;
 #ifndef FZ_SEQ_LANES
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) k_sequences(Block* blocks, con
         const bool on = lane < lanes && job < n_jobs;
         Block* b = on ? &blocks[jobs[job]] : nullptr;
         const uint32_t mask = __ballot_sync(0xFFFFFFFFu, on);
-        const uint32_t bound = __reduce_max_sync(0xFFFFFFFFu, on ? b->nseq : 0u);
+        const uint32_t bound = __reduce_max_sync(0xFFFFFFFFu, on ? b->nseq - 1 : 0u);     // nseq >= 1 for a sequence job
         if (on) seq_chain_thread(blocks, *b, K, mine, seqs, bound, mask);
         __syncwarp();
     }
@@ -185,13 +185,20 @@ __global__ void __launch_bounds__(kRecWarps * 32) k_records(Block* blocks, const
                                                             uint64_t* seqs)
 {
     __shared__ SeqConsts K;
+    __shared__ uint8_t s_y[kRecWarps][2][512];               // state -> symbol maps of the block (LL, ML)
+    __shared__ int16_t s_norm[kRecWarps][64];
+    __shared__ int s_err[kRecWarps];
     for (uint32_t i = threadIdx.x; i < sizeof(SeqConsts) / 4; i += blockDim.x) ((uint32_t*)&K)[i] = ((const uint32_t*)&c_seq_consts)[i];
     __syncthreads();
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t job = blockIdx.x * kRecWarps + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t job = blockIdx.x * kRecWarps + warp;
     if (job >= n_jobs) return;
     Block& b = blocks[jobs[job]];
     if (b.status) return;
+    const uint8_t* yLL = s_y[warp][0]; const uint8_t* yML = s_y[warp][1];
+    if (lane == 0) s_err[warp] = build_symbol_maps(blocks, b, K, s_y[warp][0], s_y[warp][1], s_norm[warp]);
+    __syncwarp();
+    if (s_err[warp]) { if (lane == 0) b.status = FZG_E_CORRUPT; return; }
     const uint32_t nseq = b.nseq, lit_regen = b.lit_regen, block_max = frames[b.frame].block_max;
     uint64_t* sq = seqs + b.seq_base;
     uint32_t rep0 = off_sym(0), rep1 = off_sym(1), rep2 = off_sym(2);      // history, warp-uniform
@@ -200,7 +207,7 @@ __global__ void __launch_bounds__(kRecWarps * 32) k_records(Block* blocks, const
         const uint32_t i = g + lane; const bool valid = i < nseq;
         const uint32_t nv = min(32u, nseq - g);
         uint32_t ll = 0, ml = 0, ofv = 4; bool ok = true;
-        if (valid) ok = raw_unpack(sq[i], K, ll, ml, ofv);
+        if (valid) ok = raw_unpack(sq[i], K, yLL, yML, ll, ml, ofv);
         const uint32_t LE = LEbase + warp_scan_incl(ll, lane), E = Ebase + warp_scan_incl(ll + ml, lane);
         // ---- repeat offsets
         uint32_t off = ofv - 3;

@@ -19,14 +19,16 @@ static const SeqConsts kConsts = { FZ_LL_BASE, FZ_ML_BASE, FZ_LL_BITS, FZ_ML_BIT
 
 // TEST-ONLY serial restatement of stage B (k_records in fz_decode.cu is warp-parallel CUDA): RAW records ->
 // positional records + span index + block totals, through the same helpers (raw_unpack, rep_update, rec_pack).
-static void records_serial(Block& b, uint32_t block_max, uint64_t* seqs)
+static void records_serial(const Block* blocks, Block& b, uint32_t block_max, uint64_t* seqs)
 {
     if (b.status) return;
     uint64_t* sq = seqs + b.seq_base;
+    static uint8_t yLL[512], yML[512]; int16_t norm_buf[64];
+    if (build_symbol_maps(blocks, b, kConsts, yLL, yML, norm_buf) != 0) { b.status = FZG_E_CORRUPT; return; }
     uint32_t rep0 = off_sym(0), rep1 = off_sym(1), rep2 = off_sym(2), E = 0, LE = 0;
     for (uint32_t i = 0; i < b.nseq; i++) {
         uint32_t ll, ml, ofv;
-        bool ok = raw_unpack(sq[i], kConsts, ll, ml, ofv);
+        bool ok = raw_unpack(sq[i], kConsts, yLL, yML, ll, ml, ofv);
         const uint32_t off = rep_update(ofv, ll == 0, rep0, rep1, rep2);
         LE += ll; E += ll + ml;
         if (!ok || (ofv > 3 && off > kOffMax) || LE > b.lit_regen || E > block_max) { b.status = FZG_E_CORRUPT; return; }
@@ -109,8 +111,8 @@ extern "C" int fze_decode_batch(size_t n, const void* const* src, const size_t* 
     alignas(16) static uint8_t chain_mem[kChainBytes];
     for (uint32_t j = 0; j < run.seq_job; j++) {
         Block& b = blocks[seq_jobs[j]];
-        seq_chain_thread(blocks.data(), b, kConsts, chain_mem, seqs.data(), b.nseq, 1);
-        records_serial(b, frames[b.frame].block_max, seqs.data());
+        seq_chain_thread(blocks.data(), b, kConsts, chain_mem, seqs.data(), b.nseq - 1, 1);
+        records_serial(blocks.data(), b, frames[b.frame].block_max, seqs.data());
     }
     // offsets
     std::vector<ItemOut> outs(n);
@@ -165,8 +167,8 @@ extern "C" int fze_trace(const void* src, size_t src_len, uint64_t* seq_out, siz
     alignas(16) static uint8_t chain_mem[kChainBytes];
     for (uint32_t j = 0; j < info.n_seq_jobs; j++) {
         Block& b = blocks[sj[j]];
-        seq_chain_thread(blocks.data(), b, kConsts, chain_mem, seqs.data(), b.nseq, 1);
-        records_serial(b, frames[b.frame].block_max, seqs.data());
+        seq_chain_thread(blocks.data(), b, kConsts, chain_mem, seqs.data(), b.nseq - 1, 1);
+        records_serial(blocks.data(), b, frames[b.frame].block_max, seqs.data());
     }
     it.dst_cap = ~0ull;
     ItemOut io; offsets_item(it, info, base, frames.data(), blocks.data(), io);      // resolves every block's starting history
