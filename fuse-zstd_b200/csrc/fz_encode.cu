@@ -18,8 +18,8 @@
  *   k_enc_lit      warp/chunk    literals: histogram -> length-limited (11 bit) code lengths with an exact
  *                                Kraft sum -> canonical codes in the decoder's order -> direct-weight tree
  *                                description -> 4 Huffman streams (sizes computed first, written in place)
- *   k_enc_seq      thread/chunk  sequences: FSE with the Predefined LL/OF/ML tables (RFC 8878 3.1.1.3.2.2),
- *                                encoding tables built once per CTA in shared memory
+ *   k_enc_seq      warp/chunk    sequences: histograms -> per-block FSE tables (normalised counts, table description,
+ *                                encoding table; Predefined for few sequences, RLE for one symbol) -> bitstream
  *   k_enc_place    thread/item   frame sizes -> offsets inside the item's dst, capacity check
  *   k_enc_write    warp/chunk    frame header + block header + sections (or the raw bytes) + XXH64 trailer
  */
@@ -32,6 +32,7 @@
 
 #include "fz_host.h"
 #include "fz_kernels.cuh"
+#include "fz_enc_core.cuh"
 
 namespace fz {
 
@@ -326,45 +327,29 @@ __global__ void __launch_bounds__(kLitWarps * 32) k_enc_lit(EncChunk* chunks, ui
     }
 }
 
-// ------------------------------------------------------------------ sequences section (FSE, predefined tables)
-struct FseCTable {          // encoding table of one predefined distribution (FSE_buildCTable)
-    uint16_t state[64];     // next-state table, tableSize entries
-    int32_t dfs[56];        // deltaFindState per symbol
-    uint32_t dnb[56];       // deltaNbBits per symbol
-    uint32_t log;
+// ------------------------------------------------------------------ sequences section (FSE)
+// One warp per chunk.  All lanes histogram the LL / OF / ML codes; lanes 0..2 then each prepare one table:
+// Predefined (few sequences), RLE (one symbol) or FSE_Compressed with counts normalised from the histogram
+// (enc_normalize), its description (enc_write_ncount) and the encoding table (enc_build_ctable), all in shared
+// memory; lane 0 finally writes the section: header, the three descriptions, the backward-readable bitstream
+// (sequences last to first, RFC 8878 3.1.1.3.2.1.1 field order).
+struct EncTables {
+    uint32_t hist[3][56];
+    int16_t norm[3][56];
+    uint16_t state[3][512];
+    uint32_t dnb[3][56];
+    int32_t dfs[3][56];
+    uint8_t tmp[3][512];
+    uint16_t cumul[3][58];
+    uint8_t desc[3][96];
+    int desc_len[3], log[3], mode[3];
 };
-
-__device__ void build_ctable(FseCTable& t, const int16_t* norm, int nsym, int log)
-{
-    const int size = 1 << log; int high = size - 1;
-    uint8_t sym[64]; uint16_t cumul[58];
-    cumul[0] = 0;
-    for (int s = 0; s < nsym; s++) {
-        if (norm[s] == -1) { cumul[s + 1] = cumul[s] + 1; sym[high--] = (uint8_t)s; }
-        else cumul[s + 1] = cumul[s] + (uint16_t)norm[s];
-    }
-    const int step = (size >> 1) + (size >> 3) + 3, mask = size - 1; int pos = 0;
-    for (int s = 0; s < nsym; s++)
-        for (int i = 0; i < norm[s]; i++) { sym[pos] = (uint8_t)s; do { pos = (pos + step) & mask; } while (pos > high); }
-    for (int u = 0; u < size; u++) { const int s = sym[u]; t.state[cumul[s]++] = (uint16_t)(size + u); }
-    int total = 0;
-    for (int s = 0; s < nsym; s++) {
-        const int n = norm[s];
-        if (n == 0) { t.dnb[s] = ((uint32_t)(log + 1) << 16) - (1u << log); t.dfs[s] = 0; }
-        else if (n == -1 || n == 1) { t.dnb[s] = ((uint32_t)log << 16) - (1u << log); t.dfs[s] = total - 1; total++; }
-        else {
-            const uint32_t maxBits = (uint32_t)log - (uint32_t)highbit((uint32_t)n - 1);
-            const uint32_t minStatePlus = (uint32_t)n << maxBits;
-            t.dnb[s] = (maxBits << 16) - minStatePlus; t.dfs[s] = total - n; total += n;
-        }
-    }
-    t.log = (uint32_t)log;
-}
 
 __device__ __forceinline__ uint32_t ll_code(uint32_t ll)
 {
     if (ll < 16) return ll;
-    if (ll < 64) { const uint32_t t[] = { 16, 16, 17, 17, 18, 18, 19, 19, 20, 20, 20, 20, 21, 21, 21, 21 }; return ll < 32 ? t[ll - 16] : (ll < 40 ? 22 : (ll < 48 ? 23 : 24)); }
+    if (ll < 32) return 16 + ((ll - 16) >> 1 < 4 ? (ll - 16) >> 1 : 4 + ((ll - 24) >> 2));   // 16,16,17,17,18,18,19,19,20 x4,21 x4
+    if (ll < 64) return ll < 40 ? 22 : (ll < 48 ? 23 : 24);
     return (uint32_t)highbit(ll) + 19;
 }
 __device__ __forceinline__ uint32_t ml_code(uint32_t mlb)      // mlb = match length - 3
@@ -380,66 +365,112 @@ __device__ __forceinline__ uint32_t ml_code(uint32_t mlb)      // mlb = match le
     return (uint32_t)highbit(mlb) + 36;
 }
 
-constexpr int kSeqEncThreads = 128;
-__global__ void __launch_bounds__(kSeqEncThreads) k_enc_seq(EncChunk* chunks, uint32_t n_chunks)
+constexpr int kSeqEncWarps = 4;
+__global__ void __launch_bounds__(kSeqEncWarps * 32) k_enc_seq(EncChunk* chunks, uint32_t n_chunks, uint32_t* ticket)
 {
-    __shared__ FseCTable tLL, tOF, tML;
+    __shared__ EncTables s_t[kSeqEncWarps];
     __shared__ SeqConsts K;
     for (uint32_t i = threadIdx.x; i < sizeof(SeqConsts) / 4; i += blockDim.x) ((uint32_t*)&K)[i] = ((const uint32_t*)&c_seq_consts)[i];
     __syncthreads();
-    if (threadIdx.x == 0) build_ctable(tLL, K.ll_def, 36, 6);
-    if (threadIdx.x == 32) build_ctable(tOF, K.of_def, 29, 5);
-    if (threadIdx.x == 64) build_ctable(tML, K.ml_def, 53, 6);
-    __syncthreads();
-    const uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ci >= n_chunks) return;
-    EncChunk& ch = chunks[ci];
-    const uint64_t* __restrict__ seq = (const uint64_t*)(ch.scratch + kScrSeq);
-    uint8_t* out = ch.scratch + kScrSeqSec;
-    const uint32_t nseq = ch.nseq;
-    uint32_t hs;
-    if (nseq < 128) { out[0] = (uint8_t)nseq; hs = 1; }
-    else if (nseq < 0x7F00) { out[0] = (uint8_t)((nseq >> 8) + 128); out[1] = (uint8_t)nseq; hs = 2; }
-    else { out[0] = 255; out[1] = (uint8_t)(nseq - 0x7F00); out[2] = (uint8_t)((nseq - 0x7F00) >> 8); hs = 3; }
-    if (nseq == 0) { ch.seq_sec = hs; return; }
-    out[hs++] = 0;                                   // Symbol_Compression_Modes: LL, OF, ML all Predefined
-    BitOut bo; bo.init(out + hs);
-    auto init_state = [](const FseCTable& t, uint32_t s) -> uint32_t {      // FSE_initCState2
-        const uint32_t nb = (t.dnb[s] + (1u << 15)) >> 16;
-        const uint32_t value = (nb << 16) - t.dnb[s];
-        return t.state[(value >> nb) + t.dfs[s]];
-    };
-    auto encode = [&bo](const FseCTable& t, uint32_t& state, uint32_t s) {  // FSE_encodeSymbol
-        const uint32_t nb = (state + t.dnb[s]) >> 16;
-        bo.add(state & ((1u << nb) - 1), nb);
-        state = t.state[(state >> nb) + t.dfs[s]];
-    };
-    uint32_t sLL, sOF, sML;
-    {
-        const uint64_t r = seq[nseq - 1];
-        const uint32_t ll = eseq_ll(r), mlb = eseq_ml(r) - 3, ofv = eseq_off(r) + 3;
-        const uint32_t lc = ll_code(ll), mc = ml_code(mlb), oc = (uint32_t)highbit(ofv);
-        sML = init_state(tML, mc); sOF = init_state(tOF, oc); sLL = init_state(tLL, lc);
-        bo.add(ll - K.ll_base[lc], K.ll_bits[lc]); bo.flush();
-        bo.add(mlb + 3 - K.ml_base[mc], K.ml_bits[mc]); bo.flush();
-        bo.add(ofv - (1u << oc), oc); bo.flush();
+    const uint32_t lane = threadIdx.x & 31;
+    EncTables& T = s_t[threadIdx.x >> 5];
+    for (;;) {
+        uint32_t ci = 0;
+        if (lane == 0) ci = atomicAdd(ticket, 1);
+        ci = __shfl_sync(0xFFFFFFFFu, ci, 0);
+        if (ci >= n_chunks) return;
+        EncChunk& ch = chunks[ci];
+        const uint64_t* __restrict__ seq = (const uint64_t*)(ch.scratch + kScrSeq);
+        uint8_t* out = ch.scratch + kScrSeqSec;
+        const uint32_t nseq = ch.nseq;
+        if (nseq == 0) { if (lane == 0) { out[0] = 0; ch.seq_sec = 1; } __syncwarp(); continue; }
+        // ---- histograms of the three codes
+        for (uint32_t i = lane; i < 3 * 56; i += 32) (&T.hist[0][0])[i] = 0;
+        __syncwarp();
+        for (uint32_t i = lane; i < nseq; i += 32) {
+            const uint64_t r = seq[i];
+            atomicAdd(&T.hist[0][ll_code(eseq_ll(r))], 1u);
+            atomicAdd(&T.hist[1][highbit(eseq_off(r) + 3)], 1u);
+            atomicAdd(&T.hist[2][ml_code(eseq_ml(r) - 3)], 1u);
+        }
+        __syncwarp();
+        // ---- one table per lane (0 LL, 1 OF, 2 ML)
+        if (lane < 3) {
+            const int t = (int)lane;
+            const int n_sym = t == 0 ? 36 : (t == 1 ? 32 : 53), max_log = t == 1 ? 8 : 9;
+            int present = 0, only = 0;
+            for (int sy = 0; sy < n_sym; sy++) if (T.hist[t][sy]) { present++; only = sy; }
+            int mode = nseq < 64 ? 0 : (present == 1 ? 1 : 2), log = 0, dlen = 0;
+            if (mode == 2) {
+                log = enc_table_log(nseq, present, max_log);
+                if (enc_normalize(T.hist[t], n_sym, nseq, log, T.norm[t]) != 0) mode = 0;
+                else { dlen = enc_write_ncount(T.desc[t], T.norm[t], n_sym, log); if (dlen < 0) mode = 0; }
+            }
+            if (mode == 1) { T.desc[t][0] = (uint8_t)only; dlen = 1; log = 0; }
+            if (mode == 0) {
+                const int16_t* def = t == 0 ? K.ll_def : (t == 1 ? K.of_def : K.ml_def);
+                const int nd = t == 0 ? 36 : (t == 1 ? 29 : 53);
+                for (int sy = 0; sy < 56; sy++) T.norm[t][sy] = sy < nd ? def[sy] : 0;
+                log = t == 1 ? 5 : 6; dlen = 0;
+            }
+            if (mode != 1) enc_build_ctable(T.state[t], T.dnb[t], T.dfs[t], T.norm[t], mode == 0 ? (t == 0 ? 36 : (t == 1 ? 29 : 53)) : n_sym, log, T.tmp[t], T.cumul[t]);
+            T.mode[t] = mode; T.log[t] = log; T.desc_len[t] = dlen;
+        }
+        __syncwarp();
+        // ---- the section, by lane 0
+        if (lane == 0) {
+            uint32_t hs;
+            if (nseq < 128) { out[0] = (uint8_t)nseq; hs = 1; }
+            else if (nseq < 0x7F00) { out[0] = (uint8_t)((nseq >> 8) + 128); out[1] = (uint8_t)nseq; hs = 2; }
+            else { out[0] = 255; out[1] = (uint8_t)(nseq - 0x7F00); out[2] = (uint8_t)((nseq - 0x7F00) >> 8); hs = 3; }
+            out[hs++] = (uint8_t)((T.mode[0] << 6) | (T.mode[1] << 4) | (T.mode[2] << 2));       // Symbol_Compression_Modes
+            for (int t = 0; t < 3; t++) for (int i = 0; i < T.desc_len[t]; i++) out[hs++] = T.desc[t][i];   // LL, OF, ML
+            BitOut bo; bo.init(out + hs);
+            auto init_state = [&](int t, uint32_t sy) -> uint32_t {               // FSE_initCState2
+                if (T.mode[t] == 1) return 0;
+                const uint32_t nb = (T.dnb[t][sy] + (1u << 15)) >> 16;
+                const uint32_t value = (nb << 16) - T.dnb[t][sy];
+                return T.state[t][(value >> nb) + T.dfs[t][sy]];
+            };
+            auto encode = [&](int t, uint32_t& st, uint32_t sy) {                 // FSE_encodeSymbol
+                if (T.mode[t] == 1) return;
+                const uint32_t nb = (st + T.dnb[t][sy]) >> 16;
+                bo.add(st & ((1u << nb) - 1), nb);
+                st = T.state[t][(st >> nb) + T.dfs[t][sy]];
+            };
+            const uint8_t* const limit = out + kEncChunkMax + kEncChunkMax / 2;   // a section this large means a Raw block anyway
+            uint32_t sLL, sOF, sML;
+            {
+                const uint64_t r = seq[nseq - 1];
+                const uint32_t ll = eseq_ll(r), mlb = eseq_ml(r) - 3, ofv = eseq_off(r) + 3;
+                const uint32_t lc = ll_code(ll), mc = ml_code(mlb), oc = (uint32_t)highbit(ofv);
+                sML = init_state(2, mc); sOF = init_state(1, oc); sLL = init_state(0, lc);
+                bo.add(ll - K.ll_base[lc], K.ll_bits[lc]); bo.flush();
+                bo.add(mlb + 3 - K.ml_base[mc], K.ml_bits[mc]); bo.flush();
+                bo.add(ofv - (1u << oc), oc); bo.flush();
+            }
+            for (uint32_t i = nseq - 1; i-- > 0;) {
+                if (bo.p > limit) break;
+                const uint64_t r = seq[i];
+                const uint32_t ll = eseq_ll(r), mlb = eseq_ml(r) - 3, ofv = eseq_off(r) + 3;
+                const uint32_t lc = ll_code(ll), mc = ml_code(mlb), oc = (uint32_t)highbit(ofv);
+                encode(1, sOF, oc); encode(2, sML, mc); bo.flush(); encode(0, sLL, lc); bo.flush();   // <= 8 + 9 and 9 bits
+                bo.add(ll - K.ll_base[lc], K.ll_bits[lc]); bo.flush();
+                bo.add(mlb + 3 - K.ml_base[mc], K.ml_bits[mc]); bo.flush();
+                bo.add(ofv - (1u << oc), oc); bo.flush();
+            }
+            // FSE_flushCState: the final states, ML, OF, LL (0 bits for an RLE table)
+            if (T.mode[2] != 1) bo.add(sML - (1u << T.log[2]), (uint32_t)T.log[2]);
+            bo.flush();
+            if (T.mode[1] != 1) bo.add(sOF - (1u << T.log[1]), (uint32_t)T.log[1]);
+            bo.flush();
+            if (T.mode[0] != 1) bo.add(sLL - (1u << T.log[0]), (uint32_t)T.log[0]);
+            bo.flush();
+            uint8_t* end = bo.close();
+            ch.seq_sec = bo.p > limit ? kEncChunkMax : (uint32_t)(end - out);
+        }
+        __syncwarp();
     }
-    const uint8_t* const limit = out + kEncChunkMax + kEncChunkMax / 2;     // a section this large means a Raw block anyway
-    for (uint32_t i = nseq - 1; i-- > 0;) {
-        if (bo.p > limit) break;
-        const uint64_t r = seq[i];
-        const uint32_t ll = eseq_ll(r), mlb = eseq_ml(r) - 3, ofv = eseq_off(r) + 3;
-        const uint32_t lc = ll_code(ll), mc = ml_code(mlb), oc = (uint32_t)highbit(ofv);
-        encode(tOF, sOF, oc); encode(tML, sML, mc); encode(tLL, sLL, lc); bo.flush();     // <= 5 + 6 + 6 bits
-        bo.add(ll - K.ll_base[lc], K.ll_bits[lc]); bo.flush();
-        bo.add(mlb + 3 - K.ml_base[mc], K.ml_bits[mc]); bo.flush();
-        bo.add(ofv - (1u << oc), oc); bo.flush();
-    }
-    bo.add(sML - 64, 6); bo.flush();                 // FSE_flushCState: the final states, ML, OF, LL
-    bo.add(sOF - 32, 5); bo.flush();
-    bo.add(sLL - 64, 6); bo.flush();
-    uint8_t* end = bo.close();
-    ch.seq_sec = bo.p > limit ? kEncChunkMax : (uint32_t)(end - out);
 }
 
 // ------------------------------------------------------------------ placement + final write
@@ -579,7 +610,7 @@ int fzh_encode_run(FzCtx* c, uint32_t first, uint32_t n, int level, size_t chunk
         if (marks) mark();
         k_enc_lit<<<std::min<uint32_t>((cnt + kLitWarps - 1) / kLitWarps, 148 * 8), kLitWarps * 32, 0, s>>>(d_chunks + lo, cnt, d_tickets + 1);
         if (marks) mark();
-        k_enc_seq<<<(cnt + kSeqEncThreads - 1) / kSeqEncThreads, kSeqEncThreads, 0, s>>>(d_chunks + lo, cnt);
+        k_enc_seq<<<std::min<uint32_t>((cnt + kSeqEncWarps - 1) / kSeqEncWarps, 148 * 7), kSeqEncWarps * 32, 0, s>>>(d_chunks + lo, cnt, d_tickets + 2);
         if (marks) mark();
         launches += 3;
         return 0;

@@ -82,11 +82,11 @@ FZ_HD uint64_t xx_lane(const uint8_t* p, uint64_t len, uint32_t j)   // accumula
         uint64_t s = 0;
         for (; s + 16 <= stripes; s += 16) {             // a serial multiply chain fed from HBM: sixteen loads in flight per thread
             uint64_t in[16];
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
             for (int k = 0; k < 16; k++) in[k] = *(const uint64_t*)(q + 32 * (s + k));
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
             for (int k = 0; k < 16; k++) acc = xx_round(acc, in[k]);

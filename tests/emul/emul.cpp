@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../fuse-zstd_b200/csrc/fz_kernels.cuh"
+#include "../../fuse-zstd_b200/csrc/fz_enc_core.cuh"
 
 using namespace fz;
 
@@ -189,4 +190,48 @@ extern "C" int fze_trace(const void* src, size_t src_len, uint64_t* seq_out, siz
     }
     *n_seq = ns; *n_lit = nl;
     return 0;
+}
+
+/* Encoder building blocks against the decoder's: normalise the histogram of syms[0..n), write the FSE table description,
+ * FSE-encode the symbols with the encoding table, then read the description back (read_ncount), rebuild the DECODING
+ * table (build_fse_table) and decode.  Returns 0 when everything round-trips, a negative stage code otherwise. */
+extern "C" int fze_fse_roundtrip(const uint8_t* syms, size_t n, int n_sym, int max_log)
+{
+    std::vector<uint32_t> count(n_sym, 0);
+    int present = 0;
+    for (size_t i = 0; i < n; i++) { if (syms[i] >= n_sym) return -100; if (!count[syms[i]]++) present++; }
+    const int log = enc_table_log((uint32_t)n, present, max_log);
+    std::vector<int16_t> norm(64, 0);
+    if (enc_normalize(count.data(), n_sym, (uint32_t)n, log, norm.data()) != 0) return -1;
+    int sum = 0; for (int s = 0; s < n_sym; s++) { if (count[s] && norm[s] < 1) return -2; sum += norm[s]; }
+    if (sum != (1 << log)) return -3;
+    uint8_t desc[160] = { 0 };
+    const int dlen = enc_write_ncount(desc, norm.data(), n_sym, log);
+    if (dlen < 0) return -4;
+    int16_t back[64]; int ns2 = 0, log2 = 0;
+    const int used = read_ncount(desc, (uint32_t)dlen, n_sym - 1, max_log, back, ns2, log2);
+    if (used != dlen || log2 != log) return -5;
+    for (int s = 0; s < n_sym; s++) if ((s < ns2 ? back[s] : 0) != norm[s]) return -6;
+    // encode (single state, symbols last to first, like the sequence coder does per state)
+    std::vector<uint16_t> state(1 << log); std::vector<uint32_t> dnb(n_sym); std::vector<int32_t> dfs(n_sym);
+    std::vector<uint8_t> tmp(1 << log); std::vector<uint16_t> cumul(n_sym + 2);
+    enc_build_ctable(state.data(), dnb.data(), dfs.data(), norm.data(), n_sym, log, tmp.data(), cumul.data());
+    std::vector<uint8_t> bs(n * 2 + 16, 0); uint64_t acc = 0; uint32_t nb_acc = 0; size_t bp = 0;
+    auto add = [&](uint32_t v, uint32_t nb) { acc |= (uint64_t)v << nb_acc; nb_acc += nb; while (nb_acc >= 8) { bs[bp++] = (uint8_t)acc; acc >>= 8; nb_acc -= 8; } };
+    uint32_t st;
+    { const uint32_t sy = syms[n - 1]; const uint32_t nbo = (dnb[sy] + (1u << 15)) >> 16; const uint32_t v = (nbo << 16) - dnb[sy]; st = state[(v >> nbo) + dfs[sy]]; }
+    for (size_t i = n - 1; i-- > 0;) { const uint32_t sy = syms[i]; const uint32_t nbo = (st + dnb[sy]) >> 16; add(st & ((1u << nbo) - 1), nbo); st = state[(st >> nbo) + dfs[sy]]; }
+    add(st - (1u << log), (uint32_t)log); add(1, 1); if (nb_acc) { bs[bp++] = (uint8_t)acc; }
+    // decode
+    std::vector<uint32_t> dt(1 << log); uint16_t cnt[64]; static const uint8_t no_extra[64] = { 0 };
+    if (build_fse_table(dt.data(), back, ns2, log2, no_extra, cnt) != 0) return -7;
+    BackBits br; if (br.init(bs.data(), (uint32_t)bp) != 0) return -8;
+    br.refill(); uint32_t ds = br.read((uint32_t)log);
+    for (size_t i = 0; i < n; i++) {
+        if (br.avail <= 32) br.refill();
+        const uint32_t c = dt[ds];
+        if (cell_sym(c) != syms[i]) return -9;
+        if (i + 1 < n) ds = cell_base(c) + br.read(cell_nb(c));
+    }
+    return br.left == 0 ? 0 : -10;
 }

@@ -16,7 +16,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        deps = [SRC] + [os.path.join(CSRC, f) for f in ("fz_core.cuh", "fz_kernels.cuh")]
+        deps = [SRC] + [os.path.join(CSRC, f) for f in ("fz_core.cuh", "fz_kernels.cuh", "fz_enc_core.cuh")]
         if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
             subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-fsanitize=undefined",
                                    "-fno-sanitize-recover=undefined", "-o", SO, SRC])
@@ -43,3 +43,8 @@ def trace(blob, max_seq=1 << 21, max_lit=1 << 22):
     st = lib().fze_trace(C.c_void_p(a.ctypes.data), C.c_size_t(a.size), C.c_void_p(seqs.ctypes.data), C.c_size_t(max_seq),
                          C.byref(ns), C.c_void_p(lits.ctypes.data), C.c_size_t(max_lit), C.byref(nl))
     return st, seqs[:ns.value], lits[:nl.value]
+
+
+def fse_roundtrip(syms, n_sym, max_log):
+    a = np.ascontiguousarray(syms, dtype=np.uint8)
+    return lib().fze_fse_roundtrip(C.c_void_p(a.ctypes.data), C.c_size_t(a.size), n_sym, max_log)

@@ -84,3 +84,18 @@ def test_batch_of_mixed_items(golden):
     assert [r[0] for r in res] == [0, 1, 0, 2, 0]
     assert hashlib.sha256(res[4][1]).hexdigest() == golden["multi_frame_skippable"][1]["plain_sha256"]
     assert res[2][1] == b""
+
+
+def test_encoder_fse_tables_round_trip_through_the_decoder_tables():
+    """normalisation + table description writer + encoding table vs read_ncount + decoding table (CPU, no GPU)"""
+    rs = np.random.RandomState(5)
+    cases = []
+    for n_sym, max_log in ((36, 9), (32, 8), (53, 9)):
+        for n in (70, 300, 5000, 14000):
+            cases.append((rs.randint(0, n_sym, n), n_sym, max_log))                                  # flat
+            cases.append((np.minimum(rs.geometric(0.35, n) - 1, n_sym - 1), n_sym, max_log))         # skewed, like LL / ML codes
+            cases.append((rs.choice([0, 1, n_sym - 1], n, p=[0.9, 0.09, 0.01]), n_sym, max_log))     # gaps of absent symbols
+            z = rs.randint(0, 3, n); z[0] = n_sym - 1; cases.append((z, n_sym, max_log))             # one rare high symbol
+            cases.append((rs.choice([3, 30 if n_sym > 30 else 7], n), n_sym, max_log))               # two symbols, long zero runs
+    for syms, n_sym, max_log in cases:
+        assert emul_util.fse_roundtrip(syms, n_sym, max_log) == 0, (n_sym, len(syms), np.bincount(syms)[:8])
