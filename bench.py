@@ -328,7 +328,7 @@ def run_b200(args, rank, local_rank, world):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        if tj.get("kernel") == top:
+        if tj.get("kernel") == top and tj.get("files_per_gpu") == F:
             traffic = tj.get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "kernel": top, "achieved": round(alg_bytes / 1e9 / (top_ms / 1e3), 2), "peak": peak, "unit": "GB/s",
                 "frac": round(alg_bytes / 1e9 / (top_ms / 1e3) / peak, 4), "traffic": traffic, "peak_source": peak_src,

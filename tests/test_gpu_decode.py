@@ -201,3 +201,19 @@ def test_fd_entry_points_follow_the_reference_flow(golden):
         assert e.value.errno == 14
     with tempfile.TemporaryFile() as src:                          # empty input decodes to empty output
         assert stream.decode_all(src) == b""
+
+
+def test_large_window_long_distance_and_level19(ref, corpus):
+    """config 4 in miniature: windowLog 23 (8 MiB window, offsets across dozens of blocks), a level-19 frame (block
+    splitting, Repeat modes, Treeless literals) and a long-distance repeat; one frame each, so one LZ77 chain each"""
+    if not ref.available:
+        pytest.skip("system libzstd absent")
+    j = corpus.json_file(4242, 24 << 20).tobytes()
+    far = j[: 6 << 20] + j[: 6 << 20]                                   # second half matches 6 MiB back
+    blobs = [ref.writer_encode(j, 3, window_log=23), ref.writer_encode(far, 3, window_log=23), ref.writer_encode(j[: 3 << 20], 19)]
+    plains = [j, far, j[: 3 << 20]]
+    assert blobs[0][4] & 0x20 == 0                                      # not Single_Segment: a Window_Descriptor is present
+    res = codec.decode_batch(blobs, [len(p) for p in plains])
+    for i, ((st, out), plain) in enumerate(zip(res, plains)):
+        assert st == 0, (i, codec.strerror(st))
+        assert hashlib.sha256(out).digest() == hashlib.sha256(plain).digest(), i
