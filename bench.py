@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--files", type=int, default=10000, help="files per GPU (config 2: 10 000)")
     ap.add_argument("--file-size", type=int, default=1 << 20)
     ap.add_argument("--level", type=int, default=3)
-    ap.add_argument("--e2e-files", type=int, default=5000, help="files per GPU in the host-buffer (e2e) leg")
+    ap.add_argument("--e2e-files", type=int, default=0, help="files per GPU in the host-buffer (e2e) leg (0: all, or half when host RAM is short)")
     ap.add_argument("--cpu-files", type=int, default=4096, help="bounded sample for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -285,7 +285,12 @@ def run_b200(args, rank, local_rank, world):
     # ---- e2e: pinned host buffers through the same C ABI call
     e2e = None
     if not args.no_e2e:
-        E = min(args.e2e_files, F)
+        E = min(args.e2e_files, F) if args.e2e_files else F
+        if not args.e2e_files:
+            import psutil
+            need = 1.5 * F * S * int(os.environ.get("LOCAL_WORLD_SIZE", world))       # pinned in + out buffers of every local rank
+            if psutil.virtual_memory().available < 2 * need:
+                E = F // 2
         src_bytes = int(w.comp_off[E - 1] + w.comp_len[E - 1])
         h_src = torch.empty(src_bytes + 64, dtype=torch.uint8, pin_memory=True)
         h_src.numpy()[:src_bytes] = w.packed[:src_bytes]

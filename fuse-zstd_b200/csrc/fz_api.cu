@@ -230,10 +230,11 @@ static int run_batch(bool encode, int device, size_t n, const void* const* src, 
     if (src_dev && dst_dev) {
         if ((rc = run(0, n, nullptr))) return rc;
     } else {
-        std::vector<size_t> cuts{ 0 };            // chunk boundaries
+        std::vector<size_t> cuts{ 0 };            // chunk boundaries: a small first chunk starts the device -> host stream early
+        size_t target = kChunkOutBytes / 4;
         for (size_t i = 0, bytes = 0; i < n; i++) {
             bytes += dst_cap[i] + src_len[i];
-            if (bytes >= kChunkOutBytes && i + 1 < n) { cuts.push_back(i + 1); bytes = 0; }
+            if (bytes >= target && i + 1 < n) { cuts.push_back(i + 1); bytes = 0; target = kChunkOutBytes; }
         }
         cuts.push_back(n);
         const size_t nchunks = cuts.size() - 1;
