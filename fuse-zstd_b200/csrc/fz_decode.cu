@@ -352,9 +352,10 @@ __device__ __forceinline__ void exec_block_warp(uint8_t* stage, const Block& b, 
     const uint8_t* __restrict__ lit = b.lit;
     const uint32_t in0 = b.rep_in[0], in1 = b.rep_in[1], in2 = b.rep_in[2];
     uint32_t Ecarry = 0, LEcarry = 0;
+    uint64_t rcur = lane < nseq ? __ldg(sq + lane) : 0;          // records of the current round; the next round's are loaded a round early
     for (uint32_t g = 0; g < nseq;) {
         const uint32_t nv = min(32u, nseq - g);
-        const uint64_t r = lane < nv ? __ldg(sq + g + lane) : 0;
+        const uint64_t r = lane < nv ? rcur : 0;
         uint32_t E = rec_e(r), LE = rec_le(r);
         const uint32_t Elast = __shfl_sync(kFull, E, nv - 1), LElast = __shfl_sync(kFull, LE, nv - 1);
         if (lane >= nv) { E = Elast; LE = LElast; }
@@ -372,8 +373,10 @@ __device__ __forceinline__ void exec_block_warp(uint8_t* stage, const Block& b, 
             warp_big_sequence(g0 + gS, lit + LEcarry, ll0, ml0, off0, lane);
             Ecarry = __shfl_sync(kFull, E, 0); LEcarry = __shfl_sync(kFull, LE, 0);
             g += 1;
+            rcur = g + lane < nseq ? __ldg(sq + g + lane) : 0;
             continue;
         }
+        rcur = g + m + lane < nseq ? __ldg(sq + g + m + lane) : 0;
         const bool mine = lane < m;
         const uint32_t gE = __shfl_sync(kFull, E, m - 1);         // end of the round's output
         const uint32_t a = (uint32_t)((uintptr_t)(g0 + gS) & 15); // stage[a + i] <-> g0[gS + i]: same low address bits as HBM
