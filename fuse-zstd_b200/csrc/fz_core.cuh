@@ -14,10 +14,10 @@
 
 #ifdef __CUDACC__
 #define FZ_HD __host__ __device__ __forceinline__
-#define FZ_D __device__ __forceinline__
+#define FZ_HD_RARE static __host__ __device__ __noinline__ // rare paths: kept out of line so that the hot loops stay small
 #else
 #define FZ_HD inline
-#define FZ_D inline
+#define FZ_HD_RARE inline
 #endif
 
 #include "../../include/fzgpu.h"
@@ -34,7 +34,7 @@ constexpr uint32_t kMagic = 0xFD2FB528u;
 constexpr uint32_t kBlockMax = 128u * 1024u;
 constexpr uint64_t kWindowMax = 1ull << 27;   // zstd-rs streaming decoder default (windowLogMax = 27)
 constexpr int kMaxLL = 35, kMaxOF = 31, kMaxML = 52;
-constexpr int kLLLog = 9, kOFLog = 8, kMLLog = 9, kHufLogMax = 12, kHufLogFast = 11;
+constexpr int kLLLog = 9, kOFLog = 8, kMLLog = 9, kHufLogMax = 12;
 
 // ------------------------------------------------------------------ descriptors (HBM)
 struct Item {            // one .zst file of the batch
@@ -69,7 +69,7 @@ enum : uint8_t { LT_RAW = 0, LT_RLE = 1, LT_HUF = 2, LT_TREELESS = 3 };
 struct Block {
     const uint8_t* src;      // block content (after the 3-byte header)
     const uint8_t* lit;      // regenerated literals: into src (Raw) or into literal scratch
-    uint64_t seq_base;       // first record in the sequence scratch (even, so records can be stored in pairs)
+    uint64_t seq_base;       // first record in the sequence scratch
     uint64_t out_off;        // offset in item dst (filled by the offsets pass)
     uint32_t csize;          // Block_Size field
     uint32_t rsize;          // regenerated size (Raw/RLE: known; Compressed: filled by the sequence pass)
@@ -324,7 +324,7 @@ FZ_HD void walk_item(uint32_t item_idx, const Item& it, ItemInfo& info, const It
                 }
                 if (nseq) {
                     if (FILL) { b.seq_base = base->seq + n_seq; seq_jobs[base->seq_job + nsj] = gb; }
-                    n_seq += (nseq + 1u) & ~1u; nsj++;
+                    n_seq += nseq; nsj++;
                 }
                 if (lh.type != LT_RAW) { if (FILL) huf_jobs[base->huf_job + nhj] = gb; nhj++; }
             }
@@ -398,7 +398,6 @@ FZ_HD int read_ncount(const uint8_t* p, uint32_t n, int max_sym, int max_log, in
 FZ_HD uint32_t cell_pack(uint32_t base, uint32_t nb, uint32_t extra, uint32_t sym) { return base | (nb << 16) | (extra << 20) | (sym << 25); }
 FZ_HD uint32_t cell_base(uint32_t c) { return c & 0xFFFFu; }
 FZ_HD uint32_t cell_nb(uint32_t c) { return (c >> 16) & 15u; }
-FZ_HD uint32_t cell_extra(uint32_t c) { return (c >> 20) & 31u; }
 FZ_HD uint32_t cell_sym(uint32_t c) { return c >> 25; }
 
 // Builds the decode table (RFC 8878 4.1.1).  extra_bits[sym] is folded into each cell so the
@@ -749,15 +748,6 @@ FZ_HD int huf_decode_stream(const uint16_t* table, int log, const uint8_t* p, ui
     return br.left == 0 ? 0 : -1;
 }
 
-FZ_HD void store_rec_pair(uint64_t* at, uint64_t a, uint64_t b)   // `at` is 16-byte aligned
-{
-#ifdef __CUDA_ARCH__
-    *(ulonglong2*)at = make_ulonglong2(a, b);
-#else
-    at[0] = a; at[1] = b;
-#endif
-}
-
 // ------------------------------------------------------------------ sequence pass, stage A: the FSE chain
 // The three-state FSE chain is the only inherently serial part of a block, so stage A does nothing
 // else: one thread per block walks the backward bitstream and leaves one 8-byte RAW record per
@@ -952,7 +942,7 @@ FZ_HD uint32_t rep_update(uint32_t ofv, bool ll0, uint32_t& rep0, uint32_t& rep1
 }
 
 // RAW slow form for a sequence whose extra bits exceed one window: the symbols are recovered from the description.
-FZ_HD uint64_t raw_slow(const Block* blocks, const Block& b, const SeqConsts& K, uint32_t sLL, uint32_t sML, uint32_t ofb,
+FZ_HD_RARE uint64_t raw_slow(const Block* blocks, const Block& b, const SeqConsts& K, uint32_t sLL, uint32_t sML, uint32_t ofb,
                         uint32_t ofx, uint32_t mlx, uint32_t llx, int& st)
 {
     const int yl = symbol_of_state(blocks, b, 0, sLL, K), ym = symbol_of_state(blocks, b, 2, sML, K);
