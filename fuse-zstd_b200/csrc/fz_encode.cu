@@ -38,7 +38,10 @@ namespace fz {
 
 constexpr uint32_t kEncChunkMax = 128u * 1024u;
 constexpr uint32_t kEncMinMatch = 4;
-constexpr uint32_t kEncHashLog = 13;
+#ifndef FZ_ENC_HASHLOG
+#define FZ_ENC_HASHLOG 13
+#endif
+constexpr uint32_t kEncHashLog = FZ_ENC_HASHLOG;
 constexpr uint32_t kEncMaxOff = 65535;                       // the table keeps the low 16 bits of a position
 constexpr uint32_t kEncMatchWarps = 4;                       // warps (= chunks in flight) per CTA in k_enc_match
 constexpr uint32_t kHufMaxLen = 11;
@@ -343,6 +346,7 @@ struct EncTables {
     uint16_t cumul[3][58];
     uint8_t desc[3][96];
     int desc_len[3], log[3], mode[3];
+    uint32_t sbuf[144];      // bitstream staging: one batch of 32 sequences is at most 32 * 11 bytes
 };
 
 __device__ __forceinline__ uint32_t ll_code(uint32_t ll)
@@ -417,58 +421,82 @@ __global__ void __launch_bounds__(kSeqEncWarps * 32) k_enc_seq(EncChunk* chunks,
             T.mode[t] = mode; T.log[t] = log; T.desc_len[t] = dlen;
         }
         __syncwarp();
-        // ---- the section, by lane 0
+        // ---- the section.  The bitstream is a serial chain (three FSE states, one bit container), but everything that
+        // feeds it is not: the lanes load and pre-digest 32 sequences at a time (codes, extra bits), the chain then runs
+        // on all lanes redundantly from shuffled values, the container is drained into shared memory and each batch's
+        // bytes go to HBM with one cooperative copy.
+        uint32_t hs = 0;
         if (lane == 0) {
-            uint32_t hs;
             if (nseq < 128) { out[0] = (uint8_t)nseq; hs = 1; }
             else if (nseq < 0x7F00) { out[0] = (uint8_t)((nseq >> 8) + 128); out[1] = (uint8_t)nseq; hs = 2; }
             else { out[0] = 255; out[1] = (uint8_t)(nseq - 0x7F00); out[2] = (uint8_t)((nseq - 0x7F00) >> 8); hs = 3; }
             out[hs++] = (uint8_t)((T.mode[0] << 6) | (T.mode[1] << 4) | (T.mode[2] << 2));       // Symbol_Compression_Modes
             for (int t = 0; t < 3; t++) for (int i = 0; i < T.desc_len[t]; i++) out[hs++] = T.desc[t][i];   // LL, OF, ML
-            BitOut bo; bo.init(out + hs);
-            auto init_state = [&](int t, uint32_t sy) -> uint32_t {               // FSE_initCState2
-                if (T.mode[t] == 1) return 0;
-                const uint32_t nb = (T.dnb[t][sy] + (1u << 15)) >> 16;
-                const uint32_t value = (nb << 16) - T.dnb[t][sy];
-                return T.state[t][(value >> nb) + T.dfs[t][sy]];
-            };
-            auto encode = [&](int t, uint32_t& st, uint32_t sy) {                 // FSE_encodeSymbol
-                if (T.mode[t] == 1) return;
-                const uint32_t nb = (st + T.dnb[t][sy]) >> 16;
-                bo.add(st & ((1u << nb) - 1), nb);
-                st = T.state[t][(st >> nb) + T.dfs[t][sy]];
-            };
-            const uint8_t* const limit = out + kEncChunkMax + kEncChunkMax / 2;   // a section this large means a Raw block anyway
-            uint32_t sLL, sOF, sML;
-            {
-                const uint64_t r = seq[nseq - 1];
-                const uint32_t ll = eseq_ll(r), mlb = eseq_ml(r) - 3, ofv = eseq_off(r) + 3;
-                const uint32_t lc = ll_code(ll), mc = ml_code(mlb), oc = (uint32_t)highbit(ofv);
-                sML = init_state(2, mc); sOF = init_state(1, oc); sLL = init_state(0, lc);
-                bo.add(ll - K.ll_base[lc], K.ll_bits[lc]); bo.flush();
-                bo.add(mlb + 3 - K.ml_base[mc], K.ml_bits[mc]); bo.flush();
-                bo.add(ofv - (1u << oc), oc); bo.flush();
-            }
-            for (uint32_t i = nseq - 1; i-- > 0;) {
-                if (bo.p > limit) break;
-                const uint64_t r = seq[i];
-                const uint32_t ll = eseq_ll(r), mlb = eseq_ml(r) - 3, ofv = eseq_off(r) + 3;
-                const uint32_t lc = ll_code(ll), mc = ml_code(mlb), oc = (uint32_t)highbit(ofv);
-                encode(1, sOF, oc); encode(2, sML, mc); bo.flush(); encode(0, sLL, lc); bo.flush();   // <= 8 + 9 and 9 bits
-                bo.add(ll - K.ll_base[lc], K.ll_bits[lc]); bo.flush();
-                bo.add(mlb + 3 - K.ml_base[mc], K.ml_bits[mc]); bo.flush();
-                bo.add(ofv - (1u << oc), oc); bo.flush();
-            }
-            // FSE_flushCState: the final states, ML, OF, LL (0 bits for an RLE table)
-            if (T.mode[2] != 1) bo.add(sML - (1u << T.log[2]), (uint32_t)T.log[2]);
-            bo.flush();
-            if (T.mode[1] != 1) bo.add(sOF - (1u << T.log[1]), (uint32_t)T.log[1]);
-            bo.flush();
-            if (T.mode[0] != 1) bo.add(sLL - (1u << T.log[0]), (uint32_t)T.log[0]);
-            bo.flush();
-            uint8_t* end = bo.close();
-            ch.seq_sec = bo.p > limit ? kEncChunkMax : (uint32_t)(end - out);
         }
+        hs = __shfl_sync(0xFFFFFFFFu, hs, 0);
+        uint8_t* const bs = out + hs;                                              // bitstream start
+        const uint32_t limit = kEncChunkMax + kEncChunkMax / 2;                    // a section this large means a Raw block anyway
+        uint32_t* const sw = T.sbuf;                                               // per-warp staging, 32-bit words
+        uint64_t acc = 0; uint32_t nacc = 0, sfill = 0, gpos = 0;                  // container (< 32 bits between steps), words staged, bytes in HBM
+        auto add = [&](uint32_t v, uint32_t nb) { acc |= (uint64_t)v << nacc; nacc += nb; };
+        auto drain = [&]() { if (nacc >= 32) { if (lane == 0) sw[sfill] = (uint32_t)acc; sfill++; acc >>= 32; nacc -= 32; } };
+        const bool rLL = T.mode[0] == 1, rOF = T.mode[1] == 1, rML = T.mode[2] == 1;
+        auto enc = [&](int t, bool rle, uint32_t& st, uint32_t sy) {                // FSE_encodeSymbol
+            if (rle) return;
+            const uint32_t nb = (st + T.dnb[t][sy]) >> 16;
+            add(st & ((1u << nb) - 1), nb);
+            st = T.state[t][(st >> nb) + T.dfs[t][sy]];
+        };
+        auto init_state = [&](int t, bool rle, uint32_t sy) -> uint32_t {           // FSE_initCState2
+            if (rle) return 0;
+            const uint32_t nb = (T.dnb[t][sy] + (1u << 15)) >> 16;
+            return T.state[t][((((nb << 16) - T.dnb[t][sy])) >> nb) + T.dfs[t][sy]];
+        };
+        uint32_t sLL = 0, sOF = 0, sML = 0;
+        bool overflow = false;
+        for (uint32_t hi = nseq; hi > 0 && !overflow;) {                            // sequences last to first, 32 per batch
+            const uint32_t cnt = min(32u, hi);
+            uint32_t codes = 0, lens = 0, ofx = 0;
+            if (lane < cnt) {
+                const uint64_t r = seq[hi - 1 - lane];
+                const uint32_t ll = eseq_ll(r), mlb = eseq_ml(r) - 3, ofv = eseq_off(r) + 3;
+                const uint32_t lc = ll_code(ll), mc = ml_code(mlb), oc = (uint32_t)highbit(ofv);
+                codes = lc | (mc << 8) | (oc << 16) | ((uint32_t)K.ll_bits[lc] << 22) | ((uint32_t)K.ml_bits[mc] << 27);
+                lens = (ll - K.ll_base[lc]) | ((mlb + 3 - K.ml_base[mc]) << 16);
+                ofx = ofv - (1u << oc);
+            }
+            for (uint32_t k = 0; k < cnt; k++) {
+                const uint32_t c = __shfl_sync(0xFFFFFFFFu, codes, k), l = __shfl_sync(0xFFFFFFFFu, lens, k), o = __shfl_sync(0xFFFFFFFFu, ofx, k);
+                const uint32_t lc = c & 255, mc = (c >> 8) & 255, oc = (c >> 16) & 63;
+                if (hi == nseq && k == 0) { sML = init_state(2, rML, mc); sOF = init_state(1, rOF, oc); sLL = init_state(0, rLL, lc); }
+                else { enc(1, rOF, sOF, oc); enc(2, rML, sML, mc); enc(0, rLL, sLL, lc); drain(); }   // <= 8 + 9 + 9 bits on top of < 32
+                add(l & 0xFFFF, (c >> 22) & 31); add(l >> 16, c >> 27); drain();                       // <= 16 + 16
+                add(o, oc); drain();                                                                    // <= 17 here (offsets < 64 KiB)
+            }
+            hi -= cnt;
+            // this batch's whole words -> HBM
+            __syncwarp();
+            const uint8_t* sb = (const uint8_t*)sw;
+            for (uint32_t i = lane; i < sfill * 4; i += 32) bs[gpos + i] = sb[i];
+            gpos += sfill * 4; sfill = 0;
+            __syncwarp();
+            overflow = hs + gpos > limit;
+        }
+        // FSE_flushCState: the final states, ML, OF, LL (0 bits for an RLE table), then the end mark
+        if (!rML) add(sML - (1u << T.log[2]), (uint32_t)T.log[2]);
+        if (!rOF) add(sOF - (1u << T.log[1]), (uint32_t)T.log[1]);
+        drain();
+        if (!rLL) add(sLL - (1u << T.log[0]), (uint32_t)T.log[0]);
+        add(1, 1); drain();
+        const uint32_t tail = (nacc + 7) / 8;                                      // < 4 bytes left in the container
+        if (lane == 0) { sw[sfill] = (uint32_t)acc; }
+        __syncwarp();
+        {
+            const uint8_t* sb = (const uint8_t*)sw;
+            for (uint32_t i = lane; i < sfill * 4 + tail; i += 32) bs[gpos + i] = sb[i];
+            gpos += sfill * 4 + tail;
+        }
+        if (lane == 0) ch.seq_sec = overflow ? kEncChunkMax : hs + gpos;
         __syncwarp();
     }
 }
@@ -606,7 +634,7 @@ int fzh_encode_run(FzCtx* c, uint32_t first, uint32_t n, int level, size_t chunk
     auto run_wave = [&](uint64_t w, bool marks) -> int {
         const uint64_t lo = w * wave; const uint32_t cnt = (uint32_t)std::min<uint64_t>(wave, n_chunks - lo);
         CK(cudaMemsetAsync(d_tickets, 0, 16, s));
-        k_enc_match<<<std::min<uint32_t>((cnt + kEncMatchWarps - 1) / kEncMatchWarps, 148 * 3), kEncMatchWarps * 32, kEncMatchWarps * (2 << kEncHashLog), s>>>(d_chunks + lo, cnt, d_tickets);
+        k_enc_match<<<std::min<uint32_t>((cnt + kEncMatchWarps - 1) / kEncMatchWarps, 148 * ((200u << 10) / (kEncMatchWarps * (2u << kEncHashLog)))), kEncMatchWarps * 32, kEncMatchWarps * (2 << kEncHashLog), s>>>(d_chunks + lo, cnt, d_tickets);
         if (marks) mark();
         k_enc_lit<<<std::min<uint32_t>((cnt + kLitWarps - 1) / kLitWarps, 148 * 8), kLitWarps * 32, 0, s>>>(d_chunks + lo, cnt, d_tickets + 1);
         if (marks) mark();
