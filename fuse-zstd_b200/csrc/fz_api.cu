@@ -45,6 +45,7 @@ extern "C" int fzg_init(const int* devices, int n_devices)
     for (int d : devs) if (d < 0 || d >= visible) return -EINVAL;
     for (int d : devs) {
         CKR(cudaSetDevice(d));
+        if (const char* g = getenv("FZG_L2_GRAN")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));   // experiment knob
         FzCtx* c = new FzCtx();
         c->dev = d;
         const char* nl = getenv("FZG_LANES");

@@ -860,7 +860,8 @@ FZ_HD int build_chain_seq_table(const Block* blocks, const Block& b, int which, 
 }
 
 // Stage B: state -> symbol maps of the LL and ML tables of block b (yLL / yML: 512 bytes each; norm_buf: 64 int16).
-FZ_HD int build_symbol_maps(const Block* blocks, const Block& b, const SeqConsts& K, uint8_t* yLL, uint8_t* yML, int16_t* norm_buf)
+FZ_HD int build_symbol_maps(const Block* blocks, const Block& b, const SeqConsts& K, uint8_t* yLL, uint8_t* yML, int16_t* norm_buf,
+                            const uint8_t*& bits)           // bits: first byte of the sequence bitstream
 {
     const uint8_t* p = b.src + b.seq_hdr; uint32_t n = b.csize - b.seq_hdr;
     for (int which = 0; which < 3; which++) {                      // stream order: LL, OF, ML (OF only to find where ML starts)
@@ -877,48 +878,39 @@ FZ_HD int build_symbol_maps(const Block* blocks, const Block& b, const SeqConsts
             if (table_norm(t, which, K, norm_buf, norm, ns, log, used) != 0) return -1;
             if (which != 1 && fse_spread(y, norm, ns, log, (uint16_t*)nullptr) != 0) return -1;
         }
-        if (t.own) { p += used; n -= used; }
+        if (t.own) { if (used > n) return -1; p += used; n -= used; }
     }
+    bits = p;
     return 0;
 }
 
-// Symbol of cell `state` of table `which` of block b, recomputed from the table description (no table in memory).
-// Only for the rare sequence whose extra bits do not fit one 32-bit window (stage A keeps no symbols).  -1 on error.
-FZ_HD int symbol_of_state(const Block* blocks, const Block& b, int which, uint32_t state, const SeqConsts& K)
+// RAW record of stage A: x[0:32) | y[32:64), y = LL cell byte offset [0:12) | ML cell byte offset [12:24) | offset code [24:29) |
+// far [31], the offsets counted from the start of the stream's shared memory (LL cells at 0, ML cells at 1024): exactly
+// what the chain loop holds in registers.  x is the 32-bit window of the bitstream that starts with the sequence's
+// extra bits (offset, match length, literal length); when those exceed 32 bits (far = 1: long lengths with a
+// far offset, rare) x is the sequence's BIT CURSOR instead and stage B reads the extra bits from the stream itself.
+FZ_HD uint64_t raw_pack(uint32_t x, uint32_t y) { return (uint64_t)x | ((uint64_t)y << 32); }
+FZ_HD uint32_t stream_bits(const uint8_t* gbase, int32_t cur, uint32_t nb)     // nb <= 32 bits of the stream, the highest at bit address cur
 {
-    const uint8_t* p = b.src + b.seq_hdr; uint32_t n = b.csize - b.seq_hdr;
-    int16_t norm_buf[64];
-    for (int w = 0; w <= which; w++) {
-        TableSrc t;
-        if (resolve_table(blocks, b, w, p, n, t) != 0) return -1;
-        uint32_t used = 0; const int16_t* norm = nullptr; int ns = 0, log = 0;
-        if (t.mode == 1) { if (t.n < 1) return -1; if (w == which) return t.p[0]; used = 1; }
-        else {
-            if (table_norm(t, w, K, norm_buf, norm, ns, log, used) != 0) return -1;
-            if (w == which) {
-                const int size = 1 << log; int high = size - 1;
-                for (int sy = 0; sy < ns; sy++) if (norm[sy] == -1) { if ((uint32_t)high == state) return sy; high--; }
-                const int step = (size >> 1) + (size >> 3) + 3, mask = size - 1; int pos = 0;
-                for (int sy = 0; sy < ns; sy++)
-                    for (int i = 0; i < norm[sy]; i++) { if ((uint32_t)pos == state) return sy; do { pos = (pos + step) & mask; } while (pos > high); }
-                return -1;
-            }
-        }
-        if (t.own) { p += used; n -= used; }
-    }
-    return -1;
+    uint64_t v = 0;
+    for (int32_t k = 0; k < (int32_t)nb; k++) { const int32_t a = cur - k; v = (v << 1) | (a >= 0 ? (gbase[a >> 3] >> (a & 7)) & 1u : 0u); }
+    return (uint32_t)v;
 }
-
-FZ_HD uint64_t raw_pack_fast(uint32_t x, uint32_t sll, uint32_t sml, uint32_t ofc) { return (uint64_t)x | ((uint64_t)(sll | (sml << 9) | (ofc << 18)) << 32); }
-FZ_HD uint64_t raw_pack_slow(uint32_t ll, uint32_t ml, uint32_t ofv) { return (uint64_t)(ll & 0x3FFFFu) | ((uint64_t)((ml - 3) & 0x1FFFFu) << 18) | ((uint64_t)(ofv & 0xFFFFFFFu) << 35) | (1ull << 63); }
-// RAW -> (literal length, match length, offset value), with the block's state -> symbol maps.  Returns false when
-// the offset code is beyond any legal window.
-FZ_HD bool raw_unpack(uint64_t r, const SeqConsts& K, const uint8_t* yLL, const uint8_t* yML, uint32_t& ll, uint32_t& ml, uint32_t& ofv)
+// RAW -> (literal length, match length, offset value), with the block's state -> symbol maps; `bits` = first byte of the
+// block's sequence bitstream.  Returns false when the offset code is beyond any legal window.
+FZ_HD bool raw_unpack(uint64_t r, const SeqConsts& K, const uint8_t* yLL, const uint8_t* yML, const uint8_t* bits, uint32_t& ll, uint32_t& ml, uint32_t& ofv)
 {
-    if (r >> 63) { ll = (uint32_t)r & 0x3FFFFu; ml = ((uint32_t)(r >> 18) & 0x1FFFFu) + 3; ofv = (uint32_t)(r >> 35) & 0xFFFFFFFu; return true; }
     const uint32_t x = (uint32_t)r, y = (uint32_t)(r >> 32);
-    const uint32_t yll = yLL[y & 511], yml = yML[(y >> 9) & 511], yof = (y >> 18) & 31;
+    const uint32_t yll = yLL[(y & 0x3FFu) >> 1], yml = yML[((y >> 12) & 0x3FFu) >> 1], yof = (y >> 24) & 31;
     const uint32_t ofb = yof, mlb = K.ml_bits[yml], llb = K.ll_bits[yll];
+    if (y >> 31) {
+        const uint8_t* gbase = (const uint8_t*)((uintptr_t)bits & ~(uintptr_t)255);
+        const int32_t cur = (int32_t)x;
+        ofv = (1u << yof) + stream_bits(gbase, cur, ofb);
+        ml = K.ml_base[yml] + stream_bits(gbase, cur - (int32_t)ofb, mlb);
+        ll = K.ll_base[yll] + stream_bits(gbase, cur - (int32_t)(ofb + mlb), llb);
+        return yof <= 27;
+    }
     ofv = (1u << yof) + shr_c(x, 32 - ofb);
     ml = K.ml_base[yml] + shr_c(shl_c(x, ofb), 32 - mlb);
     ll = K.ll_base[yll] + shr_c(shl_c(x, ofb + mlb), 32 - llb);
@@ -941,22 +933,89 @@ FZ_HD uint32_t rep_update(uint32_t ofv, bool ll0, uint32_t& rep0, uint32_t& rep1
     return off;
 }
 
-// RAW slow form for a sequence whose extra bits exceed one window: the symbols are recovered from the description.
-FZ_HD_RARE uint64_t raw_slow(const Block* blocks, const Block& b, const SeqConsts& K, uint32_t sLL, uint32_t sML, uint32_t ofb,
-                        uint32_t ofx, uint32_t mlx, uint32_t llx, int& st)
-{
-    const int yl = symbol_of_state(blocks, b, 0, sLL, K), ym = symbol_of_state(blocks, b, 2, sML, K);
-    if (yl < 0 || ym < 0 || yl > kMaxLL || ym > kMaxML) { st = FZG_E_CORRUPT; return 0; }
-    // an offset code beyond any legal window is kept visible for stage B (it tests the value)
-    return raw_pack_slow(K.ll_base[yl] + llx, K.ml_base[ym] + mlx, ofb > 27 ? 0xFFFFFFFu : (1u << ofb) + ofx);
-}
+// ---- shared-memory access of the chain loop: 32-bit shared-window addresses on the device (one LDS with an
+// immediate offset, no generic-address arithmetic), plain pointers in the host emulation
+#ifdef __CUDA_ARCH__
+typedef uint32_t sm_t;
+FZ_HD sm_t sm_of(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+FZ_HD uint32_t sm_ld16(sm_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+FZ_HD uint32_t sm_ld32(sm_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+FZ_HD sm_t ring_slot(sm_t ring, uint32_t b) { return ring | (b & 0xFCu); }            // the ring is 256-byte aligned
+FZ_HD void ring_fetch_sm(sm_t slot, const uint8_t* gsrc) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(gsrc) : "memory"); }
+FZ_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+FZ_HD uint32_t fsl_w(uint32_t lo, uint32_t hi, uint32_t n) { return __funnelshift_l(lo, hi, n); }   // high word of (hi:lo << (n & 31))
+FZ_HD uint32_t andn32(uint32_t a, uint32_t b) { uint32_t r; asm("lop3.b32 %0, %1, %2, 0, 0x30;" : "=r"(r) : "r"(a), "r"(b)); return r; }   // a & ~b
+FZ_HD uint32_t log2p(uint32_t v) { uint32_t r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }                                   // v = 2^k -> k
+FZ_HD sm_t opaque(sm_t v) { asm("" : "+r"(v)); return v; }          // keeps an address sum out of the reassociation of the final add
+#else
+typedef uintptr_t sm_t;
+FZ_HD sm_t sm_of(const void* p) { return (uintptr_t)p; }
+FZ_HD uint32_t sm_ld16(sm_t a) { return *(const uint16_t*)a; }
+FZ_HD uint32_t sm_ld32(sm_t a) { return *(const uint32_t*)a; }
+FZ_HD sm_t ring_slot(sm_t ring, uint32_t b) { return ring + (b & 0xFCu); }
+FZ_HD void ring_fetch_sm(sm_t slot, const uint8_t* gsrc) { for (int i = 0; i < 16; i++) ((uint8_t*)slot)[i] = gsrc[i]; }
+FZ_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+FZ_HD uint32_t fsl_w(uint32_t lo, uint32_t hi, uint32_t n) { n &= 31; return n ? (hi << n) | (lo >> (32 - n)) : hi; }
+FZ_HD uint32_t andn32(uint32_t a, uint32_t b) { return a & ~b; }
+FZ_HD uint32_t log2p(uint32_t v) { return (uint32_t)highbit(v); }
+FZ_HD sm_t opaque(sm_t v) { return v; }
+#endif
 
-// Stage A.  `mem` = this stream's kChainBytes of shared memory.  Writes nseq RAW records at `out`.
+// Backward bitstream of a sequences section, addressed by a BIT CURSOR instead of a bit container: `cur` is the bit
+// address of the highest unread bit, counted from gbase = (stream pointer & ~255), so that (cur >> 3) & 255 is at the
+// same time the byte's slot in the 256-byte cp.async ring.  A sequence needs no refill logic and no branches: it
+// loads the three ring words under the cursor, funnels them into a 64-bit window and moves the cursor down.
+// Bits below the first byte of the stream read as garbage; a stream that uses them ends below `lo` and is corrupt.
+struct SeqCursor {
+    int32_t cur, lo;         // lo = bit address of the stream's first bit; everything is read <=> cur == lo - 1
+    const uint8_t* gbase;
+    sm_t ring;
+    int32_t fa, fmin;        // byte offset (from gbase) of the next 16-byte chunk to fetch, going down / of the lowest chunk
+
+    FZ_HD void fill()        // every free ring slot: a slot is free once the cursor's word is below the chunk it held
+    {
+        const int32_t bw = (cur >> 3) & ~3;
+        while (fa >= fmin && fa + 256 > bw) { ring_fetch_sm(ring + ((uint32_t)fa & 255u), gbase + fa); fa -= 16; }
+    }
+    FZ_HD int init(const uint8_t* p, uint32_t n, uint8_t* ring_)
+    {
+        if (n == 0) return -1;
+        const uint8_t* lastp = p + n - 1;
+        const uint32_t lastb = *lastp;
+        if (lastb == 0) return -1;
+        gbase = (const uint8_t*)((uintptr_t)p & ~(uintptr_t)255);
+        ring = sm_of(ring_);
+        lo = (int32_t)(p - gbase) * 8;
+        cur = (int32_t)(lastp - gbase) * 8 + highbit(lastb) - 1;     // just below the sentinel bit
+        fa = (int32_t)(lastp - gbase) & ~15; fmin = (int32_t)(p - gbase) & ~15;
+        for (int i = 0; i < 16 && fa >= fmin; i++) { ring_fetch_sm(ring + ((uint32_t)fa & 255u), gbase + fa); fa -= 16; }
+        ring_commit(); ring_wait<0>();
+        return 0;
+    }
+    FZ_HD uint32_t peek() const                        // the 32 bits under the cursor, highest first
+    {
+        const uint32_t b = (uint32_t)(cur >> 3);
+        return fsl_w(sm_ld32(ring_slot(ring, b - 4)), sm_ld32(ring_slot(ring, b)), ~(uint32_t)cur & 31u);
+    }
+    FZ_HD uint32_t read(uint32_t nb) { const uint32_t v = shr_c(peek(), 32 - nb); cur -= (int32_t)nb; return v; }   // nb <= 32
+};
+
+// Stage A.  `mem` = this stream's kChainBytes of shared memory (256-byte aligned on the device).  Writes nseq RAW
+// records at `out`.
 // SIMT shape: the lanes of a warp run different blocks, so the loop must stay in lockstep or the warp
 // degenerates into serial threads: single exit, the table build (data-dependent control flow) is
 // fenced off with a warp barrier, and the loop runs a warp-uniform number of iterations (`bound` =
 // the largest nseq - 1 among the lanes in `mask`), each lane masking itself out when its block is
 // done.  The last sequence of a block updates no state; it is decoded after the loop, by all lanes at once.
+//
+// One iteration is straight-line code, ~60 instructions, and its critical path is
+//   state -> LDS cell -> sum of the extra-bit counts -> funnel -> multiply-high -> next state:
+// * the states are kept as the ADDRESSES of their cells (table base + 2 * state);
+// * with J = ((baseline >> nb) << 1 | 1) << nb, 2 * baseline is J & (J - 1) and 2^nb is J & ~(J - 1), so the nb state
+//   bits at the top of a window y are umulhi(y, 2^nb) and the window moves on by y * 2^nb: no bit counts, no variable
+//   shifts; the bits consumed by the three updates together are log2 of the product of the three powers;
+// * the window (x:xlo = the 64 bits under the cursor) does not depend on the cells, so its loads overlap theirs.
+// A sequence whose extra bits exceed 32 (long lengths with a far offset: rare) is read field by field.
 FZ_HD int decode_sequences_chain(const Block* blocks, const Block& b, const SeqConsts& K, uint8_t* mem,
                                  uint64_t* out, uint32_t bound, uint32_t mask)
 {
@@ -964,73 +1023,74 @@ FZ_HD int decode_sequences_chain(const Block* blocks, const Block& b, const SeqC
     uint16_t* scratch = cOF + kChainCellsOF;                          // 256 bytes: table-build scratch, then the bitstream ring
     int st = 0;
     int logLL = 0, logOF = 0, logML = 0;
-    SeqBits br;
-    uint32_t sLL = 0, sOF = 0, sML = 0;
+    SeqCursor cs; cs.cur = 0; cs.lo = 0; cs.gbase = nullptr; cs.ring = sm_of(scratch); cs.fa = -1; cs.fmin = 0;
+    const sm_t tLL = sm_of(cLL), tML = sm_of(cML), tOF = sm_of(cOF);
+    sm_t aLL = tLL, aML = tML, aOF = tOF;                             // addresses of the current cells
     {
         const uint8_t* p = b.src + b.seq_hdr; uint32_t n = b.csize - b.seq_hdr; uint32_t used = 0;
         if (build_chain_seq_table(blocks, b, 0, p, n, K, cLL, logLL, used, scratch) != 0) st = FZG_E_CORRUPT;
         if (!st) { p += used; n -= used; if (build_chain_seq_table(blocks, b, 1, p, n, K, cOF, logOF, used, scratch) != 0) st = FZG_E_CORRUPT; }
         if (!st) { p += used; n -= used; if (build_chain_seq_table(blocks, b, 2, p, n, K, cML, logML, used, scratch) != 0) st = FZG_E_CORRUPT; }
-        if (!st) { p += used; n -= used; if (br.init(p, n, (uint8_t*)scratch) != 0) st = FZG_E_CORRUPT; }
+        if (!st) { p += used; n -= used; if (cs.init(p, n, (uint8_t*)scratch) != 0) st = FZG_E_CORRUPT; }
         if (!st) {
-            br.refill(); br.refill();
-            sLL = br.read((uint32_t)logLL);
-            sOF = br.read((uint32_t)logOF);
-            sML = br.read((uint32_t)logML);
-            if (br.left < 0) st = FZG_E_CORRUPT;
+            aLL = tLL + 2 * cs.read((uint32_t)logLL);
+            aOF = tOF + 2 * cs.read((uint32_t)logOF);
+            aML = tML + 2 * cs.read((uint32_t)logML);
+            if (cs.cur < cs.lo - 1) st = FZG_E_CORRUPT;
         }
     }
     const uint32_t nseq = b.nseq;
     const uint32_t live = st ? 0 : nseq - 1;            // this lane's trip count (nseq >= 1 for a sequence job)
+    const uint32_t ypack = (uint32_t)tLL + ((uint32_t)tLL << 12);    // turns cell addresses into offsets inside `mem`
+    // A lane whose block is finished keeps running on garbage (every address it forms stays inside its own tables and
+    // ring, its stores are predicated off); its state as of iteration `live` is kept aside for the last sequence.
+    sm_t fLL = aLL, fML = aML, fOF = aOF; int32_t fcur = cs.cur;
     FZ_SYNCWARP(mask);
-    for (uint32_t i = 0; i < bound; i++) {
-        if ((i & 3) == 0) {                              // keep the ring full: <= 44 bytes are consumed between two visits
-            if (i < live) br.fill();
-            ring_commit(); ring_wait<2>();               // the words consumed now were fetched >= 5 visits ago
-        }
-        if (i < live) {
-            const uint32_t cl = cLL[sLL], co = cOF[sOF], cm = cML[sML];
-            const uint32_t jl = cl & 1023u, jo = co & 1023u, jm = cm & 1023u;
-            const uint32_t llb = cl >> 10, ofb = co >> 10, mlb = cm >> 10;
-            const uint32_t nLL = ctz32(jl), nML = ctz32(jm), nOF = ctz32(jo);
-            const uint32_t a3 = ofb + mlb + llb, a4 = a3 + nLL, a5 = a4 + nML, need = a5 + nOF;
-            br.refill();
-            uint64_t raw;
-            if (need <= 32) {                     // common case: every field of this sequence sits in `hi`
-                const uint32_t x = br.hi;
-                raw = raw_pack_fast(x, sLL, sML, ofb);
-                sLL = ((jl & (jl - 1)) >> 1) + shr_c(shl_c(x, a3), 32 - nLL);
-                sML = ((jm & (jm - 1)) >> 1) + shr_c(shl_c(x, a4), 32 - nML);
-                sOF = ((jo & (jo - 1)) >> 1) + shr_c(shl_c(x, a5), 32 - nOF);
-                br.skip(need);
-            } else {                              // long offsets / lengths: field by field
-                const uint32_t x = br.hi;
-                const uint32_t ofx = br.read(ofb);
-                br.refill();
-                const uint32_t mlx = br.read(mlb), llx = br.read(llb);
-                br.refill();
-                raw = a3 <= 32 ? raw_pack_fast(x, sLL, sML, ofb) : raw_slow(blocks, b, K, sLL, sML, ofb, ofx, mlx, llx, st);
-                sLL = ((jl & (jl - 1)) >> 1) + br.read(nLL);
-                sML = ((jm & (jm - 1)) >> 1) + br.read(nML);
-                sOF = ((jo & (jo - 1)) >> 1) + br.read(nOF);
-            }
-            out[i] = raw;
+    for (uint32_t i0 = 0; i0 < bound; i0 += 4, out += 4) {
+        // keep the ring full: <= 45 bytes are consumed between two visits, so a chunk fetched at visit v (>= 240 bytes
+        // below the cursor of visit v - 1) is not read before visit v + 3
+        if (i0 < live) cs.fill();
+        ring_commit(); ring_wait<3>();
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (uint32_t k = 0; k < 4; k++) {
+            const uint32_t i = i0 + k;
+            if (i == live) { fLL = aLL; fML = aML; fOF = aOF; fcur = cs.cur; }
+            const uint32_t cl = sm_ld16(aLL), co = sm_ld16(aOF), cm = sm_ld16(aML);
+            const int32_t cur0 = cs.cur;
+            const uint32_t bb = (uint32_t)(cur0 >> 3), t = ~(uint32_t)cur0 & 31u;
+            const uint32_t wa = sm_ld32(ring_slot(cs.ring, bb)), wb = sm_ld32(ring_slot(cs.ring, bb - 4)),
+                           wc = sm_ld32(ring_slot(cs.ring, bb - 8)), wd = sm_ld32(ring_slot(cs.ring, bb - 12));
+            const uint32_t x = fsl_w(wb, wa, t), x1 = fsl_w(wc, wb, t), x2 = fsl_w(wd, wc, t);     // the 96 bits under the cursor
+            const uint32_t llb = cl >> 10, ofb = co >> 10, mlb = cm >> 10, a3 = llb + ofb + mlb;   // a3 <= 63
+            const uint32_t l1 = cl - 1, o1 = co - 1, m1 = cm - 1;
+            const uint32_t pLL = andn32(cl, l1), pOF = andn32(co, o1), pML = andn32(cm, m1);       // 2^nb of the three updates
+            const sm_t bLL = opaque(tLL + (cl & l1 & 1023u)), bOF = opaque(tOF + (co & o1 & 1023u)), bML = opaque(tML + (cm & m1 & 1023u));   // cells of the baselines
+            const uint32_t nsum = log2p(pLL * pML * pOF);
+            // y = the 32 bits that follow the a3 extra bits: two clamped funnel shifts, by min(a3, 32) and by the rest
+            const uint32_t far = a3 > 32 ? 1u : 0u, rest = a3 > 32 ? a3 - 32 : 0u;
+            const uint32_t y = fsl_c(fsl_c(x2, x1, a3), fsl_c(x1, x, a3), rest);
+            const uint32_t yrec = (uint32_t)aLL + ((uint32_t)aML << 12) + (ofb << 24) + (far << 31) - ypack;
+            if (i < live) out[k] = raw_pack(far ? (uint32_t)cur0 : x, yrec);
+            const uint32_t y1 = y * pLL, y2 = y1 * pML;
+            aLL = bLL + 2 * mulhi32(y, pLL);
+            aML = bML + 2 * mulhi32(y1, pML);
+            aOF = bOF + 2 * mulhi32(y2, pOF);
+            cs.cur = cur0 - (int32_t)(a3 + nsum);
         }
     }
+    out -= (bound + 3) & ~3u;
+    if (live >= ((bound + 3) & ~3u)) { fLL = aLL; fML = aML; fOF = aOF; fcur = cs.cur; }
     ring_wait<0>();
     if (!st) {                                    // the last sequence: its three fields, no state update
-        br.fill(); ring_commit(); ring_wait<0>();
-        const uint32_t cl = cLL[sLL], co = cOF[sOF], cm = cML[sML];
-        const uint32_t llb = cl >> 10, ofb = co >> 10, mlb = cm >> 10;
-        br.refill();
-        if (ofb + mlb + llb <= 32) { out[nseq - 1] = raw_pack_fast(br.hi, sLL, sML, ofb); br.skip(ofb + mlb + llb); }
-        else {
-            const uint32_t ofx = br.read(ofb);
-            br.refill();
-            const uint32_t mlx = br.read(mlb), llx = br.read(llb);
-            out[nseq - 1] = raw_slow(blocks, b, K, sLL, sML, ofb, ofx, mlx, llx, st);
-        }
-        if (br.left != 0) st = FZG_E_CORRUPT;
+        cs.cur = fcur;
+        cs.fill(); ring_commit(); ring_wait<0>();
+        const uint32_t co = sm_ld16(fOF), cl = sm_ld16(fLL), cm = sm_ld16(fML);
+        const uint32_t ofb = co >> 10, a3 = ofb + (cl >> 10) + (cm >> 10);
+        const uint32_t far = a3 > 32 ? 1u : 0u;
+        out[nseq - 1] = raw_pack(far ? (uint32_t)fcur : cs.peek(), (uint32_t)fLL + ((uint32_t)fML << 12) + (ofb << 24) + (far << 31) - ypack);
+        if (fcur - (int32_t)a3 != cs.lo - 1) st = FZG_E_CORRUPT;
     }
     return st;
 }

@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kLitThreads, 1) k_literals(Block* blocks, cons
 #endif
 constexpr int kSeqStreams = FZ_SEQ_STREAMS;
 #ifndef FZ_SEQ_LANES
-#define FZ_SEQ_LANES 8
+#define FZ_SEQ_LANES 32
 #endif
 constexpr int kSeqLanes = FZ_SEQ_LANES;
 constexpr int kSeqWarps = (kSeqStreams + kSeqLanes - 1) / kSeqLanes;
@@ -145,7 +145,9 @@ constexpr int kSeqSmem = kSeqStreams * kChainBytes;
 __global__ void __launch_bounds__(kSeqThreads, 1) k_sequences(Block* blocks, const uint32_t* jobs, uint32_t n_jobs, uint64_t* seqs,
                                                                 uint32_t* ticket)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(256) uint8_t smem_seq[];   // kChainBytes is a multiple of 256: every stream's ring is 256-byte aligned
+    uint8_t* const smem = smem_seq;
+    if (((uint32_t)__cvta_generic_to_shared(smem) & 255u) != 0) __trap();
     __shared__ SeqConsts K;
     for (uint32_t i = threadIdx.x; i < sizeof(SeqConsts) / 4; i += blockDim.x) ((uint32_t*)&K)[i] = ((const uint32_t*)&c_seq_consts)[i];
     __syncthreads();
@@ -196,8 +198,10 @@ __global__ void __launch_bounds__(kRecWarps * 32) k_records(Block* blocks, const
     Block& b = blocks[jobs[job]];
     if (b.status) return;
     const uint8_t* yLL = s_y[warp][0]; const uint8_t* yML = s_y[warp][1];
-    if (lane == 0) s_err[warp] = build_symbol_maps(blocks, b, K, s_y[warp][0], s_y[warp][1], s_norm[warp]);
+    __shared__ const uint8_t* s_bits[kRecWarps];
+    if (lane == 0) s_err[warp] = build_symbol_maps(blocks, b, K, s_y[warp][0], s_y[warp][1], s_norm[warp], s_bits[warp]);
     __syncwarp();
+    const uint8_t* const bits = s_bits[warp];
     if (s_err[warp]) { if (lane == 0) b.status = FZG_E_CORRUPT; return; }
     const uint32_t nseq = b.nseq, lit_regen = b.lit_regen, block_max = frames[b.frame].block_max;
     uint64_t* sq = seqs + b.seq_base;
@@ -207,7 +211,7 @@ __global__ void __launch_bounds__(kRecWarps * 32) k_records(Block* blocks, const
         const uint32_t i = g + lane; const bool valid = i < nseq;
         const uint32_t nv = min(32u, nseq - g);
         uint32_t ll = 0, ml = 0, ofv = 4; bool ok = true;
-        if (valid) ok = raw_unpack(sq[i], K, yLL, yML, ll, ml, ofv);
+        if (valid) ok = raw_unpack(sq[i], K, yLL, yML, bits, ll, ml, ofv);
         const uint32_t LE = LEbase + warp_scan_incl(ll, lane), E = Ebase + warp_scan_incl(ll + ml, lane);
         // ---- repeat offsets
         uint32_t off = ofv - 3;

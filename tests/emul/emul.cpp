@@ -16,6 +16,8 @@
 
 using namespace fz;
 
+static uint64_t g_far_records = 0;     // RAW records in the far form (extra bits > 32) seen so far
+extern "C" uint64_t fze_far_records(void) { return g_far_records; }
 static const SeqConsts kConsts = { FZ_LL_BASE, FZ_ML_BASE, FZ_LL_BITS, FZ_ML_BITS, FZ_LL_DEF, FZ_OF_DEF, FZ_ML_DEF };
 
 // TEST-ONLY serial restatement of stage B (k_records in fz_decode.cu is warp-parallel CUDA): RAW records ->
@@ -25,11 +27,12 @@ static void records_serial(const Block* blocks, Block& b, uint32_t block_max, ui
     if (b.status) return;
     uint64_t* sq = seqs + b.seq_base;
     static uint8_t yLL[512], yML[512]; int16_t norm_buf[64];
-    if (build_symbol_maps(blocks, b, kConsts, yLL, yML, norm_buf) != 0) { b.status = FZG_E_CORRUPT; return; }
+    const uint8_t* bits = nullptr;
+    if (build_symbol_maps(blocks, b, kConsts, yLL, yML, norm_buf, bits) != 0) { b.status = FZG_E_CORRUPT; return; }
     uint32_t rep0 = off_sym(0), rep1 = off_sym(1), rep2 = off_sym(2), E = 0, LE = 0;
     for (uint32_t i = 0; i < b.nseq; i++) {
         uint32_t ll, ml, ofv;
-        bool ok = raw_unpack(sq[i], kConsts, yLL, yML, ll, ml, ofv);
+        bool ok = raw_unpack(sq[i], kConsts, yLL, yML, bits, ll, ml, ofv);
         const uint32_t off = rep_update(ofv, ll == 0, rep0, rep1, rep2);
         LE += ll; E += ll + ml;
         if (!ok || (ofv > 3 && off > kOffMax) || LE > b.lit_regen || E > block_max) { b.status = FZG_E_CORRUPT; return; }
@@ -113,6 +116,7 @@ extern "C" int fze_decode_batch(size_t n, const void* const* src, const size_t* 
     for (uint32_t j = 0; j < run.seq_job; j++) {
         Block& b = blocks[seq_jobs[j]];
         seq_chain_thread(blocks.data(), b, kConsts, chain_mem, seqs.data(), b.nseq - 1, 1);
+        if (!b.status) for (uint32_t i = 0; i < b.nseq; i++) g_far_records += seqs[b.seq_base + i] >> 63;
         records_serial(blocks.data(), b, frames[b.frame].block_max, seqs.data());
     }
     // offsets

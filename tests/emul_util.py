@@ -48,3 +48,25 @@ def trace(blob, max_seq=1 << 21, max_lit=1 << 22):
 def fse_roundtrip(syms, n_sym, max_log):
     a = np.ascontiguousarray(syms, dtype=np.uint8)
     return lib().fze_fse_roundtrip(C.c_void_p(a.ctypes.data), C.c_size_t(a.size), n_sym, max_log)
+
+
+def far_records():
+    """RAW records in the far form (extra bits of one sequence > 32: stage A stores the bit cursor) seen so far"""
+    L = lib(); L.fze_far_records.restype = C.c_uint64
+    return L.fze_far_records()
+
+
+def far_offset_long_length_plain(seed=11, base=200000, pieces=40):
+    """plain bytes whose level-19 parse has sequences with a long literal run AND a far offset AND a long match:
+    low-entropy noise (Huffman-compressible, hardly matchable) with slices of the first `base` bytes planted far later"""
+    rs = np.random.RandomState(seed)
+
+    def noise(n):
+        return (rs.randint(0, 12, n) * rs.randint(1, 12, n)).astype(np.uint8).tobytes()
+    head = noise(base)
+    parts = [head]
+    for j in range(pieces):
+        parts.append(noise(4200 + j * 900))
+        src = 3000 + j * 2000
+        parts.append(head[src:src + 140 + j * 25])
+    return b"".join(parts)

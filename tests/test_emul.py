@@ -76,6 +76,21 @@ def test_mutation_fuzz_matches_oracle(golden, oracle):
                 assert out == out_o
 
 
+def test_far_form_records(ref, oracle):
+    """a sequence whose extra bits exceed the 32-bit window of a RAW record travels as a bit cursor (stage A) and is
+    read back from the stream by stage B: long literal run + far offset + long match in one sequence"""
+    if not ref.available:
+        pytest.skip("system libzstd absent")
+    plain = emul_util.far_offset_long_length_plain()
+    comp = ref.writer_encode(plain, 19)
+    before = emul_util.far_records()
+    (st, out), = emul_util.decode_batch([comp], [len(plain)])
+    assert st == 0 and out == plain
+    assert emul_util.far_records() - before >= 10
+    st_o, out_o = oracle.decode(comp, cap=len(plain))
+    assert st_o == 0 and out_o == plain
+
+
 def test_batch_of_mixed_items(golden):
     good, meta = golden["json_2000_L3_writer"]
     blobs = [good, b"junk", golden["ref_touch_empty_writer"][0], good[:50], golden["multi_frame_skippable"][0]]

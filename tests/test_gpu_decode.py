@@ -217,3 +217,18 @@ def test_large_window_long_distance_and_level19(ref, corpus):
     for i, ((st, out), plain) in enumerate(zip(res, plains)):
         assert st == 0, (i, codec.strerror(st))
         assert hashlib.sha256(out).digest() == hashlib.sha256(plain).digest(), i
+
+
+def test_far_form_records(ref):
+    """sequences with more than 32 extra bits (long literal run + far offset + long match): stage A hands stage B the bit
+    cursor instead of the bits (tests/test_emul.py::test_far_form_records checks that the vector really has such sequences)"""
+    if not ref.available:
+        pytest.skip("system libzstd absent")
+    import emul_util
+    plains = [emul_util.far_offset_long_length_plain(seed) for seed in (11, 12, 13)]
+    blobs = [ref.writer_encode(p, 19) for p in plains] + [ref.writer_encode(plains[0], 3)]
+    plains.append(plains[0])
+    res = codec.decode_batch(blobs, [len(p) for p in plains])
+    for i, ((st, out), plain) in enumerate(zip(res, plains)):
+        assert st == 0, (i, codec.strerror(st))
+        assert out == plain, i

@@ -27,3 +27,10 @@ if R.available:
         s, out = R.copy_decode(host[i * cap:i * cap + int(dl[i])].tobytes(), size)
         ok += (s == 0 and out == plain[i].tobytes()); l3 += len(R.writer_encode(plain[i].tobytes(), 3))
     print("libzstd round trip: %d / %d files ok; bytes vs libzstd L3: x%.3f" % (ok, k, dl[:k].sum() / l3), file=sys.stderr)
+    k2 = min(n, 64)
+    sp = np.array([plain[i].ctypes.data for i in range(k2)], dtype=np.uint64); sl = np.full(k2, size, dtype=np.uint64)
+    bound = R.bound(size) + 64; comp = np.empty((k2, bound), dtype=np.uint8)
+    dp2 = np.array([comp[i].ctypes.data for i in range(k2)], dtype=np.uint64); dc = np.full(k2, bound, dtype=np.uint64)
+    R.batch(2, os.cpu_count(), sp, sl, dp2, dc, 3)
+    t, ol, st2 = R.batch(2, os.cpu_count(), sp, sl, dp2, dc, 3)
+    print("CPU reference writer (libzstd %d level 3, %d threads): %.2f GB/s in, ratio %.3f" % (R.version, os.cpu_count(), k2 * size / 1e9 / t, k2 * size / ol.sum()), file=sys.stderr)
