@@ -324,7 +324,7 @@ FZ_HD void walk_item(uint32_t item_idx, const Item& it, ItemInfo& info, const It
                 }
                 if (nseq) {
                     if (FILL) { b.seq_base = base->seq + n_seq; seq_jobs[base->seq_job + nsj] = gb; }
-                    n_seq += nseq; nsj++;
+                    n_seq += (nseq + 3u) & ~3u; nsj++;          // records of a block start on a 32-byte boundary (256-bit stores)
                 }
                 if (lh.type != LT_RAW) { if (FILL) huf_jobs[base->huf_job + nhj] = gb; nhj++; }
             }
@@ -947,6 +947,10 @@ FZ_HD uint32_t fsl_w(uint32_t lo, uint32_t hi, uint32_t n) { return __funnelshif
 FZ_HD uint32_t andn32(uint32_t a, uint32_t b) { uint32_t r; asm("lop3.b32 %0, %1, %2, 0, 0x30;" : "=r"(r) : "r"(a), "r"(b)); return r; }   // a & ~b
 FZ_HD uint32_t log2p(uint32_t v) { uint32_t r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }                                   // v = 2^k -> k
 FZ_HD sm_t opaque(sm_t v) { asm("" : "+r"(v)); return v; }          // keeps an address sum out of the reassociation of the final add
+FZ_HD void st_rec4(uint64_t* p, uint64_t a, uint64_t b, uint64_t c, uint64_t d)      // four records, one 256-bit store (p 32-byte aligned)
+{
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
 #else
 typedef uintptr_t sm_t;
 FZ_HD sm_t sm_of(const void* p) { return (uintptr_t)p; }
@@ -959,6 +963,7 @@ FZ_HD uint32_t fsl_w(uint32_t lo, uint32_t hi, uint32_t n) { n &= 31; return n ?
 FZ_HD uint32_t andn32(uint32_t a, uint32_t b) { return a & ~b; }
 FZ_HD uint32_t log2p(uint32_t v) { return (uint32_t)highbit(v); }
 FZ_HD sm_t opaque(sm_t v) { return v; }
+FZ_HD void st_rec4(uint64_t* p, uint64_t a, uint64_t b, uint64_t c, uint64_t d) { p[0] = a; p[1] = b; p[2] = c; p[3] = d; }
 #endif
 
 // Backward bitstream of a sequences section, addressed by a BIT CURSOR instead of a bit container: `cur` is the bit
@@ -1000,6 +1005,57 @@ struct SeqCursor {
     FZ_HD uint32_t read(uint32_t nb) { const uint32_t v = shr_c(peek(), 32 - nb); cur -= (int32_t)nb; return v; }   // nb <= 32
 };
 
+// The registers of one chain: addresses of the current LL / ML / OF cells, the table bases, and the constant that turns
+// the LL / ML addresses into the record's offsets.
+struct ChainRegs { sm_t aLL, aML, aOF, tLL, tML, tOF; uint32_t ypack; };
+
+// One sequence of one chain: emits its RAW record and moves the three states and the cursor on.  Straight-line code.
+// vote_mask != 0: all lanes of vote_mask are here together (main loop) and the rare sequence with more than 32 extra
+// bits is handled under a warp-uniform branch; vote_mask == 0: the caller is already divergent (ragged end).
+template <bool VOTED>
+FZ_HD uint64_t chain_step(ChainRegs& r, SeqCursor& cs, uint32_t vote_mask)
+{
+    const uint32_t cl = sm_ld16(r.aLL), co = sm_ld16(r.aOF), cm = sm_ld16(r.aML);
+    const int32_t cur0 = cs.cur;
+    const uint32_t bb = (uint32_t)(cur0 >> 3), t = ~(uint32_t)cur0 & 31u;
+    const uint32_t wa = sm_ld32(ring_slot(cs.ring, bb)), wb = sm_ld32(ring_slot(cs.ring, bb - 4)), wc = sm_ld32(ring_slot(cs.ring, bb - 8));
+    const uint32_t x = fsl_w(wb, wa, t), x1 = fsl_w(wc, wb, t);                               // the 64 bits under the cursor
+    const uint32_t llb = cl >> 10, ofb = co >> 10, mlb = cm >> 10, a3 = llb + ofb + mlb;      // extra bits of this sequence (<= 63)
+    const uint32_t l1 = cl - 1, o1 = co - 1, m1 = cm - 1;
+    const uint32_t pLL = andn32(cl, l1), pOF = andn32(co, o1), pML = andn32(cm, m1);          // 2^nb of the three updates
+    const sm_t bLL = opaque(r.tLL + (cl & l1 & 1023u)), bOF = opaque(r.tOF + (co & o1 & 1023u)), bML = opaque(r.tML + (cm & m1 & 1023u));   // cells of the baselines
+    const uint32_t nsum = log2p(pLL * pML * pOF);
+    uint32_t y, xrec = x, yrec = (uint32_t)r.aLL + ((uint32_t)r.aML << 12) + (ofb << 24) - r.ypack;
+    const bool far = a3 > 32;
+#if defined(__CUDA_ARCH__) && !defined(FZ_CHAIN_VOTED)
+    if (VOTED) {                                          // no control flow at all: a fourth ring word covers a3 <= 63
+        const uint32_t wd = sm_ld32(ring_slot(cs.ring, bb - 12)), x2 = fsl_w(wd, wc, t);
+        y = fsl_c(fsl_c(x2, x1, a3), fsl_c(x1, x, a3), far ? a3 - 32 : 0u);
+        xrec = far ? (uint32_t)cur0 : x; yrec += far ? 1u << 31 : 0u;
+    } else
+#endif
+    {
+        y = fsl_c(x1, x, a3);                             // the 32 bits after the extra bits
+#ifdef __CUDA_ARCH__
+        if (__builtin_expect(VOTED ? __any_sync(vote_mask, far) : far, 0))
+#else
+        if (far)
+#endif
+        {
+            if (far) {
+                SeqCursor c2 = cs; c2.cur = cur0 - (int32_t)a3;
+                y = c2.peek(); xrec = (uint32_t)cur0; yrec |= 1u << 31;
+            }
+        }
+    }
+    const uint32_t y1 = y * pLL, y2 = y1 * pML;
+    r.aLL = bLL + 2 * mulhi32(y, pLL);
+    r.aML = bML + 2 * mulhi32(y1, pML);
+    r.aOF = bOF + 2 * mulhi32(y2, pOF);
+    cs.cur = cur0 - (int32_t)(a3 + nsum);
+    return raw_pack(xrec, yrec);
+}
+
 // Stage A.  `mem` = this stream's kChainBytes of shared memory (256-byte aligned on the device).  Writes nseq RAW
 // records at `out`.
 // SIMT shape: the lanes of a warp run different blocks, so the loop must stay in lockstep or the warp
@@ -1008,14 +1064,16 @@ struct SeqCursor {
 // the largest nseq - 1 among the lanes in `mask`), each lane masking itself out when its block is
 // done.  The last sequence of a block updates no state; it is decoded after the loop, by all lanes at once.
 //
-// One iteration is straight-line code, ~60 instructions, and its critical path is
+// One iteration (chain_step) is straight-line code, ~55 instructions, and its critical path is
 //   state -> LDS cell -> sum of the extra-bit counts -> funnel -> multiply-high -> next state:
 // * the states are kept as the ADDRESSES of their cells (table base + 2 * state);
 // * with J = ((baseline >> nb) << 1 | 1) << nb, 2 * baseline is J & (J - 1) and 2^nb is J & ~(J - 1), so the nb state
 //   bits at the top of a window y are umulhi(y, 2^nb) and the window moves on by y * 2^nb: no bit counts, no variable
 //   shifts; the bits consumed by the three updates together are log2 of the product of the three powers;
 // * the window (x:xlo = the 64 bits under the cursor) does not depend on the cells, so its loads overlap theirs.
-// A sequence whose extra bits exceed 32 (long lengths with a far offset: rare) is read field by field.
+// A sequence whose extra bits exceed 32 (long lengths with a far offset: rare) hands stage B its bit cursor.
+// The loop is latency-bound: an SM holds 82 chains whatever their arrangement in warps, so what counts is the length
+// of one iteration of one chain, i.e. the instruction count and the dependent chain of chain_step.
 FZ_HD int decode_sequences_chain(const Block* blocks, const Block& b, const SeqConsts& K, uint8_t* mem,
                                  uint64_t* out, uint32_t bound, uint32_t mask)
 {
@@ -1041,56 +1099,46 @@ FZ_HD int decode_sequences_chain(const Block* blocks, const Block& b, const SeqC
     }
     const uint32_t nseq = b.nseq;
     const uint32_t live = st ? 0 : nseq - 1;            // this lane's trip count (nseq >= 1 for a sequence job)
-    const uint32_t ypack = (uint32_t)tLL + ((uint32_t)tLL << 12);    // turns cell addresses into offsets inside `mem`
-    // A lane whose block is finished keeps running on garbage (every address it forms stays inside its own tables and
-    // ring, its stores are predicated off); its state as of iteration `live` is kept aside for the last sequence.
-    sm_t fLL = aLL, fML = aML, fOF = aOF; int32_t fcur = cs.cur;
+#ifdef __CUDA_ARCH__
+    const uint32_t common = __reduce_min_sync(mask, live) & ~3u;     // iterations every lane of the warp runs
+#else
+    const uint32_t common = live & ~3u;
+#endif
+    ChainRegs r{ aLL, aML, aOF, tLL, tML, tOF, (uint32_t)tLL + ((uint32_t)tLL << 12) };
     FZ_SYNCWARP(mask);
-    for (uint32_t i0 = 0; i0 < bound; i0 += 4, out += 4) {
-        // keep the ring full: <= 45 bytes are consumed between two visits, so a chunk fetched at visit v (>= 240 bytes
-        // below the cursor of visit v - 1) is not read before visit v + 3
-        if (i0 < live) cs.fill();
+    // main loop: every lane is live, nothing is predicated; the ring is topped up every fourth sequence: <= 45 bytes are
+    // consumed between two visits, so a chunk fetched at visit v (>= 240 bytes below the cursor of visit v - 1) is not
+    // read before visit v + 3
+    uint32_t i = 0;
+    for (; i < common; i += 4, out += 4) {
+        cs.fill();
         ring_commit(); ring_wait<3>();
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-        for (uint32_t k = 0; k < 4; k++) {
-            const uint32_t i = i0 + k;
-            if (i == live) { fLL = aLL; fML = aML; fOF = aOF; fcur = cs.cur; }
-            const uint32_t cl = sm_ld16(aLL), co = sm_ld16(aOF), cm = sm_ld16(aML);
-            const int32_t cur0 = cs.cur;
-            const uint32_t bb = (uint32_t)(cur0 >> 3), t = ~(uint32_t)cur0 & 31u;
-            const uint32_t wa = sm_ld32(ring_slot(cs.ring, bb)), wb = sm_ld32(ring_slot(cs.ring, bb - 4)),
-                           wc = sm_ld32(ring_slot(cs.ring, bb - 8)), wd = sm_ld32(ring_slot(cs.ring, bb - 12));
-            const uint32_t x = fsl_w(wb, wa, t), x1 = fsl_w(wc, wb, t), x2 = fsl_w(wd, wc, t);     // the 96 bits under the cursor
-            const uint32_t llb = cl >> 10, ofb = co >> 10, mlb = cm >> 10, a3 = llb + ofb + mlb;   // a3 <= 63
-            const uint32_t l1 = cl - 1, o1 = co - 1, m1 = cm - 1;
-            const uint32_t pLL = andn32(cl, l1), pOF = andn32(co, o1), pML = andn32(cm, m1);       // 2^nb of the three updates
-            const sm_t bLL = opaque(tLL + (cl & l1 & 1023u)), bOF = opaque(tOF + (co & o1 & 1023u)), bML = opaque(tML + (cm & m1 & 1023u));   // cells of the baselines
-            const uint32_t nsum = log2p(pLL * pML * pOF);
-            // y = the 32 bits that follow the a3 extra bits: two clamped funnel shifts, by min(a3, 32) and by the rest
-            const uint32_t far = a3 > 32 ? 1u : 0u, rest = a3 > 32 ? a3 - 32 : 0u;
-            const uint32_t y = fsl_c(fsl_c(x2, x1, a3), fsl_c(x1, x, a3), rest);
-            const uint32_t yrec = (uint32_t)aLL + ((uint32_t)aML << 12) + (ofb << 24) + (far << 31) - ypack;
-            if (i < live) out[k] = raw_pack(far ? (uint32_t)cur0 : x, yrec);
-            const uint32_t y1 = y * pLL, y2 = y1 * pML;
-            aLL = bLL + 2 * mulhi32(y, pLL);
-            aML = bML + 2 * mulhi32(y1, pML);
-            aOF = bOF + 2 * mulhi32(y2, pOF);
-            cs.cur = cur0 - (int32_t)(a3 + nsum);
-        }
+        uint64_t raw[4];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (uint32_t k = 0; k < 4; k++) raw[k] = chain_step<true>(r, cs, mask);
+        st_rec4(out, raw[0], raw[1], raw[2], raw[3]);     // a scattered store costs the LSU one cycle per lane whatever its width
+    }
+    // the ragged end: lanes drop out one by one
+    for (; i < bound; i += 4, out += 4) {
+        if (i < live) cs.fill();
+        ring_commit(); ring_wait<3>();
+        for (uint32_t k = 0; k < 4; k++)
+            if (i + k < live) out[k] = chain_step<false>(r, cs, 0);
     }
     out -= (bound + 3) & ~3u;
-    if (live >= ((bound + 3) & ~3u)) { fLL = aLL; fML = aML; fOF = aOF; fcur = cs.cur; }
     ring_wait<0>();
     if (!st) {                                    // the last sequence: its three fields, no state update
-        cs.cur = fcur;
         cs.fill(); ring_commit(); ring_wait<0>();
-        const uint32_t co = sm_ld16(fOF), cl = sm_ld16(fLL), cm = sm_ld16(fML);
+        const uint32_t co = sm_ld16(r.aOF), cl = sm_ld16(r.aLL), cm = sm_ld16(r.aML);
         const uint32_t ofb = co >> 10, a3 = ofb + (cl >> 10) + (cm >> 10);
         const uint32_t far = a3 > 32 ? 1u : 0u;
-        out[nseq - 1] = raw_pack(far ? (uint32_t)fcur : cs.peek(), (uint32_t)fLL + ((uint32_t)fML << 12) + (ofb << 24) + (far << 31) - ypack);
-        if (fcur - (int32_t)a3 != cs.lo - 1) st = FZG_E_CORRUPT;
+        out[nseq - 1] = raw_pack(far ? (uint32_t)cs.cur : cs.peek(), (uint32_t)r.aLL + ((uint32_t)r.aML << 12) + (ofb << 24) + (far << 31) - r.ypack);
+        if (cs.cur - (int32_t)a3 != cs.lo - 1) st = FZG_E_CORRUPT;
     }
     return st;
 }
