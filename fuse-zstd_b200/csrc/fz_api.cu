@@ -45,7 +45,11 @@ extern "C" int fzg_init(const int* devices, int n_devices)
     for (int d : devs) if (d < 0 || d >= visible) return -EINVAL;
     for (int d : devs) {
         CKR(cudaSetDevice(d));
-        if (const char* g = getenv("FZG_L2_GRAN")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));   // experiment knob
+        if (const char* g = getenv("FZG_L2_GRAN")) {                                                                       // experiment knob
+            cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g)); size_t got = 0;
+            cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+            fprintf(stderr, "fzgpu: L2 fetch granularity: asked %s, set -> %s, now %zu\n", g, cudaGetErrorString(e), got);
+        }
         FzCtx* c = new FzCtx();
         c->dev = d;
         const char* nl = getenv("FZG_LANES");

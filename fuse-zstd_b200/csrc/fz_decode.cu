@@ -457,6 +457,23 @@ __device__ __forceinline__ void exec_block_warp(uint8_t* stage, const Block& b, 
         __syncwarp();
         Ecarry = gE; LEcarry = __shfl_sync(kFull, LE, m - 1);
         g += m;
+#ifndef FZ_EXEC_NO_PREFETCH
+        // The next round's match sources lie a random distance back in the window (HBM): ask for them now, a whole round
+        // (thousands of cycles: ~48 warps share the SM) before they are read, so that the round finds them in L2.
+        {
+            const uint32_t nn = g < nseq ? min(32u, nseq - g) : 0u;
+            const uint32_t En = rec_e(rcur), LEn = rec_le(rcur);
+            uint32_t Sn = __shfl_up_sync(kFull, En, 1), LEpn = __shfl_up_sync(kFull, LEn, 1);
+            if (lane == 0) { Sn = Ecarry; LEpn = LEcarry; }
+            const uint32_t Mn = Sn + (LEn - LEpn);
+            const uint32_t offn = off_resolve(rec_off(rcur), in0, in1, in2);
+            if (lane < nn && offn != 0 && (uint64_t)offn <= done + Mn) {
+                const uint8_t* sp = g0 + Mn - offn;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(sp));
+                if ((((uintptr_t)sp + (En - Mn) - 1) ^ (uintptr_t)sp) & ~(uintptr_t)31) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + (En - Mn) - 1));
+            }
+        }
+#endif
     }
     // literals after the last sequence
     warp_copy(g0 + Ecarry, lit + LEcarry, rsize - Ecarry, lane);
