@@ -647,30 +647,54 @@ template <int N> FZ_HD void ring_wait()
 #endif
 }
 
-struct SeqBits {
-    uint32_t hi, lo; int avail, left;
-    const uint8_t* cmin;     // 16-byte aligned address at or below the first byte of the stream
-    uint8_t* ring;           // 256 bytes of shared memory, 16-byte aligned
-    uint32_t rb;             // (uint32_t)cmin & 255
-    int32_t wa;              // offset from cmin of the next word to hand out (going down)
-    int32_t fa;              // offset from cmin of the next chunk to fetch (going down)
-    int32_t wmin;            // offset of the lowest word holding stream bytes
+// ---- shared-memory access of the chain loop: 32-bit shared-window addresses on the device (one LDS with an
+// immediate offset, no generic-address arithmetic), plain pointers in the host emulation
+#ifdef __CUDA_ARCH__
+typedef uint32_t sm_t;
+FZ_HD sm_t sm_of(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+FZ_HD uint32_t sm_ld16(sm_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+FZ_HD uint32_t sm_ld32(sm_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+FZ_HD sm_t ring_slot(sm_t ring, uint32_t b) { return ring | (b & 0xFCu); }            // the ring is 256-byte aligned
+FZ_HD void ring_fetch_sm(sm_t slot, const uint8_t* gsrc) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(gsrc) : "memory"); }
+FZ_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+FZ_HD uint32_t fsl_w(uint32_t lo, uint32_t hi, uint32_t n) { return __funnelshift_l(lo, hi, n); }   // high word of (hi:lo << (n & 31))
+FZ_HD uint32_t andn32(uint32_t a, uint32_t b) { uint32_t r; asm("lop3.b32 %0, %1, %2, 0, 0x30;" : "=r"(r) : "r"(a), "r"(b)); return r; }   // a & ~b
+FZ_HD uint32_t log2p(uint32_t v) { uint32_t r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }                                   // v = 2^k -> k
+FZ_HD sm_t opaque(sm_t v) { asm("" : "+r"(v)); return v; }          // keeps an address sum out of the reassociation of the final add
+FZ_HD void st_rec4(uint64_t* p, uint64_t a, uint64_t b, uint64_t c, uint64_t d)      // four records, one 256-bit store (p 32-byte aligned)
+{
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+#else
+typedef uintptr_t sm_t;
+FZ_HD sm_t sm_of(const void* p) { return (uintptr_t)p; }
+FZ_HD uint32_t sm_ld16(sm_t a) { return *(const uint16_t*)a; }
+FZ_HD uint32_t sm_ld32(sm_t a) { return *(const uint32_t*)a; }
+FZ_HD sm_t ring_slot(sm_t ring, uint32_t b) { return ring + (b & 0xFCu); }
+FZ_HD void ring_fetch_sm(sm_t slot, const uint8_t* gsrc) { for (int i = 0; i < 16; i++) ((uint8_t*)slot)[i] = gsrc[i]; }
+FZ_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+FZ_HD uint32_t fsl_w(uint32_t lo, uint32_t hi, uint32_t n) { n &= 31; return n ? (hi << n) | (lo >> (32 - n)) : hi; }
+FZ_HD uint32_t andn32(uint32_t a, uint32_t b) { return a & ~b; }
+FZ_HD uint32_t log2p(uint32_t v) { return (uint32_t)highbit(v); }
+FZ_HD sm_t opaque(sm_t v) { return v; }
+FZ_HD void st_rec4(uint64_t* p, uint64_t a, uint64_t b, uint64_t c, uint64_t d) { p[0] = a; p[1] = b; p[2] = c; p[3] = d; }
+#endif
 
-    FZ_HD void top_up()                          // at most one chunk per call; a slot is free once the consumer is below it
+// Backward bitstream of a sequences section, addressed by a BIT CURSOR instead of a bit container: `cur` is the bit
+// address of the highest unread bit, counted from gbase = (stream pointer & ~255), so that (cur >> 3) & 255 is at the
+// same time the byte's slot in the 256-byte cp.async ring.  A sequence needs no refill logic and no branches: it
+// loads the three ring words under the cursor, funnels them into a 64-bit window and moves the cursor down.
+// Bits below the first byte of the stream read as garbage; a stream that uses them ends below `lo` and is corrupt.
+struct SeqCursor {
+    int32_t cur, lo;         // lo = bit address of the stream's first bit; everything is read <=> cur == lo - 1
+    const uint8_t* gbase;
+    sm_t ring;
+    int32_t fa, fmin;        // byte offset (from gbase) of the next 16-byte chunk to fetch, going down / of the lowest chunk
+
+    FZ_HD void fill()        // every free ring slot: a slot is free once the cursor's word is below the chunk it held
     {
-        if (fa >= 0 && fa + 256 > wa) { ring_fetch(ring + ((rb + (uint32_t)fa) & 255u), cmin + fa); fa -= 16; }
-        ring_commit();
-    }
-    FZ_HD void fill()                            // every free slot of the ring
-    {
-        while (fa >= 0 && fa + 256 > wa) { ring_fetch(ring + ((rb + (uint32_t)fa) & 255u), cmin + fa); fa -= 16; }
-    }
-    FZ_HD uint32_t pop()
-    {
-        uint32_t w = *(const uint32_t*)(ring + ((rb + (uint32_t)wa) & 255u));
-        if (wa < wmin) w = 0;                     // below the first byte of the stream: zero bits
-        wa -= 4;
-        return w;
+        const int32_t bw = (cur >> 3) & ~3;
+        while (fa >= fmin && fa + 256 > bw) { ring_fetch_sm(ring + ((uint32_t)fa & 255u), gbase + fa); fa -= 16; }
     }
     FZ_HD int init(const uint8_t* p, uint32_t n, uint8_t* ring_)
     {
@@ -678,74 +702,71 @@ struct SeqBits {
         const uint8_t* lastp = p + n - 1;
         const uint32_t lastb = *lastp;
         if (lastb == 0) return -1;
-        ring = ring_;
-        cmin = (const uint8_t*)((uintptr_t)p & ~(uintptr_t)15);
-        rb = (uint32_t)(uintptr_t)cmin & 255u;
-        wmin = (int32_t)((p - cmin) & ~(ptrdiff_t)3);
-        wa = (int32_t)((lastp - cmin) & ~(ptrdiff_t)3);
-        fa = wa & ~15;
-        for (int i = 0; i < 16; i++) top_up();    // fill the ring
-        ring_wait<0>();
-        uint32_t w = pop();
-        const uint32_t keep = (uint32_t)((uintptr_t)lastp & 3) + 1;
-        if (keep < 4) w &= (1u << (8 * keep)) - 1;
-        const int hb = highbit(w);                // sentinel bit (w != 0: the last byte is non-zero)
-        hi = shl_c(w, 32 - (uint32_t)hb); lo = 0; avail = hb;
-        left = (int)(n - 1) * 8 + highbit(lastb);
+        gbase = (const uint8_t*)((uintptr_t)p & ~(uintptr_t)255);
+        ring = sm_of(ring_);
+        lo = (int32_t)(p - gbase) * 8;
+        cur = (int32_t)(lastp - gbase) * 8 + highbit(lastb) - 1;     // just below the sentinel bit
+        fa = (int32_t)(lastp - gbase) & ~15; fmin = (int32_t)(p - gbase) & ~15;
+        for (int i = 0; i < 16 && fa >= fmin; i++) { ring_fetch_sm(ring + ((uint32_t)fa & 255u), gbase + fa); fa -= 16; }
+        ring_commit(); ring_wait<0>();
         return 0;
     }
-    FZ_HD void refill()                           // no-op unless avail <= 32
+    FZ_HD uint32_t peek() const                        // the 32 bits under the cursor, highest first
     {
-        if (avail <= 32) {
-            const uint32_t w = pop();
-            hi |= shr_c(w, (uint32_t)avail);
-            lo = shl_c(w, 32 - (uint32_t)avail);
-            avail += 32;
-        }
+        const uint32_t b = (uint32_t)(cur >> 3);
+        return fsl_w(sm_ld32(ring_slot(ring, b - 4)), sm_ld32(ring_slot(ring, b)), ~(uint32_t)cur & 31u);
     }
-    FZ_HD uint32_t peek(uint32_t nb) const { return shr_c(hi, 32 - nb); }
-    FZ_HD void skip(uint32_t nb)
-    {
-        hi = fsl_c(lo, hi, nb); lo = shl_c(lo, nb);
-        avail -= (int)nb; left -= (int)nb;
-    }
-    FZ_HD uint32_t read(uint32_t nb) { const uint32_t v = peek(nb); skip(nb); return v; }
+    FZ_HD uint32_t read(uint32_t nb) { const uint32_t v = shr_c(peek(), 32 - nb); cur -= (int32_t)nb; return v; }   // nb <= 32
 };
 
 // One Huffman stream (RFC 8878 4.2.2): regenerates n_out bytes at `out` from the n bytes at p, through the
-// ring-fed reader.  Lanes of a warp decode different streams in lockstep: `bound` is the warp-uniform number
+// ring-fed cursor reader.  Lanes of a warp decode different streams in lockstep: `bound` is the warp-uniform number
 // of 4-symbol iterations (>= n_out / 4 of every lane in `mask`), `ok` false masks the lane out.  Symbols are
 // stored four at a time once the output is 4-byte aligned.  Returns 0 or -1.
+// Four symbols take at most 4 * 12 bits: one 64-bit window (three ring words) per iteration, shifted in registers
+// after each symbol; the chain per symbol is index -> LDS -> length -> shift.  Bits below the first byte of the stream
+// read as garbage: a valid stream never depends on them (they only fill the don't-care part of a table index), a
+// stream that consumes them ends below `lo` and is corrupt.
 FZ_HD int huf_decode_stream(const uint16_t* table, int log, const uint8_t* p, uint32_t n, uint8_t* out, uint32_t n_out,
                             uint8_t* ring, uint32_t bound, uint32_t mask, bool ok)
 {
-    SeqBits br;
-    if (ok && br.init(p, n, ring) != 0) ok = false;
-    const uint32_t ulog = (uint32_t)log;
+    SeqCursor cs; cs.cur = 0; cs.lo = 0; cs.gbase = nullptr; cs.ring = sm_of(ring); cs.fa = -1; cs.fmin = 0;
+    if (ok && cs.init(p, n, ring) != 0) ok = false;
+    const uint32_t sh = 32u - (uint32_t)log;                      // log >= 1 for any valid tree
+    const sm_t tab = sm_of(table);
     uint32_t i = 0;
     if (ok) {
         uint32_t head = (uint32_t)((4 - ((uintptr_t)out & 3)) & 3);                        // <= 3 symbols up to alignment
         if (head > n_out) head = n_out;
-        for (; i < head; i++) { br.refill(); const uint32_t c = table[br.peek(ulog)]; br.skip(c >> 8); out[i] = (uint8_t)c; }
+        for (; i < head; i++) { const uint32_t c = sm_ld16(tab + 2 * shr_c(cs.peek(), sh)); cs.cur -= (int32_t)(c >> 8); out[i] = (uint8_t)c; }
     }
     const uint32_t quads = ok ? (n_out - i) / 4 : 0;
     FZ_SYNCWARP(mask);
     for (uint32_t q = 0; q < bound; q++) {
+        if ((q & 3) == 0) {          // <= 24 bytes are consumed between two visits: a chunk fetched at visit v is not read before visit v + 8
+            if (q < quads) cs.fill();
+            ring_commit(); ring_wait<6>();
+        }
         if (q < quads) {
-            br.top_up(); ring_wait<8>();
-            br.refill();
-            const uint32_t c0 = table[br.peek(ulog)]; br.skip(c0 >> 8);
-            const uint32_t c1 = table[br.peek(ulog)]; br.skip(c1 >> 8);
-            br.refill();
-            const uint32_t c2 = table[br.peek(ulog)]; br.skip(c2 >> 8);
-            const uint32_t c3 = table[br.peek(ulog)]; br.skip(c3 >> 8);
+            const uint32_t bb = (uint32_t)(cs.cur >> 3), t = ~(uint32_t)cs.cur & 31u;
+            const uint32_t wa = sm_ld32(ring_slot(cs.ring, bb)), wb = sm_ld32(ring_slot(cs.ring, bb - 4)), wc = sm_ld32(ring_slot(cs.ring, bb - 8));
+            uint32_t x = fsl_w(wb, wa, t), x1 = fsl_w(wc, wb, t);
+            const uint32_t c0 = sm_ld16(tab + 2 * shr_c(x, sh)), n0 = c0 >> 8; x = fsl_c(x1, x, n0); x1 = shl_c(x1, n0);
+            const uint32_t c1 = sm_ld16(tab + 2 * shr_c(x, sh)), n1 = c1 >> 8; x = fsl_c(x1, x, n1); x1 = shl_c(x1, n1);
+            const uint32_t c2 = sm_ld16(tab + 2 * shr_c(x, sh)), n2 = c2 >> 8; x = fsl_c(x1, x, n2);
+            const uint32_t c3 = sm_ld16(tab + 2 * shr_c(x, sh)), n3 = c3 >> 8;
+            cs.cur -= (int32_t)(n0 + n1 + n2 + n3);
             *(uint32_t*)(out + i) = (c0 & 255u) | ((c1 & 255u) << 8) | ((c2 & 255u) << 16) | (c3 << 24);
             i += 4;
         }
     }
+    ring_wait<0>();
     if (!ok) return -1;
-    for (; i < n_out; i++) { br.top_up(); ring_wait<0>(); br.refill(); const uint32_t c = table[br.peek(ulog)]; br.skip(c >> 8); out[i] = (uint8_t)c; }
-    return br.left == 0 ? 0 : -1;
+    for (; i < n_out; i++) {
+        cs.fill(); ring_commit(); ring_wait<0>();
+        const uint32_t c = sm_ld16(tab + 2 * shr_c(cs.peek(), sh)); cs.cur -= (int32_t)(c >> 8); out[i] = (uint8_t)c;
+    }
+    return cs.cur == cs.lo - 1 ? 0 : -1;
 }
 
 // ------------------------------------------------------------------ sequence pass, stage A: the FSE chain
@@ -932,78 +953,6 @@ FZ_HD uint32_t rep_update(uint32_t ofv, bool ll0, uint32_t& rep0, uint32_t& rep1
     }
     return off;
 }
-
-// ---- shared-memory access of the chain loop: 32-bit shared-window addresses on the device (one LDS with an
-// immediate offset, no generic-address arithmetic), plain pointers in the host emulation
-#ifdef __CUDA_ARCH__
-typedef uint32_t sm_t;
-FZ_HD sm_t sm_of(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-FZ_HD uint32_t sm_ld16(sm_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
-FZ_HD uint32_t sm_ld32(sm_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
-FZ_HD sm_t ring_slot(sm_t ring, uint32_t b) { return ring | (b & 0xFCu); }            // the ring is 256-byte aligned
-FZ_HD void ring_fetch_sm(sm_t slot, const uint8_t* gsrc) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(gsrc) : "memory"); }
-FZ_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
-FZ_HD uint32_t fsl_w(uint32_t lo, uint32_t hi, uint32_t n) { return __funnelshift_l(lo, hi, n); }   // high word of (hi:lo << (n & 31))
-FZ_HD uint32_t andn32(uint32_t a, uint32_t b) { uint32_t r; asm("lop3.b32 %0, %1, %2, 0, 0x30;" : "=r"(r) : "r"(a), "r"(b)); return r; }   // a & ~b
-FZ_HD uint32_t log2p(uint32_t v) { uint32_t r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }                                   // v = 2^k -> k
-FZ_HD sm_t opaque(sm_t v) { asm("" : "+r"(v)); return v; }          // keeps an address sum out of the reassociation of the final add
-FZ_HD void st_rec4(uint64_t* p, uint64_t a, uint64_t b, uint64_t c, uint64_t d)      // four records, one 256-bit store (p 32-byte aligned)
-{
-    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
-}
-#else
-typedef uintptr_t sm_t;
-FZ_HD sm_t sm_of(const void* p) { return (uintptr_t)p; }
-FZ_HD uint32_t sm_ld16(sm_t a) { return *(const uint16_t*)a; }
-FZ_HD uint32_t sm_ld32(sm_t a) { return *(const uint32_t*)a; }
-FZ_HD sm_t ring_slot(sm_t ring, uint32_t b) { return ring + (b & 0xFCu); }
-FZ_HD void ring_fetch_sm(sm_t slot, const uint8_t* gsrc) { for (int i = 0; i < 16; i++) ((uint8_t*)slot)[i] = gsrc[i]; }
-FZ_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
-FZ_HD uint32_t fsl_w(uint32_t lo, uint32_t hi, uint32_t n) { n &= 31; return n ? (hi << n) | (lo >> (32 - n)) : hi; }
-FZ_HD uint32_t andn32(uint32_t a, uint32_t b) { return a & ~b; }
-FZ_HD uint32_t log2p(uint32_t v) { return (uint32_t)highbit(v); }
-FZ_HD sm_t opaque(sm_t v) { return v; }
-FZ_HD void st_rec4(uint64_t* p, uint64_t a, uint64_t b, uint64_t c, uint64_t d) { p[0] = a; p[1] = b; p[2] = c; p[3] = d; }
-#endif
-
-// Backward bitstream of a sequences section, addressed by a BIT CURSOR instead of a bit container: `cur` is the bit
-// address of the highest unread bit, counted from gbase = (stream pointer & ~255), so that (cur >> 3) & 255 is at the
-// same time the byte's slot in the 256-byte cp.async ring.  A sequence needs no refill logic and no branches: it
-// loads the three ring words under the cursor, funnels them into a 64-bit window and moves the cursor down.
-// Bits below the first byte of the stream read as garbage; a stream that uses them ends below `lo` and is corrupt.
-struct SeqCursor {
-    int32_t cur, lo;         // lo = bit address of the stream's first bit; everything is read <=> cur == lo - 1
-    const uint8_t* gbase;
-    sm_t ring;
-    int32_t fa, fmin;        // byte offset (from gbase) of the next 16-byte chunk to fetch, going down / of the lowest chunk
-
-    FZ_HD void fill()        // every free ring slot: a slot is free once the cursor's word is below the chunk it held
-    {
-        const int32_t bw = (cur >> 3) & ~3;
-        while (fa >= fmin && fa + 256 > bw) { ring_fetch_sm(ring + ((uint32_t)fa & 255u), gbase + fa); fa -= 16; }
-    }
-    FZ_HD int init(const uint8_t* p, uint32_t n, uint8_t* ring_)
-    {
-        if (n == 0) return -1;
-        const uint8_t* lastp = p + n - 1;
-        const uint32_t lastb = *lastp;
-        if (lastb == 0) return -1;
-        gbase = (const uint8_t*)((uintptr_t)p & ~(uintptr_t)255);
-        ring = sm_of(ring_);
-        lo = (int32_t)(p - gbase) * 8;
-        cur = (int32_t)(lastp - gbase) * 8 + highbit(lastb) - 1;     // just below the sentinel bit
-        fa = (int32_t)(lastp - gbase) & ~15; fmin = (int32_t)(p - gbase) & ~15;
-        for (int i = 0; i < 16 && fa >= fmin; i++) { ring_fetch_sm(ring + ((uint32_t)fa & 255u), gbase + fa); fa -= 16; }
-        ring_commit(); ring_wait<0>();
-        return 0;
-    }
-    FZ_HD uint32_t peek() const                        // the 32 bits under the cursor, highest first
-    {
-        const uint32_t b = (uint32_t)(cur >> 3);
-        return fsl_w(sm_ld32(ring_slot(ring, b - 4)), sm_ld32(ring_slot(ring, b)), ~(uint32_t)cur & 31u);
-    }
-    FZ_HD uint32_t read(uint32_t nb) { const uint32_t v = shr_c(peek(), 32 - nb); cur -= (int32_t)nb; return v; }   // nb <= 32
-};
 
 // The registers of one chain: addresses of the current LL / ML / OF cells, the table bases, and the constant that turns
 // the LL / ML addresses into the record's offsets.

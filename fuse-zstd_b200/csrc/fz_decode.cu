@@ -89,28 +89,40 @@ __global__ void k_fill(const Item* items, ItemInfo* infos, const ItemBase* bases
 #ifndef FZ_LIT_GROUPS
 #define FZ_LIT_GROUPS 24
 #endif
-constexpr int kLitGroups = FZ_LIT_GROUPS;       // blocks in flight per CTA
-constexpr int kLitThreads = kLitGroups * 4;
+#ifndef FZ_LIT_WARP_GROUPS
+#define FZ_LIT_WARP_GROUPS 2
+#endif
+// The Huffman chain is latency-bound (index -> LDS -> length -> shift per symbol) and an SM holds only 24 tables, so what
+// counts is that every table is busy: a warp carries just kLitWarpGroups blocks (4 lanes each, the other lanes idle), because
+// the blocks of a warp run in lockstep and finish together -- with eight blocks per warp the streams sat idle 60 % of
+// the time waiting for the longest one (ncu: 13 of 32 lanes active).  The idle lanes cost nothing: issue slots are plentiful.
+constexpr int kLitGroups = FZ_LIT_GROUPS;                 // blocks in flight per CTA
+constexpr int kLitWarpGroups = FZ_LIT_WARP_GROUPS;        // blocks per warp
+constexpr int kLitWarps = (kLitGroups + kLitWarpGroups - 1) / kLitWarpGroups;
+constexpr int kLitThreads = kLitWarps * 32;
 constexpr int kLitSmem = kLitGroups * kLitGroupBytes;
 
 __global__ void __launch_bounds__(kLitThreads, 1) k_literals(Block* blocks, const uint32_t* jobs, uint32_t n_jobs, uint32_t* ticket)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(256) uint8_t smem_lit[];     // kLitGroupBytes is a multiple of 256: the rings are 256-byte aligned
+    uint8_t* const smem = smem_lit;
     __shared__ int s_log[kLitGroups];
     __shared__ uint32_t s_used[kLitGroups];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t grp = threadIdx.x >> 2, sub = threadIdx.x & 3;
+    const uint32_t first = warp * kLitWarpGroups, mine = min((uint32_t)kLitWarpGroups, (uint32_t)kLitGroups - first);   // this warp's groups
+    const uint32_t sub = lane & 3, lg = lane >> 2;
+    const bool lane_on = lg < mine;
+    const uint32_t grp = first + (lane_on ? lg : 0);
     uint8_t* gmem = smem + grp * kLitGroupBytes;
     uint16_t* table = (uint16_t*)gmem;
     uint8_t* rings = gmem + (1u << kHufLogMax) * 2;
-    (void)warp;
     for (;;) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(ticket, 8);            // eight blocks per warp and round
+        if (lane == 0) base = atomicAdd(ticket, mine);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= n_jobs) return;
-        const uint32_t job = base + (lane >> 2);
-        const bool active = job < n_jobs;
+        const uint32_t job = base + lg;
+        const bool active = lane_on && job < n_jobs;
         Block* b = active ? &blocks[jobs[job]] : nullptr;
         const bool huf = active && b->lit_type >= LT_HUF;
         if (huf && sub == 0) { int log; uint32_t used; lit_build(blocks, *b, table, *(LitScratch*)rings, log, used); s_log[grp] = log; s_used[grp] = used; }
