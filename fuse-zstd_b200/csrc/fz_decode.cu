@@ -30,7 +30,7 @@ namespace fz {
 __global__ void k_count(const Item* items, ItemInfo* infos, uint32_t n, uint32_t* tickets)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 4) tickets[i] = 0;
+    if (i < 8) tickets[i] = 0;
     if (i >= n) return;
     ItemInfo info;
     walk_item<false>(i, items[i], info, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
@@ -86,51 +86,65 @@ __global__ void k_fill(const Item* items, ItemInfo* infos, const ItemBase* bases
 // weights, or the tree of an earlier block for Treeless literals) and fills the group's table in shared
 // memory, then each thread decodes one of the (up to) four Huffman streams, pulling its bitstream
 // through a cp.async ring.  24 groups (9 KB each) per CTA, one CTA per SM, blocks drawn from a ticket.
-#ifndef FZ_LIT_GROUPS
-#define FZ_LIT_GROUPS 24
-#endif
 #ifndef FZ_LIT_WARP_GROUPS
 #define FZ_LIT_WARP_GROUPS 2
 #endif
-// The Huffman chain is latency-bound (index -> LDS -> length -> shift per symbol) and an SM holds only 24 tables, so what
-// counts is that every table is busy: a warp carries just kLitWarpGroups blocks (4 lanes each, the other lanes idle), because
-// the blocks of a warp run in lockstep and finish together -- with eight blocks per warp the streams sat idle 60 % of
-// the time waiting for the longest one (ncu: 13 of 32 lanes active).  The idle lanes cost nothing: issue slots are plentiful.
-constexpr int kLitGroups = FZ_LIT_GROUPS;                 // blocks in flight per CTA
+// The Huffman chain is latency-bound (index -> LDS -> length -> shift per symbol), so the stage is as fast as the number
+// of tables an SM holds, all of them busy:
+// * tables of 2^11 cells (the deepest tree libzstd's encoder builds): 45 blocks in flight per SM; a deeper tree (the
+//   format allows 2^12) is put on a list and decoded by a second launch with 24 tables of 2^12 cells per SM;
+// * a warp carries just kLitWarpGroups blocks (4 lanes each, the other lanes idle), because the blocks of a warp run in
+//   lockstep and finish together -- with eight blocks per warp the streams sat idle 60 % of the time waiting for the
+//   longest one (ncu: 13 of 32 lanes active).  The idle lanes cost nothing: issue slots are plentiful.
 constexpr int kLitWarpGroups = FZ_LIT_WARP_GROUPS;        // blocks per warp
-constexpr int kLitWarps = (kLitGroups + kLitWarpGroups - 1) / kLitWarpGroups;
-constexpr int kLitThreads = kLitWarps * 32;
-constexpr int kLitSmem = kLitGroups * kLitGroupBytes;
+template <int LOG> struct LitCfg {
+    static constexpr int fit = (227 * 1024 - 1024) / (int)lit_group_bytes(LOG);
+    static constexpr int groups = fit < 32 * kLitWarpGroups ? fit : 32 * kLitWarpGroups;   // blocks in flight per CTA (one CTA per SM, <= 1024 threads)
+    static constexpr int warps = (groups + kLitWarpGroups - 1) / kLitWarpGroups;
+    static constexpr int threads = warps * 32;
+    static constexpr int smem = groups * (int)lit_group_bytes(LOG);
+};
 
-__global__ void __launch_bounds__(kLitThreads, 1) k_literals(Block* blocks, const uint32_t* jobs, uint32_t n_jobs, uint32_t* ticket)
+// n_jobs_dev != nullptr: the job count is read from device memory (the list of deferred blocks).  deferred != nullptr:
+// blocks whose tree is deeper than LOG are appended there instead of being decoded.
+template <int LOG>
+__global__ void __launch_bounds__(LitCfg<LOG>::threads, 1) k_literals(Block* blocks, const uint32_t* jobs, uint32_t n_jobs, const uint32_t* n_jobs_dev,
+                                                                       uint32_t* ticket, uint32_t* deferred, uint32_t* n_deferred)
 {
-    extern __shared__ __align__(256) uint8_t smem_lit[];     // kLitGroupBytes is a multiple of 256: the rings are 256-byte aligned
+    constexpr int kGroups = LitCfg<LOG>::groups;
+    constexpr uint32_t kGroupBytes = lit_group_bytes(LOG);
+    extern __shared__ __align__(256) uint8_t smem_lit[];     // the group size is a multiple of 256: the rings are 256-byte aligned
     uint8_t* const smem = smem_lit;
-    __shared__ int s_log[kLitGroups];
-    __shared__ uint32_t s_used[kLitGroups];
+    __shared__ int s_log[kGroups];
+    __shared__ uint32_t s_used[kGroups];
+    if (n_jobs_dev) n_jobs = *n_jobs_dev;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t first = warp * kLitWarpGroups, mine = min((uint32_t)kLitWarpGroups, (uint32_t)kLitGroups - first);   // this warp's groups
+    const uint32_t first = warp * kLitWarpGroups, mine = min((uint32_t)kLitWarpGroups, (uint32_t)kGroups - first);   // this warp's groups
     const uint32_t sub = lane & 3, lg = lane >> 2;
     const bool lane_on = lg < mine;
     const uint32_t grp = first + (lane_on ? lg : 0);
-    uint8_t* gmem = smem + grp * kLitGroupBytes;
+    uint8_t* gmem = smem + grp * kGroupBytes;
     uint16_t* table = (uint16_t*)gmem;
-    uint8_t* rings = gmem + (1u << kHufLogMax) * 2;
+    uint8_t* rings = gmem + (1u << LOG) * 2;
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(ticket, mine);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= n_jobs) return;
         const uint32_t job = base + lg;
-        const bool active = lane_on && job < n_jobs;
+        bool active = lane_on && job < n_jobs;
         Block* b = active ? &blocks[jobs[job]] : nullptr;
         const bool huf = active && b->lit_type >= LT_HUF;
-        if (huf && sub == 0) { int log; uint32_t used; lit_build(blocks, *b, table, *(LitScratch*)rings, log, used); s_log[grp] = log; s_used[grp] = used; }
+        if (huf && sub == 0) {
+            int log; uint32_t used; lit_build(blocks, *b, table, *(LitScratch*)rings, LOG, log, used); s_log[grp] = log; s_used[grp] = used;
+            if (log == -2) { if (deferred) deferred[atomicAdd(n_deferred, 1u)] = jobs[job]; else s_log[grp] = -1; }
+        }
         __syncwarp();
+        if (huf && s_log[grp] == -2) active = false;           // decoded by the second launch
         LitWork wk{ nullptr, nullptr, 0, 0, 0 };
         if (active) wk = lit_plan(*b, sub, huf ? s_log[grp] : 0, huf ? s_used[grp] : 0);
         const uint32_t bound = __reduce_max_sync(0xFFFFFFFFu, wk.kind == 2 ? wk.n_out / 4 : 0u);
-        const int bad = lit_run(wk, sub, table, huf ? s_log[grp] : 0, rings + sub * 256, bound, 0xFFFFFFFFu);
+        const int bad = lit_run(wk, sub, table, huf && active ? s_log[grp] : 0, rings + sub * 256, bound, 0xFFFFFFFFu);
         if (active && bad) b->status = FZG_E_CORRUPT;
         __syncwarp();
     }
@@ -567,7 +581,8 @@ static int g_sm_count = 148;
 
 int fzh_decode_setup(void)
 {
-    CK(cudaFuncSetAttribute(k_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, kLitSmem));
+    CK(cudaFuncSetAttribute(k_literals<kHufLogCommon>, cudaFuncAttributeMaxDynamicSharedMemorySize, LitCfg<kHufLogCommon>::smem));
+    CK(cudaFuncSetAttribute(k_literals<kHufLogMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, LitCfg<kHufLogMax>::smem));
     CK(cudaFuncSetAttribute(k_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqSmem));
     int dev = 0; CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
@@ -617,7 +632,7 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
     if ((rc = c->d_frames.reserve((n_frames + 1) * sizeof(Frame)))) return rc;
     if ((rc = c->d_blocks.reserve((n_blocks + 1) * sizeof(Block)))) return rc;
     if ((rc = c->d_seq_jobs.reserve((n_sj + 1) * 4))) return rc;
-    if ((rc = c->d_huf_jobs.reserve((n_hj + 1) * 4))) return rc;
+    if ((rc = c->d_huf_jobs.reserve((2 * n_hj + 2) * 4))) return rc;      // the job list + the list of blocks deferred to the 2^12-cell launch
     if ((rc = c->d_lit.reserve(lit_bytes + 64))) return rc;
     if ((rc = c->d_seq.reserve((n_seq + 8) * 8))) return rc;
     Frame* d_frames = (Frame*)c->d_frames.p; Block* d_blocks = (Block*)c->d_blocks.p;
@@ -634,7 +649,15 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
         while (prev.entropy_epoch.load(std::memory_order_acquire) < ctx->epoch) std::this_thread::yield();
         CK(cudaStreamWaitEvent(s, prev.ev_entropy, 0));
     }
-    if (n_hj) { k_literals<<<(uint32_t)std::min<uint64_t>((n_hj + kLitGroups - 1) / kLitGroups, (uint64_t)g_sm_count), kLitThreads, kLitSmem, s>>>(d_blocks, d_hj, (uint32_t)n_hj, d_tickets + 2); launches++; }
+    if (n_hj) {                                                      // tickets: [2] first launch, [3] deferred count, [4] second launch
+        using L1 = LitCfg<kHufLogCommon>; using L2 = LitCfg<kHufLogMax>;
+        uint32_t* d_deferred = d_hj + n_hj + 1;
+        k_literals<kHufLogCommon><<<(uint32_t)std::min<uint64_t>((n_hj + L1::groups - 1) / L1::groups, (uint64_t)g_sm_count), L1::threads, L1::smem, s>>>(
+            d_blocks, d_hj, (uint32_t)n_hj, nullptr, d_tickets + 2, d_deferred, d_tickets + 3);
+        k_literals<kHufLogMax><<<(uint32_t)std::min<uint64_t>((n_hj + L2::groups - 1) / L2::groups, (uint64_t)g_sm_count), L2::threads, L2::smem, s>>>(
+            d_blocks, d_deferred, 0, d_tickets + 3, d_tickets + 4, nullptr, nullptr);
+        launches += 2;
+    }
     mark();
     if (n_sj) {
         const uint32_t grid = (uint32_t)std::min<uint64_t>((n_sj + kSeqStreams - 1) / kSeqStreams, (uint64_t)g_sm_count);

@@ -17,18 +17,23 @@ static __constant__ SeqConsts c_seq_consts = { FZ_LL_BASE, FZ_ML_BASE, FZ_LL_BIT
 // ------------------------------------------------------------------ literals pass (four threads per block)
 // Per block (group of four threads) in shared memory: the decode table (8 KB) and 1 KB that serves first as
 // table-build scratch and then as the four bitstream rings.
-constexpr uint32_t kLitGroupBytes = (1u << kHufLogMax) * 2 + 1024;
+FZ_HD constexpr uint32_t lit_group_bytes(int table_log) { return (1u << table_log) * 2 + 1024; }
+#ifndef FZ_HUF_LOG_COMMON
+#define FZ_HUF_LOG_COMMON 11             // (tests build a variant with 9 so that ordinary frames exercise the second pass)
+#endif
+constexpr int kHufLogCommon = FZ_HUF_LOG_COMMON;   // 11: what libzstd's encoder emits at most; deeper trees (the format allows 12) take a second pass
 struct LitScratch {          // overlays the 1 KB ring area while the table is being built
     uint8_t w[256]; uint32_t ft[64]; uint16_t cnt[64]; uint32_t start[kHufLogMax + 2], rank[kHufLogMax + 2];
 };
 
-// thread 0 of the group: tree description (possibly from an earlier block: Treeless) -> table.
-// log < 0 reports a malformed description.
-FZ_HD void lit_build(const Block* blocks, const Block& b, uint16_t* table, LitScratch& sc, int& log, uint32_t& used)
+// thread 0 of the group: tree description (possibly from an earlier block: Treeless) -> table of 1 << log cells.
+// log == -1 reports a malformed description, log == -2 a tree deeper than max_log (no table is written).
+FZ_HD void lit_build(const Block* blocks, const Block& b, uint16_t* table, LitScratch& sc, int max_log, int& log, uint32_t& used)
 {
     const Block& sb = blocks[b.huf_src];
     int nw; HufInfo hi; hi.log = 0; hi.used = 0;
     if (huf_read_weights(sb.src + sb.lit_hdr, sb.lit_csize, sc.w, nw, hi, sc.ft, sc.cnt) != 0) { log = -1; used = 0; return; }
+    if (hi.log > max_log) { log = -2; used = 0; return; }
     huf_fill_table(table, sc.w, nw, hi.log, sc.start, sc.rank);
     log = hi.log; used = hi.used;
 }

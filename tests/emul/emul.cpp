@@ -105,7 +105,7 @@ extern "C" int fze_decode_batch(size_t n, const void* const* src, const size_t* 
     for (uint32_t j = 0; j < run.huf_job; j++) {
         Block& b = blocks[huf_jobs[j]];
         int log = 0; uint32_t used = 0;
-        if (b.lit_type >= LT_HUF) lit_build(blocks.data(), b, table.data(), sc, log, used);
+        if (b.lit_type >= LT_HUF) lit_build(blocks.data(), b, table.data(), sc, kHufLogMax, log, used);
         for (uint32_t sub = 0; sub < 4; sub++) {
             const LitWork wk = lit_plan(b, sub, log, used);
             if (lit_run(wk, sub, table.data(), log, ring, wk.n_out / 4, 1)) b.status = FZG_E_CORRUPT;
@@ -163,7 +163,7 @@ extern "C" int fze_trace(const void* src, size_t src_len, uint64_t* seq_out, siz
     alignas(16) static uint8_t ring[256]; static LitScratch sc;
     for (uint32_t j = 0; j < info.n_huf_jobs; j++) {
         Block& b = blocks[hj[j]]; int log = 0; uint32_t used = 0;
-        if (b.lit_type >= LT_HUF) lit_build(blocks.data(), b, table.data(), sc, log, used);
+        if (b.lit_type >= LT_HUF) lit_build(blocks.data(), b, table.data(), sc, kHufLogMax, log, used);
         for (uint32_t sub = 0; sub < 4; sub++) {
             const LitWork wk = lit_plan(b, sub, log, used);
             if (lit_run(wk, sub, table.data(), log, ring, wk.n_out / 4, 1)) return FZG_E_CORRUPT;
