@@ -84,7 +84,7 @@ extern "C" void fzg_shutdown(void)
             FzLane& L = c->lane[l];
             cudaStreamSynchronize(L.stream);
             FzDevBuf* lb[] = { &L.d_infos, &L.d_bases, &L.d_outs, &L.d_totals, &L.d_frames, &L.d_blocks, &L.d_seq_jobs, &L.d_huf_jobs,
-                               &L.d_lit, &L.d_seq };
+                               &L.d_lit, &L.d_seq, &L.d_seq_tabs, &L.d_seq_hdrs };
             for (auto* b : lb) b->release();
             L.h_totals.release();
             for (auto& e : L.ev) cudaEventDestroy(e);

@@ -363,14 +363,17 @@ struct FwdBits {
 };
 
 // RFC 8878 4.1.1.  norm[] receives probabilities (-1 = "less than one").  Returns bytes used or -1.
-FZ_HD int read_ncount(const uint8_t* p, uint32_t n, int max_sym, int max_log, int16_t* norm, int& n_sym, int& log)
+// Single exit (errors are carried in a flag): lanes of a warp that parse different descriptions reconverge after every
+// loop instead of running the rest of the caller one after the other.
+template <class NORM>
+FZ_HD int read_ncount(const uint8_t* p, uint32_t n, int max_sym, int max_log, NORM norm, int& n_sym, int& log)
 {
-    if (n == 0) return -1;
     FwdBits br{ p, n, 0 };
-    log = (int)br.peek(4) + 5; br.bitpos = 4;
-    if (log > max_log) return -1;
-    int remaining = 1 << log, sym = 0;
-    while (remaining > 0 && sym <= max_sym) {
+    bool bad = n == 0;
+    log = bad ? 5 : (int)br.peek(4) + 5; br.bitpos = 4;
+    if (log > max_log) bad = true;
+    int remaining = bad ? 0 : 1 << log, sym = 0;
+    while (remaining > 0 && sym <= max_sym && !bad) {
         int bits = highbit((uint32_t)remaining + 1) + 1;
         uint32_t v = br.peek((uint32_t)bits);
         uint32_t lower = (1u << (bits - 1)) - 1;
@@ -381,17 +384,17 @@ FZ_HD int read_ncount(const uint8_t* p, uint32_t n, int max_sym, int max_log, in
         remaining -= prob < 0 ? 1 : prob;
         norm[sym++] = (int16_t)prob;
         if (prob == 0) {
-            for (;;) {
-                uint32_t rep = br.peek(2); br.bitpos += 2;
-                for (uint32_t i = 0; i < rep; i++) { if (sym > max_sym) return -1; norm[sym++] = 0; }
-                if (rep != 3) break;
+            uint32_t rep = 3;
+            while (rep == 3 && !bad) {
+                rep = br.peek(2); br.bitpos += 2;
+                for (uint32_t i = 0; i < rep && !bad; i++) { if (sym > max_sym) bad = true; else norm[sym++] = 0; }
             }
         }
-        if (br.bitpos > n * 8) return -1;
+        if (br.bitpos > n * 8) bad = true;
     }
-    if (remaining != 0 || br.bitpos > n * 8) return -1;
+    if (remaining != 0 || br.bitpos > n * 8) bad = true;
     n_sym = sym;
-    return (int)((br.bitpos + 7) >> 3);
+    return bad ? -1 : (int)((br.bitpos + 7) >> 3);
 }
 
 // FSE decode cell, 32 bits: baseline[0:16) | nbBits[16:20) | nbExtra[20:25) | symbol[25:32)
@@ -565,21 +568,21 @@ struct SeqConsts {       // small read-only tables, staged in shared memory by t
 // Returns the mode (0 predefined, 1 rle, 2 fse); sets p/n to the description bytes.  -1 on error.
 FZ_HD int locate_table(const Block& b, int which, const uint8_t*& p, uint32_t& n)
 {
-    uint32_t pos = b.seq_hdr;
-    for (int t = 0; t < 3; t++) {
-        int mode = (b.modes >> (6 - 2 * t)) & 3;
-        if (pos > b.csize) return -1;
-        if (t == which) { p = b.src + pos; n = b.csize - pos; return mode; }
-        if (mode == 1) pos += 1;
+    uint32_t pos = b.seq_hdr; int res = -1; bool bad = false;
+    for (int t = 0; t <= which; t++) {                       // single exit: see read_ncount
+        const int mode = (b.modes >> (6 - 2 * t)) & 3;
+        if (pos > b.csize) bad = true;
+        if (bad) continue;
+        if (t == which) { p = b.src + pos; n = b.csize - pos; res = mode; }
+        else if (mode == 1) pos += 1;
         else if (mode == 2) {
             int16_t norm[64]; int ns, log;
-            int used = read_ncount(b.src + pos, b.csize - pos, t == 0 ? kMaxLL : (t == 1 ? kMaxOF : kMaxML),
-                                   t == 0 ? kLLLog : (t == 1 ? kOFLog : kMLLog), norm, ns, log);
-            if (used < 0) return -1;
-            pos += (uint32_t)used;
+            const int used = read_ncount(b.src + pos, b.csize - pos, t == 0 ? kMaxLL : (t == 1 ? kMaxOF : kMaxML),
+                                         t == 0 ? kLLLog : (t == 1 ? kOFLog : kMLLog), norm, ns, log);
+            if (used < 0) bad = true; else pos += (uint32_t)used;
         }
     }
-    return -1;
+    return bad ? -1 : res;
 }
 
 // Builds table `which` for block b (resolving Repeat through b.*_src).  used = description bytes
@@ -788,7 +791,8 @@ FZ_HD int huf_decode_stream(const uint16_t* table, int log, const uint8_t* p, ui
 // RAW record, slow form (long lengths / offsets, decoded field by field):
 //   ll[0:18) | (ml - 3)[18:35) | offset_value[35:63) | 1[63]
 constexpr uint32_t kChainCellsLL = 512, kChainCellsML = 512, kChainCellsOF = 256;
-constexpr uint32_t kChainBytes = (kChainCellsLL + kChainCellsML + kChainCellsOF) * 2 + 256;
+constexpr uint32_t kChainCellBytes = (kChainCellsLL + kChainCellsML + kChainCellsOF) * 2;
+constexpr uint32_t kChainBytes = kChainCellBytes + 256;
 
 FZ_HD uint32_t chain_pack(uint32_t base, uint32_t nb, uint32_t extra) { return ((((base >> nb) << 1) | 1u) << nb) | (extra << 10); }
 FZ_HD uint32_t ctz32(uint32_t v)
@@ -826,13 +830,16 @@ struct TableSrc { int mode; const uint8_t* p; uint32_t n; bool own; };
 FZ_HD int resolve_table(const Block* blocks, const Block& b, int which, const uint8_t* p, uint32_t n, TableSrc& t)
 {
     t.mode = (b.modes >> (6 - 2 * which)) & 3; t.p = p; t.n = n; t.own = t.mode != 3;
+    int rc = 0;
     if (!t.own) {
         const int32_t src = which == 0 ? b.ll_src : (which == 1 ? b.of_src : b.ml_src);
-        if (src < 0) return -1;
-        t.mode = locate_table(blocks[src], which, t.p, t.n);
-        if (t.mode < 0 || t.mode == 3) return -1;
+        if (src < 0) rc = -1;
+        else {
+            t.mode = locate_table(blocks[src], which, t.p, t.n);
+            if (t.mode < 0 || t.mode == 3) rc = -1;
+        }
     }
-    return 0;
+    return rc;
 }
 // Normalised counts of a Predefined / FSE_Compressed table.  norm_buf: 64 int16 of scratch.  used = description bytes.
 FZ_HD int table_norm(const TableSrc& t, int which, const SeqConsts& K, int16_t* norm_buf, const int16_t*& norm, int& ns, int& log, uint32_t& used)
@@ -851,58 +858,107 @@ FZ_HD int table_norm(const TableSrc& t, int which, const SeqConsts& K, int16_t* 
     return 0;
 }
 
-// Stage A: chain cells of table `which`.  scratch = 128 uint16 (normalised counts, then per-symbol counters).
-FZ_HD int build_chain_seq_table(const Block* blocks, const Block& b, int which, const uint8_t* p, uint32_t n,
-                                const SeqConsts& K, uint16_t* cell, int& log, uint32_t& used, uint16_t* scratch)
+// Per-thread work arrays of the table stage, element i of thread t at base[i * stride + t]: in shared memory the 32 lanes
+// of a warp then touch consecutive bytes (no bank conflicts) although each builds a different table.
+template <class T> struct Lanewise {
+    T* p; uint32_t stride;
+    FZ_HD T& operator[](uint32_t i) const { return p[i * stride]; }
+};
+struct TabWork { Lanewise<uint8_t> sym; Lanewise<int16_t> norm; Lanewise<uint16_t> cnt; };   // 512 symbols, 64 counts, 64 counters
+
+FZ_HD void st_cells8(uint16_t* p, const uint32_t* w)          // eight 16-bit cells, one 16-byte store (p 16-byte aligned)
 {
-    const int max_sym = which == 0 ? kMaxLL : (which == 1 ? kMaxOF : kMaxML);
-    const uint8_t* extra = which == 0 ? K.ll_bits : (which == 2 ? K.ml_bits : nullptr);
-    TableSrc t; used = 0;
-    if (resolve_table(blocks, b, which, p, n, t) != 0) return -1;
-    if (t.mode == 1) {
-        if (t.n < 1 || t.p[0] > max_sym) return -1;
-        const uint32_t sy = t.p[0];
-        cell[0] = (uint16_t)chain_pack(0, 0, extra ? extra[sy] : sy); log = 0;
-        if (t.own) used = 1;
-        return 0;
-    }
-    const int16_t* norm; int ns; uint32_t u; uint16_t* cnt = scratch + 64;
-    if (table_norm(t, which, K, (int16_t*)scratch, norm, ns, log, u) != 0) return -1;
-    if (t.own) used = u;
-    if (fse_spread(cell, norm, ns, log, cnt) != 0) return -1;     // the cells hold the symbols first ...
-    const int size = 1 << log;
-    for (int c = 0; c < size; c++) {                               // ... and are converted in place
-        const uint32_t sy = cell[c];
-        const uint32_t nx = cnt[sy]++;
-        const uint32_t nb = (uint32_t)(log - highbit(nx));
-        cell[c] = (uint16_t)chain_pack((nx << nb) - (uint32_t)size, nb, extra ? extra[sy] : sy);
-    }
-    return 0;
+#ifdef __CUDA_ARCH__
+    *(uint4*)p = make_uint4(w[0], w[1], w[2], w[3]);
+#else
+    for (int i = 0; i < 4; i++) { p[2 * i] = (uint16_t)w[i]; p[2 * i + 1] = (uint16_t)(w[i] >> 16); }
+#endif
 }
 
-// Stage B: state -> symbol maps of the LL and ML tables of block b (yLL / yML: 512 bytes each; norm_buf: 64 int16).
-FZ_HD int build_symbol_maps(const Block* blocks, const Block& b, const SeqConsts& K, uint8_t* yLL, uint8_t* yML, int16_t* norm_buf,
-                            const uint8_t*& bits)           // bits: first byte of the sequence bitstream
+// Chain cells (and, for LL / ML, the state -> symbol map) of table `which` of block b, straight to HBM.
+// The lanes of a warp build different tables, so every loop here has a trip count that depends only on the table size:
+// the symbol spread walks all 1 << log visits of the (pos + step) permutation instead of looping per symbol, and the
+// cells leave eight at a time.
+FZ_HD int build_chain_seq_table(const Block* blocks, const Block& b, int which, const uint8_t* p, uint32_t n,
+                                const SeqConsts& K, uint16_t* cell, int& log, uint32_t& used, const TabWork& w, uint8_t* ymap)
 {
-    const uint8_t* p = b.src + b.seq_hdr; uint32_t n = b.csize - b.seq_hdr;
-    for (int which = 0; which < 3; which++) {                      // stream order: LL, OF, ML (OF only to find where ML starts)
-        uint8_t* y = which == 0 ? yLL : yML;
-        TableSrc t;
-        if (resolve_table(blocks, b, which, p, n, t) != 0) return -1;
-        uint32_t used = 0;
-        if (t.mode == 1) {
-            if (t.n < 1) return -1;
-            if (which != 1) y[0] = t.p[0];
-            used = 1;
-        } else {
-            const int16_t* norm; int ns, log;
-            if (table_norm(t, which, K, norm_buf, norm, ns, log, used) != 0) return -1;
-            if (which != 1 && fse_spread(y, norm, ns, log, (uint16_t*)nullptr) != 0) return -1;
+    const int max_sym = which == 0 ? kMaxLL : (which == 1 ? kMaxOF : kMaxML);
+    const int max_log = which == 0 ? kLLLog : (which == 1 ? kOFLog : kMLLog);
+    const uint8_t* extra = which == 0 ? K.ll_bits : (which == 2 ? K.ml_bits : nullptr);
+    TableSrc t; used = 0; log = 0;
+    bool bad = resolve_table(blocks, b, which, p, n, t) != 0;
+    int ns = 0;
+    if (!bad && t.mode == 1) {
+        if (t.n < 1 || t.p[0] > max_sym) bad = true;
+        else {
+            const uint32_t sy = t.p[0];
+            cell[0] = (uint16_t)chain_pack(0, 0, extra ? extra[sy] : sy);
+            if (ymap) ymap[0] = (uint8_t)sy;
+            if (t.own) used = 1;
         }
-        if (t.own) { if (used > n) return -1; p += used; n -= used; }
+    } else if (!bad && t.mode == 0) {
+        const int16_t* def = which == 0 ? K.ll_def : (which == 1 ? K.of_def : K.ml_def);
+        ns = which == 0 ? 36 : (which == 1 ? 29 : 53); log = which == 1 ? 5 : 6;
+        for (int i = 0; i < ns; i++) w.norm[i] = def[i];
+    } else if (!bad) {
+        const int u = read_ncount(t.p, t.n, max_sym, max_log, w.norm, ns, log);
+        if (u < 0) { bad = true; ns = 0; log = 0; }
+        else if (t.own) used = (uint32_t)u;
     }
-    bits = p;
-    return 0;
+    const bool fse = !bad && t.mode != 1;               // a table to spread (Predefined or FSE_Compressed)
+    const int size = fse ? 1 << log : 0; int high = size - 1;
+    for (int sy = 0; sy < ns; sy++) {
+        const int pr = w.norm[sy];
+        if (pr == -1) { w.sym[high--] = (uint8_t)sy; w.cnt[sy] = 1; } else w.cnt[sy] = (uint16_t)pr;
+    }
+    {   // spread (RFC 8878 4.1.1): visit k lands on (k * step) & mask; visits above `high` are skipped, the others take the symbols in order
+        const int step = (size >> 1) + (size >> 3) + 3, mask = size - 1;
+        int sy = 0, rem = 0, pos = 0, placed = 0;
+        for (int k = 0; k < size; k++) {
+            if (pos <= high) {
+                while (rem <= 0 && sy < ns) { rem = w.norm[sy]; sy++; }          // next symbol with a probability >= 1 (sy - 1 is current)
+                if (rem <= 0) bad = true;                                         // more free cells than probabilities: malformed
+                w.sym[pos] = (uint8_t)(sy > 0 ? sy - 1 : 0); rem--; placed++;
+            }
+            pos = (pos + step) & mask;
+        }
+        while (rem <= 0 && sy < ns) { rem = w.norm[sy]; sy++; }
+        if (fse && (rem > 0 || placed != high + 1)) bad = true;                   // probabilities left over
+    }
+    for (int c0 = 0; c0 < size; c0 += 8) {                                        // cells, eight at a time (size >= 32)
+        uint32_t cw[4] = { 0, 0, 0, 0 }, yw[2] = { 0, 0 };
+        for (int j = 0; j < 8; j++) {
+            const uint32_t sy = w.sym[c0 + j];
+            const uint32_t nx = w.cnt[sy] | (bad ? 1u : 0u); w.cnt[sy] = (uint16_t)(nx + 1);   // (a malformed table may hold zero counts)
+            const uint32_t nb = (uint32_t)(log - highbit(nx)) & 15u;
+            cw[j >> 1] |= (chain_pack((nx << nb) - (uint32_t)size, nb, extra ? extra[sy] : sy) & 0xFFFFu) << (16 * (j & 1));
+            yw[j >> 2] |= sy << (8 * (j & 3));
+        }
+        st_cells8(cell + c0, cw);
+        if (ymap) { ((uint32_t*)(ymap + c0))[0] = yw[0]; ((uint32_t*)(ymap + c0))[1] = yw[1]; }
+    }
+    return bad ? -1 : 0;
+}
+
+// ------------------------------------------------------------------ sequence pass, table stage (one thread per block)
+// Everything stage A and stage B need to know about a block's three FSE tables, built once, by one thread per block with
+// all blocks of the batch in flight (the build is serial, data-dependent code: inside stage A it kept 31 lanes of a warp
+// waiting for the slowest), into HBM: the chain cells that stage A copies into shared memory, the state -> symbol maps
+// of the LL and ML tables that stage B needs, and a small header.
+//   per job: uint16 cLL[512] | cML[512] | cOF[256] | uint8 yLL[512] | yML[512]   (kJobTableBytes = 3584)
+struct SeqJobHdr { uint32_t bits_off; uint8_t logLL, logOF, logML, bad; };       // bits_off: first byte of the bitstream inside the block
+constexpr uint32_t kJobTableBytes = kChainCellBytes + 1024;
+FZ_HD void seq_tables_thread(const Block* blocks, const Block& b, const SeqConsts& K, uint8_t* tab, SeqJobHdr& h, const TabWork& w)
+{
+    uint16_t* cLL = (uint16_t*)tab; uint16_t* cML = cLL + kChainCellsLL; uint16_t* cOF = cML + kChainCellsML;
+    uint8_t* yLL = tab + kChainCellBytes; uint8_t* yML = yLL + 512;
+    const uint8_t* p = b.src + b.seq_hdr; uint32_t n = b.csize - b.seq_hdr; uint32_t used = 0;
+    int logLL = 0, logOF = 0, logML = 0; bool bad = false;
+    if (build_chain_seq_table(blocks, b, 0, p, n, K, cLL, logLL, used, w, yLL) != 0 || used > n) bad = true;
+    if (!bad) { p += used; n -= used; if (build_chain_seq_table(blocks, b, 1, p, n, K, cOF, logOF, used, w, nullptr) != 0 || used > n) bad = true; }
+    if (!bad) { p += used; n -= used; if (build_chain_seq_table(blocks, b, 2, p, n, K, cML, logML, used, w, yML) != 0 || used > n) bad = true; }
+    if (!bad) { p += used; n -= used; }
+    h.bits_off = (uint32_t)(p - b.src); h.logLL = (uint8_t)logLL; h.logOF = (uint8_t)logOF; h.logML = (uint8_t)logML; h.bad = bad;
 }
 
 // RAW record of stage A: x[0:32) | y[32:64), y = LL cell byte offset [0:12) | ML cell byte offset [12:24) | offset code [24:29) |
@@ -1012,6 +1068,7 @@ FZ_HD uint64_t chain_step(ChainRegs& r, SeqCursor& cs, uint32_t vote_mask)
 // fenced off with a warp barrier, and the loop runs a warp-uniform number of iterations (`bound` =
 // the largest nseq - 1 among the lanes in `mask`), each lane masking itself out when its block is
 // done.  The last sequence of a block updates no state; it is decoded after the loop, by all lanes at once.
+// gtab / h: the block's tables and header from the table stage (seq_tables_thread).
 //
 // One iteration (chain_step) is straight-line code, ~55 instructions, and its critical path is
 //   state -> LDS cell -> sum of the extra-bit counts -> funnel -> multiply-high -> next state:
@@ -1023,26 +1080,24 @@ FZ_HD uint64_t chain_step(ChainRegs& r, SeqCursor& cs, uint32_t vote_mask)
 // A sequence whose extra bits exceed 32 (long lengths with a far offset: rare) hands stage B its bit cursor.
 // The loop is latency-bound: an SM holds 82 chains whatever their arrangement in warps, so what counts is the length
 // of one iteration of one chain, i.e. the instruction count and the dependent chain of chain_step.
-FZ_HD int decode_sequences_chain(const Block* blocks, const Block& b, const SeqConsts& K, uint8_t* mem,
+FZ_HD int decode_sequences_chain(const Block& b, const uint8_t* gtab, const SeqJobHdr& h, uint8_t* mem,
                                  uint64_t* out, uint32_t bound, uint32_t mask)
 {
     uint16_t* cLL = (uint16_t*)mem; uint16_t* cML = cLL + kChainCellsLL; uint16_t* cOF = cML + kChainCellsML;
-    uint16_t* scratch = cOF + kChainCellsOF;                          // 256 bytes: table-build scratch, then the bitstream ring
-    int st = 0;
-    int logLL = 0, logOF = 0, logML = 0;
-    SeqCursor cs; cs.cur = 0; cs.lo = 0; cs.gbase = nullptr; cs.ring = sm_of(scratch); cs.fa = -1; cs.fmin = 0;
+    uint8_t* ring = mem + kChainCellBytes;
+    int st = h.bad ? FZG_E_CORRUPT : 0;
+    SeqCursor cs; cs.cur = 0; cs.lo = 0; cs.gbase = nullptr; cs.ring = sm_of(ring); cs.fa = -1; cs.fmin = 0;
     const sm_t tLL = sm_of(cLL), tML = sm_of(cML), tOF = sm_of(cOF);
     sm_t aLL = tLL, aML = tML, aOF = tOF;                             // addresses of the current cells
-    {
-        const uint8_t* p = b.src + b.seq_hdr; uint32_t n = b.csize - b.seq_hdr; uint32_t used = 0;
-        if (build_chain_seq_table(blocks, b, 0, p, n, K, cLL, logLL, used, scratch) != 0) st = FZG_E_CORRUPT;
-        if (!st) { p += used; n -= used; if (build_chain_seq_table(blocks, b, 1, p, n, K, cOF, logOF, used, scratch) != 0) st = FZG_E_CORRUPT; }
-        if (!st) { p += used; n -= used; if (build_chain_seq_table(blocks, b, 2, p, n, K, cML, logML, used, scratch) != 0) st = FZG_E_CORRUPT; }
-        if (!st) { p += used; n -= used; if (cs.init(p, n, (uint8_t*)scratch) != 0) st = FZG_E_CORRUPT; }
+    // the block's chain cells: HBM (table stage) -> shared memory, the same 160 chunks for every lane
+    for (uint32_t c = 0; c < kChainCellBytes; c += 16) ring_fetch_sm(tLL + c, gtab + c);
+    ring_commit(); ring_wait<0>();
+    if (!st) {
+        if (h.bits_off > b.csize || cs.init(b.src + h.bits_off, b.csize - h.bits_off, ring) != 0) st = FZG_E_CORRUPT;
         if (!st) {
-            aLL = tLL + 2 * cs.read((uint32_t)logLL);
-            aOF = tOF + 2 * cs.read((uint32_t)logOF);
-            aML = tML + 2 * cs.read((uint32_t)logML);
+            aLL = tLL + 2 * cs.read(h.logLL);
+            aOF = tOF + 2 * cs.read(h.logOF);
+            aML = tML + 2 * cs.read(h.logML);
             if (cs.cur < cs.lo - 1) st = FZG_E_CORRUPT;
         }
     }

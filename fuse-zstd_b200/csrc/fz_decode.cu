@@ -150,6 +150,28 @@ __global__ void __launch_bounds__(LitCfg<LOG>::threads, 1) k_literals(Block* blo
     }
 }
 
+// ------------------------------------------------------------------ sequences, table stage
+// One thread per block builds its three FSE tables straight into HBM (seq_tables_thread): every block of the batch is in
+// flight at once, so the serial, data-dependent build code costs its own latency once instead of stalling the chain warps.
+constexpr int kTabThreads = 32;
+__global__ void __launch_bounds__(kTabThreads) k_seq_tables(Block* blocks, const uint32_t* jobs, uint32_t n_jobs, uint8_t* tabs, SeqJobHdr* hdrs)
+{
+    __shared__ SeqConsts K;
+    __shared__ uint8_t s_sym[512 * kTabThreads];              // lane-wise work arrays (Lanewise): element i of thread t at [i * kTabThreads + t]
+    __shared__ int16_t s_norm[64 * kTabThreads];
+    __shared__ uint16_t s_cnt[64 * kTabThreads];
+    for (uint32_t i = threadIdx.x; i < sizeof(SeqConsts) / 4; i += blockDim.x) ((uint32_t*)&K)[i] = ((const uint32_t*)&c_seq_consts)[i];
+    __syncthreads();
+    const uint32_t job = blockIdx.x * kTabThreads + threadIdx.x;
+    if (job >= n_jobs) return;
+    Block& b = blocks[jobs[job]];
+    SeqJobHdr h;
+    const TabWork w{ { s_sym + threadIdx.x, kTabThreads }, { s_norm + threadIdx.x, kTabThreads }, { s_cnt + threadIdx.x, kTabThreads } };
+    seq_tables_thread(blocks, b, K, tabs + (size_t)job * kJobTableBytes, h, w);
+    hdrs[job] = h;
+    if (h.bad && !b.status) b.status = FZG_E_CORRUPT;
+}
+
 // ------------------------------------------------------------------ sequences, stage A: the FSE chain
 // One thread per block (the FSE state chain is serial), one CTA per SM.  What bounds this stage is the
 // latency of that chain times the number of chains an SM can hold, and the latter is set by shared
@@ -169,14 +191,11 @@ constexpr int kSeqThreads = kSeqWarps * 32;
 constexpr int kSeqSmem = kSeqStreams * kChainBytes;
 
 __global__ void __launch_bounds__(kSeqThreads, 1) k_sequences(Block* blocks, const uint32_t* jobs, uint32_t n_jobs, uint64_t* seqs,
-                                                                uint32_t* ticket)
+                                                                uint32_t* ticket, const uint8_t* tabs, const SeqJobHdr* hdrs)
 {
     extern __shared__ __align__(256) uint8_t smem_seq[];   // kChainBytes is a multiple of 256: every stream's ring is 256-byte aligned
     uint8_t* const smem = smem_seq;
     if (((uint32_t)__cvta_generic_to_shared(smem) & 255u) != 0) __trap();
-    __shared__ SeqConsts K;
-    for (uint32_t i = threadIdx.x; i < sizeof(SeqConsts) / 4; i += blockDim.x) ((uint32_t*)&K)[i] = ((const uint32_t*)&c_seq_consts)[i];
-    __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t first = warp * kSeqLanes, lanes = min((uint32_t)kSeqLanes, kSeqStreams - first);
     uint8_t* mine = smem + (first + (lane < lanes ? lane : 0)) * kChainBytes;
@@ -190,7 +209,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) k_sequences(Block* blocks, con
         Block* b = on ? &blocks[jobs[job]] : nullptr;
         const uint32_t mask = __ballot_sync(0xFFFFFFFFu, on);
         const uint32_t bound = __reduce_max_sync(0xFFFFFFFFu, on ? b->nseq - 1 : 0u);     // nseq >= 1 for a sequence job
-        if (on) seq_chain_thread(blocks, *b, K, mine, seqs, bound, mask);
+        if (on) seq_chain_thread(*b, tabs + (size_t)job * kJobTableBytes, hdrs[job], mine, seqs, bound, mask);
         __syncwarp();
     }
 }
@@ -210,12 +229,10 @@ __device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v, uint32_t lane)
 
 constexpr int kRecWarps = 8;
 __global__ void __launch_bounds__(kRecWarps * 32) k_records(Block* blocks, const Frame* frames, const uint32_t* jobs, uint32_t n_jobs,
-                                                            uint64_t* seqs)
+                                                            uint64_t* seqs, const uint8_t* tabs, const SeqJobHdr* hdrs)
 {
     __shared__ SeqConsts K;
-    __shared__ uint8_t s_y[kRecWarps][2][512];               // state -> symbol maps of the block (LL, ML)
-    __shared__ int16_t s_norm[kRecWarps][64];
-    __shared__ int s_err[kRecWarps];
+    __shared__ __align__(16) uint8_t s_y[kRecWarps][2][512]; // state -> symbol maps of the block (LL, ML), from the table stage
     for (uint32_t i = threadIdx.x; i < sizeof(SeqConsts) / 4; i += blockDim.x) ((uint32_t*)&K)[i] = ((const uint32_t*)&c_seq_consts)[i];
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -224,11 +241,12 @@ __global__ void __launch_bounds__(kRecWarps * 32) k_records(Block* blocks, const
     Block& b = blocks[jobs[job]];
     if (b.status) return;
     const uint8_t* yLL = s_y[warp][0]; const uint8_t* yML = s_y[warp][1];
-    __shared__ const uint8_t* s_bits[kRecWarps];
-    if (lane == 0) s_err[warp] = build_symbol_maps(blocks, b, K, s_y[warp][0], s_y[warp][1], s_norm[warp], s_bits[warp]);
+    {
+        const uint4* src = (const uint4*)(tabs + (size_t)job * kJobTableBytes + kChainCellBytes);
+        ((uint4*)s_y[warp][0])[lane] = src[lane]; ((uint4*)s_y[warp][0])[lane + 32] = src[lane + 32];
+    }
     __syncwarp();
-    const uint8_t* const bits = s_bits[warp];
-    if (s_err[warp]) { if (lane == 0) b.status = FZG_E_CORRUPT; return; }
+    const uint8_t* const bits = b.src + hdrs[job].bits_off;
     const uint32_t nseq = b.nseq, lit_regen = b.lit_regen, block_max = frames[b.frame].block_max;
     uint64_t* sq = seqs + b.seq_base;
     uint32_t rep0 = off_sym(0), rep1 = off_sym(1), rep2 = off_sym(2);      // history, warp-uniform
@@ -571,9 +589,9 @@ __global__ void k_finish(const ItemInfo* infos, const ItemBase* bases, const Fra
 // ====================================================================== host side
 using namespace fz;
 
-static const char* kStageNames[] = { "count", "scan", "fill", "literals", "sequences", "records", "offsets", "execute", "checksum",
+static const char* kStageNames[] = { "count", "scan", "fill", "literals", "tables", "sequences", "records", "offsets", "execute", "checksum",
                                      "finish" };
-const char* fzh_decode_stage_name(int s) { return s >= 0 && s < 10 ? kStageNames[s] : ""; }
+const char* fzh_decode_stage_name(int s) { return s >= 0 && s < 11 ? kStageNames[s] : ""; }
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "fzgpu: %s failed: %s (%s:%d)\n", #x, cudaGetErrorString(e_), __FILE__, __LINE__); return -5 /*-EIO*/; } } while (0)
 
@@ -635,9 +653,12 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
     if ((rc = c->d_huf_jobs.reserve((2 * n_hj + 2) * 4))) return rc;      // the job list + the list of blocks deferred to the 2^12-cell launch
     if ((rc = c->d_lit.reserve(lit_bytes + 64))) return rc;
     if ((rc = c->d_seq.reserve((n_seq + 8) * 8))) return rc;
+    if ((rc = c->d_seq_tabs.reserve((n_sj + 1) * (size_t)kJobTableBytes))) return rc;
+    if ((rc = c->d_seq_hdrs.reserve((n_sj + 1) * sizeof(SeqJobHdr)))) return rc;
     Frame* d_frames = (Frame*)c->d_frames.p; Block* d_blocks = (Block*)c->d_blocks.p;
     uint32_t* d_sj = (uint32_t*)c->d_seq_jobs.p; uint32_t* d_hj = (uint32_t*)c->d_huf_jobs.p;
     uint64_t* d_seq = (uint64_t*)c->d_seq.p;
+    uint8_t* d_tabs = (uint8_t*)c->d_seq_tabs.p; SeqJobHdr* d_hdrs = (SeqJobHdr*)c->d_seq_hdrs.p;
 
     k_fill<<<gi, tb, 0, s>>>(d_items, d_infos, d_bases, d_frames, d_blocks, d_sj, d_hj, (uint8_t*)c->d_lit.p, n); mark();
     int launches = 3;
@@ -659,12 +680,14 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
         launches += 2;
     }
     mark();
+    if (n_sj) { k_seq_tables<<<(uint32_t)((n_sj + kTabThreads - 1) / kTabThreads), kTabThreads, 0, s>>>(d_blocks, d_sj, (uint32_t)n_sj, d_tabs, d_hdrs); launches++; }
+    mark();
     if (n_sj) {
         const uint32_t grid = (uint32_t)std::min<uint64_t>((n_sj + kSeqStreams - 1) / kSeqStreams, (uint64_t)g_sm_count);
-        k_sequences<<<grid, kSeqThreads, kSeqSmem, s>>>(d_blocks, d_sj, (uint32_t)n_sj, d_seq, d_tickets); launches++;
+        k_sequences<<<grid, kSeqThreads, kSeqSmem, s>>>(d_blocks, d_sj, (uint32_t)n_sj, d_seq, d_tickets, d_tabs, d_hdrs); launches++;
     }
     mark();
-    if (n_sj) { k_records<<<(uint32_t)((n_sj + kRecWarps - 1) / kRecWarps), kRecWarps * 32, 0, s>>>(d_blocks, d_frames, d_sj, (uint32_t)n_sj, d_seq); launches++; }
+    if (n_sj) { k_records<<<(uint32_t)((n_sj + kRecWarps - 1) / kRecWarps), kRecWarps * 32, 0, s>>>(d_blocks, d_frames, d_sj, (uint32_t)n_sj, d_seq, d_tabs, d_hdrs); launches++; }
     mark();
     signal.fire();
     k_offsets<<<gi, tb, 0, s>>>(d_items, d_infos, d_bases, d_frames, d_blocks, d_outs, n); mark(); launches++;
@@ -676,12 +699,12 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
     if (n_frames && !(flags & FZG_NO_VERIFY_CHECKSUM)) { k_checksum<<<(uint32_t)((n_frames * 4 + 127) / 128), 128, 0, s>>>(d_frames, d_items, d_outs, (uint32_t)n_frames); launches++; }
     mark();
     k_finish<<<gi, tb, 0, s>>>(d_infos, d_bases, d_frames, d_outs, h_outs, n); launches++;
-    if (!prof) ev = 10;
+    if (!prof) ev = 11;
     cudaEventRecord(c->ev[ev], s);                                   // last event
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     c->timing.launches = launches;
     cudaEventElapsedTime(&c->timing.total_ms, c->ev[0], c->ev[ev]);
-    if (prof) for (int k = 0; k < 10; k++) cudaEventElapsedTime(&c->timing.kernel_ms[k], c->ev[k], c->ev[k + 1]);
+    if (prof) for (int k = 0; k < 11; k++) cudaEventElapsedTime(&c->timing.kernel_ms[k], c->ev[k], c->ev[k + 1]);
     return 0;
 }

@@ -46,7 +46,7 @@ struct FzPinBuf {
 struct FzLane {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[16] = {};
-    FzDevBuf d_infos, d_bases, d_outs, d_totals, d_frames, d_blocks, d_seq_jobs, d_huf_jobs, d_lit, d_seq;
+    FzDevBuf d_infos, d_bases, d_outs, d_totals, d_frames, d_blocks, d_seq_jobs, d_huf_jobs, d_lit, d_seq, d_seq_tabs, d_seq_hdrs;
     FzPinBuf h_totals;
     fzg_timing_t timing = {};
     cudaEvent_t ev_entropy = nullptr;      // recorded after this lane's entropy stages (literals, sequences, records)

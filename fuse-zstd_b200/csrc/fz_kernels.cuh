@@ -71,9 +71,9 @@ FZ_HD int lit_run(const LitWork& wk, uint32_t sub, const uint16_t* table, int lo
 
 // ------------------------------------------------------------------ sequences pass, stage A (one thread per block)
 // mem = kChainBytes of shared memory for this stream; bound / mask: see decode_sequences_chain.
-FZ_HD void seq_chain_thread(Block* blocks, Block& b, const SeqConsts& K, uint8_t* mem, uint64_t* seqs, uint32_t bound, uint32_t mask)
+FZ_HD void seq_chain_thread(Block& b, const uint8_t* gtab, const SeqJobHdr& h, uint8_t* mem, uint64_t* seqs, uint32_t bound, uint32_t mask)
 {
-    const int st = decode_sequences_chain(blocks, b, K, mem, seqs + b.seq_base, bound, mask);
+    const int st = decode_sequences_chain(b, gtab, h, mem, seqs + b.seq_base, bound, mask);
     if (st && !b.status) b.status = st;
 }
 

@@ -22,13 +22,12 @@ static const SeqConsts kConsts = { FZ_LL_BASE, FZ_ML_BASE, FZ_LL_BITS, FZ_ML_BIT
 
 // TEST-ONLY serial restatement of stage B (k_records in fz_decode.cu is warp-parallel CUDA): RAW records ->
 // positional records + span index + block totals, through the same helpers (raw_unpack, rep_update, rec_pack).
-static void records_serial(const Block* blocks, Block& b, uint32_t block_max, uint64_t* seqs)
+static void records_serial(const Block* blocks, Block& b, uint32_t block_max, uint64_t* seqs, const uint8_t* tab, const SeqJobHdr& h)
 {
     if (b.status) return;
     uint64_t* sq = seqs + b.seq_base;
-    static uint8_t yLL[512], yML[512]; int16_t norm_buf[64];
-    const uint8_t* bits = nullptr;
-    if (build_symbol_maps(blocks, b, kConsts, yLL, yML, norm_buf, bits) != 0) { b.status = FZG_E_CORRUPT; return; }
+    const uint8_t* yLL = tab + kChainCellBytes; const uint8_t* yML = yLL + 512;
+    const uint8_t* bits = b.src + h.bits_off;
     uint32_t rep0 = off_sym(0), rep1 = off_sym(1), rep2 = off_sym(2), E = 0, LE = 0;
     for (uint32_t i = 0; i < b.nseq; i++) {
         uint32_t ll, ml, ofv;
@@ -115,9 +114,14 @@ extern "C" int fze_decode_batch(size_t n, const void* const* src, const size_t* 
     alignas(16) static uint8_t chain_mem[kChainBytes];
     for (uint32_t j = 0; j < run.seq_job; j++) {
         Block& b = blocks[seq_jobs[j]];
-        seq_chain_thread(blocks.data(), b, kConsts, chain_mem, seqs.data(), b.nseq - 1, 1);
+        alignas(16) static uint8_t tab[kJobTableBytes]; SeqJobHdr h;
+        static uint8_t w_sym[512]; static int16_t w_norm[64]; static uint16_t w_cnt[64];
+        const TabWork tw{ { w_sym, 1 }, { w_norm, 1 }, { w_cnt, 1 } };
+        seq_tables_thread(blocks.data(), b, kConsts, tab, h, tw);
+        if (h.bad && !b.status) b.status = FZG_E_CORRUPT;
+        seq_chain_thread(b, tab, h, chain_mem, seqs.data(), b.nseq - 1, 1);
         if (!b.status) for (uint32_t i = 0; i < b.nseq; i++) g_far_records += seqs[b.seq_base + i] >> 63;
-        records_serial(blocks.data(), b, frames[b.frame].block_max, seqs.data());
+        records_serial(blocks.data(), b, frames[b.frame].block_max, seqs.data(), tab, h);
     }
     // offsets
     std::vector<ItemOut> outs(n);
@@ -172,8 +176,13 @@ extern "C" int fze_trace(const void* src, size_t src_len, uint64_t* seq_out, siz
     alignas(16) static uint8_t chain_mem[kChainBytes];
     for (uint32_t j = 0; j < info.n_seq_jobs; j++) {
         Block& b = blocks[sj[j]];
-        seq_chain_thread(blocks.data(), b, kConsts, chain_mem, seqs.data(), b.nseq - 1, 1);
-        records_serial(blocks.data(), b, frames[b.frame].block_max, seqs.data());
+        alignas(16) static uint8_t tab[kJobTableBytes]; SeqJobHdr h;
+        static uint8_t w_sym[512]; static int16_t w_norm[64]; static uint16_t w_cnt[64];
+        const TabWork tw{ { w_sym, 1 }, { w_norm, 1 }, { w_cnt, 1 } };
+        seq_tables_thread(blocks.data(), b, kConsts, tab, h, tw);
+        if (h.bad && !b.status) b.status = FZG_E_CORRUPT;
+        seq_chain_thread(b, tab, h, chain_mem, seqs.data(), b.nseq - 1, 1);
+        records_serial(blocks.data(), b, frames[b.frame].block_max, seqs.data(), tab, h);
     }
     it.dst_cap = ~0ull;
     ItemOut io; offsets_item(it, info, base, frames.data(), blocks.data(), io);      // resolves every block's starting history
