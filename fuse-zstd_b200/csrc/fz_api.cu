@@ -130,7 +130,11 @@ static inline size_t al16(size_t v) { return (v + 15) & ~(size_t)15; }
 // Device-resident batches run as one launch sequence.  Host-resident batches are cut into chunks of
 // ~2 GiB of (input + output) and pipelined on three streams: while chunk c is decoded, chunk c+1 crosses PCIe
 // host->device and chunk c-1 device->host, so the call costs about max(PCIe, kernels) instead of their sum.
-static constexpr size_t kChunkOutBytes = 2ull << 30;     // large enough that a chunk's kernels are throughput- not latency-bound
+static size_t chunk_bytes()                             // (input + output) bytes per chunk of a host-resident batch
+{
+    static const size_t v = [] { const char* e = getenv("FZG_CHUNK_MB"); return e && atoi(e) > 0 ? (size_t)atoi(e) << 20 : (size_t)2 << 30; }();
+    return v;
+}
 
 static int run_batch(bool encode, int device, size_t n, const void* const* src, const size_t* src_len, void* const* dst,
                      const size_t* dst_cap, size_t* dst_len, int* status, int flags, int level, size_t chunk)
@@ -236,10 +240,10 @@ static int run_batch(bool encode, int device, size_t n, const void* const* src, 
         if ((rc = run(0, n, nullptr))) return rc;
     } else {
         std::vector<size_t> cuts{ 0 };            // chunk boundaries: a small first chunk starts the device -> host stream early
-        size_t target = kChunkOutBytes / 4;
+        size_t target = chunk_bytes() / 4;
         for (size_t i = 0, bytes = 0; i < n; i++) {
             bytes += dst_cap[i] + src_len[i];
-            if (bytes >= target && i + 1 < n) { cuts.push_back(i + 1); bytes = 0; target = kChunkOutBytes; }
+            if (bytes >= target && i + 1 < n) { cuts.push_back(i + 1); bytes = 0; target = chunk_bytes(); }
         }
         cuts.push_back(n);
         const size_t nchunks = cuts.size() - 1;

@@ -84,17 +84,36 @@ FZ_HD uint64_t xx_lane(const uint8_t* p, uint64_t len, uint32_t j)   // accumula
     const uint64_t stripes = len >> 5;
     const uint8_t* q = p + 8 * j;
     if (((uintptr_t)p & 7) == 0) {
+        // a serial multiply chain fed from HBM: two batches of sixteen loads, the next one in flight while this one is consumed
         uint64_t s = 0;
-        for (; s + 16 <= stripes; s += 16) {             // a serial multiply chain fed from HBM: sixteen loads in flight per thread
-            uint64_t in[16];
+        uint64_t cur[16], nxt[16];
+        const bool any = stripes >= 16;
+        if (any) {
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-            for (int k = 0; k < 16; k++) in[k] = *(const uint64_t*)(q + 32 * (s + k));
+            for (int k = 0; k < 16; k++) cur[k] = *(const uint64_t*)(q + 32 * k);
+        }
+        for (; s + 32 <= stripes; s += 16) {
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-            for (int k = 0; k < 16; k++) acc = xx_round(acc, in[k]);
+            for (int k = 0; k < 16; k++) nxt[k] = *(const uint64_t*)(q + 32 * (s + 16 + k));
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+            for (int k = 0; k < 16; k++) acc = xx_round(acc, cur[k]);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+            for (int k = 0; k < 16; k++) cur[k] = nxt[k];
+        }
+        if (any) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+            for (int k = 0; k < 16; k++) acc = xx_round(acc, cur[k]);
+            s += 16;
         }
         for (; s < stripes; s++) acc = xx_round(acc, *(const uint64_t*)(q + 32 * s));
     } else {
