@@ -43,7 +43,13 @@ constexpr uint32_t kEncMinMatch = 4;
 #endif
 constexpr uint32_t kEncHashLog = FZ_ENC_HASHLOG;
 constexpr uint32_t kEncMaxOff = 65535;                       // the table keeps the low 16 bits of a position
-constexpr uint32_t kEncMatchWarps = 4;                       // warps (= chunks in flight) per CTA in k_enc_match
+#ifndef FZ_ENC_MATCH_WARPS
+#define FZ_ENC_MATCH_WARPS 4
+#endif
+constexpr uint32_t kEncMatchWarps = FZ_ENC_MATCH_WARPS;      // warps (= chunks in flight) per CTA in k_enc_match
+#ifndef FZ_ENC_LAZY
+#define FZ_ENC_LAZY 1
+#endif
 constexpr uint32_t kHufMaxLen = 11;
 
 struct EncChunk {
@@ -139,6 +145,11 @@ __global__ void __launch_bounds__(kEncMatchWarps * 32) k_enc_match(EncChunk* chu
                 const uint32_t l = __ffs(avail) - 1;
                 const uint32_t pl = base + l;
                 const uint32_t ml = __shfl_sync(0xFFFFFFFFu, len, l);
+#if FZ_ENC_LAZY
+                // lazy step: every lane already knows its own match, so looking one position ahead is free -- a longer
+                // match starting at the next byte wins and this byte becomes a literal
+                if (pl >= cur && l < 31 && ((avail >> (l + 1)) & 1u) && __shfl_sync(0xFFFFFFFFu, len, l + 1) > ml) { avail &= ~(1u << l); continue; }
+#endif
                 const uint32_t off = pl - (uint32_t)__shfl_sync(0xFFFFFFFFu, cand, l);
                 if (pl >= cur) {
                     const uint32_t ll = pl - anchor;
