@@ -233,8 +233,15 @@ __global__ void __launch_bounds__(kRecWarps * 32) k_records(Block* blocks, const
 {
     __shared__ SeqConsts K;
     __shared__ __align__(16) uint8_t s_y[kRecWarps][2][512]; // state -> symbol maps of the block (LL, ML), from the table stage
+    constexpr uint32_t kFullMask = 0xFFFFFFFFu;
     for (uint32_t i = threadIdx.x; i < sizeof(SeqConsts) / 4; i += blockDim.x) ((uint32_t*)&K)[i] = ((const uint32_t*)&c_seq_consts)[i];
     __syncthreads();
+#ifdef FZ_REC_PACKED_TABLES
+    __shared__ uint32_t s_llpk[36], s_mlpk[53];              // per length code: baseline | extra bits << 24
+    if (threadIdx.x < 36) s_llpk[threadIdx.x] = K.ll_base[threadIdx.x] | ((uint32_t)K.ll_bits[threadIdx.x] << 24);
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + 53) s_mlpk[threadIdx.x - 64] = K.ml_base[threadIdx.x - 64] | ((uint32_t)K.ml_bits[threadIdx.x - 64] << 24);
+    __syncthreads();
+#endif
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t job = blockIdx.x * kRecWarps + warp;
     if (job >= n_jobs) return;
@@ -251,38 +258,78 @@ __global__ void __launch_bounds__(kRecWarps * 32) k_records(Block* blocks, const
     uint64_t* sq = seqs + b.seq_base;
     uint32_t rep0 = off_sym(0), rep1 = off_sym(1), rep2 = off_sym(2);      // history, warp-uniform
     uint32_t Ebase = 0, LEbase = 0; bool bad = false;
+#ifdef FZ_REC_PREFETCH
+    uint64_t rnext = lane < nseq ? sq[lane] : 0;                           // the records of a step are loaded a step early
+#endif
     for (uint32_t g = 0; g < nseq && !bad; g += 32) {
         const uint32_t i = g + lane; const bool valid = i < nseq;
         const uint32_t nv = min(32u, nseq - g);
         uint32_t ll = 0, ml = 0, ofv = 4; bool ok = true;
-        if (valid) ok = raw_unpack(sq[i], K, yLL, yML, bits, ll, ml, ofv);
-        const uint32_t LE = LEbase + warp_scan_incl(ll, lane), E = Ebase + warp_scan_incl(ll + ml, lane);
+#ifdef FZ_REC_PREFETCH
+        const uint64_t r = rnext;
+        rnext = i + 32 < nseq ? sq[i + 32] : 0;
+#else
+        const uint64_t r = valid ? sq[i] : 0;
+#endif
+#ifdef FZ_REC_PACKED_TABLES
+        {
+            const uint32_t x = (uint32_t)r, y = (uint32_t)(r >> 32);
+            const uint32_t cl = s_llpk[yLL[(y & 0x3FFu) >> 1]], cm = s_mlpk[yML[((y >> 12) & 0x3FFu) >> 1]], yof = (y >> 24) & 31;
+            const uint32_t llb = cl >> 24, mlb = cm >> 24;
+            if (valid) {
+                if (y >> 31) ok = raw_unpack(r, K, yLL, yML, bits, ll, ml, ofv);
+                else {
+                    ofv = (1u << yof) + shr_c(x, 32 - yof);
+                    ml = (cm & 0xFFFFFFu) + shr_c(shl_c(x, yof), 32 - mlb);
+                    ll = (cl & 0xFFFFFFu) + shr_c(shl_c(x, yof + mlb), 32 - llb);
+                    ok = yof <= 27;
+                }
+            }
+        }
+#else
+        if (valid) ok = raw_unpack(r, K, yLL, yML, bits, ll, ml, ofv);
+#endif
+        uint32_t LE, E;
+#ifndef FZ_REC_NO_PACKED_SCAN
+        if (__all_sync(kFullMask, ll < 1024u && ll + ml < 4096u)) {        // one packed scan when the lengths are small (15 + 17 bits)
+            const uint32_t v = warp_scan_incl(ll | ((ll + ml) << 15), lane);
+            LE = LEbase + (v & 0x7FFFu); E = Ebase + (v >> 15);
+        } else
+#endif
+        { LE = LEbase + warp_scan_incl(ll, lane); E = Ebase + warp_scan_incl(ll + ml, lane); }
         // ---- repeat offsets
         uint32_t off = ofv - 3;
-        uint32_t reps = __ballot_sync(0xFFFFFFFFu, valid && ofv <= 3);
-        uint32_t pos = 0;                                                  // history is valid as of lane `pos`
-        auto advance = [&](uint32_t upto) {                                // lanes [pos, upto) are plain offsets: push the last three
-            const uint32_t cnt = upto - pos;
-            const uint32_t o1 = __shfl_sync(0xFFFFFFFFu, off, (upto - 1) & 31), o2 = __shfl_sync(0xFFFFFFFFu, off, (upto - 2) & 31),
-                           o3 = __shfl_sync(0xFFFFFFFFu, off, (upto - 3) & 31);
-            const uint32_t n0 = cnt >= 1 ? o1 : rep0, n1 = cnt >= 2 ? o2 : (cnt == 1 ? rep0 : rep1),
-                           n2 = cnt >= 3 ? o3 : (cnt == 2 ? rep0 : (cnt == 1 ? rep1 : rep2));
-            rep0 = n0; rep1 = n1; rep2 = n2; pos = upto;
-        };
-        while (reps) {
-            const uint32_t r = __ffs(reps) - 1; reps &= reps - 1;
-            advance(r);
-            const uint32_t ofr = __shfl_sync(0xFFFFFFFFu, ofv, r); const bool ll0 = __shfl_sync(0xFFFFFFFFu, ll, r) == 0;
-            const uint32_t o = rep_update(ofr, ll0, rep0, rep1, rep2);
-            if (lane == r) off = o;
-            pos = r + 1;
+        uint32_t reps = __ballot_sync(kFullMask, valid && ofv <= 3);
+#ifdef FZ_REC_REP_FAST
+        if (reps == 0 && nv >= 3) {                                        // no repeat code in this step: the history is its last three offsets
+            rep0 = __shfl_sync(kFullMask, off, nv - 1); rep1 = __shfl_sync(kFullMask, off, nv - 2); rep2 = __shfl_sync(kFullMask, off, nv - 3);
+        } else
+#endif
+        {
+            uint32_t pos = 0;                                              // history is valid as of lane `pos`
+            auto advance = [&](uint32_t upto) {                            // lanes [pos, upto) are plain offsets: push the last three
+                const uint32_t cnt = upto - pos;
+                const uint32_t o1 = __shfl_sync(kFullMask, off, (upto - 1) & 31), o2 = __shfl_sync(kFullMask, off, (upto - 2) & 31),
+                               o3 = __shfl_sync(kFullMask, off, (upto - 3) & 31);
+                const uint32_t n0 = cnt >= 1 ? o1 : rep0, n1 = cnt >= 2 ? o2 : (cnt == 1 ? rep0 : rep1),
+                               n2 = cnt >= 3 ? o3 : (cnt == 2 ? rep0 : (cnt == 1 ? rep1 : rep2));
+                rep0 = n0; rep1 = n1; rep2 = n2; pos = upto;
+            };
+            while (reps) {
+                const uint32_t rr = __ffs(reps) - 1; reps &= reps - 1;
+                advance(rr);
+                const uint32_t ofr = __shfl_sync(kFullMask, ofv, rr); const bool ll0 = __shfl_sync(kFullMask, ll, rr) == 0;
+                const uint32_t o = rep_update(ofr, ll0, rep0, rep1, rep2);
+                if (lane == rr) off = o;
+                pos = rr + 1;
+            }
+            advance(nv);
         }
-        advance(nv);
         ok = ok && !(ofv > 3 && off > kOffMax) && LE <= lit_regen && E <= block_max;
-        bad = __any_sync(0xFFFFFFFFu, valid && !ok);
+        bad = __any_sync(kFullMask, valid && !ok);
         if (bad) break;
         if (valid) sq[i] = rec_pack(E, LE, off);
-        Ebase = __shfl_sync(0xFFFFFFFFu, E, 31); LEbase = __shfl_sync(0xFFFFFFFFu, LE, 31);
+        Ebase = __shfl_sync(kFullMask, E, 31); LEbase = __shfl_sync(kFullMask, LE, 31);
     }
     const uint32_t rsize = Ebase + (lit_regen - LEbase);
     if (bad || rsize > block_max) { if (lane == 0) b.status = FZG_E_CORRUPT; return; }
