@@ -10,11 +10,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.environ.get("FZG_LIB") or os.path.join(HERE, "libfzgpu.so")   # FZG_LIB: a differently tuned build (kernel experiments)
 
 OK, E_MAGIC, E_TRUNCATED, E_UNSUPPORTED, E_CORRUPT, E_DSTSIZE, E_CHECKSUM, E_FCS = range(8)
-SRC_DEVICE, DST_DEVICE, NO_VERIFY_CHECKSUM, PROFILE = 1, 2, 4, 8
+SRC_DEVICE, DST_DEVICE, NO_VERIFY_CHECKSUM, PROFILE, SEEK_TABLE = 1, 2, 4, 8, 16
 
 EXPORTS = ["fzg_init", "fzg_shutdown", "fzg_device_count", "fzg_decode_fd", "fzg_encode_fd", "fzg_decode_batch",
            "fzg_encode_batch", "fzg_encode_bound", "fzg_frame_info", "fzg_strerror", "fzg_last_timing",
-           "fzg_stage_name", "fzg_stream"]
+           "fzg_stage_name", "fzg_stream", "fzg_decode_range", "fzg_decode_range_fd", "fzg_seek_footer"]
 
 
 class Timing(C.Structure):
@@ -57,6 +57,15 @@ def lib():
         L.fzg_last_timing.restype = C.c_int; L.fzg_last_timing.argtypes = [C.c_int, C.POINTER(Timing)]
         L.fzg_stage_name.restype = C.c_char_p; L.fzg_stage_name.argtypes = [C.c_int]
         L.fzg_stream.restype = C.c_void_p; L.fzg_stream.argtypes = [C.c_int]
+        if not hasattr(L, "fzg_decode_range"):            # an older tuned build loaded through FZG_LIB (kernel experiments)
+            _lib = L
+            return _lib
+        L.fzg_decode_range.restype = C.c_int
+        L.fzg_decode_range.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_uint64, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]
+        L.fzg_decode_range_fd.restype = C.c_int
+        L.fzg_decode_range_fd.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]
+        L.fzg_seek_footer.restype = C.c_int
+        L.fzg_seek_footer.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
@@ -174,3 +183,26 @@ def encode_fd(src_fd, dst_fd, level, src_size, shard_key=0):
     if rc != 0:
         raise OSError(-rc if rc < 0 else errno.EIO, "zstd encode failed")
     return out.value
+
+
+def seek_footer(tail, file_size):
+    """Host-only: (rc, n_frames, table_bytes) of the seek table whose footer ends `tail` (the last >= 9 bytes of a file)."""
+    a = np.frombuffer(tail, dtype=np.uint8)
+    nf, tb = C.c_uint32(0), C.c_uint64(0)
+    rc = lib().fzg_seek_footer(a.ctypes.data if a.size else None, a.size, file_size, C.byref(nf), C.byref(tb))
+    return rc, nf.value, tb.value
+
+
+def decode_range(data, offset, size, device=0):
+    """Plain bytes [offset, offset + size) of a .zst image that ends in a seek table; only the frames touched are decoded.
+    -> (rc, bytes); rc == -errno.ENOENT when there is no seek table."""
+    a = np.frombuffer(data, dtype=np.uint8)
+    out = np.empty(max(size, 1), dtype=np.uint8); got = C.c_size_t(0)
+    rc = lib().fzg_decode_range(device, a.ctypes.data, a.size, offset, size, out.ctypes.data, C.byref(got))
+    return rc, out[:got.value].tobytes()
+
+
+def decode_range_fd(fd, offset, size, shard_key=0):
+    out = np.empty(max(size, 1), dtype=np.uint8); got = C.c_size_t(0)
+    rc = lib().fzg_decode_range_fd(fd, shard_key, offset, size, out.ctypes.data, C.byref(got))
+    return rc, out[:got.value].tobytes()

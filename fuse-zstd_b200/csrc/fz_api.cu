@@ -406,12 +406,102 @@ extern "C" int fzg_encode_fd(int src_fd, int dst_fd, int level, uint64_t src_siz
     size_t cap = fzg_encode_bound(in.size(), 0);
     std::vector<uint8_t> out(cap);
     const void* sp = in.data(); size_t sl = in.size(); void* dp = out.data(); size_t dl = 0; int ist = 0;
-    rc = fzg_encode_batch(c->dev, 1, &sp, &sl, &dp, &cap, &dl, &ist, level, 0, 0);
+    static const bool seek = getenv("FZG_SEEK_TABLE") != nullptr;          // files written through the mount carry a seek table
+    rc = fzg_encode_batch(c->dev, 1, &sp, &sl, &dp, &cap, &dl, &ist, level, 0, seek ? FZG_SEEK_TABLE : 0);
     if (rc) return rc;
     if (ist) return -EIO;
     if ((rc = write_all(dst_fd, out.data(), dl))) return rc;
     if (out_size) *out_size = dl;
     return 0;
+}
+
+// ---------------------------------------------------------------------------------- seek table, partial reads
+static inline uint32_t rd32le(const uint8_t* p) { return p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+// Footer of the zstd seekable format at the end of a file: Number_Of_Frames | descriptor | 0x8F92EAB1.  `tail` = the last
+// `tail_len` (>= 9) bytes of the file.  On success: the number of frames and the size of the whole skippable frame.
+extern "C" int fzg_seek_footer(const void* tail, size_t tail_len, uint64_t file_size, uint32_t* n_frames, uint64_t* table_bytes)
+{
+    if (!tail || !n_frames || !table_bytes) return -EINVAL;
+    if (tail_len < 9 || file_size < 17) return -ENOENT;
+    const uint8_t* f = (const uint8_t*)tail + tail_len - 9;
+    if (rd32le(f + 5) != 0x8F92EAB1u) return -ENOENT;
+    if (f[4] & 0x7C) return -ENOENT;                         // reserved descriptor bits
+    const uint32_t nf = rd32le(f); const uint32_t entry = (f[4] & 0x80) ? 12 : 8;
+    const uint64_t bytes = 8 + (uint64_t)entry * nf + 9;
+    if (bytes > file_size) return -ENOENT;
+    *n_frames = nf; *table_bytes = bytes;
+    return 0;
+}
+
+// Decodes plain bytes [offset, offset + size) of a .zst file that carries a seek table, reading and decoding only the
+// frames the range touches.  rd(buf, len, file_offset) reads the compressed file.  -ENOENT: no (valid) seek table.
+template <class READ>
+static int decode_range(FzCtx* c, READ rd, uint64_t file_size, uint64_t offset, size_t size, void* dst, size_t* got)
+{
+    *got = 0;
+    uint8_t foot[9];
+    if (file_size < 17) return -ENOENT;
+    int rc = rd(foot, 9, file_size - 9); if (rc) return rc;
+    uint32_t nf = 0; uint64_t tb = 0;
+    if ((rc = fzg_seek_footer(foot, 9, file_size, &nf, &tb))) return rc;
+    std::vector<uint8_t> tab(tb);
+    if ((rc = rd(tab.data(), tb, file_size - tb))) return rc;
+    if ((rd32le(tab.data()) & 0xFFFFFFF0u) != 0x184D2A50u || rd32le(tab.data() + 4) != tb - 8) return -ENOENT;
+    const uint32_t entry = (foot[4] & 0x80) ? 12 : 8;
+    // frames overlapping the range
+    uint64_t coff = 0, doff = 0, c_lo = 0, d_lo = 0; uint32_t f0 = nf, f1 = nf;
+    std::vector<uint64_t> cs, ds;
+    for (uint32_t f = 0; f < nf; f++) {
+        const uint64_t csz = rd32le(tab.data() + 8 + (size_t)entry * f), dsz = rd32le(tab.data() + 12 + (size_t)entry * f);
+        if (f0 == nf && doff + dsz > offset && size) { f0 = f; c_lo = coff; d_lo = doff; }
+        if (f0 != nf && f1 == nf) { cs.push_back(csz); ds.push_back(dsz); if (doff + dsz >= offset + size) f1 = f + 1; }
+        coff += csz; doff += dsz;
+    }
+    if (coff + tb != file_size) return -ENOENT;              // the table does not describe this file
+    if (f0 == nf) return 0;                                  // range at or past the end: nothing to read
+    if (f1 == nf) f1 = nf;
+    const size_t k = cs.size();
+    uint64_t c_bytes = 0, d_bytes = 0;
+    for (size_t i = 0; i < k; i++) { c_bytes += cs[i]; d_bytes += ds[i]; }
+    std::vector<uint8_t> comp(c_bytes ? c_bytes : 1), plain(d_bytes ? d_bytes : 1);
+    if ((rc = rd(comp.data(), c_bytes, c_lo))) return rc;
+    std::vector<const void*> sp(k); std::vector<void*> dp(k); std::vector<size_t> sl(k), dc(k), dl(k); std::vector<int> st(k);
+    { uint64_t a = 0, b = 0; for (size_t i = 0; i < k; i++) { sp[i] = comp.data() + a; sl[i] = cs[i]; dp[i] = plain.data() + b; dc[i] = ds[i]; a += cs[i]; b += ds[i]; } }
+    rc = fzg_decode_batch(c->dev, k, sp.data(), sl.data(), dp.data(), dc.data(), dl.data(), st.data(), 0);
+    if (rc) return rc;
+    for (size_t i = 0; i < k; i++) { if (st[i]) return st[i]; if (dl[i] != ds[i]) return FZG_E_CORRUPT; }
+    const uint64_t skip = offset - d_lo, avail = d_bytes - skip;
+    const size_t n = (size_t)std::min<uint64_t>(size, avail);
+    memcpy(dst, plain.data() + skip, n);
+    *got = n;
+    return 0;
+}
+
+extern "C" int fzg_decode_range(int device, const void* src, size_t len, uint64_t offset, size_t size, void* dst, size_t* got)
+{
+    if (!src || !dst || !got) return -EINVAL;
+    int rc = ensure_init(); if (rc) return rc;
+    FzCtx* c = ctx_for(device);
+    if (!c) return -ENODEV;
+    auto rd = [&](uint8_t* buf, size_t n, uint64_t at) -> int { if (at + n > len) return -EIO; memcpy(buf, (const uint8_t*)src + at, n); return 0; };
+    return decode_range(c, rd, len, offset, size, dst, got);
+}
+
+extern "C" int fzg_decode_range_fd(int src_fd, uint64_t shard_key, uint64_t offset, size_t size, void* dst, size_t* got)
+{
+    if (!dst || !got) return -EINVAL;
+    int rc = ensure_init(); if (rc) return rc;
+    FzCtx* c = ctx_for_key(shard_key);
+    if (!c) return -ENODEV;
+    const off_t end = lseek(src_fd, 0, SEEK_END);
+    if (end < 0) return -errno;
+    auto rd = [&](uint8_t* buf, size_t n, uint64_t at) -> int {
+        size_t done = 0;
+        while (done < n) { const ssize_t r = pread(src_fd, buf + done, n - done, (off_t)(at + done)); if (r < 0) { if (errno == EINTR) continue; return -errno; } if (r == 0) return -EIO; done += (size_t)r; }
+        return 0;
+    };
+    return decode_range(c, rd, (uint64_t)end, offset, size, dst, got);
 }
 
 // ---------------------------------------------------------------------------------- misc

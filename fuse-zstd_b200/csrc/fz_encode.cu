@@ -25,6 +25,7 @@
  */
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -134,9 +135,14 @@ __global__ void __launch_bounds__(kEncMatchWarps * 32) k_enc_match(EncChunk* chu
                 const uint32_t maxlen = size - p;
                 uint64_t x = ld8u(a) ^ v;
                 if ((uint32_t)x == 0) {                                     // at least 4 bytes
-                    while (x == 0 && len + 8 < maxlen) { len += 8; x = ld8u(a + len) ^ ld8u(b + len); }
-                    len += x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8;
-                    if (len > maxlen) len = maxlen;
+                    // 8 bytes per probe while a whole probe fits in the chunk, then byte by byte: nothing past the last byte of
+                    // the chunk is read (the source buffer may end exactly where its allocation ends)
+                    for (;;) {
+                        if (x) { len += (uint32_t)(__ffsll((long long)x) - 1) >> 3; break; }
+                        len += 8;
+                        if (len + 8 > maxlen) { while (len < maxlen && a[len] == b[len]) len++; break; }
+                        x = ld8u(a + len) ^ ld8u(b + len);
+                    }
                 }
             }
             // greedy selection, left to right
@@ -515,12 +521,18 @@ __global__ void __launch_bounds__(kSeqEncWarps * 32) k_enc_seq(EncChunk* chunks,
 // ------------------------------------------------------------------ placement + final write
 __device__ __forceinline__ uint32_t frame_header_size(uint32_t size) { return 4 + 1 + (size < 256 ? 1 : (size < 65536 + 256 ? 2 : 4)); }
 
-__global__ void k_enc_place(const Item* items, EncChunk* chunks, const uint32_t* first_chunk, ItemOut* outs, uint32_t n_items)
+// Seek table (FZG_SEEK_TABLE): the zstd "seekable format" -- a skippable frame after the last data frame holding
+// (Compressed_Size, Decompressed_Size) of every frame and a footer (Number_Of_Frames, descriptor 0, 0x8F92EAB1).  Stock
+// decoders skip it; fzg_decode_range uses it to decode only the frames a read touches.
+__device__ __forceinline__ void st32le(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
+
+__global__ void k_enc_place(const Item* items, EncChunk* chunks, const uint32_t* first_chunk, ItemOut* outs, uint32_t n_items, int seek)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_items) return;
     uint64_t pos = 0; int status = 0;
-    for (uint32_t c = first_chunk[i]; c < first_chunk[i + 1]; c++) {
+    const uint32_t c0 = first_chunk[i], c1 = first_chunk[i + 1];
+    for (uint32_t c = c0; c < c1; c++) {
         EncChunk& ch = chunks[c];
         const uint32_t body = ch.lit_sec + ch.seq_sec;
         const bool compressed = ch.size >= 32 && body + 8 < ch.size && body < kEncChunkMax;
@@ -528,7 +540,17 @@ __global__ void k_enc_place(const Item* items, EncChunk* chunks, const uint32_t*
         ch.frame_size = frame_header_size(ch.size) + 3 + (compressed ? body : ch.size) + 4;
         ch.out_off = pos; pos += ch.frame_size;
     }
+    const uint32_t nf = c1 - c0;
+    const uint64_t table_at = pos;
+    if (seek) pos += 8 + 8ull * nf + 9;
     if (pos > items[i].dst_cap) status = FZG_E_DSTSIZE;
+    if (seek && !status) {
+        uint8_t* t = items[i].dst + table_at;
+        st32le(t, 0x184D2A5Eu); st32le(t + 4, 8 * nf + 9);
+        for (uint32_t c = c0; c < c1; c++) { st32le(t + 8 + 8 * (c - c0), chunks[c].frame_size); st32le(t + 12 + 8 * (c - c0), chunks[c].size); }
+        uint8_t* f = t + 8 + 8ull * nf;
+        st32le(f, nf); f[4] = 0; st32le(f + 5, 0x8F92EAB1u);
+    }
     outs[i].dst_len = status ? 0 : pos; outs[i].status = status; outs[i].fail = status != 0;
 }
 
@@ -586,7 +608,7 @@ size_t fzh_encode_bound(size_t src_len, size_t chunk)
 {
     const size_t cs = enc_chunk_size(chunk);
     const size_t frames = src_len ? (src_len + cs - 1) / cs : 1;
-    return src_len + frames * 16 + 16;
+    return src_len + frames * 16 + 16 + (8 + 8 * frames + 9);          // + room for the seek table
 }
 
 int fzh_encode_setup(void)
@@ -619,62 +641,86 @@ int fzh_encode_run(FzCtx* c, uint32_t first, uint32_t n, int level, size_t chunk
     if ((rc = c->e_items.reserve(n_chunks * sizeof(EncChunk)))) return rc;
     if ((rc = c->d_outs.reserve(n * sizeof(ItemOut)))) return rc;
     if ((rc = c->d_totals.reserve(128))) return rc;
-    const uint64_t wave = std::min<uint64_t>(n_chunks, 8192);
+    // The per-chunk scratch is large, so the chunks are processed in waves of <= kWaveChunks (1 GiB of input).  Frame
+    // offsets depend only on the chunks of the same item, so a wave that holds whole items is sized, placed and written
+    // in one pass; an item larger than a wave is sized wave by wave first and then regenerated and written (the stages
+    // are deterministic).
+    constexpr uint64_t kWaveChunks = 8192;
+    const uint64_t wave = std::min<uint64_t>(n_chunks, kWaveChunks);
     if ((rc = c->e_work.reserve(wave * (uint64_t)kScrBytes))) return rc;
     EncChunk* hc = (EncChunk*)c->e_chunks_h.p;
     memcpy(c->e_first_h.p, first_chunk.data(), (n + 1) * 4);
-    for (uint32_t i = 0; i < n; i++) {
-        uint64_t off = 0;
-        for (uint32_t k = first_chunk[i]; k < first_chunk[i + 1]; k++) {
-            EncChunk& ch = hc[k];
-            ch.src = h_items[i].src + off; ch.size = (uint32_t)std::min<uint64_t>(cs, h_items[i].src_len - off); off += ch.size;
-            ch.scratch = (uint8_t*)c->e_work.p + (uint64_t)(k % wave) * kScrBytes;
-            ch.item = i; ch.nseq = ch.nlit = ch.lit_sec = ch.seq_sec = ch.frame_size = ch.raw = 0; ch.out_off = 0;
-        }
+    struct Group { uint32_t ia, ib; };                 // items [ia, ib): one single-pass wave, or one oversized item
+    std::vector<Group> groups;
+    for (uint32_t ia = 0; ia < n;) {
+        uint32_t ib = ia + 1;
+        while (ib < n && first_chunk[ib + 1] - first_chunk[ia] <= wave) ib++;
+        groups.push_back({ ia, ib }); ia = ib;
     }
+    for (const Group& g : groups)
+        for (uint32_t i = g.ia; i < g.ib; i++) {
+            uint64_t off = 0;
+            for (uint32_t k = first_chunk[i]; k < first_chunk[i + 1]; k++) {
+                EncChunk& ch = hc[k];
+                ch.src = h_items[i].src + off; ch.size = (uint32_t)std::min<uint64_t>(cs, h_items[i].src_len - off); off += ch.size;
+                ch.scratch = (uint8_t*)c->e_work.p + (uint64_t)((k - first_chunk[g.ia]) % wave) * kScrBytes;
+                ch.item = i; ch.nseq = ch.nlit = ch.lit_sec = ch.seq_sec = ch.frame_size = ch.raw = 0; ch.out_off = 0;
+            }
+        }
     EncChunk* d_chunks = (EncChunk*)c->e_items.p;
     ItemOut* d_outs = (ItemOut*)c->d_outs.p;
     uint32_t* d_tickets = (uint32_t*)c->d_totals.p;
     CK(cudaMemcpyAsync(d_chunks, hc, n_chunks * sizeof(EncChunk), cudaMemcpyHostToDevice, s));
+    const int seek = (flags & FZG_SEEK_TABLE) ? 1 : 0;
     int ev = 0;
     auto mark = [&]() { if (prof || ev == 0) cudaEventRecord(c->ev[ev], s); ev++; };
     mark();
     int launches = 0;
-    const uint64_t n_waves = (n_chunks + wave - 1) / wave;
     uint32_t* d_first = (uint32_t*)c->e_first_h.p;                         // pinned host memory, read zero-copy
-    auto run_wave = [&](uint64_t w, bool marks) -> int {
-        const uint64_t lo = w * wave; const uint32_t cnt = (uint32_t)std::min<uint64_t>(wave, n_chunks - lo);
+    static const bool dbg = getenv("FZG_DEBUG_SYNC") != nullptr;           // locate a faulting kernel: synchronise after every stage
+    auto check = [&](const char* what) -> int {
+        if (!dbg) return 0;
+        const cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { fprintf(stderr, "fzgpu: %s: %s\n", what, cudaGetErrorString(e)); return -5; }
+        return 0;
+    };
+    auto run_wave = [&](uint64_t lo, uint32_t cnt, bool marks) -> int {   // match -> literals -> sequences for chunks [lo, lo + cnt)
         CK(cudaMemsetAsync(d_tickets, 0, 16, s));
         k_enc_match<<<std::min<uint32_t>((cnt + kEncMatchWarps - 1) / kEncMatchWarps, 148 * ((200u << 10) / (kEncMatchWarps * (2u << kEncHashLog)))), kEncMatchWarps * 32, kEncMatchWarps * (2 << kEncHashLog), s>>>(d_chunks + lo, cnt, d_tickets);
+        if (check("k_enc_match")) return -5;
         if (marks) mark();
         k_enc_lit<<<std::min<uint32_t>((cnt + kLitWarps - 1) / kLitWarps, 148 * 8), kLitWarps * 32, 0, s>>>(d_chunks + lo, cnt, d_tickets + 1);
+        if (check("k_enc_lit")) return -5;
         if (marks) mark();
         k_enc_seq<<<std::min<uint32_t>((cnt + kSeqEncWarps - 1) / kSeqEncWarps, 148 * 7), kSeqEncWarps * 32, 0, s>>>(d_chunks + lo, cnt, d_tickets + 2);
+        if (check("k_enc_seq")) return -5;
         if (marks) mark();
         launches += 3;
         return 0;
     };
-    // k_enc_write needs every frame's offset, i.e. every chunk's compressed size, while the per-chunk scratch only
-    // holds one wave (8192 chunks = 1 GiB of input).  One wave: match -> lit -> seq -> place -> write.  Several waves:
-    // pass 1 sizes all waves, then each wave is regenerated (the stages are deterministic) and written.
-    if (n_waves == 1) {
-        if ((rc = run_wave(0, true))) return rc;
-        k_enc_place<<<(n + 127) / 128, 128, 0, s>>>(h_items, d_chunks, d_first, d_outs, n); mark();
-        k_enc_write<<<(uint32_t)((n_chunks * 32 + 127) / 128), 128, 0, s>>>(h_items, d_chunks, d_outs, (uint32_t)n_chunks); mark();
-        launches += 2;
-    } else {
-        for (uint64_t w = 0; w < n_waves; w++) if ((rc = run_wave(w, false))) return rc;
-        mark(); mark(); mark();
-        k_enc_place<<<(n + 127) / 128, 128, 0, s>>>(h_items, d_chunks, d_first, d_outs, n); mark();
-        launches++;
-        for (uint64_t w = 0; w < n_waves; w++) {
-            const uint64_t lo = w * wave; const uint32_t cnt = (uint32_t)std::min<uint64_t>(wave, n_chunks - lo);
-            if ((rc = run_wave(w, false))) return rc;
-            k_enc_write<<<(cnt * 32 + 127) / 128, 128, 0, s>>>(h_items, d_chunks + lo, d_outs, cnt);
+    const bool one = groups.size() == 1 && first_chunk[n] <= wave;         // per-stage events only make sense for a single wave
+    for (const Group& g : groups) {
+        const uint64_t lo = first_chunk[g.ia]; const uint64_t cnt = first_chunk[g.ib] - lo; const uint32_t ni = g.ib - g.ia;
+        if (cnt <= wave) {
+            if ((rc = run_wave(lo, (uint32_t)cnt, one))) return rc;
+            k_enc_place<<<(ni + 127) / 128, 128, 0, s>>>(h_items + g.ia, d_chunks, d_first + g.ia, d_outs + g.ia, ni, seek); if (one) mark();
+            if (check("k_enc_place")) return -5;
+            k_enc_write<<<(uint32_t)((cnt * 32 + 127) / 128), 128, 0, s>>>(h_items, d_chunks + lo, d_outs, (uint32_t)cnt); if (one) mark();
+            if (check("k_enc_write")) return -5;
+            launches += 2;
+        } else {                                                           // one oversized item
+            for (uint64_t w = lo; w < lo + cnt; w += wave) if ((rc = run_wave(w, (uint32_t)std::min<uint64_t>(wave, lo + cnt - w), false))) return rc;
+            k_enc_place<<<1, 128, 0, s>>>(h_items + g.ia, d_chunks, d_first + g.ia, d_outs + g.ia, 1, seek);
             launches++;
+            for (uint64_t w = lo; w < lo + cnt; w += wave) {
+                const uint32_t wc = (uint32_t)std::min<uint64_t>(wave, lo + cnt - w);
+                if ((rc = run_wave(w, wc, false))) return rc;
+                k_enc_write<<<(wc * 32 + 127) / 128, 128, 0, s>>>(h_items, d_chunks + w, d_outs, wc);
+                launches++;
+            }
         }
-        mark();
     }
+    if (!one) { while (ev < 5) mark(); }
     if (!prof) ev = 5;
     cudaEventRecord(c->ev[ev], s);
     CK(cudaMemcpyAsync(h_outs, d_outs, n * sizeof(ItemOut), cudaMemcpyDeviceToHost, s));

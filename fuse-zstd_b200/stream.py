@@ -4,6 +4,9 @@
   Encoder(writer, level) + set_pledged_src_size + include_checksum + write + finish
                                          /root/reference/src/main.rs:781-791
   decode_all(source)                     /root/reference/tests/utils.rs:12-17
+  read_range(source, offset, size)       the read path, /root/reference/src/main.rs:495-513, without the whole-file
+                                         decode at open: only the frames the range touches (needs the seek table
+                                         FZG_SEEK_TABLE writes)
 
 Arguments are Python file objects (anything with fileno()), standing in for the dup'd
 std::fs::File handles the reference passes.  Error behaviour follows the reference: a decode
@@ -61,3 +64,16 @@ class Encoder:
         n = codec.encode_fd(self._spool.fileno(), self.writer.fileno(), self.level, size, self.inode)
         self._spool.close()
         return n
+
+
+def read_range(source, offset, size, inode=0):
+    """Plain bytes [offset, offset + size) of the .zst file `source`.  Files that carry a seek table are decoded
+    partially; any other file is decoded whole (what the reference does at open) and sliced."""
+    import errno
+    rc, data = codec.decode_range_fd(source.fileno(), offset, size, inode)
+    if rc == 0:
+        return data
+    if rc != -errno.ENOENT:
+        raise OSError(errno.EFAULT, "decode failed: %s" % codec.strerror(rc))        # src/main.rs:467
+    os.lseek(source.fileno(), 0, os.SEEK_SET)
+    return decode_all(source, inode)[offset:offset + size]

@@ -40,7 +40,8 @@ enum {
     FZG_SRC_DEVICE = 1,         /* src[i] are device pointers (batch already resident in HBM)   */
     FZG_DST_DEVICE = 2,         /* dst[i] are device pointers                                   */
     FZG_NO_VERIFY_CHECKSUM = 4, /* skip XXH64 verification (default: verify, as libzstd does)   */
-    FZG_PROFILE = 8             /* record CUDA-event time per kernel (see fzg_last_timing)      */
+    FZG_PROFILE = 8,            /* record CUDA-event time per kernel (see fzg_last_timing)      */
+    FZG_SEEK_TABLE = 16         /* encode: append a seek table (zstd seekable format) per file  */
 };
 
 /* Creates one context (stream, pinned staging, scratch) per listed CUDA device.  devices == NULL
@@ -89,6 +90,18 @@ size_t fzg_encode_bound(size_t src_len, size_t chunk_size);
  * without decoding it.  *content_size = UINT64_MAX when some frame omits the field.
  */
 int fzg_frame_info(const void* src, size_t len, uint64_t* content_size, uint64_t* compressed_size);
+
+/*
+ * Partial reads (the reference decodes the whole file on open and serves read(offset, size) from the
+ * tmpfile, src/main.rs:495-513).  A file written with FZG_SEEK_TABLE ends in a skippable frame of the zstd seekable
+ * format; these calls read that table and decode ONLY the frames that hold plain bytes [offset, offset + size).
+ * *got = bytes produced (short at end of file).  Returns -ENOENT when the file has no valid seek table (the caller
+ * falls back to fzg_decode_fd), a positive FZG_E_* status for a corrupt frame, -errno for I/O failures.
+ */
+int fzg_decode_range(int device, const void* src, size_t len, uint64_t offset, size_t size, void* dst, size_t* got);
+int fzg_decode_range_fd(int src_fd, uint64_t shard_key, uint64_t offset, size_t size, void* dst, size_t* got);
+/* host-only: parses the seek-table footer from the last bytes of a file (no GPU) */
+int fzg_seek_footer(const void* tail, size_t tail_len, uint64_t file_size, uint32_t* n_frames, uint64_t* table_bytes);
 
 const char* fzg_strerror(int code);
 

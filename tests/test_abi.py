@@ -57,3 +57,19 @@ def test_compute_fails_loudly_without_gpu(codec, golden):
     with pytest.raises(OSError) as e:
         codec.decode_batch([golden["json_2000_L3_writer"][0]])
     assert e.value.errno == 19   # ENODEV: no CPU fallback
+
+
+def test_seek_footer_parser_host_only():
+    """fzg_seek_footer (no GPU): the footer of the zstd seekable format -- Number_Of_Frames | descriptor | 0x8F92EAB1"""
+    import struct
+    import errno
+    import importlib
+    codec = importlib.import_module("fuse-zstd_b200.codec")
+    foot = struct.pack("<IBI", 5, 0, 0x8F92EAB1)
+    assert codec.seek_footer(foot, 1000) == (0, 5, 8 + 8 * 5 + 9)
+    assert codec.seek_footer(b"xxxx" + foot, 1000) == (0, 5, 57)                        # a longer tail is fine
+    assert codec.seek_footer(struct.pack("<IBI", 5, 0x80, 0x8F92EAB1), 1000) == (0, 5, 8 + 12 * 5 + 9)   # entries with checksums
+    assert codec.seek_footer(struct.pack("<IBI", 5, 0, 0x8F92EAB2), 1000)[0] == -errno.ENOENT          # wrong magic
+    assert codec.seek_footer(struct.pack("<IBI", 5, 0x04, 0x8F92EAB1), 1000)[0] == -errno.ENOENT       # reserved bits
+    assert codec.seek_footer(foot, 40)[0] == -errno.ENOENT                                # table larger than the file
+    assert codec.seek_footer(foot[:8], 1000)[0] == -errno.ENOENT

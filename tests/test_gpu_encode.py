@@ -146,3 +146,70 @@ def test_device_resident_encode(corpus):
     back = codec.decode_batch(comps, [size] * n)
     for i, (s, out) in enumerate(back):
         assert s == 0 and out == plain[i].tobytes(), i
+
+
+def test_seek_table_and_partial_reads(corpus, ref, oracle):
+    """FZG_SEEK_TABLE: the file ends in a skippable frame of the zstd seekable format.  Stock libzstd (driven as the
+    reference's reader drives it) and the oracle still decode the whole file; fzg_decode_range serves read(offset, size)
+    by decoding only the frames it touches (the reference's read path: src/main.rs:495-513)."""
+    import errno
+    rs = np.random.RandomState(3)
+    j = corpus.json_file(777, 5 << 20).tobytes()
+    plains = [j, j[:131072], j[:131073], j[:300], b"", rs.randint(0, 256, 400000, dtype=np.uint8).tobytes()]
+    res = codec.encode_batch(plains, flags=codec.SEEK_TABLE)
+    for plain, (st, comp) in zip(plains, res):
+        assert st == 0
+        nframes = max(1, (len(plain) + 131071) // 131072)
+        rc, nf, tb = codec.seek_footer(comp[-9:], len(comp))
+        assert (rc, nf, tb) == (0, nframes, 8 + 8 * nframes + 9)
+        if ref.available:
+            s, out = ref.copy_decode(comp, len(plain))
+            assert s == 0 and out == plain
+        s, out = oracle.decode(comp, cap=len(plain))
+        assert s == 0 and out == plain
+        (s, out), = codec.decode_batch([comp], [len(plain)])
+        assert s == 0 and out == plain
+        n = len(plain)
+        reads = [(0, 0), (0, 1), (0, n), (n, 10), (n + 5, 10), (max(n - 7, 0), 100), (131071, 2), (131072, 131072), (100000, 300000)]
+        reads += [(int(rs.randint(0, n + 1)), int(rs.randint(0, 400000))) for _ in range(12)]
+        for off, size in reads:
+            rc, got = codec.decode_range(comp, off, size)
+            assert rc == 0, (n, off, size, rc)
+            assert got == plain[off:off + size], (n, off, size)
+    # through a file descriptor: only the touched compressed bytes are read
+    with tempfile.TemporaryFile() as fh:
+        fh.write(res[0][1]); fh.flush()
+        for off, size in ((0, 4096), (1 << 20, 128 << 10), (5 * (1 << 20) - 100, 4096)):
+            rc, got = codec.decode_range_fd(fh.fileno(), off, size)
+            assert rc == 0 and got == plains[0][off:off + size]
+    with tempfile.TemporaryFile() as fh:                                   # the host mirror: seek table -> partial decode, else whole file
+        fh.write(res[0][1]); fh.flush()
+        assert stream.read_range(fh, 3 << 20, 1000) == plains[0][3 << 20:(3 << 20) + 1000]
+    with tempfile.TemporaryFile() as fh:
+        fh.write(codec.encode_batch([j[:300000]])[0][1]); fh.flush()
+        assert stream.read_range(fh, 250000, 100000) == j[250000:300000]
+    # a file without a seek table: the caller is told to fall back to a whole-file decode
+    (st, comp), = codec.encode_batch([j[:200000]])
+    assert st == 0 and codec.decode_range(comp, 10, 10)[0] == -errno.ENOENT
+    # a corrupted frame under a valid table is reported, not served
+    bad = bytearray(res[0][1]); bad[200000] ^= 0x55
+    rc, _ = codec.decode_range(bytes(bad), 0, 5 << 20)
+    assert rc > 0
+
+
+def test_many_files_single_pass_waves(corpus):
+    """more than one wave of chunks (8192 = 1 GiB of input): waves are cut at file boundaries, each sized and written in one pass"""
+    n, size = 300, 4 << 20
+    plain = corpus.json_files(4100000, n, size, threads=os.cpu_count())
+    import torch
+    d_src = torch.from_numpy(plain).cuda()
+    cap = codec.encode_bound(size)
+    d_dst = torch.zeros(n * cap, dtype=torch.uint8, device="cuda")
+    sp = [d_src.data_ptr() + i * size for i in range(n)]; dp = [d_dst.data_ptr() + i * cap for i in range(n)]
+    dl, st = codec.encode_batch_ptrs(0, sp, [size] * n, dp, [cap] * n, 3, 0, codec.SRC_DEVICE | codec.DST_DEVICE)
+    assert not st.any()
+    d_back = torch.zeros(n * size, dtype=torch.uint8, device="cuda")
+    bp = [d_back.data_ptr() + i * size for i in range(n)]
+    dl2, st2 = codec.decode_batch_ptrs(0, dp, dl, bp, [size] * n, codec.SRC_DEVICE | codec.DST_DEVICE)
+    assert not st2.any() and (dl2 == size).all()
+    assert torch.equal(d_back, d_src.reshape(-1))
