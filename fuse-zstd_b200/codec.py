@@ -14,7 +14,9 @@ SRC_DEVICE, DST_DEVICE, NO_VERIFY_CHECKSUM, PROFILE, SEEK_TABLE = 1, 2, 4, 8, 16
 
 EXPORTS = ["fzg_init", "fzg_shutdown", "fzg_device_count", "fzg_decode_fd", "fzg_encode_fd", "fzg_decode_batch",
            "fzg_encode_batch", "fzg_encode_bound", "fzg_frame_info", "fzg_strerror", "fzg_last_timing",
-           "fzg_stage_name", "fzg_stream", "fzg_decode_range", "fzg_decode_range_fd", "fzg_seek_footer"]
+           "fzg_stage_name", "fzg_stream", "fzg_decode_range", "fzg_decode_range_fd", "fzg_seek_footer",
+           "fzg_cache_configure", "fzg_cache_prefetch", "fzg_cache_prefetch_async", "fzg_cache_open", "fzg_cache_invalidate",
+           "fzg_cache_stats"]
 
 
 class Timing(C.Structure):
@@ -64,6 +66,16 @@ def lib():
         L.fzg_decode_range.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_uint64, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]
         L.fzg_decode_range_fd.restype = C.c_int
         L.fzg_decode_range_fd.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]
+        L.fzg_cache_configure.restype = C.c_int; L.fzg_cache_configure.argtypes = [C.c_size_t]
+        L.fzg_cache_prefetch.restype = C.c_int
+        L.fzg_cache_prefetch.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_size_t]
+        L.fzg_cache_prefetch_async.restype = C.c_int
+        L.fzg_cache_prefetch_async.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_size_t]
+        L.fzg_cache_open.restype = C.c_int
+        L.fzg_cache_open.argtypes = [C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+        L.fzg_cache_invalidate.restype = C.c_int; L.fzg_cache_invalidate.argtypes = [C.c_uint64]
+        L.fzg_cache_stats.restype = None
+        L.fzg_cache_stats.argtypes = [C.POINTER(C.c_uint64)] * 4
         L.fzg_seek_footer.restype = C.c_int
         L.fzg_seek_footer.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
         _lib = L
@@ -206,3 +218,35 @@ def decode_range_fd(fd, offset, size, shard_key=0):
     out = np.empty(max(size, 1), dtype=np.uint8); got = C.c_size_t(0)
     rc = lib().fzg_decode_range_fd(fd, shard_key, offset, size, out.ctypes.data, C.byref(got))
     return rc, out[:got.value].tobytes()
+
+
+# ---- batch formation + decoded-file cache
+def cache_configure(capacity_bytes):
+    return _check(lib().fzg_cache_configure(capacity_bytes), "fzg_cache_configure")
+
+
+def cache_prefetch(paths, keys, device=0, background=False):
+    """Decode the listed .zst files as one batch and keep the plain bytes, keyed by inode -> files added."""
+    n = len(paths)
+    p = (C.c_char_p * n)(*[os.fsencode(x) for x in paths]); k = (C.c_uint64 * n)(*keys)
+    f = lib().fzg_cache_prefetch_async if background else lib().fzg_cache_prefetch
+    return _check(f(device, p, k, n), "fzg_cache_prefetch")
+
+
+def cache_open(src_fd, dst_fd, key):
+    """open_wrapper's codec call with the cache in front -> (status, plain size, hit)."""
+    size, hit = C.c_uint64(0), C.c_int(0)
+    rc = lib().fzg_cache_open(src_fd, dst_fd, key, C.byref(size), C.byref(hit))
+    if rc < 0:
+        raise OSError(-rc, "fzg_cache_open: %s" % os.strerror(-rc))
+    return rc, size.value, bool(hit.value)
+
+
+def cache_invalidate(key):
+    return lib().fzg_cache_invalidate(key)
+
+
+def cache_stats():
+    v = [C.c_uint64(0) for _ in range(4)]
+    lib().fzg_cache_stats(*[C.byref(x) for x in v])
+    return dict(hits=v[0].value, misses=v[1].value, bytes=v[2].value, files=v[3].value)

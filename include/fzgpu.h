@@ -103,6 +103,21 @@ int fzg_decode_range_fd(int src_fd, uint64_t shard_key, uint64_t offset, size_t 
 /* host-only: parses the seek-table footer from the last bytes of a file (no GPU) */
 int fzg_seek_footer(const void* tail, size_t tail_len, uint64_t file_size, uint32_t* n_frames, uint64_t* table_bytes);
 
+/*
+ * Batch formation + decoded-file cache.  fuse-zstd decodes one file per open() on one thread
+ * (DESIGN.md:5-7 of the reference) and forgets the result with the last handle (src/file.rs:104-117); a GPU decodes ten
+ * thousand files in the time of one.  fzg_cache_prefetch decodes the listed .zst files (e.g. the siblings readdir_wrapper,
+ * src/main.rs:307-387, has just listed) as ONE batch and keeps the plain bytes, keyed by inode; fzg_cache_open is
+ * open_wrapper's codec call (src/main.rs:463-467) with that cache in front of fzg_decode_fd (an entry is served only
+ * while the source file still has the size and mtime it was decoded from).  LRU eviction above the configured capacity.
+ */
+int fzg_cache_configure(size_t capacity_bytes);   /* default 1 GiB; 0 disables prefetching */
+int fzg_cache_prefetch(int device, const char* const* paths, const uint64_t* keys, size_t n);        /* -> files added */
+int fzg_cache_prefetch_async(int device, const char* const* paths, const uint64_t* keys, size_t n);  /* detached thread */
+int fzg_cache_open(int src_fd, int dst_fd, uint64_t key, uint64_t* out_size, int* hit);
+int fzg_cache_invalidate(uint64_t key);           /* after store_to_source_file / rename / unlink */
+void fzg_cache_stats(uint64_t* hits, uint64_t* misses, uint64_t* bytes, uint64_t* files);
+
 const char* fzg_strerror(int code);
 
 /* ---- measurement hooks (bench.py); not part of the reference surface ---- */
