@@ -90,7 +90,6 @@ struct Block {
 //               history the block started with (see off_sym)
 // Sequence i therefore writes literals lit[LE(i-1) .. LE(i)) at E(i-1), then its match up to E(i):
 // every copy's source and destination are known without a serial scan.
-constexpr uint32_t kSpan = 256;                // bytes of output per span-index entry
 FZ_HD uint64_t rec_pack(uint32_t e, uint32_t le, uint32_t off) { return (uint64_t)e | ((uint64_t)le << 18) | ((uint64_t)off << 36); }
 FZ_HD uint32_t rec_e(uint64_t r) { return (uint32_t)r & 0x3FFFFu; }
 FZ_HD uint32_t rec_le(uint64_t r) { return (uint32_t)(r >> 18) & 0x3FFFFu; }
@@ -585,58 +584,11 @@ FZ_HD int locate_table(const Block& b, int which, const uint8_t*& p, uint32_t& n
     return bad ? -1 : res;
 }
 
-// Builds table `which` for block b (resolving Repeat through b.*_src).  used = description bytes
-// consumed in b itself (0 for Predefined / Repeat).  `scratch` = 128 uint16 (normalised counts, then
-// per-symbol counters) in shared memory: nothing on this path touches local memory.  Returns 0 or -1.
-FZ_HD int build_seq_table(const Block* blocks, const Block& b, int which, const uint8_t* p, uint32_t n,
-                          const SeqConsts& K, uint32_t* table, int& log, uint32_t& used, uint16_t* scratch)
-{
-    int16_t* norm = (int16_t*)scratch; uint16_t* cnt = scratch + 64;
-    int mode = (b.modes >> (6 - 2 * which)) & 3;
-    const int max_sym = which == 0 ? kMaxLL : (which == 1 ? kMaxOF : kMaxML);
-    const int max_log = which == 0 ? kLLLog : (which == 1 ? kOFLog : kMLLog);
-    const uint8_t* extra = which == 0 ? K.ll_bits : (which == 2 ? K.ml_bits : nullptr);
-    const bool own = mode != 3;          // description bytes live in this block
-    used = 0;
-    if (!own) {
-        int32_t src = which == 0 ? b.ll_src : (which == 1 ? b.of_src : b.ml_src);
-        if (src < 0) return -1;
-        mode = locate_table(blocks[src], which, p, n);
-        if (mode < 0 || mode == 3) return -1;
-    }
-    if (mode == 0) {
-        const int16_t* def = which == 0 ? K.ll_def : (which == 1 ? K.of_def : K.ml_def);
-        log = which == 1 ? 5 : 6;
-        return build_fse_table(table, def, which == 0 ? 36 : (which == 1 ? 29 : 53), log, extra, cnt);
-    }
-    if (mode == 1) {
-        if (n < 1 || p[0] > max_sym) return -1;
-        uint32_t s = p[0];
-        table[0] = cell_pack(0, 0, extra ? extra[s] : s, s); log = 0;
-        if (own) used = 1;
-        return 0;
-    }
-    int ns;
-    int u = read_ncount(p, n, max_sym, max_log, norm, ns, log);
-    if (u < 0) return -1;
-    if (own) used = (uint32_t)u;
-    return build_fse_table(table, norm, ns, log, extra, cnt);
-}
-
 // ------------------------------------------------------------------ sequence bitstream reader
 // The sequence pass is one serial dependency chain per block and the lanes of a warp run different
 // blocks in lockstep, so the reader must neither wait for HBM nor branch.  The backward bitstream is
 // mirrored into a 256-byte shared-memory ring (ring byte = global address & 255) by cp.async, 16 bytes
-// at a time and ~240 bytes ahead of use; the consumer takes 32-bit words from the ring with one LDS
-// and serves bits from a top-aligned 64-bit container (hi:lo).
-FZ_HD void ring_fetch(uint8_t* ring_slot, const uint8_t* gsrc)        // one aligned 16-byte chunk -> ring
-{
-#ifdef __CUDA_ARCH__
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(ring_slot)), "l"(gsrc) : "memory");
-#else
-    for (int i = 0; i < 16; i++) ring_slot[i] = gsrc[i];
-#endif
-}
+// at a time and ~240 bytes ahead of use; the consumer addresses the ring with a bit cursor (SeqCursor).
 FZ_HD void ring_commit()
 {
 #ifdef __CUDA_ARCH__
@@ -795,35 +747,6 @@ constexpr uint32_t kChainCellBytes = (kChainCellsLL + kChainCellsML + kChainCell
 constexpr uint32_t kChainBytes = kChainCellBytes + 256;
 
 FZ_HD uint32_t chain_pack(uint32_t base, uint32_t nb, uint32_t extra) { return ((((base >> nb) << 1) | 1u) << nb) | (extra << 10); }
-FZ_HD uint32_t ctz32(uint32_t v)
-{
-#ifdef __CUDA_ARCH__
-    return (uint32_t)__ffs((int)v) - 1u;
-#else
-    return (uint32_t)__builtin_ctz(v);
-#endif
-}
-
-// RFC 8878 4.1.1 symbol spread: tab[cell] = symbol for all 1 << log cells; cnt[s] = first `next` value of symbol s
-// (cnt may be nullptr).  Returns 0 or -1.
-template <class T>
-FZ_HD int fse_spread(T* tab, const int16_t* norm, int n_sym, int log, uint16_t* cnt)
-{
-    const int size = 1 << log; int high = size - 1;
-    for (int s = 0; s < n_sym; s++) {
-        if (norm[s] == -1) { tab[high--] = (T)s; if (cnt) cnt[s] = 1; }
-        else if (cnt) cnt[s] = (uint16_t)norm[s];
-    }
-    const int step = (size >> 1) + (size >> 3) + 3, mask = size - 1; int pos = 0;
-    for (int s = 0; s < n_sym; s++) {
-        for (int i = 0; i < norm[s]; i++) {
-            tab[pos] = (T)s;
-            do { pos = (pos + step) & mask; } while (pos > high);
-        }
-    }
-    return pos == 0 ? 0 : -1;
-}
-
 // Where table `which` (0 LL, 1 OF, 2 ML) of block b is described (its own sequences section, or -- Repeat mode --
 // the section of the block recorded in b.*_src) and how.  p / n on entry: the current position in b's section.
 struct TableSrc { int mode; const uint8_t* p; uint32_t n; bool own; };
@@ -841,23 +764,6 @@ FZ_HD int resolve_table(const Block* blocks, const Block& b, int which, const ui
     }
     return rc;
 }
-// Normalised counts of a Predefined / FSE_Compressed table.  norm_buf: 64 int16 of scratch.  used = description bytes.
-FZ_HD int table_norm(const TableSrc& t, int which, const SeqConsts& K, int16_t* norm_buf, const int16_t*& norm, int& ns, int& log, uint32_t& used)
-{
-    used = 0;
-    if (t.mode == 0) {
-        norm = which == 0 ? K.ll_def : (which == 1 ? K.of_def : K.ml_def);
-        ns = which == 0 ? 36 : (which == 1 ? 29 : 53); log = which == 1 ? 5 : 6;
-        return 0;
-    }
-    const int max_sym = which == 0 ? kMaxLL : (which == 1 ? kMaxOF : kMaxML);
-    const int max_log = which == 0 ? kLLLog : (which == 1 ? kOFLog : kMLLog);
-    const int u = read_ncount(t.p, t.n, max_sym, max_log, norm_buf, ns, log);
-    if (u < 0) return -1;
-    norm = norm_buf; used = (uint32_t)u;
-    return 0;
-}
-
 // Per-thread work arrays of the table stage, element i of thread t at base[i * stride + t]: in shared memory the 32 lanes
 // of a warp then touch consecutive bytes (no bank conflicts) although each builds a different table.
 template <class T> struct Lanewise {
