@@ -15,7 +15,7 @@ SRC_DEVICE, DST_DEVICE, NO_VERIFY_CHECKSUM, PROFILE, SEEK_TABLE = 1, 2, 4, 8, 16
 EXPORTS = ["fzg_init", "fzg_shutdown", "fzg_device_count", "fzg_decode_fd", "fzg_encode_fd", "fzg_decode_batch",
            "fzg_encode_batch", "fzg_encode_bound", "fzg_frame_info", "fzg_strerror", "fzg_last_timing",
            "fzg_stage_name", "fzg_stream", "fzg_decode_range", "fzg_decode_range_fd", "fzg_seek_footer",
-           "fzg_cache_configure", "fzg_cache_prefetch", "fzg_cache_prefetch_async", "fzg_cache_open", "fzg_cache_invalidate",
+           "fzg_cache_configure", "fzg_cache_reserve", "fzg_cache_prefetch", "fzg_cache_prefetch_async", "fzg_cache_open", "fzg_cache_invalidate",
            "fzg_cache_stats"]
 
 
@@ -67,6 +67,7 @@ def lib():
         L.fzg_decode_range_fd.restype = C.c_int
         L.fzg_decode_range_fd.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]
         L.fzg_cache_configure.restype = C.c_int; L.fzg_cache_configure.argtypes = [C.c_size_t]
+        L.fzg_cache_reserve.restype = C.c_int; L.fzg_cache_reserve.argtypes = []
         L.fzg_cache_prefetch.restype = C.c_int
         L.fzg_cache_prefetch.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_size_t]
         L.fzg_cache_prefetch_async.restype = C.c_int
@@ -223,6 +224,10 @@ def decode_range_fd(fd, offset, size, shard_key=0):
 # ---- batch formation + decoded-file cache
 def cache_configure(capacity_bytes):
     return _check(lib().fzg_cache_configure(capacity_bytes), "fzg_cache_configure")
+
+
+def cache_reserve():
+    return _check(lib().fzg_cache_reserve(), "fzg_cache_reserve")
 
 
 def cache_prefetch(paths, keys, device=0, background=False):

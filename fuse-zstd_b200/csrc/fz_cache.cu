@@ -8,73 +8,98 @@
  * src/main.rs:307-387, lookup_wrapper :215-305) the host hands the sibling .zst paths to fzg_cache_prefetch, which decodes
  * all of them in ONE fzg_decode_batch call and keeps the plain bytes; open_wrapper then calls fzg_cache_open, which is a
  * memcpy + write when the file is cached (and still the file that was decoded: size + mtime are compared) and an
- * ordinary fzg_decode_fd otherwise.  Entries leave in LRU order when the capacity is exceeded, or by
+ * ordinary fzg_decode_fd otherwise.  The plain bytes live in pinned slabs that are filled batch after batch and reused
+ * oldest-first once the capacity is reached (everything in the reused slab leaves together); single entries leave by
  * fzg_cache_invalidate after a write / rename / unlink (store_to_source_file, src/main.rs:755-832).
  */
+#include <cuda_runtime.h>
 #include <errno.h>
 #include <fcntl.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <condition_variable>
 #include <list>
 #include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/fzgpu.h"
 
 namespace {
 
-struct Bytes {                                      // plain bytes, NOT zero-filled on allocation (a vector would memset them first)
-    std::unique_ptr<uint8_t[]> p; size_t n = 0;
-    void alloc(size_t k) { p.reset(new uint8_t[k ? k : 1]); n = k; }
-    uint8_t* data() const { return p.get(); }
-    size_t size() const { return n; }
+// Plain bytes live in PINNED slabs (cudaMallocHost is slow -- ~0.4 ms per MiB -- so slabs are allocated once, up to the
+// capacity, and then reused oldest-first): a batch's results are contiguous in one slab, so its device -> host copy is one DMA
+// at PCIe speed instead of a staged copy per file into freshly faulted pageable memory, which made the host side of a batch
+// ten times longer than its kernels.
+constexpr size_t kSlabBytes = (size_t)256 << 20;
+struct Slab {
+    uint8_t* p = nullptr; size_t cap = 0, used = 0;
+    std::vector<uint64_t> keys;                      // entries that live here (stale keys are harmless: see evict_slab)
 };
 struct Entry {
-    Bytes plain;
-    uint64_t src_size; int64_t mtime_ns;           // the source file the bytes were decoded from
-    std::list<uint64_t>::iterator lru;
+    int slab = 0; size_t off = 0, n = 0; uint64_t id = 0;
+    uint64_t src_size; int64_t mtime_ns;            // the source file the bytes were decoded from
 };
 
 std::mutex g_mu;
+std::condition_variable g_cv;
+std::unordered_set<uint64_t> g_pending;            // keys of the batches in flight: an open of one of them waits for its batch
 std::unordered_map<uint64_t, Entry> g_map;         // key = fuse-zstd inode (src/main.rs:744-753)
-std::list<uint64_t> g_lru;                         // front = most recently used
+std::vector<Slab> g_slabs;
+int g_cur = -1;                                    // slab being filled
 size_t g_capacity = (size_t)1 << 30, g_bytes = 0;
-uint64_t g_hits = 0, g_misses = 0, g_prefetched = 0;
+uint64_t g_hits = 0, g_misses = 0, g_prefetched = 0, g_next_id = 1;
+
+std::mutex g_batch_mu;                             // one prefetch batch at a time (they share the compressed-input arena)
+uint8_t* g_arena = nullptr; size_t g_arena_cap = 0;   // pinned, grow-only: the compressed files of the batch being formed
+
+void evict_slab_locked(int si)
+{
+    Slab& sl = g_slabs[si];
+    for (uint64_t k : sl.keys) { auto it = g_map.find(k); if (it != g_map.end() && it->second.slab == si) { g_bytes -= it->second.n; g_map.erase(it); } }
+    sl.keys.clear(); sl.used = 0;
+}
+void drop_all_locked()
+{
+    for (Slab& sl : g_slabs) if (sl.p) cudaFreeHost(sl.p);
+    g_slabs.clear(); g_map.clear(); g_cur = -1; g_bytes = 0;
+}
+// `need` contiguous pinned bytes for one batch: the current slab, a new slab while the capacity allows, else the oldest slab
+// (whose entries leave).  Returns the slab index or -1.
+int alloc_locked(size_t need, size_t* off)
+{
+    if (g_cur >= 0 && g_slabs[g_cur].used + need <= g_slabs[g_cur].cap) { *off = g_slabs[g_cur].used; g_slabs[g_cur].used += need; return g_cur; }
+    size_t total = 0;
+    for (const Slab& sl : g_slabs) total += sl.cap;
+    const size_t want = need > kSlabBytes ? need : (g_capacity < kSlabBytes ? (need > g_capacity ? need : g_capacity) : kSlabBytes);
+    for (size_t t = 1; t < g_slabs.size(); t++) {                  // a reserved slab that has not been used yet
+        const int c = (int)((g_cur + t) % g_slabs.size());
+        if (g_slabs[c].used == 0 && g_slabs[c].keys.empty() && g_slabs[c].cap >= need) { g_cur = c; *off = 0; g_slabs[c].used = need; return c; }
+    }
+    if (g_slabs.empty() || total + want <= g_capacity) {
+        Slab sl;
+        if (cudaMallocHost((void**)&sl.p, want) != cudaSuccess) { cudaGetLastError(); return -1; }
+        sl.cap = want; g_slabs.push_back(std::move(sl)); g_cur = (int)g_slabs.size() - 1;
+    } else {
+        int next = -1;
+        for (size_t t = 1; t <= g_slabs.size(); t++) { const int c = (int)((g_cur + t) % g_slabs.size()); if (g_slabs[c].cap >= need) { next = c; break; } }
+        if (next < 0) return -1;
+        g_cur = next; evict_slab_locked(g_cur);
+    }
+    *off = 0; g_slabs[g_cur].used = need;
+    return g_cur;
+}
 
 int64_t mtime_ns(const struct stat& st) { return (int64_t)st.st_mtim.tv_sec * 1000000000ll + st.st_mtim.tv_nsec; }
-
-void evict_locked(size_t need)
-{
-    while (!g_lru.empty() && g_bytes + need > g_capacity) {
-        const uint64_t k = g_lru.back(); g_lru.pop_back();
-        auto it = g_map.find(k);
-        if (it != g_map.end()) { g_bytes -= it->second.plain.size(); g_map.erase(it); }
-    }
-}
-
-int read_file(const char* path, std::vector<uint8_t>& buf, struct stat& st)
-{
-    const int fd = open(path, O_RDONLY | O_CLOEXEC);
-    if (fd < 0) return -errno;
-    if (fstat(fd, &st) != 0) { const int e = -errno; close(fd); return e; }
-    buf.resize((size_t)st.st_size);
-    size_t got = 0;
-    while (got < buf.size()) {
-        const ssize_t r = read(fd, buf.data() + got, buf.size() - got);
-        if (r < 0) { if (errno == EINTR) continue; const int e = -errno; close(fd); return e; }
-        if (r == 0) break;
-        got += (size_t)r;
-    }
-    close(fd);
-    buf.resize(got);
-    return 0;
-}
 
 int write_all(int fd, const uint8_t* p, size_t n)
 {
@@ -90,10 +115,28 @@ int write_all(int fd, const uint8_t* p, size_t n)
 
 extern "C" int fzg_cache_configure(size_t capacity_bytes)
 {
+    std::lock_guard<std::mutex> batch(g_batch_mu);
     std::lock_guard<std::mutex> lk(g_mu);
+    if (capacity_bytes != g_capacity) drop_all_locked();          // the slabs are sized for a capacity: a new one starts empty
     g_capacity = capacity_bytes;
-    evict_locked(0);
     return 0;
+}
+
+// Allocates the pinned slabs up to the configured capacity now (cudaMallocHost costs ~1 ms per MiB on this box: a mount does
+// it once at start instead of inside its first batches).  Returns the number of slabs, or -errno.
+extern "C" int fzg_cache_reserve(void)
+{
+    std::lock_guard<std::mutex> batch(g_batch_mu);
+    std::lock_guard<std::mutex> lk(g_mu);
+    size_t total = 0;
+    for (const Slab& sl : g_slabs) total += sl.cap;
+    while (total + kSlabBytes <= g_capacity) {
+        Slab sl;
+        if (cudaMallocHost((void**)&sl.p, kSlabBytes) != cudaSuccess) { cudaGetLastError(); return -ENOMEM; }
+        sl.cap = kSlabBytes; total += kSlabBytes; g_slabs.push_back(std::move(sl));
+    }
+    if (g_cur < 0 && !g_slabs.empty()) g_cur = 0;
+    return (int)g_slabs.size();
 }
 
 // Decodes the listed .zst files that are not cached yet as ONE batch on `device` and keeps the results.  Files that
@@ -102,45 +145,74 @@ extern "C" int fzg_cache_configure(size_t capacity_bytes)
 extern "C" int fzg_cache_prefetch(int device, const char* const* paths, const uint64_t* keys, size_t n)
 {
     if (!paths || !keys) return -EINVAL;
+    std::lock_guard<std::mutex> batch(g_batch_mu);
     std::vector<size_t> todo;
     {
         std::lock_guard<std::mutex> lk(g_mu);
         if (g_capacity == 0) return 0;
-        for (size_t i = 0; i < n; i++) if (!g_map.count(keys[i])) todo.push_back(i);
+        for (size_t i = 0; i < n; i++) if (!g_map.count(keys[i]) && g_pending.insert(keys[i]).second) todo.push_back(i);
     }
     if (todo.empty()) return 0;
+    struct Done {                                      // whatever happens, the keys stop being pending and waiters wake up
+        const std::vector<size_t>& todo; const uint64_t* keys;
+        ~Done() { { std::lock_guard<std::mutex> lk(g_mu); for (size_t i : todo) g_pending.erase(keys[i]); } g_cv.notify_all(); }
+    } done{ todo, keys };
+    static const bool trace = getenv("FZG_TRACE") != nullptr;
+    struct timespec t0; clock_gettime(CLOCK_MONOTONIC, &t0);
+    auto ms = [&]() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (t.tv_sec - t0.tv_sec) * 1e3 + (t.tv_nsec - t0.tv_nsec) * 1e-6; };
     const size_t m = todo.size();
-    std::vector<std::vector<uint8_t>> comp(m); std::vector<Bytes> plain(m);
-    std::vector<struct stat> sts(m);
-    std::vector<const void*> sp; std::vector<void*> dp; std::vector<size_t> sl, dc, which;
-    size_t budget = 0;
+    // ---- the compressed files, one after the other in the pinned arena (the batch is then ONE host -> device copy)
+    std::vector<struct stat> sts(m); std::vector<int> fds(m, -1); std::vector<size_t> coff(m, 0), clen(m, 0);
+    size_t ctotal = 0;
     for (size_t j = 0; j < m; j++) {
-        if (read_file(paths[todo[j]], comp[j], sts[j]) != 0 || comp[j].empty()) continue;
+        fds[j] = open(paths[todo[j]], O_RDONLY | O_CLOEXEC);
+        if (fds[j] < 0 || fstat(fds[j], &sts[j]) != 0 || sts[j].st_size == 0) { if (fds[j] >= 0) close(fds[j]); fds[j] = -1; continue; }
+        coff[j] = ctotal; clen[j] = (size_t)sts[j].st_size; ctotal += (clen[j] + 15 & ~(size_t)15) + 16;
+    }
+    if (ctotal + 64 > g_arena_cap) {
+        if (g_arena) cudaFreeHost(g_arena);
+        g_arena = nullptr; g_arena_cap = 0;
+        const size_t want = ctotal + ctotal / 4 + (1 << 20);
+        if (cudaMallocHost((void**)&g_arena, want) != cudaSuccess) { cudaGetLastError(); g_arena = nullptr; for (int fd : fds) if (fd >= 0) close(fd); return -ENOMEM; }
+        g_arena_cap = want;
+    }
+    for (size_t j = 0; j < m; j++) {
+        if (fds[j] < 0) continue;
+        size_t got = 0;
+        while (got < clen[j]) { const ssize_t r = read(fds[j], g_arena + coff[j] + got, clen[j] - got); if (r < 0 && errno == EINTR) continue; if (r <= 0) break; got += (size_t)r; }
+        close(fds[j]);
+        if (got != clen[j]) fds[j] = -1;
+    }
+    // ---- sizes from the frame headers; the results are contiguous in one pinned slab (ONE device -> host copy)
+    std::vector<const void*> sp; std::vector<void*> dp; std::vector<size_t> sl, dc, which, doff;
+    size_t dtotal = 0;
+    for (size_t j = 0; j < m; j++) {
+        if (fds[j] < 0) continue;
         uint64_t content = 0, csize = 0;
-        if (fzg_frame_info(comp[j].data(), comp[j].size(), &content, &csize) != 0 || content == UINT64_MAX) continue;   // unknown size: left to open()
-        if (budget + content > g_capacity) break;              // a prefetch never evicts more than the cache holds
-        budget += content;
-        plain[j].alloc(content);
-        sp.push_back(comp[j].data()); sl.push_back(comp[j].size()); dp.push_back(plain[j].data()); dc.push_back(content); which.push_back(j);
+        if (fzg_frame_info(g_arena + coff[j], clen[j], &content, &csize) != 0 || content == UINT64_MAX) continue;   // unknown size: left to open()
+        if (dtotal + content > g_capacity) break;              // a prefetch never asks for more than the cache holds
+        which.push_back(j); doff.push_back(dtotal); dc.push_back(content); dtotal += content;
     }
     const size_t k = which.size();
     if (k == 0) return 0;
+    int si; size_t base = 0; uint8_t* slab_p;
+    { std::lock_guard<std::mutex> lk(g_mu); si = alloc_locked(dtotal, &base); if (si < 0) return -ENOMEM; slab_p = g_slabs[si].p; }
+    for (size_t a = 0; a < k; a++) { sp.push_back(g_arena + coff[which[a]]); sl.push_back(clen[which[a]]); dp.push_back(slab_p + base + doff[a]); }
     std::vector<size_t> dl(k); std::vector<int> st(k);
+    const double t_read = ms();
     const int rc = fzg_decode_batch(device, k, sp.data(), sl.data(), dp.data(), dc.data(), dl.data(), st.data(), 0);
     if (rc) return rc;
+    if (trace) fprintf(stderr, "fzgpu: prefetch of %zu files: read + size + alloc %.1f ms, decode batch %.1f ms\n", k, t_read, ms() - t_read);
     int added = 0;
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::mutex> lk(g_mu);
     for (size_t a = 0; a < k; a++) {
         if (st[a] != 0) continue;
         const size_t j = which[a]; const uint64_t key = keys[todo[j]];
-        if (g_map.count(key)) continue;
-        plain[j].n = dl[a];
-        evict_locked(plain[j].size());
-        if (g_bytes + plain[j].size() > g_capacity) continue;
-        g_lru.push_front(key);
-        Entry e; e.plain = std::move(plain[j]); e.src_size = (uint64_t)sts[j].st_size; e.mtime_ns = mtime_ns(sts[j]); e.lru = g_lru.begin();
-        g_bytes += e.plain.size();
-        g_map.emplace(key, std::move(e));
+        if (g_map.count(key) || si >= (int)g_slabs.size()) continue;
+        Entry e; e.slab = si; e.off = base + doff[a]; e.n = dl[a]; e.id = g_next_id++; e.src_size = (uint64_t)sts[j].st_size; e.mtime_ns = mtime_ns(sts[j]);
+        g_bytes += e.n;
+        g_slabs[si].keys.push_back(key);
+        g_map.emplace(key, e);
         added++; g_prefetched++;
     }
     return added;
@@ -169,12 +241,12 @@ extern "C" int fzg_cache_open(int src_fd, int dst_fd, uint64_t key, uint64_t* ou
     if (fstat(src_fd, &st) != 0) return -errno;
     {
         std::unique_lock<std::mutex> lk(g_mu);
+        g_cv.wait(lk, [&] { return !g_pending.count(key); });      // its batch is in flight: waiting costs less than a decode of its own
         auto it = g_map.find(key);
         if (it != g_map.end() && it->second.src_size == (uint64_t)st.st_size && it->second.mtime_ns == mtime_ns(st)) {
-            g_lru.erase(it->second.lru); g_lru.push_front(key); it->second.lru = g_lru.begin();
             g_hits++;
-            const size_t sz = it->second.plain.size();
-            const int rc = write_all(dst_fd, it->second.plain.data(), sz);      // under the lock: the entry cannot be evicted meanwhile
+            const size_t sz = it->second.n;
+            const int rc = write_all(dst_fd, g_slabs[it->second.slab].p + it->second.off, sz);   // under the lock: its slab cannot be reused meanwhile
             lk.unlock();
             if (rc) return rc;
             if (lseek(src_fd, 0, SEEK_END) < 0) return -errno;  // copy_decode leaves the source at its end
@@ -182,7 +254,7 @@ extern "C" int fzg_cache_open(int src_fd, int dst_fd, uint64_t key, uint64_t* ou
             if (hit) *hit = 1;
             return 0;
         }
-        if (it != g_map.end()) { g_bytes -= it->second.plain.size(); g_lru.erase(it->second.lru); g_map.erase(it); }   // stale
+        if (it != g_map.end()) { g_bytes -= it->second.n; g_map.erase(it); }   // stale
         g_misses++;
     }
     if (hit) *hit = 0;
@@ -194,7 +266,7 @@ extern "C" int fzg_cache_invalidate(uint64_t key)
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_map.find(key);
     if (it == g_map.end()) return 0;
-    g_bytes -= it->second.plain.size(); g_lru.erase(it->second.lru); g_map.erase(it);
+    g_bytes -= it->second.n; g_map.erase(it);
     return 1;
 }
 

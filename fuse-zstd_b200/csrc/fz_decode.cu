@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kTabThreads) k_seq_tables(Block* blocks, const
 #endif
 constexpr int kSeqStreams = FZ_SEQ_STREAMS;
 #ifndef FZ_SEQ_LANES
-#define FZ_SEQ_LANES 32
+#define FZ_SEQ_LANES 21
 #endif
 constexpr int kSeqLanes = FZ_SEQ_LANES;
 constexpr int kSeqWarps = (kSeqStreams + kSeqLanes - 1) / kSeqLanes;
@@ -227,7 +227,10 @@ __device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v, uint32_t lane)
     return v;
 }
 
-constexpr int kRecWarps = 8;
+#ifndef FZ_REC_WARPS
+#define FZ_REC_WARPS 8
+#endif
+constexpr int kRecWarps = FZ_REC_WARPS;
 __global__ void __launch_bounds__(kRecWarps * 32) k_records(Block* blocks, const Frame* frames, const uint32_t* jobs, uint32_t n_jobs,
                                                             uint64_t* seqs, const uint8_t* tabs, const SeqJobHdr* hdrs)
 {
@@ -376,7 +379,7 @@ __global__ void k_offsets(const Item* items, const ItemInfo* infos, const ItemBa
 constexpr int kExecWarps = FZ_EXEC_WARPS;                    // warps (= frames in flight) per CTA
 constexpr int kExecCtasPerSm = FZ_EXEC_CTAS;
 #ifndef FZ_EXEC_STAGE
-#define FZ_EXEC_STAGE 1024
+#define FZ_EXEC_STAGE 512
 #endif
 constexpr uint32_t kStage = FZ_EXEC_STAGE;                            // bytes of round output a warp assembles in shared memory
 constexpr uint32_t kStageBytes = kStage + 48;                // + alignment slack (the stage mirrors the low 4 address bits) + load slack

@@ -1,0 +1,620 @@
+/*
+ * fzfs.cpp -- a raw-/dev/fuse host that restates fuse-zstd's filesystem surface in C++ so that the
+ * GPU codec can be exercised and measured THROUGH A MOUNT in an environment without Rust, libfuse or fio.
+ *
+ * What it restates (paths relative to /root/reference):
+ *   the Filesystem callbacks            src/main.rs:835-1207    -> Fs::dispatch (one thread, one request at a time, as fuser does)
+ *   lookup / readdir / getattr          src/main.rs:215-405     `.zst` suffix added / stripped, other regular files hidden,
+ *                                                               size = xattr user.real_size (8-byte BE), perms 0666 / 0777
+ *   open (decode on first open)         src/main.rs:451-493     unlinked tmpfile, codec call, user.real_size written, fsync;
+ *                                                               a file that is already open is dup'ed, not decoded again
+ *   read / write / truncate             src/main.rs:495-513, 558-593, 408-449
+ *   flush / fsync / release (encode)    src/main.rs:174-213, 755-832   temp file in the target directory, codec call,
+ *                                                               user.ino kept, atomic rename, user.real_size, fsync
+ *   create / mkdir / unlink / rmdir / rename   src/main.rs:515-555, 601-707
+ *   handle table                        src/file.rs             fh -> {flags, needs_sync, tmpfile, refs}; unlink clears refs
+ *   inode numbers                       src/main.rs:719-753     own counter counting down from 2^64-1, kept in the xattr user.ino
+ *                                                               of every entry (an in-memory map when the data directory's
+ *                                                               filesystem has no user xattrs)
+ * What it does not restate: the sled inode cache (a hash map here), --convert mode, logging / Sentry, the CLI beyond the
+ * three options the tests use.
+ *
+ * The codec sits behind four C functions (fzfs_codec.h): the product binary links fzfs_codec_gpu.cpp (libfzgpu.so: cached /
+ * batched decode, GPU encode, directory readahead), the measurement baseline links oracle/fzfs_codec_ref.c (the reference's
+ * libzstd calls, test infrastructure).  There is no fallback from one to the other.
+ */
+#include <dirent.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <linux/fuse.h>
+#include <signal.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mount.h>
+#include <sys/stat.h>
+#include <sys/statvfs.h>
+#include <sys/uio.h>
+#include <sys/xattr.h>
+#include <unistd.h>
+
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "fzfs_codec.h"
+
+namespace {
+
+constexpr uint64_t kTtlSec = 1;                 // dcache lifetime (src/main.rs:25)
+bool g_verbose = false;
+void logf(const char* fmt, ...)
+{
+    if (!g_verbose) return;
+    va_list ap; va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap); fputc('\n', stderr);
+}
+
+bool ends_with(const std::string& s, const char* suf) { const size_t n = strlen(suf); return s.size() >= n && s.compare(s.size() - n, n, suf) == 0; }
+std::string dir_of(const std::string& p) { const size_t k = p.rfind('/'); return k == std::string::npos ? "." : p.substr(0, k); }
+
+uint64_t be64(const uint8_t* b) { uint64_t v = 0; for (int i = 0; i < 8; i++) v = (v << 8) | b[i]; return v; }
+void put_be64(uint8_t* b, uint64_t v) { for (int i = 7; i >= 0; i--) { b[i] = (uint8_t)v; v >>= 8; } }
+
+// Sum of Frame_Content_Size over the frames of a .zst file, by walking frame and block headers with pread (no decoding):
+// used when user.real_size is absent, so that a file does not look empty before its first open (README.md:20-23 of the
+// reference lists that as a limitation).  Returns false when a frame omits the field or the file is malformed.
+bool content_size_from_headers(int fd, uint64_t* out)
+{
+    struct stat st;
+    if (fstat(fd, &st) != 0) return false;
+    const uint64_t n = (uint64_t)st.st_size;
+    uint64_t ip = 0, total = 0;
+    uint8_t h[18];
+    while (ip < n) {
+        const ssize_t got = pread(fd, h, sizeof h, (off_t)ip);
+        if (got < 8) return false;
+        const uint32_t magic = h[0] | (h[1] << 8) | (h[2] << 16) | ((uint32_t)h[3] << 24);
+        if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) { ip += 8 + (uint64_t)(h[4] | (h[5] << 8) | (h[6] << 16) | ((uint32_t)h[7] << 24)); continue; }
+        if (magic != 0xFD2FB528u) return false;
+        const uint32_t fhd = h[4], fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, did = fhd & 3;
+        uint32_t pos = 5 + (single ? 0 : 1) + (did == 3 ? 4 : did);
+        const uint32_t fb = fcs_flag == 0 ? single : (fcs_flag == 1 ? 2 : (fcs_flag == 2 ? 4 : 8));
+        if (fb == 0 || (ssize_t)(pos + fb) > got) return false;
+        uint64_t fcs = 0;
+        for (uint32_t i = 0; i < fb; i++) fcs |= (uint64_t)h[pos + i] << (8 * i);
+        if (fb == 2) fcs += 256;
+        total += fcs; ip += pos + fb;
+        for (;;) {                                               // block headers
+            uint8_t b[3];
+            if (pread(fd, b, 3, (off_t)ip) != 3) return false;
+            const uint32_t bh = b[0] | (b[1] << 8) | (b[2] << 16), type = (bh >> 1) & 3, size = bh >> 3;
+            ip += 3 + (type == 1 ? 1 : size);
+            if (bh & 1) break;
+        }
+        if (fhd & 4) ip += 4;
+    }
+    *out = total;
+    return ip == n;
+}
+
+struct Handle { int flags; bool needs_sync; int fd; bool has_refs; uint64_t ino; std::string path; };
+
+class Fs {
+public:
+    Fs(std::string data_dir, int level, bool readahead) : data_(std::move(data_dir)), level_(level), readahead_(readahead)
+    {
+        uint8_t b[8];
+        if (getxattr(data_.c_str(), "user.ino_idx", b, 8) == 8) ino_idx_ = be64(b);
+    }
+    int dev = -1;
+    void loop();
+
+private:
+    std::string data_; int level_; bool readahead_;
+    uint64_t ino_idx_ = UINT64_MAX;
+    bool xattr_ok_ = true;
+    std::unordered_map<uint64_t, std::string> paths_;            // ino -> path in the data directory (the reference: sled)
+    std::unordered_map<std::string, uint64_t> mem_ino_;          // path -> ino when user xattrs are not available
+    std::unordered_map<std::string, uint64_t> mem_size_;         // path -> real size, same case
+    std::unordered_map<uint64_t, Handle> handles_;
+    std::unordered_map<uint64_t, std::unordered_set<uint64_t>> by_ino_;
+    std::unordered_set<std::string> prefetched_dirs_;
+
+    // ---- inode numbers (src/main.rs:719-753)
+    uint64_t next_ino()
+    {
+        const uint64_t r = ino_idx_;
+        if (ino_idx_ - 1 <= FUSE_ROOT_ID) ino_idx_ = UINT64_MAX;
+        ino_idx_--;
+        uint8_t b[8]; put_be64(b, ino_idx_);
+        if (xattr_ok_ && setxattr(data_.c_str(), "user.ino_idx", b, 8, 0) != 0 && (errno == ENOTSUP || errno == EPERM)) xattr_ok_ = false;
+        return r;
+    }
+    uint64_t ino_of(const std::string& path)
+    {
+        uint8_t b[8];
+        if (xattr_ok_) {
+            if (getxattr(path.c_str(), "user.ino", b, 8) == 8) return be64(b);
+            if (errno == ENOTSUP) xattr_ok_ = false;
+        }
+        if (!xattr_ok_) { auto it = mem_ino_.find(path); if (it != mem_ino_.end()) return it->second; }
+        const uint64_t ino = next_ino();
+        put_be64(b, ino);
+        if (!xattr_ok_ || setxattr(path.c_str(), "user.ino", b, 8, 0) != 0) { if (xattr_ok_ && errno == ENOTSUP) xattr_ok_ = false; mem_ino_[path] = ino; }
+        return ino;
+    }
+    uint64_t real_size(const std::string& path)                   // src/main.rs:40-47, plus the header walk when the xattr is absent
+    {
+        uint8_t b[8];
+        if (xattr_ok_ && getxattr(path.c_str(), "user.real_size", b, 8) == 8) return be64(b);
+        auto it = mem_size_.find(path);
+        if (it != mem_size_.end()) return it->second;
+        uint64_t sz = 0;
+        const int fd = open(path.c_str(), O_RDONLY | O_CLOEXEC);
+        if (fd >= 0) { if (!content_size_from_headers(fd, &sz)) sz = 0; close(fd); }
+        return sz;
+    }
+    void set_real_size(const std::string& path, int fd, uint64_t size)
+    {
+        uint8_t b[8]; put_be64(b, size);
+        if (!xattr_ok_ || fsetxattr(fd, "user.real_size", b, 8, 0) != 0) mem_size_[path] = size;
+    }
+    int path_of(uint64_t ino, std::string& out)                   // get_path, src/main.rs:147-172
+    {
+        if (ino == FUSE_ROOT_ID) { out = data_; return 0; }
+        auto it = paths_.find(ino);
+        if (it != paths_.end()) { out = it->second; return 0; }
+        auto h = by_ino_.find(ino);
+        if (h != by_ino_.end()) for (uint64_t fh : h->second) { const Handle& x = handles_[fh]; if (x.has_refs) { out = x.path; return 0; } }
+        return ENOENT;
+    }
+    void fill_attr(struct fuse_attr& a, const struct stat& st, uint64_t ino, uint64_t size)
+    {
+        memset(&a, 0, sizeof a);
+        a.ino = ino; a.size = size; a.blocks = (size + 511) / 512;
+        a.atime = (uint64_t)st.st_atime; a.mtime = (uint64_t)st.st_mtime; a.ctime = (uint64_t)st.st_ctime;
+        a.mode = S_ISDIR(st.st_mode) ? (S_IFDIR | 0777) : (S_IFREG | 0666);     // access_all, src/main.rs:61-71
+        a.nlink = (uint32_t)st.st_nlink; a.uid = st.st_uid; a.gid = st.st_gid; a.blksize = (uint32_t)st.st_blksize;
+    }
+    int attr_of_path(const std::string& path, uint64_t ino, struct fuse_attr& a)
+    {
+        struct stat st;
+        if (stat(path.c_str(), &st) != 0) return errno;
+        fill_attr(a, st, ino, S_ISDIR(st.st_mode) ? (uint64_t)st.st_size : real_size(path));
+        auto h = by_ino_.find(ino);                                // an open file: the size of its tmpfile is the truth
+        if (h != by_ino_.end() && !h->second.empty()) { struct stat ts; if (fstat(handles_[*h->second.begin()].fd, &ts) == 0) { a.size = (uint64_t)ts.st_size; a.blocks = (a.size + 511) / 512; } }
+        return 0;
+    }
+
+    // ---- handle table (src/file.rs)
+    uint64_t new_fh() { for (uint64_t i = 0;; i++) if (!handles_.count(i)) return i; }
+    uint64_t insert_handle(uint64_t ino, int flags, int fd, const std::string& path)
+    {
+        const uint64_t fh = new_fh();
+        handles_[fh] = Handle{ flags, false, fd, true, ino, path };
+        by_ino_[ino].insert(fh);
+        return fh;
+    }
+    void forget_ino(uint64_t ino)                                 // OpenedFiles::unlink: later syncs of these handles are no-ops
+    {
+        auto it = by_ino_.find(ino);
+        if (it == by_ino_.end()) return;
+        for (uint64_t fh : it->second) handles_[fh].has_refs = false;
+        by_ino_.erase(it);
+    }
+
+    // ---- the two codec call sites
+    int store_to_source_file(int plain_fd, const std::string& dir, const std::string& name, uint64_t* ino_out);   // src/main.rs:755-832
+    int sync_to_fs(uint64_t fh, bool close_it, bool force);                                                        // src/main.rs:174-213
+    int do_open(uint64_t ino, int flags, uint64_t* fh_out);                                                        // src/main.rs:451-493
+    void readahead_dir(const std::string& dir);
+
+    // ---- protocol
+    void reply(uint64_t unique, int err, const void* p = nullptr, size_t n = 0)
+    {
+        struct fuse_out_header oh; oh.len = (uint32_t)(sizeof oh + (err ? 0 : n)); oh.error = -err; oh.unique = unique;
+        struct iovec iov[2] = { { &oh, sizeof oh }, { const_cast<void*>(p), err ? 0 : n } };
+        if (writev(dev, iov, err || n == 0 ? 1 : 2) < 0 && errno != ENOENT) logf("fzfs: reply failed: %s", strerror(errno));
+    }
+    void entry_out(struct fuse_entry_out& e, const struct fuse_attr& a) { memset(&e, 0, sizeof e); e.nodeid = a.ino; e.entry_valid = kTtlSec; e.attr_valid = kTtlSec; e.attr = a; }
+    int lookup(uint64_t parent, const char* name, struct fuse_attr& a);
+    void dispatch(const struct fuse_in_header* in, const uint8_t* arg, size_t arglen);
+};
+
+int Fs::lookup(uint64_t parent, const char* name, struct fuse_attr& a)      // lookup_wrapper, src/main.rs:215-305 (without --convert)
+{
+    std::string dir;
+    if (int e = path_of(parent, dir)) return e;
+    if (parent == FUSE_ROOT_ID && strcmp(name, ".fuse-zstd-inode_cache") == 0) return ENOENT;
+    struct stat st;
+    std::string p = dir + "/" + name;
+    if (stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode)) {
+        const uint64_t ino = ino_of(p);
+        paths_[ino] = p;
+        fill_attr(a, st, ino, (uint64_t)st.st_size);
+        return 0;
+    }
+    p += ".zst";
+    if (stat(p.c_str(), &st) != 0 || !S_ISREG(st.st_mode)) return ENOENT;
+    const uint64_t ino = ino_of(p);
+    paths_[ino] = p;
+    return attr_of_path(p, ino, a);
+}
+
+int Fs::store_to_source_file(int plain_fd, const std::string& dir, const std::string& name, uint64_t* ino_out)
+{
+    std::string tmpl = dir + "/.tmpXXXXXX";
+    std::vector<char> tbuf(tmpl.begin(), tmpl.end()); tbuf.push_back(0);
+    const int out = mkstemp(tbuf.data());                          // NamedTempFile::new_in(dir)
+    if (out < 0) return errno;
+    const std::string tmp_path(tbuf.data()), path = dir + "/" + name;
+    int err = 0;
+    struct stat st;
+    if (fsync(plain_fd) != 0 || fstat(plain_fd, &st) != 0) err = errno;
+    const uint64_t real = (uint64_t)st.st_size;
+    uint64_t ino = 0;
+    if (!err) {
+        const int src = dup(plain_fd);                             // try_clone: shares the offset, so rewind first (src/main.rs:776-779)
+        if (src < 0) err = errno;
+        else {
+            if (lseek(src, 0, SEEK_SET) < 0) err = errno;
+            if (!err) { uint8_t b[8]; ino = getxattr(path.c_str(), "user.ino", b, 8) == 8 ? be64(b) : 0; }
+            if (!err && fzfs_encode(src, out, level_, real, ino, nullptr) != 0) err = EIO;      // src/errors.rs:4-10
+            close(src);
+        }
+    }
+    if (!err) {                                                    // user.ino travels with the name (the rename changes the backing inode)
+        if (!ino) { auto it = mem_ino_.find(path); ino = it != mem_ino_.end() ? it->second : next_ino(); }
+        uint8_t b[8]; put_be64(b, ino);
+        if (!xattr_ok_ || fsetxattr(out, "user.ino", b, 8, 0) != 0) { if (errno == ENOTSUP) xattr_ok_ = false; mem_ino_[path] = ino; }
+        if (fsync(out) != 0) err = errno;
+    }
+    if (!err && rename(tmp_path.c_str(), path.c_str()) != 0) err = errno;      // persist: atomic
+    if (!err) { set_real_size(path, out, real); if (fsync(out) != 0) err = errno; fzfs_invalidate(ino); }
+    if (err) unlink(tmp_path.c_str());
+    close(out);
+    if (ino_out) *ino_out = ino;
+    return err;
+}
+
+int Fs::sync_to_fs(uint64_t fh, bool close_it, bool force)
+{
+    auto it = handles_.find(fh);
+    if (it == handles_.end()) return close_it ? EBADF : ENOENT;
+    Handle h = it->second;
+    if (close_it) {
+        handles_.erase(it);
+        if (h.has_refs) { auto m = by_ino_.find(h.ino); if (m != by_ino_.end()) { m->second.erase(fh); if (m->second.empty()) by_ino_.erase(m); } }
+    }
+    int err = 0;
+    if ((h.needs_sync || force) && h.has_refs) {
+        const size_t k = h.path.rfind('/');
+        err = store_to_source_file(h.fd, h.path.substr(0, k), h.path.substr(k + 1), nullptr);
+        if (!err && !close_it) handles_[fh].needs_sync = false;
+    }
+    if (close_it) close(h.fd);
+    return err;
+}
+
+void Fs::readahead_dir(const std::string& dir)                      // batch formation: the siblings of what was just touched
+{
+    if (!readahead_ || !prefetched_dirs_.insert(dir).second) return;
+    DIR* d = opendir(dir.c_str());
+    if (!d) return;
+    std::vector<std::string> paths; std::vector<uint64_t> keys;
+    while (struct dirent* e = readdir(d)) {
+        const std::string n = e->d_name;
+        if (!ends_with(n, ".zst")) continue;
+        const std::string p = dir + "/" + n;
+        struct stat st;
+        if (stat(p.c_str(), &st) != 0 || !S_ISREG(st.st_mode)) continue;
+        const uint64_t ino = ino_of(p);
+        paths_[ino] = p; paths.push_back(p); keys.push_back(ino);
+    }
+    closedir(d);
+    std::vector<const char*> c(paths.size());
+    for (size_t i = 0; i < paths.size(); i++) c[i] = paths[i].c_str();
+    if (!c.empty()) fzfs_prefetch(c.data(), keys.data(), c.size());
+}
+
+int Fs::do_open(uint64_t ino, int flags, uint64_t* fh_out)
+{
+    auto m = by_ino_.find(ino);
+    if (m != by_ino_.end() && !m->second.empty()) {                 // OpenedFiles::duplicate: dup the tmpfile, no decode
+        const Handle& h0 = handles_[*m->second.begin()];
+        const int fd = dup(h0.fd);
+        if (fd < 0) return errno;
+        *fh_out = insert_handle(ino, flags, fd, h0.path);
+        return 0;
+    }
+    std::string path;
+    if (int e = path_of(ino, path)) return e;
+    readahead_dir(dir_of(path));
+    const int src = open(path.c_str(), O_RDONLY | O_CLOEXEC);
+    if (src < 0) return errno;
+    char tmpl[] = "/tmp/fzfs-XXXXXX";
+    const int tmp = mkstemp(tmpl);                                  // tempfile::tempfile(): unlinked at once
+    if (tmp < 0) { const int e = errno; close(src); return e; }
+    unlink(tmpl);
+    uint64_t size = 0;
+    if (fzfs_decode(src, tmp, ino, &size) != 0) { close(src); close(tmp); return EFAULT; }     // src/main.rs:467
+    lseek(tmp, 0, SEEK_SET);
+    struct stat st;
+    int err = fstat(tmp, &st) != 0 ? errno : 0;
+    if (!err) {
+        uint8_t b[8]; put_be64(b, (uint64_t)st.st_size);
+        uint8_t cur[8];
+        const bool same = xattr_ok_ && fgetxattr(src, "user.real_size", cur, 8) == 8 && memcmp(cur, b, 8) == 0;
+        if (!same) {                                                // the reference rewrites and fsyncs on EVERY first open (src/main.rs:473-484);
+            set_real_size(path, src, (uint64_t)st.st_size);         // an unchanged value needs neither
+            if (xattr_ok_ && fsync(src) != 0) err = errno;
+        }
+    }
+    close(src);
+    if (err) { close(tmp); return err; }
+    *fh_out = insert_handle(ino, flags, tmp, path);
+    return 0;
+}
+
+void Fs::dispatch(const struct fuse_in_header* in, const uint8_t* arg, size_t arglen)
+{
+    const uint64_t u = in->unique, node = in->nodeid;
+    switch (in->opcode) {
+    case FUSE_LOOKUP: {
+        struct fuse_attr a; struct fuse_entry_out e;
+        const int err = lookup(node, (const char*)arg, a);
+        if (err) return reply(u, err);
+        entry_out(e, a); return reply(u, 0, &e, sizeof e);
+    }
+    case FUSE_FORGET: case FUSE_BATCH_FORGET: case FUSE_INTERRUPT: return;      // no reply
+    case FUSE_GETATTR: {
+        std::string p; struct fuse_attr_out o; memset(&o, 0, sizeof o);
+        int err = path_of(node, p);
+        if (!err) err = attr_of_path(p, node, o.attr);
+        if (err) return reply(u, err);
+        o.attr_valid = kTtlSec; return reply(u, 0, &o, sizeof o);
+    }
+    case FUSE_SETATTR: {                                            // only truncation (src/main.rs:408-449)
+        const struct fuse_setattr_in* s = (const struct fuse_setattr_in*)arg;
+        int err = 0;
+        if (s->valid & FATTR_SIZE) {
+            if (s->valid & FATTR_FH) { auto h = handles_.find(s->fh); if (h != handles_.end() && ftruncate(h->second.fd, (off_t)s->size) != 0) err = errno; }
+            auto m = by_ino_.find(node);
+            if (m != by_ino_.end()) for (uint64_t fh : m->second) if (ftruncate(handles_[fh].fd, (off_t)s->size) != 0) err = errno;
+        }
+        std::string p; struct fuse_attr_out o; memset(&o, 0, sizeof o);
+        if (!err) err = path_of(node, p);
+        if (!err) err = attr_of_path(p, node, o.attr);
+        if (err) return reply(u, err);
+        o.attr_valid = kTtlSec; return reply(u, 0, &o, sizeof o);
+    }
+    case FUSE_OPEN: {
+        const struct fuse_open_in* oi = (const struct fuse_open_in*)arg;
+        uint64_t fh = 0;
+        const int err = do_open(node, (int)oi->flags, &fh);
+        if (err) return reply(u, err);
+        struct fuse_open_out o; memset(&o, 0, sizeof o); o.fh = fh;
+        return reply(u, 0, &o, sizeof o);
+    }
+    case FUSE_READ: {
+        const struct fuse_read_in* r = (const struct fuse_read_in*)arg;
+        auto h = handles_.find(r->fh);
+        if (h == handles_.end()) return reply(u, ENOENT);
+        std::vector<uint8_t> buf(r->size);
+        const ssize_t n = pread(h->second.fd, buf.data(), r->size, (off_t)r->offset);
+        if (n < 0) return reply(u, errno);
+        return reply(u, 0, buf.data(), (size_t)n);
+    }
+    case FUSE_WRITE: {
+        const struct fuse_write_in* w = (const struct fuse_write_in*)arg;
+        auto h = handles_.find(w->fh);
+        if (h == handles_.end()) return reply(u, EBADF);
+        h->second.needs_sync = true;
+        off_t off = (off_t)w->offset;
+        if (h->second.flags & O_APPEND) off = lseek(h->second.fd, 0, SEEK_END);     // src/main.rs:576-588
+        const ssize_t n = pwrite(h->second.fd, arg + sizeof *w, w->size, off);
+        if (n < 0) return reply(u, errno);
+        struct fuse_write_out o; memset(&o, 0, sizeof o); o.size = (uint32_t)n;
+        return reply(u, 0, &o, sizeof o);
+    }
+    case FUSE_FLUSH: return reply(u, sync_to_fs(((const struct fuse_flush_in*)arg)->fh, false, false));
+    case FUSE_FSYNC: return reply(u, sync_to_fs(((const struct fuse_fsync_in*)arg)->fh, false, true));
+    case FUSE_RELEASE: {
+        const int err = sync_to_fs(((const struct fuse_release_in*)arg)->fh, true, false);
+        return reply(u, err == EBADF ? 0 : err);                    // src/main.rs:1010-1013
+    }
+    case FUSE_OPENDIR: {
+        std::string p;
+        if (int e = path_of(node, p)) return reply(u, e);
+        readahead_dir(p);
+        struct fuse_open_out o; memset(&o, 0, sizeof o);
+        return reply(u, 0, &o, sizeof o);
+    }
+    case FUSE_RELEASEDIR: case FUSE_FSYNCDIR: return reply(u, 0);
+    case FUSE_READDIR: {                                            // readdir_wrapper, src/main.rs:307-387
+        const struct fuse_read_in* r = (const struct fuse_read_in*)arg;
+        std::string dir;
+        if (int e = path_of(node, dir)) return reply(u, e);
+        DIR* d = opendir(dir.c_str());
+        if (!d) return reply(u, errno);
+        std::vector<uint8_t> out; uint64_t idx = 0;
+        while (struct dirent* e = readdir(d)) {
+            std::string n = e->d_name;
+            if (n == "." || n == "..") continue;
+            if (node == FUSE_ROOT_ID && n == ".fuse-zstd-inode_cache") continue;
+            const std::string p = dir + "/" + n;
+            struct stat st;
+            if (stat(p.c_str(), &st) != 0) continue;
+            uint32_t type;
+            if (S_ISDIR(st.st_mode)) type = DT_DIR;
+            else if (S_ISREG(st.st_mode) && ends_with(n, ".zst")) { type = DT_REG; n.resize(n.size() - 4); }
+            else continue;                                          // other regular files are hidden, other types skipped
+            idx++;
+            if (idx <= r->offset) continue;
+            const uint64_t ino = ino_of(p);
+            paths_[ino] = p;
+            const size_t ent = FUSE_NAME_OFFSET + n.size(), padded = FUSE_DIRENT_ALIGN(ent);
+            if (out.size() + padded > r->size) break;
+            const size_t at = out.size(); out.resize(at + padded, 0);
+            struct fuse_dirent* de = (struct fuse_dirent*)(out.data() + at);
+            de->ino = ino; de->off = idx; de->namelen = (uint32_t)n.size(); de->type = type;
+            memcpy(de->name, n.data(), n.size());
+        }
+        closedir(d);
+        return reply(u, 0, out.data(), out.size());
+    }
+    case FUSE_CREATE: {                                             // create_wrapper, src/main.rs:515-555: an EMPTY file goes through the encoder
+        const struct fuse_create_in* c = (const struct fuse_create_in*)arg;
+        const std::string name = std::string((const char*)arg + sizeof *c) + ".zst";
+        std::string dir;
+        if (int e = path_of(node, dir)) return reply(u, e);
+        char tmpl[] = "/tmp/fzfs-XXXXXX";
+        const int tmp = mkstemp(tmpl);
+        if (tmp < 0) return reply(u, errno);
+        unlink(tmpl);
+        uint64_t ino = 0;
+        if (int e = store_to_source_file(tmp, dir, name, &ino)) { close(tmp); return reply(u, e); }
+        const std::string p = dir + "/" + name;
+        paths_[ino] = p;
+        struct { struct fuse_entry_out e; struct fuse_open_out o; } out; memset(&out, 0, sizeof out);
+        struct fuse_attr a; struct stat st;
+        if (stat(p.c_str(), &st) != 0) { const int e = errno; close(tmp); return reply(u, e); }
+        fill_attr(a, st, ino, 0);
+        entry_out(out.e, a);
+        out.o.fh = insert_handle(ino, (int)c->flags, tmp, p);
+        return reply(u, 0, &out, sizeof out);
+    }
+    case FUSE_MKDIR: {
+        const struct fuse_mkdir_in* mk = (const struct fuse_mkdir_in*)arg;
+        std::string dir;
+        if (int e = path_of(node, dir)) return reply(u, e);
+        const std::string p = dir + "/" + (const char*)(arg + sizeof *mk);
+        if (mkdir(p.c_str(), 0777) != 0) return reply(u, errno);
+        struct stat st;
+        if (stat(p.c_str(), &st) != 0) return reply(u, errno);
+        const uint64_t ino = ino_of(p);
+        paths_[ino] = p;
+        struct fuse_attr a; struct fuse_entry_out e;
+        fill_attr(a, st, ino, (uint64_t)st.st_size);
+        entry_out(e, a); return reply(u, 0, &e, sizeof e);
+    }
+    case FUSE_UNLINK: case FUSE_RMDIR: {
+        std::string dir;
+        if (int e = path_of(node, dir)) return reply(u, e);
+        const bool file = in->opcode == FUSE_UNLINK;
+        const std::string p = dir + "/" + (const char*)arg + (file ? ".zst" : "");
+        if (!file && p == data_ + "/.fuse-zstd-inode_cache") return reply(u, ENOENT);
+        struct stat st;
+        const bool had = stat(p.c_str(), &st) == 0;
+        const uint64_t ino = had ? ino_of(p) : 0;
+        if ((file ? unlink(p.c_str()) : rmdir(p.c_str())) != 0) return reply(u, errno);
+        // forget the entry only once it is gone (the reference drops its inode mapping first, src/main.rs:601-648, so a failed
+        // rmdir of a non-empty directory leaves that directory unreachable until the kernel looks it up again)
+        if (had) { paths_.erase(ino); forget_ino(ino); mem_ino_.erase(p); mem_size_.erase(p); fzfs_invalidate(ino); }
+        return reply(u, 0);
+    }
+    case FUSE_RENAME: case FUSE_RENAME2: {                          // rename_wrapper, src/main.rs:650-707
+        uint64_t newdir; const char* names;
+        if (in->opcode == FUSE_RENAME) { newdir = ((const struct fuse_rename_in*)arg)->newdir; names = (const char*)arg + sizeof(struct fuse_rename_in); }
+        else { newdir = ((const struct fuse_rename2_in*)arg)->newdir; names = (const char*)arg + sizeof(struct fuse_rename2_in); }
+        const char* oldname = names; const char* newname = names + strlen(names) + 1;
+        struct fuse_attr a;
+        if (int e = lookup(node, oldname, a)) return reply(u, e);
+        const bool file = (a.mode & S_IFMT) == S_IFREG;
+        std::string from, to;
+        if (int e = path_of(node, from)) return reply(u, e);
+        if (int e = path_of(newdir, to)) return reply(u, e);
+        from += std::string("/") + oldname + (file ? ".zst" : ""); to += std::string("/") + newname + (file ? ".zst" : "");
+        struct stat st;
+        if (stat(to.c_str(), &st) == 0) { const uint64_t old = ino_of(to); paths_.erase(old); forget_ino(old); fzfs_invalidate(old); }
+        if (rename(from.c_str(), to.c_str()) != 0) return reply(u, errno);
+        paths_[a.ino] = to;
+        // every path that starts with the old name moves with it: the entry itself, and for a directory everything below it
+        // (the kernel keeps using the inode numbers it has cached; the reference leaves those, and open handles, pointing at
+        // the old location -- its TODO at src/main.rs:703)
+        auto moved = [&](const std::string& p, std::string& out) { if (p == from) { out = to; return true; } if (p.size() > from.size() && p.compare(0, from.size(), from) == 0 && p[from.size()] == '/') { out = to + p.substr(from.size()); return true; } return false; };
+        std::string np;
+        for (auto& kv : paths_) if (moved(kv.second, np)) kv.second = np;
+        for (auto& kv : handles_) if (kv.second.has_refs && moved(kv.second.path, np)) kv.second.path = np;
+        auto rekey = [&](std::unordered_map<std::string, uint64_t>& mp) { std::vector<std::pair<std::string, uint64_t>> add; for (auto it = mp.begin(); it != mp.end();) { if (moved(it->first, np)) { add.emplace_back(np, it->second); it = mp.erase(it); } else ++it; } for (auto& kv : add) mp[kv.first] = kv.second; };
+        rekey(mem_ino_); rekey(mem_size_);
+        return reply(u, 0);
+    }
+    case FUSE_STATFS: {
+        struct statvfs sv; struct fuse_statfs_out o; memset(&o, 0, sizeof o);
+        if (statvfs(data_.c_str(), &sv) != 0) return reply(u, errno);
+        o.st.blocks = sv.f_blocks; o.st.bfree = sv.f_bfree; o.st.bavail = sv.f_bavail; o.st.files = sv.f_files; o.st.ffree = sv.f_ffree;
+        o.st.bsize = (uint32_t)sv.f_bsize; o.st.namelen = 251; o.st.frsize = (uint32_t)sv.f_frsize;
+        return reply(u, 0, &o, sizeof o);
+    }
+    case FUSE_ACCESS: return reply(u, 0);
+    default: (void)arglen; return reply(u, ENOSYS);
+    }
+}
+
+volatile sig_atomic_t g_stop = 0;
+
+void Fs::loop()
+{
+    std::vector<uint8_t> buf((1u << 20) + 65536);
+    for (;;) {
+        const ssize_t n = read(dev, buf.data(), buf.size());
+        if (n < 0) { if (errno == EINTR && !g_stop) continue; if (errno == ENOENT) continue; break; }      // ENODEV: unmounted
+        if ((size_t)n < sizeof(struct fuse_in_header)) break;
+        const struct fuse_in_header* in = (const struct fuse_in_header*)buf.data();
+        const uint8_t* arg = buf.data() + sizeof *in; const size_t arglen = (size_t)n - sizeof *in;
+        logf("fzfs: op %u node %llu", in->opcode, (unsigned long long)in->nodeid);
+        if (in->opcode == FUSE_INIT) {
+            const struct fuse_init_in* ii = (const struct fuse_init_in*)arg;
+            struct fuse_init_out o; memset(&o, 0, sizeof o);
+            o.major = FUSE_KERNEL_VERSION; o.minor = ii->minor < FUSE_KERNEL_MINOR_VERSION ? ii->minor : FUSE_KERNEL_MINOR_VERSION;
+            o.max_readahead = ii->max_readahead;
+            o.flags = (FUSE_BIG_WRITES | FUSE_MAX_PAGES) & ii->flags;     // no atomic O_TRUNC: truncation arrives as SETATTR, as with fuser
+            o.max_background = 16; o.congestion_threshold = 12; o.max_write = 1u << 20; o.max_pages = 256; o.time_gran = 1;
+            reply(in->unique, 0, &o, sizeof o);
+            continue;
+        }
+        if (in->opcode == FUSE_DESTROY) { reply(in->unique, 0); break; }
+        dispatch(in, arg, arglen);
+    }
+    for (auto& kv : handles_) close(kv.second.fd);
+}
+
+std::string g_mountpoint;
+void on_signal(int) { g_stop = 1; umount2(g_mountpoint.c_str(), MNT_DETACH); }
+
+}  // namespace
+
+int main(int argc, char** argv)
+{
+    std::string data_dir, mountpoint; int level = 0; bool readahead = true; size_t cache_mb = 1024;
+    for (int i = 1; i < argc; i++) {
+        const std::string a = argv[i];
+        auto val = [&](const char* name) -> const char* { if (i + 1 >= argc) { fprintf(stderr, "fzfs: %s needs a value\n", name); exit(2); } return argv[++i]; };
+        if (a == "--data-dir") data_dir = val("--data-dir");
+        else if (a == "--mount-point") mountpoint = val("--mount-point");
+        else if (a == "--compression-level") level = atoi(val("--compression-level"));
+        else if (a == "--no-readahead") readahead = false;
+        else if (a == "--cache-mb") cache_mb = (size_t)atoll(val("--cache-mb"));
+        else if (a == "--verbose") g_verbose = true;
+        else { fprintf(stderr, "usage: %s --data-dir DIR --mount-point DIR [--compression-level 0..19] [--no-readahead] [--cache-mb N] [--verbose]\n", argv[0]); return 2; }
+    }
+    if (data_dir.empty() || mountpoint.empty()) { fprintf(stderr, "fzfs: --data-dir and --mount-point are required\n"); return 2; }
+    if (level < 0 || level > 19) level = 0;                         // src/main.rs:1283-1296
+    if (int rc = fzfs_codec_init(readahead ? cache_mb << 20 : 0)) { fprintf(stderr, "fzfs: codec unavailable (%s): %s\n", fzfs_codec_name(), strerror(rc < 0 ? -rc : rc)); return 1; }
+    Fs fs(data_dir, level, readahead);
+    fs.dev = open("/dev/fuse", O_RDWR | O_CLOEXEC);
+    if (fs.dev < 0) { perror("fzfs: /dev/fuse"); return 1; }
+    char opts[160];
+    snprintf(opts, sizeof opts, "fd=%d,rootmode=40000,user_id=%u,group_id=%u,allow_other,default_permissions", fs.dev, getuid(), getgid());
+    if (mount("fuse-zstd", mountpoint.c_str(), "fuse.fzfs", MS_NOSUID | MS_NODEV, opts) != 0) { perror("fzfs: mount"); return 1; }
+    g_mountpoint = mountpoint;
+    struct sigaction sa; memset(&sa, 0, sizeof sa); sa.sa_handler = on_signal;
+    sigaction(SIGINT, &sa, nullptr); sigaction(SIGTERM, &sa, nullptr);
+    fprintf(stderr, "fzfs: %s mounted on %s (codec: %s, level %d, readahead %s)\n", data_dir.c_str(), mountpoint.c_str(), fzfs_codec_name(), level, readahead ? "on" : "off");
+    fs.loop();
+    umount2(mountpoint.c_str(), MNT_DETACH);
+    return 0;
+}

@@ -1,0 +1,24 @@
+/*
+ * fzfs_codec.h -- the codec boundary of the fzfs host: exactly the two call sites fuse-zstd has
+ * (/root/reference/src/main.rs:463-467 and :781-791) plus the two hooks batch formation needs.
+ * Implementations: fzfs_codec_gpu.cpp (product: libfzgpu.so) and oracle/fzfs_codec_ref.c (measurement baseline: the
+ * reference's libzstd calls).  All return 0 or a non-zero error; the host maps decode failures to EFAULT and encode
+ * failures to EIO as the reference does.
+ */
+#ifndef FZFS_CODEC_H
+#define FZFS_CODEC_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+int fzfs_codec_init(size_t cache_bytes);            /* 0 = no decoded-file cache / readahead */
+const char* fzfs_codec_name(void);
+int fzfs_decode(int src_fd, int dst_fd, uint64_t ino, uint64_t* out_size);                       /* copy_decode */
+int fzfs_encode(int src_fd, int dst_fd, int level, uint64_t src_size, uint64_t ino, uint64_t* out_size);   /* Encoder ... finish */
+int fzfs_prefetch(const char* const* paths, const uint64_t* inos, size_t n);                     /* returns at once */
+void fzfs_invalidate(uint64_t ino);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,29 @@
+/* fzfs_codec_gpu.cpp -- the product codec of the fzfs host: libfzgpu.so (include/fzgpu.h).  No CPU path. */
+#include "fzfs_codec.h"
+#include "../../include/fzgpu.h"
+
+static bool g_cache = false;
+
+extern "C" int fzfs_codec_init(size_t cache_bytes)
+{
+    const int rc = fzg_init(nullptr, 0);
+    if (rc) return rc;
+    g_cache = cache_bytes != 0;
+    if (int e = fzg_cache_configure(cache_bytes)) return e;
+    const int slabs = g_cache ? fzg_cache_reserve() : 0;             // pinned memory is slow to allocate: before the mount appears
+    return slabs < 0 ? slabs : 0;
+}
+extern "C" const char* fzfs_codec_name(void) { return "fzgpu (CUDA, sm_100a)"; }
+extern "C" int fzfs_decode(int src_fd, int dst_fd, uint64_t ino, uint64_t* out_size)
+{
+    return g_cache ? fzg_cache_open(src_fd, dst_fd, ino, out_size, nullptr) : fzg_decode_fd(src_fd, dst_fd, ino, out_size);
+}
+extern "C" int fzfs_encode(int src_fd, int dst_fd, int level, uint64_t src_size, uint64_t ino, uint64_t* out_size)
+{
+    return fzg_encode_fd(src_fd, dst_fd, level, src_size, ino, out_size);
+}
+extern "C" int fzfs_prefetch(const char* const* paths, const uint64_t* inos, size_t n)
+{
+    return g_cache ? fzg_cache_prefetch_async(0, paths, inos, n) : 0;
+}
+extern "C" void fzfs_invalidate(uint64_t ino) { if (g_cache) fzg_cache_invalidate(ino); }

@@ -109,9 +109,10 @@ int fzg_seek_footer(const void* tail, size_t tail_len, uint64_t file_size, uint3
  * thousand files in the time of one.  fzg_cache_prefetch decodes the listed .zst files (e.g. the siblings readdir_wrapper,
  * src/main.rs:307-387, has just listed) as ONE batch and keeps the plain bytes, keyed by inode; fzg_cache_open is
  * open_wrapper's codec call (src/main.rs:463-467) with that cache in front of fzg_decode_fd (an entry is served only
- * while the source file still has the size and mtime it was decoded from).  LRU eviction above the configured capacity.
+ * while the source file still has the size and mtime it was decoded from).  Pinned slabs, reused oldest-first above the configured capacity.
  */
 int fzg_cache_configure(size_t capacity_bytes);   /* default 1 GiB; 0 disables prefetching */
+int fzg_cache_reserve(void);                      /* allocate the pinned slabs now (slow: once, at mount time) */
 int fzg_cache_prefetch(int device, const char* const* paths, const uint64_t* keys, size_t n);        /* -> files added */
 int fzg_cache_prefetch_async(int device, const char* const* paths, const uint64_t* keys, size_t n);  /* detached thread */
 int fzg_cache_open(int src_fd, int dst_fd, uint64_t key, uint64_t* out_size, int* hit);

@@ -22,7 +22,9 @@
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
+#include <errno.h>
 #include <pthread.h>
+#include <unistd.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -98,6 +100,41 @@ int fzr_copy_decode(const void* src, size_t src_len, void* dst, size_t dst_cap, 
             if (dst_cap - op < out.pos) { rc = 5; break; }
             memcpy((uint8_t*)dst + op, chunk, out.pos); op += out.pos;   /* write(2) into the tmpfile */
         } else if (eof && in.pos == in.size && hint != 0) { rc = 2; break; }  /* UnexpectedEof inside a frame */
+    }
+    free(inbuf); p_freeDCtx(d);
+    if (out_len) *out_len = op;
+    return rc;
+}
+
+/* the same loop on file descriptors, as fuse-zstd runs it: read(2) of up to 131075 bytes into the BufReader, write(2) of every
+ * <= 8 KiB chunk into the tmpfile (src/main.rs:463-467).  Used by the CPU arm of the mount benchmark (oracle/fzfs_codec_ref.c). */
+int fzr_copy_decode_fd(int src_fd, int dst_fd, uint64_t* out_len)
+{
+    if (!fzr_available()) return -1;
+    void* d = p_createDCtx();
+    uint8_t* inbuf = (uint8_t*)malloc(IN_CAP);
+    uint8_t chunk[COPY_CHUNK];
+    size_t hint = 0; uint64_t op = 0;
+    int rc = 0, eof = 0;
+    in_buf_t in = { inbuf, 0, 0 };
+    for (;;) {
+        if (in.pos == in.size && !eof) {
+            ssize_t n;
+            do n = read(src_fd, inbuf, IN_CAP); while (n < 0 && errno == EINTR);
+            if (n < 0) { rc = 1; break; }
+            in.size = (size_t)n; in.pos = 0;
+            if (n == 0) eof = 1;
+        }
+        if (eof && in.pos == in.size && hint == 0) break;
+        out_buf_t out = { chunk, COPY_CHUNK, 0 };
+        hint = p_decompressStream(d, &out, &in);
+        if (p_isError(hint)) { rc = 1; break; }
+        if (out.pos) {
+            size_t w = 0;
+            while (w < out.pos) { ssize_t k = write(dst_fd, chunk + w, out.pos - w); if (k < 0) { if (errno == EINTR) continue; rc = 1; break; } w += (size_t)k; }
+            if (rc) break;
+            op += out.pos;
+        } else if (eof && in.pos == in.size && hint != 0) { rc = 2; break; }
     }
     free(inbuf); p_freeDCtx(d);
     if (out_len) *out_len = op;

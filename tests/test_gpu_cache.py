@@ -72,11 +72,17 @@ def test_prefetch_then_open(ref, corpus):
         assert codec.cache_invalidate(keys[5]) == 1 and codec.cache_invalidate(keys[5]) == 0
         st, out, hit, _ = _open_through_cache(paths[5], keys[5])
         assert st == 0 and not hit and out == plain[5].tobytes()
-        # LRU: a capacity of 8 files keeps the 8 most recently used
+        # a new capacity starts empty; a prefetch never takes more than the cache holds; slabs are reused oldest-first
         codec.cache_configure(8 << 20)
-        assert codec.cache_stats()["files"] <= 8
-        st, out, hit, _ = _open_through_cache(paths[n - 1], keys[n - 1])
-        assert st == 0 and hit
+        assert codec.cache_stats()["files"] == 0
+        assert codec.cache_prefetch(paths[:n], keys[:n]) == 8                # 8 x 1 MiB fit
+        for i in range(8):
+            assert _open_through_cache(paths[i], keys[i])[2]
+        assert codec.cache_prefetch(paths[8:20], keys[8:20]) == 8             # the slab is reused: the first eight leave
+        st, out, hit, _ = _open_through_cache(paths[0], keys[0])
+        assert st == 0 and not hit and out == plain[0].tobytes()
+        st, out, hit, _ = _open_through_cache(paths[9], keys[9])
+        assert st == 0 and hit and out == plain[9].tobytes()
         codec.cache_configure(0)
         assert codec.cache_stats()["files"] == 0 and codec.cache_prefetch(paths, keys) == 0
         codec.cache_configure(1 << 30)

@@ -1,0 +1,249 @@
+"""The reference's mount-level flow tests (/root/reference/tests/cmdline.rs, glitches.rs; convert mode excluded), restated
+against the fzfs host (fuse-zstd_b200/csrc/fzfs.cpp).
+
+Two hosts are built from the same source:
+  * fuse-zstd_b200/fzfs      the product: libfzgpu.so behind the codec boundary          -> `-m gpu`
+  * oracle/_ref/fzfs_ref     TEST ONLY: the reference's libzstd calls behind the boundary -> runs here, on the CPU, and pins
+                             the HOST LOGIC (namespace, handle table, sync flow, xattrs) to the byte strings the reference's
+                             own tests pin (tests/cmdline.rs:34-43, 160-178)
+Needs /dev/fuse and mount(2) (root); skipped otherwise.
+"""
+import importlib
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GPU_HOST = os.path.join(ROOT, "fuse-zstd_b200", "fzfs")
+REF_HOST = os.path.join(ROOT, "oracle", "_ref", "fzfs_ref")
+
+
+def _can_mount():
+    return os.path.exists("/dev/fuse") and os.geteuid() == 0
+
+
+class Mount:
+    def __init__(self, host, *extra):
+        self.data = tempfile.mkdtemp(prefix="fzdata")
+        self.mp = tempfile.mkdtemp(prefix="fzmnt")
+        self.proc = subprocess.Popen([host, "--data-dir", self.data, "--mount-point", self.mp, *extra], stderr=subprocess.PIPE)
+        for _ in range(400):
+            if os.path.ismount(self.mp) or self.proc.poll() is not None:
+                break
+            time.sleep(0.025)
+        if not os.path.ismount(self.mp):
+            err = self.proc.stderr.read().decode() if self.proc.poll() is not None else ""
+            self.close()
+            raise RuntimeError("mount failed: " + err)
+
+    def close(self):
+        if self.proc.poll() is None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=10)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        subprocess.call(["umount", "-l", self.mp], stderr=subprocess.DEVNULL)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def _hosts():
+    out = [pytest.param(REF_HOST, id="reference-codec")]
+    out.append(pytest.param(GPU_HOST, id="gpu-codec", marks=pytest.mark.gpu))
+    return out
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build():
+    if not _can_mount():
+        pytest.skip("needs /dev/fuse and root")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    pyoracle.build()
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "fuse-zstd_b200", "csrc"), "all"])
+
+
+def _populate(mp):
+    os.makedirs(os.path.join(mp, "first/second/third"))
+    os.makedirs(os.path.join(mp, "first/second/empty"))
+    for rel, text in (("file1.txt", b"1st file in root"), ("first/file1.txt", b"1st file in first"), ("first/file2.txt", b"2nd file in first"),
+                      ("first/second/file1.txt", b"1st file in second"), ("first/second/file2.txt", b"2nd file in second"),
+                      ("first/second/file3.txt", b"3rd file in second"), ("first/second/third/file1.txt", b"1st file in third")):
+        with open(os.path.join(mp, rel), "wb") as fh:
+            fh.write(text)
+
+
+def _decoded(path, oracle):
+    with open(path, "rb") as fh:
+        blob = fh.read()
+    st, out = oracle.decode(blob, cap=1 << 22)
+    assert st == 0, path
+    return out
+
+
+@pytest.mark.parametrize("host", _hosts())
+def test_touch_mkdir_ls_cat(host, oracle):
+    """tests/cmdline.rs: touch (:33-43, the 13-byte frame), mkdir (:45-54), ls (:56-93), cat (:95-115)"""
+    with Mount(host) as m:
+        open(os.path.join(m.mp, "file.txt"), "wb").close()
+        assert open(os.path.join(m.data, "file.txt.zst"), "rb").read() == bytes.fromhex("28b52ffd240001000099e9d851")
+        os.mkdir(os.path.join(m.mp, "directory"))
+        assert os.path.isdir(os.path.join(m.data, "directory"))
+        os.unlink(os.path.join(m.mp, "file.txt")); os.rmdir(os.path.join(m.mp, "directory"))
+        _populate(m.mp)
+        assert sorted(os.listdir(m.mp)) == ["file1.txt", "first"]
+        assert sorted(os.listdir(os.path.join(m.mp, "first"))) == ["file1.txt", "file2.txt", "second"]
+        assert sorted(os.listdir(os.path.join(m.mp, "first/second"))) == ["empty", "file1.txt", "file2.txt", "file3.txt", "third"]
+        assert os.listdir(os.path.join(m.mp, "first/second/empty")) == []
+        assert sorted(os.listdir(os.path.join(m.data, "first"))) == ["file1.txt.zst", "file2.txt.zst", "second"]
+        assert open(os.path.join(m.mp, "first/second/third/file1.txt"), "rb").read() == b"1st file in third"
+        assert subprocess.check_output(["cat", os.path.join(m.mp, "first/file2.txt")]) == b"2nd file in first"
+        assert _decoded(os.path.join(m.data, "first/second/file3.txt.zst"), oracle) == b"3rd file in second"
+        with open(os.path.join(m.data, "plain.bin"), "wb") as fh:       # not a .zst file: hidden (src/main.rs:338-344)
+            fh.write(b"x")
+        assert "plain.bin" not in os.listdir(m.mp)
+        assert os.stat(os.path.join(m.mp, "file1.txt")).st_size == len(b"1st file in root")
+
+
+@pytest.mark.parametrize("host", _hosts())
+def test_tee_truncate_append(host, oracle):
+    """tests/cmdline.rs:117-179: overwrite, truncate and append through the mount; the last state is the 35-byte frame the
+    reference writer produces for "truncated and appended" """
+    with Mount(host) as m:
+        p = os.path.join(m.mp, "file.txt")
+        with open(p, "wb") as fh:
+            fh.write(b"first version of the file")
+        assert _decoded(os.path.join(m.data, "file.txt.zst"), oracle) == b"first version of the file"
+        with open(p, "wb") as fh:                                         # O_TRUNC
+            fh.write(b"truncated")
+        assert open(p, "rb").read() == b"truncated"
+        with open(p, "ab") as fh:
+            fh.write(b" and appended")
+        assert open(p, "rb").read() == b"truncated and appended"
+        blob = open(os.path.join(m.data, "file.txt.zst"), "rb").read()
+        assert _decoded(os.path.join(m.data, "file.txt.zst"), oracle) == b"truncated and appended"
+        if host == REF_HOST:
+            assert blob == bytes.fromhex("28b52ffd2416b100007472756e636174656420616e6420617070656e6465643d98a66b")
+        xs = os.getxattr(os.path.join(m.data, "file.txt.zst"), "user.real_size") if _xattr_ok(m.data) else None
+        assert xs in (None, (22).to_bytes(8, "big"))                      # src/main.rs:821: 8-byte big-endian
+
+
+def _xattr_ok(d):
+    try:
+        os.setxattr(d, "user.fz_probe", b"1"); os.removexattr(d, "user.fz_probe")
+        return True
+    except OSError:
+        return False
+
+
+@pytest.mark.parametrize("host", _hosts())
+def test_mv_rm_rmdir(host, oracle):
+    """tests/cmdline.rs:181-290"""
+    with Mount(host) as m:
+        _populate(m.mp)
+        mp, dd = m.mp, m.data
+        os.rename(os.path.join(mp, "first/second/file1.txt"), os.path.join(mp, "first/second/fileI.txt"))
+        assert os.path.exists(os.path.join(dd, "first/second/fileI.txt.zst")) and not os.path.exists(os.path.join(dd, "first/second/file1.txt.zst"))
+        os.rename(os.path.join(mp, "first/second/file2.txt"), os.path.join(mp, "first/file3.txt"))
+        assert _decoded(os.path.join(dd, "first/file3.txt.zst"), oracle) == b"2nd file in second"
+        os.rename(os.path.join(mp, "first/file1.txt"), os.path.join(mp, "first/second/third/file1.txt"))       # onto an existing file
+        assert not os.path.exists(os.path.join(dd, "first/file1.txt.zst"))
+        assert _decoded(os.path.join(dd, "first/second/third/file1.txt.zst"), oracle) == b"1st file in first"
+        assert open(os.path.join(mp, "first/second/third/file1.txt"), "rb").read() == b"1st file in first"
+        os.rename(os.path.join(mp, "first/second/empty"), os.path.join(mp, "first/second/void"))
+        assert os.path.isdir(os.path.join(dd, "first/second/void")) and not os.path.exists(os.path.join(dd, "first/second/empty"))
+        subprocess.check_call(["mv", os.path.join(mp, "first/second"), mp])
+        assert os.path.isdir(os.path.join(dd, "second/void")) and not os.path.exists(os.path.join(dd, "first/second"))
+        assert subprocess.call(["mv", "-T", os.path.join(mp, "second/third"), os.path.join(mp, "second/file3.txt")], stderr=subprocess.DEVNULL) != 0
+        assert os.path.isdir(os.path.join(dd, "second/third"))
+        os.unlink(os.path.join(mp, "second/file3.txt"))
+        assert not os.path.exists(os.path.join(dd, "second/file3.txt.zst"))
+        with pytest.raises(OSError):
+            os.rmdir(os.path.join(mp, "second/third"))                    # not empty
+        os.unlink(os.path.join(mp, "second/third/file1.txt")); os.rmdir(os.path.join(mp, "second/third"))
+        assert not os.path.exists(os.path.join(dd, "second/third"))
+
+
+@pytest.mark.parametrize("host", _hosts())
+def test_parallel_write_append_flush(host, oracle):
+    """tests/glitches.rs:19-91, 196-234: several handles on one file behave as on a plain directory; every close of a
+    written handle re-encodes the whole file"""
+    def parallel_write(d):
+        p = os.path.join(d, "file.txt")
+        f1 = os.open(p, os.O_WRONLY | os.O_CREAT, 0o644); f2 = os.open(p, os.O_WRONLY | os.O_CREAT, 0o644); f3 = os.open(p, os.O_WRONLY | os.O_CREAT, 0o644)
+        os.write(f2, b"SECOND"); os.write(f1, b"FIRST"); os.fsync(f1); os.close(f1)
+        os.write(f3, b"THIRD"); os.fsync(f2); os.close(f2); os.fsync(f3); os.close(f3)
+        return open(p, "rb").read()
+
+    def append(d):
+        p = os.path.join(d, "app.txt")
+        with open(p, "wb") as fh:
+            fh.write(b"BASIC")
+        with open(p, "ab") as fh:
+            fh.write(b"APPENDED"); fh.flush(); os.fsync(fh.fileno())
+        return open(p, "rb").read()
+
+    with Mount(host) as m, tempfile.TemporaryDirectory() as plain:
+        assert parallel_write(m.mp) == parallel_write(plain)
+        assert append(m.mp) == append(plain) == b"BASICAPPENDED"
+        assert _decoded(os.path.join(m.data, "app.txt.zst"), oracle) == b"BASICAPPENDED"
+        p = os.path.join(m.mp, "flush.txt")                               # glitches.rs:196-234
+        fd = os.open(p, os.O_WRONLY | os.O_CREAT, 0o644)
+        os.write(fd, b"KEEPIT"); d2 = os.dup(fd); os.close(d2)            # closing a dup flushes
+        assert _decoded(os.path.join(m.data, "flush.txt.zst"), oracle) == b"KEEPIT"
+        os.pwrite(fd, b"OVERRIDE", 0); os.close(fd)
+        assert _decoded(os.path.join(m.data, "flush.txt.zst"), oracle) == b"OVERRIDE"
+
+
+@pytest.mark.parametrize("host", _hosts())
+def test_files_written_by_stock_zstd_and_unlink_while_open(host, ref, corpus, oracle):
+    """a frame written by stock zstd (no checksum, tests/convert.rs:16-25) is served; a larger level-3 file reads back
+    bit-exactly in 128 KiB reads; a file unlinked while open is not written back (src/file.rs:119-127); a corrupt file
+    fails open() with EFAULT (src/main.rs:467)"""
+    if not ref.available:
+        pytest.skip("system libzstd absent")
+    big = corpus.json_file(2024, 3 << 20).tobytes()
+    with Mount(host) as m:
+        with open(os.path.join(m.data, "stock.zst"), "wb") as fh:
+            fh.write(bytes.fromhex("28b52ffd200f790000636f6d707265737365642064617461"))
+        with open(os.path.join(m.data, "big.json.zst"), "wb") as fh:
+            fh.write(ref.writer_encode(big, 3))
+        with open(os.path.join(m.data, "bad.zst"), "wb") as fh:
+            fh.write(b"this is not zstd")
+        assert open(os.path.join(m.mp, "stock"), "rb").read() == b"compressed data"
+        assert os.stat(os.path.join(m.mp, "big.json")).st_size == len(big)   # from the frame header: no xattr yet
+        got = bytearray()
+        with open(os.path.join(m.mp, "big.json"), "rb", buffering=0) as fh:
+            while True:
+                b = fh.read(128 << 10)
+                if not b:
+                    break
+                got += b
+        assert bytes(got) == big
+        with pytest.raises(OSError) as e:
+            open(os.path.join(m.mp, "bad"), "rb")
+        assert e.value.errno == 14
+        p = os.path.join(m.mp, "gone.txt")
+        fd = os.open(p, os.O_WRONLY | os.O_CREAT, 0o644)
+        os.write(fd, b"never stored"); os.unlink(p); os.close(fd)
+        assert not os.path.exists(os.path.join(m.data, "gone.txt.zst"))
+
+
+def test_product_host_fails_loudly_without_a_gpu():
+    """no CPU fallback: the product host refuses to mount when the CUDA codec cannot start"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with tempfile.TemporaryDirectory() as d, tempfile.TemporaryDirectory() as mp:
+        r = subprocess.run([GPU_HOST, "--data-dir", d, "--mount-point", mp], stderr=subprocess.PIPE, timeout=60)
+        assert r.returncode != 0 and b"codec unavailable" in r.stderr
+        assert not os.path.ismount(mp)

@@ -9,6 +9,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 size = (int(sys.argv[2]) if len(sys.argv) > 2 else 1024) << 10
 R = pyoracle.Ref(); assert R.available
 codec.init([0])
+codec.cache_configure(1 << 30); codec.cache_reserve()
 plain = corpus.json_files(8800000, n, size, threads=os.cpu_count())
 with tempfile.TemporaryDirectory() as d:
     paths = []

@@ -1,0 +1,77 @@
+"""Read throughput THROUGH THE MOUNT (BASELINE.json: "fio read MB/s via mount"): the job shape of
+/root/reference/benchmarks/parallel-files.fio (J jobs, each its own directory of nrfiles files of 1 MiB, opened one at a time
+and read with 128 KiB reads, psync) without fio, which this image does not have.  Two arms, same data directory, same
+reader processes, same fzfs host source (fuse-zstd_b200/csrc/fzfs.cpp):
+  gpu        fuse-zstd_b200/fzfs      GPU codec, directory readahead + decoded-file cache
+  reference  oracle/_ref/fzfs_ref     the reference's libzstd calls on the host's one FUSE thread (the restated CPU path; the
+                                      unmodified fuse-zstd binary cannot be built here: no Rust toolchain)
+usage: mount_bench.py [--jobs 16] [--nrfiles 125] [--filesize-kib 1024] [--arms gpu,reference]"""
+import argparse, importlib, json, multiprocessing as mp, os, shutil, subprocess, sys, tempfile, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def reader(args):
+    d, bs = args
+    n = 0
+    for name in sorted(os.listdir(d)):
+        fd = os.open(os.path.join(d, name), os.O_RDONLY)
+        while True:
+            b = os.read(fd, bs)
+            if not b:
+                break
+            n += len(b)
+        os.close(fd)
+    return n
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--jobs", type=int, default=16); ap.add_argument("--nrfiles", type=int, default=125)
+    ap.add_argument("--filesize-kib", type=int, default=1024); ap.add_argument("--arms", default="reference,gpu")
+    ap.add_argument("--cache-mb", type=int, default=3072)
+    a = ap.parse_args()
+    import pyoracle
+    corpus = importlib.import_module("fuse-zstd_b200.corpus")
+    pyoracle.build()
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "fuse-zstd_b200", "csrc"), "all"])
+    R = pyoracle.Ref(); assert R.available
+    size = a.filesize_kib << 10
+    data = tempfile.mkdtemp(prefix="fzbench_data")
+    t0 = time.time()
+    for j in range(a.jobs):
+        os.mkdir(os.path.join(data, "job%02d" % j))
+        plain = corpus.json_files(3300000 + j * a.nrfiles, a.nrfiles, size, threads=os.cpu_count())
+        for i in range(a.nrfiles):
+            with open(os.path.join(data, "job%02d" % j, "f%05d.zst" % i), "wb") as fh:
+                fh.write(R.writer_encode(plain[i].tobytes(), 3))
+    total = a.jobs * a.nrfiles * size
+    print("corpus: %d jobs x %d files x %d KiB = %.2f GB plain, built in %.1f s" % (a.jobs, a.nrfiles, a.filesize_kib, total / 1e9, time.time() - t0), file=sys.stderr)
+    hosts = {"gpu": [os.path.join(ROOT, "fuse-zstd_b200", "fzfs"), "--cache-mb", str(a.cache_mb)], "reference": [os.path.join(ROOT, "oracle", "_ref", "fzfs_ref")]}
+    out = {"metric": "mount_read_MBps", "unit": "MB/s", "jobs": a.jobs, "nrfiles": a.nrfiles, "filesize": size, "bs": 131072,
+           "workload": "benchmarks/parallel-files.fio shape (jobs x nrfiles x filesize, one open file per job) + sequential 128 KiB reads of every file"}
+    for arm in a.arms.split(","):
+        mpnt = tempfile.mkdtemp(prefix="fzbench_mnt")
+        proc = subprocess.Popen(hosts[arm] + ["--data-dir", data, "--mount-point", mpnt])
+        for _ in range(2400):                         # the GPU host allocates its pinned cache before it mounts
+            if os.path.ismount(mpnt) or proc.poll() is not None:
+                break
+            time.sleep(0.025)
+        assert os.path.ismount(mpnt), arm
+        try:
+            dirs = [(os.path.join(mpnt, "job%02d" % j), 131072) for j in range(a.jobs)]
+            with mp.Pool(a.jobs) as pool:
+                t0 = time.perf_counter()
+                got = sum(pool.map(reader, dirs))
+                dt = time.perf_counter() - t0
+            assert got == total, (arm, got, total)
+            out[arm] = round(total / 1e6 / dt, 1)
+            print("%s: %.2f GB through the mount in %.2f s -> %.1f MB/s" % (arm, total / 1e9, dt, total / 1e6 / dt), file=sys.stderr)
+        finally:
+            proc.terminate(); proc.wait(timeout=20)
+            subprocess.call(["umount", "-l", mpnt], stderr=subprocess.DEVNULL)
+    shutil.rmtree(data, ignore_errors=True)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
