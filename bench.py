@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--cpu-files", type=int, default=4096, help="bounded sample for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-mount", action="store_true", help="skip the read-through-the-mount leg (tools/mount_bench.py)")
     return ap.parse_args()
 
 
@@ -351,6 +352,23 @@ def run_b200(args, rank, local_rank, world):
                          "writes), one file per thread; 1 warm + 1 timed pass" % (n_s, F, w.ref.version),
                "value_1_thread": round(v_one, 4), "sample_1_thread_files": n_1}
 
+    # ---- BASELINE.json's second figure, "fio read MB/s via mount": the fzfs host with the GPU codec and with the
+    # reference's libzstd calls, same data directory, parallel-files.fio shape (fio itself is not in this image).  N=1 only.
+    mount = None
+    if not args.no_mount and world == 1:
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "mount_bench.py"), "--jobs", "16", "--nrfiles", "125"],
+                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+            if r.returncode == 0:
+                mj = json.loads(r.stdout.decode().strip().splitlines()[-1])
+                mount = {"gpu_MBps": mj.get("gpu"), "reference_cpu_MBps": mj.get("reference"), "workload": mj.get("workload"),
+                         "jobs": mj.get("jobs"), "nrfiles": mj.get("nrfiles"), "filesize": mj.get("filesize"), "bs": mj.get("bs"),
+                         "note": "one FUSE thread in both arms, as fuse-zstd; reference = copy_decode restated on libzstd (oracle/_ref/fzfs_ref)"}
+            else:
+                log("mount leg failed: " + r.stderr.decode()[-400:])
+        except Exception as e:      # no /dev/fuse, no mount permission, timeout: the leg is reported as absent, the bench line stands
+            log("mount leg unavailable: %r" % (e,))
+
     out = {"metric": METRIC, "value": round(world * w.plain_bytes / 1e9 / (ms / 1e3), 3), "unit": UNIT, "n_gpus": world,
            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -359,7 +377,7 @@ def run_b200(args, rank, local_rank, world):
                       "files_per_gpu": F, "file_size": S, "level": args.level, "ratio": round(w.plain_bytes / w.comp_bytes, 3),
                       "compressed_bytes_per_gpu": w.comp_bytes, "sharding": "by inode, no collective",
                       "l2": "working set %.1f GB per step >> 126 MB L2, no flush needed" % (alg_bytes / 1e9)},
-           "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+           "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "mount": mount}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
