@@ -26,7 +26,7 @@ class Timing(C.Structure):
 
 def build(force=False):
     """nvcc -gencode arch=compute_100a,code=sm_100a ... (csrc/Makefile); cross-compiles without a GPU."""
-    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "csrc")] + (["-B"] if force else []))
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "csrc"), "all"] + (["-B"] if force else []))
 
 
 _lib = None
