@@ -361,7 +361,9 @@ def run_b200(args, rank, local_rank, world):
                                stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
             if r.returncode == 0:
                 mj = json.loads(r.stdout.decode().strip().splitlines()[-1])
-                mount = {"gpu_MBps": mj.get("gpu"), "reference_cpu_MBps": mj.get("reference"), "workload": mj.get("workload"),
+                mount = {"gpu_MBps": mj.get("gpu"), "reference_cpu_MBps": mj.get("reference"),
+                         "gpu_write_verify_MBps": mj.get("gpu_write_verify"), "reference_cpu_write_verify_MBps": mj.get("reference_write_verify"),
+                         "workload": mj.get("workload"),
                          "jobs": mj.get("jobs"), "nrfiles": mj.get("nrfiles"), "filesize": mj.get("filesize"), "bs": mj.get("bs"),
                          "note": "one FUSE thread in both arms, as fuse-zstd; reference = copy_decode restated on libzstd (oracle/_ref/fzfs_ref)"}
             else:

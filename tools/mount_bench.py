@@ -24,11 +24,34 @@ def reader(args):
     return n
 
 
+def writer(args):
+    """write-and-verify.fio in small: every file written sequentially with `bs` writes and closed (close = whole-file encode,
+    /root/reference/src/main.rs:595-599), then read back and compared"""
+    d, bs, nfiles, size, seed = args
+    import importlib
+    corpus = importlib.import_module("fuse-zstd_b200.corpus")
+    plain = corpus.json_files(seed, nfiles, size, threads=1)
+    n = 0
+    for i in range(nfiles):
+        body = plain[i].tobytes()
+        p = os.path.join(d, "w%04d" % i)
+        fd = os.open(p, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+        for o in range(0, size, bs):
+            os.write(fd, body[o:o + bs])
+        os.close(fd)
+        with open(p, "rb") as fh:
+            assert fh.read() == body, p
+        n += size
+    return n
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--jobs", type=int, default=16); ap.add_argument("--nrfiles", type=int, default=125)
     ap.add_argument("--filesize-kib", type=int, default=1024); ap.add_argument("--arms", default="reference,gpu")
     ap.add_argument("--cache-mb", type=int, default=3072)
+    ap.add_argument("--write-files", type=int, default=8, help="files per job in the write-and-verify phase (0: skip)")
+    ap.add_argument("--write-mib", type=int, default=20)
     a = ap.parse_args()
     import pyoracle
     corpus = importlib.import_module("fuse-zstd_b200.corpus")
@@ -66,6 +89,19 @@ def main():
             assert got == total, (arm, got, total)
             out[arm] = round(total / 1e6 / dt, 1)
             print("%s: %.2f GB through the mount in %.2f s -> %.1f MB/s" % (arm, total / 1e9, dt, total / 1e6 / dt), file=sys.stderr)
+            if a.write_files:
+                wjobs = min(a.jobs, 5)                                # write-and-verify.fio: 5 workers
+                for j in range(wjobs):
+                    os.mkdir(os.path.join(mpnt, "wjob%02d" % j))
+                wargs = [(os.path.join(mpnt, "wjob%02d" % j), 131072, a.write_files, a.write_mib << 20, 4400000 + 1000 * j) for j in range(wjobs)]
+                with mp.Pool(wjobs) as pool:
+                    t0 = time.perf_counter()
+                    wrote = sum(pool.map(writer, wargs))
+                    dt = time.perf_counter() - t0
+                out[arm + "_write_verify"] = round(wrote / 1e6 / dt, 1)
+                print("%s: wrote + verified %.2f GB through the mount in %.2f s -> %.1f MB/s" % (arm, wrote / 1e9, dt, wrote / 1e6 / dt), file=sys.stderr)
+                for j in range(wjobs):
+                    shutil.rmtree(os.path.join(data, "wjob%02d" % j), ignore_errors=True)
         finally:
             proc.terminate(); proc.wait(timeout=20)
             subprocess.call(["umount", "-l", mpnt], stderr=subprocess.DEVNULL)
