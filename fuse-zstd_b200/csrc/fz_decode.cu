@@ -239,12 +239,6 @@ __global__ void __launch_bounds__(kRecWarps * 32) k_records(Block* blocks, const
     constexpr uint32_t kFullMask = 0xFFFFFFFFu;
     for (uint32_t i = threadIdx.x; i < sizeof(SeqConsts) / 4; i += blockDim.x) ((uint32_t*)&K)[i] = ((const uint32_t*)&c_seq_consts)[i];
     __syncthreads();
-#ifdef FZ_REC_PACKED_TABLES
-    __shared__ uint32_t s_llpk[36], s_mlpk[53];              // per length code: baseline | extra bits << 24
-    if (threadIdx.x < 36) s_llpk[threadIdx.x] = K.ll_base[threadIdx.x] | ((uint32_t)K.ll_bits[threadIdx.x] << 24);
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + 53) s_mlpk[threadIdx.x - 64] = K.ml_base[threadIdx.x - 64] | ((uint32_t)K.ml_bits[threadIdx.x - 64] << 24);
-    __syncthreads();
-#endif
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t job = blockIdx.x * kRecWarps + warp;
     if (job >= n_jobs) return;
@@ -258,81 +252,64 @@ __global__ void __launch_bounds__(kRecWarps * 32) k_records(Block* blocks, const
     __syncwarp();
     const uint8_t* const bits = b.src + hdrs[job].bits_off;
     const uint32_t nseq = b.nseq, lit_regen = b.lit_regen, block_max = frames[b.frame].block_max;
-    uint64_t* sq = seqs + b.seq_base;
+    uint64_t* sq = seqs + b.seq_base;                                      // 32-byte aligned (walk_item pads the record counts)
     uint32_t rep0 = off_sym(0), rep1 = off_sym(1), rep2 = off_sym(2);      // history, warp-uniform
     uint32_t Ebase = 0, LEbase = 0; bool bad = false;
-#ifdef FZ_REC_PREFETCH
-    uint64_t rnext = lane < nseq ? sq[lane] : 0;                           // the records of a step are loaded a step early
-#endif
-    for (uint32_t g = 0; g < nseq && !bad; g += 32) {
-        const uint32_t i = g + lane; const bool valid = i < nseq;
-        const uint32_t nv = min(32u, nseq - g);
-        uint32_t ll = 0, ml = 0, ofv = 4; bool ok = true;
-#ifdef FZ_REC_PREFETCH
-        const uint64_t r = rnext;
-        rnext = i + 32 < nseq ? sq[i + 32] : 0;
-#else
-        const uint64_t r = valid ? sq[i] : 0;
-#endif
-#ifdef FZ_REC_PACKED_TABLES
-        {
-            const uint32_t x = (uint32_t)r, y = (uint32_t)(r >> 32);
-            const uint32_t cl = s_llpk[yLL[(y & 0x3FFu) >> 1]], cm = s_mlpk[yML[((y >> 12) & 0x3FFu) >> 1]], yof = (y >> 24) & 31;
-            const uint32_t llb = cl >> 24, mlb = cm >> 24;
-            if (valid) {
-                if (y >> 31) ok = raw_unpack(r, K, yLL, yML, bits, ll, ml, ofv);
-                else {
-                    ofv = (1u << yof) + shr_c(x, 32 - yof);
-                    ml = (cm & 0xFFFFFFu) + shr_c(shl_c(x, yof), 32 - mlb);
-                    ll = (cl & 0xFFFFFFu) + shr_c(shl_c(x, yof + mlb), 32 - llb);
-                    ok = yof <= 27;
-                }
+    // 64 sequences per step, two per lane (positions 2 * lane and 2 * lane + 1): the per-step work of the warp -- scans, repeat-offset
+    // history, carries -- is paid once per 64 sequences, and a lane moves its two records as one 16-byte access.
+    for (uint32_t g = 0; g < nseq && !bad; g += 64) {
+        const uint32_t i0 = g + 2 * lane;
+        const bool v0 = i0 < nseq, v1 = i0 + 1 < nseq;
+        const uint32_t nv = min(64u, nseq - g);
+        uint64_t r0 = 0, r1 = 0;
+        if (v1) { const uint4 q = *(const uint4*)(sq + i0); r0 = (uint64_t)q.x | ((uint64_t)q.y << 32); r1 = (uint64_t)q.z | ((uint64_t)q.w << 32); }
+        else if (v0) r0 = sq[i0];
+        uint32_t ll0 = 0, ml0 = 0, ofv0 = 4, ll1 = 0, ml1 = 0, ofv1 = 4; bool ok = true;
+        if (v0) ok = raw_unpack(r0, K, yLL, yML, bits, ll0, ml0, ofv0);
+        if (v1) ok = raw_unpack(r1, K, yLL, yML, bits, ll1, ml1, ofv1) && ok;
+        // ---- cumulative positions: scan of the lane pairs (one packed scan when the lengths are small: 15 + 17 bits)
+        const uint32_t pLL = ll0 + ll1, pE = pLL + ml0 + ml1;
+        uint32_t xLL, xE;                                                  // exclusive prefix of this lane's pair
+        if (__all_sync(kFullMask, pLL < 1024u && pE < 4096u)) {
+            const uint32_t v = warp_scan_incl(pLL | (pE << 15), lane);
+            xLL = (v & 0x7FFFu) - pLL; xE = (v >> 15) - pE;
+        } else { xLL = warp_scan_incl(pLL, lane) - pLL; xE = warp_scan_incl(pE, lane) - pE; }
+        const uint32_t LE0 = LEbase + xLL + ll0, LE1 = LE0 + ll1;
+        const uint32_t E0 = Ebase + xE + ll0 + ml0, E1 = E0 + ll1 + ml1;
+        // ---- repeat offsets: the history hops from one repeat code to the next, in position order
+        uint32_t off0 = ofv0 - 3, off1 = ofv1 - 3;
+        const uint32_t b0 = __ballot_sync(kFullMask, v0 && ofv0 <= 3), b1 = __ballot_sync(kFullMask, v1 && ofv1 <= 3);
+        uint32_t pos = 0;                                                  // history is valid as of position `pos`
+        auto off_at = [&](uint32_t q) { return __shfl_sync(kFullMask, (q & 1) ? off1 : off0, (q >> 1) & 31); };     // q is warp-uniform
+        auto advance = [&](uint32_t upto) {                                // positions [pos, upto) are plain offsets: push the last three
+            const uint32_t cnt = upto - pos;
+            const uint32_t o1 = off_at(upto - 1), o2 = off_at(upto - 2), o3 = off_at(upto - 3);
+            const uint32_t n0 = cnt >= 1 ? o1 : rep0, n1 = cnt >= 2 ? o2 : (cnt == 1 ? rep0 : rep1),
+                           n2 = cnt >= 3 ? o3 : (cnt == 2 ? rep0 : (cnt == 1 ? rep1 : rep2));
+            rep0 = n0; rep1 = n1; rep2 = n2; pos = upto;
+        };
+        uint32_t lanes = b0 | b1;
+        while (lanes) {
+            const uint32_t L = __ffs(lanes) - 1; lanes &= lanes - 1;
+            for (uint32_t h = 0; h < 2; h++) {
+                if (!(((h ? b1 : b0) >> L) & 1u)) continue;
+                const uint32_t q = 2 * L + h;
+                advance(q);
+                const uint32_t ofr = __shfl_sync(kFullMask, h ? ofv1 : ofv0, L); const bool llz = __shfl_sync(kFullMask, h ? ll1 : ll0, L) == 0;
+                const uint32_t o = rep_update(ofr, llz, rep0, rep1, rep2);
+                if (lane == L) { if (h) off1 = o; else off0 = o; }
+                pos = q + 1;
             }
         }
-#else
-        if (valid) ok = raw_unpack(r, K, yLL, yML, bits, ll, ml, ofv);
-#endif
-        uint32_t LE, E;
-#ifndef FZ_REC_NO_PACKED_SCAN
-        if (__all_sync(kFullMask, ll < 1024u && ll + ml < 4096u)) {        // one packed scan when the lengths are small (15 + 17 bits)
-            const uint32_t v = warp_scan_incl(ll | ((ll + ml) << 15), lane);
-            LE = LEbase + (v & 0x7FFFu); E = Ebase + (v >> 15);
-        } else
-#endif
-        { LE = LEbase + warp_scan_incl(ll, lane); E = Ebase + warp_scan_incl(ll + ml, lane); }
-        // ---- repeat offsets
-        uint32_t off = ofv - 3;
-        uint32_t reps = __ballot_sync(kFullMask, valid && ofv <= 3);
-#ifdef FZ_REC_REP_FAST
-        if (reps == 0 && nv >= 3) {                                        // no repeat code in this step: the history is its last three offsets
-            rep0 = __shfl_sync(kFullMask, off, nv - 1); rep1 = __shfl_sync(kFullMask, off, nv - 2); rep2 = __shfl_sync(kFullMask, off, nv - 3);
-        } else
-#endif
-        {
-            uint32_t pos = 0;                                              // history is valid as of lane `pos`
-            auto advance = [&](uint32_t upto) {                            // lanes [pos, upto) are plain offsets: push the last three
-                const uint32_t cnt = upto - pos;
-                const uint32_t o1 = __shfl_sync(kFullMask, off, (upto - 1) & 31), o2 = __shfl_sync(kFullMask, off, (upto - 2) & 31),
-                               o3 = __shfl_sync(kFullMask, off, (upto - 3) & 31);
-                const uint32_t n0 = cnt >= 1 ? o1 : rep0, n1 = cnt >= 2 ? o2 : (cnt == 1 ? rep0 : rep1),
-                               n2 = cnt >= 3 ? o3 : (cnt == 2 ? rep0 : (cnt == 1 ? rep1 : rep2));
-                rep0 = n0; rep1 = n1; rep2 = n2; pos = upto;
-            };
-            while (reps) {
-                const uint32_t rr = __ffs(reps) - 1; reps &= reps - 1;
-                advance(rr);
-                const uint32_t ofr = __shfl_sync(kFullMask, ofv, rr); const bool ll0 = __shfl_sync(kFullMask, ll, rr) == 0;
-                const uint32_t o = rep_update(ofr, ll0, rep0, rep1, rep2);
-                if (lane == rr) off = o;
-                pos = rr + 1;
-            }
-            advance(nv);
-        }
-        ok = ok && !(ofv > 3 && off > kOffMax) && LE <= lit_regen && E <= block_max;
-        bad = __any_sync(kFullMask, valid && !ok);
+        advance(nv);
+        ok = ok && !(ofv0 > 3 && off0 > kOffMax) && !(ofv1 > 3 && off1 > kOffMax) && LE1 <= lit_regen && E1 <= block_max;
+        bad = __any_sync(kFullMask, v0 && !ok);
         if (bad) break;
-        if (valid) sq[i] = rec_pack(E, LE, off);
-        Ebase = __shfl_sync(kFullMask, E, 31); LEbase = __shfl_sync(kFullMask, LE, 31);
+        if (v1) {
+            const uint64_t a0 = rec_pack(E0, LE0, off0), a1 = rec_pack(E1, LE1, off1);
+            *(uint4*)(sq + i0) = make_uint4((uint32_t)a0, (uint32_t)(a0 >> 32), (uint32_t)a1, (uint32_t)(a1 >> 32));
+        } else if (v0) sq[i0] = rec_pack(E0, LE0, off0);
+        Ebase = __shfl_sync(kFullMask, E1, 31); LEbase = __shfl_sync(kFullMask, LE1, 31);
     }
     const uint32_t rsize = Ebase + (lit_regen - LEbase);
     if (bad || rsize > block_max) { if (lane == 0) b.status = FZG_E_CORRUPT; return; }
