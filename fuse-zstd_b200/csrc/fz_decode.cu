@@ -257,13 +257,15 @@ __global__ void __launch_bounds__(kRecWarps * 32) k_records(Block* blocks, const
     uint32_t Ebase = 0, LEbase = 0; bool bad = false;
     // 64 sequences per step, two per lane (positions 2 * lane and 2 * lane + 1): the per-step work of the warp -- scans, repeat-offset
     // history, carries -- is paid once per 64 sequences, and a lane moves its two records as one 16-byte access.
+    uint4 qn = make_uint4(0, 0, 0, 0);                                     // the records of a step are loaded a step early
+    if (2 * lane + 1 < nseq) qn = *(const uint4*)(sq + 2 * lane); else if (2 * lane < nseq) { const uint64_t t = sq[2 * lane]; qn.x = (uint32_t)t; qn.y = (uint32_t)(t >> 32); }
     for (uint32_t g = 0; g < nseq && !bad; g += 64) {
         const uint32_t i0 = g + 2 * lane;
         const bool v0 = i0 < nseq, v1 = i0 + 1 < nseq;
         const uint32_t nv = min(64u, nseq - g);
-        uint64_t r0 = 0, r1 = 0;
-        if (v1) { const uint4 q = *(const uint4*)(sq + i0); r0 = (uint64_t)q.x | ((uint64_t)q.y << 32); r1 = (uint64_t)q.z | ((uint64_t)q.w << 32); }
-        else if (v0) r0 = sq[i0];
+        const uint64_t r0 = (uint64_t)qn.x | ((uint64_t)qn.y << 32), r1 = (uint64_t)qn.z | ((uint64_t)qn.w << 32);
+        qn = make_uint4(0, 0, 0, 0);
+        if (i0 + 65 < nseq) qn = *(const uint4*)(sq + i0 + 64); else if (i0 + 64 < nseq) { const uint64_t t = sq[i0 + 64]; qn.x = (uint32_t)t; qn.y = (uint32_t)(t >> 32); }
         uint32_t ll0 = 0, ml0 = 0, ofv0 = 4, ll1 = 0, ml1 = 0, ofv1 = 4; bool ok = true;
         if (v0) ok = raw_unpack(r0, K, yLL, yML, bits, ll0, ml0, ofv0);
         if (v1) ok = raw_unpack(r1, K, yLL, yML, bits, ll1, ml1, ofv1) && ok;
