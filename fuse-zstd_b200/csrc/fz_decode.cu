@@ -594,6 +594,257 @@ __global__ void __launch_bounds__(kExecWarps * 32, kExecCtasPerSm) k_execute(Fra
     }
 }
 
+// ------------------------------------------------------------------ execute, several warps per frame
+// One warp per frame needs thousands of frames to fill the GPU and takes ~5 ms for a 1 MiB frame.  A batch with FEW
+// frames (one file opened through the mount, config 4's large single-frame files) is executed by W warps per frame
+// instead: a CTA owns a frame, a CTA round takes 32 W sequences (one per thread) into one shared-memory stage of
+// W x 512 bytes.  A thread's literal run and match are placed by the positional records as before; what changes is
+// how a thread learns that the source bytes of its match are there.  Sources below the round are in HBM (the
+// previous flush is separated from this round by a barrier).  Sources inside the round are tracked by a BITMAP with
+// one bit per stage byte: a writer sets the bits of the bytes it has stored (release), a reader takes the longest
+// ready prefix of the (up to 8) bytes it wants (acquire) and retries later for the rest.  This is exact dataflow: no
+// frontier, no ordering between lanes or warps, and the lowest unfinished sequence can always advance (everything
+// below its position belongs to finished sequences or to itself), so the polling terminates.  An offset below 8 is
+// widened to its first multiple >= 8 as soon as the match has produced that many bytes (the output is periodic from
+// M - off on), so short periods also move 8 bytes per step after the first few.
+// Two barriers per round: before the flush (the stage is complete) and after it (HBM readable, bitmap cleared).
+template <int W> struct ExecCta {
+    static constexpr uint32_t threads = W * 32;
+    static constexpr uint32_t stage = W * kStage;
+    static constexpr uint32_t stage_bytes = stage + 48;
+    static constexpr uint32_t bitmap_words = stage_bytes / 32 + 2;     // one bit per stage byte (+ the word a window may spill into)
+    static constexpr int ctas_per_sm = W >= 32 ? 1 : 32 / W;
+};
+
+// stage bytes [o, o + nb) are stored: publish them (release: the byte stores above are visible to whoever sees the bits)
+__device__ __forceinline__ void bm_mark(uint32_t* bm, uint32_t o, uint32_t nb)
+{
+    const uint32_t sh = o & 31u, m = (1u << nb) - 1u;
+    const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(bm + (o >> 5));
+    asm volatile("red.release.cta.shared.or.b32 [%0], %1;" ::"r"(a0), "r"(m << sh) : "memory");
+    if (sh + nb > 32) asm volatile("red.relaxed.cta.shared.or.b32 [%0], %1;" ::"r"(a0 + 4), "r"(m >> (32 - sh)) : "memory");
+}
+// how many of the stage bytes starting at o are stored (0 .. 32)
+__device__ __forceinline__ uint32_t bm_ready(const uint32_t* bm, uint32_t o)
+{
+    const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(bm + (o >> 5));
+    uint32_t w0, w1;
+    asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(w0) : "r"(a0) : "memory");
+    asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(w1) : "r"(a0 + 4) : "memory");
+    const uint32_t bits = __funnelshift_r(w0, w1, o & 31u);
+    return (uint32_t)__ffs((int)~bits) - 1u;                     // all 32 ready: 0xFFFFFFFF, larger than any request
+}
+
+__device__ __forceinline__ void group_copy(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t tid, uint32_t nthr)
+{
+    if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) {
+        const uint32_t nv = n >> 4;
+        for (uint32_t i = tid; i < nv; i += nthr) ((uint4*)dst)[i] = ((const uint4*)src)[i];
+        for (uint32_t i = (nv << 4) + tid; i < n; i += nthr) dst[i] = src[i];
+    } else {
+        for (uint32_t i = tid; i < n; i += nthr) dst[i] = src[i];
+    }
+}
+
+// One sequence that does not fit the stage, copied by the whole CTA straight to HBM (arguments CTA-uniform).
+// Every byte below dst is readable on entry (barrier after the previous flush).
+template <int W>
+__device__ __forceinline__ void cta_big_sequence(uint8_t* dst, const uint8_t* lit, uint32_t ll, uint32_t ml, uint32_t off, uint32_t tid)
+{
+    constexpr uint32_t T = W * 32;
+    group_copy(dst, lit, ll, tid, T);
+    __syncthreads();
+    uint8_t* m = dst + ll;
+    if (off != 0) {                                          // 0: flagged corrupt by the caller
+        const uint8_t* s = m - off;
+        if (off >= 16 * T) {                                 // source and destination of a 16 T-byte round never overlap
+            for (uint32_t i = 0; i < ml; i += 16 * T) {
+                const uint32_t nb = min(16u, ml > i + 16 * tid ? ml - i - 16 * tid : 0u);
+                for (uint32_t k = 0; k < nb; k++) m[i + 16 * tid + k] = s[i + 16 * tid + k];
+                __syncthreads();
+            }
+        } else {                                             // periodic with period `off`; the period lies below m: written
+            for (uint32_t i = tid; i < ml; i += T) m[i] = s[i % off];
+        }
+    }
+    __syncthreads();
+}
+
+template <int W>
+__device__ __forceinline__ void exec_block_cta(uint8_t* stage, uint32_t* bm, uint32_t* cnt, const Block& b,
+                                               const uint64_t* __restrict__ sq, uint8_t* g0, uint64_t done, int& status, uint32_t tid)
+{
+    constexpr uint32_t T = W * 32, kCtaStage = ExecCta<W>::stage;
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    const uint32_t nseq = b.nseq, rsize = b.rsize;
+    const uint8_t* __restrict__ lit = b.lit;
+    const uint32_t in0 = b.rep_in[0], in1 = b.rep_in[1], in2 = b.rep_in[2];
+    for (uint32_t i = tid; i < ExecCta<W>::bitmap_words; i += T) bm[i] = 0;
+    __syncthreads();
+    uint32_t Ecarry = 0, LEcarry = 0;                            // CTA-uniform
+    uint64_t rcur = tid < nseq ? __ldg(sq + tid) : 0;            // the round's records; the next round's are loaded a round early
+    uint64_t rprev = (lane == 0 && warp > 0 && tid <= nseq) ? __ldg(sq + tid - 1) : 0;   // record before a warp's first one
+    for (uint32_t g = 0; g < nseq;) {
+        const uint32_t nv = min(T, nseq - g);
+        const uint64_t rl = __ldg(sq + g + nv - 1);
+        const uint32_t Elast = rec_e(rl), LElast = rec_le(rl);
+        const uint64_t r = tid < nv ? rcur : 0;
+        uint32_t E = rec_e(r), LE = rec_le(r);
+        if (tid >= nv) { E = Elast; LE = LElast; }
+        uint32_t S = __shfl_up_sync(kFull, E, 1), LEp = __shfl_up_sync(kFull, LE, 1);
+        if (lane == 0) {
+            if (warp == 0) { S = Ecarry; LEp = LEcarry; }
+            else if (tid <= nv) { S = rec_e(rprev); LEp = rec_le(rprev); }
+            else { S = Elast; LEp = LElast; }
+        }
+        const uint32_t gS = Ecarry;                              // output position where this round starts
+        uint32_t off = tid < nv ? off_resolve(rec_off(r), in0, in1, in2) : 1;
+        if (tid < nv && (uint64_t)off > done + S + (LE - LEp)) { off = 0; status = FZG_E_CORRUPT; }   // reaches before the frame start
+        // sequences of this round: the leading ones whose output fits the stage (E never decreases)
+        uint32_t n = nv;
+        if (Elast - gS > kCtaStage) {
+            const uint32_t fit = __ballot_sync(kFull, tid < nv && E - gS <= kCtaStage);
+            if (lane == 0) cnt[warp] = (uint32_t)__popc(fit);
+            __syncthreads();
+            n = 0;
+            for (int w = 0; w < W; w++) n += cnt[w];
+            __syncthreads();
+        }
+        if (n == 0) {                                            // sequence g alone is larger than the stage
+            const uint64_t r0 = __ldg(sq + g);
+            const uint32_t E0 = rec_e(r0), LE0 = rec_le(r0), M0 = gS + (LE0 - LEcarry);
+            uint32_t off0 = off_resolve(rec_off(r0), in0, in1, in2);
+            if ((uint64_t)off0 > done + M0) off0 = 0;
+            cta_big_sequence<W>(g0 + gS, lit + LEcarry, LE0 - LEcarry, E0 - M0, off0, tid);
+            Ecarry = E0; LEcarry = LE0;
+            g += 1;
+            rcur = g + tid < nseq ? __ldg(sq + g + tid) : 0;
+            rprev = (lane == 0 && warp > 0 && g + tid <= nseq) ? __ldg(sq + g + tid - 1) : 0;
+            continue;
+        }
+        const uint64_t re = __ldg(sq + g + n - 1);
+        const uint32_t gE = rec_e(re), LEend = rec_le(re);       // end of the round's output / literals
+        rcur = g + n + tid < nseq ? __ldg(sq + g + n + tid) : 0;
+        rprev = (lane == 0 && warp > 0 && g + n + tid <= nseq) ? __ldg(sq + g + n + tid - 1) : 0;
+        const bool mine = tid < n;
+        if (!mine) { S = gE; E = gE; LE = LEend; LEp = LEend; }
+        const uint32_t M = S + (LE - LEp);
+        const uint32_t a = (uint32_t)((uintptr_t)(g0 + gS) & 15); // stage[a + i] <-> g0[gS + i]: same low address bits as HBM
+        uint8_t* const st = stage + a - gS;                       // st[p] is the stage byte of output position p (gS <= p < gE)
+        const uint32_t ob = a - gS;                               // ob + p: bitmap index of output position p
+        // ---- 1. literal runs
+        {
+            uint32_t pos = S; const uint8_t* src = lit + LEp;
+            bool go = mine && pos < M;
+            while (__any_sync(kFull, go)) {
+                if (go) {
+                    const uint32_t nb = min(8u, M - pos);
+                    st_stage(st + pos, ld8_any(src, nb), nb);
+                    bm_mark(bm, ob + pos, nb);
+                    pos += nb; src += nb; go = pos < M;
+                }
+            }
+        }
+        // ---- 2. matches
+        {
+            uint32_t pos = M;
+            bool pending = mine && pos < E;
+            const uint32_t eoff = off < 8 ? off * ((off + 7) / max(off, 1u)) : off;   // first multiple of a short period that is >= 8
+            while (__any_sync(kFull, pending)) {
+                bool moved = false;
+                if (pending) {
+                    uint32_t nb = min(8u, E - pos);
+                    uint64_t v = 0;
+                    if (off != 0) {                               // 0: corrupt, zeros
+                        const uint32_t d = pos - M >= eoff - off ? eoff : off;        // the source stays at or above M - off
+                        nb = min(nb, d);
+                        const int32_t s = (int32_t)pos - (int32_t)d;
+                        if (s < (int32_t)gS) {                    // before the round: HBM / L2 (earlier rounds, earlier blocks)
+                            nb = min(nb, gS - (uint32_t)s);       // a step straddling the round start is split
+                            v = ld8_any((const uint8_t*)g0 + s, nb);
+                        } else {
+                            nb = min(nb, bm_ready(bm, ob + (uint32_t)s));
+                            if (nb) v = ld8_any((const uint8_t*)st + s, nb);
+                        }
+                    }
+                    if (nb) { st_stage(st + pos, v, nb); bm_mark(bm, ob + pos, nb); pos += nb; pending = pos < E; moved = true; }
+                }
+                if (!__any_sync(kFull, moved)) __nanosleep(32);   // every unfinished lane waits for another warp
+            }
+        }
+        __syncthreads();
+        // ---- 3. flush stage[a .. a + (gE - gS)) -> g0 + gS: head bytes, aligned 16-byte body, tail bytes
+        {
+            const uint32_t nby = gE - gS;
+            uint8_t* gd = g0 + gS;
+            const uint32_t head = min(nby, (16 - a) & 15);
+            if (tid < head) gd[tid] = stage[a + tid];
+            const uint32_t nvec = (nby - head) >> 4;
+            for (uint32_t i = tid; i < nvec; i += T) *(uint4*)(gd + head + 16 * i) = *(const uint4*)(stage + a + head + 16 * i);
+            const uint32_t tail0 = head + (nvec << 4);
+            if (tail0 + tid < nby) gd[tail0 + tid] = stage[a + tail0 + tid];
+            for (uint32_t i = tid; i < ExecCta<W>::bitmap_words; i += T) bm[i] = 0;
+        }
+        __syncthreads();
+        Ecarry = gE; LEcarry = LEend;
+        g += n;
+        // the next round's match sources: ask for them now (see k_execute)
+        {
+            const uint32_t nn = g < nseq ? min(T, nseq - g) : 0u;
+            const uint32_t En = rec_e(rcur), LEn = rec_le(rcur);
+            uint32_t Sn = __shfl_up_sync(kFull, En, 1), LEpn = __shfl_up_sync(kFull, LEn, 1);
+            if (lane == 0) { if (warp == 0) { Sn = Ecarry; LEpn = LEcarry; } else { Sn = rec_e(rprev); LEpn = rec_le(rprev); } }
+            const uint32_t Mn = Sn + (LEn - LEpn);
+            const uint32_t offn = off_resolve(rec_off(rcur), in0, in1, in2);
+            if (tid < nn && offn != 0 && (uint64_t)offn <= done + Mn && offn > Mn - Ecarry) {
+                const uint8_t* sp = g0 + Mn - offn;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(sp));
+                if ((((uintptr_t)sp + (En - Mn) - 1) ^ (uintptr_t)sp) & ~(uintptr_t)31) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + (En - Mn) - 1));
+            }
+        }
+    }
+    // literals after the last sequence
+    group_copy(g0 + Ecarry, lit + LEcarry, rsize - Ecarry, tid, T);
+}
+
+template <int W>
+__global__ void __launch_bounds__(ExecCta<W>::threads, ExecCta<W>::ctas_per_sm) k_execute_cta(Frame* frames, const Block* blocks, const Item* items,
+                                                                                             const ItemOut* outs, const uint64_t* seqs,
+                                                                                             uint32_t n_frames, uint32_t* ticket)
+{
+    constexpr uint32_t T = ExecCta<W>::threads;
+    __shared__ __align__(16) uint8_t s_stage[ExecCta<W>::stage_bytes];
+    __shared__ uint32_t s_bm[ExecCta<W>::bitmap_words], s_cnt[W], s_f;
+    const uint32_t tid = threadIdx.x;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_f = atomicAdd(ticket, 1);
+        __syncthreads();
+        const uint32_t f = s_f;
+        if (f >= n_frames) return;
+        Frame& fr = frames[f];
+        if (outs[fr.item].fail) continue;
+        uint8_t* const fbase = items[fr.item].dst + fr.out_off;
+        uint64_t done = 0;
+        int status = 0;
+        for (uint32_t kb = 0; kb < fr.n_blocks; kb++) {
+            const Block& b = blocks[fr.first_block + kb];
+            uint8_t* const g0 = fbase + done;
+            const uint32_t rsize = b.rsize;
+            if (b.type == BT_RAW) group_copy(g0, b.src, rsize, tid, T);
+            else if (b.type == BT_RLE) {
+                const uint8_t v = b.src[0];
+                for (uint32_t i = tid; i < rsize; i += T) g0[i] = v;
+            } else if (b.nseq == 0) group_copy(g0, b.lit, rsize, tid, T);
+            else exec_block_cta<W>(s_stage, s_bm, s_cnt, b, seqs + b.seq_base, g0, done, status, tid);
+            __syncthreads();                   // later blocks read this one back (the window)
+            done += rsize;
+        }
+        status = __reduce_max_sync(kFull, status);
+        if ((tid & 31) == 0 && status) fr.status = status;
+    }
+}
+
 // Four threads per frame, one XXH64 accumulator each (stripe = 32 bytes, lane j owns bytes 8j..8j+7).
 __global__ void k_checksum(Frame* frames, const Item* items, const ItemOut* outs, uint32_t n_frames)
 {
@@ -630,6 +881,12 @@ const char* fzh_decode_stage_name(int s) { return s >= 0 && s < 11 ? kStageNames
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "fzgpu: %s failed: %s (%s:%d)\n", #x, cudaGetErrorString(e_), __FILE__, __LINE__); return -5 /*-EIO*/; } } while (0)
 
 static int g_sm_count = 148;
+static int exec_warps_override()          // FZG_EXEC_W: warps per frame in the execute stage (1, 2, 4, 8, 16, 32; else by batch shape); read per call (tests)
+{
+    const char* e = getenv("FZG_EXEC_W");
+    const int v = e ? atoi(e) : 0;
+    return (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ? v : 0;
+}
 
 int fzh_decode_setup(void)
 {
@@ -726,8 +983,27 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
     signal.fire();
     k_offsets<<<gi, tb, 0, s>>>(d_items, d_infos, d_bases, d_frames, d_blocks, d_outs, n); mark(); launches++;
     if (n_frames) {
-        const uint32_t grid = (uint32_t)std::min<uint64_t>((n_frames + kExecWarps - 1) / kExecWarps, (uint64_t)g_sm_count * kExecCtasPerSm);
-        k_execute<<<grid, kExecWarps * 32, 0, s>>>(d_frames, d_blocks, d_items, d_outs, d_seq, (uint32_t)n_frames, d_tickets + 1); launches++;
+        // warps per frame: as many as it takes to fill the GPU's 32 warp slots per SM with the frames of this batch
+        // (tools/exec_width_probe.py: 1 file 5.7 -> 0.8 ms at 32; 592 files 7.0 -> 2.4 ms at 8; 2368 files 8.5 -> 7.7 ms at 2;
+        // from ~4700 frames on one warp per frame wins: k_execute has fewer instructions per sequence than the dataflow kernel)
+        const int w_env = exec_warps_override();
+        int w = w_env;
+        if (!w) { w = 32; while (w > 1 && n_frames * (uint64_t)w > (uint64_t)g_sm_count * 32) w >>= 1; }
+        auto cta = [&](auto wc) {
+            constexpr int W = decltype(wc)::value;
+            const uint32_t grid = (uint32_t)std::min<uint64_t>(n_frames, (uint64_t)g_sm_count * ExecCta<W>::ctas_per_sm);
+            k_execute_cta<W><<<grid, ExecCta<W>::threads, 0, s>>>(d_frames, d_blocks, d_items, d_outs, d_seq, (uint32_t)n_frames, d_tickets + 1);
+        };
+        if (w == 1) {
+            const uint32_t grid = (uint32_t)std::min<uint64_t>((n_frames + kExecWarps - 1) / kExecWarps, (uint64_t)g_sm_count * kExecCtasPerSm);
+            k_execute<<<grid, kExecWarps * 32, 0, s>>>(d_frames, d_blocks, d_items, d_outs, d_seq, (uint32_t)n_frames, d_tickets + 1);
+        }
+        else if (w == 2) cta(std::integral_constant<int, 2>{});
+        else if (w == 4) cta(std::integral_constant<int, 4>{});
+        else if (w == 8) cta(std::integral_constant<int, 8>{});
+        else if (w == 16) cta(std::integral_constant<int, 16>{});
+        else cta(std::integral_constant<int, 32>{});
+        launches++;
     }
     mark();
     if (n_frames && !(flags & FZG_NO_VERIFY_CHECKSUM)) { k_checksum<<<(uint32_t)((n_frames * 4 + 127) / 128), 128, 0, s>>>(d_frames, d_items, d_outs, (uint32_t)n_frames); launches++; }

@@ -31,11 +31,24 @@ def _init():
     yield
 
 
+@pytest.fixture(params=["1", "2", "8", "32"])
+def exec_w(request):
+    """warps per frame in the execute stage: k_execute (1) or k_execute_cta<2 / 8 / 32>; without the fixture the library
+    chooses by batch shape (few frames -> many warps per frame)"""
+    old = os.environ.get("FZG_EXEC_W")
+    os.environ["FZG_EXEC_W"] = request.param
+    yield request.param
+    if old is None:
+        os.environ.pop("FZG_EXEC_W", None)
+    else:
+        os.environ["FZG_EXEC_W"] = old
+
+
 def sha(b):
     return hashlib.sha256(b).hexdigest()
 
 
-def test_golden_vectors_bit_exact(golden, oracle):
+def test_golden_vectors_bit_exact(golden, oracle, exec_w):
     names = sorted(golden)
     res = codec.decode_batch([golden[n][0] for n in names], [golden[n][1]["plain_len"] for n in names])
     for n, (st, out) in zip(names, res):
@@ -77,7 +90,7 @@ def test_error_statuses_match_oracle(golden, oracle):
     assert st in (codec.E_DSTSIZE, codec.E_CORRUPT)
 
 
-def test_mutation_fuzz_matches_oracle(golden, oracle):
+def test_mutation_fuzz_matches_oracle(golden, oracle, exec_w):
     rs = np.random.RandomState(1234)
     for name in ("json_20000_L3_writer", "json_200k_L3_nopledge_nochk", "json_120k_L19_wlog11_repeat", "rle_mode_of_ml",
                  "direct_weights_huffman"):
@@ -114,7 +127,7 @@ def _mixed_plain(rs, corpus, idx, size):
     return j[: size // 2] + j[: size - size // 2]                                     # long-distance match
 
 
-def test_seeded_corpus_vs_oracle(ref, oracle, corpus):
+def test_seeded_corpus_vs_oracle(ref, oracle, corpus, exec_w):
     """levels 1/3/19 x sizes 0..600k x 6 input kinds; reference-writer and bulk framing"""
     if not ref.available:
         pytest.skip("system libzstd absent: cannot produce fresh frames")
@@ -134,7 +147,7 @@ def test_seeded_corpus_vs_oracle(ref, oracle, corpus):
         assert st_o == 0 and out_o == out
 
 
-def test_window_and_multiframe(ref, corpus):
+def test_window_and_multiframe(ref, corpus, exec_w):
     if not ref.available:
         pytest.skip("system libzstd absent")
     plain = corpus.json_file(77, 3 << 20).tobytes()
@@ -203,7 +216,7 @@ def test_fd_entry_points_follow_the_reference_flow(golden):
         assert stream.decode_all(src) == b""
 
 
-def test_large_window_long_distance_and_level19(ref, corpus):
+def test_large_window_long_distance_and_level19(ref, corpus, exec_w):
     """config 4 in miniature: windowLog 23 (8 MiB window, offsets across dozens of blocks), a level-19 frame (block
     splitting, Repeat modes, Treeless literals) and a long-distance repeat; one frame each, so one LZ77 chain each"""
     if not ref.available:
@@ -219,7 +232,7 @@ def test_large_window_long_distance_and_level19(ref, corpus):
         assert hashlib.sha256(out).digest() == hashlib.sha256(plain).digest(), i
 
 
-def test_far_form_records(ref):
+def test_far_form_records(ref, exec_w):
     """sequences with more than 32 extra bits (long literal run + far offset + long match): stage A hands stage B the bit
     cursor instead of the bits (tests/test_emul.py::test_far_form_records checks that the vector really has such sequences)"""
     if not ref.available:
