@@ -58,6 +58,9 @@ extern "C" int fzg_init(const int* devices, int n_devices)
             CKR(cudaStreamCreateWithFlags(&c->lane[l].stream, cudaStreamNonBlocking));
             for (auto& e : c->lane[l].ev) CKR(cudaEventCreate(&e));
             CKR(cudaEventCreateWithFlags(&c->lane[l].ev_entropy, cudaEventDisableTiming));
+            CKR(cudaStreamCreateWithFlags(&c->lane[l].side, cudaStreamNonBlocking));
+            CKR(cudaEventCreateWithFlags(&c->lane[l].ev_fork, cudaEventDisableTiming));
+            CKR(cudaEventCreateWithFlags(&c->lane[l].ev_join, cudaEventDisableTiming));
         }
         c->stream = c->lane[0].stream;
         CKR(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -84,11 +87,13 @@ extern "C" void fzg_shutdown(void)
             FzLane& L = c->lane[l];
             cudaStreamSynchronize(L.stream);
             FzDevBuf* lb[] = { &L.d_infos, &L.d_bases, &L.d_outs, &L.d_totals, &L.d_frames, &L.d_blocks, &L.d_seq_jobs, &L.d_huf_jobs,
-                               &L.d_lit, &L.d_seq, &L.d_seq_tabs, &L.d_seq_hdrs };
+                               &L.d_lit, &L.d_seq, &L.d_seq_tabs, &L.d_seq_hdrs, &L.d_prog };
             for (auto* b : lb) b->release();
             L.h_totals.release();
             for (auto& e : L.ev) cudaEventDestroy(e);
             cudaEventDestroy(L.ev_entropy);
+            cudaEventDestroy(L.ev_fork); cudaEventDestroy(L.ev_join);
+            cudaStreamDestroy(L.side);
             cudaStreamDestroy(L.stream);
         }
         for (auto& e : c->ev) cudaEventDestroy(e);

@@ -609,12 +609,20 @@ __global__ void __launch_bounds__(kExecWarps * 32, kExecCtasPerSm) k_execute(Fra
 // M - off on), so short periods also move 8 bytes per step after the first few.
 // Two barriers per round: before the flush (the stage is complete) and after it (HBM readable, bitmap cleared).
 template <int W> struct ExecCta {
-    static constexpr uint32_t threads = W * 32;
+    static constexpr bool hash = W == 8 || W == 16;                     // a checksum warp rides along (below)
+    static constexpr uint32_t exec_threads = W * 32;
+    static constexpr uint32_t threads = exec_threads + (hash ? 32 : 0);
     static constexpr uint32_t stage = W * kStage;
     static constexpr uint32_t stage_bytes = stage + 48;
     static constexpr uint32_t bitmap_words = stage_bytes / 32 + 2;     // one bit per stage byte (+ the word a window may spill into)
-    static constexpr int ctas_per_sm = W >= 32 ? 1 : 32 / W;
+    static constexpr int ctas_per_sm = 32 / W > 0 ? 32 / W : 1;
 };
+// barrier among the executing warps only (the checksum warp never takes part)
+template <int W> __device__ __forceinline__ void exec_sync()
+{
+    if constexpr (ExecCta<W>::hash) asm volatile("bar.sync 1, %0;" ::"n"(W * 32) : "memory");
+    else __syncthreads();
+}
 
 // stage bytes [o, o + nb) are stored: publish them (release: the byte stores above are visible to whoever sees the bits)
 __device__ __forceinline__ void bm_mark(uint32_t* bm, uint32_t o, uint32_t nb)
@@ -646,6 +654,18 @@ __device__ __forceinline__ void group_copy(uint8_t* dst, const uint8_t* src, uin
     }
 }
 
+// After a barrier among the executing warps: the frame's bytes below `upto` are in HBM, tell whoever hashes the frame --
+// the CTA's own checksum warp (shared memory) or, for W = 32, the frame's checksum CTA on another SM (global memory).
+struct ExecProg { volatile unsigned long long* s; unsigned long long* g; };
+template <int W> __device__ __forceinline__ void exec_publish(const ExecProg& prog, uint64_t upto, uint32_t tid)
+{
+    if constexpr (ExecCta<W>::hash) {
+        if (tid == 0) { __threadfence_block(); *prog.s = upto; }
+    } else if constexpr (W == 32) {
+        if (tid == 0 && prog.g) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(prog.g), "l"((unsigned long long)upto) : "memory");
+    }
+}
+
 // One sequence that does not fit the stage, copied by the whole CTA straight to HBM (arguments CTA-uniform).
 // Every byte below dst is readable on entry (barrier after the previous flush).
 template <int W>
@@ -653,7 +673,7 @@ __device__ __forceinline__ void cta_big_sequence(uint8_t* dst, const uint8_t* li
 {
     constexpr uint32_t T = W * 32;
     group_copy(dst, lit, ll, tid, T);
-    __syncthreads();
+    exec_sync<W>();
     uint8_t* m = dst + ll;
     if (off != 0) {                                          // 0: flagged corrupt by the caller
         const uint8_t* s = m - off;
@@ -661,17 +681,17 @@ __device__ __forceinline__ void cta_big_sequence(uint8_t* dst, const uint8_t* li
             for (uint32_t i = 0; i < ml; i += 16 * T) {
                 const uint32_t nb = min(16u, ml > i + 16 * tid ? ml - i - 16 * tid : 0u);
                 for (uint32_t k = 0; k < nb; k++) m[i + 16 * tid + k] = s[i + 16 * tid + k];
-                __syncthreads();
+                exec_sync<W>();
             }
         } else {                                             // periodic with period `off`; the period lies below m: written
             for (uint32_t i = tid; i < ml; i += T) m[i] = s[i % off];
         }
     }
-    __syncthreads();
+    exec_sync<W>();
 }
 
 template <int W>
-__device__ __forceinline__ void exec_block_cta(uint8_t* stage, uint32_t* bm, uint32_t* cnt, const Block& b,
+__device__ __forceinline__ void exec_block_cta(uint8_t* stage, uint32_t* bm, uint32_t* cnt, const ExecProg& prog, const Block& b,
                                                const uint64_t* __restrict__ sq, uint8_t* g0, uint64_t done, int& status, uint32_t tid)
 {
     constexpr uint32_t T = W * 32, kCtaStage = ExecCta<W>::stage;
@@ -680,7 +700,7 @@ __device__ __forceinline__ void exec_block_cta(uint8_t* stage, uint32_t* bm, uin
     const uint8_t* __restrict__ lit = b.lit;
     const uint32_t in0 = b.rep_in[0], in1 = b.rep_in[1], in2 = b.rep_in[2];
     for (uint32_t i = tid; i < ExecCta<W>::bitmap_words; i += T) bm[i] = 0;
-    __syncthreads();
+    exec_sync<W>();
     uint32_t Ecarry = 0, LEcarry = 0;                            // CTA-uniform
     uint64_t rcur = tid < nseq ? __ldg(sq + tid) : 0;            // the round's records; the next round's are loaded a round early
     uint64_t rprev = (lane == 0 && warp > 0 && tid <= nseq) ? __ldg(sq + tid - 1) : 0;   // record before a warp's first one
@@ -705,10 +725,10 @@ __device__ __forceinline__ void exec_block_cta(uint8_t* stage, uint32_t* bm, uin
         if (Elast - gS > kCtaStage) {
             const uint32_t fit = __ballot_sync(kFull, tid < nv && E - gS <= kCtaStage);
             if (lane == 0) cnt[warp] = (uint32_t)__popc(fit);
-            __syncthreads();
+            exec_sync<W>();
             n = 0;
             for (int w = 0; w < W; w++) n += cnt[w];
-            __syncthreads();
+            exec_sync<W>();
         }
         if (n == 0) {                                            // sequence g alone is larger than the stage
             const uint64_t r0 = __ldg(sq + g);
@@ -716,6 +736,7 @@ __device__ __forceinline__ void exec_block_cta(uint8_t* stage, uint32_t* bm, uin
             uint32_t off0 = off_resolve(rec_off(r0), in0, in1, in2);
             if ((uint64_t)off0 > done + M0) off0 = 0;
             cta_big_sequence<W>(g0 + gS, lit + LEcarry, LE0 - LEcarry, E0 - M0, off0, tid);
+            exec_publish<W>(prog, done + E0, tid);
             Ecarry = E0; LEcarry = LE0;
             g += 1;
             rcur = g + tid < nseq ? __ldg(sq + g + tid) : 0;
@@ -772,7 +793,7 @@ __device__ __forceinline__ void exec_block_cta(uint8_t* stage, uint32_t* bm, uin
                 if (!__any_sync(kFull, moved)) __nanosleep(32);   // every unfinished lane waits for another warp
             }
         }
-        __syncthreads();
+        exec_sync<W>();
         // ---- 3. flush stage[a .. a + (gE - gS)) -> g0 + gS: head bytes, aligned 16-byte body, tail bytes
         {
             const uint32_t nby = gE - gS;
@@ -785,7 +806,8 @@ __device__ __forceinline__ void exec_block_cta(uint8_t* stage, uint32_t* bm, uin
             if (tail0 + tid < nby) gd[tail0 + tid] = stage[a + tail0 + tid];
             for (uint32_t i = tid; i < ExecCta<W>::bitmap_words; i += T) bm[i] = 0;
         }
-        __syncthreads();
+        exec_sync<W>();
+        exec_publish<W>(prog, done + gE, tid);
         Ecarry = gE; LEcarry = LEend;
         g += n;
         // the next round's match sources: ask for them now (see k_execute)
@@ -807,41 +829,155 @@ __device__ __forceinline__ void exec_block_cta(uint8_t* stage, uint32_t* bm, uin
     group_copy(g0 + Ecarry, lit + LEcarry, rsize - Ecarry, tid, T);
 }
 
+// Checksum beside the execution.  XXH64 is one serial multiply chain per frame (~40 cycles per 32-byte stripe, four
+// accumulators = four lanes), which costs as much as the LZ77 itself once a frame has many warps, and a separate pass
+// over a large frame is bound by HBM latency on top.  So the hash follows the executing warps through the frame: they
+// publish how far the frame is flushed (release), the hashing warp takes the stripes below that mark straight from L2
+// (acquire, ld.cg) and compares with the stored trailer at the end.
+//   W = 8, 16: a 9th / 17th warp of the CTA (it shares the SM's issue slots with the polling warps, so its loop is kept
+//              short: no software pipelining -- measured);
+//   W = 32:    when the batch has at most half as many frames as the GPU has SMs, a second CTA per frame on an SM of
+//              its own (all CTAs of the grid are resident, so waiting on each other is safe), at the full chain speed.
+__device__ __forceinline__ uint64_t ldcg64_any(const uint8_t* q)
+{
+    const uintptr_t a = (uintptr_t)q & ~(uintptr_t)7;
+    const uint32_t sh = (uint32_t)((uintptr_t)q & 7) * 8;
+    const uint64_t w0 = __ldcg((const unsigned long long*)a);
+    if (sh == 0) return w0;
+    const uint64_t w1 = __ldcg((const unsigned long long*)(a + 8));
+    return (w0 >> sh) | (w1 << (64 - sh));
+}
+// how far the frame is flushed (acquire: the bytes below the mark are visible; no fence, so loads in flight stay in flight)
+template <bool REMOTE> __device__ __forceinline__ uint64_t hash_peek(const ExecProg& prog)
+{
+    unsigned long long v;
+    if constexpr (REMOTE) asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(prog.g) : "memory");
+    else asm volatile("ld.acquire.cta.shared.u64 %0, [%1];" : "=l"(v) : "r"((uint32_t)__cvta_generic_to_shared((const void*)prog.s)) : "memory");
+    return v;
+}
+template <bool REMOTE> __device__ __forceinline__ uint64_t hash_wait(const ExecProg& prog, uint64_t need)
+{
+    uint64_t avail;
+    while ((avail = hash_peek<REMOTE>(prog)) < need) __nanosleep(100);
+    return avail;
+}
+template <bool REMOTE>
+__device__ __forceinline__ bool hash_frame(const ExecProg& prog, const uint8_t* p, uint64_t len, uint32_t stored, uint32_t lane)
+{
+    const uint32_t j = lane & 3;                                   // eight redundant groups of four accumulators
+    uint64_t acc = j == 0 ? XP1 + XP2 : (j == 1 ? XP2 : (j == 2 ? 0 : 0 - XP1));
+    const uint64_t stripes = len >> 5;
+    const uint8_t* q = p + 8 * j;
+    const bool aligned = ((uintptr_t)p & 7) == 0;
+    uint64_t cs = 0;
+    while (cs < stripes) {
+        uint64_t upto = min(hash_wait<REMOTE>(prog, (cs + 1) << 5) >> 5, stripes);
+        if (!aligned) {
+            for (; cs < upto; cs++) acc = xx_round(acc, ldcg64_any(q + 32 * cs));
+        } else if (REMOTE && upto - cs >= 64) {
+            // The data comes from L2 (~1000 cycles away), the chain takes ~40 cycles per stripe: keep 64 + 64 stripes in
+            // flight.  One load instruction of the warp fetches eight stripes (lane = stripe-in-group * 4 + accumulator,
+            // 256 contiguous bytes); a shuffle hands each word to its accumulator lane when its turn comes.
+            uint64_t cur[8], nxt[8];
+            const uint8_t* ql = p + 32 * (lane >> 2) + 8 * j;
+#pragma unroll
+            for (int k = 0; k < 8; k++) cur[k] = __ldcg((const unsigned long long*)(ql + 32 * (cs + 8 * k)));
+            for (;;) {
+                if (upto - cs < 128) upto = min(hash_peek<REMOTE>(prog) >> 5, stripes);
+                const bool more = upto - cs >= 128;
+                if (more) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) nxt[k] = __ldcg((const unsigned long long*)(ql + 32 * (cs + 64 + 8 * k)));
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+#pragma unroll
+                    for (int g = 0; g < 8; g++) acc = xx_round(acc, __shfl_sync(kFull, cur[k], g * 4 + j));
+                }
+                cs += 64;
+                if (!more) break;
+#pragma unroll
+                for (int k = 0; k < 8; k++) cur[k] = nxt[k];
+            }
+        } else {
+            for (; cs + 8 <= upto; cs += 8) {
+                uint64_t x[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) x[k] = __ldcg((const unsigned long long*)(q + 32 * (cs + k)));
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc = xx_round(acc, x[k]);
+            }
+            for (; cs < upto; cs++) acc = xx_round(acc, __ldcg((const unsigned long long*)(q + 32 * cs)));
+        }
+    }
+    hash_wait<REMOTE>(prog, len);
+    const uint64_t v1 = __shfl_sync(kFull, acc, 0), v2 = __shfl_sync(kFull, acc, 1), v3 = __shfl_sync(kFull, acc, 2), v4 = __shfl_sync(kFull, acc, 3);
+    return (uint32_t)xx_combine(v1, v2, v3, v4, p, len) == stored;
+}
+
+// gprog (W = 32 only): null, or one progress word per frame (zeroed): the grid is then 2 n_frames CTAs, CTA f executes
+// frame f and CTA n_frames + f hashes it.
 template <int W>
 __global__ void __launch_bounds__(ExecCta<W>::threads, ExecCta<W>::ctas_per_sm) k_execute_cta(Frame* frames, const Block* blocks, const Item* items,
                                                                                              const ItemOut* outs, const uint64_t* seqs,
-                                                                                             uint32_t n_frames, uint32_t* ticket)
+                                                                                             uint32_t n_frames, uint32_t* ticket, int verify,
+                                                                                             unsigned long long* gprog)
 {
-    constexpr uint32_t T = ExecCta<W>::threads;
+    constexpr uint32_t T = ExecCta<W>::exec_threads;
+    constexpr bool H = ExecCta<W>::hash;
     __shared__ __align__(16) uint8_t s_stage[ExecCta<W>::stage_bytes];
-    __shared__ uint32_t s_bm[ExecCta<W>::bitmap_words], s_cnt[W], s_f;
+    __shared__ uint32_t s_bm[ExecCta<W>::bitmap_words], s_cnt[W], s_f, s_bad;
+    __shared__ unsigned long long s_prog;
     const uint32_t tid = threadIdx.x;
+    const bool remote = W == 32 && gprog != nullptr;
+    if (remote && blockIdx.x >= n_frames) {                        // a checksum CTA: one warp works
+        if (tid >= 32) return;
+        const uint32_t f = blockIdx.x - n_frames;
+        Frame& fr = frames[f];
+        if (outs[fr.item].fail || !verify || !fr.has_checksum) return;
+        const ExecProg prog{ nullptr, gprog + f };
+        if (!hash_frame<true>(prog, items[fr.item].dst + fr.out_off, fr.out_size, fr.checksum, tid) && tid == 0)
+            atomicCAS(&fr.status, 0, FZG_E_CHECKSUM);             // an error found by the executing CTA wins, in either order
+        return;
+    }
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_f = atomicAdd(ticket, 1);
+        if (tid == 0) { s_f = remote ? blockIdx.x : atomicAdd(ticket, 1); s_prog = 0; s_bad = 0; }
         __syncthreads();
         const uint32_t f = s_f;
         if (f >= n_frames) return;
         Frame& fr = frames[f];
-        if (outs[fr.item].fail) continue;
+        const bool skip = outs[fr.item].fail;
+        const ExecProg prog{ &s_prog, remote ? gprog + f : nullptr };
         uint8_t* const fbase = items[fr.item].dst + fr.out_off;
-        uint64_t done = 0;
-        int status = 0;
-        for (uint32_t kb = 0; kb < fr.n_blocks; kb++) {
-            const Block& b = blocks[fr.first_block + kb];
-            uint8_t* const g0 = fbase + done;
-            const uint32_t rsize = b.rsize;
-            if (b.type == BT_RAW) group_copy(g0, b.src, rsize, tid, T);
-            else if (b.type == BT_RLE) {
-                const uint8_t v = b.src[0];
-                for (uint32_t i = tid; i < rsize; i += T) g0[i] = v;
-            } else if (b.nseq == 0) group_copy(g0, b.lit, rsize, tid, T);
-            else exec_block_cta<W>(s_stage, s_bm, s_cnt, b, seqs + b.seq_base, g0, done, status, tid);
-            __syncthreads();                   // later blocks read this one back (the window)
-            done += rsize;
+        if (skip) { }
+        else if (H && tid >= T) {                                  // the checksum warp
+            if (verify && fr.has_checksum && !hash_frame<false>(prog, fbase, fr.out_size, fr.checksum, tid & 31) && tid == T) s_bad = 1;
+        } else {
+            uint64_t done = 0;
+            int status = 0;
+            for (uint32_t kb = 0; kb < fr.n_blocks; kb++) {
+                const Block& b = blocks[fr.first_block + kb];
+                uint8_t* const g0 = fbase + done;
+                const uint32_t rsize = b.rsize;
+                if (b.type == BT_RAW) group_copy(g0, b.src, rsize, tid, T);
+                else if (b.type == BT_RLE) {
+                    const uint8_t v = b.src[0];
+                    for (uint32_t i = tid; i < rsize; i += T) g0[i] = v;
+                } else if (b.nseq == 0) group_copy(g0, b.lit, rsize, tid, T);
+                else exec_block_cta<W>(s_stage, s_bm, s_cnt, prog, b, seqs + b.seq_base, g0, done, status, tid);
+                exec_sync<W>();                    // later blocks read this one back (the window)
+                done += rsize;
+                exec_publish<W>(prog, done, tid);
+            }
+            status = __reduce_max_sync(kFull, status);
+            if ((tid & 31) == 0 && status) fr.status = status;      // plain store: overrides a checksum verdict
         }
-        status = __reduce_max_sync(kFull, status);
-        if ((tid & 31) == 0 && status) fr.status = status;
+        if constexpr (H) {
+            __syncthreads();
+            if (tid == 0 && s_bad && !fr.status) fr.status = FZG_E_CHECKSUM;
+        }
+        if (remote) return;
     }
 }
 
@@ -961,52 +1097,75 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
         while (prev.entropy_epoch.load(std::memory_order_acquire) < ctx->epoch) std::this_thread::yield();
         CK(cudaStreamWaitEvent(s, prev.ev_entropy, 0));
     }
+    // A small batch fills neither the literal stage's SMs nor the sequence stage's: the two do not depend on each other,
+    // so the literals run on a side stream beside tables / sequences / records (one file: 0.3 ms off the critical path).
+    using L1 = LitCfg<kHufLogCommon>; using L2 = LitCfg<kHufLogMax>;
+    const uint32_t lit_grid1 = (uint32_t)std::min<uint64_t>((n_hj + L1::groups - 1) / L1::groups, (uint64_t)g_sm_count);
+    const uint32_t lit_grid2 = (uint32_t)std::min<uint64_t>((n_hj + L2::groups - 1) / L2::groups, (uint64_t)g_sm_count);
+    const uint32_t seq_grid = (uint32_t)std::min<uint64_t>((n_sj + kSeqStreams - 1) / kSeqStreams, (uint64_t)g_sm_count);
+    const bool side = n_hj && n_sj && lit_grid1 + seq_grid <= (uint32_t)g_sm_count;
+    cudaStream_t sl = side ? c->side : s;
+    if (side) { CK(cudaEventRecord(c->ev_fork, s)); CK(cudaStreamWaitEvent(sl, c->ev_fork, 0)); }
     if (n_hj) {                                                      // tickets: [2] first launch, [3] deferred count, [4] second launch
-        using L1 = LitCfg<kHufLogCommon>; using L2 = LitCfg<kHufLogMax>;
         uint32_t* d_deferred = d_hj + n_hj + 1;
-        k_literals<kHufLogCommon><<<(uint32_t)std::min<uint64_t>((n_hj + L1::groups - 1) / L1::groups, (uint64_t)g_sm_count), L1::threads, L1::smem, s>>>(
-            d_blocks, d_hj, (uint32_t)n_hj, nullptr, d_tickets + 2, d_deferred, d_tickets + 3);
-        k_literals<kHufLogMax><<<(uint32_t)std::min<uint64_t>((n_hj + L2::groups - 1) / L2::groups, (uint64_t)g_sm_count), L2::threads, L2::smem, s>>>(
-            d_blocks, d_deferred, 0, d_tickets + 3, d_tickets + 4, nullptr, nullptr);
+        k_literals<kHufLogCommon><<<lit_grid1, L1::threads, L1::smem, sl>>>(d_blocks, d_hj, (uint32_t)n_hj, nullptr, d_tickets + 2, d_deferred, d_tickets + 3);
+        k_literals<kHufLogMax><<<lit_grid2, L2::threads, L2::smem, sl>>>(d_blocks, d_deferred, 0, d_tickets + 3, d_tickets + 4, nullptr, nullptr);
         launches += 2;
     }
+    if (side) CK(cudaEventRecord(c->ev_join, sl));
     mark();
     if (n_sj) { k_seq_tables<<<(uint32_t)((n_sj + kTabThreads - 1) / kTabThreads), kTabThreads, 0, s>>>(d_blocks, d_sj, (uint32_t)n_sj, d_tabs, d_hdrs); launches++; }
     mark();
     if (n_sj) {
-        const uint32_t grid = (uint32_t)std::min<uint64_t>((n_sj + kSeqStreams - 1) / kSeqStreams, (uint64_t)g_sm_count);
-        k_sequences<<<grid, kSeqThreads, kSeqSmem, s>>>(d_blocks, d_sj, (uint32_t)n_sj, d_seq, d_tickets, d_tabs, d_hdrs); launches++;
+        k_sequences<<<seq_grid, kSeqThreads, kSeqSmem, s>>>(d_blocks, d_sj, (uint32_t)n_sj, d_seq, d_tickets, d_tabs, d_hdrs); launches++;
     }
     mark();
     if (n_sj) { k_records<<<(uint32_t)((n_sj + kRecWarps - 1) / kRecWarps), kRecWarps * 32, 0, s>>>(d_blocks, d_frames, d_sj, (uint32_t)n_sj, d_seq, d_tabs, d_hdrs); launches++; }
     mark();
     signal.fire();
+    if (side) CK(cudaStreamWaitEvent(s, c->ev_join, 0));
     k_offsets<<<gi, tb, 0, s>>>(d_items, d_infos, d_bases, d_frames, d_blocks, d_outs, n); mark(); launches++;
+    bool checksum_done = false;                                          // the CTA kernels with a checksum warp verify XXH64 themselves
     if (n_frames) {
-        // warps per frame: as many as it takes to fill the GPU's 32 warp slots per SM with the frames of this batch
-        // (tools/exec_width_probe.py: 1 file 5.7 -> 0.8 ms at 32; 592 files 7.0 -> 2.4 ms at 8; 2368 files 8.5 -> 7.7 ms at 2;
-        // from ~4700 frames on one warp per frame wins: k_execute has fewer instructions per sequence than the dataflow kernel)
+        // Warps per frame, by batch shape (tools/exec_width_probe.py; ms for the whole pipeline on 1 MiB files, one warp
+        // per frame -> chosen width: 1 file 8.1 -> 2.4, 64 files 9.6 -> 2.6, 148 files 10.4 -> 3.3, 592 files 10.8 -> 4.9,
+        // 1184 files 11.7 -> 7.9; 16 x 64 MiB windowLog-23 frames 497 -> 59).  32 with a checksum CTA per frame while
+        // every CTA can have an SM of its own, 8 (checksum warp inside the CTA) up to two waves of CTAs, 2 up to ~2400
+        // frames; beyond that one warp per frame wins: k_execute has fewer instructions per sequence than the dataflow kernel.
         const int w_env = exec_warps_override();
-        int w = w_env;
-        if (!w) { w = 32; while (w > 1 && n_frames * (uint64_t)w > (uint64_t)g_sm_count * 32) w >>= 1; }
-        auto cta = [&](auto wc) {
+        const uint64_t sms = (uint64_t)g_sm_count;
+        const int w = w_env ? w_env : (n_frames * 2 <= sms ? 32 : (n_frames <= sms * 8 ? 8 : (n_frames <= sms * 16 ? 2 : 1)));
+        const int verify = (flags & FZG_NO_VERIFY_CHECKSUM) ? 0 : 1;
+        auto cta = [&](auto wc) -> int {
             constexpr int W = decltype(wc)::value;
-            const uint32_t grid = (uint32_t)std::min<uint64_t>(n_frames, (uint64_t)g_sm_count * ExecCta<W>::ctas_per_sm);
-            k_execute_cta<W><<<grid, ExecCta<W>::threads, 0, s>>>(d_frames, d_blocks, d_items, d_outs, d_seq, (uint32_t)n_frames, d_tickets + 1);
+            uint32_t grid = (uint32_t)std::min<uint64_t>(n_frames, (uint64_t)g_sm_count * ExecCta<W>::ctas_per_sm);
+            unsigned long long* gprog = nullptr;
+            if (W == 32 && verify && n_frames * 2 <= (uint64_t)g_sm_count) {      // a checksum CTA per frame, every CTA on an SM of its own
+                int r = c->d_prog.reserve(n_frames * 8);
+                if (r) return r;
+                gprog = (unsigned long long*)c->d_prog.p;
+                CK(cudaMemsetAsync(gprog, 0, n_frames * 8, s));
+                grid = (uint32_t)n_frames * 2;
+                checksum_done = true;
+            }
+            k_execute_cta<W><<<grid, ExecCta<W>::threads, 0, s>>>(d_frames, d_blocks, d_items, d_outs, d_seq, (uint32_t)n_frames, d_tickets + 1, verify, gprog);
+            if (ExecCta<W>::hash) checksum_done = true;
+            return 0;
         };
         if (w == 1) {
             const uint32_t grid = (uint32_t)std::min<uint64_t>((n_frames + kExecWarps - 1) / kExecWarps, (uint64_t)g_sm_count * kExecCtasPerSm);
             k_execute<<<grid, kExecWarps * 32, 0, s>>>(d_frames, d_blocks, d_items, d_outs, d_seq, (uint32_t)n_frames, d_tickets + 1);
         }
-        else if (w == 2) cta(std::integral_constant<int, 2>{});
-        else if (w == 4) cta(std::integral_constant<int, 4>{});
-        else if (w == 8) cta(std::integral_constant<int, 8>{});
-        else if (w == 16) cta(std::integral_constant<int, 16>{});
-        else cta(std::integral_constant<int, 32>{});
+        else if (w == 2) rc = cta(std::integral_constant<int, 2>{});
+        else if (w == 4) rc = cta(std::integral_constant<int, 4>{});
+        else if (w == 8) rc = cta(std::integral_constant<int, 8>{});
+        else if (w == 16) rc = cta(std::integral_constant<int, 16>{});
+        else rc = cta(std::integral_constant<int, 32>{});
+        if (rc) return rc;
         launches++;
     }
     mark();
-    if (n_frames && !(flags & FZG_NO_VERIFY_CHECKSUM)) { k_checksum<<<(uint32_t)((n_frames * 4 + 127) / 128), 128, 0, s>>>(d_frames, d_items, d_outs, (uint32_t)n_frames); launches++; }
+    if (n_frames && !(flags & FZG_NO_VERIFY_CHECKSUM) && !checksum_done) { k_checksum<<<(uint32_t)((n_frames * 4 + 127) / 128), 128, 0, s>>>(d_frames, d_items, d_outs, (uint32_t)n_frames); launches++; }
     mark();
     k_finish<<<gi, tb, 0, s>>>(d_infos, d_bases, d_frames, d_outs, h_outs, n); launches++;
     if (!prof) ev = 11;

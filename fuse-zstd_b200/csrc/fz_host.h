@@ -46,10 +46,12 @@ struct FzPinBuf {
 struct FzLane {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[16] = {};
-    FzDevBuf d_infos, d_bases, d_outs, d_totals, d_frames, d_blocks, d_seq_jobs, d_huf_jobs, d_lit, d_seq, d_seq_tabs, d_seq_hdrs;
+    FzDevBuf d_infos, d_bases, d_outs, d_totals, d_frames, d_blocks, d_seq_jobs, d_huf_jobs, d_lit, d_seq, d_seq_tabs, d_seq_hdrs, d_prog;
     FzPinBuf h_totals;
     fzg_timing_t timing = {};
     cudaEvent_t ev_entropy = nullptr;      // recorded after this lane's entropy stages (literals, sequences, records)
+    cudaStream_t side = nullptr;           // small batches: the literal stage runs here, beside the sequence stages
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::atomic<uint64_t> entropy_epoch{ 0 };   // call number whose ev_entropy has been enqueued
 };
 constexpr int kMaxLanes = 4;
