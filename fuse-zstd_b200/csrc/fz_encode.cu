@@ -75,7 +75,7 @@ constexpr uint32_t kScrBytes = kScrSeqSec + kEncChunkMax + kEncChunkMax / 2 + 10
 FZ_HD uint64_t eseq_pack(uint32_t ll, uint32_t ml, uint32_t off) { return (uint64_t)ll | ((uint64_t)ml << 18) | ((uint64_t)off << 36); }
 FZ_HD uint32_t eseq_ll(uint64_t r) { return (uint32_t)r & 0x3FFFFu; }
 FZ_HD uint32_t eseq_ml(uint64_t r) { return (uint32_t)(r >> 18) & 0x3FFFFu; }
-FZ_HD uint32_t eseq_off(uint64_t r) { return (uint32_t)(r >> 36); }
+FZ_HD uint32_t eseq_off(uint64_t r) { return (uint32_t)(r >> 36); }   // Offset_Value (repeat code 1..3, or distance + 3)
 
 __device__ __forceinline__ uint64_t ld8u(const uint8_t* g)   // 8 bytes at any alignment (may read up to 15 bytes past g)
 {
@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(kEncMatchWarps * 32) k_enc_match(EncChunk* chu
         for (uint32_t i = lane; i < (1u << kEncHashLog); i += 32) table[i] = 0;
         __syncwarp();
         uint32_t anchor = 0, cur = 0, nseq = 0, nlit = 0;
+        uint32_t rep0 = 1, rep1 = 4, rep2 = 8;                              // repeat-offset history of a frame's first block (RFC 8878 3.1.1.5)
         // positions whose 8-byte probe would run past the chunk are left to the trailing literals
         const uint32_t limit = size >= 16 ? size - 12 : 0;
         for (uint32_t base = 0; base < limit; base += 32) {
@@ -160,7 +161,20 @@ __global__ void __launch_bounds__(kEncMatchWarps * 32) k_enc_match(EncChunk* chu
                 if (pl >= cur) {
                     const uint32_t ll = pl - anchor;
                     for (uint32_t i = lane; i < ll; i += 32) lit[nlit + i] = src[anchor + i];
-                    if (lane == 0) seq[nseq] = eseq_pack(ll, ml, off);
+                    // Offset_Value: 1..3 name an entry of the history (shifted by one when the literal run is empty, where 3
+                    // means rep0 - 1), anything else is the distance + 3.  Structured text repeats its distances, and a
+                    // repeat code costs 2-3 bits against ~16 for a distance.
+                    uint32_t ov = off + 3;
+                    const uint32_t r0 = rep0, r1 = rep1, r2 = rep2;
+                    if (ll) {
+                        if (off == r0) ov = 1;
+                        else if (off == r1) { ov = 2; rep0 = r1; rep1 = r0; }
+                        else { if (off == r2) ov = 3; rep0 = off; rep1 = r0; rep2 = r1; }
+                    } else {
+                        if (off == r1) { ov = 1; rep0 = r1; rep1 = r0; }
+                        else { if (off == r2) ov = 2; else if (off == r0 - 1 && off) ov = 3; rep0 = off; rep1 = r0; rep2 = r1; }
+                    }
+                    if (lane == 0) seq[nseq] = eseq_pack(ll, ml, ov);
                     nseq++; nlit += ll;
                     anchor = cur = pl + ml;
                 }
@@ -411,7 +425,7 @@ __global__ void __launch_bounds__(kSeqEncWarps * 32) k_enc_seq(EncChunk* chunks,
         for (uint32_t i = lane; i < nseq; i += 32) {
             const uint64_t r = seq[i];
             atomicAdd(&T.hist[0][ll_code(eseq_ll(r))], 1u);
-            atomicAdd(&T.hist[1][highbit(eseq_off(r) + 3)], 1u);
+            atomicAdd(&T.hist[1][highbit(eseq_off(r))], 1u);
             atomicAdd(&T.hist[2][ml_code(eseq_ml(r) - 3)], 1u);
         }
         __syncwarp();
@@ -476,7 +490,7 @@ __global__ void __launch_bounds__(kSeqEncWarps * 32) k_enc_seq(EncChunk* chunks,
             uint32_t codes = 0, lens = 0, ofx = 0;
             if (lane < cnt) {
                 const uint64_t r = seq[hi - 1 - lane];
-                const uint32_t ll = eseq_ll(r), mlb = eseq_ml(r) - 3, ofv = eseq_off(r) + 3;
+                const uint32_t ll = eseq_ll(r), mlb = eseq_ml(r) - 3, ofv = eseq_off(r);
                 const uint32_t lc = ll_code(ll), mc = ml_code(mlb), oc = (uint32_t)highbit(ofv);
                 codes = lc | (mc << 8) | (oc << 16) | ((uint32_t)K.ll_bits[lc] << 22) | ((uint32_t)K.ml_bits[mc] << 27);
                 lens = (ll - K.ll_base[lc]) | ((mlb + 3 - K.ml_base[mc]) << 16);
