@@ -133,11 +133,11 @@ static inline size_t al16(size_t v) { return (v + 15) & ~(size_t)15; }
 
 // ---------------------------------------------------------------------------------- batched decode / encode
 // Device-resident batches run as one launch sequence.  Host-resident batches are cut into chunks of
-// ~2 GiB of (input + output) and pipelined on three streams: while chunk c is decoded, chunk c+1 crosses PCIe
+// ~512 MiB of (input + output) and pipelined on three streams: while chunk c is decoded, chunk c+1 crosses PCIe
 // host->device and chunk c-1 device->host, so the call costs about max(PCIe, kernels) instead of their sum.
 static size_t chunk_bytes()                             // (input + output) bytes per chunk of a host-resident batch
 {
-    static const size_t v = [] { const char* e = getenv("FZG_CHUNK_MB"); return e && atoi(e) > 0 ? (size_t)atoi(e) << 20 : (size_t)2 << 30; }();
+    static const size_t v = [] { const char* e = getenv("FZG_CHUNK_MB"); return e && atoi(e) > 0 ? (size_t)atoi(e) << 20 : (size_t)512 << 20; }();
     return v;
 }
 

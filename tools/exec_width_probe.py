@@ -31,6 +31,7 @@ def pack(blobs):
 
 
 def run(tag, d_src, off, lens, d_dst, size, n, digest, widths, reps=5):
+    reps = int(os.environ.get("PROBE_REPS", reps))      # 1 under ncu
     sp = (d_src.data_ptr() + off[:n]).astype(np.uint64)
     dp = (d_dst.data_ptr() + np.arange(n, dtype=np.uint64) * np.uint64(size)).astype(np.uint64)
     sl = np.asarray(lens[:n], dtype=np.uint64); dc = np.full(n, size, dtype=np.uint64)

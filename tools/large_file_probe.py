@@ -1,6 +1,7 @@
 """Config 4 in small: a few LARGE single-frame files (level 3, windowLog 23 = 8 MiB window, matches reach across dozens of
-blocks), device-resident batched decode.  A frame is executed by ONE warp (LZ77 is a chain), so this shape is bound by
-frames in flight, not by the GPU: the number to quote next to config 2.   usage: large_file_probe.py [files] [MiB per file]"""
+blocks), device-resident batched decode.  With so few frames each one is executed by a CTA of 32 warps with a checksum
+CTA beside it (k_execute_cta, DESIGN.md section 2 "Few frames"); FZG_EXEC_W=1 gives the one-warp-per-frame figure.
+usage: large_file_probe.py [files] [MiB per file]"""
 import importlib, os, sys, time, hashlib
 from concurrent.futures import ThreadPoolExecutor
 import numpy as np, torch
