@@ -79,7 +79,7 @@ extern "C" void fzg_shutdown(void)
     for (FzCtx* c : g_ctx) {
         cudaSetDevice(c->dev);
         cudaStreamSynchronize(c->stream);
-        FzDevBuf* db[] = { &c->d_stage_src, &c->d_stage_dst, &c->e_items, &c->e_outs, &c->e_work, &c->d_outs, &c->d_totals };
+        FzDevBuf* db[] = { &c->d_stage_src, &c->d_stage_dst, &c->e_items, &c->e_outs, &c->e_work, &c->e_tab, &c->d_outs, &c->d_totals };
         for (auto* b : db) b->release();
         FzPinBuf* pb[] = { &c->h_items, &c->h_outs, &c->h_totals, &c->h_stage_src, &c->h_stage_dst, &c->e_chunks_h, &c->e_first_h };
         for (auto* b : pb) b->release();

@@ -51,6 +51,19 @@ constexpr uint32_t kEncMatchWarps = FZ_ENC_MATCH_WARPS;      // warps (= chunks 
 #ifndef FZ_ENC_LAZY
 #define FZ_ENC_LAZY 1
 #endif
+// Level >= 3: the matcher keeps a SECOND table, 2^kEncLongLog 16-bit entries per warp keyed by an 8-byte hash, in global memory
+// (i.e. in L2: 64 KB per warp, ~1800 warps resident), and hashes 5 bytes instead of 4 for the shared-memory table: 128 Ki
+// positions per chunk want more than 8 Ki slots.  Measured (256 x 4 MiB JSON): ratio 2.40 -> 2.63 (x1.26 -> x1.145 of libzstd
+// level 3's bytes) for 16.5 -> ~12.5 GB/s; both tables in L2 cost twice the L2 transactions for the same ratio (every 2-byte
+// table access is a 32-byte sector transaction, which is what bounds the stage then).  Levels 1-2 keep the single table.
+#ifndef FZ_ENC_LONGLOG
+#define FZ_ENC_LONGLOG 15
+#endif
+#ifndef FZ_ENC_PREFETCH
+#define FZ_ENC_PREFETCH 1
+#endif
+constexpr uint32_t kEncLongLog = FZ_ENC_LONGLOG;
+constexpr uint32_t kEncLongBytes = 2u << kEncLongLog;          // the long table of one warp
 constexpr uint32_t kHufMaxLen = 11;
 
 struct EncChunk {
@@ -88,11 +101,13 @@ __device__ __forceinline__ uint64_t ld8u(const uint8_t* g)   // 8 bytes at any a
 }
 
 // ------------------------------------------------------------------ LZ77 matching
-__global__ void __launch_bounds__(kEncMatchWarps * 32) k_enc_match(EncChunk* chunks, uint32_t n_chunks, uint32_t* ticket)
+template <bool LONG>
+__global__ void __launch_bounds__(kEncMatchWarps * 32) k_enc_match(EncChunk* chunks, uint32_t n_chunks, uint32_t* ticket, uint8_t* gtab)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t* table = (uint16_t*)smem + warp * (1u << kEncHashLog);
+    uint16_t* ltable = LONG ? (uint16_t*)(gtab + (size_t)(blockIdx.x * kEncMatchWarps + warp) * kEncLongBytes) : nullptr;
     for (;;) {
         uint32_t ci = 0;
         if (lane == 0) ci = atomicAdd(ticket, 1);
@@ -103,17 +118,42 @@ __global__ void __launch_bounds__(kEncMatchWarps * 32) k_enc_match(EncChunk* chu
         const uint32_t size = ch.size;
         uint8_t* lit = ch.scratch + kScrLit;
         uint64_t* seq = (uint64_t*)(ch.scratch + kScrSeq);
-        for (uint32_t i = lane; i < (1u << kEncHashLog); i += 32) table[i] = 0;
+        for (uint32_t i = lane; i < (1u << kEncHashLog) / 8; i += 32) ((uint4*)table)[i] = make_uint4(0, 0, 0, 0);
+        if constexpr (LONG) for (uint32_t i = lane; i < (1u << kEncLongLog) / 8; i += 32) ((uint4*)ltable)[i] = make_uint4(0, 0, 0, 0);
         __syncwarp();
         uint32_t anchor = 0, cur = 0, nseq = 0, nlit = 0;
         uint32_t rep0 = 1, rep1 = 4, rep2 = 8;                              // repeat-offset history of a frame's first block (RFC 8878 3.1.1.5)
         // positions whose 8-byte probe would run past the chunk are left to the trailing literals
         const uint32_t limit = size >= 16 ? size - 12 : 0;
+        // The step's 8 input bytes and (LONG) its long-table entries are loaded one step EARLY, so that neither load sits on
+        // the step's dependent chain (table -> candidate bytes -> extension).  An entry read early misses the positions the
+        // previous step inserts after the read: the candidate is then an older occurrence, still verified byte by byte.
+        uint64_t v_nx = 0; uint32_t hl_nx = 0, el_nx = 0;
+        if (lane < limit) {
+            v_nx = ld8u(src + lane);
+            if constexpr (LONG) { hl_nx = (uint32_t)((v_nx * 0x9E3779B185EBCA87ull) >> (64 - kEncLongLog)); el_nx = ltable[hl_nx]; }
+        }
         for (uint32_t base = 0; base < limit; base += 32) {
             const uint32_t p = base + lane;
             const bool in = p < limit;
-            uint64_t v = 0; uint32_t h = 0;
-            if (in) { v = ld8u(src + p); h = ((uint32_t)v * 2654435761u) >> (32 - kEncHashLog); }
+            const uint64_t v = in ? v_nx : 0; const uint32_t hl = hl_nx, el = el_nx;
+            uint32_t h = 0;
+            if (p + 32 < limit) {
+                v_nx = ld8u(src + p + 32);
+                if constexpr (LONG) { hl_nx = (uint32_t)((v_nx * 0x9E3779B185EBCA87ull) >> (64 - kEncLongLog)); el_nx = ltable[hl_nx]; }
+            }
+#if FZ_ENC_PREFETCH
+            if constexpr (LONG) {                                           // this step's long candidate: its bytes are needed ~100 instructions from now
+                if (in) {
+                    int32_t c = (int32_t)((p & ~0xFFFFu) | el); if (c >= (int32_t)p) c -= 65536;
+                    if (c >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + c));
+                }
+            }
+#endif
+            if (in) {
+                if constexpr (LONG) h = (uint32_t)(((v << 24) * 0x9E3779B185EBCA87ull) >> (64 - kEncHashLog));
+                else h = ((uint32_t)v * 2654435761u) >> (32 - kEncHashLog);
+            }
             // candidates: the nearest earlier lane of this step with the same hash, else the table
             const uint32_t same = __match_any_sync(0xFFFFFFFFu, in ? h : (0x80000000u | lane));
             const uint32_t below = same & ((1u << lane) - 1);
@@ -127,8 +167,27 @@ __global__ void __launch_bounds__(kEncMatchWarps * 32) k_enc_match(EncChunk* chu
                     cand = c;
                 }
             }
+            uint32_t samel = 0; int32_t candl = -1;
+            if constexpr (LONG) {                                           // the last position with the same 8 bytes (hashed)
+                samel = __match_any_sync(0xFFFFFFFFu, in ? hl : (0x80000000u | lane));
+                const uint32_t belowl = samel & ((1u << lane) - 1);
+                if (in && p >= cur) {
+                    if (belowl) candl = (int32_t)(base + (31 - __clz(belowl)));
+                    else { int32_t c = (int32_t)((p & ~0xFFFFu) | el); if (c >= (int32_t)p) c -= 65536; candl = c; }
+                }
+            }
             __syncwarp();
             if (in && (same >> lane) == 1) table[h] = (uint16_t)p;          // the highest lane of a group records it
+            if constexpr (LONG) {
+                if (in && (samel >> lane) == 1) ltable[hl] = (uint16_t)p;
+                // keep the candidate that shares the longer prefix of the first 8 bytes (the nearer one on a tie)
+                if (in && p >= cur) {
+                    const bool okl = candl >= 0 && p - (uint32_t)candl <= kEncMaxOff, oks = cand >= 0 && p - (uint32_t)cand <= kEncMaxOff;
+                    const uint64_t xl = okl ? ld8u(src + candl) ^ v : 1ull, xs = oks ? ld8u(src + cand) ^ v : 1ull;
+                    const uint32_t pl = xl ? (uint32_t)(__ffsll((long long)xl) - 1) >> 3 : 8u, ps = xs ? (uint32_t)(__ffsll((long long)xs) - 1) >> 3 : 8u;
+                    if (!oks || (okl && (pl > ps || (pl == ps && candl > cand)))) cand = okl ? candl : -1;
+                }
+            }
             // verify + extend (8 bytes per probe)
             uint32_t len = 0;
             if (in && p >= cur && cand >= 0 && p - (uint32_t)cand <= kEncMaxOff) {
@@ -627,7 +686,8 @@ size_t fzh_encode_bound(size_t src_len, size_t chunk)
 
 int fzh_encode_setup(void)
 {
-    CK(cudaFuncSetAttribute(k_enc_match, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncMatchWarps * (2 << kEncHashLog)));
+    CK(cudaFuncSetAttribute(k_enc_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncMatchWarps * (2 << kEncHashLog)));
+    CK(cudaFuncSetAttribute(k_enc_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncMatchWarps * (2 << kEncHashLog)));
     return 0;
 }
 
@@ -635,7 +695,8 @@ int fzh_encode_setup(void)
 // The per-chunk scratch is large (5.5 bytes per input byte in the worst case), so the chunks are processed in waves.
 int fzh_encode_run(FzCtx* c, uint32_t first, uint32_t n, int level, size_t chunk, int flags)
 {
-    (void)level;
+    // the reference passes 0..19, 0 = libzstd's default = 3 (src/main.rs:1237, 1283-1296): 1-2 select the single-table matcher
+    const bool long_table = !(level == 1 || level == 2);
     cudaStream_t s = c->stream;
     const bool prof = flags & FZG_PROFILE;
     c->timing = fzg_timing_t{};
@@ -700,7 +761,12 @@ int fzh_encode_run(FzCtx* c, uint32_t first, uint32_t n, int level, size_t chunk
     };
     auto run_wave = [&](uint64_t lo, uint32_t cnt, bool marks) -> int {   // match -> literals -> sequences for chunks [lo, lo + cnt)
         CK(cudaMemsetAsync(d_tickets, 0, 16, s));
-        k_enc_match<<<std::min<uint32_t>((cnt + kEncMatchWarps - 1) / kEncMatchWarps, 148 * ((200u << 10) / (kEncMatchWarps * (2u << kEncHashLog)))), kEncMatchWarps * 32, kEncMatchWarps * (2 << kEncHashLog), s>>>(d_chunks + lo, cnt, d_tickets);
+        const uint32_t match_ctas = std::min<uint32_t>((cnt + kEncMatchWarps - 1) / kEncMatchWarps, 148 * ((200u << 10) / (kEncMatchWarps * (2u << kEncHashLog))));
+        const uint32_t match_smem = kEncMatchWarps * (2 << kEncHashLog);
+        if (long_table) {
+            if (c->e_tab.reserve((size_t)match_ctas * kEncMatchWarps * kEncLongBytes)) return -12;
+            k_enc_match<true><<<match_ctas, kEncMatchWarps * 32, match_smem, s>>>(d_chunks + lo, cnt, d_tickets, (uint8_t*)c->e_tab.p);
+        } else k_enc_match<false><<<match_ctas, kEncMatchWarps * 32, match_smem, s>>>(d_chunks + lo, cnt, d_tickets, nullptr);
         if (check("k_enc_match")) return -5;
         if (marks) mark();
         k_enc_lit<<<std::min<uint32_t>((cnt + kLitWarps - 1) / kLitWarps, 148 * 8), kLitWarps * 32, 0, s>>>(d_chunks + lo, cnt, d_tickets + 1);

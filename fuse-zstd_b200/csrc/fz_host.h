@@ -70,7 +70,7 @@ struct FzCtx {
     FzDevBuf d_stage_src, d_stage_dst;
     FzPinBuf h_items, h_outs, h_totals, h_stage_src, h_stage_dst, e_chunks_h, e_first_h;
     // encoder scratch
-    FzDevBuf e_items, e_outs, e_work, d_outs, d_totals;
+    FzDevBuf e_items, e_outs, e_work, e_tab, d_outs, d_totals;
     fzg_timing_t timing = {};
 };
 

@@ -61,10 +61,12 @@ def test_empty_file_is_the_reference_frame():
     assert comp.hex() == "28b52ffd2400010000" "99e9d851"
 
 
-def test_round_trip_through_libzstd_oracle_and_cuda_decoder(ref, oracle, corpus):
+@pytest.mark.parametrize("level", [1, 3])
+def test_round_trip_through_libzstd_oracle_and_cuda_decoder(ref, oracle, corpus, level):
+    """level 1-2: one shared-memory hash table; level 0 / 3+: 5-byte + 8-byte hashes, the second table in L2"""
     cases = _inputs(corpus)
     names = sorted(cases)
-    res = codec.encode_batch([cases[n] for n in names])
+    res = codec.encode_batch([cases[n] for n in names], level=level)
     comps = []
     for n, (st, comp) in zip(names, res):
         assert st == 0, n
@@ -92,7 +94,8 @@ def test_checksum_is_present_and_checked(corpus, oracle):
 
 
 def test_ratio_against_libzstd_level3(ref, corpus):
-    """the stated bound: total bytes <= 1.35 x libzstd level 3 (reference-writer framing) on the JSON corpus"""
+    """the stated bound: total bytes <= 1.20 x libzstd level 3 (reference-writer framing) on the JSON corpus at the reference's
+    default level (measured x1.145); <= 1.35 x at level 1 (measured x1.26)"""
     if not ref.available:
         pytest.skip("system libzstd absent")
     n, size = 64, 1 << 20
@@ -103,7 +106,12 @@ def test_ratio_against_libzstd_level3(ref, corpus):
     theirs = sum(len(ref.writer_encode(plain[i].tobytes(), 3)) for i in range(n))
     ratio = ours / theirs
     print("\nencoder: %d bytes vs libzstd L3 %d bytes -> x%.3f ; ratio %.3f vs %.3f" % (ours, theirs, ratio, n * size / ours, n * size / theirs))
-    assert ratio <= 1.35
+    assert ratio <= 1.20
+    fast = codec.encode_batch([plain[i] for i in range(n)], level=1)
+    assert all(st == 0 for st, _ in fast)
+    ratio1 = sum(len(c) for _, c in fast) / theirs
+    print("level 1: x%.3f" % ratio1)
+    assert ratio < ratio1 <= 1.35
 
 
 def test_encoder_flow_through_fd_entry_points(ref, corpus):

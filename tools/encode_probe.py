@@ -5,6 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.ins
 codec = importlib.import_module("fuse-zstd_b200.codec"); corpus = importlib.import_module("fuse-zstd_b200.corpus")
 import pyoracle
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+level = int(sys.argv[2]) if len(sys.argv) > 2 else 3      # 1-2: single-table matcher, else the two-table one
 size = 4 << 20
 codec.init([0])
 plain = corpus.json_files(7000000, n, size, threads=os.cpu_count())
@@ -15,10 +16,10 @@ sp = [d_src.data_ptr() + i * size for i in range(n)]; dp = [d_dst.data_ptr() + i
 fl = codec.SRC_DEVICE | codec.DST_DEVICE | codec.PROFILE
 for it in range(4):
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    dl, st = codec.encode_batch_ptrs(0, sp, [size] * n, dp, [cap] * n, 3, 0, fl)
+    dl, st = codec.encode_batch_ptrs(0, sp, [size] * n, dp, [cap] * n, level, 0, fl)
     dt = time.perf_counter() - t0
     t = codec.last_timing(0)
-    print("encode %d x 4 MiB: %.1f ms wall, gpu %.1f ms -> %.1f GB/s in, ratio %.3f, stages %s" % (n, dt * 1e3, t["total_ms"], n * size / 1e9 / (t["total_ms"] / 1e3), n * size / dl.sum(), {k: round(v, 2) for k, v in list(t["stages"].items())[:5]}), file=sys.stderr)
+    print("level %d: encode %d x 4 MiB: %.1f ms wall, gpu %.1f ms -> %.1f GB/s in, ratio %.3f, stages %s" % (level, n, dt * 1e3, t["total_ms"], n * size / 1e9 / (t["total_ms"] / 1e3), n * size / dl.sum(), {k: round(v, 2) for k, v in list(t["stages"].items())[:5]}), file=sys.stderr)
 assert not st.any()
 R = pyoracle.Ref()
 if R.available:
