@@ -63,7 +63,8 @@ int fzg_decode_fd(int src_fd, int dst_fd, uint64_t shard_key, uint64_t* out_size
  * Replaces  Encoder::new(w, level) + set_pledged_src_size(Some(n)) + include_checksum(true) +
  *           io::copy + finish()                                       src/main.rs:781-791
  * Reads src_size bytes from src_fd (current offset), writes zstd frames to dst_fd.  level follows
- * src/main.rs:1233-1241 (0 => default 3).  Every frame carries Frame_Content_Size and the XXH64
+ * src/main.rs:1233-1241 (0 => default 3): 1 and 2 select the faster single-table matcher, every other
+ * value the two-table one.  Every frame carries Frame_Content_Size and the XXH64
  * content checksum; the output is a concatenation of independent frames that stock libzstd
  * (>= 1.0) decodes to the input.
  */
