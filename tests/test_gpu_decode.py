@@ -161,6 +161,25 @@ def test_window_and_multiframe(ref, corpus, exec_w):
         assert st == 0 and out == plain, i
 
 
+def test_unaligned_frames_and_their_checksums(ref, corpus, exec_w):
+    """concatenated frames of odd sizes: every frame after the first starts at an odd address of the output, which is the
+    unaligned path of the checksum that runs beside the execution (widths 8 and 32) and of k_checksum (1, 2); a flipped
+    trailer bit in the LAST frame must be reported as a checksum error, nothing else"""
+    if not ref.available:
+        pytest.skip("system libzstd absent")
+    j = corpus.json_file(991, 1 << 20).tobytes()
+    sizes = [1001, 77777, 131073, 33, 262147, 5]
+    parts, plain, o = [], b"", 0
+    for sz in sizes:
+        parts.append(ref.writer_encode(j[o:o + sz], 3)); plain += j[o:o + sz]; o += sz
+    good = b"".join(parts)
+    bad = bytearray(good); bad[-1] ^= 0x10
+    res = codec.decode_batch([good, bytes(bad), good], [len(plain)] * 3)
+    assert res[0][0] == 0 and res[0][1] == plain
+    assert res[1][0] == codec.E_CHECKSUM, codec.strerror(res[1][0])
+    assert res[2][0] == 0 and res[2][1] == plain
+
+
 def test_device_resident_batch(golden):
     """FZG_SRC_DEVICE | FZG_DST_DEVICE: what bench.py's `value` times"""
     import torch
