@@ -761,7 +761,9 @@ int fzh_encode_run(FzCtx* c, uint32_t first, uint32_t n, int level, size_t chunk
     };
     auto run_wave = [&](uint64_t lo, uint32_t cnt, bool marks) -> int {   // match -> literals -> sequences for chunks [lo, lo + cnt)
         CK(cudaMemsetAsync(d_tickets, 0, 16, s));
-        const uint32_t match_ctas = std::min<uint32_t>((cnt + kEncMatchWarps - 1) / kEncMatchWarps, 148 * ((200u << 10) / (kEncMatchWarps * (2u << kEncHashLog))));
+        static const uint32_t ctas_per_sm = [] { const char* e = getenv("FZG_ENC_CTAS_PER_SM"); const uint32_t full = (200u << 10) / (kEncMatchWarps * (2u << kEncHashLog));
+                                                 return e && atoi(e) > 0 ? std::min<uint32_t>((uint32_t)atoi(e), full) : full; }();
+        const uint32_t match_ctas = std::min<uint32_t>((cnt + kEncMatchWarps - 1) / kEncMatchWarps, 148 * ctas_per_sm);
         const uint32_t match_smem = kEncMatchWarps * (2 << kEncHashLog);
         if (long_table) {
             if (c->e_tab.reserve((size_t)match_ctas * kEncMatchWarps * kEncLongBytes)) return -12;
