@@ -721,7 +721,9 @@ int fzh_encode_run(FzCtx* c, uint32_t first, uint32_t n, int level, size_t chunk
     // in one pass; an item larger than a wave is sized wave by wave first and then regenerated and written (the stages
     // are deterministic).
     constexpr uint64_t kWaveChunks = 8192;
-    const uint64_t wave = std::min<uint64_t>(n_chunks, kWaveChunks);
+    const char* wave_env = getenv("FZG_ENC_WAVE_CHUNKS");              // tests: a small wave puts ordinary files on the two-pass path
+    const uint64_t wave_max = wave_env && atoi(wave_env) > 0 ? (uint64_t)atoi(wave_env) : kWaveChunks;
+    const uint64_t wave = std::min<uint64_t>(n_chunks, wave_max);
     if ((rc = c->e_work.reserve(wave * (uint64_t)kScrBytes))) return rc;
     EncChunk* hc = (EncChunk*)c->e_chunks_h.p;
     memcpy(c->e_first_h.p, first_chunk.data(), (n + 1) * 4);

@@ -205,6 +205,32 @@ def test_seek_table_and_partial_reads(corpus, ref, oracle):
     assert rc > 0
 
 
+@pytest.mark.parametrize("level", [1, 3])
+def test_file_larger_than_a_wave_two_pass_path(ref, oracle, corpus, level):
+    """a file with more chunks than a wave holds is sized wave by wave, then regenerated and written: the stages must produce the
+    same bytes both times (the matcher's tables, early loads and turn order included).  FZG_ENC_WAVE_CHUNKS=8 makes a 3 MiB file
+    (24 chunks) such a file; small neighbours share the call."""
+    plain = [corpus.json_file(4100 + i, s).tobytes() for i, s in enumerate([200000, (3 << 20) + 12345, 70000, (2 << 20) + 1])]
+    old = os.environ.get("FZG_ENC_WAVE_CHUNKS")
+    os.environ["FZG_ENC_WAVE_CHUNKS"] = "8"
+    try:
+        small = codec.encode_batch(plain, level=level)
+    finally:
+        if old is None:
+            os.environ.pop("FZG_ENC_WAVE_CHUNKS", None)
+        else:
+            os.environ["FZG_ENC_WAVE_CHUNKS"] = old
+    normal = codec.encode_batch(plain, level=level)
+    for p, (st, comp), (st2, comp2) in zip(plain, small, normal):
+        assert st == 0 and st2 == 0
+        assert comp == comp2, "the two-pass path and the single-pass path must agree byte for byte"
+        st_o, out_o = oracle.decode(comp, cap=len(p))
+        assert st_o == 0 and out_o == p
+        if ref.available:
+            st_r, out_r = ref.copy_decode(comp, len(p))
+            assert st_r == 0 and out_r == p
+
+
 def test_many_files_single_pass_waves(corpus):
     """more than one wave of chunks (8192 = 1 GiB of input): waves are cut at file boundaries, each sized and written in one pass"""
     n, size = 300, 4 << 20
