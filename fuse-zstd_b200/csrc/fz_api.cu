@@ -244,11 +244,15 @@ static int run_batch(bool encode, int device, size_t n, const void* const* src, 
     if (src_dev && dst_dev) {
         if ((rc = run(0, n, nullptr))) return rc;
     } else {
-        std::vector<size_t> cuts{ 0 };            // chunk boundaries: a small first chunk starts the device -> host stream early
+        // chunk boundaries: a small first chunk starts the device -> host stream early.  A chunk also wants enough ITEMS: a frame
+        // is a serial chain (~1 GB/s at 32 warps per frame), so a chunk of one or two large files would run at that speed while
+        // 64 of them side by side cost the same time -- large files make large chunks (up to 16 x the byte target).
+        std::vector<size_t> cuts{ 0 };
         size_t target = chunk_bytes() / 4;
-        for (size_t i = 0, bytes = 0; i < n; i++) {
-            bytes += dst_cap[i] + src_len[i];
-            if (bytes >= target && i + 1 < n) { cuts.push_back(i + 1); bytes = 0; target = chunk_bytes(); }
+        constexpr size_t kMinItems = 64;
+        for (size_t i = 0, bytes = 0, items = 0; i < n; i++) {
+            bytes += dst_cap[i] + src_len[i]; items++;
+            if (((bytes >= target && (items >= kMinItems || encode)) || bytes >= 16 * chunk_bytes()) && i + 1 < n) { cuts.push_back(i + 1); bytes = 0; items = 0; target = chunk_bytes(); }
         }
         cuts.push_back(n);
         const size_t nchunks = cuts.size() - 1;

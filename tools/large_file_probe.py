@@ -1,7 +1,7 @@
 """Config 4 in small: a few LARGE single-frame files (level 3, windowLog 23 = 8 MiB window, matches reach across dozens of
 blocks), device-resident batched decode.  With so few frames each one is executed by a CTA of 32 warps with a checksum
 CTA beside it (k_execute_cta, DESIGN.md section 2 "Few frames"); FZG_EXEC_W=1 gives the one-warp-per-frame figure.
-usage: large_file_probe.py [files] [MiB per file]"""
+usage: large_file_probe.py [files] [MiB per file] [host]      (host: also through pinned HOST buffers, the e2e path)"""
 import importlib, os, sys, time, hashlib
 from concurrent.futures import ThreadPoolExecutor
 import numpy as np, torch
@@ -33,3 +33,10 @@ assert not st.any() and (dl == size).all()
 k = min(n, 2)
 assert hashlib.sha256(d_dst[:k * size].cpu().numpy().tobytes()).digest() == hashlib.sha256(plain[:k].tobytes()).digest()
 print("bytes verified", file=sys.stderr)
+if len(sys.argv) > 3 and sys.argv[3] == "host":
+    h_src = torch.from_numpy(packed).pin_memory(); h_dst = torch.empty(n * size, dtype=torch.uint8, pin_memory=True)
+    sp = (h_src.data_ptr() + off).astype(np.uint64); dp = (h_dst.data_ptr() + np.arange(n, dtype=np.uint64) * np.uint64(size)).astype(np.uint64)
+    for it in range(3):
+        t0 = time.perf_counter(); dl, st = codec.decode_batch_ptrs(0, sp, sl, dp, dc, 0); dt = time.perf_counter() - t0
+        print("host buffers: %.1f ms -> %.1f GB/s e2e" % (dt * 1e3, n * size / 1e9 / dt), file=sys.stderr)
+    assert not st.any() and hashlib.sha256(h_dst[:k * size].numpy().tobytes()).digest() == hashlib.sha256(plain[:k].tobytes()).digest()
