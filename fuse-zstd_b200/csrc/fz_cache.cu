@@ -176,12 +176,22 @@ extern "C" int fzg_cache_prefetch(int device, const char* const* paths, const ui
         if (cudaMallocHost((void**)&g_arena, want) != cudaSuccess) { cudaGetLastError(); g_arena = nullptr; for (int fd : fds) if (fd >= 0) close(fd); return -ENOMEM; }
         g_arena_cap = want;
     }
-    for (size_t j = 0; j < m; j++) {
-        if (fds[j] < 0) continue;
-        size_t got = 0;
-        while (got < clen[j]) { const ssize_t r = read(fds[j], g_arena + coff[j] + got, clen[j] - got); if (r < 0 && errno == EINTR) continue; if (r <= 0) break; got += (size_t)r; }
-        close(fds[j]);
-        if (got != clen[j]) fds[j] = -1;
+    // the reads are page-cache copies (~6 GB/s on one thread: 14 ms for a directory of 256 x 1 MiB): a few threads share them
+    auto read_range = [&](size_t lo, size_t hi) {
+        for (size_t j = lo; j < hi; j++) {
+            if (fds[j] < 0) continue;
+            size_t got = 0;
+            while (got < clen[j]) { const ssize_t r = read(fds[j], g_arena + coff[j] + got, clen[j] - got); if (r < 0 && errno == EINTR) continue; if (r <= 0) break; got += (size_t)r; }
+            close(fds[j]);
+            if (got != clen[j]) fds[j] = -1;
+        }
+    };
+    {
+        const size_t nt = ctotal >= (8u << 20) ? std::min<size_t>(4, m) : 1;
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < nt; t++) th.emplace_back(read_range, m * t / nt, m * (t + 1) / nt);
+        read_range(0, m / nt);
+        for (auto& x : th) x.join();
     }
     // ---- sizes from the frame headers; the results are contiguous in one pinned slab (ONE device -> host copy)
     std::vector<const void*> sp; std::vector<void*> dp; std::vector<size_t> sl, dc, which, doff;
