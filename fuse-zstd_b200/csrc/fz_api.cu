@@ -58,7 +58,8 @@ extern "C" int fzg_init(const int* devices, int n_devices)
             CKR(cudaStreamCreateWithFlags(&c->lane[l].stream, cudaStreamNonBlocking));
             for (auto& e : c->lane[l].ev) CKR(cudaEventCreate(&e));
             CKR(cudaEventCreateWithFlags(&c->lane[l].ev_entropy, cudaEventDisableTiming));
-            CKR(cudaStreamCreateWithFlags(&c->lane[l].side, cudaStreamNonBlocking));
+            { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);      // lowest priority: its CTAs take what the main stream leaves
+              CKR(cudaStreamCreateWithPriority(&c->lane[l].side, cudaStreamNonBlocking, lo)); }
             CKR(cudaEventCreateWithFlags(&c->lane[l].ev_fork, cudaEventDisableTiming));
             CKR(cudaEventCreateWithFlags(&c->lane[l].ev_join, cudaEventDisableTiming));
         }

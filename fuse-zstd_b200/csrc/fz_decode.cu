@@ -1126,6 +1126,7 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
     if (side) CK(cudaStreamWaitEvent(s, c->ev_join, 0));
     k_offsets<<<gi, tb, 0, s>>>(d_items, d_infos, d_bases, d_frames, d_blocks, d_outs, n); mark(); launches++;
     bool checksum_done = false;                                          // the CTA kernels with a checksum warp verify XXH64 themselves
+    uint32_t n_tail = 0;                                                 // frames at the end of the batch executed (and hashed) by k_execute_cta<8>
     if (n_frames) {
         // Warps per frame, by batch shape (tools/exec_width_probe.py; ms for the whole pipeline on 1 MiB files, one warp
         // per frame -> chosen width: 1 file 8.1 -> 2.4, 64 files 9.6 -> 2.6, 148 files 10.4 -> 3.3, 592 files 10.8 -> 4.9,
@@ -1153,8 +1154,30 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
             return 0;
         };
         if (w == 1) {
-            const uint32_t grid = (uint32_t)std::min<uint64_t>((n_frames + kExecWarps - 1) / kExecWarps, (uint64_t)g_sm_count * kExecCtasPerSm);
-            k_execute<<<grid, kExecWarps * 32, 0, s>>>(d_frames, d_blocks, d_items, d_outs, d_seq, (uint32_t)n_frames, d_tickets + 1);
+            // One warp per frame runs the batch in waves of 32 x SMs frames (equal-sized files finish in step), and a last wave with
+            // few frames costs a whole frame time (5.7 ms per MiB) on a nearly empty GPU: 10 000 files = 2 waves + 528 frames took
+            // 27.3 ms against 24.6 ms for 9 472.  So the frames beyond the last full wave, when they are few (up to 1/8 of the batch),
+            // go to k_execute_cta<8> on the low-priority side stream, launched right after k_execute: its CTAs find no room until
+            // k_execute's start to retire and then fill what the drain leaves idle (they hash their frames themselves; k_checksum
+            // covers the rest).  Measured: 10 000 files 27.3 -> 26.0 ms with 625 frames moved (416 or 500, still three waves:
+            // 27.4 / 27.2; 833, 1 250, 1 667: 26.4 / 26.9 / 27.8); 5 000 files 17.0 -> 13.4 ms; moving frames out of a batch of
+            // exactly one wave (4 736) costs 4 %, out of a well-filled last wave (6 000, 7 200 files) changes nothing.
+            static const bool tail_on = [] { const char* e = getenv("FZG_EXEC_TAIL"); return !e || atoi(e) != 0; }();
+            if (tail_on && !w_env && n_frames >= sms * 32) {
+                const uint64_t rest = n_frames % (sms * 32);
+                if (rest && rest <= n_frames / 8) n_tail = (uint32_t)(rest + n_frames / 128);       // a well-filled last wave is left alone
+            }
+            const uint32_t n1 = (uint32_t)n_frames - n_tail;
+            if (n_tail) CK(cudaEventRecord(c->ev_fork, s));
+            const uint32_t grid = (uint32_t)std::min<uint64_t>((n1 + kExecWarps - 1) / kExecWarps, (uint64_t)g_sm_count * kExecCtasPerSm);
+            k_execute<<<grid, kExecWarps * 32, 0, s>>>(d_frames, d_blocks, d_items, d_outs, d_seq, n1, d_tickets + 1);
+            if (n_tail) {
+                CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+                k_execute_cta<8><<<std::min<uint32_t>(n_tail, (uint32_t)sms * ExecCta<8>::ctas_per_sm), ExecCta<8>::threads, 0, c->side>>>(d_frames + n1, d_blocks, d_items, d_outs, d_seq, n_tail, d_tickets + 5, verify, nullptr);
+                CK(cudaEventRecord(c->ev_join, c->side));
+                CK(cudaStreamWaitEvent(s, c->ev_join, 0));
+                launches++;
+            }
         }
         else if (w == 2) rc = cta(std::integral_constant<int, 2>{});
         else if (w == 4) rc = cta(std::integral_constant<int, 4>{});
@@ -1165,7 +1188,7 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
         launches++;
     }
     mark();
-    if (n_frames && !(flags & FZG_NO_VERIFY_CHECKSUM) && !checksum_done) { k_checksum<<<(uint32_t)((n_frames * 4 + 127) / 128), 128, 0, s>>>(d_frames, d_items, d_outs, (uint32_t)n_frames); launches++; }
+    if (n_frames > n_tail && !(flags & FZG_NO_VERIFY_CHECKSUM) && !checksum_done) { k_checksum<<<(uint32_t)(((n_frames - n_tail) * 4 + 127) / 128), 128, 0, s>>>(d_frames, d_items, d_outs, (uint32_t)(n_frames - n_tail)); launches++; }
     mark();
     k_finish<<<gi, tb, 0, s>>>(d_infos, d_bases, d_frames, d_outs, h_outs, n); launches++;
     if (!prof) ev = 11;

@@ -180,6 +180,30 @@ def test_unaligned_frames_and_their_checksums(ref, corpus, exec_w):
     assert res[2][0] == 0 and res[2][1] == plain
 
 
+def test_many_frames_split_between_the_two_executors(ref, corpus):
+    """more than 32 x SMs frames: one warp per frame for most of the batch, the last 1/16 on the side stream with 8 warps per
+    frame and the checksum beside them (the drain of k_execute); every output compared, one bad trailer in each part found"""
+    if not ref.available:
+        pytest.skip("system libzstd absent")
+    n, size = 5200, 24 * 1024
+    plain = corpus.json_files(700000, n, size)
+    cap = ref.bound(size) + 64
+    comp = np.empty((n, cap), dtype=np.uint8)
+    sp = np.array([plain[i].ctypes.data for i in range(n)], dtype=np.uint64); sl = np.full(n, size, dtype=np.uint64)
+    dp = np.array([comp[i].ctypes.data for i in range(n)], dtype=np.uint64); dc = np.full(n, cap, dtype=np.uint64)
+    _, ol, st = ref.batch(2, os.cpu_count() or 1, sp, sl, dp, dc, 3)
+    assert not st.any()
+    for bad in (17, n - 5):                                   # one in k_execute's part, one in the tail
+        comp[bad, int(ol[bad]) - 1] ^= 0x01
+    out = np.zeros((n, size), dtype=np.uint8)
+    dl, st = codec.decode_batch_ptrs(0, dp, ol, [out[i].ctypes.data for i in range(n)], [size] * n, 0)
+    want = np.zeros(n, dtype=np.int32); want[17] = want[n - 5] = codec.E_CHECKSUM
+    assert (st == want).all(), np.nonzero(st != want)[0][:10]
+    ok = np.ones(n, dtype=bool); ok[17] = ok[n - 5] = False
+    assert (dl[ok] == size).all()
+    assert hashlib.sha256(out[ok].tobytes()).digest() == hashlib.sha256(plain[ok].tobytes()).digest()
+
+
 def test_device_resident_batch(golden):
     """FZG_SRC_DEVICE | FZG_DST_DEVICE: what bench.py's `value` times"""
     import torch
