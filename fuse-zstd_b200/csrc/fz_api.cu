@@ -13,6 +13,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <new>
 #include <thread>
 #include <vector>
 
@@ -76,6 +77,7 @@ extern "C" int fzg_init(const int* devices, int n_devices)
 
 extern "C" void fzg_shutdown(void)
 {
+    fzg_cache_drain();                                 // no prefetch thread may be inside a CUDA call while the contexts go
     std::lock_guard<std::mutex> lk(g_mu);
     for (FzCtx* c : g_ctx) {
         cudaSetDevice(c->dev);
@@ -197,7 +199,11 @@ static int run_batch(bool encode, int device, size_t n, const void* const* src, 
         dst_contig = is_pinned(dst[0]);
         for (size_t i = 0; i + 1 < n && dst_contig; i++) dst_contig = (uint8_t*)dst[i] + dst_cap[i] == (uint8_t*)dst[i + 1];
         size_t total = 0;
-        for (size_t i = 0; i < n; i++) total += dst_contig ? dst_cap[i] : al16(dst_cap[i]) + 16;
+        for (size_t i = 0; i < n; i++) {
+            const size_t add = dst_contig ? dst_cap[i] : al16(dst_cap[i]) + 16;
+            if (add < dst_cap[i] || total > SIZE_MAX / 2 - add) return -EINVAL;      // capacities that do not add up to a size
+            total += add;
+        }
         if ((rc = c->d_stage_dst.reserve(total + 64))) return rc;
         uint8_t* dbase = (uint8_t*)c->d_stage_dst.p; size_t off = 0;
         for (size_t i = 0; i < n; i++) { items[i].dst = dbase + off; off += dst_contig ? dst_cap[i] : al16(dst_cap[i]) + 16; }
@@ -304,22 +310,29 @@ static int run_batch(bool encode, int device, size_t n, const void* const* src, 
 extern "C" int fzg_decode_batch(int device, size_t n, const void* const* src, const size_t* src_len, void* const* dst,
                                 const size_t* dst_cap, size_t* dst_len, int* status, int flags)
 {
-    return run_batch(false, device, n, src, src_len, dst, dst_cap, dst_len, status, flags, 0, 0);
+    try { return run_batch(false, device, n, src, src_len, dst, dst_cap, dst_len, status, flags, 0, 0); }
+    catch (const std::bad_alloc&) { return -ENOMEM; }
+    catch (...) { return -EIO; }
 }
 
 extern "C" int fzg_encode_batch(int device, size_t n, const void* const* src, const size_t* src_len, void* const* dst,
                                 const size_t* dst_cap, size_t* dst_len, int* status, int level, size_t chunk_size, int flags)
 {
-    return run_batch(true, device, n, src, src_len, dst, dst_cap, dst_len, status, flags, level, chunk_size);
+    try { return run_batch(true, device, n, src, src_len, dst, dst_cap, dst_len, status, flags, level, chunk_size); }
+    catch (const std::bad_alloc&) { return -ENOMEM; }
+    catch (...) { return -EIO; }
 }
 
 extern "C" size_t fzg_encode_bound(size_t src_len, size_t chunk_size) { return fzh_encode_bound(src_len, chunk_size); }
 
 // ---------------------------------------------------------------------------------- host header walk
-extern "C" int fzg_frame_info(const void* src_, size_t len, uint64_t* content_size, uint64_t* compressed_size)
+// Walks frame, skippable-frame and block headers on the host.  content = sum of Frame_Content_Size (UINT64_MAX when a
+// frame does not declare it), bound = the most the blocks can regenerate: Block_Size for Raw / RLE blocks, Block_Maximum_Size
+// for a Compressed one (RFC 8878 3.1.1.2.4) -- what a caller may allocate whatever the (untrusted) FCS field says.
+static int walk_headers(const uint8_t* src, size_t len, uint64_t* content, uint64_t* compressed, uint64_t* bound_out)
 {
-    const uint8_t* src = (const uint8_t*)src_;
-    uint64_t ip = 0, total = 0; bool unknown = false;
+    uint64_t ip = 0, total = 0, bound = 0; bool unknown = false, over = false;
+    auto add = [&](uint64_t& acc, uint64_t v) { if (acc > UINT64_MAX - v) over = true; else acc += v; };
     while (ip < len) {
         if (len - ip < 4) return FZG_E_TRUNCATED;
         uint32_t magic = rd32u(src + ip);
@@ -333,7 +346,8 @@ extern "C" int fzg_frame_info(const void* src_, size_t len, uint64_t* content_si
         FrameHdr h; int st = parse_frame_header(src + ip, len - ip, h);
         if (st) return st;
         ip += h.hsize;
-        if (h.has_fcs) total += h.fcs; else unknown = true;
+        if (h.has_fcs) add(total, h.fcs); else unknown = true;
+        const uint64_t block_max = h.window < kBlockMax ? h.window : kBlockMax;
         for (;;) {
             if (len - ip < 3) return FZG_E_TRUNCATED;
             uint32_t bh = rd24(src + ip); ip += 3;
@@ -341,14 +355,22 @@ extern "C" int fzg_frame_info(const void* src_, size_t len, uint64_t* content_si
             if (type == 3) return FZG_E_CORRUPT;
             uint64_t adv = type == BT_RLE ? 1 : bsize;
             if (len - ip < adv) return FZG_E_TRUNCATED;
+            add(bound, type == BT_COMPRESSED ? block_max : (uint64_t)bsize);
             ip += adv;
             if (bh & 1) break;
         }
         if (h.checksum) { if (len - ip < 4) return FZG_E_TRUNCATED; ip += 4; }
     }
-    if (content_size) *content_size = unknown ? UINT64_MAX : total;
-    if (compressed_size) *compressed_size = ip;
+    if (over) return FZG_E_UNSUPPORTED;                    // sizes that do not fit 64 bits: nothing real
+    if (content) *content = unknown ? UINT64_MAX : total;
+    if (compressed) *compressed = ip;
+    if (bound_out) *bound_out = bound;
     return FZG_OK;
+}
+
+extern "C" int fzg_frame_info(const void* src_, size_t len, uint64_t* content_size, uint64_t* compressed_size)
+{
+    return walk_headers((const uint8_t*)src_, len, content_size, compressed_size, nullptr);
 }
 
 // ---------------------------------------------------------------------------------- fd entry points
@@ -378,7 +400,10 @@ static int write_all(int fd, const uint8_t* p, size_t n)
     return 0;
 }
 
-extern "C" int fzg_decode_fd(int src_fd, int dst_fd, uint64_t shard_key, uint64_t* out_size)
+// The reference streams through constant memory (copy_decode, src/main.rs:463-467) and fails ONE open with EFAULT on a bad
+// file (:467); this entry point buffers whole files, so nothing in the (untrusted) input may size an allocation beyond what
+// its block headers can regenerate, and no exception may cross the C boundary (the fzfs daemon is one thread).
+static int decode_fd_impl(int src_fd, int dst_fd, uint64_t shard_key, uint64_t* out_size)
 {
     int rc = ensure_init(); if (rc) return rc;
     FzCtx* c = ctx_for_key(shard_key);
@@ -387,25 +412,31 @@ extern "C" int fzg_decode_fd(int src_fd, int dst_fd, uint64_t shard_key, uint64_
     if ((rc = read_all(src_fd, in, 0))) return rc;
     if (out_size) *out_size = 0;
     if (in.empty()) return 0;                      // empty input: success, empty output
-    uint64_t content = 0, csize = 0;
-    int st = fzg_frame_info(in.data(), in.size(), &content, &csize);
+    uint64_t content = 0, csize = 0, bound = 0;
+    int st = walk_headers(in.data(), in.size(), &content, &csize, &bound);
     if (st) return st;
-    uint64_t cap = content == UINT64_MAX ? (uint64_t)in.size() * 8 + (1 << 20) : content;
-    for (int attempt = 0; attempt < 6; attempt++) {
-        std::vector<uint8_t> out(cap ? cap : 1);
-        const void* sp = in.data(); size_t sl = in.size(); void* dp = out.data(); size_t dc = cap, dl = 0; int ist = 0;
-        rc = fzg_decode_batch(c->dev, 1, &sp, &sl, &dp, &dc, &dl, &ist, 0);
-        if (rc) return rc;
-        if (ist == FZG_E_DSTSIZE && content == UINT64_MAX) { cap *= 4; continue; }
-        if (ist) return ist;
-        if ((rc = write_all(dst_fd, out.data(), dl))) return rc;
-        if (out_size) *out_size = dl;
-        return 0;
-    }
-    return FZG_E_DSTSIZE;
+    if (content != UINT64_MAX && content > bound) return FZG_E_FCS;        // an FCS its blocks cannot reach: libzstd fails the frame too
+    const uint64_t cap = content == UINT64_MAX ? bound : content;         // unknown size: the block walk bounds it, one attempt
+    static const uint64_t cap_max = [] { const char* e = getenv("FZG_MAX_DECODE_BYTES"); return e ? strtoull(e, nullptr, 0) : (uint64_t)1 << 40; }();
+    if (cap > cap_max || cap > (uint64_t)SIZE_MAX / 2) return -ENOMEM;
+    uint8_t* out = (uint8_t*)malloc(cap ? cap : 1);
+    if (!out) return -ENOMEM;
+    const void* sp = in.data(); size_t sl = in.size(); void* dp = out; size_t dc = cap, dl = 0; int ist = 0;
+    rc = fzg_decode_batch(c->dev, 1, &sp, &sl, &dp, &dc, &dl, &ist, 0);
+    if (!rc && ist) rc = ist;
+    if (!rc) rc = write_all(dst_fd, out, dl);
+    if (!rc && out_size) *out_size = dl;
+    free(out);
+    return rc;
+}
+extern "C" int fzg_decode_fd(int src_fd, int dst_fd, uint64_t shard_key, uint64_t* out_size)
+{
+    try { return decode_fd_impl(src_fd, dst_fd, shard_key, out_size); }
+    catch (const std::bad_alloc&) { return -ENOMEM; }
+    catch (...) { return -EIO; }
 }
 
-extern "C" int fzg_encode_fd(int src_fd, int dst_fd, int level, uint64_t src_size, uint64_t shard_key, uint64_t* out_size)
+static int encode_fd_impl(int src_fd, int dst_fd, int level, uint64_t src_size, uint64_t shard_key, uint64_t* out_size)
 {
     int rc = ensure_init(); if (rc) return rc;
     FzCtx* c = ctx_for_key(shard_key);
@@ -423,6 +454,13 @@ extern "C" int fzg_encode_fd(int src_fd, int dst_fd, int level, uint64_t src_siz
     if ((rc = write_all(dst_fd, out.data(), dl))) return rc;
     if (out_size) *out_size = dl;
     return 0;
+}
+
+extern "C" int fzg_encode_fd(int src_fd, int dst_fd, int level, uint64_t src_size, uint64_t shard_key, uint64_t* out_size)
+{
+    try { return encode_fd_impl(src_fd, dst_fd, level, src_size, shard_key, out_size); }
+    catch (const std::bad_alloc&) { return -ENOMEM; }
+    catch (...) { return -EIO; }
 }
 
 // ---------------------------------------------------------------------------------- seek table, partial reads
@@ -495,7 +533,9 @@ extern "C" int fzg_decode_range(int device, const void* src, size_t len, uint64_
     FzCtx* c = ctx_for(device);
     if (!c) return -ENODEV;
     auto rd = [&](uint8_t* buf, size_t n, uint64_t at) -> int { if (at + n > len) return -EIO; memcpy(buf, (const uint8_t*)src + at, n); return 0; };
-    return decode_range(c, rd, len, offset, size, dst, got);
+    try { return decode_range(c, rd, len, offset, size, dst, got); }
+    catch (const std::bad_alloc&) { return -ENOMEM; }
+    catch (...) { return -EIO; }
 }
 
 extern "C" int fzg_decode_range_fd(int src_fd, uint64_t shard_key, uint64_t offset, size_t size, void* dst, size_t* got)
@@ -511,7 +551,9 @@ extern "C" int fzg_decode_range_fd(int src_fd, uint64_t shard_key, uint64_t offs
         while (done < n) { const ssize_t r = pread(src_fd, buf + done, n - done, (off_t)(at + done)); if (r < 0) { if (errno == EINTR) continue; return -errno; } if (r == 0) return -EIO; done += (size_t)r; }
         return 0;
     };
-    return decode_range(c, rd, (uint64_t)end, offset, size, dst, got);
+    try { return decode_range(c, rd, (uint64_t)end, offset, size, dst, got); }
+    catch (const std::bad_alloc&) { return -ENOMEM; }
+    catch (...) { return -EIO; }
 }
 
 // ---------------------------------------------------------------------------------- misc

@@ -193,39 +193,62 @@ extern "C" int fzg_cache_prefetch(int device, const char* const* paths, const ui
         read_range(0, m / nt);
         for (auto& x : th) x.join();
     }
-    // ---- sizes from the frame headers; the results are contiguous in one pinned slab (ONE device -> host copy)
-    std::vector<const void*> sp; std::vector<void*> dp; std::vector<size_t> sl, dc, which, doff;
-    size_t dtotal = 0;
+    // ---- sizes from the frame headers.  The results of a GROUP of files are contiguous in one pinned slab (one device -> host
+    // copy per group); a group never asks for more than a slab holds, so a directory larger than a slab is decoded as
+    // several batches instead of not at all (the slabs are reserved at mount time with kSlabBytes each).
+    size_t limit;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        limit = g_capacity < kSlabBytes ? g_capacity : kSlabBytes;
+        for (const Slab& sl : g_slabs) if (sl.cap > limit && sl.cap <= g_capacity) limit = sl.cap;
+    }
+    std::vector<size_t> which, dcs;                        // files with a declared size that the cache can hold
     for (size_t j = 0; j < m; j++) {
         if (fds[j] < 0) continue;
         uint64_t content = 0, csize = 0;
         if (fzg_frame_info(g_arena + coff[j], clen[j], &content, &csize) != 0 || content == UINT64_MAX) continue;   // unknown size: left to open()
-        if (dtotal + content > g_capacity) break;              // a prefetch never asks for more than the cache holds
-        which.push_back(j); doff.push_back(dtotal); dc.push_back(content); dtotal += content;
+        if (content > limit) continue;                     // larger than a slab (or a lying header): left to open(), the others go on
+        which.push_back(j); dcs.push_back((size_t)content);
     }
-    const size_t k = which.size();
-    if (k == 0) return 0;
-    int si; size_t base = 0; uint8_t* slab_p;
-    { std::lock_guard<std::mutex> lk(g_mu); si = alloc_locked(dtotal, &base); if (si < 0) return -ENOMEM; slab_p = g_slabs[si].p; }
-    for (size_t a = 0; a < k; a++) { sp.push_back(g_arena + coff[which[a]]); sl.push_back(clen[which[a]]); dp.push_back(slab_p + base + doff[a]); }
-    std::vector<size_t> dl(k); std::vector<int> st(k);
-    const double t_read = ms();
-    const int rc = fzg_decode_batch(device, k, sp.data(), sl.data(), dp.data(), dc.data(), dl.data(), st.data(), 0);
-    if (rc) return rc;
-    if (trace) fprintf(stderr, "fzgpu: prefetch of %zu files: read + size + alloc %.1f ms, decode batch %.1f ms\n", k, t_read, ms() - t_read);
     int added = 0;
-    std::unique_lock<std::mutex> lk(g_mu);
-    for (size_t a = 0; a < k; a++) {
-        if (st[a] != 0) continue;
-        const size_t j = which[a]; const uint64_t key = keys[todo[j]];
-        if (g_map.count(key) || si >= (int)g_slabs.size()) continue;
-        Entry e; e.slab = si; e.off = base + doff[a]; e.n = dl[a]; e.id = g_next_id++; e.src_size = (uint64_t)sts[j].st_size; e.mtime_ns = mtime_ns(sts[j]);
-        g_bytes += e.n;
-        g_slabs[si].keys.push_back(key);
-        g_map.emplace(key, e);
-        added++; g_prefetched++;
+    for (size_t g0 = 0; g0 < which.size();) {
+        size_t g1 = g0, dtotal = 0;
+        std::vector<size_t> doff;
+        while (g1 < which.size() && dcs[g1] <= limit - dtotal) { doff.push_back(dtotal); dtotal += dcs[g1]; g1++; }
+        const size_t k = g1 - g0;                          // >= 1: every file fits a slab by itself
+        int si; size_t base = 0; uint8_t* slab_p;
+        { std::lock_guard<std::mutex> lk(g_mu); si = alloc_locked(dtotal ? dtotal : 1, &base); if (si < 0) return added ? added : -ENOMEM; slab_p = g_slabs[si].p; }
+        std::vector<const void*> sp(k); std::vector<void*> dp(k); std::vector<size_t> sl(k), dc(k), dl(k); std::vector<int> st(k);
+        for (size_t a = 0; a < k; a++) { const size_t j = which[g0 + a]; sp[a] = g_arena + coff[j]; sl[a] = clen[j]; dp[a] = slab_p + base + doff[a]; dc[a] = dcs[g0 + a]; }
+        const double t_read = ms();
+        const int rc = fzg_decode_batch(device, k, sp.data(), sl.data(), dp.data(), dc.data(), dl.data(), st.data(), 0);
+        if (rc) return added ? added : rc;
+        if (trace) fprintf(stderr, "fzgpu: prefetch of %zu files (%zu bytes): up to here %.1f ms, decode batch %.1f ms\n", k, dtotal, t_read, ms() - t_read);
+        std::unique_lock<std::mutex> lk(g_mu);
+        for (size_t a = 0; a < k; a++) {
+            if (st[a] != 0) continue;
+            const size_t j = which[g0 + a]; const uint64_t key = keys[todo[j]];
+            if (g_map.count(key) || si >= (int)g_slabs.size()) continue;
+            Entry e; e.slab = si; e.off = base + doff[a]; e.n = dl[a]; e.id = g_next_id++; e.src_size = (uint64_t)sts[j].st_size; e.mtime_ns = mtime_ns(sts[j]);
+            g_bytes += e.n;
+            g_slabs[si].keys.push_back(key);
+            g_map.emplace(key, e);
+            added++; g_prefetched++;
+        }
+        g0 = g1;
     }
     return added;
+}
+
+// Prefetch threads in flight: fzg_cache_drain (fzg_shutdown, the fzfs daemon before it exits) waits for them, so that none
+// is inside a CUDA call when the process tears the runtime down.
+static std::mutex g_async_mu;
+static std::condition_variable g_async_cv;
+static int g_async_live = 0;
+extern "C" void fzg_cache_drain(void)
+{
+    std::unique_lock<std::mutex> lk(g_async_mu);
+    g_async_cv.wait(lk, [] { return g_async_live == 0; });
 }
 
 // The same, on a detached thread: the FUSE loop (one thread, src/main.rs:1325) does not wait for the batch.
@@ -234,10 +257,13 @@ extern "C" int fzg_cache_prefetch_async(int device, const char* const* paths, co
     if (!paths || !keys) return -EINVAL;
     std::vector<std::string> p(n); std::vector<uint64_t> k(keys, keys + n);
     for (size_t i = 0; i < n; i++) p[i] = paths[i];
+    { std::lock_guard<std::mutex> lk(g_async_mu); g_async_live++; }
     std::thread([device, p = std::move(p), k = std::move(k)]() {
         std::vector<const char*> c(p.size());
         for (size_t i = 0; i < p.size(); i++) c[i] = p[i].c_str();
-        fzg_cache_prefetch(device, c.data(), k.data(), c.size());
+        try { fzg_cache_prefetch(device, c.data(), k.data(), c.size()); } catch (...) { }
+        { std::lock_guard<std::mutex> lk(g_async_mu); g_async_live--; }
+        g_async_cv.notify_all();
     }).detach();
     return 0;
 }

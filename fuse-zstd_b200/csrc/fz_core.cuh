@@ -323,7 +323,7 @@ FZ_HD void walk_item(uint32_t item_idx, const Item& it, ItemInfo& info, const It
                 }
                 if (nseq) {
                     if (FILL) { b.seq_base = base->seq + n_seq; seq_jobs[base->seq_job + nsj] = gb; }
-                    n_seq += (nseq + 3u) & ~3u; nsj++;          // records of a block start on a 32-byte boundary (256-bit stores)
+                    n_seq += (nseq + 1u + 3u) & ~3u; nsj++;     // + the tail record (k_records); records of a block start on a 32-byte boundary (256-bit stores)
                 }
                 if (lh.type != LT_RAW) { if (FILL) huf_jobs[base->huf_job + nhj] = gb; nhj++; }
             }

@@ -22,6 +22,7 @@
 
 #include "fz_host.h"
 #include "fz_kernels.cuh"
+#include "fz_exec_tile.cuh"
 
 namespace fz {
 
@@ -315,7 +316,10 @@ __global__ void __launch_bounds__(kRecWarps * 32) k_records(Block* blocks, const
     }
     const uint32_t rsize = Ebase + (lit_regen - LEbase);
     if (bad || rsize > block_max) { if (lane == 0) b.status = FZG_E_CORRUPT; return; }
-    if (lane == 0) { b.rsize = rsize; b.rep_out[0] = rep0; b.rep_out[1] = rep1; b.rep_out[2] = rep2; }
+    if (lane == 0) {
+        b.rsize = rsize; b.rep_out[0] = rep0; b.rep_out[1] = rep1; b.rep_out[2] = rep2;
+        sq[nseq] = rec_pack(rsize, lit_regen, 1);        // the TAIL record: the literals after the last sequence as one more literal run (k_execute_tile)
+    }
 }
 
 // ------------------------------------------------------------------ offsets
@@ -364,13 +368,6 @@ constexpr uint32_t kStage = FZ_EXEC_STAGE;                            // bytes o
 constexpr uint32_t kStageBytes = kStage + 48;                // + alignment slack (the stage mirrors the low 4 address bits) + load slack
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 
-__device__ __forceinline__ uint64_t funnel8(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t byte_shift)
-{
-    if (byte_shift >= 4) { x0 = x1; x1 = x2; x2 = x3; }
-    const uint32_t r = (byte_shift & 3) * 8;
-    const uint32_t lo = __funnelshift_r(x0, x1, r), hi = __funnelshift_r(x1, x2, r);
-    return (uint64_t)lo | ((uint64_t)hi << 32);
-}
 // nb (1..8) bytes starting at generic address g (HBM or shared memory); never touches an 8-byte word that holds no wanted byte
 __device__ __forceinline__ uint64_t ld8_any(const uint8_t* g, uint32_t nb)
 {
@@ -641,17 +638,6 @@ __device__ __forceinline__ uint32_t bm_ready(const uint32_t* bm, uint32_t o)
     asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(w1) : "r"(a0 + 4) : "memory");
     const uint32_t bits = __funnelshift_r(w0, w1, o & 31u);
     return (uint32_t)__ffs((int)~bits) - 1u;                     // all 32 ready: 0xFFFFFFFF, larger than any request
-}
-
-__device__ __forceinline__ void group_copy(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t tid, uint32_t nthr)
-{
-    if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) {
-        const uint32_t nv = n >> 4;
-        for (uint32_t i = tid; i < nv; i += nthr) ((uint4*)dst)[i] = ((const uint4*)src)[i];
-        for (uint32_t i = (nv << 4) + tid; i < n; i += nthr) dst[i] = src[i];
-    } else {
-        for (uint32_t i = tid; i < n; i += nthr) dst[i] = src[i];
-    }
 }
 
 // After a barrier among the executing warps: the frame's bytes below `upto` are in HBM, tell whoever hashes the frame --
@@ -1017,9 +1003,10 @@ const char* fzh_decode_stage_name(int s) { return s >= 0 && s < 11 ? kStageNames
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "fzgpu: %s failed: %s (%s:%d)\n", #x, cudaGetErrorString(e_), __FILE__, __LINE__); return -5 /*-EIO*/; } } while (0)
 
 static int g_sm_count = 148;
-static int exec_warps_override()          // FZG_EXEC_W: warps per frame in the execute stage (1, 2, 4, 8, 16, 32; else by batch shape); read per call (tests)
-{
+static int exec_warps_override()          // FZG_EXEC_W: the execute kernel, read per call (tests).  t128 / t256 / t512 / t1024: k_execute_tile with that many
+{                                         // threads per frame (returned as -threads); 1: k_execute (warp per frame); 2..32: k_execute_cta<W>; else by batch shape
     const char* e = getenv("FZG_EXEC_W");
+    if (e && e[0] == 't') { const int t = atoi(e + 1); return (t == 128 || t == 256 || t == 512 || t == 1024) ? -t : 0; }
     const int v = e ? atoi(e) : 0;
     return (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ? v : 0;
 }
@@ -1029,6 +1016,10 @@ int fzh_decode_setup(void)
     CK(cudaFuncSetAttribute(k_literals<kHufLogCommon>, cudaFuncAttributeMaxDynamicSharedMemorySize, LitCfg<kHufLogCommon>::smem));
     CK(cudaFuncSetAttribute(k_literals<kHufLogMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, LitCfg<kHufLogMax>::smem));
     CK(cudaFuncSetAttribute(k_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqSmem));
+    CK(cudaFuncSetAttribute(k_execute_tile<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<128>::smem));
+    CK(cudaFuncSetAttribute(k_execute_tile<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<256>::smem));
+    CK(cudaFuncSetAttribute(k_execute_tile<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<512>::smem));
+    CK(cudaFuncSetAttribute(k_execute_tile<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<1024>::smem));
     int dev = 0; CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
     return 0;
@@ -1135,7 +1126,9 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
         // frames; beyond that one warp per frame wins: k_execute has fewer instructions per sequence than the dataflow kernel.
         const int w_env = exec_warps_override();
         const uint64_t sms = (uint64_t)g_sm_count;
-        const int w = w_env ? w_env : (n_frames * 2 <= sms ? 32 : (n_frames <= sms * 8 ? 8 : (n_frames <= sms * 16 ? 2 : 1)));
+        // default: k_execute_tile (a CTA per frame, output-centric); threads per frame by batch shape: enough CTAs to fill the SMs
+        // at 256 threads, else wider CTAs for the few frames there are.  FZG_EXEC_W selects the round-1 kernels instead.
+        const int w = w_env ? w_env : (n_frames >= sms * 4 ? -256 : (n_frames >= sms * 2 ? -512 : -1024));
         const int verify = (flags & FZG_NO_VERIFY_CHECKSUM) ? 0 : 1;
         auto cta = [&](auto wc) -> int {
             constexpr int W = decltype(wc)::value;
@@ -1153,7 +1146,16 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
             if (ExecCta<W>::hash) checksum_done = true;
             return 0;
         };
-        if (w == 1) {
+        auto tile = [&](auto tc) {
+            constexpr int T = decltype(tc)::value;
+            const uint32_t grid = (uint32_t)std::min<uint64_t>(n_frames, (uint64_t)g_sm_count * TileCfg<T>::ctas_per_sm);
+            k_execute_tile<T><<<grid, T, TileCfg<T>::smem, s>>>(d_frames, d_blocks, d_items, d_outs, d_seq, (uint32_t)n_frames, d_tickets + 1);
+        };
+        if (w == -128) tile(std::integral_constant<int, 128>{});
+        else if (w == -256) tile(std::integral_constant<int, 256>{});
+        else if (w == -512) tile(std::integral_constant<int, 512>{});
+        else if (w == -1024) tile(std::integral_constant<int, 1024>{});
+        else if (w == 1) {
             // One warp per frame runs the batch in waves of 32 x SMs frames (equal-sized files finish in step), and a last wave with
             // few frames costs a whole frame time (5.7 ms per MiB) on a nearly empty GPU: 10 000 files = 2 waves + 528 frames took
             // 27.3 ms against 24.6 ms for 9 472.  So the frames beyond the last full wave, when they are few (up to 1/8 of the batch),

@@ -616,5 +616,6 @@ int main(int argc, char** argv)
     fprintf(stderr, "fzfs: %s mounted on %s (codec: %s, level %d, readahead %s)\n", data_dir.c_str(), mountpoint.c_str(), fzfs_codec_name(), level, readahead ? "on" : "off");
     fs.loop();
     umount2(mountpoint.c_str(), MNT_DETACH);
+    fzfs_codec_shutdown();                             // no readahead thread may still be decoding when the process exits
     return 0;
 }

@@ -1,6 +1,6 @@
 /*
  * fzfs_codec.h -- the codec boundary of the fzfs host: exactly the two call sites fuse-zstd has
- * (/root/reference/src/main.rs:463-467 and :781-791) plus the two hooks batch formation needs.
+ * (/root/reference/src/main.rs:463-467 and :781-791) plus the hooks batch formation needs.
  * Implementations: fzfs_codec_gpu.cpp (product: libfzgpu.so) and oracle/fzfs_codec_ref.c (measurement baseline: the
  * reference's libzstd calls).  All return 0 or a non-zero error; the host maps decode failures to EFAULT and encode
  * failures to EIO as the reference does.
@@ -18,6 +18,7 @@ int fzfs_decode(int src_fd, int dst_fd, uint64_t ino, uint64_t* out_size);      
 int fzfs_encode(int src_fd, int dst_fd, int level, uint64_t src_size, uint64_t ino, uint64_t* out_size);   /* Encoder ... finish */
 int fzfs_prefetch(const char* const* paths, const uint64_t* inos, size_t n);                     /* returns at once */
 void fzfs_invalidate(uint64_t ino);
+void fzfs_codec_shutdown(void);                    /* before the daemon exits: nothing of the codec may still be running */
 #ifdef __cplusplus
 }
 #endif

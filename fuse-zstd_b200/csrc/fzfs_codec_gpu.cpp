@@ -24,6 +24,9 @@ extern "C" int fzfs_encode(int src_fd, int dst_fd, int level, uint64_t src_size,
 }
 extern "C" int fzfs_prefetch(const char* const* paths, const uint64_t* inos, size_t n)
 {
-    return g_cache ? fzg_cache_prefetch_async(0, paths, inos, n) : 0;
+    if (!g_cache || n == 0) return 0;
+    const int devs = fzg_device_count();                             // a directory's batch goes to one GPU: sharded by inode like the opens
+    return fzg_cache_prefetch_async(devs > 0 ? (int)(inos[0] % (uint64_t)devs) : 0, paths, inos, n);
 }
 extern "C" void fzfs_invalidate(uint64_t ino) { if (g_cache) fzg_cache_invalidate(ino); }
+extern "C" void fzfs_codec_shutdown(void) { fzg_shutdown(); }      // drains the prefetch threads first

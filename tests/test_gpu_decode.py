@@ -31,10 +31,10 @@ def _init():
     yield
 
 
-@pytest.fixture(params=["1", "2", "8", "32"])
+@pytest.fixture(params=["t128", "t256", "t1024", "1", "8"])
 def exec_w(request):
-    """warps per frame in the execute stage: k_execute (1) or k_execute_cta<2 / 8 / 32>; without the fixture the library
-    chooses by batch shape (few frames -> many warps per frame)"""
+    """the execute kernel: k_execute_tile with 128 / 256 / 1024 threads per frame (the default kernel; without the fixture the
+    library chooses the width by batch shape), or round 1's k_execute (1) / k_execute_cta<8>"""
     old = os.environ.get("FZG_EXEC_W")
     os.environ["FZG_EXEC_W"] = request.param
     yield request.param
