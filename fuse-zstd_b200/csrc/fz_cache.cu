@@ -196,9 +196,10 @@ extern "C" int fzg_cache_prefetch(int device, const char* const* paths, const ui
     // ---- sizes from the frame headers.  The results of a GROUP of files are contiguous in one pinned slab (one device -> host
     // copy per group); a group never asks for more than a slab holds, so a directory larger than a slab is decoded as
     // several batches instead of not at all (the slabs are reserved at mount time with kSlabBytes each).
-    size_t limit;
+    size_t limit, budget;                                  // per group / for the whole call: a prefetch never takes more than the cache holds
     {
         std::lock_guard<std::mutex> lk(g_mu);
+        budget = g_capacity;
         limit = g_capacity < kSlabBytes ? g_capacity : kSlabBytes;
         for (const Slab& sl : g_slabs) if (sl.cap > limit && sl.cap <= g_capacity) limit = sl.cap;
     }
@@ -208,6 +209,8 @@ extern "C" int fzg_cache_prefetch(int device, const char* const* paths, const ui
         uint64_t content = 0, csize = 0;
         if (fzg_frame_info(g_arena + coff[j], clen[j], &content, &csize) != 0 || content == UINT64_MAX) continue;   // unknown size: left to open()
         if (content > limit) continue;                     // larger than a slab (or a lying header): left to open(), the others go on
+        if (content > budget) break;                       // the cache is full of this very call's files
+        budget -= (size_t)content;
         which.push_back(j); dcs.push_back((size_t)content);
     }
     int added = 0;

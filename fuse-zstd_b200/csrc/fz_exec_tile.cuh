@@ -59,18 +59,17 @@ __device__ __forceinline__ void group_copy(uint8_t* dst, const uint8_t* src, uin
     }
 }
 
-constexpr uint32_t kTileChunk = 256;                        // records per bulk copy (2 KB)
-
 template <int T> struct TileCfg {
     static constexpr uint32_t threads = T;
     static constexpr uint32_t round_bytes = 16u * T;
     static constexpr uint32_t rmax = 2u * T;                                     // records a round may use (>= 3 bytes each)
-    static constexpr uint32_t need = 2u * rmax / kTileChunk + 3u;               // chunks alive at once: [g - 1, g + 2 rmax]
-    static constexpr uint32_t slots = need <= 8 ? 8 : (need <= 16 ? 16 : 32);   // power of two
-    static constexpr uint32_t ring = slots * kTileChunk;                         // records in the ring
-    static constexpr uint32_t window = 128u * T;                                 // bytes of the frame's most recent output kept in shared memory (power of two)
-    static constexpr uint32_t smem = ring * 8u + window;                         // dynamic shared memory: record ring | window
-    static constexpr int ctas_per_sm = T <= 128 ? 8 : (T <= 256 ? 4 : (T <= 512 ? 2 : 1));
+    static constexpr uint32_t chunk = T / 2;                                     // records per bulk copy
+    static constexpr uint32_t slots = 16;                                        // chunks in the ring: [g - 1, g + 2 rmax] is 8 chunks + 3
+    static constexpr uint32_t ring = slots * chunk;                              // records in the ring (8 T)
+    static constexpr uint32_t window = T <= 128 ? 16384u : (T <= 512 ? 32768u : 65536u);               // bytes of the frame's most recent output kept in shared memory (power of two)
+    // dynamic shared memory: record ring | expanded records of the round | window
+    static constexpr uint32_t xr_off = ring * 8u, win_off = xr_off + (rmax + 2u) * 16u, smem = win_off + window;
+    static constexpr int ctas_per_sm = (int)((227u * 1024u) / (smem + 2048u + 6u * T)) < (2048 / T) ? (int)((227u * 1024u) / (smem + 2048u + 6u * T)) : (2048 / T);
 };
 
 // ---- mbarrier / bulk copy (PTX ISA 8.x, sm_90+)
@@ -87,12 +86,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     } while (!ok);
 }
-// exact-size L2 prefetch (16-byte units): the next round's far match sources
-__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) { asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory"); }
 
-// nb (1..8) bytes at any alignment.  The bytes live either in global memory (the far window, L2 / HBM) or in the CTA's
-// shared-memory window, a ring indexed by the low bits of the global address -- so the two aligned 8-byte words that hold
-// them are given as two generic pointers (the second word of a ring source may wrap).
+// nb (1..8) bytes at any alignment, given the two aligned 8-byte words that hold them as GENERIC pointers: the bytes live in
+// global memory (literals; the far window in L2 / HBM) or in the CTA's shared-memory window, whose second word may wrap.
 __device__ __forceinline__ uint64_t ld8_pair(const void* p0, const void* p1, uint32_t sh, uint32_t nb)
 {
     uint32_t x0, x1, x2 = 0, x3 = 0;
@@ -112,190 +108,185 @@ __device__ __forceinline__ void tile_merge(TileOut& o, uint64_t v, uint32_t n, u
 __device__ __forceinline__ uint32_t tile_byte(const TileOut& o, uint32_t k) { return (uint32_t)((k < 8 ? o.lo >> (8 * k) : o.hi >> (8 * (k - 8))) & 0xFF); }
 
 // The CTA's shared-memory window: the most recent `window` bytes of the frame, a ring indexed by the low bits of the
-// GLOBAL address of an output byte (granules are 16-byte aligned in both).  Scattered loads are what bounds this stage: a
-// warp-wide load of 32 random global addresses occupies the L1 pipeline for 32-64 cycles, the same load from shared
-// memory for 2-4 (bank conflicts only), and 50-75 % of the match sources lie within the last 32-128 KB.
+// GLOBAL address of an output byte (granules are 16-byte aligned in both).
 struct TileWin {
     uint8_t* p;               // generic pointer to the ring
     uint32_t mask;            // window - 1
     __device__ __forceinline__ uint8_t* at(const uint8_t* g) const { return p + ((uint32_t)(uintptr_t)g & mask); }
 };
-// n (1..8) bytes of the frame at global address g: from the ring (in_win) or from global memory
-__device__ __forceinline__ uint64_t tile_load(const TileWin& w, const uint8_t* g, uint32_t n, bool in_win)
-{
-    const uint32_t sh = (uint32_t)((uintptr_t)g & 7);
-    const uint8_t* a = g - sh;
-    const void* p0 = in_win ? (const void*)w.at(a) : (const void*)a;
-    const void* p1 = in_win ? (const void*)w.at(a + 8) : (const void*)(a + 8);
-    return ld8_pair(p0, p1, sh, n);
-}
-
-// A hole whose source reaches into the thread's own granule (distances below ~24: rare): byte by byte, own bytes
-// from the registers (if no earlier hole still covers them), the others from the ring if their granule is stored.
-// Returns false when a byte is not there yet.
-__device__ __noinline__ bool tile_fill_bytes(TileOut& o, int32_t s, uint32_t n, uint32_t d, int32_t P, int32_t base, uint32_t pass,
-                                             const uint16_t* flag, const uint8_t* g0, const TileWin& w, int32_t safe_lo,
-                                             uint32_t unfilled /* bytes of the granule still covered by holes */)
-{
-    uint64_t v = 0;
-    for (uint32_t k = 0; k < n; k++) {
-        const int32_t q = s + (int32_t)k;
-        uint32_t byte;
-        if (q >= P) {
-            const uint32_t at = (uint32_t)(q - P);
-            if ((unfilled >> at) & 1u) return false;
-            byte = tile_byte(o, at);
-        } else {
-            const int32_t j = (q - base) >> 4;
-            if (j >= 0) { const uint32_t f = flag[j]; if (f == 0 || f >= pass) return false; }
-            byte = q >= safe_lo ? *(volatile const uint8_t*)w.at(g0 + q) : *(volatile const uint8_t*)(g0 + q);
-        }
-        v |= (uint64_t)byte << (8 * k);
-    }
-    tile_merge(o, v, n, d);
-    return true;
-}
 
 // One compressed block with sequences, by the whole CTA.  g0 = the block's first output byte, done = bytes of the frame
 // before it, cg = running chunk number of the CTA's record ring (see k_execute_tile), win_from = block-relative position
 // from which on the shared-memory window holds the frame's bytes (<= 0: since some earlier block).
+struct TileSm {                                   // static shared memory of the kernel
+    uint64_t* ring; uint4* xr; uint16_t* mark; uint16_t* have /*[2][T + 1]*/; uint32_t* wtot; uint32_t* next /*[2]*/;
+    uint32_t ring_sm, bar_sm;
+};
+
 template <int T>
-__device__ __forceinline__ void tile_block(uint64_t* ring, const uint32_t ring_sm, const uint32_t bar_sm, uint16_t* flag, uint32_t* s_next /*[2]*/,
-                                           const TileWin& win, int32_t win_from, const Block& b, const uint64_t* __restrict__ sq, uint8_t* g0,
-                                           uint64_t done, uint32_t& cg, int& status, const uint32_t tid)
+__device__ __forceinline__ void tile_block(const TileSm& sm, const TileWin& win, int32_t win_from, const Block& b, const uint64_t* __restrict__ sq,
+                                           uint8_t* g0, uint64_t done, uint32_t& cg, int& status, const uint32_t tid)
 {
     using C = TileCfg<T>;
+    const uint32_t lane = tid & 31, warp = tid >> 5;
     const uint32_t nseq = b.nseq, rsize = b.rsize, nrec = nseq + 1;
     const uint8_t* __restrict__ lit = b.lit;
     const uint32_t in0 = b.rep_in[0], in1 = b.rep_in[1], in2 = b.rep_in[2];
-    const uint32_t n_chunks = (nrec + kTileChunk - 1) / kTileChunk;
-    const uint32_t rbase = cg * kTileChunk;                              // ring position of record 0
+    const uint32_t n_chunks = (nrec + C::chunk - 1) / C::chunk;
+    const uint32_t rbase = cg * C::chunk;                                // ring position of record 0
     const uint32_t reach = (uint32_t)(done < (1ull << 28) ? done : (1ull << 28));   // off <= 2^27: anything beyond is always inside the frame
     const uint32_t a0 = (uint32_t)((uintptr_t)g0 & 15);
-    auto rec = [&](uint32_t idx) -> uint2 { return *(const uint2*)(ring + ((rbase + idx) & (C::ring - 1))); };
+    auto rec = [&](uint32_t idx) -> uint64_t { return sm.ring[(rbase + idx) & (C::ring - 1)]; };
+    uint16_t* const have0 = sm.have; uint16_t* const have1 = sm.have + T + 1;
     uint32_t issued = 0;                                                 // chunks of this block in flight or landed (CTA-uniform)
     uint32_t g = 0, gS = 0;                                              // first record with E > gS; start of the round (CTA-uniform)
-    uint32_t par = 0;                                                    // s_next is double-buffered: a fast thread may finish the next round's walk before a slow one has read this round's
+    uint32_t par = 0;                                                    // sm.next is double-buffered: a fast thread may finish the next round's walk before a slow one has read this round's
     while (gS < rsize) {
         // ---- records: chunks [c_lo, c_need] are read by this round, everything up to c_top is asked for now
-        const uint32_t c_lo = g ? (g - 1) / kTileChunk : 0;
-        const uint32_t c_need = min(n_chunks - 1, (g + C::rmax) / kTileChunk);
-        const uint32_t c_top = min(min(n_chunks - 1, (g + 2 * C::rmax) / kTileChunk), c_lo + C::slots - 1);
+        const uint32_t c_lo = g ? (g - 1) / C::chunk : 0;
+        const uint32_t c_need = min(n_chunks - 1, (g + C::rmax) / C::chunk);
+        const uint32_t c_top = min(min(n_chunks - 1, (g + 2 * C::rmax) / C::chunk), c_lo + C::slots - 1);
         if (tid == 0) {
             for (uint32_t c = issued; c <= c_top; c++) {
                 const uint32_t slot = (cg + c) & (C::slots - 1);
-                const uint32_t n = min(kTileChunk, nrec - c * kTileChunk);
+                const uint32_t n = min(C::chunk, nrec - c * C::chunk);
                 const uint32_t bytes = ((n + 1) & ~1u) * 8;              // 16-byte units: the pad record exists (walk_item)
-                mbar_expect_tx(bar_sm + 8 * slot, bytes);
-                bulk_g2s(ring_sm + slot * kTileChunk * 8, sq + (size_t)c * kTileChunk, bytes, bar_sm + 8 * slot);
+                mbar_expect_tx(sm.bar_sm + 8 * slot, bytes);
+                bulk_g2s(sm.ring_sm + slot * C::chunk * 8, sq + (size_t)c * C::chunk, bytes, sm.bar_sm + 8 * slot);
             }
         }
         issued = max(issued, c_top + 1);
-        for (uint32_t c = c_lo; c <= c_need; c++) mbar_wait(bar_sm + 8 * ((cg + c) & (C::slots - 1)), ((cg + c) / C::slots) & 1u);
+        for (uint32_t c = c_lo; c <= c_need; c++) mbar_wait(sm.bar_sm + 8 * ((cg + c) & (C::slots - 1)), ((cg + c) / C::slots) & 1u);
         // ---- geometry of the round: granules are 16-byte aligned in memory; it ends on a granule boundary or at the block's end
         const uint32_t last = min(g + C::rmax - 1, nseq);
         const uint32_t a = (a0 + gS) & 15;
         const int32_t base = (int32_t)gS - (int32_t)a;                   // position of granule 0's first byte
-        uint32_t gE = min((uint32_t)(base + (int32_t)C::round_bytes), rec_e(rec(last).x));
+        uint32_t gE = min((uint32_t)(base + (int32_t)C::round_bytes), rec_e(rec(last)));
         if (gE < rsize) gE -= (a0 + gE) & 15;
         // the ring slots of positions below base + round_bytes - window are overwritten during this round
         const int32_t safe_lo = max(win_from, base + (int32_t)C::round_bytes - (int32_t)C::window);
         const int32_t P = base + 16 * (int32_t)tid;
         const uint32_t lo = (uint32_t)max(P, (int32_t)gS), hi = (uint32_t)min(P + 16, (int32_t)gE);
         const bool active = P + 16 > (int32_t)gS && P < (int32_t)gE;
-        flag[tid] = 0;
-        // ---- the first sequence that reaches beyond lo
-        uint32_t i = g;
-        {
-            uint32_t cnt = 0;
+        // ---- the round's records, expanded once: { M, E, literal source - S, distance } and marked at the first granule they own
+        sm.mark[tid] = 0; have0[tid] = 0; have1[tid] = 0;
+        __syncthreads();                                                 // (also: the previous round's reads of xr / mark are done)
+        const uint32_t nr = last - g + 1;
 #pragma unroll
-            for (uint32_t step = C::rmax / 2; step; step >>= 1) {
-                const uint32_t c = cnt + step;
-                if (g + c - 1 <= last && rec_e(rec(g + c - 1).x) <= lo) cnt = c;
+        for (uint32_t k = 0; k < 2; k++) {
+            const uint32_t r = tid + k * T;
+            if (r < nr) {
+                const uint64_t q = rec(g + r), qp = g + r ? rec(g + r - 1) : 0ull;
+                const uint32_t E = rec_e(q), Ep = rec_e(qp), LEp = rec_le(qp), M = Ep + (rec_le(q) - LEp);
+                uint32_t off = off_resolve(rec_off(q), in0, in1, in2);
+                if (r < nr - 1 || g + r < nseq) { if (off == 0 || off > reach + M) { off = 0; status = FZG_E_CORRUPT; } }     // reaches before the frame start (the tail record has no match)
+                sm.xr[r] = make_uint4(M, E, LEp - Ep, off);
+                // granules whose first byte this sequence produces: P_G in [Ep, E); record g owns granule 0 whatever its start
+                const int32_t G0 = r ? (int32_t)(Ep - (uint32_t)base + 15u) >> 4 : 0, G1 = ((int32_t)(E - (uint32_t)base + 15u) >> 4) - 1;
+                if (G0 <= G1 && G0 < T) sm.mark[G0] = (uint16_t)(r + 1);
             }
-            i = g + cnt;
         }
-        uint32_t Eprev = 0, LEprev = 0;
-        if (i) { const uint2 r = rec(i - 1); const uint64_t q = (uint64_t)r.x | ((uint64_t)r.y << 32); Eprev = rec_e(q); LEprev = rec_le(q); }
+        __syncthreads();
+        // ---- the first sequence that reaches beyond the granule's first byte: running maximum of the marks
+        uint32_t i;
+        {
+            uint32_t v = sm.mark[tid];
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, dd); if (lane >= (uint32_t)dd) v = max(v, t); }
+            if (lane == 31) sm.wtot[warp] = v;
+            __syncthreads();
+            uint32_t carry = 0;
+            for (uint32_t w = 0; w < warp; w++) carry = max(carry, sm.wtot[w]);
+            i = max(v, carry) - 1;                                       // >= 0: granule 0 is marked
+        }
         uint32_t cur = lo;
         TileOut o{ 0, 0 };
-        int32_t hs0 = 0, hs1 = 0, hs2 = 0; uint32_t hm0 = 0, hm1 = 0, hm2 = 0;      // holes: source position, (d | n << 4), 0: free
-        bool pending = active;
+        uint32_t mine = 0;                                               // bytes of the granule that are in `o`
+        uint32_t h0 = 0, h1 = 0, h2 = 0;                                 // holes: (s - base) [0:15) | d [15:19) | n [19:23), 0 = free slot
+        const uint32_t full = active ? ((1u << (hi - (uint32_t)P)) - 1u) & ~((1u << (lo - (uint32_t)P)) - 1u) : 0u;
+        bool pending = active, linger = false;
         for (uint32_t pass = 1;; pass++) {
+            uint16_t* const have_w = (pass & 1) ? have1 : have0;         // written in this pass, read in the next
+            const uint16_t* const have_r = (pass & 1) ? have0 : have1;
+            if (linger) { have_w[tid] = (uint16_t)full; linger = false; }
             if (pending) {
-                // ---- holes of the earlier passes: their sources lie inside the round, i.e. in the ring once stored
-                if (hm0 | hm1 | hm2) {
-                    auto fill = [&](int32_t s, uint32_t& m) {
-                        if (!m) return;
-                        const uint32_t d = m & 15u, n = m >> 4;
-                        if (s + (int32_t)n > P) {                             // reaches into this very granule
-                            uint32_t unfilled = 0;
-                            if (hm0) unfilled |= ((1u << (hm0 >> 4)) - 1u) << (hm0 & 15u);
-                            if (hm1) unfilled |= ((1u << (hm1 >> 4)) - 1u) << (hm1 & 15u);
-                            if (hm2) unfilled |= ((1u << (hm2 >> 4)) - 1u) << (hm2 & 15u);
-                            if (tile_fill_bytes(o, s, n, d, P, base, pass, flag, g0, win, safe_lo, unfilled)) m = 0;
-                            return;
+                // ---- holes of the earlier passes: their sources lie inside the round, i.e. in the window once stored
+                if (h0 | h1 | h2) {
+#pragma unroll 1
+                    for (int k = 0; k < 3; k++) {
+                        uint32_t h = h0;
+                        if (h) {
+                            const uint32_t sb = h & 0x7FFFu, d = (h >> 15) & 15u, n = h >> 19;
+                            const uint32_t hv = (uint32_t)have_r[sb >> 4] | ((uint32_t)have_r[(sb >> 4) + 1] << 16);
+                            const uint32_t need = ((1u << n) - 1u) << (sb & 15u);
+                            if ((hv & need) == need) {
+                                const uint8_t* gp = g0 + base + (int32_t)sb;
+                                const uint32_t sh = (uint32_t)((uintptr_t)gp & 7);
+                                tile_merge(o, ld8_pair(win.at(gp - sh), win.at(gp - sh + 8), sh, n), n, d);
+                                mine |= ((1u << n) - 1u) << d;
+                                h = 0;
+                            }
                         }
-                        const int32_t j0 = (s - base) >> 4, j1 = (s + (int32_t)n - 1 - base) >> 4;
-                        bool ok = true;
-                        if (j0 >= 0) { const uint32_t f = flag[j0]; ok = f != 0 && f < pass; }
-                        if (j1 >= 0 && j1 != j0) { const uint32_t f = flag[j1]; ok = ok && f != 0 && f < pass; }
-                        if (ok) { tile_merge(o, tile_load(win, g0 + s, n, s >= safe_lo), n, d); m = 0; }
-                    };
-                    fill(hs0, hm0); fill(hs1, hm1); fill(hs2, hm2);
+                        h0 = h1; h1 = h2; h2 = h;
+                    }
+                    // compact: free slots last
+                    if (!h0) { h0 = h1; h1 = h2; h2 = 0; }
+                    if (!h0) { h0 = h1; h1 = 0; }
+                    if (!h1) { h1 = h2; h2 = 0; }
                 }
                 // ---- the walk
-                while (cur < hi) {
-                    const uint2 rr = rec(i);
-                    const uint64_t r = (uint64_t)rr.x | ((uint64_t)rr.y << 32);
-                    const uint32_t E = rec_e(r), LE = rec_le(r);
-                    const uint32_t M = Eprev + (LE - LEprev);
+                while (cur < hi && !h2) {
+                    const uint4 x = sm.xr[i];                                 // { M, E, literal source - S, distance }
                     const uint32_t d = cur - (uint32_t)P;
-                    uint32_t n;
-                    if (cur < M) {                                            // literal run
-                        n = min(min(M, hi) - cur, 8u);
-                        const uint8_t* src = lit + LEprev + (cur - Eprev);
-                        const uintptr_t al = (uintptr_t)src & ~(uintptr_t)7;
+                    const bool is_lit = cur < x.x;
+                    uint32_t n = min(min(is_lit ? x.x : x.y, hi) - cur, 8u);
+                    const uint8_t* src = lit + (uint32_t)(x.z + cur);         // literal run: lit[LEp + (cur - S)] (x.z = LEp - S, modulo 2^32)
+                    bool in_win = false, hole = false;
+                    if (!is_lit) {
+                        const uint32_t off = x.w;
+                        // the last period before the match: s in [M - off, M), the piece ends at M at the latest
+                        const uint32_t into = cur - x.x;
+                        uint32_t back = off;
+                        if (into >= off && off) back = (into / off + 1u) * off;
+                        const int32_t s = (int32_t)cur - (int32_t)back;
+                        n = min(n, x.x - (uint32_t)s);
+                        if (s < (int32_t)gS && s + (int32_t)n > (int32_t)gS) n = gS - (uint32_t)s;        // a piece lies below the round or inside it
+                        src = g0 + s;
+                        in_win = s >= safe_lo;
+                        hole = s >= (int32_t)gS;
+                        if (off == 0) { hole = false; in_win = false; src = (const uint8_t*)sm.xr; n = min(min(x.y, hi) - cur, 8u); }   // corrupt (the frame fails): any readable bytes
+                        if (hole) {
+                            const uint32_t h = (uint32_t)(s - base) | (d << 15) | (n << 19);
+                            if (!h0) h0 = h; else if (!h1) h1 = h; else h2 = h;
+                        }
+                    }
+                    if (!hole) {
                         const uint32_t sh = (uint32_t)((uintptr_t)src & 7);
-                        const uint2 w0 = __ldg((const uint2*)al);
-                        uint2 w1 = make_uint2(0, 0);
-                        if (sh + n > 8) w1 = __ldg((const uint2*)(al + 8));
-                        tile_merge(o, funnel8(w0.x, w0.y, w1.x, w1.y, sh), n, d);
-                    } else {                                                  // match
-                        n = min(min(E, hi) - cur, 8u);
-                        uint32_t off = off_resolve(rec_off(r), in0, in1, in2);
-                        if (off == 0 || off > reach + M) { off = 0; status = FZG_E_CORRUPT; }      // reaches before the frame start
-                        if (off) {
-                            // the last period before the match: s in [M - off, M), the piece ends at M at the latest
-                            const uint32_t into = cur - M;
-                            const uint32_t k = into < off ? 1u : into / off + 1u;
-                            const int32_t s = (int32_t)cur - (int32_t)(k * off);
-                            n = min(n, (uint32_t)((int32_t)M - s));
-                            if (s + (int32_t)n <= (int32_t)gS) tile_merge(o, tile_load(win, g0 + s, n, s >= safe_lo), n, d);   // below the round
-                            else {
-                                const uint32_t m = d | (n << 4);
-                                if (!hm0) { hs0 = s; hm0 = m; } else if (!hm1) { hs1 = s; hm1 = m; } else if (!hm2) { hs2 = s; hm2 = m; }
-                                else break;                                   // no free slot: the walk waits for a pass
-                            }
-                        }                                                     // corrupt: zeros
+                        const uint8_t* al = src - sh;
+                        const void* p0 = in_win ? (const void*)win.at(al) : (const void*)al;
+                        const void* p1 = in_win ? (const void*)win.at(al + 8) : (const void*)(al + 8);
+                        tile_merge(o, ld8_pair(p0, p1, sh, n), n, d);
+                        mine |= ((1u << n) - 1u) << d;
                     }
                     cur += n;
-                    if (cur == E) { i++; Eprev = E; LEprev = LE; }
+                    if (cur == x.y) i++;
                 }
-                if (cur == hi && !(hm0 | hm1 | hm2)) {
-                    uint8_t* gp = g0 + P; uint8_t* wp = win.at(gp);
-                    if (hi - lo == 16) {
-                        const uint4 v = make_uint4((uint32_t)o.lo, (uint32_t)(o.lo >> 32), (uint32_t)o.hi, (uint32_t)(o.hi >> 32));
-                        *(uint4*)gp = v; *(uint4*)wp = v;
-                    } else for (uint32_t k = lo - (uint32_t)P; k < hi - (uint32_t)P; k++) { const uint8_t v = (uint8_t)tile_byte(o, k); gp[k] = v; wp[k] = v; }   // a block's first / last granule
-                    flag[tid] = (uint16_t)pass;
-                    if (hi == gE) s_next[par] = i;
-                    pending = false;
+                // ---- publish what the granule has; a complete one leaves for global memory
+                uint8_t* gp = g0 + P; uint8_t* wp = win.at(gp);
+                const uint4 v = make_uint4((uint32_t)o.lo, (uint32_t)(o.lo >> 32), (uint32_t)o.hi, (uint32_t)(o.hi >> 32));
+                if (hi - lo == 16) *(uint4*)wp = v;
+                else for (uint32_t k = lo - (uint32_t)P; k < hi - (uint32_t)P; k++) wp[k] = (uint8_t)tile_byte(o, k);          // a block's first / last granule
+                have_w[tid] = (uint16_t)mine;
+                if (mine == full) {
+                    if (hi - lo == 16) *(uint4*)gp = v;
+                    else for (uint32_t k = lo - (uint32_t)P; k < hi - (uint32_t)P; k++) gp[k] = (uint8_t)tile_byte(o, k);
+                    if (hi == gE) sm.next[par] = i;
+                    pending = false; linger = true;
                 }
             }
             if (!__syncthreads_or(pending)) break;
         }
-        g = s_next[par]; gS = gE; par ^= 1u;
+        g = g + sm.next[par]; gS = gE; par ^= 1u;
     }
     cg += n_chunks;
 }
@@ -305,16 +296,19 @@ __global__ void __launch_bounds__(T, TileCfg<T>::ctas_per_sm) k_execute_tile(Fra
                                                                             const uint64_t* seqs, uint32_t n_frames, uint32_t* ticket)
 {
     using C = TileCfg<T>;
-    extern __shared__ __align__(128) uint64_t tile_ring[];             // record ring (C::ring records) | window (C::window bytes)
+    extern __shared__ __align__(128) uint8_t tile_dyn[];               // record ring | expanded records | window
     __shared__ __align__(8) uint64_t s_bar[C::slots];
-    __shared__ uint16_t s_flag[T];
-    __shared__ uint32_t s_next[2], s_f;
+    __shared__ uint16_t s_mark[T], s_have[2 * (T + 1)];
+    __shared__ uint32_t s_wtot[32], s_next[2], s_f;
     const uint32_t tid = threadIdx.x;
-    const uint32_t ring_sm = (uint32_t)__cvta_generic_to_shared(tile_ring), bar_sm = (uint32_t)__cvta_generic_to_shared(s_bar);
-    const TileWin win{ (uint8_t*)(tile_ring + C::ring), C::window - 1 };
+    TileSm sm;
+    sm.ring = (uint64_t*)tile_dyn; sm.xr = (uint4*)(tile_dyn + C::xr_off); sm.mark = s_mark; sm.have = s_have; sm.wtot = s_wtot; sm.next = s_next;
+    sm.ring_sm = (uint32_t)__cvta_generic_to_shared(tile_dyn); sm.bar_sm = (uint32_t)__cvta_generic_to_shared(s_bar);
+    const TileWin win{ tile_dyn + C::win_off, C::window - 1 };
     if (tid == 0) {
-        for (uint32_t s = 0; s < C::slots; s++) mbar_init(bar_sm + 8 * s, 1);
+        for (uint32_t s = 0; s < C::slots; s++) mbar_init(sm.bar_sm + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_have[T] = 0; s_have[2 * T + 1] = 0;                           // the entry a hole's second granule may read past the round
     }
     uint32_t cg = 0;                                   // chunks ever issued into the ring: slot = cg % slots, phase = cg / slots
     for (;;) {
@@ -341,7 +335,7 @@ __global__ void __launch_bounds__(T, TileCfg<T>::ctas_per_sm) k_execute_tile(Fra
             else {
                 const uint64_t back = done - win_done;                   // bytes of the frame before this block that the window mirrors
                 const int32_t win_from = back < (uint64_t)C::window ? -(int32_t)back : -(int32_t)C::window;
-                tile_block<T>(tile_ring, ring_sm, bar_sm, s_flag, s_next, win, win_from, b, seqs + b.seq_base, g0, done, cg, status, tid);
+                tile_block<T>(sm, win, win_from, b, seqs + b.seq_base, g0, done, cg, status, tid);
             }
             __syncthreads();                           // later blocks read this one back (the window)
             done += rsize;

@@ -73,3 +73,14 @@ def test_seek_footer_parser_host_only():
     assert codec.seek_footer(struct.pack("<IBI", 5, 0x04, 0x8F92EAB1), 1000)[0] == -errno.ENOENT       # reserved bits
     assert codec.seek_footer(foot, 40)[0] == -errno.ENOENT                                # table larger than the file
     assert codec.seek_footer(foot[:8], 1000)[0] == -errno.ENOENT
+
+
+def test_frame_info_sums_do_not_wrap():
+    """two frames whose Frame_Content_Size fields add up past 2^64: refused, not wrapped (host-side header walk, no GPU)"""
+    import struct
+    codec = importlib.import_module("fuse-zstd_b200.codec")
+    one = struct.pack("<IB", 0xFD2FB528, 0xC0) + bytes([0x00]) + struct.pack("<Q", (1 << 64) - 16) + bytes([1, 0, 0])   # windowed, empty last Raw block
+    st, content, csize = codec.frame_info(one)
+    assert st == 0 and content == (1 << 64) - 16 and csize == len(one)
+    st, content, _ = codec.frame_info(one + one)
+    assert st == codec.E_UNSUPPORTED

@@ -111,3 +111,28 @@ def test_background_prefetch(ref, corpus):
             assert st == 0 and hashlib.sha256(out).digest() == hashlib.sha256(plain[i].tobytes()).digest()
         for k in keys:
             codec.cache_invalidate(k)
+
+
+def test_directory_larger_than_a_slab(ref, corpus):
+    """slabs reserved at mount time hold 256 MiB each: a directory of 300 MiB is decoded as two batches, not dropped"""
+    if not ref.available:
+        pytest.skip("system libzstd absent")
+    n, size = 300, 1 << 20
+    plain = corpus.json_files(5570000, 4, size, threads=os.cpu_count())
+    comps = [ref.writer_encode(plain[i].tobytes(), 3) for i in range(4)]
+    with tempfile.TemporaryDirectory() as d:
+        paths = []
+        for i in range(n):
+            p = os.path.join(d, "h%03d.zst" % i)
+            with open(p, "wb") as fh:
+                fh.write(comps[i % 4])
+            paths.append(p)
+        keys = list(range(9000, 9000 + n))
+        codec.cache_configure(1 << 30)
+        assert codec.cache_reserve() >= 2
+        assert codec.cache_prefetch(paths, keys) == n
+        for i in (0, 1, 254, 255, 256, 257, n - 1):
+            st, out, hit, _ = _open_through_cache(paths[i], keys[i])
+            assert st == 0 and hit and hashlib.sha256(out).digest() == hashlib.sha256(plain[i % 4].tobytes()).digest()
+        for k in keys:
+            codec.cache_invalidate(k)

@@ -288,3 +288,36 @@ def test_far_form_records(ref, exec_w):
     for i, ((st, out), plain) in enumerate(zip(res, plains)):
         assert st == 0, (i, codec.strerror(st))
         assert out == plain, i
+
+
+def test_untrusted_sizes_in_the_fd_entry_point(ref):
+    """fzg_decode_fd buffers whole files, so nothing in the input may size an allocation beyond what its block headers can
+    regenerate: a frame that declares 2^62 bytes fails that one open (src/main.rs:467: EFAULT) instead of taking the process
+    down, and a highly compressible file WITHOUT Frame_Content_Size decodes in one attempt (bound = the block walk)."""
+    import errno
+    import struct
+    import tempfile
+    # FCS_flag 3 (8-byte field), Single_Segment, no checksum; one last Raw block of 5 bytes
+    lying = struct.pack("<IB", 0xFD2FB528, 0xE0) + struct.pack("<Q", 1 << 62) + bytes([5 << 3 | 1, 0, 0]) + b"hello"
+    st, content, _ = codec.frame_info(lying)
+    assert st == codec.E_UNSUPPORTED or content == 1 << 62        # single segment: window = FCS > 2^27 is already refused by the header walk
+    lying2 = struct.pack("<IB", 0xFD2FB528, 0xC0) + bytes([0x00]) + struct.pack("<Q", 1 << 62) + bytes([5 << 3 | 1, 0, 0]) + b"hello"   # windowed: 1 KiB window
+    st, content, _ = codec.frame_info(lying2)
+    assert st == 0 and content == 1 << 62
+    for blob in (lying, lying2):
+        with tempfile.TemporaryFile() as src, tempfile.TemporaryFile() as dst:
+            src.write(blob); src.seek(0)
+            with pytest.raises(OSError) as ei:
+                codec.decode_fd(src.fileno(), dst.fileno())
+            assert ei.value.errno == errno.EFAULT
+            assert dst.seek(0, 2) == 0
+    if not ref.available:
+        pytest.skip("system libzstd absent")
+    plain = bytes(48 << 20)                                       # zeros: ratio far beyond any fixed guess
+    comp = ref.writer_encode(plain, 3, pledge=False)
+    assert len(comp) * 1024 < len(plain) and codec.frame_info(comp)[1] is None
+    with tempfile.TemporaryFile() as src, tempfile.TemporaryFile() as dst:
+        src.write(comp); src.seek(0)
+        assert codec.decode_fd(src.fileno(), dst.fileno()) == len(plain)
+        dst.seek(0)
+        assert hashlib.sha256(dst.read()).digest() == hashlib.sha256(plain).digest()
