@@ -424,6 +424,23 @@ __device__ __forceinline__ void warp_big_sequence(uint8_t* dst, const uint8_t* l
     __syncwarp();
 }
 
+// The next round's match sources, asked for a round ahead.  FZ_EXEC_PREFETCH: 1 = prefetch.global.L2 of the first and last byte's
+// line (round 1), 2 = cp.async.bulk.prefetch.L2 of exactly the 16-byte units that hold the match source (TMA unit, no registers).
+#ifndef FZ_EXEC_PREFETCH
+#define FZ_EXEC_PREFETCH 1
+#endif
+__device__ __forceinline__ void exec_prefetch(const uint8_t* sp, uint32_t len)
+{
+#if FZ_EXEC_PREFETCH == 1
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(sp));
+    if ((((uintptr_t)sp + len - 1) ^ (uintptr_t)sp) & ~(uintptr_t)31) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + len - 1));
+#elif FZ_EXEC_PREFETCH == 2
+    const uintptr_t a = (uintptr_t)sp & ~(uintptr_t)15;
+    const uint32_t bytes = (uint32_t)((((uintptr_t)sp + len + 15) & ~(uintptr_t)15) - a);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(bytes < 64u ? bytes : 64u) : "memory");
+#endif
+}
+
 __device__ __forceinline__ void exec_block_warp(uint8_t* stage, const Block& b, const uint64_t* __restrict__ sq, uint8_t* g0,
                                                 uint64_t done, int& status, uint32_t lane)
 {
@@ -532,7 +549,7 @@ __device__ __forceinline__ void exec_block_warp(uint8_t* stage, const Block& b, 
         __syncwarp();
         Ecarry = gE; LEcarry = __shfl_sync(kFull, LE, m - 1);
         g += m;
-#ifndef FZ_EXEC_NO_PREFETCH
+#if FZ_EXEC_PREFETCH
         // The next round's match sources lie a random distance back in the window (HBM): ask for them now, a whole round
         // (thousands of cycles: ~48 warps share the SM) before they are read, so that the round finds them in L2.
         {
@@ -542,11 +559,7 @@ __device__ __forceinline__ void exec_block_warp(uint8_t* stage, const Block& b, 
             if (lane == 0) { Sn = Ecarry; LEpn = LEcarry; }
             const uint32_t Mn = Sn + (LEn - LEpn);
             const uint32_t offn = off_resolve(rec_off(rcur), in0, in1, in2);
-            if (lane < nn && offn != 0 && (uint64_t)offn <= done + Mn) {
-                const uint8_t* sp = g0 + Mn - offn;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(sp));
-                if ((((uintptr_t)sp + (En - Mn) - 1) ^ (uintptr_t)sp) & ~(uintptr_t)31) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + (En - Mn) - 1));
-            }
+            if (lane < nn && offn != 0 && (uint64_t)offn <= done + Mn) exec_prefetch(g0 + Mn - offn, En - Mn);
         }
 #endif
     }
@@ -556,6 +569,147 @@ __device__ __forceinline__ void exec_block_warp(uint8_t* stage, const Block& b, 
     __syncwarp();
 }
 
+// ---- the same round, with the 8-byte STEPS of its copies dealt out evenly over the lanes.
+// exec_block_warp gives a lane one sequence and lets it loop over its literal run and its match: a round then takes as many
+// step iterations as its longest run plus its longest match (about eight on JSON text, 21 of 32 lanes busy) for an average
+// of 1.7 steps per sequence.  Here a scan over the step counts of the round's sequences numbers the steps (position order),
+// lane l takes steps l and l + 32 (a round holds at most 64), finds their sequence with a five-shuffle binary search over
+// the scan and fetches its fields with three shuffles: two iterations for the same round.  A step is atomic (<= 8 bytes, one
+// source); a match step that would read its own match (offset < length) takes its bytes from the last period BEFORE the
+// match instead (x[p] = x[M - off + (p - M) mod off]), so a step only ever depends on bytes below its sequence's match.
+// Steps whose source lies inside the round wait for the frontier (the first unfinished step, in position order) to pass it.
+__device__ __forceinline__ void exec_block_steps(uint8_t* stage, const Block& b, const uint64_t* __restrict__ sq, uint8_t* g0,
+                                                 uint64_t done, int& status, uint32_t lane)
+{
+    const uint32_t nseq = b.nseq, rsize = b.rsize;
+    const uint8_t* __restrict__ lit = b.lit;
+    const uint32_t in0 = b.rep_in[0], in1 = b.rep_in[1], in2 = b.rep_in[2];
+    uint32_t Ecarry = 0, LEcarry = 0;
+    uint64_t rcur = lane < nseq ? __ldg(sq + lane) : 0;          // records of the current round; the next round's are loaded a round early
+    for (uint32_t g = 0; g < nseq;) {
+        const uint32_t nv = min(32u, nseq - g);
+        const uint64_t r = lane < nv ? rcur : 0;
+        uint32_t E = rec_e(r), LE = rec_le(r);
+        const uint32_t Elast = __shfl_sync(kFull, E, nv - 1), LElast = __shfl_sync(kFull, LE, nv - 1);
+        if (lane >= nv) { E = Elast; LE = LElast; }
+        uint32_t S = __shfl_up_sync(kFull, E, 1), LEp = __shfl_up_sync(kFull, LE, 1);
+        if (lane == 0) { S = Ecarry; LEp = LEcarry; }
+        const uint32_t gS = Ecarry;                              // output position where this round starts
+        const uint32_t ll = LE - LEp, M = S + ll, ml = E - M;
+        uint32_t off = lane < nv ? off_resolve(rec_off(r), in0, in1, in2) : 1;
+        if (lane < nv && (uint64_t)off > done + M) { off = 0; status = FZG_E_CORRUPT; }     // reaches before the frame start
+        // steps of every sequence, numbered in position order
+        const uint32_t c = lane < nv ? ((ll + 7) >> 3) + ((ml + 7) >> 3) : 0u;
+        const uint32_t cs = warp_scan_incl(c, lane);
+        // sequences of this round: the leading ones whose output fits the stage and whose steps fit two per lane
+        const uint32_t fit = __ballot_sync(kFull, lane < nv && E - gS <= kStage && cs <= 64u);
+        const uint32_t m = fit == kFull ? 32u : (uint32_t)__ffs((int)~fit) - 1u;
+        if (m == 0) {                                            // sequence g alone is larger than the stage
+            const uint32_t ll0 = __shfl_sync(kFull, ll, 0), ml0 = __shfl_sync(kFull, ml, 0), off0 = __shfl_sync(kFull, off, 0);
+            warp_big_sequence(g0 + gS, lit + LEcarry, ll0, ml0, off0, lane);
+            Ecarry = __shfl_sync(kFull, E, 0); LEcarry = __shfl_sync(kFull, LE, 0);
+            g += 1;
+            rcur = g + lane < nseq ? __ldg(sq + g + lane) : 0;
+            continue;
+        }
+        rcur = g + m + lane < nseq ? __ldg(sq + g + m + lane) : 0;
+        const uint32_t gE = __shfl_sync(kFull, E, m - 1);         // end of the round's output
+        const uint32_t n_steps = __shfl_sync(kFull, cs, m - 1);
+        const uint32_t a = (uint32_t)((uintptr_t)(g0 + gS) & 15); // stage[a + i] <-> g0[gS + i]: same low address bits as HBM
+        uint8_t* const st = stage + a - gS;                       // st[p] is the stage byte of output position p (gS <= p < gE)
+        // a sequence in three words: (S - gS) [0:10) | ll [10:20) | ml [20:30);  distance;  LEp [0:18) | first step [18:25)
+        const uint32_t w1 = (S - gS) | (ll << 10) | (ml << 20), w3 = LEp | ((cs - c) << 18);
+        // ---- a lane's two steps: pos / n = destination, src = literal offset or match distance, kind: 0 none, 1 literal, 2 match
+        uint32_t posA = 0, nA = 0, srcA = 0, mA = 0, kindA = 0, posB = 0, nB = 0, srcB = 0, mB = 0, kindB = 0;
+        auto deal = [&](uint32_t k, uint32_t& pos, uint32_t& n, uint32_t& src, uint32_t& mstart, uint32_t& kind) {
+            uint32_t j = 0;                                       // the sequence of step k: the first one whose inclusive count exceeds k
+#pragma unroll
+            for (uint32_t stp = 16; stp; stp >>= 1) { const uint32_t t = __shfl_sync(kFull, cs, j + stp - 1); if (t <= k) j += stp; }
+            const uint32_t v1 = __shfl_sync(kFull, w1, j), v2 = __shfl_sync(kFull, off, j), v3 = __shfl_sync(kFull, w3, j);
+            const uint32_t oS = gS + (v1 & 1023u), oll = (v1 >> 10) & 1023u, oml = v1 >> 20, oM = oS + oll;
+            const uint32_t t = k - (v3 >> 18), nl = (oll + 7) >> 3;
+            kind = 0;
+            if (k < n_steps) {
+                if (t < nl) { kind = 1; pos = oS + 8 * t; n = min(8u, oM - pos); src = (v3 & 0x3FFFFu) + 8 * t; }
+                else { kind = 2; pos = oM + 8 * (t - nl); n = min(8u, oM + oml - pos); src = v2; mstart = oM; }
+            }
+        };
+        deal(lane, posA, nA, srcA, mA, kindA);
+        if (n_steps > 32) deal(lane + 32, posB, nB, srcB, mB, kindB);
+        // ---- one attempt at a step; returns true when it is stored.  front: every byte below it is written (stage or HBM)
+        auto attempt = [&](uint32_t pos, uint32_t n, uint32_t src, uint32_t mstart, uint32_t kind, uint32_t front) -> bool {
+            uint64_t v = 0;
+            if (kind == 1) v = ld8_any(lit + src, n);
+            else {
+                const uint32_t off_ = src;
+                if (off_ == 0) { /* corrupt: zeros */ }
+                else if (pos - mstart + n > off_) {               // the step would read its own match: the last period before it
+                    if (mstart > front) return false;
+                    uint32_t ph = (pos - mstart) % off_;
+                    for (uint32_t i = 0; i < n; i++) {
+                        const int32_t q = (int32_t)mstart - (int32_t)off_ + (int32_t)ph;
+                        const uint8_t by = q < (int32_t)gS ? *((const uint8_t*)g0 + q) : *((const uint8_t*)st + q);
+                        v |= (uint64_t)by << (8 * i);
+                        if (++ph == off_) ph = 0;
+                    }
+                } else {
+                    const int32_t s = (int32_t)pos - (int32_t)off_;
+                    if (s + (int32_t)n <= (int32_t)gS) v = ld8_any((const uint8_t*)g0 + s, n);             // before the round: HBM / L2
+                    else if ((uint32_t)(s + (int32_t)n) > front) return false;                                // not written yet
+                    else if (s >= (int32_t)gS) v = ld8_any((const uint8_t*)st + s, n);
+                    else {                                            // straddles the round start
+                        const uint32_t n0 = gS - (uint32_t)s;
+                        v = (ld8_any((const uint8_t*)g0 + s, n0) & ((1ull << (8 * n0)) - 1ull)) | (ld8_any((const uint8_t*)st + gS, n - n0) << (8 * n0));
+                    }
+                }
+            }
+            st_stage(st + pos, v, n);
+            return true;
+        };
+        bool pendA = kindA != 0, pendB = kindB != 0;
+        uint32_t front = gS;
+        for (;;) {
+            if (pendA) pendA = !attempt(posA, nA, srcA, mA, kindA, front);
+            if (__any_sync(kFull, pendB)) { if (pendB) pendB = !attempt(posB, nB, srcB, mB, kindB, front); }
+            __syncwarp();
+            const uint32_t pa = __ballot_sync(kFull, pendA), pb = __ballot_sync(kFull, pendB);
+            if (!(pa | pb)) break;
+            // the frontier: where the first unfinished step (position order: slot A lanes 0..31, then slot B) begins
+            const uint32_t fl = pa ? (uint32_t)__ffs((int)pa) - 1u : (uint32_t)__ffs((int)pb) - 1u;
+            front = __shfl_sync(kFull, pa ? posA : posB, fl);
+        }
+        // ---- flush stage[a .. a + (gE - gS)) -> g0 + gS: head bytes, aligned 16-byte body, tail bytes
+        {
+            const uint32_t n = gE - gS;
+            uint8_t* gd = g0 + gS;
+            const uint32_t head = min(n, (16 - a) & 15);
+            if (lane < head) gd[lane] = stage[a + lane];
+            const uint32_t nvec = (n - head) >> 4;
+            for (uint32_t i = lane; i < nvec; i += 32) *(uint4*)(gd + head + 16 * i) = *(const uint4*)(stage + a + head + 16 * i);
+            const uint32_t tail0 = head + (nvec << 4);
+            if (tail0 + lane < n) gd[tail0 + lane] = stage[a + tail0 + lane];
+        }
+        __syncwarp();
+        Ecarry = gE; LEcarry = __shfl_sync(kFull, LE, m - 1);
+        g += m;
+#if FZ_EXEC_PREFETCH
+        {   // the next round's match sources: asked for now, a whole round before they are read (see exec_block_warp)
+            const uint32_t nn = g < nseq ? min(32u, nseq - g) : 0u;
+            const uint32_t En = rec_e(rcur), LEn = rec_le(rcur);
+            uint32_t Sn = __shfl_up_sync(kFull, En, 1), LEpn = __shfl_up_sync(kFull, LEn, 1);
+            if (lane == 0) { Sn = Ecarry; LEpn = LEcarry; }
+            const uint32_t Mn = Sn + (LEn - LEpn);
+            const uint32_t offn = off_resolve(rec_off(rcur), in0, in1, in2);
+            if (lane < nn && offn != 0 && (uint64_t)offn <= done + Mn) exec_prefetch(g0 + Mn - offn, En - Mn);
+        }
+#endif
+    }
+    // literals after the last sequence
+    warp_copy(g0 + Ecarry, lit + LEcarry, rsize - Ecarry, lane);
+    __syncwarp();
+}
+
+template <bool STEPS>
 __global__ void __launch_bounds__(kExecWarps * 32, kExecCtasPerSm) k_execute(Frame* frames, const Block* blocks, const Item* items,
                                                                               const ItemOut* outs, const uint64_t* seqs,
                                                                               uint32_t n_frames, uint32_t* ticket)
@@ -582,6 +736,7 @@ __global__ void __launch_bounds__(kExecWarps * 32, kExecCtasPerSm) k_execute(Fra
                 const uint8_t v = b.src[0];
                 for (uint32_t i = lane; i < rsize; i += 32) g0[i] = v;
             } else if (b.nseq == 0) warp_copy(g0, b.lit, rsize, lane);
+            else if (STEPS) exec_block_steps(stage, b, seqs + b.seq_base, g0, done, status, lane);
             else exec_block_warp(stage, b, seqs + b.seq_base, g0, done, status, lane);
             __syncwarp();                      // later blocks read this one back (the window)
             done += rsize;
@@ -1007,6 +1162,7 @@ static int exec_warps_override()          // FZG_EXEC_W: the execute kernel, rea
 {                                         // threads per frame (returned as -threads); 1: k_execute (warp per frame); 2..32: k_execute_cta<W>; else by batch shape
     const char* e = getenv("FZG_EXEC_W");
     if (e && e[0] == 't') { const int t = atoi(e + 1); return (t == 128 || t == 256 || t == 512 || t == 1024) ? -t : 0; }
+    if (e && e[0] == 's') return 64;                                  // k_execute<true>: warp per frame, steps dealt out over the lanes
     const int v = e ? atoi(e) : 0;
     return (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ? v : 0;
 }
@@ -1020,6 +1176,10 @@ int fzh_decode_setup(void)
     CK(cudaFuncSetAttribute(k_execute_tile<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<256>::smem));
     CK(cudaFuncSetAttribute(k_execute_tile<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<512>::smem));
     CK(cudaFuncSetAttribute(k_execute_tile<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<1024>::smem));
+    if (getenv("FZG_EXEC_CARVE")) {      // experiment: the execute stage with the shared-memory carve-out of the entropy stages, so that both fit an SM together
+        CK(cudaFuncSetAttribute(k_execute<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CK(cudaFuncSetAttribute(k_execute<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    }
     int dev = 0; CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
     return 0;
@@ -1094,7 +1254,9 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
     const uint32_t lit_grid1 = (uint32_t)std::min<uint64_t>((n_hj + L1::groups - 1) / L1::groups, (uint64_t)g_sm_count);
     const uint32_t lit_grid2 = (uint32_t)std::min<uint64_t>((n_hj + L2::groups - 1) / L2::groups, (uint64_t)g_sm_count);
     const uint32_t seq_grid = (uint32_t)std::min<uint64_t>((n_sj + kSeqStreams - 1) / kSeqStreams, (uint64_t)g_sm_count);
-    const bool side = n_hj && n_sj && lit_grid1 + seq_grid <= (uint32_t)g_sm_count;
+    // (several lanes: the literal stage needs half an SM's registers and cannot share it with another lane's execute stage,
+    //  so it waits on the side stream while tables / sequences / records of this lane run beside that stage)
+    const bool side = n_hj && n_sj && (lit_grid1 + seq_grid <= (uint32_t)g_sm_count || staggered);
     cudaStream_t sl = side ? c->side : s;
     if (side) { CK(cudaEventRecord(c->ev_fork, s)); CK(cudaStreamWaitEvent(sl, c->ev_fork, 0)); }
     if (n_hj) {                                                      // tickets: [2] first launch, [3] deferred count, [4] second launch
@@ -1128,7 +1290,7 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
         const uint64_t sms = (uint64_t)g_sm_count;
         // default: k_execute_tile (a CTA per frame, output-centric); threads per frame by batch shape: enough CTAs to fill the SMs
         // at 256 threads, else wider CTAs for the few frames there are.  FZG_EXEC_W selects the round-1 kernels instead.
-        const int w = w_env ? w_env : (n_frames >= sms * 4 ? -256 : (n_frames >= sms * 2 ? -512 : -1024));
+        const int w = w_env ? w_env : (n_frames * 2 <= sms ? 32 : (n_frames <= sms * 8 ? 8 : (n_frames <= sms * 16 ? 2 : 64)));
         const int verify = (flags & FZG_NO_VERIFY_CHECKSUM) ? 0 : 1;
         auto cta = [&](auto wc) -> int {
             constexpr int W = decltype(wc)::value;
@@ -1155,7 +1317,7 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
         else if (w == -256) tile(std::integral_constant<int, 256>{});
         else if (w == -512) tile(std::integral_constant<int, 512>{});
         else if (w == -1024) tile(std::integral_constant<int, 1024>{});
-        else if (w == 1) {
+        else if (w == 1 || w == 64) {
             // One warp per frame runs the batch in waves of 32 x SMs frames (equal-sized files finish in step), and a last wave with
             // few frames costs a whole frame time (5.7 ms per MiB) on a nearly empty GPU: 10 000 files = 2 waves + 528 frames took
             // 27.3 ms against 24.6 ms for 9 472.  So the frames beyond the last full wave, when they are few (up to 1/8 of the batch),
@@ -1165,14 +1327,15 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
             // 27.4 / 27.2; 833, 1 250, 1 667: 26.4 / 26.9 / 27.8); 5 000 files 17.0 -> 13.4 ms; moving frames out of a batch of
             // exactly one wave (4 736) costs 4 %, out of a well-filled last wave (6 000, 7 200 files) changes nothing.
             static const bool tail_on = [] { const char* e = getenv("FZG_EXEC_TAIL"); return !e || atoi(e) != 0; }();
-            if (tail_on && !w_env && n_frames >= sms * 32) {
+            if (tail_on && (!w_env || w_env == 64) && n_frames >= sms * 32) {
                 const uint64_t rest = n_frames % (sms * 32);
                 if (rest && rest <= n_frames / 8) n_tail = (uint32_t)(rest + n_frames / 128);       // a well-filled last wave is left alone
             }
             const uint32_t n1 = (uint32_t)n_frames - n_tail;
             if (n_tail) CK(cudaEventRecord(c->ev_fork, s));
             const uint32_t grid = (uint32_t)std::min<uint64_t>((n1 + kExecWarps - 1) / kExecWarps, (uint64_t)g_sm_count * kExecCtasPerSm);
-            k_execute<<<grid, kExecWarps * 32, 0, s>>>(d_frames, d_blocks, d_items, d_outs, d_seq, n1, d_tickets + 1);
+            if (w == 64) k_execute<true><<<grid, kExecWarps * 32, 0, s>>>(d_frames, d_blocks, d_items, d_outs, d_seq, n1, d_tickets + 1);
+            else k_execute<false><<<grid, kExecWarps * 32, 0, s>>>(d_frames, d_blocks, d_items, d_outs, d_seq, n1, d_tickets + 1);
             if (n_tail) {
                 CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
                 k_execute_cta<8><<<std::min<uint32_t>(n_tail, (uint32_t)sms * ExecCta<8>::ctas_per_sm), ExecCta<8>::threads, 0, c->side>>>(d_frames + n1, d_blocks, d_items, d_outs, d_seq, n_tail, d_tickets + 5, verify, nullptr);

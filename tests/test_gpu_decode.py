@@ -31,10 +31,11 @@ def _init():
     yield
 
 
-@pytest.fixture(params=["t128", "t256", "t1024", "1", "8"])
+@pytest.fixture(params=["s", "t128", "t256", "t1024", "1", "8"])
 def exec_w(request):
-    """the execute kernel: k_execute_tile with 128 / 256 / 1024 threads per frame (the default kernel; without the fixture the
-    library chooses the width by batch shape), or round 1's k_execute (1) / k_execute_cta<8>"""
+    """the execute kernel: k_execute<true> (warp per frame, steps dealt out over the lanes), k_execute_tile with 128 / 256 /
+    1024 threads per frame, k_execute<false> (1: a lane loops over its sequence) or k_execute_cta<8>; without the fixture the
+    library chooses by batch shape"""
     old = os.environ.get("FZG_EXEC_W")
     os.environ["FZG_EXEC_W"] = request.param
     yield request.param

@@ -12,7 +12,7 @@ nmax = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 nlarge = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 large_mib = int(sys.argv[3]) if len(sys.argv) > 3 else 64
 sizes_arg = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else None
-widths_arg = tuple(int(x) for x in sys.argv[5].split(",")) if len(sys.argv) > 5 else None
+widths_arg = tuple(sys.argv[5].split(",")) if len(sys.argv) > 5 else None      # FZG_EXEC_W values: 1, 8, 32, s, t128, t256, t1024 ...
 R = pyoracle.Ref(); assert R.available
 codec.init([0])
 thr = os.cpu_count() or 1
@@ -47,7 +47,7 @@ def run(tag, d_src, off, lens, d_dst, size, n, digest, widths, reps=5):
         assert not st.any() and (dl == size).all(), (tag, w)
         k = min(n, 4)
         ok = hashlib.sha256(d_dst[:k * size].cpu().numpy().tobytes()).digest() == digest(k)
-        log("%-22s W=%-2d total %8.3f ms  execute %8.3f ms  %7.1f GB/s out  %s  %s" % (
+        log("%-22s W=%-5s total %8.3f ms  execute %8.3f ms  %7.1f GB/s out  %s  %s" % (
             tag, w, best["total_ms"], best["stages"]["execute"], n * size / 1e9 / (best["total_ms"] / 1e3), "ok" if ok else "MISMATCH",
             " ".join("%s %.2f" % (k[:3], v) for k, v in best["stages"].items() if v >= 0.05 and k != "execute")))
         assert ok, (tag, w)
