@@ -14,7 +14,15 @@ are sharded by inode (rank r owns files r*F .. r*F+F-1), no data-path collective
   roofline      dominant kernel: (compressed in + uncompressed out) bytes / its CUDA-event time vs measured HBM GB/s
   cpu_baseline  the reference's CPU path (zstd-rs copy_decode restated on libzstd, oracle/_ref) on this box's cores
 
---impl reference times only that CPU path (all host threads, bounded sample per step).
+--impl reference times only that CPU path (all host threads, the same files per step as the GPU arm).
+
+--config selects BASELINE.json's other configurations (the default, 2, is the headline and what the driver runs):
+  3  the 64 GiB corpus (65 536 x 1 MiB), partitioned over the ranks by `inode mod n` (shard.partition_by_inode; file i
+     carries inode 2^64 - 1 - i, fuse-zstd's descending counter, src/main.rs:719-753): STRONG scaling, total work fixed
+  4  large single-frame files (default 16 x 1 GiB per GPU), windowLog 23 (8 MiB window); level 3 stands in for level 19, which
+     compresses ~1 MB/s per core (a true level-19 file is in the parity tests): long match distances, few frames
+  5  the write path: fzg_encode_batch of N x 4 MiB plain files per GPU (default 10 000), every emitted file of a sample
+     decoded by libzstd and compared; ratio against libzstd level 3 reported
 """
 import argparse
 import hashlib
@@ -32,6 +40,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "zstd_decode_uncompressed_GBps"
+ENC_METRIC = "zstd_encode_uncompressed_GBps"
+ENC_FIRST = 7000000          # first file index of the config-5 corpus
 UNIT = "GB/s"
 
 
@@ -45,47 +55,56 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--files", type=int, default=10000, help="files per GPU (config 2: 10 000)")
-    ap.add_argument("--file-size", type=int, default=1 << 20)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json configuration (see the module docstring)")
+    ap.add_argument("--files", type=int, default=0, help="files per GPU (configs 2, 4, 5: 10 000 / 16 / 10 000) or in total (config 3: 65 536)")
+    ap.add_argument("--file-size", type=int, default=0, help="bytes per file (configs 2, 3: 1 MiB; 4: 1 GiB; 5: 4 MiB)")
     ap.add_argument("--level", type=int, default=3)
     ap.add_argument("--e2e-files", type=int, default=0, help="files per GPU in the host-buffer (e2e) leg (0: all, or half when host RAM is short)")
-    ap.add_argument("--cpu-files", type=int, default=4096, help="bounded sample for the CPU baseline")
+    ap.add_argument("--cpu-files", type=int, default=0, help="files per step of the CPU arm (0: the inline cpu_baseline leg takes a bounded sample, --impl reference all the files of a step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-mount", action="store_true", help="skip the read-through-the-mount leg (tools/mount_bench.py)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    a.files = a.files or {2: 10000, 3: 65536, 4: 16, 5: 10000}[a.config]
+    a.file_size = a.file_size or {2: 1 << 20, 3: 1 << 20, 4: 1 << 30, 5: 4 << 20}[a.config]
+    return a
 
 
 # ----------------------------------------------------------------------------------------------- workload
 class Workload:
-    """F files of S bytes: plain -> level-3 frames by the reference-writer restatement (oracle/_ref, libzstd);
-    packed compressed bytes stay on the host (numpy), offsets 16-byte aligned."""
+    """The files `indices` of the synthetic corpus, S bytes each: plain -> level-`level` frames by the reference-writer
+    restatement (oracle/_ref, libzstd; window_log != 0 sets ZSTD_c_windowLog); the packed compressed bytes stay on the host
+    (numpy), offsets 16-byte aligned."""
 
-    def __init__(self, first, n, size, level, threads, keep_plain=512):
+    def __init__(self, indices, size, level, threads, keep_plain=512, window_log=0):
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import pyoracle
         corpus = importlib.import_module("fuse-zstd_b200.corpus")
         pyoracle.build()
         self.ref = pyoracle.Ref()
+        idx = np.asarray(list(indices), dtype=np.int64)
+        n = len(idx)
         self.n, self.size = n, size
-        chunk = 500
+        chunk = max(1, min(500, (1 << 30) // max(size, 1)))            # <= 1 GiB of plain bytes on the host at a time
+        keep_plain = min(keep_plain, max(1, (64 << 20) // max(size, 1)))
         self.comp_len = np.zeros(n, dtype=np.uint64)
         self.comp_off = np.zeros(n, dtype=np.uint64)
         parts, off = [], 0
         self.plain_head = None
         bound = (self.ref.bound(size) if self.ref.available else size + size // 128 + 512) + 64
+        contiguous = n > 0 and bool((np.diff(idx) == 1).all())
         t_gen = t_cmp = 0.0
         for c0 in range(0, n, chunk):
             m = min(chunk, n - c0)
             t0 = time.time()
-            plain = corpus.json_files(first + c0, m, size, threads=threads)
+            plain = corpus.json_files(int(idx[c0]), m, size, threads=threads) if contiguous else corpus.json_files_idx(idx[c0:c0 + m], size, threads=threads)
             t1 = time.time()
             comp = np.empty((m, bound), dtype=np.uint8)
             if self.ref.available:
                 sp = plain.ctypes.data + np.arange(m, dtype=np.uint64) * np.uint64(size)
                 dp = comp.ctypes.data + np.arange(m, dtype=np.uint64) * np.uint64(bound)
                 _, ol, st = self.ref.batch(2, threads, sp.astype(np.uint64), np.full(m, size, dtype=np.uint64),
-                                           dp.astype(np.uint64), np.full(m, bound, dtype=np.uint64), level)
+                                           dp.astype(np.uint64), np.full(m, bound, dtype=np.uint64), level | (window_log << 8))
                 assert not st.any(), "libzstd encode failed"
             else:                                   # same image should carry libzstd; pyarrow's bundled zstd otherwise
                 import pyarrow as pa
@@ -103,21 +122,41 @@ class Workload:
                 L = int(ol[i])
                 self.comp_len[c0 + i] = L; self.comp_off[c0 + i] = off
                 off += (L + 15 & ~15) + 16
-            parts.append((comp, ol))
+            parts.append([comp[j, :int(ol[j])].copy() for j in range(m)])
+            del comp
             if c0 == 0:
                 k = min(keep_plain, m)
                 self.plain_head = plain[:k].copy()
         self.packed = np.zeros(off + 64, dtype=np.uint8)
         i = 0
-        for comp, ol in parts:
-            for j in range(len(ol)):
-                o, L = int(self.comp_off[i]), int(ol[j])
-                self.packed[o:o + L] = comp[j, :L]
+        for part in parts:
+            for blob in part:
+                o = int(self.comp_off[i])
+                self.packed[o:o + len(blob)] = blob
                 i += 1
         del parts
         self.comp_bytes = int(self.comp_len.sum())
         self.plain_bytes = n * size
         self.gen_s, self.cmp_s = t_gen, t_cmp
+
+
+def rank_files(args, rank, world):
+    """The file indices rank `rank` decodes, the scaling mode, and the name of the workload."""
+    shard = importlib.import_module("fuse-zstd_b200.shard")
+    F, S = args.files, args.file_size
+    if args.config == 3:
+        inodes = (np.uint64(0xFFFFFFFFFFFFFFFF) - np.arange(F, dtype=np.uint64))      # fuse-zstd's descending inode counter
+        mine = shard.partition_by_inode(inodes, world)[rank]
+        return mine, "strong", ("config3: the %d x %d B corpus (%.1f GiB) partitioned over %d GPU(s) by inode mod n, zstd level %d, "
+                                "reference-writer frames, device-resident" % (F, S, F * S / 2**30, world, args.level))
+    first = rank * F
+    if args.config == 4:
+        return np.arange(first + 9000000, first + 9000000 + F), "weak", (
+            "config4: %d x %d B single-frame files per GPU, windowLog 23 (8 MiB window), zstd level %d standing in for level 19, "
+            "reference-writer frames, device-resident" % (F, S, args.level))
+    return np.arange(first, first + F), "weak", (
+        "config2: batched decode of %d x %d B synthetic JSON files per GPU, zstd level %d, reference-writer frames (FCS + XXH64 "
+        "verified), device-resident" % (F, S, args.level))
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -186,11 +225,18 @@ def cpu_reference(w, threads, n_files, passes, oneshot=False):
 
 
 def run_reference(args, rank):
+    """The reference's own CPU implementation of the path on this box's host cores: copy_decode (configs 2-4) or the writer
+    (config 5) restated call for call on libzstd (oracle/_ref), all host threads, the SAME files per step as one GPU of the
+    b200 arm (--cpu-files bounds it)."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n = min(args.cpu_files, args.files)
-    w = Workload(0, n, args.file_size, args.level, threads)
+    if args.config == 5:
+        return run_reference_encode(args, threads)
+    mine, scaling, name = rank_files(args, 0, 1)
+    if args.cpu_files:
+        mine = mine[:args.cpu_files]
+    w = Workload(mine, args.file_size, args.level, threads, window_log=23 if args.config == 4 else 0)
     if not w.ref.available:
         print(json.dumps({"impl": "reference", "unavailable": "libzstd.so.1 not present on this box"})); return
     n = w.n
@@ -206,21 +252,78 @@ def run_reference(args, rank):
             ts.append(t)
     sec = sum(ts) / len(ts)
     val = n * w.size / 1e9 / sec
-    sample = "%d of the %d x %d B level-%d files per step, copy_decode restated on libzstd %d (oracle/_ref), %d threads" % (
-        n, args.files, args.file_size, args.level, w.ref.version, threads)
+    sample = "all %d files of a step (%d B each, level %d), copy_decode restated on libzstd %d (oracle/_ref), %d threads" % (
+        n, args.file_size, args.level, w.ref.version, threads)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "config2: batched decode of %d x %d B synthetic JSON files, zstd level %d" % (args.files, args.file_size, args.level),
-                   "sample_files_per_step": n, "ratio": round(w.plain_bytes / w.comp_bytes, 3)},
+        "config": {"workload": name.replace(", device-resident", ""), "files_per_gpu": n, "file_size": args.file_size, "level": args.level,
+                   "ratio": round(w.plain_bytes / w.comp_bytes, 3)},
         "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
 
+def run_reference_encode(args, threads):
+    """config 5 on the CPU: Encoder::new(level) + set_pledged_src_size + include_checksum + finish (src/main.rs:781-791) on libzstd."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    corpus = importlib.import_module("fuse-zstd_b200.corpus")
+    ref = pyoracle.Ref()
+    if not ref.available:
+        print(json.dumps({"impl": "reference", "unavailable": "libzstd.so.1 not present on this box"})); return
+    F, S = args.files, args.file_size
+    n = min(F, args.cpu_files or max(threads * 8, (8 << 30) // S))      # a step of <= 8 GiB of input: a few seconds of all cores
+    plain = corpus.json_files(ENC_FIRST, n, S, threads=threads)
+    bound = ref.bound(S) + 64
+    comp = np.empty((n, bound), dtype=np.uint8)
+    sp = (plain.ctypes.data + np.arange(n, dtype=np.uint64) * np.uint64(S)).astype(np.uint64)
+    dp = (comp.ctypes.data + np.arange(n, dtype=np.uint64) * np.uint64(bound)).astype(np.uint64)
+    sl, dc = np.full(n, S, dtype=np.uint64), np.full(n, bound, dtype=np.uint64)
+    ts = []
+    for k in range(args.warmup + args.steps):
+        t, ol, st = ref.batch(2, threads, sp, sl, dp, dc, args.level)
+        assert not st.any()
+        if k >= args.warmup:
+            ts.append(t)
+    sec = sum(ts) / len(ts)
+    val = n * S / 1e9 / sec
+    sample = "%d of the %d x %d B files per step, the reference's writer restated on libzstd %d level %d (oracle/_ref), %d threads" % (
+        n, F, S, ref.version, args.level, threads)
+    print(json.dumps({
+        "impl": "reference", "metric": ENC_METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "config5: level-%d encode of %d x %d B synthetic JSON files" % (args.level, F, S), "sample_files_per_step": n,
+                   "ratio": round(n * S / float(ol.sum()), 3)},
+        "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def bind_to_gpu_numa(index):
+    """Pins this process to the CPUs of its GPU's NUMA node (NVML), so that the pinned host buffers of the e2e leg -- first
+    touch -- and the threads that feed them are local to the GPU's PCIe root.  Returns the number of CPUs, or 0 when unknown."""
+    if os.environ.get("FZG_NUMA_BIND", "1") == "0":
+        return 0
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 1) + 63) // 64)
+        cpus = [64 * w_ + b for w_, m in enumerate(words) for b in range(64) if (m >> b) & 1]
+        cpus = sorted(set(cpus) & os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 # ----------------------------------------------------------------------------------------------- B200 arm
 def run_b200(args, rank, local_rank, world):
+    numa_cpus = bind_to_gpu_numa(gpu_index_for_nvml(local_rank)) if world > 1 else 0      # before torch allocates anything
     import torch
     import torch.distributed as dist
     assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (there is no CPU path)"
@@ -234,11 +337,17 @@ def run_b200(args, rank, local_rank, world):
     codec.init([local_rank])
     dev = local_rank
     threads = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
-    F, S = args.files, args.file_size
-    t0 = time.time()
-    w = Workload(shard.files_for_rank(rank, F)[0], F, S, args.level, threads)
-    log("[rank %d] corpus: %d files, ratio %.3f, gen %.1fs compress %.1fs (%d threads)" % (
-        rank, F, w.plain_bytes / w.comp_bytes, w.gen_s, w.cmp_s, threads))
+    if numa_cpus:
+        threads = max(1, min(threads, numa_cpus))
+        log("[rank %d] bound to the %d CPUs of GPU %d's NUMA node" % (rank, numa_cpus, local_rank))
+    if args.config == 5:
+        return run_b200_encode(args, rank, local_rank, world, codec, shard, threads)
+    S = args.file_size
+    mine, scaling, workload_name = rank_files(args, rank, world)
+    F = len(mine)                                                    # files of THIS rank
+    w = Workload(mine, S, args.level, threads, window_log=23 if args.config == 4 else 0)
+    log("[rank %d] corpus: %d files of %d B, ratio %.3f, gen %.1fs compress %.1fs (%d threads)" % (
+        rank, F, S, w.plain_bytes / w.comp_bytes, w.gen_s, w.cmp_s, threads))
 
     d_src = torch.from_numpy(w.packed).cuda()
     d_dst = torch.zeros(F * S + 256, dtype=torch.uint8, device="cuda")
@@ -282,6 +391,7 @@ def run_b200(args, rank, local_rank, world):
     clocks = sampler.result()
     ms = ev0.elapsed_time(ev1) / args.steps
     ms = shard.max_over_ranks(ms, "cuda")
+    total_plain = shard.sum_over_ranks(w.plain_bytes, "cuda")         # bytes all ranks produced per step
 
     # ---- e2e: pinned host buffers through the same C ABI call
     e2e = None
@@ -311,9 +421,10 @@ def run_b200(args, rank, local_rank, world):
         torch.cuda.synchronize()
         e_ms = (time.perf_counter() - t_0) * 1e3 / reps
         e_ms = shard.max_over_ranks(e_ms, "cuda")
-        e2e = {"value": round(world * E * S / 1e9 / (e_ms / 1e3), 3), "unit": UNIT,
+        e2e = {"value": round(shard.sum_over_ranks(E * S, "cuda") / 1e9 / (e_ms / 1e3), 3), "unit": UNIT,
                "h2d_bytes_per_step": int(w.comp_len[:E].sum()), "d2h_bytes_per_step": E * S,
-               "files_per_step_per_gpu": E, "ms_per_step": round(e_ms, 3), "timer": "host wall clock around the blocking C-ABI call"}
+               "files_per_step_per_gpu": E, "ms_per_step": round(e_ms, 3), "timer": "host wall clock around the blocking C-ABI call",
+               "numa_bound_cpus": numa_cpus}
         del h_src, h_dst
 
     if rank != 0:
@@ -345,8 +456,9 @@ def run_b200(args, rank, local_rank, world):
     cpu = None
     if not args.no_cpu_baseline and world == 1 and w.ref.available:
         allc = os.cpu_count() or 1
-        v_all, n_s = cpu_reference(w, allc, args.cpu_files, 1)
-        v_one, n_1 = cpu_reference(w, 1, max(64, args.cpu_files // 16), 1)
+        n_cpu = args.cpu_files or (4096 if S <= (4 << 20) else F)    # a bounded sample: about a second of all cores
+        v_all, n_s = cpu_reference(w, allc, n_cpu, 1)
+        v_one, n_1 = cpu_reference(w, 1, max(1, min(F, max(64 if S <= (4 << 20) else 1, n_cpu // 16))), 1)
         cpu = {"value": round(v_all, 4), "unit": UNIT, "cores": allc, "kind": "reference",
                "sample": "first %d of the %d files, copy_decode restated on libzstd %d (oracle/_ref: 131075-B reads, 8 KiB "
                          "writes), one file per thread; 1 warm + 1 timed pass" % (n_s, F, w.ref.version),
@@ -355,7 +467,7 @@ def run_b200(args, rank, local_rank, world):
     # ---- BASELINE.json's second figure, "fio read MB/s via mount": the fzfs host with the GPU codec and with the
     # reference's libzstd calls, same data directory, parallel-files.fio shape (fio itself is not in this image).  N=1 only.
     mount = None
-    if not args.no_mount and world == 1:
+    if not args.no_mount and world == 1 and args.config == 2:
         try:
             r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "mount_bench.py"), "--jobs", "16", "--nrfiles", "125"],
                                stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
@@ -371,15 +483,153 @@ def run_b200(args, rank, local_rank, world):
         except Exception as e:      # no /dev/fuse, no mount permission, timeout: the leg is reported as absent, the bench line stands
             log("mount leg unavailable: %r" % (e,))
 
-    out = {"metric": METRIC, "value": round(world * w.plain_bytes / 1e9 / (ms / 1e3), 3), "unit": UNIT, "n_gpus": world,
+    out = {"metric": METRIC, "value": round(total_plain / 1e9 / (ms / 1e3), 3), "unit": UNIT, "n_gpus": world,
            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-           "config": {"workload": "config2: batched decode of %d x %d B synthetic JSON files per GPU, zstd level %d, reference-writer "
-                                  "frames (FCS + XXH64 verified), device-resident" % (F, S, args.level),
+           "scaling": scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+           "config": {"workload": workload_name,
                       "files_per_gpu": F, "file_size": S, "level": args.level, "ratio": round(w.plain_bytes / w.comp_bytes, 3),
-                      "compressed_bytes_per_gpu": w.comp_bytes, "sharding": "by inode, no collective",
+                      "compressed_bytes_per_gpu": w.comp_bytes, "sharding": "by inode (ino mod n), no collective" if args.config == 3 else "by inode, no collective",
                       "l2": "working set %.1f GB per step >> 126 MB L2, no flush needed" % (alg_bytes / 1e9)},
            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "mount": mount}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_b200_encode(args, rank, local_rank, world, codec, shard, threads):
+    """config 5, the write path (store_to_source_file, /root/reference/src/main.rs:781-791): fzg_encode_batch over F plain files
+    of S bytes resident in HBM; every step re-encodes all of them.  Round trip and ratio are checked against libzstd on a sample."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    corpus = importlib.import_module("fuse-zstd_b200.corpus")
+    ref = pyoracle.Ref()
+    dev = local_rank
+    F, S = args.files, args.file_size
+    first = ENC_FIRST + rank * F
+    cap = codec.encode_bound(S)
+    d_src = torch.empty(F * S, dtype=torch.uint8, device="cuda")
+    d_dst = torch.zeros(F * cap, dtype=torch.uint8, device="cuda")
+    chunk = max(1, (1 << 30) // S)
+    head = None
+    t0 = time.time()
+    for c0 in range(0, F, chunk):                                    # generated and uploaded a GiB at a time
+        m = min(chunk, F - c0)
+        plain = corpus.json_files(first + c0, m, S, threads=threads)
+        d_src[c0 * S:(c0 + m) * S] = torch.from_numpy(plain.reshape(-1)).cuda()
+        if c0 == 0:
+            head = plain[:min(m, 64)].copy()
+    log("[rank %d] config 5 corpus: %d x %d B plain files in HBM, %.1fs" % (rank, F, S, time.time() - t0))
+    sp = (d_src.data_ptr() + np.arange(F, dtype=np.uint64) * np.uint64(S)).astype(np.uint64)
+    dp = (d_dst.data_ptr() + np.arange(F, dtype=np.uint64) * np.uint64(cap)).astype(np.uint64)
+    sl, dc = np.full(F, S, dtype=np.uint64), np.full(F, cap, dtype=np.uint64)
+    flags = codec.SRC_DEVICE | codec.DST_DEVICE | codec.PROFILE
+    stream = torch.cuda.ExternalStream(codec.stream_handle(dev), device=torch.device("cuda", dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        dl, st = codec.encode_batch_ptrs(dev, sp, sl, dp, dc, args.level, 0, flags)
+    assert not st.any(), "encode failed: statuses %s" % np.unique(st)
+    out_bytes = int(dl.sum())
+    # every emitted file of the sample round-trips through the reference's reader (libzstd copy_decode), byte for byte
+    k = len(head)
+    verify = None
+    if ref.available:
+        host = d_dst[:k * cap].cpu().numpy()
+        l3 = 0
+        for i in range(k):
+            s_, plain_back = ref.copy_decode(host[i * cap:i * cap + int(dl[i])].tobytes(), S)
+            assert s_ == 0 and plain_back == head[i].tobytes(), "libzstd does not reproduce file %d from the GPU encoder's output" % i
+            l3 += len(ref.writer_encode(head[i].tobytes(), args.level))
+        verify = {"files_round_tripped_through_libzstd": k, "bytes_vs_libzstd_same_level": round(float(dl[:k].sum()) / l3, 4),
+                  "libzstd_ratio": round(k * S / l3, 3)}
+    sampler = ClockSampler(gpu_index_for_nvml(local_rank)); sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_ms, launches = {}, 0
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        codec.encode_batch_ptrs(dev, sp, sl, dp, dc, args.level, 0, flags)
+        t = codec.last_timing(dev, encode=True)
+        launches += t["launches"]
+        for nm, ms_ in t["stages"].items():
+            stage_ms[nm] = stage_ms.get(nm, 0.0) + ms_
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.result()
+    ms = shard.max_over_ranks(ev0.elapsed_time(ev1) / args.steps, "cuda")
+
+    # ---- e2e: pinned host buffers, H2D of the plain bytes and D2H of the frames inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        E = min(args.e2e_files or max(64, (8 << 30) // S), F)
+        h_src = torch.empty(E * S, dtype=torch.uint8, pin_memory=True)
+        h_src.copy_(d_src[:E * S])
+        h_dst = torch.empty(E * cap, dtype=torch.uint8, pin_memory=True)
+        hsp = (h_src.data_ptr() + np.arange(E, dtype=np.uint64) * np.uint64(S)).astype(np.uint64)
+        hdp = (h_dst.data_ptr() + np.arange(E, dtype=np.uint64) * np.uint64(cap)).astype(np.uint64)
+        for _ in range(2):
+            edl, est = codec.encode_batch_ptrs(dev, hsp, sl[:E], hdp, dc[:E], args.level, 0, 0)
+        assert not est.any()
+        barrier()
+        reps = max(3, min(args.steps, 5))
+        t_0 = time.perf_counter()
+        for _ in range(reps):
+            codec.encode_batch_ptrs(dev, hsp, sl[:E], hdp, dc[:E], args.level, 0, 0)
+        torch.cuda.synchronize()
+        e_ms = shard.max_over_ranks((time.perf_counter() - t_0) * 1e3 / reps, "cuda")
+        e2e = {"value": round(world * E * S / 1e9 / (e_ms / 1e3), 3), "unit": UNIT, "h2d_bytes_per_step": E * S,
+               "d2h_bytes_per_step": int(edl.sum()), "files_per_step_per_gpu": E, "ms_per_step": round(e_ms, 3),
+               "timer": "host wall clock around the blocking C-ABI call"}
+        del h_src, h_dst
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg_bytes = F * S + out_bytes                                     # uncompressed in + compressed out (SURVEY 8d)
+    top = max(stage_ms, key=stage_ms.get)
+    top_ms = stage_ms[top] / args.steps
+    roofline = {"bound": "hbm", "kernel": top, "achieved": round(alg_bytes / 1e9 / (top_ms / 1e3), 2), "peak": peak, "unit": "GB/s",
+                "frac": round(alg_bytes / 1e9 / (top_ms / 1e3) / peak, 4), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(top_ms, 4),
+                "pipeline_frac": round(alg_bytes / 1e9 / (ms / 1e3) / peak, 4),
+                "stage_ms": {k_: round(v / args.steps, 4) for k_, v in stage_ms.items()}}
+    cpu = None
+    if not args.no_cpu_baseline and world == 1 and ref.available:
+        allc = os.cpu_count() or 1
+        n_cpu = min(F, args.cpu_files or max(allc * 8, (4 << 30) // S))
+        plain = corpus.json_files(first, n_cpu, S, threads=allc)
+        bound = ref.bound(S) + 64
+        comp = np.empty((n_cpu, bound), dtype=np.uint8)
+        csp = (plain.ctypes.data + np.arange(n_cpu, dtype=np.uint64) * np.uint64(S)).astype(np.uint64)
+        cdp = (comp.ctypes.data + np.arange(n_cpu, dtype=np.uint64) * np.uint64(bound)).astype(np.uint64)
+        csl, cdc = np.full(n_cpu, S, dtype=np.uint64), np.full(n_cpu, bound, dtype=np.uint64)
+        ref.batch(2, allc, csp, csl, cdp, cdc, args.level)
+        t_, ol_, st_ = ref.batch(2, allc, csp, csl, cdp, cdc, args.level)
+        assert not st_.any()
+        cpu = {"value": round(n_cpu * S / 1e9 / t_, 4), "unit": UNIT, "cores": allc, "kind": "reference",
+               "sample": "first %d of the %d files, the reference's writer (Encoder::new(level) + pledged size + checksum, src/main.rs:781-791) "
+                         "restated on libzstd %d level %d, one file per thread; 1 warm + 1 timed pass" % (n_cpu, F, ref.version, args.level),
+               "ratio": round(n_cpu * S / float(ol_.sum()), 3)}
+    out = {"metric": ENC_METRIC, "value": round(world * F * S / 1e9 / (ms / 1e3), 3), "unit": UNIT, "n_gpus": world,
+           "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+           "config": {"workload": "config5: level-%d multi-frame encode (release / flush of the write path) of %d x %d B synthetic JSON files per "
+                                  "GPU, FCS + XXH64 in every frame, device-resident" % (args.level, F, S),
+                      "files_per_gpu": F, "file_size": S, "level": args.level, "ratio": round(F * S / out_bytes, 3),
+                      "compressed_bytes_per_gpu": out_bytes, "sharding": "by inode, no collective", "verify": verify,
+                      "l2": "working set %.1f GB per step >> 126 MB L2, no flush needed" % (alg_bytes / 1e9)},
+           "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "mount": None}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -163,12 +163,13 @@ def encode_batch(blobs, level=3, chunk_size=0, device=0, flags=0):
     return [(int(s), o[:int(l)].tobytes()) for s, l, o in zip(st, dl, outs)]
 
 
-def last_timing(device=0):
+def last_timing(device=0, encode=False):
+    """Stage times of the last call on `device` (FZG_PROFILE); encode=True names the stages of fzg_encode_batch."""
     t = Timing()
     _check(lib().fzg_last_timing(device, C.byref(t)), "fzg_last_timing")
     stages = {}
     for k in range(16):
-        nm = lib().fzg_stage_name(k).decode()
+        nm = lib().fzg_stage_name(k + (16 if encode else 0)).decode()
         if nm:
             stages[nm] = t.kernel_ms[k]
     return dict(total_ms=t.total_ms, launches=t.launches, bytes_in=t.bytes_in, bytes_out=t.bytes_out, stages=stages)

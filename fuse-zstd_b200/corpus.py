@@ -44,3 +44,18 @@ def json_files(first, n, size, threads=None, out=None):
     if n and size:
         _get().fzc_generate_many(first, n, out.ctypes.data, size, out.strides[0], threads or os.cpu_count() or 1)
     return out
+
+
+def json_files_idx(indices, size, threads=None, out=None):
+    """-> numpy uint8[len(indices), size]: the files with the given indices (any order, e.g. one rank's shard by inode)."""
+    from concurrent.futures import ThreadPoolExecutor
+    idx = [int(i) for i in indices]
+    if out is None:
+        out = np.empty((len(idx), size), dtype=np.uint8)
+    L = _get()
+    if idx and size:
+        def one(k):
+            L.fzc_generate(idx[k], out[k].ctypes.data, size)            # ctypes releases the GIL
+        with ThreadPoolExecutor(threads or os.cpu_count() or 1) as ex:
+            list(ex.map(one, range(len(idx))))
+    return out

@@ -217,7 +217,7 @@ static void* batch_worker(void* arg)
         size_t o = 0; int rc;
         if (b->mode == 0) rc = fzr_copy_decode(b->src[i], b->src_len[i], b->dst[i], b->dst_cap[i], &o);
         else if (b->mode == 1) rc = fzr_decode_oneshot(b->src[i], b->src_len[i], b->dst[i], b->dst_cap[i], &o);
-        else rc = fzr_writer_encode(b->src[i], b->src_len[i], b->dst[i], b->dst_cap[i], b->level, 1, 1, 0, &o);
+        else rc = fzr_writer_encode(b->src[i], b->src_len[i], b->dst[i], b->dst_cap[i], b->level & 0xFF, 1, 1, (b->level >> 8) & 0xFF, &o);   /* level | windowLog << 8 */
         b->out_len[i] = o; b->status[i] = rc;
     }
     return NULL;
