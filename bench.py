@@ -321,6 +321,48 @@ def bind_to_gpu_numa(index):
         return 0
 
 
+def host_link_ceiling(torch, shard, barrier, h_src, h_dst, d_src, d_dst, in_bytes, out_bytes):
+    """What the box's host link lets `e2e` reach at most, measured with the e2e leg's own pinned buffers on all ranks AT ONCE
+    (tools/pcie_bw.py is the stand-alone version): H2D alone, D2H alone, both together -> GB/s summed over the ranks.  The
+    ceiling models a step as: both directions busy until the compressed input (the smaller side) is in, then D2H alone."""
+    n_in, n_out = min(in_bytes, 1 << 30), min(out_bytes, 1 << 30)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def h2d():
+        with torch.cuda.stream(s1):
+            d_src[:n_in].copy_(h_src[:n_in], non_blocking=True)
+
+    def d2h():
+        with torch.cuda.stream(s2):
+            h_dst[:n_out].copy_(d_dst[:n_out], non_blocking=True)
+
+    def timed(fs, reps=3):
+        for f in fs:
+            f()
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            for f in fs:
+                f()
+        torch.cuda.synchronize()
+        return shard.max_over_ranks((time.perf_counter() - t0) / reps, "cuda")
+    try:
+        t_h, t_d, t_b = timed([h2d]), timed([d2h]), timed([h2d, d2h])
+        tot_in, tot_out = shard.sum_over_ranks(n_in, "cuda"), shard.sum_over_ranks(n_out, "cuda")
+        r_h, r_d = tot_in / 1e9 / t_h, tot_out / 1e9 / t_d                      # alone
+        r_b = (tot_in + tot_out) / 1e9 / t_b                                    # both directions at once, in + out
+        step_in, step_out = shard.sum_over_ranks(in_bytes, "cuda") / 1e9, shard.sum_over_ranks(out_bytes, "cuda") / 1e9
+        t_overlap = 2 * step_in / r_b                                           # each direction gets about half of r_b while both run
+        t_step = t_overlap + max(0.0, step_out - step_in) / r_d
+        return {"h2d_alone_GBps": round(r_h, 2), "d2h_alone_GBps": round(r_d, 2), "both_GBps": round(r_b, 2),
+                "ceiling_GBps": round(step_out / t_step, 2), "how": "pinned copies of <= 1 GiB on every rank at once; ceiling = uncompressed "
+                "bytes / (2 x in / both + (out - in) / d2h_alone)"}
+    except Exception as e:       # pragma: no cover
+        log("host link probe failed: %r" % (e,))
+        return None
+
+
 # ----------------------------------------------------------------------------------------------- B200 arm
 def run_b200(args, rank, local_rank, world):
     numa_cpus = bind_to_gpu_numa(gpu_index_for_nvml(local_rank)) if world > 1 else 0      # before torch allocates anything
@@ -421,10 +463,12 @@ def run_b200(args, rank, local_rank, world):
         torch.cuda.synchronize()
         e_ms = (time.perf_counter() - t_0) * 1e3 / reps
         e_ms = shard.max_over_ranks(e_ms, "cuda")
+        link = host_link_ceiling(torch, shard, barrier, h_src, h_dst, d_src, d_dst, src_bytes, E * S)
         e2e = {"value": round(shard.sum_over_ranks(E * S, "cuda") / 1e9 / (e_ms / 1e3), 3), "unit": UNIT,
                "h2d_bytes_per_step": int(w.comp_len[:E].sum()), "d2h_bytes_per_step": E * S,
                "files_per_step_per_gpu": E, "ms_per_step": round(e_ms, 3), "timer": "host wall clock around the blocking C-ABI call",
-               "numa_bound_cpus": numa_cpus}
+               "numa_bound_cpus": numa_cpus, "host_link": link,
+               "frac_of_host_link_ceiling": round(shard.sum_over_ranks(E * S, "cuda") / 1e9 / (e_ms / 1e3) / link["ceiling_GBps"], 3) if link else None}
         del h_src, h_dst
 
     if rank != 0:

@@ -1304,7 +1304,15 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
                 grid = (uint32_t)n_frames * 2;
                 checksum_done = true;
             }
-            k_execute_cta<W><<<grid, ExecCta<W>::threads, 0, s>>>(d_frames, d_blocks, d_items, d_outs, d_seq, (uint32_t)n_frames, d_tickets + 1, verify, gprog);
+            if (gprog) {
+                // The checksum CTAs wait for the executing CTAs of the same grid: a COOPERATIVE launch makes the runtime guarantee that
+                // every CTA of the grid is resident at once (it refuses the launch otherwise) instead of this code arguing it.
+                Frame* a0 = d_frames; const Block* a1 = d_blocks; const Item* a2 = d_items; const ItemOut* a3 = d_outs; const uint64_t* a4 = d_seq;
+                uint32_t a5 = (uint32_t)n_frames; uint32_t* a6 = d_tickets + 1; int a7 = verify; unsigned long long* a8 = gprog;
+                void* args[] = { &a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8 };
+                CK(cudaLaunchCooperativeKernel((const void*)k_execute_cta<W>, dim3(grid), dim3(ExecCta<W>::threads), args, 0, s));
+            } else
+                k_execute_cta<W><<<grid, ExecCta<W>::threads, 0, s>>>(d_frames, d_blocks, d_items, d_outs, d_seq, (uint32_t)n_frames, d_tickets + 1, verify, gprog);
             if (ExecCta<W>::hash) checksum_done = true;
             return 0;
         };

@@ -322,3 +322,37 @@ def test_untrusted_sizes_in_the_fd_entry_point(ref):
         assert codec.decode_fd(src.fileno(), dst.fileno()) == len(plain)
         dst.seek(0)
         assert hashlib.sha256(dst.read()).digest() == hashlib.sha256(plain).digest()
+
+
+def test_guard_bands_around_every_output(golden, exec_w):
+    """compute-sanitizer is closed on this pool (profiles/r02_compute_sanitizer_closed.txt), so the bounds are checked the
+    plain way: every output of a device-resident batch (all golden frames + mutated copies of them, which fail half way
+    through) sits between two 256-byte guard bands and is given exactly its capacity; no kernel may touch a guard."""
+    import torch
+    rng = np.random.default_rng(77)
+    names = [n for n in sorted(golden) if golden[n][1]["plain_len"] > 0]
+    blobs, caps = [], []
+    for n in names:
+        comp, meta = golden[n]
+        blobs.append(bytes(comp)); caps.append(meta["plain_len"])
+        for _ in range(3):                                        # corrupted twins: wrong sizes, bad offsets, broken streams
+            b = bytearray(comp)
+            for _ in range(int(rng.integers(1, 4))):
+                b[int(rng.integers(4, len(b)))] ^= 1 << int(rng.integers(0, 8))
+            blobs.append(bytes(b)); caps.append(meta["plain_len"])
+    G = 256
+    offs, tot = [], 0
+    for c in caps:
+        offs.append(tot + G); tot += G + ((c + 255) & ~255) + G
+    d_dst = torch.full((tot,), 0xA5, dtype=torch.uint8, device="cuda")
+    srcs = [torch.frombuffer(bytearray(b), dtype=torch.uint8).cuda() for b in blobs]
+    torch.cuda.synchronize()
+    dl, st = codec.decode_batch_ptrs(0, [s.data_ptr() for s in srcs], [s.numel() for s in srcs],
+                                     [d_dst.data_ptr() + o for o in offs], caps, codec.SRC_DEVICE | codec.DST_DEVICE)
+    host = d_dst.cpu().numpy()
+    for i, (o, c) in enumerate(zip(offs, caps)):
+        assert (host[o - G:o] == 0xA5).all(), "wrote before output %d" % i
+        assert (host[o + c:o + ((c + 255) & ~255) + G] == 0xA5).all(), "wrote past the capacity of output %d" % i
+    for k, n in enumerate(names):                                 # the intact ones are still right
+        i = 4 * k
+        assert st[i] == 0 and dl[i] == caps[i] and sha(host[offs[i]:offs[i] + caps[i]].tobytes()) == golden[n][1]["plain_sha256"], n
