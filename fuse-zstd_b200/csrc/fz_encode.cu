@@ -3,11 +3,14 @@
  * /root/reference/src/main.rs:781-791 (Encoder::new(level) + set_pledged_src_size + include_checksum(true) +
  * io::copy + finish) for a whole batch of files per call.
  *
- * Output format: every file becomes a concatenation of INDEPENDENT frames, one per chunk of <= 128 KiB of
- * input, each with Frame_Content_Size, Single_Segment and the XXH64 content checksum (what the reference's
- * writer sets), holding one block (Compressed, or Raw when that is not smaller).  The reference's decoder
- * (zstd::stream::copy_decode, /root/reference/src/main.rs:463) reads concatenated frames as one file, and
- * independent frames are what lets both this encoder and the decoder run one CTA / warp per frame.
+ * Output format: every file becomes a concatenation of INDEPENDENT frames of <= `chunk_size` bytes of input (default
+ * 1 MiB), each with Frame_Content_Size, Single_Segment and the XXH64 content checksum (what the reference's writer
+ * sets), holding blocks of <= 128 KiB (Compressed, or Raw when that is not smaller).  The blocks of a frame SHARE THE
+ * WINDOW: a match may reach up to 64 KiB back, into the previous blocks of its frame.  The unit of parallel work is still
+ * the block ("chunk"): its matcher first seeds its hash tables from the 64 KiB of the frame before it, and it spends repeat
+ * codes only once its own first three offsets have defined the history (a block does not know the history the previous
+ * block ends with -- blocks are matched in parallel -- and after three plain offsets it no longer matters).  The
+ * reference's decoder (zstd::stream::copy_decode, /root/reference/src/main.rs:463) reads concatenated frames as one file.
  * `level` is accepted as the reference passes it (0..19, 0 => default) and selects the one strategy
  * implemented here, which sits below libzstd level 3 in ratio.
  *
@@ -51,19 +54,35 @@ constexpr uint32_t kEncMatchWarps = FZ_ENC_MATCH_WARPS;      // warps (= chunks 
 #ifndef FZ_ENC_LAZY
 #define FZ_ENC_LAZY 1
 #endif
-// Level >= 3: the matcher keeps a SECOND table, 2^kEncLongLog 16-bit entries per warp keyed by an 8-byte hash, in global memory
-// (i.e. in L2: 64 KB per warp, ~1800 warps resident), and hashes 5 bytes instead of 4 for the shared-memory table: 128 Ki
-// positions per chunk want more than 8 Ki slots.  Measured (256 x 4 MiB JSON): ratio 2.40 -> 2.63 (x1.26 -> x1.145 of libzstd
-// level 3's bytes) for 16.5 -> ~12.5 GB/s; both tables in L2 cost twice the L2 transactions for the same ratio (every 2-byte
-// table access is a 32-byte sector transaction, which is what bounds the stage then).  Levels 1-2 keep the single table.
-#ifndef FZ_ENC_LONGLOG
-#define FZ_ENC_LONGLOG 15
-#endif
+// Matcher modes, chosen by the level the reference passes (src/main.rs:781-785; 0 = libzstd's default = 3):
+//   0  levels 1-2   the shared-memory table alone (4-byte hash, 2^13 16-bit entries per warp, 64 KiB of reach)
+//   1  levels 0, 3  + a SECOND table per warp in global memory (i.e. in L2), keyed by an 8-byte hash: 2^16 16-bit entries (the low
+//                   bits of a frame position: 64 KiB of reach); the shared table then hashes 5 bytes
+//   2  levels 4-19  the second table holds whole frame positions in 32 bits and reaches 256 KiB back, across the blocks of a frame
+// Measured on 256 x 4 MiB JSON (libzstd level 3: ratio 3.015), GB/s of input / ratio / bytes against libzstd level 3:
+//   mode 0: 14.9 / 2.42 / x1.246;   mode 1: 10.1 / 2.716 / x1.110;   mode 2: 7.3 / 2.762 / x1.092
+//   (mode 1 with 2^15 / 2^17 entries: 10.8 / 2.682 and 9.6 / 2.736; mode 2 with 2^15 entries: 8.2 / 2.695, with 1 MiB of reach: 6.8 /
+//   2.695 -- what buys ratio is slots, not reach: 65 % of libzstd's own matches lie within 64 KiB, 90 % within 256 KiB,
+//   profiles/r02_match_histogram.json.  Every 2- or 4-byte table access is a 32-byte sector transaction in L2, which is what
+//   bounds the stage.)
 #ifndef FZ_ENC_PREFETCH
 #define FZ_ENC_PREFETCH 1
 #endif
-constexpr uint32_t kEncLongLog = FZ_ENC_LONGLOG;
-constexpr uint32_t kEncLongBytes = 2u << kEncLongLog;          // the long table of one warp
+template <int MODE> struct EncMode {
+    static constexpr bool has_long = MODE != 0, wide = MODE == 2;
+    static constexpr uint32_t long_log = 16;
+    static constexpr uint32_t long_bytes = has_long ? (wide ? 4u : 2u) << long_log : 0u;      // the long table of one warp
+    static constexpr uint32_t long_window = wide ? 256u * 1024u : 65535u;
+    static constexpr uint32_t window = has_long ? long_window : 65535u;                      // farthest candidate of any table
+    __device__ static __forceinline__ uint32_t put(uint32_t P) { return wide ? P + 1 : (P & 0xFFFFu); }
+    __device__ static __forceinline__ int32_t get(uint32_t el, uint32_t P)
+    {
+        if (wide) return (int32_t)el - 1;                              // 0 = empty
+        int32_t c = (int32_t)((P & ~0xFFFFu) | el); if (c >= (int32_t)P) c -= 65536; return c;
+    }
+    __device__ static __forceinline__ uint32_t load(const uint8_t* t, uint32_t h) { return wide ? ((const uint32_t*)t)[h] : (uint32_t)((const uint16_t*)t)[h]; }
+    __device__ static __forceinline__ void store(uint8_t* t, uint32_t h, uint32_t P) { if (wide) ((uint32_t*)t)[h] = put(P); else ((uint16_t*)t)[h] = (uint16_t)put(P); }
+};
 constexpr uint32_t kHufMaxLen = 11;
 
 struct EncChunk {
@@ -75,7 +94,11 @@ struct EncChunk {
     uint32_t lit_sec, seq_sec;   // section sizes in bytes (0 lit_sec = not compressible -> raw block)
     uint32_t frame_size;     // bytes this chunk occupies in the output
     uint32_t raw;            // 1: the block is stored Raw (set by k_enc_place)
-    uint64_t out_off;        // offset of the frame inside the item's dst
+    uint64_t out_off;        // offset of this block's bytes (frame header included for a frame's first block) inside the item's dst
+    uint32_t foff;           // offset of the chunk inside its frame: src - foff is the frame's first byte
+    uint32_t fsize;          // content size of the frame
+    uint32_t nblk;           // blocks in the frame (meaningful in the frame's first chunk)
+    uint32_t pad;
 };
 
 // scratch layout per chunk (offsets from EncChunk::scratch); sized for the worst case
@@ -101,13 +124,15 @@ __device__ __forceinline__ uint64_t ld8u(const uint8_t* g)   // 8 bytes at any a
 }
 
 // ------------------------------------------------------------------ LZ77 matching
-template <bool LONG>
+template <int MODE>
 __global__ void __launch_bounds__(kEncMatchWarps * 32) k_enc_match(EncChunk* chunks, uint32_t n_chunks, uint32_t* ticket, uint8_t* gtab)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t* table = (uint16_t*)smem + warp * (1u << kEncHashLog);
-    uint16_t* ltable = LONG ? (uint16_t*)(gtab + (size_t)(blockIdx.x * kEncMatchWarps + warp) * kEncLongBytes) : nullptr;
+    using EM = EncMode<MODE>;
+    constexpr bool LONG = EM::has_long;
+    uint8_t* ltable = LONG ? gtab + (size_t)(blockIdx.x * kEncMatchWarps + warp) * EM::long_bytes : nullptr;
     for (;;) {
         uint32_t ci = 0;
         if (lane == 0) ci = atomicAdd(ticket, 1);
@@ -115,14 +140,30 @@ __global__ void __launch_bounds__(kEncMatchWarps * 32) k_enc_match(EncChunk* chu
         if (ci >= n_chunks) return;
         EncChunk& ch = chunks[ci];
         const uint8_t* __restrict__ src = ch.src;
-        const uint32_t size = ch.size;
+        const uint32_t size = ch.size, foff = ch.foff;
+        const uint8_t* __restrict__ fsrc = src - foff;                     // the frame: table entries and candidates are frame positions
         uint8_t* lit = ch.scratch + kScrLit;
         uint64_t* seq = (uint64_t*)(ch.scratch + kScrSeq);
         for (uint32_t i = lane; i < (1u << kEncHashLog) / 8; i += 32) ((uint4*)table)[i] = make_uint4(0, 0, 0, 0);
-        if constexpr (LONG) for (uint32_t i = lane; i < (1u << kEncLongLog) / 8; i += 32) ((uint4*)ltable)[i] = make_uint4(0, 0, 0, 0);
+        if constexpr (LONG) for (uint32_t i = lane; i < EM::long_bytes / 16; i += 32) ((uint4*)ltable)[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        // ---- the window of the previous blocks: the tables are seeded with the positions of the 64 KiB before this block
+        // (inserts only; when several lanes of a step hash alike any one of them stays, and every candidate is verified)
+        for (uint32_t q0 = foff > EM::window ? foff - EM::window : 0; q0 < foff; q0 += 32) {
+            const uint32_t q = q0 + lane;
+            if (q < foff) {
+                const uint64_t v = ld8u(fsrc + q);
+                if constexpr (LONG) {
+                    if (foff - q <= kEncMaxOff) table[(uint32_t)(((v << 24) * 0x9E3779B185EBCA87ull) >> (64 - kEncHashLog))] = (uint16_t)q;
+                    EM::store(ltable, (uint32_t)((v * 0x9E3779B185EBCA87ull) >> (64 - EM::long_log)), q);
+                } else table[((uint32_t)v * 2654435761u) >> (32 - kEncHashLog)] = (uint16_t)q;
+            }
+        }
         __syncwarp();
         uint32_t anchor = 0, cur = 0, nseq = 0, nlit = 0;
-        uint32_t rep0 = 1, rep1 = 4, rep2 = 8;                              // repeat-offset history of a frame's first block (RFC 8878 3.1.1.5)
+        // repeat-offset history: {1, 4, 8} at the start of a frame (RFC 8878 3.1.1.5); a later block learns it from its own first
+        // three offsets (`known`) and spends no repeat code before that
+        uint32_t rep0 = 1, rep1 = 4, rep2 = 8, known = foff == 0 ? 3u : 0u;
         // positions whose 8-byte probe would run past the chunk are left to the trailing literals
         const uint32_t limit = size >= 16 ? size - 12 : 0;
         // The step's 8 input bytes and (LONG) its long-table entries are loaded one step EARLY, so that neither load sits on
@@ -131,7 +172,7 @@ __global__ void __launch_bounds__(kEncMatchWarps * 32) k_enc_match(EncChunk* chu
         uint64_t v_nx = 0; uint32_t hl_nx = 0, el_nx = 0;
         if (lane < limit) {
             v_nx = ld8u(src + lane);
-            if constexpr (LONG) { hl_nx = (uint32_t)((v_nx * 0x9E3779B185EBCA87ull) >> (64 - kEncLongLog)); el_nx = ltable[hl_nx]; }
+            if constexpr (LONG) { hl_nx = (uint32_t)((v_nx * 0x9E3779B185EBCA87ull) >> (64 - EM::long_log)); el_nx = EM::load(ltable, hl_nx); }
         }
         for (uint32_t base = 0; base < limit; base += 32) {
             const uint32_t p = base + lane;
@@ -140,13 +181,13 @@ __global__ void __launch_bounds__(kEncMatchWarps * 32) k_enc_match(EncChunk* chu
             uint32_t h = 0;
             if (p + 32 < limit) {
                 v_nx = ld8u(src + p + 32);
-                if constexpr (LONG) { hl_nx = (uint32_t)((v_nx * 0x9E3779B185EBCA87ull) >> (64 - kEncLongLog)); el_nx = ltable[hl_nx]; }
+                if constexpr (LONG) { hl_nx = (uint32_t)((v_nx * 0x9E3779B185EBCA87ull) >> (64 - EM::long_log)); el_nx = EM::load(ltable, hl_nx); }
             }
 #if FZ_ENC_PREFETCH
             if constexpr (LONG) {                                           // this step's long candidate: its bytes are needed ~100 instructions from now
                 if (in) {
-                    int32_t c = (int32_t)((p & ~0xFFFFu) | el); if (c >= (int32_t)p) c -= 65536;
-                    if (c >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + c));
+                    const int32_t c = EM::get(el, foff + p);
+                    if (c >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(fsrc + c));
                 }
             }
 #endif
@@ -157,13 +198,14 @@ __global__ void __launch_bounds__(kEncMatchWarps * 32) k_enc_match(EncChunk* chu
             // candidates: the nearest earlier lane of this step with the same hash, else the table
             const uint32_t same = __match_any_sync(0xFFFFFFFFu, in ? h : (0x80000000u | lane));
             const uint32_t below = same & ((1u << lane) - 1);
-            int32_t cand = -1;
+            const uint32_t P = foff + p;                                    // frame position of this lane
+            int32_t cand = -1;                                              // candidates are frame positions (< P), possibly in an earlier block
             if (in) {
-                if (below) cand = (int32_t)(base + (31 - __clz(below)));
+                if (below) cand = (int32_t)(foff + base + (31 - __clz(below)));
                 else {
                     const uint32_t e = table[h];
-                    int32_t c = (int32_t)((p & ~0xFFFFu) | e);
-                    if (c >= (int32_t)p) c -= 65536;
+                    int32_t c = (int32_t)((P & ~0xFFFFu) | e);
+                    if (c >= (int32_t)P) c -= 65536;
                     cand = c;
                 }
             }
@@ -172,26 +214,26 @@ __global__ void __launch_bounds__(kEncMatchWarps * 32) k_enc_match(EncChunk* chu
                 samel = __match_any_sync(0xFFFFFFFFu, in ? hl : (0x80000000u | lane));
                 const uint32_t belowl = samel & ((1u << lane) - 1);
                 if (in && p >= cur) {
-                    if (belowl) candl = (int32_t)(base + (31 - __clz(belowl)));
-                    else { int32_t c = (int32_t)((p & ~0xFFFFu) | el); if (c >= (int32_t)p) c -= 65536; candl = c; }
+                    if (belowl) candl = (int32_t)(foff + base + (31 - __clz(belowl)));
+                    else candl = EM::get(el, P);
                 }
             }
             __syncwarp();
-            if (in && (same >> lane) == 1) table[h] = (uint16_t)p;          // the highest lane of a group records it
+            if (in && (same >> lane) == 1) table[h] = (uint16_t)P;          // the highest lane of a group records it
             if constexpr (LONG) {
-                if (in && (samel >> lane) == 1) ltable[hl] = (uint16_t)p;
+                if (in && (samel >> lane) == 1) EM::store(ltable, hl, P);
                 // keep the candidate that shares the longer prefix of the first 8 bytes (the nearer one on a tie)
                 if (in && p >= cur) {
-                    const bool okl = candl >= 0 && p - (uint32_t)candl <= kEncMaxOff, oks = cand >= 0 && p - (uint32_t)cand <= kEncMaxOff;
-                    const uint64_t xl = okl ? ld8u(src + candl) ^ v : 1ull, xs = oks ? ld8u(src + cand) ^ v : 1ull;
+                    const bool okl = candl >= 0 && P - (uint32_t)candl <= EM::long_window, oks = cand >= 0 && P - (uint32_t)cand <= kEncMaxOff;
+                    const uint64_t xl = okl ? ld8u(fsrc + candl) ^ v : 1ull, xs = oks ? ld8u(fsrc + cand) ^ v : 1ull;
                     const uint32_t pl = xl ? (uint32_t)(__ffsll((long long)xl) - 1) >> 3 : 8u, ps = xs ? (uint32_t)(__ffsll((long long)xs) - 1) >> 3 : 8u;
                     if (!oks || (okl && (pl > ps || (pl == ps && candl > cand)))) cand = okl ? candl : -1;
                 }
             }
             // verify + extend (8 bytes per probe)
             uint32_t len = 0;
-            if (in && p >= cur && cand >= 0 && p - (uint32_t)cand <= kEncMaxOff) {
-                const uint8_t* a = src + cand; const uint8_t* b = src + p;
+            if (in && p >= cur && cand >= 0 && P - (uint32_t)cand <= EM::window) {
+                const uint8_t* a = fsrc + cand; const uint8_t* b = src + p;
                 const uint32_t maxlen = size - p;
                 uint64_t x = ld8u(a) ^ v;
                 if ((uint32_t)x == 0) {                                     // at least 4 bytes
@@ -216,7 +258,7 @@ __global__ void __launch_bounds__(kEncMatchWarps * 32) k_enc_match(EncChunk* chu
                 // match starting at the next byte wins and this byte becomes a literal
                 if (pl >= cur && l < 31 && ((avail >> (l + 1)) & 1u) && __shfl_sync(0xFFFFFFFFu, len, l + 1) > ml) { avail &= ~(1u << l); continue; }
 #endif
-                const uint32_t off = pl - (uint32_t)__shfl_sync(0xFFFFFFFFu, cand, l);
+                const uint32_t off = foff + pl - (uint32_t)__shfl_sync(0xFFFFFFFFu, cand, l);
                 if (pl >= cur) {
                     const uint32_t ll = pl - anchor;
                     for (uint32_t i = lane; i < ll; i += 32) lit[nlit + i] = src[anchor + i];
@@ -225,7 +267,8 @@ __global__ void __launch_bounds__(kEncMatchWarps * 32) k_enc_match(EncChunk* chu
                     // repeat code costs 2-3 bits against ~16 for a distance.
                     uint32_t ov = off + 3;
                     const uint32_t r0 = rep0, r1 = rep1, r2 = rep2;
-                    if (ll) {
+                    if (known < 3) { known++; rep0 = off; rep1 = r0; rep2 = r1; }     // history still unknown: a plain offset
+                    else if (ll) {
                         if (off == r0) ov = 1;
                         else if (off == r1) { ov = 2; rep0 = r1; rep1 = r0; }
                         else { if (off == r2) ov = 3; rep0 = off; rep1 = r0; rep2 = r1; }
@@ -561,7 +604,7 @@ __global__ void __launch_bounds__(kSeqEncWarps * 32) k_enc_seq(EncChunk* chunks,
                 if (hi == nseq && k == 0) { sML = init_state(2, rML, mc); sOF = init_state(1, rOF, oc); sLL = init_state(0, rLL, lc); }
                 else { enc(1, rOF, sOF, oc); enc(2, rML, sML, mc); enc(0, rLL, sLL, lc); drain(); }   // <= 8 + 9 + 9 bits on top of < 32
                 add(l & 0xFFFF, (c >> 22) & 31); add(l >> 16, c >> 27); drain();                       // <= 16 + 16
-                add(o, oc); drain();                                                                    // <= 17 here (offsets < 64 KiB)
+                add(o, oc); drain();                                                                    // <= 24 here (offsets inside a frame of <= 8 MiB)
             }
             hi -= cnt;
             // this batch's whole words -> HBM
@@ -605,24 +648,33 @@ __global__ void k_enc_place(const Item* items, EncChunk* chunks, const uint32_t*
     if (i >= n_items) return;
     uint64_t pos = 0; int status = 0;
     const uint32_t c0 = first_chunk[i], c1 = first_chunk[i + 1];
+    uint32_t nf = 0;
     for (uint32_t c = c0; c < c1; c++) {
         EncChunk& ch = chunks[c];
         const uint32_t body = ch.lit_sec + ch.seq_sec;
         const bool compressed = ch.size >= 32 && body + 8 < ch.size && body < kEncChunkMax;
         ch.raw = compressed ? 0 : 1;
-        ch.frame_size = frame_header_size(ch.size) + 3 + (compressed ? body : ch.size) + 4;
+        const bool first = ch.foff == 0, last = ch.foff + ch.size == ch.fsize;
+        // the bytes this block puts into the file: the frame header before a frame's first block, the checksum after its last
+        ch.frame_size = (first ? frame_header_size(ch.fsize) : 0) + 3 + (compressed ? body : ch.size) + (last ? 4 : 0);
         ch.out_off = pos; pos += ch.frame_size;
+        nf += first;
     }
-    const uint32_t nf = c1 - c0;
     const uint64_t table_at = pos;
     if (seek) pos += 8 + 8ull * nf + 9;
     if (pos > items[i].dst_cap) status = FZG_E_DSTSIZE;
     if (seek && !status) {
         uint8_t* t = items[i].dst + table_at;
         st32le(t, 0x184D2A5Eu); st32le(t + 4, 8 * nf + 9);
-        for (uint32_t c = c0; c < c1; c++) { st32le(t + 8 + 8 * (c - c0), chunks[c].frame_size); st32le(t + 12 + 8 * (c - c0), chunks[c].size); }
-        uint8_t* f = t + 8 + 8ull * nf;
-        st32le(f, nf); f[4] = 0; st32le(f + 5, 0x8F92EAB1u);
+        uint32_t f = 0;
+        for (uint32_t c = c0; c < c1;) {                              // one entry per frame: (compressed size, content size)
+            uint32_t csz = 0; const uint32_t nb = chunks[c].nblk;
+            for (uint32_t k = 0; k < nb; k++) csz += chunks[c + k].frame_size;
+            st32le(t + 8 + 8 * f, csz); st32le(t + 12 + 8 * f, chunks[c].fsize);
+            c += nb; f++;
+        }
+        uint8_t* e = t + 8 + 8ull * nf;
+        st32le(e, nf); e[4] = 0; st32le(e + 5, 0x8F92EAB1u);
     }
     outs[i].dst_len = status ? 0 : pos; outs[i].status = status; outs[i].fail = status != 0;
 }
@@ -635,25 +687,20 @@ __global__ void __launch_bounds__(128) k_enc_write(const Item* items, const EncC
     const EncChunk& ch = chunks[ci];
     if (outs[ch.item].fail) return;
     uint8_t* o = items[ch.item].dst + ch.out_off;
-    const uint32_t size = ch.size;
-    const bool compressed = ch.raw == 0;
+    const uint32_t size = ch.size, fsize = ch.fsize;
+    const bool compressed = ch.raw == 0, first = ch.foff == 0, last = ch.foff + size == fsize;
     const uint32_t body = compressed ? ch.lit_sec + ch.seq_sec : size;
-    const uint32_t fh = frame_header_size(size);
-    // XXH64 of the chunk: lanes 0..3 own one accumulator each
-    uint64_t acc = lane < 4 ? xx_lane(ch.src, size, lane) : 0;
-    const uint64_t v1 = __shfl_sync(0xFFFFFFFFu, acc, 0), v2 = __shfl_sync(0xFFFFFFFFu, acc, 1), v3 = __shfl_sync(0xFFFFFFFFu, acc, 2),
-                   v4 = __shfl_sync(0xFFFFFFFFu, acc, 3);
+    const uint32_t fh = first ? frame_header_size(fsize) : 0;
     if (lane == 0) {
-        o[0] = 0x28; o[1] = 0xB5; o[2] = 0x2F; o[3] = 0xFD;
-        // Frame_Header_Descriptor: FCS flag | Single_Segment | Content_Checksum (what the reference's writer sets)
-        if (size < 256) { o[4] = 0x24; o[5] = (uint8_t)size; }
-        else if (size < 65536 + 256) { o[4] = 0x64; o[5] = (uint8_t)(size - 256); o[6] = (uint8_t)((size - 256) >> 8); }
-        else { o[4] = 0xA4; o[5] = (uint8_t)size; o[6] = (uint8_t)(size >> 8); o[7] = (uint8_t)(size >> 16); o[8] = (uint8_t)(size >> 24); }
-        const uint32_t bh = 1u | ((compressed ? 2u : 0u) << 1) | (body << 3);          // Last_Block | type | size
+        if (first) {
+            o[0] = 0x28; o[1] = 0xB5; o[2] = 0x2F; o[3] = 0xFD;
+            // Frame_Header_Descriptor: FCS flag | Single_Segment | Content_Checksum (what the reference's writer sets)
+            if (fsize < 256) { o[4] = 0x24; o[5] = (uint8_t)fsize; }
+            else if (fsize < 65536 + 256) { o[4] = 0x64; o[5] = (uint8_t)(fsize - 256); o[6] = (uint8_t)((fsize - 256) >> 8); }
+            else { o[4] = 0xA4; o[5] = (uint8_t)fsize; o[6] = (uint8_t)(fsize >> 8); o[7] = (uint8_t)(fsize >> 16); o[8] = (uint8_t)(fsize >> 24); }
+        }
+        const uint32_t bh = (last ? 1u : 0u) | ((compressed ? 2u : 0u) << 1) | (body << 3);          // Last_Block | type | size
         o[fh] = (uint8_t)bh; o[fh + 1] = (uint8_t)(bh >> 8); o[fh + 2] = (uint8_t)(bh >> 16);
-        const uint32_t x = (uint32_t)xx_combine(v1, v2, v3, v4, ch.src, size);
-        uint8_t* t = o + fh + 3 + body;
-        t[0] = (uint8_t)x; t[1] = (uint8_t)(x >> 8); t[2] = (uint8_t)(x >> 16); t[3] = (uint8_t)(x >> 24);
     }
     uint8_t* b = o + fh + 3;
     if (compressed) {
@@ -662,6 +709,27 @@ __global__ void __launch_bounds__(128) k_enc_write(const Item* items, const EncC
         for (uint32_t i = lane; i < ch.seq_sec; i += 32) b[ch.lit_sec + i] = ss[i];
     } else {
         for (uint32_t i = lane; i < size; i += 32) b[i] = ch.src[i];
+    }
+}
+
+// Content_Checksum of every frame: XXH64 is one serial chain over the frame's plain bytes, so a warp per FRAME (the warp of
+// the frame's first chunk; lanes 0..3 own one accumulator each) walks the input once more and stores the low 32 bits
+// after the frame's last block.
+__global__ void __launch_bounds__(128) k_enc_hash(const Item* items, const EncChunk* chunks, const ItemOut* outs, uint32_t n_chunks)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (ci >= n_chunks) return;
+    const EncChunk& ch = chunks[ci];
+    if (ch.foff != 0 || outs[ch.item].fail) return;
+    const EncChunk& lastc = chunks[ci + ch.nblk - 1];
+    const uint64_t acc = lane < 4 ? xx_lane(ch.src, ch.fsize, lane) : 0;
+    const uint64_t v1 = __shfl_sync(0xFFFFFFFFu, acc, 0), v2 = __shfl_sync(0xFFFFFFFFu, acc, 1), v3 = __shfl_sync(0xFFFFFFFFu, acc, 2),
+                   v4 = __shfl_sync(0xFFFFFFFFu, acc, 3);
+    if (lane == 0) {
+        const uint32_t x = (uint32_t)xx_combine(v1, v2, v3, v4, ch.src, ch.fsize);
+        uint8_t* t = items[ch.item].dst + lastc.out_off + lastc.frame_size - 4;
+        t[0] = (uint8_t)x; t[1] = (uint8_t)(x >> 8); t[2] = (uint8_t)(x >> 16); t[3] = (uint8_t)(x >> 24);
     }
 }
 
@@ -675,7 +743,10 @@ using namespace fz;
 static const char* kEncStageNames[] = { "enc_match", "enc_lit", "enc_seq", "enc_place", "enc_write" };
 const char* fzh_encode_stage_name(int s) { return s >= 0 && s < 5 ? kEncStageNames[s] : ""; }
 
-static size_t enc_chunk_size(size_t chunk) { return chunk == 0 || chunk > kEncChunkMax ? kEncChunkMax : std::max<size_t>(chunk, 1024); }
+static size_t enc_chunk_size(size_t chunk) { return chunk == 0 || chunk > kEncChunkMax ? kEncChunkMax : std::max<size_t>(chunk, 1024); }   // bytes per block
+// bytes per independent frame (`chunk_size` of fzg_encode_batch): default 1 MiB = eight blocks that share a window
+constexpr size_t kEncFrameDefault = 1u << 20, kEncFrameMax = 8u << 20;
+static size_t enc_frame_size(size_t chunk) { return chunk == 0 ? kEncFrameDefault : std::min<size_t>(std::max<size_t>(chunk, 1024), kEncFrameMax); }
 
 size_t fzh_encode_bound(size_t src_len, size_t chunk)
 {
@@ -686,8 +757,9 @@ size_t fzh_encode_bound(size_t src_len, size_t chunk)
 
 int fzh_encode_setup(void)
 {
-    CK(cudaFuncSetAttribute(k_enc_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncMatchWarps * (2 << kEncHashLog)));
-    CK(cudaFuncSetAttribute(k_enc_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncMatchWarps * (2 << kEncHashLog)));
+    CK(cudaFuncSetAttribute(k_enc_match<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncMatchWarps * (2 << kEncHashLog)));
+    CK(cudaFuncSetAttribute(k_enc_match<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncMatchWarps * (2 << kEncHashLog)));
+    CK(cudaFuncSetAttribute(k_enc_match<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncMatchWarps * (2 << kEncHashLog)));
     return 0;
 }
 
@@ -696,18 +768,23 @@ int fzh_encode_setup(void)
 int fzh_encode_run(FzCtx* c, uint32_t first, uint32_t n, int level, size_t chunk, int flags)
 {
     // the reference passes 0..19, 0 = libzstd's default = 3 (src/main.rs:1237, 1283-1296): 1-2 select the single-table matcher
-    const bool long_table = !(level == 1 || level == 2);
+    const int mode = (level == 1 || level == 2) ? 0 : ((level == 0 || level == 3) ? 1 : 2);      // see EncMode
     cudaStream_t s = c->stream;
     const bool prof = flags & FZG_PROFILE;
     c->timing = fzg_timing_t{};
     if (n == 0) return 0;
     const Item* h_items = (const Item*)c->h_items.p + first;
     ItemOut* h_outs = (ItemOut*)c->h_outs.p + first;
-    const size_t cs = enc_chunk_size(chunk);
-    // ---- chunk descriptors, built on the host (sizes are known up front: src/main.rs:773 reads st_size)
+    const size_t fs = enc_frame_size(chunk), cs = std::min<size_t>(fs, kEncChunkMax);      // frame / block sizes
+    auto blocks_of = [&](uint64_t len) -> uint64_t {                  // blocks of a file: frames of fs bytes, blocks of cs bytes inside
+        if (len == 0) return 1;
+        const uint64_t full = len / fs, rem = len % fs;
+        return full * ((fs + cs - 1) / cs) + (rem + cs - 1) / cs;
+    };
+    // ---- chunk (= block) descriptors, built on the host (sizes are known up front: src/main.rs:773 reads st_size)
     std::vector<uint32_t> first_chunk(n + 1);
     uint64_t n_chunks = 0;
-    for (uint32_t i = 0; i < n; i++) { first_chunk[i] = (uint32_t)n_chunks; n_chunks += h_items[i].src_len ? (h_items[i].src_len + cs - 1) / cs : 1; }
+    for (uint32_t i = 0; i < n; i++) { first_chunk[i] = (uint32_t)n_chunks; n_chunks += blocks_of(h_items[i].src_len); }
     first_chunk[n] = (uint32_t)n_chunks;
     if (n_chunks >= (1ull << 31)) return -22;
     int rc;
@@ -736,12 +813,16 @@ int fzh_encode_run(FzCtx* c, uint32_t first, uint32_t n, int level, size_t chunk
     }
     for (const Group& g : groups)
         for (uint32_t i = g.ia; i < g.ib; i++) {
-            uint64_t off = 0;
+            uint64_t off = 0; uint32_t frame_first = first_chunk[i];
             for (uint32_t k = first_chunk[i]; k < first_chunk[i + 1]; k++) {
                 EncChunk& ch = hc[k];
-                ch.src = h_items[i].src + off; ch.size = (uint32_t)std::min<uint64_t>(cs, h_items[i].src_len - off); off += ch.size;
+                const uint64_t fstart = off - off % fs;                                    // the frame this block belongs to
+                ch.fsize = (uint32_t)std::min<uint64_t>(fs, h_items[i].src_len - fstart); ch.foff = (uint32_t)(off - fstart);
+                if (ch.foff == 0) frame_first = k;
+                ch.src = h_items[i].src + off; ch.size = (uint32_t)std::min<uint64_t>(cs, fstart + ch.fsize - off); off += ch.size;
                 ch.scratch = (uint8_t*)c->e_work.p + (uint64_t)((k - first_chunk[g.ia]) % wave) * kScrBytes;
-                ch.item = i; ch.nseq = ch.nlit = ch.lit_sec = ch.seq_sec = ch.frame_size = ch.raw = 0; ch.out_off = 0;
+                ch.item = i; ch.nseq = ch.nlit = ch.lit_sec = ch.seq_sec = ch.frame_size = ch.raw = 0; ch.out_off = 0; ch.nblk = 0; ch.pad = 0;
+                hc[frame_first].nblk++;
             }
         }
     EncChunk* d_chunks = (EncChunk*)c->e_items.p;
@@ -767,10 +848,13 @@ int fzh_encode_run(FzCtx* c, uint32_t first, uint32_t n, int level, size_t chunk
                                                  return e && atoi(e) > 0 ? std::min<uint32_t>((uint32_t)atoi(e), full) : full; }();
         const uint32_t match_ctas = std::min<uint32_t>((cnt + kEncMatchWarps - 1) / kEncMatchWarps, 148 * ctas_per_sm);
         const uint32_t match_smem = kEncMatchWarps * (2 << kEncHashLog);
-        if (long_table) {
-            if (c->e_tab.reserve((size_t)match_ctas * kEncMatchWarps * kEncLongBytes)) return -12;
-            k_enc_match<true><<<match_ctas, kEncMatchWarps * 32, match_smem, s>>>(d_chunks + lo, cnt, d_tickets, (uint8_t*)c->e_tab.p);
-        } else k_enc_match<false><<<match_ctas, kEncMatchWarps * 32, match_smem, s>>>(d_chunks + lo, cnt, d_tickets, nullptr);
+        if (mode == 2) {
+            if (c->e_tab.reserve((size_t)match_ctas * kEncMatchWarps * EncMode<2>::long_bytes)) return -12;
+            k_enc_match<2><<<match_ctas, kEncMatchWarps * 32, match_smem, s>>>(d_chunks + lo, cnt, d_tickets, (uint8_t*)c->e_tab.p);
+        } else if (mode == 1) {
+            if (c->e_tab.reserve((size_t)match_ctas * kEncMatchWarps * EncMode<1>::long_bytes)) return -12;
+            k_enc_match<1><<<match_ctas, kEncMatchWarps * 32, match_smem, s>>>(d_chunks + lo, cnt, d_tickets, (uint8_t*)c->e_tab.p);
+        } else k_enc_match<0><<<match_ctas, kEncMatchWarps * 32, match_smem, s>>>(d_chunks + lo, cnt, d_tickets, nullptr);
         if (check("k_enc_match")) return -5;
         if (marks) mark();
         k_enc_lit<<<std::min<uint32_t>((cnt + kLitWarps - 1) / kLitWarps, 148 * 8), kLitWarps * 32, 0, s>>>(d_chunks + lo, cnt, d_tickets + 1);
@@ -789,13 +873,15 @@ int fzh_encode_run(FzCtx* c, uint32_t first, uint32_t n, int level, size_t chunk
             if ((rc = run_wave(lo, (uint32_t)cnt, one))) return rc;
             k_enc_place<<<(ni + 127) / 128, 128, 0, s>>>(h_items + g.ia, d_chunks, d_first + g.ia, d_outs + g.ia, ni, seek); if (one) mark();
             if (check("k_enc_place")) return -5;
-            k_enc_write<<<(uint32_t)((cnt * 32 + 127) / 128), 128, 0, s>>>(h_items, d_chunks + lo, d_outs, (uint32_t)cnt); if (one) mark();
+            k_enc_write<<<(uint32_t)((cnt * 32 + 127) / 128), 128, 0, s>>>(h_items, d_chunks + lo, d_outs, (uint32_t)cnt);
+            k_enc_hash<<<(uint32_t)((cnt * 32 + 127) / 128), 128, 0, s>>>(h_items, d_chunks + lo, d_outs, (uint32_t)cnt); if (one) mark();
             if (check("k_enc_write")) return -5;
-            launches += 2;
+            launches += 3;
         } else {                                                           // one oversized item
             for (uint64_t w = lo; w < lo + cnt; w += wave) if ((rc = run_wave(w, (uint32_t)std::min<uint64_t>(wave, lo + cnt - w), false))) return rc;
             k_enc_place<<<1, 128, 0, s>>>(h_items + g.ia, d_chunks, d_first + g.ia, d_outs + g.ia, 1, seek);
-            launches++;
+            k_enc_hash<<<(uint32_t)((cnt * 32 + 127) / 128), 128, 0, s>>>(h_items, d_chunks + lo, d_outs, (uint32_t)cnt);       // needs the placement only
+            launches += 2;
             for (uint64_t w = lo; w < lo + cnt; w += wave) {
                 const uint32_t wc = (uint32_t)std::min<uint64_t>(wave, lo + cnt - w);
                 if ((rc = run_wave(w, wc, false))) return rc;

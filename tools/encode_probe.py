@@ -18,7 +18,7 @@ for it in range(4):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     dl, st = codec.encode_batch_ptrs(0, sp, [size] * n, dp, [cap] * n, level, 0, fl)
     dt = time.perf_counter() - t0
-    t = codec.last_timing(0)
+    t = codec.last_timing(0, encode=True)
     print("level %d: encode %d x 4 MiB: %.1f ms wall, gpu %.1f ms -> %.1f GB/s in, ratio %.3f, stages %s" % (level, n, dt * 1e3, t["total_ms"], n * size / 1e9 / (t["total_ms"] / 1e3), n * size / dl.sum(), {k: round(v, 2) for k, v in list(t["stages"].items())[:5]}), file=sys.stderr)
 assert not st.any()
 R = pyoracle.Ref()
