@@ -10,10 +10,15 @@ import argparse, importlib, json, multiprocessing as mp, os, shutil, subprocess,
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 
+def natural_key(name):
+    import re
+    return [int(t) if t.isdigit() else t for t in re.split(r"(\d+)", name)]
+
+
 def reader(args):
     d, bs = args
     n = 0
-    for name in sorted(os.listdir(d)):
+    for name in sorted(os.listdir(d), key=natural_key):          # file index order, as a fio job walks its nrfiles
         fd = os.open(os.path.join(d, name), os.O_RDONLY)
         while True:
             b = os.read(fd, bs)
