@@ -378,6 +378,44 @@ __device__ __forceinline__ uint64_t ld8_any(const uint8_t* g, uint32_t nb)
     if (sh + nb > 8) w1 = *(const uint2*)(a + 8);
     return funnel8(w0.x, w0.y, w1.x, w1.y, sh);
 }
+// L2 residency (FZ_EXEC_L2HINT).  The window reads of ~4 700 frames in flight miss L2 almost always and every miss ALLOCATES a line:
+// 55 GB of fills per 12 ms turn the 126 MB L2 over every ~26 us, in which a frame produces 2 KB -- so only matches closer than
+// that find their source in L2 (15 % of them), although 47 % lie within the 26 KB that are a frame's fair share.  With the
+// hint the streaming data (window misses, records, literals) is marked evict-first and leaves the plain output stores alone.
+#ifndef FZ_EXEC_L2HINT
+#define FZ_EXEC_L2HINT 0
+#endif
+__device__ __forceinline__ uint64_t l2_stream_policy()
+{
+    uint64_t p = 0;
+#if FZ_EXEC_L2HINT
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+#endif
+    return p;
+}
+// nb (1..8) bytes at global address g (never shared memory), streamed through L2
+__device__ __forceinline__ uint64_t ld8_stream(const uint8_t* g, uint32_t nb, uint64_t pol)
+{
+#if FZ_EXEC_L2HINT
+    const uintptr_t a = (uintptr_t)g & ~(uintptr_t)7;
+    const uint32_t sh = (uint32_t)((uintptr_t)g & 7);
+    uint32_t x0, x1, x2 = 0, x3 = 0;
+    asm volatile("ld.global.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(x0), "=r"(x1) : "l"(a), "l"(pol) : "memory");
+    if (sh + nb > 8) asm volatile("ld.global.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(x2), "=r"(x3) : "l"(a + 8), "l"(pol) : "memory");
+    return funnel8(x0, x1, x2, x3, sh);
+#else
+    (void)pol; return ld8_any(g, nb);
+#endif
+}
+__device__ __forceinline__ uint64_t ldrec_stream(const uint64_t* p, uint64_t pol)
+{
+#if FZ_EXEC_L2HINT
+    uint64_t v; asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol)); return v;
+#else
+    (void)pol; return __ldg(p);
+#endif
+}
+
 // nb (1..8) low bytes of v -> the stage at any alignment: predicated byte stores through the shared window (no generic
 // addressing, no branches).  (Word-sized red.shared.or on a zeroed stage was measured slower: 27.8 -> 31.3 ms.)
 #define FZ_ST_BYTE(I, W, SH) asm volatile("{ .reg .pred q; .reg .b32 t; setp.gt.u32 q, %2, " #I "; shr.b32 t, %1, " #SH "; @q st.shared.u8 [%0+" #I "], t; }" ::"r"(a), "r"(W), "r"(nb) : "memory")
@@ -447,8 +485,9 @@ __device__ __forceinline__ void exec_block_warp(uint8_t* stage, const Block& b, 
     const uint32_t nseq = b.nseq, rsize = b.rsize, lit_regen = b.lit_regen;
     const uint8_t* __restrict__ lit = b.lit;
     const uint32_t in0 = b.rep_in[0], in1 = b.rep_in[1], in2 = b.rep_in[2];
+    const uint64_t pol = l2_stream_policy();
     uint32_t Ecarry = 0, LEcarry = 0;
-    uint64_t rcur = lane < nseq ? __ldg(sq + lane) : 0;          // records of the current round; the next round's are loaded a round early
+    uint64_t rcur = lane < nseq ? ldrec_stream(sq + lane, pol) : 0;          // records of the current round; the next round's are loaded a round early
     for (uint32_t g = 0; g < nseq;) {
         const uint32_t nv = min(32u, nseq - g);
         const uint64_t r = lane < nv ? rcur : 0;
@@ -469,10 +508,10 @@ __device__ __forceinline__ void exec_block_warp(uint8_t* stage, const Block& b, 
             warp_big_sequence(g0 + gS, lit + LEcarry, ll0, ml0, off0, lane);
             Ecarry = __shfl_sync(kFull, E, 0); LEcarry = __shfl_sync(kFull, LE, 0);
             g += 1;
-            rcur = g + lane < nseq ? __ldg(sq + g + lane) : 0;
+            rcur = g + lane < nseq ? ldrec_stream(sq + g + lane, pol) : 0;
             continue;
         }
-        rcur = g + m + lane < nseq ? __ldg(sq + g + m + lane) : 0;
+        rcur = g + m + lane < nseq ? ldrec_stream(sq + g + m + lane, pol) : 0;
         const bool mine = lane < m;
         const uint32_t gE = __shfl_sync(kFull, E, m - 1);         // end of the round's output
         const uint32_t a = (uint32_t)((uintptr_t)(g0 + gS) & 15); // stage[a + i] <-> g0[gS + i]: same low address bits as HBM
@@ -484,7 +523,7 @@ __device__ __forceinline__ void exec_block_warp(uint8_t* stage, const Block& b, 
             while (__any_sync(kFull, go)) {
                 if (go) {
                     const uint32_t nb = min(8u, M - pos);
-                    st_stage(st + pos, ld8_any(src, nb), nb);
+                    st_stage(st + pos, ld8_stream(src, nb, pol), nb);
                     pos += nb; src += nb; go = pos < M;
                 }
             }
@@ -521,7 +560,7 @@ __device__ __forceinline__ void exec_block_warp(uint8_t* stage, const Block& b, 
                             const uint32_t lim = lane == first ? pos : ((s >= (int32_t)M) ? pos : front);
                             if (s < (int32_t)gS) {                 // before the round: HBM / L2 (earlier rounds, earlier blocks)
                                 nb = min(nb, gS - (uint32_t)s);    // a step straddling the round start is split
-                                v = ld8_any((const uint8_t*)g0 + s, nb);
+                                v = ld8_stream((const uint8_t*)g0 + s, nb, pol);
                             } else if ((uint32_t)s + nb <= lim) v = ld8_any((const uint8_t*)st + s, nb);
                             else if ((uint32_t)s < lim) { nb = lim - (uint32_t)s; v = ld8_any((const uint8_t*)st + s, nb); }
                             else nb = 0;
