@@ -1161,6 +1161,222 @@ __global__ void __launch_bounds__(ExecCta<W>::threads, ExecCta<W>::ctas_per_sm) 
     }
 }
 
+// ------------------------------------------------------------------ execute, a few warps per frame, barrier passes
+// k_execute keeps 32 frames in flight per SM and is bound by the DRAM fetches of their window reads (15 % L2 hit rate, see
+// DESIGN.md section 2).  Here W (2 or 4) warps share a frame, so 32 / W frames are in flight per SM at the same number of warps,
+// WITHOUT the per-byte bookkeeping of k_execute_cta: the round is k_execute's round with 32 W sequences, one per thread, and its
+// frontier loop with the warp replaced by the CTA -- every pass ends in one barrier at which each warp posts its first
+// unfinished thread; the minimum is the CTA's first unfinished thread and the position it has reached is the frontier of the
+// next pass.  Sources before the round come from HBM / L2 at once, so nearly everything is done in the first pass.
+template <int W> struct ExecPass {
+    static constexpr uint32_t T = W * 32, stage = W * kStage, stage_bytes = stage + 48;
+    static constexpr int ctas_per_sm = 32 / W;
+};
+
+template <int W>
+__device__ __forceinline__ void exec_block_pass(uint8_t* stage, uint32_t* cnt, uint32_t* fr /*[2][W]*/, const Block& b, const uint64_t* __restrict__ sq,
+                                                uint8_t* g0, uint64_t done, int& status, uint32_t tid)
+{
+    constexpr uint32_t T = ExecPass<W>::T, kCtaStage = ExecPass<W>::stage;
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    const uint32_t nseq = b.nseq, rsize = b.rsize;
+    const uint8_t* __restrict__ lit = b.lit;
+    const uint32_t in0 = b.rep_in[0], in1 = b.rep_in[1], in2 = b.rep_in[2];
+    uint32_t Ecarry = 0, LEcarry = 0, fpar = 0;                  // CTA-uniform
+    uint64_t rcur = tid < nseq ? __ldg(sq + tid) : 0;            // the round's records; the next round's are loaded a round early
+    uint64_t rprev = (lane == 0 && warp > 0 && tid <= nseq) ? __ldg(sq + tid - 1) : 0;   // record before a warp's first one
+    for (uint32_t g = 0; g < nseq;) {
+        const uint32_t nv = min(T, nseq - g);
+        const uint64_t rl = __ldg(sq + g + nv - 1);
+        const uint32_t Elast = rec_e(rl), LElast = rec_le(rl);
+        const uint64_t r = tid < nv ? rcur : 0;
+        uint32_t E = rec_e(r), LE = rec_le(r);
+        if (tid >= nv) { E = Elast; LE = LElast; }
+        uint32_t S = __shfl_up_sync(kFull, E, 1), LEp = __shfl_up_sync(kFull, LE, 1);
+        if (lane == 0) {
+            if (warp == 0) { S = Ecarry; LEp = LEcarry; }
+            else if (tid <= nv) { S = rec_e(rprev); LEp = rec_le(rprev); }
+            else { S = Elast; LEp = LElast; }
+        }
+        const uint32_t gS = Ecarry;                              // output position where this round starts
+        uint32_t off = tid < nv ? off_resolve(rec_off(r), in0, in1, in2) : 1;
+        if (tid < nv && (uint64_t)off > done + S + (LE - LEp)) { off = 0; status = FZG_E_CORRUPT; }   // reaches before the frame start
+        // sequences of this round: the leading ones whose output fits the stage (E never decreases)
+        uint32_t n = nv;
+        if (Elast - gS > kCtaStage) {
+            const uint32_t fit = __ballot_sync(kFull, tid < nv && E - gS <= kCtaStage);
+            if (lane == 0) cnt[warp] = (uint32_t)__popc(fit);
+            __syncthreads();
+            n = 0;
+            for (int w = 0; w < W; w++) n += cnt[w];
+            __syncthreads();
+        }
+        if (n == 0) {                                            // sequence g alone is larger than the stage
+            const uint64_t r0 = __ldg(sq + g);
+            const uint32_t E0 = rec_e(r0), LE0 = rec_le(r0), M0 = gS + (LE0 - LEcarry);
+            uint32_t off0 = off_resolve(rec_off(r0), in0, in1, in2);
+            if ((uint64_t)off0 > done + M0) off0 = 0;
+            group_copy(g0 + gS, lit + LEcarry, LE0 - LEcarry, tid, T);
+            __syncthreads();
+            {
+                uint8_t* m = g0 + M0; const uint32_t ml0 = E0 - M0;
+                if (off0 != 0) {
+                    const uint8_t* sp = m - off0;
+                    if (off0 >= 16 * T) {                                // source and destination of a 16 T-byte round never overlap
+                        for (uint32_t i = 0; i < ml0; i += 16 * T) {
+                            const uint32_t nb = min(16u, ml0 > i + 16 * tid ? ml0 - i - 16 * tid : 0u);
+                            for (uint32_t k = 0; k < nb; k++) m[i + 16 * tid + k] = sp[i + 16 * tid + k];
+                            __syncthreads();
+                        }
+                    } else for (uint32_t i = tid; i < ml0; i += T) m[i] = sp[i % off0];   // periodic; the period lies below m: written
+                }
+            }
+            __syncthreads();
+            Ecarry = E0; LEcarry = LE0;
+            g += 1;
+            rcur = g + tid < nseq ? __ldg(sq + g + tid) : 0;
+            rprev = (lane == 0 && warp > 0 && g + tid <= nseq) ? __ldg(sq + g + tid - 1) : 0;
+            continue;
+        }
+        const uint64_t re = __ldg(sq + g + n - 1);
+        const uint32_t gE = rec_e(re), LEend = rec_le(re);       // end of the round's output / literals
+        rcur = g + n + tid < nseq ? __ldg(sq + g + n + tid) : 0;
+        rprev = (lane == 0 && warp > 0 && g + n + tid <= nseq) ? __ldg(sq + g + n + tid - 1) : 0;
+        const bool mine = tid < n;
+        if (!mine) { S = gE; E = gE; LE = LEend; LEp = LEend; }
+        const uint32_t M = S + (LE - LEp);
+        const uint32_t a = (uint32_t)((uintptr_t)(g0 + gS) & 15); // stage[a + i] <-> g0[gS + i]: same low address bits as HBM
+        uint8_t* const st = stage + a - gS;                       // st[p] is the stage byte of output position p (gS <= p < gE)
+        // ---- 1. literal runs
+        {
+            uint32_t pos = S; const uint8_t* src = lit + LEp;
+            bool go = mine && pos < M;
+            while (__any_sync(kFull, go)) {
+                if (go) {
+                    const uint32_t nb = min(8u, M - pos);
+                    st_stage(st + pos, ld8_any(src, nb), nb);
+                    pos += nb; src += nb; go = pos < M;
+                }
+            }
+        }
+        // ---- 2. matches, in passes
+        {
+            uint32_t pos = M;
+            bool pending = mine && pos < E;
+            for (;;) {
+                // the CTA's first unfinished thread and the position it has reached (key = tid << 16 | pos - gS)
+                const uint32_t pm = __ballot_sync(kFull, pending);
+                const uint32_t wl = pm ? (uint32_t)__ffs((int)pm) - 1u : 0u;
+                const uint32_t wpos = __shfl_sync(kFull, pos, wl);
+                if (lane == 0) fr[fpar * W + warp] = pm ? (((warp << 5) | wl) << 16) | (wpos - gS) : 0xFFFFFFFFu;
+                __syncthreads();                                  // (also: the stage bytes of the previous pass / the literal runs are visible)
+                uint32_t key = 0xFFFFFFFFu;
+#pragma unroll
+                for (int w = 0; w < W; w++) key = min(key, fr[fpar * W + w]);
+                fpar ^= 1u;
+                if (key == 0xFFFFFFFFu) break;
+                const uint32_t first = key >> 16, front = gS + (key & 0xFFFFu);   // every output byte below `front` is written (HBM or stage)
+                bool go = pending;
+                while (__any_sync(kFull, go)) {
+                    if (go) {
+                        uint32_t nb = min(8u, E - pos);
+                        uint64_t v = 0;
+                        if (off == 0) { /* corrupt: zeros */ }
+                        else if (off < 8 && off < nb) {           // the step overlaps itself: expand the period byte by byte
+                            const int32_t s0 = (int32_t)pos - (int32_t)off;
+                            const bool ok = tid == first || (uint32_t)(s0 + (int32_t)off) <= front || s0 >= (int32_t)M;   // period written?
+                            if (ok) {
+                                const uint8_t* sp = s0 < (int32_t)gS ? (const uint8_t*)g0 + s0 : (const uint8_t*)st + s0;
+                                const uint32_t take = s0 < (int32_t)gS ? min(off, gS - (uint32_t)s0) : off;   // a period straddling the round start
+                                uint64_t pat = ld8_any(sp, take);
+                                if (take < off) pat = (pat & ((1ull << (8 * take)) - 1)) | (ld8_any((const uint8_t*)st + gS, off - take) << (8 * take));
+                                for (uint32_t i = 0; i < nb; i++) v |= ((pat >> (8 * (i % off))) & 0xFF) << (8 * i);
+                            } else nb = 0;
+                        } else {
+                            const int32_t s = (int32_t)pos - (int32_t)off;
+                            // available bytes: below `front`, or this thread's own match bytes written so far
+                            const uint32_t lim = tid == first ? pos : ((s >= (int32_t)M) ? pos : front);
+                            if (s < (int32_t)gS) {                 // before the round: HBM / L2 (earlier rounds, earlier blocks)
+                                nb = min(nb, gS - (uint32_t)s);    // a step straddling the round start is split
+                                v = ld8_any((const uint8_t*)g0 + s, nb);
+                            } else if ((uint32_t)s + nb <= lim) v = ld8_any((const uint8_t*)st + s, nb);
+                            else if ((uint32_t)s < lim) { nb = lim - (uint32_t)s; v = ld8_any((const uint8_t*)st + s, nb); }
+                            else nb = 0;
+                        }
+                        if (nb) { st_stage(st + pos, v, nb); pos += nb; go = pos < E; }
+                        else go = false;                          // its source is still being produced by a lower thread
+                    }
+                }
+                pending = mine && pos < E;
+            }
+        }
+        // ---- 3. flush stage[a .. a + (gE - gS)) -> g0 + gS: head bytes, aligned 16-byte body, tail bytes (the break above came after a barrier)
+        {
+            const uint32_t nby = gE - gS;
+            uint8_t* gd = g0 + gS;
+            const uint32_t head = min(nby, (16 - a) & 15);
+            if (tid < head) gd[tid] = stage[a + tid];
+            const uint32_t nvec = (nby - head) >> 4;
+            for (uint32_t i = tid; i < nvec; i += T) *(uint4*)(gd + head + 16 * i) = *(const uint4*)(stage + a + head + 16 * i);
+            const uint32_t tail0 = head + (nvec << 4);
+            if (tail0 + tid < nby) gd[tail0 + tid] = stage[a + tail0 + tid];
+        }
+        __syncthreads();
+        Ecarry = gE; LEcarry = LEend;
+        g += n;
+#if FZ_EXEC_PREFETCH
+        {   // the next round's match sources: asked for now (see k_execute)
+            const uint32_t nn = g < nseq ? min(T, nseq - g) : 0u;
+            const uint32_t En = rec_e(rcur), LEn = rec_le(rcur);
+            uint32_t Sn = __shfl_up_sync(kFull, En, 1), LEpn = __shfl_up_sync(kFull, LEn, 1);
+            if (lane == 0) { if (warp == 0) { Sn = Ecarry; LEpn = LEcarry; } else { Sn = rec_e(rprev); LEpn = rec_le(rprev); } }
+            const uint32_t Mn = Sn + (LEn - LEpn);
+            const uint32_t offn = off_resolve(rec_off(rcur), in0, in1, in2);
+            if (tid < nn && offn != 0 && (uint64_t)offn <= done + Mn && offn > Mn - Ecarry) exec_prefetch(g0 + Mn - offn, En - Mn);
+        }
+#endif
+    }
+    // literals after the last sequence
+    group_copy(g0 + Ecarry, lit + LEcarry, rsize - Ecarry, tid, T);
+}
+
+template <int W>
+__global__ void __launch_bounds__(ExecPass<W>::T, ExecPass<W>::ctas_per_sm) k_execute_pass(Frame* frames, const Block* blocks, const Item* items,
+                                                                                         const ItemOut* outs, const uint64_t* seqs,
+                                                                                         uint32_t n_frames, uint32_t* ticket)
+{
+    constexpr uint32_t T = ExecPass<W>::T;
+    __shared__ __align__(16) uint8_t s_stage[ExecPass<W>::stage_bytes];
+    __shared__ uint32_t s_cnt[W], s_fr[2 * W], s_f;
+    const uint32_t tid = threadIdx.x;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_f = atomicAdd(ticket, 1);
+        __syncthreads();
+        const uint32_t f = s_f;
+        if (f >= n_frames) return;
+        Frame& fr = frames[f];
+        if (outs[fr.item].fail) continue;
+        uint8_t* const fbase = items[fr.item].dst + fr.out_off;
+        uint64_t done = 0;
+        int status = 0;
+        for (uint32_t kb = 0; kb < fr.n_blocks; kb++) {
+            const Block& b = blocks[fr.first_block + kb];
+            uint8_t* const g0 = fbase + done;
+            const uint32_t rsize = b.rsize;
+            if (b.type == BT_RAW) group_copy(g0, b.src, rsize, tid, T);
+            else if (b.type == BT_RLE) {
+                const uint8_t v = b.src[0];
+                for (uint32_t i = tid; i < rsize; i += T) g0[i] = v;
+            } else if (b.nseq == 0) group_copy(g0, b.lit, rsize, tid, T);
+            else exec_block_pass<W>(s_stage, s_cnt, s_fr, b, seqs + b.seq_base, g0, done, status, tid);
+            __syncthreads();                               // later blocks read this one back (the window)
+            done += rsize;
+        }
+        if (__syncthreads_or(status) && tid == 0) fr.status = FZG_E_CORRUPT;
+    }
+}
+
 // Four threads per frame, one XXH64 accumulator each (stripe = 32 bytes, lane j owns bytes 8j..8j+7).
 __global__ void k_checksum(Frame* frames, const Item* items, const ItemOut* outs, uint32_t n_frames)
 {
@@ -1201,6 +1417,7 @@ static int exec_warps_override()          // FZG_EXEC_W: the execute kernel, rea
 {                                         // threads per frame (returned as -threads); 1: k_execute (warp per frame); 2..32: k_execute_cta<W>; else by batch shape
     const char* e = getenv("FZG_EXEC_W");
     if (e && e[0] == 't') { const int t = atoi(e + 1); return (t == 128 || t == 256 || t == 512 || t == 1024) ? -t : 0; }
+    if (e && e[0] == 'p') { const int t = atoi(e + 1); return (t == 2 || t == 4 || t == 8) ? 200 + t : 0; }     // k_execute_pass<W>
     if (e && e[0] == 's') return 64;                                  // k_execute<true>: warp per frame, steps dealt out over the lanes
     const int v = e ? atoi(e) : 0;
     return (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ? v : 0;
@@ -1215,10 +1432,6 @@ int fzh_decode_setup(void)
     CK(cudaFuncSetAttribute(k_execute_tile<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<256>::smem));
     CK(cudaFuncSetAttribute(k_execute_tile<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<512>::smem));
     CK(cudaFuncSetAttribute(k_execute_tile<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<1024>::smem));
-    if (getenv("FZG_EXEC_CARVE")) {      // experiment: the execute stage with the shared-memory carve-out of the entropy stages, so that both fit an SM together
-        CK(cudaFuncSetAttribute(k_execute<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CK(cudaFuncSetAttribute(k_execute<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    }
     int dev = 0; CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
     return 0;
@@ -1360,7 +1573,15 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
             const uint32_t grid = (uint32_t)std::min<uint64_t>(n_frames, (uint64_t)g_sm_count * TileCfg<T>::ctas_per_sm);
             k_execute_tile<T><<<grid, T, TileCfg<T>::smem, s>>>(d_frames, d_blocks, d_items, d_outs, d_seq, (uint32_t)n_frames, d_tickets + 1);
         };
-        if (w == -128) tile(std::integral_constant<int, 128>{});
+        auto pass = [&](auto wc) {
+            constexpr int W = decltype(wc)::value;
+            const uint32_t grid = (uint32_t)std::min<uint64_t>(n_frames, (uint64_t)g_sm_count * ExecPass<W>::ctas_per_sm);
+            k_execute_pass<W><<<grid, ExecPass<W>::T, 0, s>>>(d_frames, d_blocks, d_items, d_outs, d_seq, (uint32_t)n_frames, d_tickets + 1);
+        };
+        if (w == 202) pass(std::integral_constant<int, 2>{});
+        else if (w == 204) pass(std::integral_constant<int, 4>{});
+        else if (w == 208) pass(std::integral_constant<int, 8>{});
+        else if (w == -128) tile(std::integral_constant<int, 128>{});
         else if (w == -256) tile(std::integral_constant<int, 256>{});
         else if (w == -512) tile(std::integral_constant<int, 512>{});
         else if (w == -1024) tile(std::integral_constant<int, 1024>{});

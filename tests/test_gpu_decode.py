@@ -31,7 +31,7 @@ def _init():
     yield
 
 
-@pytest.fixture(params=["s", "t128", "t256", "t1024", "1", "8"])
+@pytest.fixture(params=["p4", "p2", "s", "t128", "t256", "t1024", "1", "8"])
 def exec_w(request):
     """the execute kernel: k_execute<true> (warp per frame, steps dealt out over the lanes), k_execute_tile with 128 / 256 /
     1024 threads per frame, k_execute<false> (1: a lane loops over its sequence) or k_execute_cta<8>; without the fixture the
