@@ -1542,7 +1542,7 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
         const uint64_t sms = (uint64_t)g_sm_count;
         // default: k_execute_tile (a CTA per frame, output-centric); threads per frame by batch shape: enough CTAs to fill the SMs
         // at 256 threads, else wider CTAs for the few frames there are.  FZG_EXEC_W selects the round-1 kernels instead.
-        const int w = w_env ? w_env : (n_frames * 2 <= sms ? 32 : (n_frames <= sms * 8 ? 8 : (n_frames <= sms * 16 ? 2 : 64)));
+        const int w = w_env ? w_env : (n_frames * 2 <= sms ? 32 : (n_frames <= sms * 8 ? 8 : (n_frames <= sms * 16 ? 2 : 1)));
         const int verify = (flags & FZG_NO_VERIFY_CHECKSUM) ? 0 : 1;
         auto cta = [&](auto wc) -> int {
             constexpr int W = decltype(wc)::value;

@@ -276,6 +276,20 @@ def test_large_window_long_distance_and_level19(ref, corpus, exec_w):
         assert hashlib.sha256(out).digest() == hashlib.sha256(plain).digest(), i
 
 
+def test_true_level19_with_an_8_mib_window(ref, corpus):
+    """config 4's real settings on a file large enough to use them: libzstd level 19 (btultra2: block splitting, Repeat modes,
+    Treeless literals, long matches) with windowLog 23 on 10 MiB, so offsets reach 8 MiB back across ~130 blocks"""
+    if not ref.available:
+        pytest.skip("system libzstd absent")
+    j = corpus.json_file(191919, 10 << 20).tobytes()
+    j = j[: 9 << 20] + j[: 1 << 20]                                    # the last MiB repeats the first: matches 9 MiB -> capped at the window
+    blob = ref.writer_encode(j, 19, window_log=23)
+    assert blob[4] & 0x20 == 0 and blob[5] == ((23 - 10) << 3)           # Window_Descriptor: 8 MiB
+    (st, out), = codec.decode_batch([blob], [len(j)])
+    assert st == 0, codec.strerror(st)
+    assert hashlib.sha256(out).digest() == hashlib.sha256(j).digest()
+
+
 def test_far_form_records(ref, exec_w):
     """sequences with more than 32 extra bits (long literal run + far offset + long match): stage A hands stage B the bit
     cursor instead of the bits (tests/test_emul.py::test_far_form_records checks that the vector really has such sequences)"""
