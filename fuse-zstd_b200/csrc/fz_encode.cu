@@ -221,7 +221,10 @@ __global__ void __launch_bounds__(kEncMatchWarps * 32) k_enc_match(EncChunk* chu
             __syncwarp();
             if (in && (same >> lane) == 1) table[h] = (uint16_t)P;          // the highest lane of a group records it
             if constexpr (LONG) {
-                if (in && (samel >> lane) == 1) EM::store(ltable, hl, P);
+#ifndef FZ_ENC_LONG_STRIDE
+#define FZ_ENC_LONG_STRIDE 1
+#endif
+                if (in && (samel >> lane) == 1 && (FZ_ENC_LONG_STRIDE == 1 || (P & (FZ_ENC_LONG_STRIDE - 1)) == 0)) EM::store(ltable, hl, P);
                 // keep the candidate that shares the longer prefix of the first 8 bytes (the nearer one on a tie)
                 if (in && p >= cur) {
                     const bool okl = candl >= 0 && P - (uint32_t)candl <= EM::long_window, oks = cand >= 0 && P - (uint32_t)cand <= kEncMaxOff;

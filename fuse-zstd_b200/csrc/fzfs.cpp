@@ -356,6 +356,8 @@ void Fs::readahead_dir(const std::string& dir, const std::string& path)
     }
     const size_t i1 = std::min(ra.names.size(), i0 + kRaWindow);
     if (i0 >= i1) return;
+    // entries well behind the reader have been served (and their slabs may be reused): a later pass over the directory asks again
+    for (size_t i = i0 > 2 * kRaWindow ? i0 - 2 * kRaWindow : 0, e = i0 > kRaWindow ? i0 - kRaWindow : 0; i < e; i++) ra.asked[i] = 0;
     size_t ahead = 0;
     for (size_t i = i0; i < i1; i++) ahead += ra.asked[i];
     if (ahead * 2 > i1 - i0) return;                                  // more than half of the window is on its way or here

@@ -50,6 +50,30 @@ def writer(args):
     return n
 
 
+def writer_fio(args):
+    """/root/reference/benchmarks/write-and-verify.fio as written: rw=randwrite bs=4k size=100m nrfiles=5 (20 MB per file), every
+    4 KiB block of a file written exactly once in random order, the file closed (= whole-file encode on release), then read back
+    and compared (fio: verify=crc32c).  iodepth / direct / libaio have no meaning through a one-thread FUSE loop."""
+    d, nfiles, size, seed = args
+    import importlib
+    import numpy as np
+    corpus = importlib.import_module("fuse-zstd_b200.corpus")
+    plain = corpus.json_files(seed, nfiles, size, threads=1)
+    rs = np.random.RandomState(seed)
+    n = 0
+    for i in range(nfiles):
+        body = plain[i].tobytes()
+        p = os.path.join(d, "v%04d" % i)
+        fd = os.open(p, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+        for blk in rs.permutation((size + 4095) // 4096):
+            os.pwrite(fd, body[blk * 4096:(blk + 1) * 4096], int(blk) * 4096)
+        os.close(fd)
+        with open(p, "rb") as fh:
+            assert fh.read() == body, p
+        n += size
+    return n
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--jobs", type=int, default=16); ap.add_argument("--nrfiles", type=int, default=125)
@@ -57,6 +81,7 @@ def main():
     ap.add_argument("--cache-mb", type=int, default=3072)
     ap.add_argument("--write-files", type=int, default=8, help="files per job in the write-and-verify phase (0: skip)")
     ap.add_argument("--write-mib", type=int, default=20)
+    ap.add_argument("--fio-write", action="store_true", help="also run write-and-verify.fio's own shape: 5 jobs x 5 files x 20 MB, 4 KiB random writes")
     a = ap.parse_args()
     import pyoracle
     corpus = importlib.import_module("fuse-zstd_b200.corpus")
@@ -107,6 +132,18 @@ def main():
                 print("%s: wrote + verified %.2f GB through the mount in %.2f s -> %.1f MB/s" % (arm, wrote / 1e9, dt, wrote / 1e6 / dt), file=sys.stderr)
                 for j in range(wjobs):
                     shutil.rmtree(os.path.join(data, "wjob%02d" % j), ignore_errors=True)
+            if a.fio_write:
+                for j in range(5):
+                    os.mkdir(os.path.join(mpnt, "vjob%02d" % j))
+                vargs = [(os.path.join(mpnt, "vjob%02d" % j), 5, 20 * 1000 * 1000, 4500000 + 1000 * j) for j in range(5)]
+                with mp.Pool(5) as pool:
+                    t0 = time.perf_counter()
+                    wrote = sum(pool.map(writer_fio, vargs))
+                    dt = time.perf_counter() - t0
+                out[arm + "_fio_write_and_verify"] = round(wrote / 1e6 / dt, 1)
+                print("%s: write-and-verify.fio shape (5 x 5 x 20 MB, 4 KiB random writes): %.2f GB in %.2f s -> %.1f MB/s" % (arm, wrote / 1e9, dt, wrote / 1e6 / dt), file=sys.stderr)
+                for j in range(5):
+                    shutil.rmtree(os.path.join(data, "vjob%02d" % j), ignore_errors=True)
         finally:
             proc.terminate(); proc.wait(timeout=20)
             subprocess.call(["umount", "-l", mpnt], stderr=subprocess.DEVNULL)
