@@ -17,10 +17,13 @@ struct FzDevBuf {
     int reserve(size_t n)   // grow-only; contents are NOT preserved
     {
         if (n <= cap) return 0;
-        size_t want = n + n / 4 + 4096;
+        size_t want = n + (n / 4 < ((size_t)1 << 30) ? n / 4 : ((size_t)1 << 30)) + 4096;     // grow-only with some slack, at most 1 GiB of it
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); p = nullptr; return -12; /* -ENOMEM */ }
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            cudaGetLastError(); p = nullptr; want = n + 4096;                               // a batch that nearly fills HBM: no slack
+            if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); p = nullptr; return -12; /* -ENOMEM */ }
+        }
         cap = want; return 0;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
