@@ -10,30 +10,37 @@
  *   - almost nothing inside a few KB of output depends on anything else inside it: a CTA can produce a ROUND of T x 16
  *     output bytes with all its threads at once, no polling, no per-byte bookkeeping;
  *   - what a frame needs from the memory system is its own recent output.  A CTA per frame and four CTAs per SM keep
- *     ~600 frames in flight, i.e. the last ~200 KB of every frame stays in the 126 MB L2 (round 1 kept 4 736 frames
- *     in flight, one per warp: 26 KB of L2 each, and fetched almost every match from DRAM: 123 GB per 14 GB).
+ *     600-1 000 frames in flight instead of 4 736 (k_execute: one per warp, 15 % L2 hit rate on its window reads,
+ *     123 GB of DRAM traffic per 14 GB of algorithmic bytes).
  *
- * A thread owns one 16-byte-aligned GRANULE of the round.  It finds the first sequence that reaches into the granule
- * (binary search over the E fields of the positional records), then walks the sequences forward, piece by piece:
- * a piece is <= 8 bytes of one literal run or one match that fall inside the granule.  A piece is an unaligned
- * 8-byte load (two aligned loads + funnel shift) merged into the granule's four registers; a finished granule leaves
- * with one 16-byte store.  No byte stores, no shared-memory stage: the output buffer (L1 / L2) is the window, for
- * sources inside the round as well.
+ * A thread owns one 16-byte-aligned GRANULE of the round.  Per round the CTA first expands the round's records (at most 2 T,
+ * two per thread) into execute-friendly 16-byte entries { M, E, literal source - S, resolved distance } and MARKS, for every
+ * record, the first granule whose first byte it produces; a running maximum over the marks (warp shuffles + one barrier)
+ * gives every granule the sequence it starts in -- no search.  The thread then walks the sequences forward, piece by piece: a
+ * piece is <= 8 bytes of one literal run or one match that fall inside the granule, an unaligned 8-byte load (two aligned
+ * loads + funnel shift) merged into the granule's four registers; a finished granule leaves with one 16-byte store to HBM and
+ * one to the WINDOW: the frame's most recent 16-64 KB live in a shared-memory ring indexed by the low bits of the global
+ * address, so that a near match source is an LDS (bank conflicts only) instead of a scattered global load.
  *
  * A match piece copies from `off` bytes back.  Zstandard's overlap rule (offset < length: the copy reads what it
  * has just written) is periodicity: x[p] = x[p - k off] for as long as p - (k - 1) off >= M (M = start of the match), so
  * every piece is re-aimed at the last period BEFORE the match, [M - off, M) -- a piece never depends on its own
- * match.  Source below the round: plain load (the previous rounds are behind a barrier).  Source inside the round
- * (9-14 % of the pieces at 2-4 KB rounds): the piece becomes a HOLE (source position, length, place in the granule),
- * the walk goes on, and the holes are filled in later PASSES of the round, separated by __syncthreads_or: a granule
- * publishes the number of the pass it was stored in, a hole accepts sources stored in EARLIER passes only (so the
- * barrier orders the global stores and the loads, no fences).  The lowest unfinished granule can always finish
- * (everything below it is stored), so a round takes at most T passes; ordinary text takes 2-3.
+ * match.  Source below the round: window or HBM at once (the previous rounds are behind a barrier).  Source inside the
+ * round (9-14 % of the pieces at 2-4 KB rounds): the piece becomes a HOLE (source position, length, place in the granule),
+ * the walk goes on, and the holes are filled in later PASSES of the round, separated by __syncthreads_or: after every pass
+ * a thread publishes its (partial) granule in the window together with a 16-bit mask of the bytes that are there; a hole
+ * is filled as soon as the masks of the PREVIOUS pass cover its source bytes (double-buffered masks: the barrier orders
+ * the stores and the loads, no fences).  The lowest unfinished granule can always finish, so a round takes at most T
+ * passes; ordinary text takes 3-4.
  *
- * The positional records reach shared memory through TMA bulk copies (cp.async.bulk + mbarrier, UBLKCP in SASS):
- * chunks of 256 records, a ring of 8+ chunks, issued two rounds ahead by thread 0, so a round never waits for its
+ * The positional records reach shared memory through TMA bulk copies (cp.async.bulk + mbarrier, UBLKCP.S.G in SASS):
+ * chunks of T / 2 records, a ring of 16 chunks, issued two rounds ahead by thread 0, so a round never waits for its
  * records.  Record index nseq of a block is the TAIL record written by k_records (E = block size, LE = all
  * literals): the literals after the last sequence are one more literal run and need no code of their own.
+ *
+ * Measured (profiles/r02_notes.md section 2): 4.9-6.5 MB of DRAM reads per 1 MiB file against 11.7 for k_execute, but
+ * 1 468 warp-instructions per 512 bytes of output against 918 -- 45 ms for config 2 against 27.  Selectable
+ * (FZG_EXEC_W=t128 .. t1024) and covered by the decode tests, not the default executor.
  */
 #pragma once
 #include "fz_kernels.cuh"
