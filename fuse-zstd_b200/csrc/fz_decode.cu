@@ -608,6 +608,198 @@ __device__ __forceinline__ void exec_block_warp(uint8_t* stage, const Block& b, 
     __syncwarp();
 }
 
+// ---- the same round with TWO sequences per lane (64 per round, sequence k of the round on lane k / 2, slot k % 2) and half the
+// warps per SM: the same number of copies in flight per SM from half as many frames, i.e. twice the L2 share per frame.
+constexpr uint32_t kStage2 = 2 * kStage;
+__device__ __forceinline__ void exec_block_warp2(uint8_t* stage, const Block& b, const uint64_t* __restrict__ sq, uint8_t* g0,
+                                                 uint64_t done, int& status, uint32_t lane)
+{
+    const uint32_t nseq = b.nseq, rsize = b.rsize;
+    const uint8_t* __restrict__ lit = b.lit;
+    const uint32_t in0 = b.rep_in[0], in1 = b.rep_in[1], in2 = b.rep_in[2];
+    uint32_t Ecarry = 0, LEcarry = 0;
+    uint64_t rc[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) rc[q] = 2 * lane + q < nseq ? __ldg(sq + 2 * lane + q) : 0;
+    for (uint32_t g = 0; g < nseq;) {
+        const uint32_t nv = min(64u, nseq - g);
+        uint32_t E[2], LE[2], S[2], LEp[2], M[2], off[2]; bool valid[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) { valid[q] = 2 * lane + q < nv; const uint64_t r = valid[q] ? rc[q] : 0; E[q] = rec_e(r); LE[q] = rec_le(r); off[q] = rec_off(r); }
+        const uint32_t ll_ = (nv - 1) >> 1, lq_ = (nv - 1) & 1;        // lane / slot of the round's last sequence
+        const uint32_t Elast = __shfl_sync(kFull, lq_ ? E[1] : E[0], ll_), LElast = __shfl_sync(kFull, lq_ ? LE[1] : LE[0], ll_);
+#pragma unroll
+        for (int q = 0; q < 2; q++) if (!valid[q]) { E[q] = Elast; LE[q] = LElast; }
+        S[0] = __shfl_up_sync(kFull, E[1], 1); LEp[0] = __shfl_up_sync(kFull, LE[1], 1);
+        if (lane == 0) { S[0] = Ecarry; LEp[0] = LEcarry; }
+        S[1] = E[0]; LEp[1] = LE[0];
+        const uint32_t gS = Ecarry;                              // output position where this round starts
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            M[q] = S[q] + (LE[q] - LEp[q]);
+            off[q] = valid[q] ? off_resolve(off[q], in0, in1, in2) : 1;
+            if (valid[q] && (uint64_t)off[q] > done + M[q]) { off[q] = 0; status = FZG_E_CORRUPT; }     // reaches before the frame start
+        }
+        // sequences of this round: the leading ones whose output fits the stage (E never decreases: a prefix in sequence order)
+        const uint32_t m = (uint32_t)__popc(__ballot_sync(kFull, valid[0] && E[0] - gS <= kStage2)) + (uint32_t)__popc(__ballot_sync(kFull, valid[1] && E[1] - gS <= kStage2));
+        if (m == 0) {                                            // sequence g alone is larger than the stage
+            const uint32_t ll0 = __shfl_sync(kFull, LE[0] - LEp[0], 0), ml0 = __shfl_sync(kFull, E[0] - M[0], 0), off0 = __shfl_sync(kFull, off[0], 0);
+            warp_big_sequence(g0 + gS, lit + LEcarry, ll0, ml0, off0, lane);
+            Ecarry = __shfl_sync(kFull, E[0], 0); LEcarry = __shfl_sync(kFull, LE[0], 0);
+            g += 1;
+#pragma unroll
+            for (int q = 0; q < 2; q++) rc[q] = g + 2 * lane + q < nseq ? __ldg(sq + g + 2 * lane + q) : 0;
+            continue;
+        }
+#pragma unroll
+        for (int q = 0; q < 2; q++) rc[q] = g + m + 2 * lane + q < nseq ? __ldg(sq + g + m + 2 * lane + q) : 0;
+        const uint32_t el_ = (m - 1) >> 1, eq_ = (m - 1) & 1;
+        const uint32_t gE = __shfl_sync(kFull, eq_ ? E[1] : E[0], el_);         // end of the round's output
+        const uint32_t LEend = __shfl_sync(kFull, eq_ ? LE[1] : LE[0], el_);
+        const uint32_t a = (uint32_t)((uintptr_t)(g0 + gS) & 15); // stage[a + i] <-> g0[gS + i]: same low address bits as HBM
+        uint8_t* const st = stage + a - gS;                       // st[p] is the stage byte of output position p (gS <= p < gE)
+        bool mine[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) mine[q] = 2 * lane + q < m;
+        // ---- 1. literal runs
+        {
+            uint32_t pos[2]; const uint8_t* src[2]; bool go[2];
+#pragma unroll
+            for (int q = 0; q < 2; q++) { pos[q] = S[q]; src[q] = lit + LEp[q]; go[q] = mine[q] && pos[q] < M[q]; }
+            while (__any_sync(kFull, go[0] || go[1])) {
+                uint64_t v[2] = { 0, 0 }; uint32_t nbq[2] = { 0, 0 };
+#pragma unroll
+                for (int q = 0; q < 2; q++) if (go[q]) { nbq[q] = min(8u, M[q] - pos[q]); v[q] = ld8_any(src[q], nbq[q]); }      // both slots' loads first
+#pragma unroll
+                for (int q = 0; q < 2; q++)
+                    if (go[q]) { st_stage(st + pos[q], v[q], nbq[q]); pos[q] += nbq[q]; src[q] += nbq[q]; go[q] = pos[q] < M[q]; }
+            }
+        }
+        __syncwarp();
+        // ---- 2. matches
+        {
+            uint32_t pos[2]; bool pending[2];
+#pragma unroll
+            for (int q = 0; q < 2; q++) { pos[q] = M[q]; pending[q] = mine[q] && pos[q] < E[q]; }
+            while (__any_sync(kFull, pending[0] || pending[1])) {
+                const uint32_t p0 = __ballot_sync(kFull, pending[0]), p1 = __ballot_sync(kFull, pending[1]);
+                const uint32_t fl = (uint32_t)__ffs((int)(p0 | p1)) - 1u, fq = (p0 >> fl) & 1u ? 0u : 1u;   // first unfinished sequence, in sequence order
+                const uint32_t front = __shfl_sync(kFull, fq ? pos[1] : pos[0], fl);                         // everything below it is written
+                bool go[2] = { pending[0], pending[1] };
+                while (__any_sync(kFull, go[0] || go[1])) {
+                    // both slots' loads are issued before either slot's stores (a slot only reads below `front` or its own bytes)
+                    uint64_t vv[2] = { 0, 0 }; uint32_t nbq[2] = { 0, 0 };
+#pragma unroll
+                    for (int q = 0; q < 2; q++)
+                        if (go[q]) {
+                            const bool is_first = lane == fl && (uint32_t)q == fq;
+                            uint32_t nb = min(8u, E[q] - pos[q]);
+                            uint64_t v = 0;
+                            const uint32_t of = off[q];
+                            if (of == 0) { /* corrupt: zeros */ }
+                            else if (of < 8 && of < nb) {         // the step overlaps itself: expand the period byte by byte
+                                const int32_t s0 = (int32_t)pos[q] - (int32_t)of;
+                                const bool ok = is_first || (uint32_t)(s0 + (int32_t)of) <= front || s0 >= (int32_t)M[q];   // period written?
+                                if (ok) {
+                                    const uint8_t* sp = s0 < (int32_t)gS ? (const uint8_t*)g0 + s0 : (const uint8_t*)st + s0;
+                                    const uint32_t take = s0 < (int32_t)gS ? min(of, gS - (uint32_t)s0) : of;   // a period straddling the round start
+                                    uint64_t pat = ld8_any(sp, take);
+                                    if (take < of) pat = (pat & ((1ull << (8 * take)) - 1)) | (ld8_any((const uint8_t*)st + gS, of - take) << (8 * take));
+                                    for (uint32_t i = 0; i < nb; i++) v |= ((pat >> (8 * (i % of))) & 0xFF) << (8 * i);
+                                } else nb = 0;
+                            } else {
+                                const int32_t s = (int32_t)pos[q] - (int32_t)of;
+                                // available bytes: below `front`, or this sequence's own match bytes written so far
+                                const uint32_t lim = is_first ? pos[q] : ((s >= (int32_t)M[q]) ? pos[q] : front);
+                                if (s < (int32_t)gS) {             // before the round: HBM / L2 (earlier rounds, earlier blocks)
+                                    nb = min(nb, gS - (uint32_t)s);
+                                    v = ld8_any((const uint8_t*)g0 + s, nb);
+                                } else if ((uint32_t)s + nb <= lim) v = ld8_any((const uint8_t*)st + s, nb);
+                                else if ((uint32_t)s < lim) { nb = lim - (uint32_t)s; v = ld8_any((const uint8_t*)st + s, nb); }
+                                else nb = 0;
+                            }
+                            vv[q] = v; nbq[q] = nb;
+                        }
+#pragma unroll
+                    for (int q = 0; q < 2; q++)
+                        if (go[q]) {
+                            if (nbq[q]) { st_stage(st + pos[q], vv[q], nbq[q]); pos[q] += nbq[q]; go[q] = pos[q] < E[q]; }
+                            else go[q] = false;                   // its source is still being produced by a lower sequence
+                        }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 2; q++) pending[q] = mine[q] && pos[q] < E[q];
+            }
+        }
+        __syncwarp();
+        // ---- 3. flush stage[a .. a + (gE - gS)) -> g0 + gS: head bytes, aligned 16-byte body, tail bytes
+        {
+            const uint32_t n = gE - gS;
+            uint8_t* gd = g0 + gS;
+            const uint32_t head = min(n, (16 - a) & 15);
+            if (lane < head) gd[lane] = stage[a + lane];
+            const uint32_t nvec = (n - head) >> 4;
+            for (uint32_t i = lane; i < nvec; i += 32) *(uint4*)(gd + head + 16 * i) = *(const uint4*)(stage + a + head + 16 * i);
+            const uint32_t tail0 = head + (nvec << 4);
+            if (tail0 + lane < n) gd[tail0 + lane] = stage[a + tail0 + lane];
+        }
+        __syncwarp();
+        Ecarry = gE; LEcarry = LEend;
+        g += m;
+#if FZ_EXEC_PREFETCH
+        {   // the next round's match sources, a round ahead (see exec_block_warp)
+            const uint32_t nn = g < nseq ? min(64u, nseq - g) : 0u;
+            const uint32_t En0 = rec_e(rc[0]), LEn0 = rec_le(rc[0]), En1 = rec_e(rc[1]), LEn1 = rec_le(rc[1]);
+            uint32_t Sn0 = __shfl_up_sync(kFull, En1, 1), LEpn0 = __shfl_up_sync(kFull, LEn1, 1);
+            if (lane == 0) { Sn0 = Ecarry; LEpn0 = LEcarry; }
+            const uint32_t Mn0 = Sn0 + (LEn0 - LEpn0), Mn1 = En0 + (LEn1 - LEn0);
+            const uint32_t o0 = off_resolve(rec_off(rc[0]), in0, in1, in2), o1 = off_resolve(rec_off(rc[1]), in0, in1, in2);
+            if (2 * lane < nn && o0 != 0 && (uint64_t)o0 <= done + Mn0) exec_prefetch(g0 + Mn0 - o0, En0 - Mn0);
+            if (2 * lane + 1 < nn && o1 != 0 && (uint64_t)o1 <= done + Mn1) exec_prefetch(g0 + Mn1 - o1, En1 - Mn1);
+        }
+#endif
+    }
+    // literals after the last sequence
+    warp_copy(g0 + Ecarry, lit + LEcarry, rsize - Ecarry, lane);
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kExecWarps * 32, kExecCtasPerSm / 2) k_execute2(Frame* frames, const Block* blocks, const Item* items,
+                                                                                  const ItemOut* outs, const uint64_t* seqs,
+                                                                                  uint32_t n_frames, uint32_t* ticket)
+{
+    __shared__ __align__(16) uint8_t s_stage[kExecWarps][kStage2 + 48];
+    const uint32_t lane = threadIdx.x & 31;
+    uint8_t* stage = s_stage[threadIdx.x >> 5];
+    for (;;) {
+        uint32_t f = 0;
+        if (lane == 0) f = atomicAdd(ticket, 1);
+        f = __shfl_sync(kFull, f, 0);
+        if (f >= n_frames) return;
+        Frame& fr = frames[f];
+        if (outs[fr.item].fail) continue;
+        uint8_t* const fbase = items[fr.item].dst + fr.out_off;
+        uint64_t done = 0;
+        int status = 0;
+        for (uint32_t kb = 0; kb < fr.n_blocks; kb++) {
+            const Block& b = blocks[fr.first_block + kb];
+            uint8_t* const g0 = fbase + done;
+            const uint32_t rsize = b.rsize;
+            if (b.type == BT_RAW) warp_copy(g0, b.src, rsize, lane);
+            else if (b.type == BT_RLE) {
+                const uint8_t v = b.src[0];
+                for (uint32_t i = lane; i < rsize; i += 32) g0[i] = v;
+            } else if (b.nseq == 0) warp_copy(g0, b.lit, rsize, lane);
+            else exec_block_warp2(stage, b, seqs + b.seq_base, g0, done, status, lane);
+            __syncwarp();                      // later blocks read this one back (the window)
+            done += rsize;
+        }
+        status = __reduce_max_sync(kFull, status);
+        if (lane == 0 && status) fr.status = status;
+    }
+}
+
 // ---- the same round, with the 8-byte STEPS of its copies dealt out evenly over the lanes.
 // exec_block_warp gives a lane one sequence and lets it loop over its literal run and its match: a round then takes as many
 // step iterations as its longest run plus its longest match (about eight on JSON text, 21 of 32 lanes busy) for an average
@@ -1418,6 +1610,7 @@ static int exec_warps_override()          // FZG_EXEC_W: the execute kernel, rea
     const char* e = getenv("FZG_EXEC_W");
     if (e && e[0] == 't') { const int t = atoi(e + 1); return (t == 128 || t == 256 || t == 512 || t == 1024) ? -t : 0; }
     if (e && e[0] == 'p') { const int t = atoi(e + 1); return (t == 2 || t == 4 || t == 8) ? 200 + t : 0; }     // k_execute_pass<W>
+    if (e && e[0] == 'd') return 65;                                  // k_execute2: two sequences per lane, half the warps per SM
     if (e && e[0] == 's') return 64;                                  // k_execute<true>: warp per frame, steps dealt out over the lanes
     const int v = e ? atoi(e) : 0;
     return (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ? v : 0;
@@ -1581,6 +1774,10 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
         if (w == 202) pass(std::integral_constant<int, 2>{});
         else if (w == 204) pass(std::integral_constant<int, 4>{});
         else if (w == 208) pass(std::integral_constant<int, 8>{});
+        else if (w == 65) {
+            const uint32_t grid = (uint32_t)std::min<uint64_t>((n_frames + kExecWarps - 1) / kExecWarps, (uint64_t)g_sm_count * (kExecCtasPerSm / 2));
+            k_execute2<<<grid, kExecWarps * 32, 0, s>>>(d_frames, d_blocks, d_items, d_outs, d_seq, (uint32_t)n_frames, d_tickets + 1);
+        }
         else if (w == -128) tile(std::integral_constant<int, 128>{});
         else if (w == -256) tile(std::integral_constant<int, 256>{});
         else if (w == -512) tile(std::integral_constant<int, 512>{});

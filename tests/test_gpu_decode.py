@@ -31,11 +31,13 @@ def _init():
     yield
 
 
-@pytest.fixture(params=["p4", "p2", "s", "t128", "t256", "t1024", "1", "8"])
+@pytest.fixture(params=["1", "8", "s", "d", "p4", "t128", "t1024"])
 def exec_w(request):
-    """the execute kernel: k_execute<true> (warp per frame, steps dealt out over the lanes), k_execute_tile with 128 / 256 /
-    1024 threads per frame, k_execute<false> (1: a lane loops over its sequence) or k_execute_cta<8>; without the fixture the
-    library chooses by batch shape"""
+    """the execute kernel (FZG_EXEC_W): 1 = k_execute<false> (warp per frame, a lane loops over its sequence: the default for
+    large batches), 8 = k_execute_cta<8> (bitmap dataflow: small batches), and round 2's alternatives -- s = k_execute<true>
+    (steps dealt out over the lanes), d = k_execute2 (two sequences per lane), p4 = k_execute_pass<4> (four warps per frame,
+    barrier passes), t128 / t1024 = k_execute_tile (output-centric, shared-memory window, TMA record ring); without the
+    fixture the library chooses by batch shape"""
     old = os.environ.get("FZG_EXEC_W")
     os.environ["FZG_EXEC_W"] = request.param
     yield request.param
