@@ -13,6 +13,22 @@
  */
 #pragma once
 
+// ld8_any in two halves: issue the (one or two) aligned 8-byte loads now, build the value later -- so that several copies' loads
+// are in flight before the first of them is used (a warp stalls at the first USE of a load, not at the load)
+struct Ld8 { uint2 w0, w1; uint32_t sh; };
+__device__ __forceinline__ Ld8 ld8_issue(const uint8_t* g, uint32_t nb)
+{
+    Ld8 r; r.w0 = make_uint2(0, 0); r.w1 = make_uint2(0, 0); r.sh = 0;
+    if (nb) {
+        const uintptr_t a = (uintptr_t)g & ~(uintptr_t)7;
+        r.sh = (uint32_t)((uintptr_t)g & 7);
+        r.w0 = *(const uint2*)a;
+        if (r.sh + nb > 8) r.w1 = *(const uint2*)(a + 8);
+    }
+    return r;
+}
+__device__ __forceinline__ uint64_t ld8_finish(const Ld8& r) { return funnel8(r.w0.x, r.w0.y, r.w1.x, r.w1.y, r.sh); }
+
 // ---- the same round with TWO sequences per lane (64 per round, sequence k of the round on lane k / 2, slot k % 2) and half the
 // warps per SM: the same number of copies in flight per SM from half as many frames, i.e. twice the L2 share per frame.
 constexpr uint32_t kStage2 = 2 * kStage;
@@ -72,12 +88,12 @@ __device__ __forceinline__ void exec_block_warp2(uint8_t* stage, const Block& b,
 #pragma unroll
             for (int q = 0; q < 2; q++) { pos[q] = S[q]; src[q] = lit + LEp[q]; go[q] = mine[q] && pos[q] < M[q]; }
             while (__any_sync(kFull, go[0] || go[1])) {
-                uint64_t v[2] = { 0, 0 }; uint32_t nbq[2] = { 0, 0 };
+                Ld8 ld[2]; uint32_t nbq[2] = { 0, 0 };
 #pragma unroll
-                for (int q = 0; q < 2; q++) if (go[q]) { nbq[q] = min(8u, M[q] - pos[q]); v[q] = ld8_any(src[q], nbq[q]); }      // both slots' loads first
+                for (int q = 0; q < 2; q++) { nbq[q] = go[q] ? min(8u, M[q] - pos[q]) : 0u; ld[q] = ld8_issue(src[q], nbq[q]); }       // both slots' loads first
 #pragma unroll
                 for (int q = 0; q < 2; q++)
-                    if (go[q]) { st_stage(st + pos[q], v[q], nbq[q]); pos[q] += nbq[q]; src[q] += nbq[q]; go[q] = pos[q] < M[q]; }
+                    if (go[q]) { st_stage(st + pos[q], ld8_finish(ld[q]), nbq[q]); pos[q] += nbq[q]; src[q] += nbq[q]; go[q] = pos[q] < M[q]; }
             }
         }
         __syncwarp();
@@ -93,9 +109,10 @@ __device__ __forceinline__ void exec_block_warp2(uint8_t* stage, const Block& b,
                 bool go[2] = { pending[0], pending[1] };
                 while (__any_sync(kFull, go[0] || go[1])) {
                     // both slots' loads are issued before either slot's stores (a slot only reads below `front` or its own bytes)
-                    uint64_t vv[2] = { 0, 0 }; uint32_t nbq[2] = { 0, 0 };
+                    uint64_t vv[2] = { 0, 0 }; uint32_t nbq[2] = { 0, 0 }; Ld8 ld[2]; bool raw[2] = { false, false };
 #pragma unroll
-                    for (int q = 0; q < 2; q++)
+                    for (int q = 0; q < 2; q++) {
+                        const uint8_t* sp = (const uint8_t*)g0; uint32_t nl = 0;        // what to load for this slot (nl == 0: nothing)
                         if (go[q]) {
                             const bool is_first = lane == fl && (uint32_t)q == fq;
                             uint32_t nb = min(8u, E[q] - pos[q]);
@@ -106,9 +123,9 @@ __device__ __forceinline__ void exec_block_warp2(uint8_t* stage, const Block& b,
                                 const int32_t s0 = (int32_t)pos[q] - (int32_t)of;
                                 const bool ok = is_first || (uint32_t)(s0 + (int32_t)of) <= front || s0 >= (int32_t)M[q];   // period written?
                                 if (ok) {
-                                    const uint8_t* sp = s0 < (int32_t)gS ? (const uint8_t*)g0 + s0 : (const uint8_t*)st + s0;
+                                    const uint8_t* pp = s0 < (int32_t)gS ? (const uint8_t*)g0 + s0 : (const uint8_t*)st + s0;
                                     const uint32_t take = s0 < (int32_t)gS ? min(of, gS - (uint32_t)s0) : of;   // a period straddling the round start
-                                    uint64_t pat = ld8_any(sp, take);
+                                    uint64_t pat = ld8_any(pp, take);
                                     if (take < of) pat = (pat & ((1ull << (8 * take)) - 1)) | (ld8_any((const uint8_t*)st + gS, of - take) << (8 * take));
                                     for (uint32_t i = 0; i < nb; i++) v |= ((pat >> (8 * (i % of))) & 0xFF) << (8 * i);
                                 } else nb = 0;
@@ -116,15 +133,18 @@ __device__ __forceinline__ void exec_block_warp2(uint8_t* stage, const Block& b,
                                 const int32_t s = (int32_t)pos[q] - (int32_t)of;
                                 // available bytes: below `front`, or this sequence's own match bytes written so far
                                 const uint32_t lim = is_first ? pos[q] : ((s >= (int32_t)M[q]) ? pos[q] : front);
-                                if (s < (int32_t)gS) {             // before the round: HBM / L2 (earlier rounds, earlier blocks)
-                                    nb = min(nb, gS - (uint32_t)s);
-                                    v = ld8_any((const uint8_t*)g0 + s, nb);
-                                } else if ((uint32_t)s + nb <= lim) v = ld8_any((const uint8_t*)st + s, nb);
-                                else if ((uint32_t)s < lim) { nb = lim - (uint32_t)s; v = ld8_any((const uint8_t*)st + s, nb); }
+                                if (s < (int32_t)gS) { nb = min(nb, gS - (uint32_t)s); sp = (const uint8_t*)g0 + s; nl = nb; }       // before the round: HBM / L2
+                                else if ((uint32_t)s + nb <= lim) { sp = (const uint8_t*)st + s; nl = nb; }
+                                else if ((uint32_t)s < lim) { nb = lim - (uint32_t)s; sp = (const uint8_t*)st + s; nl = nb; }
                                 else nb = 0;
                             }
                             vv[q] = v; nbq[q] = nb;
                         }
+                        raw[q] = nl != 0;
+                        ld[q] = ld8_issue(sp, nl);                 // both slots' loads are issued before either is used
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; q++) if (raw[q]) vv[q] = ld8_finish(ld[q]);
 #pragma unroll
                     for (int q = 0; q < 2; q++)
                         if (go[q]) {
