@@ -16,7 +16,7 @@ EXPORTS = ["fzg_init", "fzg_shutdown", "fzg_device_count", "fzg_decode_fd", "fzg
            "fzg_encode_batch", "fzg_encode_bound", "fzg_frame_info", "fzg_strerror", "fzg_last_timing",
            "fzg_stage_name", "fzg_stream", "fzg_decode_range", "fzg_decode_range_fd", "fzg_seek_footer",
            "fzg_cache_configure", "fzg_cache_reserve", "fzg_cache_prefetch", "fzg_cache_prefetch_async", "fzg_cache_open", "fzg_cache_invalidate",
-           "fzg_cache_stats", "fzg_cache_drain"]
+           "fzg_cache_stats", "fzg_cache_drain", "fzg_cache_view", "fzg_cache_unview"]
 
 
 class Timing(C.Structure):

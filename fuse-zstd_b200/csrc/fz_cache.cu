@@ -43,6 +43,7 @@ namespace {
 constexpr size_t kSlabBytes = (size_t)256 << 20;
 struct Slab {
     uint8_t* p = nullptr; size_t cap = 0, used = 0;
+    int pins = 0;                                    // views handed out by fzg_cache_view: a pinned slab is never reused
     std::vector<uint64_t> keys;                      // entries that live here (stale keys are harmless: see evict_slab)
 };
 struct Entry {
@@ -91,7 +92,7 @@ int alloc_locked(size_t need, size_t* off)
         sl.cap = want; g_slabs.push_back(std::move(sl)); g_cur = (int)g_slabs.size() - 1;
     } else {
         int next = -1;
-        for (size_t t = 1; t <= g_slabs.size(); t++) { const int c = (int)((g_cur + t) % g_slabs.size()); if (g_slabs[c].cap >= need) { next = c; break; } }
+        for (size_t t = 1; t <= g_slabs.size(); t++) { const int c = (int)((g_cur + t) % g_slabs.size()); if (g_slabs[c].cap >= need && g_slabs[c].pins == 0) { next = c; break; } }
         if (next < 0) return -1;
         g_cur = next; evict_slab_locked(g_cur);
     }
@@ -117,7 +118,10 @@ extern "C" int fzg_cache_configure(size_t capacity_bytes)
 {
     std::lock_guard<std::mutex> batch(g_batch_mu);
     std::lock_guard<std::mutex> lk(g_mu);
-    if (capacity_bytes != g_capacity) drop_all_locked();          // the slabs are sized for a capacity: a new one starts empty
+    if (capacity_bytes != g_capacity) {
+        for (const Slab& sl : g_slabs) if (sl.pins) return -EBUSY;  // a view still points into a slab
+        drop_all_locked();                                        // the slabs are sized for a capacity: a new one starts empty
+    }
     g_capacity = capacity_bytes;
     return 0;
 }
@@ -298,6 +302,32 @@ extern "C" int fzg_cache_open(int src_fd, int dst_fd, uint64_t key, uint64_t* ou
     }
     if (hit) *hit = 0;
     return fzg_decode_fd(src_fd, dst_fd, key, out_size);
+}
+
+
+// The plain bytes of a cached file IN PLACE: a read-only open needs no tmpfile at all (open_wrapper copies the decoded bytes into
+// one, src/main.rs:462-466, and every read then copies them out again).  The slab that holds the entry is pinned until
+// fzg_cache_unview; the entry may be invalidated meanwhile, the bytes stay (a reader keeps what it opened, as with the
+// reference's tmpfile).  -ENOENT: not cached (or stale): the caller decodes the ordinary way.
+extern "C" int fzg_cache_view(int src_fd, uint64_t key, const void** data, uint64_t* size, void** token)
+{
+    if (!data || !size || !token) return -EINVAL;
+    struct stat st;
+    if (fstat(src_fd, &st) != 0) return -errno;
+    std::unique_lock<std::mutex> lk(g_mu);
+    g_cv.wait(lk, [&] { return !g_pending.count(key); });
+    auto it = g_map.find(key);
+    if (it == g_map.end() || it->second.src_size != (uint64_t)st.st_size || it->second.mtime_ns != mtime_ns(st)) return -ENOENT;
+    Slab& sl = g_slabs[it->second.slab];
+    sl.pins++; g_hits++;
+    *data = sl.p + it->second.off; *size = it->second.n; *token = (void*)(uintptr_t)(it->second.slab + 1);
+    return 0;
+}
+extern "C" void fzg_cache_unview(void* token)
+{
+    const size_t si = (size_t)(uintptr_t)token;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (si >= 1 && si <= g_slabs.size() && g_slabs[si - 1].pins > 0) g_slabs[si - 1].pins--;
 }
 
 extern "C" int fzg_cache_invalidate(uint64_t key)

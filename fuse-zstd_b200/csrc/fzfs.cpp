@@ -100,7 +100,11 @@ bool content_size_from_headers(int fd, uint64_t* out)
     return ip == n;
 }
 
-struct Handle { int flags; bool needs_sync; int fd; bool has_refs; uint64_t ino; std::string path; };
+struct Handle {
+    int flags; bool needs_sync; int fd; bool has_refs; uint64_t ino; std::string path;
+    // a read-only open served from the decoded-file cache IN PLACE (fd == -1): no tmpfile until somebody writes, truncates or fsyncs
+    const uint8_t* view = nullptr; uint64_t view_size = 0; void* pin = nullptr;
+};
 
 class Fs {
 public:
@@ -124,6 +128,7 @@ private:
     // readahead window per directory: the .zst entries in natural order, which of them were handed to the codec
     struct DirRa { std::vector<std::string> names; std::vector<uint8_t> asked; std::unordered_map<std::string, size_t> index; int64_t mtime_ns = -1; };
     std::unordered_map<std::string, DirRa> ra_;
+    std::vector<uint8_t> rbuf_;                                  // FUSE_READ reply buffer
 
     // ---- inode numbers (src/main.rs:719-753)
     uint64_t next_ino()
@@ -187,7 +192,12 @@ private:
         if (stat(path.c_str(), &st) != 0) return errno;
         fill_attr(a, st, ino, S_ISDIR(st.st_mode) ? (uint64_t)st.st_size : real_size(path));
         auto h = by_ino_.find(ino);                                // an open file: the size of its tmpfile is the truth
-        if (h != by_ino_.end() && !h->second.empty()) { struct stat ts; if (fstat(handles_[*h->second.begin()].fd, &ts) == 0) { a.size = (uint64_t)ts.st_size; a.blocks = (a.size + 511) / 512; } }
+        if (h != by_ino_.end() && !h->second.empty()) {
+            const Handle& h0 = handles_[*h->second.begin()];
+            struct stat ts;
+            if (h0.view) { a.size = h0.view_size; a.blocks = (a.size + 511) / 512; }
+            else if (fstat(h0.fd, &ts) == 0) { a.size = (uint64_t)ts.st_size; a.blocks = (a.size + 511) / 512; }
+        }
         return 0;
     }
 
@@ -199,6 +209,30 @@ private:
         handles_[fh] = Handle{ flags, false, fd, true, ino, path };
         by_ino_[ino].insert(fh);
         return fh;
+    }
+    void drop_handle_backing(Handle& h) { if (h.view) { fzfs_unview(h.pin); h.view = nullptr; h.pin = nullptr; } else if (h.fd >= 0) close(h.fd); h.fd = -1; }
+    // every in-place handle of `ino` gets the ordinary backing after all: ONE tmpfile holding the plain bytes, dup'ed per handle
+    int materialize(uint64_t ino)
+    {
+        auto m = by_ino_.find(ino);
+        if (m == by_ino_.end()) return 0;
+        int tmp = -1;
+        for (uint64_t fh : m->second) {
+            Handle& h = handles_[fh];
+            if (!h.view) continue;
+            int fd;
+            if (tmp < 0) {
+                char tmpl[] = "/tmp/fzfs-XXXXXX";
+                tmp = mkstemp(tmpl);
+                if (tmp < 0) return errno;
+                unlink(tmpl);
+                for (uint64_t o = 0; o < h.view_size;) { const ssize_t w = pwrite(tmp, h.view + o, h.view_size - o, (off_t)o); if (w < 0) { if (errno == EINTR) continue; const int e = errno; close(tmp); return e; } o += (uint64_t)w; }
+                fd = tmp;
+            } else fd = dup(tmp);
+            if (fd < 0) return errno;
+            fzfs_unview(h.pin); h.view = nullptr; h.pin = nullptr; h.fd = fd;
+        }
+        return 0;
     }
     void forget_ino(uint64_t ino)                                 // OpenedFiles::unlink: later syncs of these handles are no-ops
     {
@@ -292,12 +326,22 @@ int Fs::sync_to_fs(uint64_t fh, bool close_it, bool force)
         if (h.has_refs) { auto m = by_ino_.find(h.ino); if (m != by_ino_.end()) { m->second.erase(fh); if (m->second.empty()) by_ino_.erase(m); } }
     }
     int err = 0;
+    if ((h.needs_sync || force) && h.has_refs && h.view) {          // fsync of an in-place handle: it needs a file to encode from
+        if (!close_it) { err = materialize(h.ino); if (err) return err; h = handles_[fh]; }
+        else {                                                      // (closing: this copy of the handle is the only one left)
+            char tmpl[] = "/tmp/fzfs-XXXXXX"; const int tmp = mkstemp(tmpl);
+            if (tmp < 0) return errno;
+            unlink(tmpl);
+            for (uint64_t o = 0; o < h.view_size;) { const ssize_t w = pwrite(tmp, h.view + o, h.view_size - o, (off_t)o); if (w < 0) { if (errno == EINTR) continue; break; } o += (uint64_t)w; }
+            fzfs_unview(h.pin); h.view = nullptr; h.pin = nullptr; h.fd = tmp;
+        }
+    }
     if ((h.needs_sync || force) && h.has_refs) {
         const size_t k = h.path.rfind('/');
         err = store_to_source_file(h.fd, h.path.substr(0, k), h.path.substr(k + 1), nullptr);
         if (!err && !close_it) handles_[fh].needs_sync = false;
     }
-    if (close_it) close(h.fd);
+    if (close_it) drop_handle_backing(h);
     return err;
 }
 
@@ -380,10 +424,20 @@ int Fs::do_open(uint64_t ino, int flags, uint64_t* fh_out)
 {
     auto m = by_ino_.find(ino);
     if (m != by_ino_.end() && !m->second.empty()) {                 // OpenedFiles::duplicate: dup the tmpfile, no decode
+        if ((flags & O_ACCMODE) != O_RDONLY) { if (int e = materialize(ino)) return e; }    // a writer joins: every handle moves to one tmpfile
         const Handle& h0 = handles_[*m->second.begin()];
-        const int fd = dup(h0.fd);
+        if (h0.view) {                                               // another reader of bytes that are served in place: share them
+            const int src = open(h0.path.c_str(), O_RDONLY | O_CLOEXEC);
+            const void* data = nullptr; uint64_t vs = 0; void* pin = nullptr;
+            const bool ok = src >= 0 && fzfs_view(src, ino, &data, &vs, &pin) == 0 && data == (const void*)h0.view;
+            if (src >= 0) close(src);
+            if (!ok) { if (pin) fzfs_unview(pin); if (int e = materialize(ino)) return e; }
+            else { const std::string hp = h0.path; *fh_out = insert_handle(ino, flags, -1, hp); Handle& nh = handles_[*fh_out]; nh.view = (const uint8_t*)data; nh.view_size = vs; nh.pin = pin; return 0; }
+        }
+        const Handle& h1 = handles_[*m->second.begin()];
+        const int fd = dup(h1.fd);
         if (fd < 0) return errno;
-        *fh_out = insert_handle(ino, flags, fd, h0.path);
+        *fh_out = insert_handle(ino, flags, fd, h1.path);
         return 0;
     }
     std::string path;
@@ -391,6 +445,21 @@ int Fs::do_open(uint64_t ino, int flags, uint64_t* fh_out)
     readahead_dir(dir_of(path), path);
     const int src = open(path.c_str(), O_RDONLY | O_CLOEXEC);
     if (src < 0) return errno;
+    if (readahead_ && (flags & O_ACCMODE) == O_RDONLY) {            // a reader of a file the readahead has decoded: its bytes in place, no tmpfile
+        const void* data = nullptr; uint64_t vs = 0; void* pin = nullptr;
+        if (fzfs_view(src, ino, &data, &vs, &pin) == 0) {
+            uint8_t b[8]; put_be64(b, vs);
+            uint8_t cur[8];
+            int verr = 0;
+            const bool same = xattr_ok_ && fgetxattr(src, "user.real_size", cur, 8) == 8 && memcmp(cur, b, 8) == 0;
+            if (!same) { set_real_size(path, src, vs); if (xattr_ok_ && fsync(src) != 0) verr = errno; }   // as below (src/main.rs:473-484)
+            close(src);
+            if (verr) { fzfs_unview(pin); return verr; }
+            *fh_out = insert_handle(ino, flags, -1, path);
+            Handle& nh = handles_[*fh_out]; nh.view = (const uint8_t*)data; nh.view_size = vs; nh.pin = pin;
+            return 0;
+        }
+    }
     char tmpl[] = "/tmp/fzfs-XXXXXX";
     const int tmp = mkstemp(tmpl);                                  // tempfile::tempfile(): unlinked at once
     if (tmp < 0) { const int e = errno; close(src); return e; }
@@ -437,9 +506,10 @@ void Fs::dispatch(const struct fuse_in_header* in, const uint8_t* arg, size_t ar
         const struct fuse_setattr_in* s = (const struct fuse_setattr_in*)arg;
         int err = 0;
         if (s->valid & FATTR_SIZE) {
-            if (s->valid & FATTR_FH) { auto h = handles_.find(s->fh); if (h != handles_.end() && ftruncate(h->second.fd, (off_t)s->size) != 0) err = errno; }
+            err = materialize(node);
+            if (!err && (s->valid & FATTR_FH)) { auto h = handles_.find(s->fh); if (h != handles_.end() && ftruncate(h->second.fd, (off_t)s->size) != 0) err = errno; }
             auto m = by_ino_.find(node);
-            if (m != by_ino_.end()) for (uint64_t fh : m->second) if (ftruncate(handles_[fh].fd, (off_t)s->size) != 0) err = errno;
+            if (!err && m != by_ino_.end()) for (uint64_t fh : m->second) if (ftruncate(handles_[fh].fd, (off_t)s->size) != 0) err = errno;
         }
         std::string p; struct fuse_attr_out o; memset(&o, 0, sizeof o);
         if (!err) err = path_of(node, p);
@@ -459,10 +529,14 @@ void Fs::dispatch(const struct fuse_in_header* in, const uint8_t* arg, size_t ar
         const struct fuse_read_in* r = (const struct fuse_read_in*)arg;
         auto h = handles_.find(r->fh);
         if (h == handles_.end()) return reply(u, ENOENT);
-        std::vector<uint8_t> buf(r->size);
-        const ssize_t n = pread(h->second.fd, buf.data(), r->size, (off_t)r->offset);
+        if (h->second.view) {                                       // served in place: straight from the cache's pinned memory
+            const uint64_t vs = h->second.view_size, off = r->offset < vs ? r->offset : vs;
+            return reply(u, 0, h->second.view + off, (size_t)std::min<uint64_t>(r->size, vs - off));
+        }
+        if (rbuf_.size() < r->size) rbuf_.resize(r->size);         // one reply buffer for the (single-threaded) loop: the reference's
+        const ssize_t n = pread(h->second.fd, rbuf_.data(), r->size, (off_t)r->offset);   // vec![0; size] per request (src/main.rs:503) zeroes 128 KiB each time
         if (n < 0) return reply(u, errno);
-        return reply(u, 0, buf.data(), (size_t)n);
+        return reply(u, 0, rbuf_.data(), (size_t)n);
     }
     case FUSE_WRITE: {
         const struct fuse_write_in* w = (const struct fuse_write_in*)arg;
@@ -636,7 +710,7 @@ void Fs::loop()
         if (in->opcode == FUSE_DESTROY) { reply(in->unique, 0); break; }
         dispatch(in, arg, arglen);
     }
-    for (auto& kv : handles_) close(kv.second.fd);
+    for (auto& kv : handles_) drop_handle_backing(kv.second);
 }
 
 std::string g_mountpoint;

@@ -18,6 +18,8 @@ int fzfs_decode(int src_fd, int dst_fd, uint64_t ino, uint64_t* out_size);      
 int fzfs_encode(int src_fd, int dst_fd, int level, uint64_t src_size, uint64_t ino, uint64_t* out_size);   /* Encoder ... finish */
 int fzfs_prefetch(const char* const* paths, const uint64_t* inos, size_t n);                     /* returns at once */
 void fzfs_invalidate(uint64_t ino);
+int fzfs_view(int src_fd, uint64_t ino, const void** data, uint64_t* size, void** pin);        /* read-only open: the plain bytes in place, or non-zero (use fzfs_decode) */
+void fzfs_unview(void* pin);
 void fzfs_codec_shutdown(void);                    /* before the daemon exits: nothing of the codec may still be running */
 #ifdef __cplusplus
 }

@@ -30,3 +30,8 @@ extern "C" int fzfs_prefetch(const char* const* paths, const uint64_t* inos, siz
 }
 extern "C" void fzfs_invalidate(uint64_t ino) { if (g_cache) fzg_cache_invalidate(ino); }
 extern "C" void fzfs_codec_shutdown(void) { fzg_shutdown(); }      // drains the prefetch threads first
+extern "C" int fzfs_view(int src_fd, uint64_t ino, const void** data, uint64_t* size, void** pin)
+{
+    return g_cache ? fzg_cache_view(src_fd, ino, data, size, pin) : -1;
+}
+extern "C" void fzfs_unview(void* pin) { fzg_cache_unview(pin); }

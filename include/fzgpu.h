@@ -119,6 +119,9 @@ int fzg_cache_prefetch_async(int device, const char* const* paths, const uint64_
 int fzg_cache_open(int src_fd, int dst_fd, uint64_t key, uint64_t* out_size, int* hit);
 int fzg_cache_invalidate(uint64_t key);           /* after store_to_source_file / rename / unlink */
 void fzg_cache_stats(uint64_t* hits, uint64_t* misses, uint64_t* bytes, uint64_t* files);
+int fzg_cache_view(int src_fd, uint64_t key, const void** data, uint64_t* size, void** token);   /* the cached plain bytes in place (read-only opens:
+                                                     no tmpfile copy of src/main.rs:462-466); 0, or -ENOENT when not cached / stale; pinned until ... */
+void fzg_cache_unview(void* token);               /* ... the view is given back */
 void fzg_cache_drain(void);                       /* waits for the prefetch batches in flight (called by fzg_shutdown; a daemon calls it before exit) */
 
 const char* fzg_strerror(int code);

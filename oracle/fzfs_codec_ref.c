@@ -42,3 +42,5 @@ int fzfs_encode(int src_fd, int dst_fd, int level, uint64_t src_size, uint64_t i
 int fzfs_prefetch(const char* const* paths, const uint64_t* inos, size_t n) { (void)paths; (void)inos; (void)n; return 0; }
 void fzfs_invalidate(uint64_t ino) { (void)ino; }
 void fzfs_codec_shutdown(void) { }
+int fzfs_view(int src_fd, uint64_t ino, const void** data, uint64_t* size, void** pin) { (void)src_fd; (void)ino; (void)data; (void)size; (void)pin; return -1; }
+void fzfs_unview(void* pin) { (void)pin; }
