@@ -238,6 +238,54 @@ def test_files_written_by_stock_zstd_and_unlink_while_open(host, ref, corpus, or
         assert not os.path.exists(os.path.join(m.data, "gone.txt.zst"))
 
 
+@pytest.mark.parametrize("host", _hosts())
+def test_readers_served_in_place_then_a_writer_joins(host, ref, corpus, oracle):
+    """A read-only open of a file the readahead has decoded is served from the cache in place (GPU host; the CPU host takes the
+    tmpfile path for the same calls).  The reference's handle semantics must survive it: every handle of an inode sees one
+    file (src/file.rs:67-102) -- a second reader shares the bytes, a writer that joins moves all handles to one tmpfile, its
+    writes are visible to the readers, fsync of a read-only handle re-encodes (src/main.rs:709-712), truncation reaches them."""
+    if not ref.available:
+        pytest.skip("system libzstd absent")
+    files = {("d/f%03d" % i): corpus.json_file(880000 + i, 300000 + 1000 * i).tobytes() for i in range(6)}
+    with Mount(host) as m:
+        os.makedirs(os.path.join(m.data, "d"))
+        for rel, plain in files.items():
+            with open(os.path.join(m.data, rel + ".zst"), "wb") as fh:
+                fh.write(ref.writer_encode(plain, 3))
+        p = os.path.join(m.mp, "d/f002"); plain = files["d/f002"]
+        r1 = os.open(p, os.O_RDONLY)
+        assert os.pread(r1, 4096, 1000) == plain[1000:5096]
+        r2 = os.open(p, os.O_RDONLY)                                       # shares the bytes
+        assert os.pread(r2, 100, len(plain) - 50) == plain[-50:]
+        assert os.fstat(r1).st_size == len(plain)
+        w = os.open(p, os.O_RDWR)                                          # a writer joins
+        os.pwrite(w, b"PATCHED!", 2000)
+        assert os.pread(r1, 8, 2000) == b"PATCHED!" and os.pread(r2, 8, 2000) == b"PATCHED!"
+        os.close(w)                                                        # release of a written handle: whole-file encode
+        want = plain[:2000] + b"PATCHED!" + plain[2008:]
+        st, back = oracle.decode(open(os.path.join(m.data, "d/f002.zst"), "rb").read(), cap=len(want))
+        assert st == 0 and back == want
+        os.close(r1); os.close(r2)
+        assert open(p, "rb").read() == want
+        # fsync of a read-only handle that is served in place: forced re-encode, same content afterwards
+        q = os.path.join(m.mp, "d/f004")
+        r = os.open(q, os.O_RDONLY)
+        before = os.stat(os.path.join(m.data, "d/f004.zst")).st_ino
+        os.fsync(r)
+        assert os.stat(os.path.join(m.data, "d/f004.zst")).st_ino != before     # atomic rename: a new backing inode
+        assert os.pread(r, 1 << 20, 0) == files["d/f004"]
+        os.close(r)
+        st, back = oracle.decode(open(os.path.join(m.data, "d/f004.zst"), "rb").read(), cap=len(files["d/f004"]))
+        assert st == 0 and back == files["d/f004"]
+        # truncation while a reader holds the file
+        t = os.path.join(m.mp, "d/f005")
+        r = os.open(t, os.O_RDONLY)
+        assert os.pread(r, 10, 0) == files["d/f005"][:10]
+        os.truncate(t, 1234)
+        assert os.fstat(r).st_size == 1234 and os.pread(r, 5000, 0) == files["d/f005"][:1234]
+        os.close(r)
+
+
 def test_product_host_fails_loudly_without_a_gpu():
     """no CPU fallback: the product host refuses to mount when the CUDA codec cannot start"""
     import torch
