@@ -13,7 +13,7 @@ OK, E_MAGIC, E_TRUNCATED, E_UNSUPPORTED, E_CORRUPT, E_DSTSIZE, E_CHECKSUM, E_FCS
 SRC_DEVICE, DST_DEVICE, NO_VERIFY_CHECKSUM, PROFILE, SEEK_TABLE = 1, 2, 4, 8, 16
 
 EXPORTS = ["fzg_init", "fzg_shutdown", "fzg_device_count", "fzg_decode_fd", "fzg_encode_fd", "fzg_decode_batch",
-           "fzg_encode_batch", "fzg_encode_bound", "fzg_frame_info", "fzg_strerror", "fzg_last_timing",
+           "fzg_encode_batch", "fzg_encode_bound", "fzg_frame_info", "fzg_strerror", "fzg_last_timing", "fzg_streamed_copies",
            "fzg_stage_name", "fzg_stream", "fzg_decode_range", "fzg_decode_range_fd", "fzg_seek_footer",
            "fzg_cache_configure", "fzg_cache_reserve", "fzg_cache_prefetch", "fzg_cache_prefetch_async", "fzg_cache_open", "fzg_cache_invalidate",
            "fzg_cache_stats", "fzg_cache_drain", "fzg_cache_view", "fzg_cache_unview"]
@@ -57,6 +57,7 @@ def lib():
         L.fzg_frame_info.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.fzg_strerror.restype = C.c_char_p; L.fzg_strerror.argtypes = [C.c_int]
         L.fzg_last_timing.restype = C.c_int; L.fzg_last_timing.argtypes = [C.c_int, C.POINTER(Timing)]
+        L.fzg_streamed_copies.restype = C.c_uint64; L.fzg_streamed_copies.argtypes = [C.c_int]
         L.fzg_stage_name.restype = C.c_char_p; L.fzg_stage_name.argtypes = [C.c_int]
         L.fzg_stream.restype = C.c_void_p; L.fzg_stream.argtypes = [C.c_int]
         if not hasattr(L, "fzg_decode_range"):            # an older tuned build loaded through FZG_LIB (kernel experiments)
@@ -173,6 +174,11 @@ def last_timing(device=0, encode=False):
         if nm:
             stages[nm] = t.kernel_ms[k]
     return dict(total_ms=t.total_ms, launches=t.launches, bytes_in=t.bytes_in, bytes_out=t.bytes_out, stages=stages)
+
+
+def streamed_copies(device=0):
+    """device -> host copies queued behind a running execute stage since init (few large frames into host buffers)"""
+    return int(lib().fzg_streamed_copies(device))
 
 
 def stream_handle(device=0):

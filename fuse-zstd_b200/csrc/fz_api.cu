@@ -59,6 +59,7 @@ extern "C" int fzg_init(const int* devices, int n_devices)
             CKR(cudaStreamCreateWithFlags(&c->lane[l].stream, cudaStreamNonBlocking));
             for (auto& e : c->lane[l].ev) CKR(cudaEventCreate(&e));
             CKR(cudaEventCreateWithFlags(&c->lane[l].ev_entropy, cudaEventDisableTiming));
+            CKR(cudaEventCreateWithFlags(&c->lane[l].ev_prog, cudaEventDisableTiming));
             { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);      // lowest priority: its CTAs take what the main stream leaves
               CKR(cudaStreamCreateWithPriority(&c->lane[l].side, cudaStreamNonBlocking, lo)); }
             CKR(cudaEventCreateWithFlags(&c->lane[l].ev_fork, cudaEventDisableTiming));
@@ -67,6 +68,7 @@ extern "C" int fzg_init(const int* devices, int n_devices)
         c->stream = c->lane[0].stream;
         CKR(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         CKR(cudaStreamCreateWithFlags(&c->copy_stream2, cudaStreamNonBlocking));
+        CKR(cudaStreamCreateWithFlags(&c->poll_stream, cudaStreamNonBlocking));
         for (auto& e : c->ev) CKR(cudaEventCreate(&e));
         int rc = fzh_decode_setup(); if (rc) return rc;
         rc = fzh_encode_setup(); if (rc) return rc;
@@ -94,13 +96,13 @@ extern "C" void fzg_shutdown(void)
             for (auto* b : lb) b->release();
             L.h_totals.release();
             for (auto& e : L.ev) cudaEventDestroy(e);
-            cudaEventDestroy(L.ev_entropy);
+            cudaEventDestroy(L.ev_entropy); cudaEventDestroy(L.ev_prog); L.h_prog.release();
             cudaEventDestroy(L.ev_fork); cudaEventDestroy(L.ev_join);
             cudaStreamDestroy(L.side);
             cudaStreamDestroy(L.stream);
         }
         for (auto& e : c->ev) cudaEventDestroy(e);
-        cudaStreamDestroy(c->copy_stream); cudaStreamDestroy(c->copy_stream2);
+        cudaStreamDestroy(c->copy_stream); cudaStreamDestroy(c->copy_stream2); cudaStreamDestroy(c->poll_stream);
         delete c;
     }
     g_ctx.clear(); g_dev.clear();
@@ -142,6 +144,12 @@ static size_t chunk_bytes()                             // (input + output) byte
 {
     static const size_t v = [] { const char* e = getenv("FZG_CHUNK_MB"); return e && atoi(e) > 0 ? (size_t)atoi(e) << 20 : (size_t)512 << 20; }();
     return v;
+}
+
+static size_t stream_out_min_bytes()                     // output bytes of a chunk from which its device -> host copy follows the execute stage
+{
+    const char* e = getenv("FZG_STREAM_OUT_MB");           // read per call (tests); "0" streams every eligible chunk, a huge value none
+    return e ? (size_t)atoll(e) << 20 : (size_t)256 << 20;
 }
 
 static int run_batch(bool encode, int device, size_t n, const void* const* src, const size_t* src_len, void* const* dst,
@@ -283,9 +291,17 @@ static int run_batch(bool encode, int device, size_t n, const void* const* src, 
             const size_t lo = cuts[k], hi = cuts[k + 1];
             if (k + 1 < nchunks && (rc = h2d(k + 1))) return rc;
             const double ta = now_ms();
-            if ((rc = run(lo, hi - lo, src_dev ? nullptr : c->ev[12 + (k & 1)]))) return rc;   // returns once chunk k is decoded
-            if (trace) fprintf(stderr, "fzgpu: chunk %zu/%zu items %zu: run %.2f -> %.2f ms (gpu %.2f ms)\n", k, nchunks, hi - lo, ta, now_ms(), c->timing.total_ms);
-            if (!dst_dev) {
+            // few large frames: their bytes go home while the chains still run (FzStreamOut); otherwise after the chunk, below
+            size_t out_bytes = 0;
+            for (size_t i = lo; i < hi; i++) out_bytes += dst_cap[i];
+            const bool arm = !dst_dev && !encode && (hi - lo < 64 || c->n_lanes == 1) && out_bytes >= stream_out_min_bytes();
+            c->so.dst = arm ? dst : nullptr; c->so.copy = s_out; c->so.poll = c->poll_stream; c->so.done = false;
+            rc = run(lo, hi - lo, src_dev ? nullptr : c->ev[12 + (k & 1)]);                    // returns once chunk k is decoded
+            const bool streamed = c->so.done;
+            c->so.dst = nullptr; c->so.done = false;
+            if (rc) return rc;
+            if (trace) fprintf(stderr, "fzgpu: chunk %zu/%zu items %zu: run %.2f -> %.2f ms (gpu %.2f ms)%s\n", k, nchunks, hi - lo, ta, now_ms(), c->timing.total_ms, streamed ? " [output streamed behind the execute stage]" : "");
+            if (!dst_dev && !streamed) {
                 bool all_full = dst_contig;
                 for (size_t i = lo; i < hi && all_full; i++) all_full = !outs[i].status && outs[i].dst_len == dst_cap[i];
                 if (all_full) {
@@ -581,6 +597,14 @@ extern "C" int fzg_last_timing(int device, fzg_timing_t* out)
     std::lock_guard<std::mutex> lk(c->mu);
     *out = c->timing;
     return 0;
+}
+
+extern "C" uint64_t fzg_streamed_copies(int device)
+{
+    FzCtx* c = ctx_for(device);
+    if (!c) return 0;
+    std::lock_guard<std::mutex> lk(c->mu);
+    return c->so.pieces;
 }
 
 extern "C" const char* fzg_stage_name(int stage) { return stage < 16 ? fzh_decode_stage_name(stage) : fzh_encode_stage_name(stage - 16); }

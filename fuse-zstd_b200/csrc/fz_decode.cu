@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 
+#include <time.h>
 #include <algorithm>
 #include <thread>
 
@@ -1084,6 +1085,56 @@ int fzh_decode_setup(void)
     return 0;
 }
 
+// Device -> host while the execute stage runs (FzStreamOut, fz_host.h).  Every frame of the chunk has an executing CTA that
+// publishes (release, GPU scope) the number of bytes it has flushed; the words are read on a stream of their own every ~0.2 ms
+// and each frame's newly finished bytes are queued on the copy-out stream in pieces of at least kPiece.  The copy engine reads
+// HBM after the progress word that covers the bytes was observed, and the flush precedes the release: it sees final bytes.
+// A frame that fails (corrupt, checksum) may leave part of its output in the caller's buffer; its status says so, as always.
+static int stream_out(FzCtx* ctx, FzLane* c, uint32_t first, uint32_t n_frames, const Frame* d_frames, const unsigned long long* d_prog, cudaEvent_t last)
+{
+    constexpr uint64_t kPiece = 4ull << 20;
+    FzStreamOut& so = ctx->so;
+    int rc = c->h_prog.reserve((size_t)n_frames * (sizeof(Frame) + 16));
+    if (rc) return rc;
+    Frame* hf = (Frame*)c->h_prog.p;
+    unsigned long long* hp = (unsigned long long*)(hf + n_frames);
+    uint64_t* sent = (uint64_t*)(hp + n_frames);
+    const Item* items = (const Item*)ctx->h_items.p + first;
+    const ItemOut* outs = (const ItemOut*)ctx->h_outs.p + first;
+    CK(cudaStreamWaitEvent(so.poll, c->ev_prog, 0));
+    CK(cudaMemcpyAsync(hf, d_frames, (size_t)n_frames * sizeof(Frame), cudaMemcpyDeviceToHost, so.poll));
+    for (uint32_t f = 0; f < n_frames; f++) sent[f] = 0;
+    auto send = [&](uint32_t f, uint64_t upto) -> int {
+        const Frame& fr = hf[f];
+        uint8_t* h = (uint8_t*)so.dst[first + fr.item] + fr.out_off + sent[f];
+        const uint8_t* d = items[fr.item].dst + fr.out_off + sent[f];
+        CK(cudaMemcpyAsync(h, d, (size_t)(upto - sent[f]), cudaMemcpyDeviceToHost, so.copy));
+        sent[f] = upto;
+        return 0;
+    };
+    for (;;) {
+        const cudaError_t q = cudaEventQuery(last);
+        if (q != cudaSuccess && q != cudaErrorNotReady) return -5;
+        if (q == cudaSuccess) break;
+        CK(cudaMemcpyAsync(hp, d_prog, (size_t)n_frames * 8, cudaMemcpyDeviceToHost, so.poll));
+        CK(cudaStreamSynchronize(so.poll));
+        for (uint32_t f = 0; f < n_frames; f++) {
+            const uint64_t avail = std::min<uint64_t>(hp[f], hf[f].out_size) & ~(uint64_t)4095;
+            if (avail >= sent[f] + kPiece) { if ((rc = send(f, avail))) return rc; so.pieces++; }
+        }
+        struct timespec ts = { 0, 200000 }; nanosleep(&ts, nullptr);
+    }
+    CK(cudaStreamSynchronize(so.poll));
+    // the kernels are done (k_finish wrote the per-item results into pinned memory): what is left of every good item
+    for (uint32_t f = 0; f < n_frames; f++) {
+        const Frame& fr = hf[f];
+        if (outs[fr.item].status || fr.out_off + fr.out_size > outs[fr.item].dst_len) continue;
+        if (fr.out_size > sent[f] && (rc = send(f, fr.out_size))) return rc;
+    }
+    so.done = true;
+    return 0;
+}
+
 // Runs the whole pipeline for items [first, first + n) of c->h_items (Item records holding device
 // pointers).  Results land in c->h_outs[first ..] (pinned).  Blocking on the context's stream.
 int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int flags, bool staggered)
@@ -1178,6 +1229,7 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
     if (side) CK(cudaStreamWaitEvent(s, c->ev_join, 0));
     k_offsets<<<gi, tb, 0, s>>>(d_items, d_infos, d_bases, d_frames, d_blocks, d_outs, n); mark(); launches++;
     bool checksum_done = false;                                          // the CTA kernels with a checksum warp verify XXH64 themselves
+    unsigned long long* frame_prog = nullptr;                            // per-frame flushed-bytes words, when this run keeps them (W = 32 + checksum CTAs)
     uint32_t n_tail = 0;                                                 // frames at the end of the batch executed (and hashed) by k_execute_cta<8>
     if (n_frames) {
         // Warps per frame, by batch shape (tools/exec_width_probe.py; ms for the whole pipeline on 1 MiB files, one warp
@@ -1200,6 +1252,8 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
                 if (r) return r;
                 gprog = (unsigned long long*)c->d_prog.p;
                 CK(cudaMemsetAsync(gprog, 0, n_frames * 8, s));
+                CK(cudaEventRecord(c->ev_prog, s));                  // k_offsets done (frames final), progress words zeroed
+                frame_prog = gprog;
                 grid = (uint32_t)n_frames * 2;
                 checksum_done = true;
             }
@@ -1277,6 +1331,9 @@ int fzh_decode_run(FzCtx* ctx, int lane_idx, uint32_t first, uint32_t n, int fla
     k_finish<<<gi, tb, 0, s>>>(d_infos, d_bases, d_frames, d_outs, h_outs, n); launches++;
     if (!prof) ev = 11;
     cudaEventRecord(c->ev[ev], s);                                   // last event
+    if (ctx->so.dst && frame_prog && lane_idx == 0) {
+        if ((rc = stream_out(ctx, c, first, (uint32_t)n_frames, d_frames, frame_prog, c->ev[ev]))) return rc;
+    }
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     c->timing.launches = launches;

@@ -50,14 +50,25 @@ struct FzLane {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[16] = {};
     FzDevBuf d_infos, d_bases, d_outs, d_totals, d_frames, d_blocks, d_seq_jobs, d_huf_jobs, d_lit, d_seq, d_seq_tabs, d_seq_hdrs, d_prog;
-    FzPinBuf h_totals;
+    FzPinBuf h_totals, h_prog;
     fzg_timing_t timing = {};
+    cudaEvent_t ev_prog = nullptr;         // recorded once the frames' progress words are zeroed (see FzStreamOut)
     cudaEvent_t ev_entropy = nullptr;      // recorded after this lane's entropy stages (literals, sequences, records)
     cudaStream_t side = nullptr;           // small batches: the literal stage runs here, beside the sequence stages
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::atomic<uint64_t> entropy_epoch{ 0 };   // call number whose ev_entropy has been enqueued
 };
 constexpr int kMaxLanes = 4;
+
+// Few large frames into host buffers: a frame is a serial chain (~1.2 GB/s) that publishes how far it is flushed, so the
+// device -> host copy of a chunk need not wait for the chunk: fzh_decode_run polls the progress words while the execute stage
+// runs and sends the finished part of every frame down the copy-out stream, piece by piece.  run_batch arms it per chunk.
+struct FzStreamOut {
+    void* const* dst = nullptr;            // host destinations of the call's items (indexed like h_items); null: off
+    cudaStream_t copy = nullptr, poll = nullptr;
+    bool done = false;                     // set by fzh_decode_run when it has queued every device -> host copy of the chunk itself
+    uint64_t pieces = 0;                   // copies queued while the kernels were still running (statistics)
+};
 
 struct FzCtx {
     int dev = -1;
@@ -69,6 +80,8 @@ struct FzCtx {
     FzLane lane[kMaxLanes];
     int n_lanes = 1;
     uint64_t epoch = 0;                    // call counter (staggering of the lanes, see fzh_decode_run)
+    cudaStream_t poll_stream = nullptr;    // small reads of progress words beside the running kernels
+    FzStreamOut so;
     // staging for host-resident batches
     FzDevBuf d_stage_src, d_stage_dst;
     FzPinBuf h_items, h_outs, h_totals, h_stage_src, h_stage_dst, e_chunks_h, e_first_h;

@@ -135,6 +135,10 @@ typedef struct {
 } fzg_timing_t;
 int fzg_last_timing(int device, fzg_timing_t* out);
 const char* fzg_stage_name(int stage);
+/* Host-resident decode of few large frames: device -> host copies of finished parts of a frame are queued while the frame is
+ * still being executed (chunks of >= FZG_STREAM_OUT_MB MiB of output, default 256, at most half as many frames as SMs).
+ * Returns how many such copies this context has queued since fzg_init (a counter for tests and traces). */
+uint64_t fzg_streamed_copies(int device);
 void* fzg_stream(int device); /* cudaStream_t of the context (for external event timing) */
 
 #ifdef __cplusplus

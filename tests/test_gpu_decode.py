@@ -372,3 +372,42 @@ def test_guard_bands_around_every_output(golden, exec_w):
     for k, n in enumerate(names):                                 # the intact ones are still right
         i = 4 * k
         assert st[i] == 0 and dl[i] == caps[i] and sha(host[offs[i]:offs[i] + caps[i]].tobytes()) == golden[n][1]["plain_sha256"], n
+
+
+def test_large_frames_go_home_behind_the_execute_stage(ref, corpus):
+    """few large frames into host buffers (SURVEY 8 config 4 in small): the device -> host copy follows the frames' progress
+    words while they are still executed; every byte compared, and what the streaming must not break: an item of several
+    frames, a bad trailer (reported, the other items intact), a small item, a capacity larger than the content"""
+    if not ref.available:
+        pytest.skip("system libzstd absent")
+    big = [corpus.json_file(5100 + i, (20 << 20) + 4097 * i).tobytes() for i in range(3)]
+    blobs = [ref.writer_encode(b, 3, window_log=23) for b in big]
+    multi_plain = corpus.json_file(5200, 9 << 20).tobytes()
+    blobs.append(b"".join(ref.writer_encode(multi_plain[o:o + (3 << 20) + 5], 3) for o in range(0, len(multi_plain), (3 << 20) + 5)))
+    bad = bytearray(blobs[1]); bad[-2] ^= 0x40
+    blobs.append(bytes(bad))
+    small = corpus.json_file(5300, 1000).tobytes()
+    blobs.append(ref.writer_encode(small, 3))
+    plains = big + [multi_plain, None, small]
+    caps = [len(big[0]), len(big[1]) + 12345, len(big[2]), len(multi_plain), len(big[1]), 4096]
+    old = os.environ.get("FZG_STREAM_OUT_MB")
+    try:
+        os.environ["FZG_STREAM_OUT_MB"] = "16"
+        before = codec.streamed_copies(0)
+        res = codec.decode_batch(blobs, caps)
+        streamed = codec.streamed_copies(0) - before
+        os.environ["FZG_STREAM_OUT_MB"] = "1000000"
+        res_plain = codec.decode_batch(blobs, caps)
+        assert codec.streamed_copies(0) - before == streamed
+    finally:
+        if old is None:
+            os.environ.pop("FZG_STREAM_OUT_MB", None)
+        else:
+            os.environ["FZG_STREAM_OUT_MB"] = old
+    assert streamed >= 6, streamed                    # 4 MiB pieces of 20 MiB frames, queued while the chains ran
+    for r in (res, res_plain):
+        for i, (st, out) in enumerate(r):
+            if plains[i] is None:
+                assert st == codec.E_CHECKSUM, (i, codec.strerror(st))
+            else:
+                assert st == 0 and out == plains[i], i
