@@ -517,16 +517,17 @@ def run_b200(args, rank, local_rank, world):
     mount = None
     if not args.no_mount and world == 1 and args.config == 2:
         try:
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "mount_bench.py"), "--jobs", "16", "--nrfiles", "125", "--fio-write"],
-                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "mount_bench.py"), "--jobs", "16", "--nrfiles", "250", "--fio-write",
+                                "--arms", "reference,gpu:1,gpu"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=400)
             if r.returncode == 0:
                 mj = json.loads(r.stdout.decode().strip().splitlines()[-1])
-                mount = {"gpu_MBps": mj.get("gpu"), "reference_cpu_MBps": mj.get("reference"),
+                mount = {"gpu_MBps": mj.get("gpu"), "gpu_1_serving_thread_MBps": mj.get("gpu_1_threads"), "reference_cpu_MBps": mj.get("reference"),
                          "gpu_write_verify_MBps": mj.get("gpu_write_verify"), "reference_cpu_write_verify_MBps": mj.get("reference_write_verify"),
                          "gpu_fio_write_and_verify_MBps": mj.get("gpu_fio_write_and_verify"), "reference_cpu_fio_write_and_verify_MBps": mj.get("reference_fio_write_and_verify"),
                          "workload": mj.get("workload"),
                          "jobs": mj.get("jobs"), "nrfiles": mj.get("nrfiles"), "filesize": mj.get("filesize"), "bs": mj.get("bs"),
-                         "note": "one FUSE thread in both arms, as fuse-zstd; reference = copy_decode restated on libzstd (oracle/_ref/fzfs_ref)"}
+                         "note": "reference = copy_decode restated on libzstd behind the same host (oracle/_ref/fzfs_ref), one serving thread as fuse-zstd / fuser; "
+                                 "gpu = 8 serving threads (READs of cached files run side by side), gpu_1_serving_thread = the same host with one"}
             else:
                 log("mount leg failed: " + r.stderr.decode()[-400:])
         except Exception as e:      # no /dev/fuse, no mount permission, timeout: the leg is reported as absent, the bench line stands

@@ -13,10 +13,10 @@ OK, E_MAGIC, E_TRUNCATED, E_UNSUPPORTED, E_CORRUPT, E_DSTSIZE, E_CHECKSUM, E_FCS
 SRC_DEVICE, DST_DEVICE, NO_VERIFY_CHECKSUM, PROFILE, SEEK_TABLE = 1, 2, 4, 8, 16
 
 EXPORTS = ["fzg_init", "fzg_shutdown", "fzg_device_count", "fzg_decode_fd", "fzg_encode_fd", "fzg_decode_batch",
-           "fzg_encode_batch", "fzg_encode_bound", "fzg_frame_info", "fzg_strerror", "fzg_last_timing", "fzg_streamed_copies",
+           "fzg_encode_batch", "fzg_encode_bound", "fzg_frame_info", "fzg_strerror", "fzg_last_timing", "fzg_streamed_copies", "fzg_reserve_staging",
            "fzg_stage_name", "fzg_stream", "fzg_decode_range", "fzg_decode_range_fd", "fzg_seek_footer",
            "fzg_cache_configure", "fzg_cache_reserve", "fzg_cache_prefetch", "fzg_cache_prefetch_async", "fzg_cache_open", "fzg_cache_invalidate",
-           "fzg_cache_stats", "fzg_cache_drain", "fzg_cache_view", "fzg_cache_unview"]
+           "fzg_cache_stats", "fzg_cache_drain", "fzg_cache_view", "fzg_cache_unview", "fzg_cache_wait", "fzg_cache_pending"]
 
 
 class Timing(C.Structure):

@@ -174,27 +174,38 @@ static int run_batch(bool encode, int device, size_t n, const void* const* src, 
 
     // ---- device layout of the sources
     const uint8_t* h2d_base = nullptr;            // pinned host region mirrored at d_stage_src
+    bool src_scatter = false;                     // or: every item in pinned memory of its own
     if (!src_dev) {
         // a caller's pinned buffer whose items lie in increasing order is copied as it is (gaps included)
         bool span_ok = src_len[0] && is_pinned(src[0]) && is_pinned((const uint8_t*)src[n - 1] + (src_len[n - 1] ? src_len[n - 1] - 1 : 0));
         size_t sum = 0;
         for (size_t i = 0; i < n && span_ok; i++) {
             sum += src_len[i];
-            if (i + 1 < n && (const uint8_t*)src[i] + src_len[i] > (const uint8_t*)src[i + 1]) span_ok = false;
+            if (i + 1 < n) {                                  // increasing, and close together: a large gap is where another allocation may begin
+                const uint8_t* end = (const uint8_t*)src[i] + src_len[i];
+                if (end > (const uint8_t*)src[i + 1] || (size_t)((const uint8_t*)src[i + 1] - end) > ((size_t)256 << 10)) span_ok = false;
+            }
         }
         const size_t span = span_ok ? (size_t)((const uint8_t*)src[n - 1] + src_len[n - 1] - (const uint8_t*)src[0]) : 0;
         if (span_ok && span <= 2 * sum + (64u << 10) * n) {
             if ((rc = c->d_stage_src.reserve(span + 64))) return rc;
             h2d_base = (const uint8_t*)src[0];
             for (size_t i = 0; i < n; i++) items[i].src = (uint8_t*)c->d_stage_src.p + ((const uint8_t*)src[i] - h2d_base);
-        } else {                                  // pack into pinned staging
+        } else {
             size_t total = 0;
             for (size_t i = 0; i < n; i++) total += al16(src_len[i]) + 16;
             if ((rc = c->d_stage_src.reserve(total + 64))) return rc;
-            if ((rc = c->h_stage_src.reserve(total + 64))) return rc;
-            uint8_t* hbase = (uint8_t*)c->h_stage_src.p; size_t off = 0;
+            // pinned buffers that do not form one span (the cache's batches come from several arenas): a copy per item, no packing
+            src_scatter = is_pinned(src[0]);
+            for (size_t i = 1; i < n && src_scatter; i++) src_scatter = is_pinned(src[i]);
+            uint8_t* hbase = nullptr;
+            if (!src_scatter) {                   // pageable: pack into pinned staging
+                if ((rc = c->h_stage_src.reserve(total + 64))) return rc;
+                hbase = (uint8_t*)c->h_stage_src.p;
+            }
+            size_t off = 0;
             for (size_t i = 0; i < n; i++) {
-                if (src_len[i]) memcpy(hbase + off, src[i], src_len[i]);
+                if (hbase && src_len[i]) memcpy(hbase + off, src[i], src_len[i]);
                 items[i].src = (uint8_t*)c->d_stage_src.p + off; off += al16(src_len[i]) + 16;
             }
             h2d_base = hbase;
@@ -277,9 +288,23 @@ static int run_batch(bool encode, int device, size_t n, const void* const* src, 
         auto h2d = [&](size_t k) -> int {         // chunk k: host -> device on the copy-in stream
             if (src_dev) return 0;
             const size_t lo = cuts[k], hi = cuts[k + 1];
+            if (src_scatter) {
+                for (size_t i = lo; i < hi; i++) if (src_len[i]) CKR(cudaMemcpyAsync((void*)items[i].src, src[i], src_len[i], cudaMemcpyHostToDevice, s_in));
+                CKR(cudaEventRecord(c->ev[12 + (k & 1)], s_in));
+                return 0;
+            }
             const uint8_t* d_lo = items[lo].src; const uint8_t* d_hi = items[hi - 1].src + src_len[hi - 1];
             const size_t off = (size_t)(d_lo - (const uint8_t*)c->d_stage_src.p);
-            if (d_hi > d_lo) CKR(cudaMemcpyAsync((void*)d_lo, h2d_base + off, (size_t)(d_hi - d_lo), cudaMemcpyHostToDevice, s_in));
+            if (d_hi > d_lo) {
+                cudaError_t e = cudaMemcpyAsync((void*)d_lo, h2d_base + off, (size_t)(d_hi - d_lo), cudaMemcpyHostToDevice, s_in);
+                if (e == cudaErrorInvalidValue && h2d_base == (const uint8_t*)src[0]) {
+                    // the caller's items looked like one pinned span but are not one allocation: a copy per item (same device layout)
+                    cudaGetLastError();
+                    e = cudaSuccess;
+                    for (size_t i = lo; i < hi && e == cudaSuccess; i++) if (src_len[i]) e = cudaMemcpyAsync((void*)items[i].src, src[i], src_len[i], cudaMemcpyHostToDevice, s_in);
+                }
+                CKR(e);
+            }
             CKR(cudaEventRecord(c->ev[12 + (k & 1)], s_in));
             return 0;
         };
@@ -322,6 +347,22 @@ static int run_batch(bool encode, int device, size_t n, const void* const* src, 
     }
     c->timing = acc;
     c->timing.bytes_in = bytes_in; c->timing.bytes_out = bytes_out;
+    return 0;
+}
+
+// Grows the staging of `device` for host-resident batches now (HBM for the compressed and the plain bytes, pinned control blocks for
+// `items` files).  Allocating and freeing while batches are in flight stalls them: a daemon calls this once, before it mounts.
+extern "C" int fzg_reserve_staging(int device, size_t items, size_t src_bytes, size_t dst_bytes)
+{
+    int rc = ensure_init(); if (rc) return rc;
+    FzCtx* c = ctx_for(device);
+    if (!c) return -ENODEV;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CKR(cudaSetDevice(c->dev));
+    if ((rc = c->h_items.reserve(items * sizeof(Item)))) return rc;
+    if ((rc = c->h_outs.reserve(items * sizeof(ItemOut)))) return rc;
+    if ((rc = c->d_stage_src.reserve(src_bytes + 64))) return rc;
+    if ((rc = c->d_stage_dst.reserve(dst_bytes + 64))) return rc;
     return 0;
 }
 

@@ -22,6 +22,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <condition_variable>
 #include <list>
 #include <memory>
@@ -60,8 +61,77 @@ int g_cur = -1;                                    // slab being filled
 size_t g_capacity = (size_t)1 << 30, g_bytes = 0;
 uint64_t g_hits = 0, g_misses = 0, g_prefetched = 0, g_next_id = 1;
 
-std::mutex g_batch_mu;                             // one prefetch batch at a time (they share the compressed-input arena)
-uint8_t* g_arena = nullptr; size_t g_arena_cap = 0;   // pinned, grow-only: the compressed files of the batch being formed
+// The compressed files of a batch being formed live in a pinned arena of its own (grow-only, pooled: pinned memory is slow to
+// allocate), so the file reads of one batch overlap the decode of another.
+struct Arena { uint8_t* p = nullptr; size_t cap = 0; bool busy = false; };
+constexpr int kArenas = 8;
+constexpr size_t kArenaBytes = (size_t)48 << 20;      // reserved per arena at mount time (a window of 64 x 1 MiB files at ratio 2 needs 32 MiB)
+std::mutex g_arena_mu;
+std::condition_variable g_arena_cv;
+Arena g_arenas[kArenas];
+Arena* arena_acquire(size_t need)
+{
+    std::unique_lock<std::mutex> lk(g_arena_mu);
+    Arena* a = nullptr;
+    g_arena_cv.wait(lk, [&] {
+        for (Arena& x : g_arenas) if (!x.busy && x.cap >= need) { a = &x; return true; }      // one that is large enough already
+        for (Arena& x : g_arenas) if (!x.busy) { a = &x; return true; }
+        return false;
+    });
+    a->busy = true;
+    lk.unlock();
+    if (a->cap < need) {
+        if (a->p) cudaFreeHost(a->p);
+        a->p = nullptr; a->cap = 0;
+        const size_t want = need + need / 4 + (1 << 20);
+        if (cudaMallocHost((void**)&a->p, want) != cudaSuccess) { cudaGetLastError(); a->p = nullptr; lk.lock(); a->busy = false; lk.unlock(); g_arena_cv.notify_one(); return nullptr; }
+        a->cap = want;
+    }
+    return a;
+}
+void arena_release(Arena* a)
+{
+    { std::lock_guard<std::mutex> lk(g_arena_mu); a->busy = false; }
+    g_arena_cv.notify_one();
+}
+
+// Group commit of the decode calls.  One 1 MiB frame takes ~2.5 ms on the GPU whether it travels with 30 others or with 500, and
+// the windows of sixteen directories are topped up at about the same time: every batch queues its files here, and whoever
+// gets the decode lock next takes EVERYTHING that is queued -- its own batch and the ones that arrived while the previous call
+// ran -- to the device as one fzg_decode_batch call.  The batch size follows the load.
+struct DecodeJob {
+    int device;
+    std::vector<const void*> sp; std::vector<void*> dp; std::vector<size_t> sl, dc, dl; std::vector<int> st;
+    int rc = 0; bool done = false;
+};
+std::mutex g_decode_mu, g_queue_mu;
+std::vector<DecodeJob*> g_queue;
+void decode_commit(DecodeJob* mine)
+{
+    { std::lock_guard<std::mutex> q(g_queue_mu); g_queue.push_back(mine); }
+    std::lock_guard<std::mutex> leader(g_decode_mu);
+    if (mine->done) return;                                        // a leader before this one took it along
+    std::vector<DecodeJob*> jobs;
+    { std::lock_guard<std::mutex> q(g_queue_mu); jobs.swap(g_queue); }
+    for (size_t a = 0; a < jobs.size();) {                          // one call per device among the queued jobs
+        const int device = jobs[a]->device;
+        std::vector<DecodeJob*> grp;
+        for (size_t b = a; b < jobs.size(); b++) if (jobs[b] && jobs[b]->device == device) { grp.push_back(jobs[b]); jobs[b] = nullptr; }
+        if (grp.size() == 1) {
+            DecodeJob* j = grp[0];
+            j->rc = fzg_decode_batch(device, j->sp.size(), j->sp.data(), j->sl.data(), j->dp.data(), j->dc.data(), j->dl.data(), j->st.data(), 0);
+        } else {
+            std::vector<const void*> sp; std::vector<void*> dp; std::vector<size_t> sl, dc;
+            for (DecodeJob* j : grp) { sp.insert(sp.end(), j->sp.begin(), j->sp.end()); dp.insert(dp.end(), j->dp.begin(), j->dp.end()); sl.insert(sl.end(), j->sl.begin(), j->sl.end()); dc.insert(dc.end(), j->dc.begin(), j->dc.end()); }
+            std::vector<size_t> dl(sp.size()); std::vector<int> st(sp.size());
+            const int rc = fzg_decode_batch(device, sp.size(), sp.data(), sl.data(), dp.data(), dc.data(), dl.data(), st.data(), 0);
+            size_t o = 0;
+            for (DecodeJob* j : grp) { j->rc = rc; for (size_t i = 0; i < j->sp.size(); i++) { j->dl[i] = dl[o + i]; j->st[i] = st[o + i]; } o += j->sp.size(); }
+        }
+        for (DecodeJob* j : grp) j->done = true;
+        while (a < jobs.size() && !jobs[a]) a++;
+    }
+}
 
 void evict_slab_locked(int si)
 {
@@ -116,9 +186,9 @@ int write_all(int fd, const uint8_t* p, size_t n)
 
 extern "C" int fzg_cache_configure(size_t capacity_bytes)
 {
-    std::lock_guard<std::mutex> batch(g_batch_mu);
     std::lock_guard<std::mutex> lk(g_mu);
     if (capacity_bytes != g_capacity) {
+        if (!g_pending.empty()) return -EBUSY;                        // a batch in flight is about to write into a slab
         for (const Slab& sl : g_slabs) if (sl.pins) return -EBUSY;  // a view still points into a slab
         drop_all_locked();                                        // the slabs are sized for a capacity: a new one starts empty
     }
@@ -130,7 +200,6 @@ extern "C" int fzg_cache_configure(size_t capacity_bytes)
 // it once at start instead of inside its first batches).  Returns the number of slabs, or -errno.
 extern "C" int fzg_cache_reserve(void)
 {
-    std::lock_guard<std::mutex> batch(g_batch_mu);
     std::lock_guard<std::mutex> lk(g_mu);
     size_t total = 0;
     for (const Slab& sl : g_slabs) total += sl.cap;
@@ -140,22 +209,45 @@ extern "C" int fzg_cache_reserve(void)
         sl.cap = kSlabBytes; total += kSlabBytes; g_slabs.push_back(std::move(sl));
     }
     if (g_cur < 0 && !g_slabs.empty()) g_cur = 0;
+    // the arenas of the batches and the HBM staging of their decode calls (up to kArenas batches travel together): allocated now,
+    // because pinning memory or growing HBM buffers later stalls the batches that are in flight (measured: 0.7 s once, early in a run)
+    if (g_capacity) {
+        std::lock_guard<std::mutex> al(g_arena_mu);
+        for (Arena& a : g_arenas) if (!a.busy && a.cap < kArenaBytes) {
+            if (a.p) cudaFreeHost(a.p);
+            a.p = nullptr; a.cap = 0;
+            if (cudaMallocHost((void**)&a.p, kArenaBytes) != cudaSuccess) { cudaGetLastError(); a.p = nullptr; return -ENOMEM; }
+            a.cap = kArenaBytes;
+        }
+        const size_t per_call = std::min<size_t>(g_capacity, kArenas * kSlabBytes / 4);
+        for (int d = 0; d < fzg_device_count(); d++) if (int rc = fzg_reserve_staging(d, 4096, kArenas * kArenaBytes, per_call + (4096u << 5))) return rc;
+    }
     return (int)g_slabs.size();
 }
 
 // Decodes the listed .zst files that are not cached yet as ONE batch on `device` and keeps the results.  Files that
 // cannot be read or do not decode are skipped (open() will report them the ordinary way).  Returns the number of files
 // added, or -errno.
+// which of the listed files are neither cached nor on their way: they become pending (an open of one of them waits for its batch)
+static std::vector<size_t> prefetch_select(const uint64_t* keys, size_t n)
+{
+    std::vector<size_t> todo;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_capacity == 0) return todo;
+    for (size_t i = 0; i < n; i++) if (!g_map.count(keys[i]) && g_pending.insert(keys[i]).second) todo.push_back(i);
+    return todo;
+}
+static int prefetch_run(int device, const char* const* paths, const uint64_t* keys, const std::vector<size_t>& todo);
+
 extern "C" int fzg_cache_prefetch(int device, const char* const* paths, const uint64_t* keys, size_t n)
 {
     if (!paths || !keys) return -EINVAL;
-    std::lock_guard<std::mutex> batch(g_batch_mu);
-    std::vector<size_t> todo;
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        if (g_capacity == 0) return 0;
-        for (size_t i = 0; i < n; i++) if (!g_map.count(keys[i]) && g_pending.insert(keys[i]).second) todo.push_back(i);
-    }
+    const std::vector<size_t> todo = prefetch_select(keys, n);
+    return prefetch_run(device, paths, keys, todo);
+}
+
+static int prefetch_run(int device, const char* const* paths, const uint64_t* keys, const std::vector<size_t>& todo)
+{
     if (todo.empty()) return 0;
     struct Done {                                      // whatever happens, the keys stop being pending and waiters wake up
         const std::vector<size_t>& todo; const uint64_t* keys;
@@ -173,19 +265,16 @@ extern "C" int fzg_cache_prefetch(int device, const char* const* paths, const ui
         if (fds[j] < 0 || fstat(fds[j], &sts[j]) != 0 || sts[j].st_size == 0) { if (fds[j] >= 0) close(fds[j]); fds[j] = -1; continue; }
         coff[j] = ctotal; clen[j] = (size_t)sts[j].st_size; ctotal += (clen[j] + 15 & ~(size_t)15) + 16;
     }
-    if (ctotal + 64 > g_arena_cap) {
-        if (g_arena) cudaFreeHost(g_arena);
-        g_arena = nullptr; g_arena_cap = 0;
-        const size_t want = ctotal + ctotal / 4 + (1 << 20);
-        if (cudaMallocHost((void**)&g_arena, want) != cudaSuccess) { cudaGetLastError(); g_arena = nullptr; for (int fd : fds) if (fd >= 0) close(fd); return -ENOMEM; }
-        g_arena_cap = want;
-    }
+    Arena* const arena = arena_acquire(ctotal + 64);
+    if (!arena) { for (int fd : fds) if (fd >= 0) close(fd); return -ENOMEM; }
+    struct ArenaGuard { Arena* a; ~ArenaGuard() { arena_release(a); } } arena_guard{ arena };
+    uint8_t* const abuf = arena->p;
     // the reads are page-cache copies (~6 GB/s on one thread: 14 ms for a directory of 256 x 1 MiB): a few threads share them
     auto read_range = [&](size_t lo, size_t hi) {
         for (size_t j = lo; j < hi; j++) {
             if (fds[j] < 0) continue;
             size_t got = 0;
-            while (got < clen[j]) { const ssize_t r = read(fds[j], g_arena + coff[j] + got, clen[j] - got); if (r < 0 && errno == EINTR) continue; if (r <= 0) break; got += (size_t)r; }
+            while (got < clen[j]) { const ssize_t r = read(fds[j], abuf + coff[j] + got, clen[j] - got); if (r < 0 && errno == EINTR) continue; if (r <= 0) break; got += (size_t)r; }
             close(fds[j]);
             if (got != clen[j]) fds[j] = -1;
         }
@@ -211,7 +300,7 @@ extern "C" int fzg_cache_prefetch(int device, const char* const* paths, const ui
     for (size_t j = 0; j < m; j++) {
         if (fds[j] < 0) continue;
         uint64_t content = 0, csize = 0;
-        if (fzg_frame_info(g_arena + coff[j], clen[j], &content, &csize) != 0 || content == UINT64_MAX) continue;   // unknown size: left to open()
+        if (fzg_frame_info(abuf + coff[j], clen[j], &content, &csize) != 0 || content == UINT64_MAX) continue;   // unknown size: left to open()
         if (content > limit) continue;                     // larger than a slab (or a lying header): left to open(), the others go on
         if (content > budget) break;                       // the cache is full of this very call's files
         budget -= (size_t)content;
@@ -224,14 +313,18 @@ extern "C" int fzg_cache_prefetch(int device, const char* const* paths, const ui
         while (g1 < which.size() && dcs[g1] <= limit - dtotal) { doff.push_back(dtotal); dtotal += dcs[g1]; g1++; }
         const size_t k = g1 - g0;                          // >= 1: every file fits a slab by itself
         int si; size_t base = 0; uint8_t* slab_p;
-        { std::lock_guard<std::mutex> lk(g_mu); si = alloc_locked(dtotal ? dtotal : 1, &base); if (si < 0) return added ? added : -ENOMEM; slab_p = g_slabs[si].p; }
-        std::vector<const void*> sp(k); std::vector<void*> dp(k); std::vector<size_t> sl(k), dc(k), dl(k); std::vector<int> st(k);
-        for (size_t a = 0; a < k; a++) { const size_t j = which[g0 + a]; sp[a] = g_arena + coff[j]; sl[a] = clen[j]; dp[a] = slab_p + base + doff[a]; dc[a] = dcs[g0 + a]; }
+        // (the slab stays pinned while the batch is in flight: another batch must not reuse it before this one has landed)
+        { std::lock_guard<std::mutex> lk(g_mu); si = alloc_locked(dtotal ? dtotal : 1, &base); if (si < 0) return added ? added : -ENOMEM; slab_p = g_slabs[si].p; g_slabs[si].pins++; }
+        DecodeJob job; job.device = device;
+        job.sp.resize(k); job.dp.resize(k); job.sl.resize(k); job.dc.resize(k); job.dl.assign(k, 0); job.st.assign(k, 0);
+        for (size_t a = 0; a < k; a++) { const size_t j = which[g0 + a]; job.sp[a] = abuf + coff[j]; job.sl[a] = clen[j]; job.dp[a] = slab_p + base + doff[a]; job.dc[a] = dcs[g0 + a]; }
         const double t_read = ms();
-        const int rc = fzg_decode_batch(device, k, sp.data(), sl.data(), dp.data(), dc.data(), dl.data(), st.data(), 0);
-        if (rc) return added ? added : rc;
-        if (trace) fprintf(stderr, "fzgpu: prefetch of %zu files (%zu bytes): up to here %.1f ms, decode batch %.1f ms\n", k, dtotal, t_read, ms() - t_read);
+        decode_commit(&job);
+        const std::vector<size_t>& dl = job.dl; const std::vector<int>& st = job.st;
+        if (trace) fprintf(stderr, "fzgpu: prefetch of %zu files (%zu bytes): up to here %.1f ms, decode (own batch or a combined one) %.1f ms\n", k, dtotal, t_read, ms() - t_read);
         std::unique_lock<std::mutex> lk(g_mu);
+        if (si < (int)g_slabs.size() && g_slabs[si].pins > 0) g_slabs[si].pins--;
+        if (job.rc) return added ? added : job.rc;
         for (size_t a = 0; a < k; a++) {
             if (st[a] != 0) continue;
             const size_t j = which[g0 + a]; const uint64_t key = keys[todo[j]];
@@ -262,16 +355,29 @@ extern "C" void fzg_cache_drain(void)
 extern "C" int fzg_cache_prefetch_async(int device, const char* const* paths, const uint64_t* keys, size_t n)
 {
     if (!paths || !keys) return -EINVAL;
+    // the files become pending HERE, before this returns: the caller can ask fzg_cache_pending / fzg_cache_wait about them at once
+    std::vector<size_t> todo = prefetch_select(keys, n);
+    if (todo.empty()) return 0;
     std::vector<std::string> p(n); std::vector<uint64_t> k(keys, keys + n);
-    for (size_t i = 0; i < n; i++) p[i] = paths[i];
+    for (size_t i : todo) p[i] = paths[i];
     { std::lock_guard<std::mutex> lk(g_async_mu); g_async_live++; }
-    std::thread([device, p = std::move(p), k = std::move(k)]() {
+    const std::vector<size_t> undo = todo;
+    try {
+    std::thread([device, p = std::move(p), k = std::move(k), todo = std::move(todo)]() {
         std::vector<const char*> c(p.size());
         for (size_t i = 0; i < p.size(); i++) c[i] = p[i].c_str();
-        try { fzg_cache_prefetch(device, c.data(), k.data(), c.size()); } catch (...) { }
+        try { prefetch_run(device, c.data(), k.data(), todo); }
+        catch (...) { { std::lock_guard<std::mutex> lk(g_mu); for (size_t i : todo) g_pending.erase(k[i]); } g_cv.notify_all(); }
         { std::lock_guard<std::mutex> lk(g_async_mu); g_async_live--; }
         g_async_cv.notify_all();
     }).detach();
+    } catch (...) {                                                  // no thread to be had: nobody must wait for these files
+        { std::lock_guard<std::mutex> lk(g_mu); for (size_t i : undo) g_pending.erase(keys[i]); }
+        g_cv.notify_all();
+        { std::lock_guard<std::mutex> lk(g_async_mu); g_async_live--; }
+        g_async_cv.notify_all();
+        return -EAGAIN;
+    }
     return 0;
 }
 
@@ -322,6 +428,17 @@ extern "C" int fzg_cache_view(int src_fd, uint64_t key, const void** data, uint6
     sl.pins++; g_hits++;
     *data = sl.p + it->second.off; *size = it->second.n; *token = (void*)(uintptr_t)(it->second.slab + 1);
     return 0;
+}
+// Blocks while `key` belongs to a prefetch batch in flight (a caller that serialises its opens waits here, outside its own lock).
+extern "C" int fzg_cache_pending(uint64_t key)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g_pending.count(key) ? 1 : 0;
+}
+extern "C" void fzg_cache_wait(uint64_t key)
+{
+    std::unique_lock<std::mutex> lk(g_mu);
+    g_cv.wait(lk, [&] { return !g_pending.count(key); });
 }
 extern "C" void fzg_cache_unview(void* token)
 {

@@ -3,7 +3,8 @@
  * GPU codec can be exercised and measured THROUGH A MOUNT in an environment without Rust, libfuse or fio.
  *
  * What it restates (paths relative to /root/reference):
- *   the Filesystem callbacks            src/main.rs:835-1207    -> Fs::dispatch (one thread, one request at a time, as fuser does)
+ *   the Filesystem callbacks            src/main.rs:835-1207    -> Fs::dispatch (--threads 1: one request at a time, as fuser does;
+ *                                                               more: READs of different requests run side by side, see Fs::loop)
  *   lookup / readdir / getattr          src/main.rs:215-405     `.zst` suffix added / stripped, other regular files hidden,
  *                                                               size = xattr user.real_size (8-byte BE), perms 0666 / 0777
  *   open (decode on first open)         src/main.rs:451-493     unlinked tmpfile, codec call, user.real_size written, fsync;
@@ -27,6 +28,7 @@
 #include <errno.h>
 #include <fcntl.h>
 #include <linux/fuse.h>
+#include <sched.h>
 #include <signal.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -39,8 +41,15 @@
 #include <sys/xattr.h>
 #include <unistd.h>
 
+#include <time.h>
+
 #include <algorithm>
+#include <atomic>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -51,6 +60,13 @@ namespace {
 
 constexpr uint64_t kTtlSec = 1;                 // dcache lifetime (src/main.rs:25)
 bool g_verbose = false;
+// --stats: per opcode, how many requests, the time they took in the host and (of that) the time spent waiting for the host's lock
+// or for a readahead batch; printed when the mount goes away
+bool g_stats = false;
+struct OpStat { std::atomic<uint64_t> n{ 0 }, ns{ 0 }, wait_ns{ 0 }, max_ns{ 0 }; };
+OpStat g_op[64];
+thread_local uint64_t t_wait_ns = 0;
+inline uint64_t now_ns() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (uint64_t)t.tv_sec * 1000000000ull + (uint64_t)t.tv_nsec; }
 void logf(const char* fmt, ...)
 {
     if (!g_verbose) return;
@@ -102,6 +118,9 @@ bool content_size_from_headers(int fd, uint64_t* out)
 
 struct Handle {
     int flags; bool needs_sync; int fd; bool has_refs; uint64_t ino; std::string path;
+    // READs in flight on this handle: they copy out of the backing WITHOUT the host's lock, so whoever replaces or closes the backing
+    // waits for this to reach zero first (holding the lock exclusively, which keeps new READs from starting)
+    std::shared_ptr<std::atomic<int>> busy = std::make_shared<std::atomic<int>>(0);
     // a read-only open served from the decoded-file cache IN PLACE (fd == -1): no tmpfile until somebody writes, truncates or fsyncs
     const uint8_t* view = nullptr; uint64_t view_size = 0; void* pin = nullptr;
 };
@@ -114,7 +133,8 @@ public:
         if (getxattr(data_.c_str(), "user.ino_idx", b, 8) == 8) ino_idx_ = be64(b);
     }
     int dev = -1;
-    void loop();
+    int n_threads = 1;
+    void loop(int threads);
 
 private:
     std::string data_; int level_; bool readahead_;
@@ -128,7 +148,12 @@ private:
     // readahead window per directory: the .zst entries in natural order, which of them were handed to the codec
     struct DirRa { std::vector<std::string> names; std::vector<uint8_t> asked; std::unordered_map<std::string, size_t> index; int64_t mtime_ns = -1; };
     std::unordered_map<std::string, DirRa> ra_;
-    std::vector<uint8_t> rbuf_;                                  // FUSE_READ reply buffer
+    // Several threads may serve requests (Fs::loop).  Everything that changes the tables above, touches the data directory or calls
+    // the codec takes mu_ exclusively -- the reference's one-request-at-a-time semantics, unchanged; a READ only looks a handle up and
+    // copies bytes out of its tmpfile or its in-place view, so READs take mu_ shared and run side by side.
+    std::shared_mutex mu_;
+    std::atomic<int> parked_{ 0 };                               // OPEN requests waiting for their readahead batch on threads of their own
+    void serve();
 
     // ---- inode numbers (src/main.rs:719-753)
     uint64_t next_ino()
@@ -206,11 +231,13 @@ private:
     uint64_t insert_handle(uint64_t ino, int flags, int fd, const std::string& path)
     {
         const uint64_t fh = new_fh();
-        handles_[fh] = Handle{ flags, false, fd, true, ino, path };
+        Handle nh; nh.flags = flags; nh.needs_sync = false; nh.fd = fd; nh.has_refs = true; nh.ino = ino; nh.path = path;
+        handles_[fh] = nh;
         by_ino_[ino].insert(fh);
         return fh;
     }
-    void drop_handle_backing(Handle& h) { if (h.view) { fzfs_unview(h.pin); h.view = nullptr; h.pin = nullptr; } else if (h.fd >= 0) close(h.fd); h.fd = -1; }
+    static void quiesce(const Handle& h) { while (h.busy->load(std::memory_order_acquire) > 0) sched_yield(); }
+    void drop_handle_backing(Handle& h) { quiesce(h); if (h.view) { fzfs_unview(h.pin); h.view = nullptr; h.pin = nullptr; } else if (h.fd >= 0) close(h.fd); h.fd = -1; }
     // every in-place handle of `ino` gets the ordinary backing after all: ONE tmpfile holding the plain bytes, dup'ed per handle
     int materialize(uint64_t ino)
     {
@@ -230,6 +257,7 @@ private:
                 fd = tmp;
             } else fd = dup(tmp);
             if (fd < 0) return errno;
+            quiesce(h);
             fzfs_unview(h.pin); h.view = nullptr; h.pin = nullptr; h.fd = fd;
         }
         return 0;
@@ -249,11 +277,14 @@ private:
     void readahead_dir(const std::string& dir, const std::string& path);     // path empty: the directory was listed, its first window
 
     // ---- protocol
-    void reply(uint64_t unique, int err, const void* p = nullptr, size_t n = 0)
+    void reply(uint64_t unique, int err, const void* p = nullptr, size_t n = 0) { (void)send(unique, err, p, n); }
+    bool send(uint64_t unique, int err, const void* p = nullptr, size_t n = 0)      // false: the kernel no longer wants the answer (interrupted)
     {
         struct fuse_out_header oh; oh.len = (uint32_t)(sizeof oh + (err ? 0 : n)); oh.error = -err; oh.unique = unique;
         struct iovec iov[2] = { { &oh, sizeof oh }, { const_cast<void*>(p), err ? 0 : n } };
-        if (writev(dev, iov, err || n == 0 ? 1 : 2) < 0 && errno != ENOENT) logf("fzfs: reply failed: %s", strerror(errno));
+        if (writev(dev, iov, err || n == 0 ? 1 : 2) >= 0) return true;
+        if (errno != ENOENT) logf("fzfs: reply failed: %s", strerror(errno));
+        return false;
     }
     void entry_out(struct fuse_entry_out& e, const struct fuse_attr& a) { memset(&e, 0, sizeof e); e.nodeid = a.ino; e.entry_valid = kTtlSec; e.attr_valid = kTtlSec; e.attr = a; }
     int lookup(uint64_t parent, const char* name, struct fuse_attr& a);
@@ -333,6 +364,7 @@ int Fs::sync_to_fs(uint64_t fh, bool close_it, bool force)
             if (tmp < 0) return errno;
             unlink(tmpl);
             for (uint64_t o = 0; o < h.view_size;) { const ssize_t w = pwrite(tmp, h.view + o, h.view_size - o, (off_t)o); if (w < 0) { if (errno == EINTR) continue; break; } o += (uint64_t)w; }
+            quiesce(h);
             fzfs_unview(h.pin); h.view = nullptr; h.pin = nullptr; h.fd = tmp;
         }
     }
@@ -375,6 +407,7 @@ static bool natural_less(const std::string& a, const std::string& b)
 // and a directory decoded at once was evicted by the other jobs' directories before its reader arrived (measured: 365 MB/s
 // against 610 for the CPU path; see profiles/r02_notes.md).
 constexpr size_t kRaWindow = 64;
+constexpr int kWaitForBatch = -1;               // do_open: try again once fzfs_wait(ino) has returned
 void Fs::readahead_dir(const std::string& dir, const std::string& path)
 {
     if (!readahead_) return;
@@ -443,6 +476,7 @@ int Fs::do_open(uint64_t ino, int flags, uint64_t* fh_out)
     std::string path;
     if (int e = path_of(ino, path)) return e;
     readahead_dir(dir_of(path), path);
+    if (readahead_ && fzfs_pending(ino)) return kWaitForBatch;      // its batch is on the way (maybe asked for just now): the caller waits WITHOUT the lock
     const int src = open(path.c_str(), O_RDONLY | O_CLOEXEC);
     if (src < 0) return errno;
     if (readahead_ && (flags & O_ACCMODE) == O_RDONLY) {            // a reader of a file the readahead has decoded: its bytes in place, no tmpfile
@@ -487,6 +521,32 @@ int Fs::do_open(uint64_t ino, int flags, uint64_t* fh_out)
 void Fs::dispatch(const struct fuse_in_header* in, const uint8_t* arg, size_t arglen)
 {
     const uint64_t u = in->unique, node = in->nodeid;
+    const uint64_t w0 = g_stats ? now_ns() : 0;
+    if (in->opcode == FUSE_READ) {
+        // the lock only for the lookup; the copy (128 KiB into the kernel: most of a READ's time) runs beside everything else
+        const struct fuse_read_in* r = (const struct fuse_read_in*)arg;
+        std::shared_ptr<std::atomic<int>> busy; const uint8_t* view = nullptr; uint64_t vs = 0; int fd = -1;
+        {
+            std::shared_lock<std::shared_mutex> lk(mu_);
+            if (g_stats) t_wait_ns = now_ns() - w0;
+            auto h = handles_.find(r->fh);
+            if (h == handles_.end()) { lk.unlock(); return reply(u, ENOENT); }
+            busy = h->second.busy; busy->fetch_add(1, std::memory_order_acquire);
+            view = h->second.view; vs = h->second.view_size; fd = h->second.fd;
+        }
+        struct Idle { std::atomic<int>& b; ~Idle() { b.fetch_sub(1, std::memory_order_release); } } idle{ *busy };
+        if (view) {                                                  // served in place: straight from the cache's pinned memory
+            const uint64_t off = r->offset < vs ? r->offset : vs;
+            return reply(u, 0, view + off, (size_t)std::min<uint64_t>(r->size, vs - off));
+        }
+        static thread_local std::vector<uint8_t> rbuf;             // one reply buffer per serving thread: the reference's
+        if (rbuf.size() < r->size) rbuf.resize(r->size);           // vec![0; size] per request (src/main.rs:503) zeroes 128 KiB each time
+        const ssize_t n = pread(fd, rbuf.data(), r->size, (off_t)r->offset);
+        if (n < 0) return reply(u, errno);
+        return reply(u, 0, rbuf.data(), (size_t)n);
+    }
+    std::unique_lock<std::shared_mutex> lk(mu_);
+    if (g_stats) t_wait_ns = now_ns() - w0;
     switch (in->opcode) {
     case FUSE_LOOKUP: {
         struct fuse_attr a; struct fuse_entry_out e;
@@ -520,23 +580,32 @@ void Fs::dispatch(const struct fuse_in_header* in, const uint8_t* arg, size_t ar
     case FUSE_OPEN: {
         const struct fuse_open_in* oi = (const struct fuse_open_in*)arg;
         uint64_t fh = 0;
-        const int err = do_open(node, (int)oi->flags, &fh);
+        const int flags = (int)oi->flags;
+        int err = do_open(node, flags, &fh);
+        if (err == kWaitForBatch) {
+            // A reader that has caught up with the readahead finds its file in a batch in flight.  The request is parked on a thread
+            // of its own, which answers it when the batch has landed (a reply may come from any thread, in any order): the serving
+            // threads go on with everybody else's requests meanwhile.
+            lk.unlock();
+            parked_.fetch_add(1);
+            try {
+                std::thread([this, u, node, flags] {
+                    uint64_t fh2 = 0; int e;
+                    do { fzfs_wait(node); std::unique_lock<std::shared_mutex> lk2(mu_); e = do_open(node, flags, &fh2); } while (e == kWaitForBatch);
+                    struct fuse_open_out o2; memset(&o2, 0, sizeof o2); o2.fh = fh2;
+                    if (e) reply(u, e);
+                    else if (!send(u, 0, &o2, sizeof o2)) { std::unique_lock<std::shared_mutex> lk3(mu_); sync_to_fs(fh2, true, false); }   // the opener is gone: no RELEASE will come
+                    parked_.fetch_sub(1);
+                }).detach();
+                return;
+            } catch (...) { parked_.fetch_sub(1); }                 // no thread to be had: wait here after all
+            lk.lock();
+            while ((err = do_open(node, flags, &fh)) == kWaitForBatch) { lk.unlock(); fzfs_wait(node); lk.lock(); }
+        }
         if (err) return reply(u, err);
         struct fuse_open_out o; memset(&o, 0, sizeof o); o.fh = fh;
-        return reply(u, 0, &o, sizeof o);
-    }
-    case FUSE_READ: {
-        const struct fuse_read_in* r = (const struct fuse_read_in*)arg;
-        auto h = handles_.find(r->fh);
-        if (h == handles_.end()) return reply(u, ENOENT);
-        if (h->second.view) {                                       // served in place: straight from the cache's pinned memory
-            const uint64_t vs = h->second.view_size, off = r->offset < vs ? r->offset : vs;
-            return reply(u, 0, h->second.view + off, (size_t)std::min<uint64_t>(r->size, vs - off));
-        }
-        if (rbuf_.size() < r->size) rbuf_.resize(r->size);         // one reply buffer for the (single-threaded) loop: the reference's
-        const ssize_t n = pread(h->second.fd, rbuf_.data(), r->size, (off_t)r->offset);   // vec![0; size] per request (src/main.rs:503) zeroes 128 KiB each time
-        if (n < 0) return reply(u, errno);
-        return reply(u, 0, rbuf_.data(), (size_t)n);
+        if (!send(u, 0, &o, sizeof o)) sync_to_fs(fh, true, false);   // the opener is gone: no RELEASE will come
+        return;
     }
     case FUSE_WRITE: {
         const struct fuse_write_in* w = (const struct fuse_write_in*)arg;
@@ -686,8 +755,9 @@ void Fs::dispatch(const struct fuse_in_header* in, const uint8_t* arg, size_t ar
 }
 
 volatile sig_atomic_t g_stop = 0;
+std::string g_mountpoint;
 
-void Fs::loop()
+void Fs::serve()
 {
     std::vector<uint8_t> buf((1u << 20) + 65536);
     for (;;) {
@@ -704,23 +774,52 @@ void Fs::loop()
             o.max_readahead = ii->max_readahead;
             o.flags = (FUSE_BIG_WRITES | FUSE_MAX_PAGES) & ii->flags;     // no atomic O_TRUNC: truncation arrives as SETATTR, as with fuser
             o.max_background = 16; o.congestion_threshold = 12; o.max_write = 1u << 20; o.max_pages = 256; o.time_gran = 1;
+            if (n_threads > 1) { o.max_background = (uint16_t)std::min(1024, 16 * n_threads); o.congestion_threshold = (uint16_t)(o.max_background * 3 / 4); }   // the kernel's own readahead is background traffic
             reply(in->unique, 0, &o, sizeof o);
-            continue;
+            return;                                                   // the caller starts the serving threads now
         }
-        if (in->opcode == FUSE_DESTROY) { reply(in->unique, 0); break; }
+        if (in->opcode == FUSE_DESTROY) { reply(in->unique, 0); g_stop = 1; break; }
+        if (!g_stats) { dispatch(in, arg, arglen); continue; }
+        const uint32_t op = in->opcode < 64 ? in->opcode : 0;
+        const uint64_t t0 = now_ns();
+        t_wait_ns = 0;
         dispatch(in, arg, arglen);
+        const uint64_t dt = now_ns() - t0;
+        g_op[op].n++; g_op[op].ns += dt; g_op[op].wait_ns += t_wait_ns;
+        uint64_t mx = g_op[op].max_ns.load(); while (dt > mx && !g_op[op].max_ns.compare_exchange_weak(mx, dt)) { }
+    }
+}
+
+// The kernel hands each request to whichever thread is waiting in read() on the device (what libfuse's multi-threaded loop does).
+// The first call to serve() answers FUSE_INIT on this thread and returns; then `threads` of them serve until the unmount.
+void Fs::loop(int threads)
+{
+    n_threads = threads;
+    serve();
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back([this] { serve(); });
+    serve();
+    if (!pool.empty()) umount2(g_mountpoint.c_str(), MNT_DETACH);    // the others are waiting in read(): the unmount sends them home
+    for (auto& t : pool) t.join();
+    while (parked_.load() > 0) usleep(1000);                         // batches always land (or fail): nobody waits for long
+    if (g_stats) {
+        static const char* names[64] = {};
+        names[FUSE_LOOKUP] = "lookup"; names[FUSE_GETATTR] = "getattr"; names[FUSE_SETATTR] = "setattr"; names[FUSE_OPEN] = "open"; names[FUSE_READ] = "read";
+        names[FUSE_WRITE] = "write"; names[FUSE_FLUSH] = "flush"; names[FUSE_RELEASE] = "release"; names[FUSE_FSYNC] = "fsync"; names[FUSE_OPENDIR] = "opendir";
+        names[FUSE_READDIR] = "readdir"; names[FUSE_CREATE] = "create"; names[FUSE_UNLINK] = "unlink"; names[FUSE_RENAME] = "rename"; names[FUSE_MKDIR] = "mkdir";
+        for (int op = 0; op < 64; op++) if (g_op[op].n) fprintf(stderr, "fzfs: stats %-8s n %8llu  in the host %9.1f ms (%.1f us each, max %.1f us), of which waiting %9.1f ms\n", names[op] ? names[op] : "other",
+            (unsigned long long)g_op[op].n.load(), g_op[op].ns / 1e6, g_op[op].ns / 1e3 / g_op[op].n, g_op[op].max_ns / 1e3, g_op[op].wait_ns / 1e6);
     }
     for (auto& kv : handles_) drop_handle_backing(kv.second);
 }
 
-std::string g_mountpoint;
 void on_signal(int) { g_stop = 1; umount2(g_mountpoint.c_str(), MNT_DETACH); }
 
 }  // namespace
 
 int main(int argc, char** argv)
 {
-    std::string data_dir, mountpoint; int level = 0; bool readahead = true; size_t cache_mb = 1024;
+    std::string data_dir, mountpoint; int level = 0; bool readahead = true; size_t cache_mb = 1024; int threads = 0;
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
         auto val = [&](const char* name) -> const char* { if (i + 1 >= argc) { fprintf(stderr, "fzfs: %s needs a value\n", name); exit(2); } return argv[++i]; };
@@ -729,12 +828,16 @@ int main(int argc, char** argv)
         else if (a == "--compression-level") level = atoi(val("--compression-level"));
         else if (a == "--no-readahead") readahead = false;
         else if (a == "--cache-mb") cache_mb = (size_t)atoll(val("--cache-mb"));
+        else if (a == "--threads") threads = atoi(val("--threads"));
         else if (a == "--verbose") g_verbose = true;
-        else { fprintf(stderr, "usage: %s --data-dir DIR --mount-point DIR [--compression-level 0..19] [--no-readahead] [--cache-mb N] [--verbose]\n", argv[0]); return 2; }
+        else if (a == "--stats") g_stats = true;
+        else { fprintf(stderr, "usage: %s --data-dir DIR --mount-point DIR [--compression-level 0..19] [--no-readahead] [--cache-mb N] [--threads N] [--stats] [--verbose]\n", argv[0]); return 2; }
     }
     if (data_dir.empty() || mountpoint.empty()) { fprintf(stderr, "fzfs: --data-dir and --mount-point are required\n"); return 2; }
     if (level < 0 || level > 19) level = 0;                         // src/main.rs:1283-1296
     if (int rc = fzfs_codec_init(readahead ? cache_mb << 20 : 0)) { fprintf(stderr, "fzfs: codec unavailable (%s): %s\n", fzfs_codec_name(), strerror(rc < 0 ? -rc : rc)); return 1; }
+    if (threads <= 0) threads = fzfs_codec_threads();                  // the codec's default: 1 for the reference's (fuser's loop), more for the GPU's
+    if (threads > 64) threads = 64;
     Fs fs(data_dir, level, readahead);
     fs.dev = open("/dev/fuse", O_RDWR | O_CLOEXEC);
     if (fs.dev < 0) { perror("fzfs: /dev/fuse"); return 1; }
@@ -744,8 +847,8 @@ int main(int argc, char** argv)
     g_mountpoint = mountpoint;
     struct sigaction sa; memset(&sa, 0, sizeof sa); sa.sa_handler = on_signal;
     sigaction(SIGINT, &sa, nullptr); sigaction(SIGTERM, &sa, nullptr);
-    fprintf(stderr, "fzfs: %s mounted on %s (codec: %s, level %d, readahead %s)\n", data_dir.c_str(), mountpoint.c_str(), fzfs_codec_name(), level, readahead ? "on" : "off");
-    fs.loop();
+    fprintf(stderr, "fzfs: %s mounted on %s (codec: %s, level %d, readahead %s, %d serving thread%s)\n", data_dir.c_str(), mountpoint.c_str(), fzfs_codec_name(), level, readahead ? "on" : "off", threads, threads == 1 ? "" : "s");
+    fs.loop(threads);
     umount2(mountpoint.c_str(), MNT_DETACH);
     fzfs_codec_shutdown();                             // no readahead thread may still be decoding when the process exits
     return 0;

@@ -122,6 +122,9 @@ void fzg_cache_stats(uint64_t* hits, uint64_t* misses, uint64_t* bytes, uint64_t
 int fzg_cache_view(int src_fd, uint64_t key, const void** data, uint64_t* size, void** token);   /* the cached plain bytes in place (read-only opens:
                                                      no tmpfile copy of src/main.rs:462-466); 0, or -ENOENT when not cached / stale; pinned until ... */
 void fzg_cache_unview(void* token);               /* ... the view is given back */
+int fzg_cache_pending(uint64_t key);              /* 1 while `key` belongs to a prefetch batch in flight (set before fzg_cache_prefetch_async returns) */
+void fzg_cache_wait(uint64_t key);                /* returns once `key` is in no prefetch batch in flight (several batches decode side by side
+                                                     and are taken to the GPU together; an open waits for its file here, outside its own locks) */
 void fzg_cache_drain(void);                       /* waits for the prefetch batches in flight (called by fzg_shutdown; a daemon calls it before exit) */
 
 const char* fzg_strerror(int code);
@@ -139,6 +142,10 @@ const char* fzg_stage_name(int stage);
  * still being executed (chunks of >= FZG_STREAM_OUT_MB MiB of output, default 256, at most half as many frames as SMs).
  * Returns how many such copies this context has queued since fzg_init (a counter for tests and traces). */
 uint64_t fzg_streamed_copies(int device);
+/* Host-resident batches are staged in HBM; the staging grows on demand, and growing it (cudaFree + cudaMalloc) stalls whatever
+ * else the device is doing.  A daemon that knows its batch sizes reserves them once: `items` files, src_bytes compressed,
+ * dst_bytes plain per call.  fzg_cache_reserve does this for the cache's own batches. */
+int fzg_reserve_staging(int device, size_t items, size_t src_bytes, size_t dst_bytes);
 void* fzg_stream(int device); /* cudaStream_t of the context (for external event timing) */
 
 #ifdef __cplusplus

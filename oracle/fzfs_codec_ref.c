@@ -21,6 +21,7 @@ int fzr_writer_encode(const void* src, size_t src_len, void* dst, size_t dst_cap
 
 int fzfs_codec_init(size_t cache_bytes) { (void)cache_bytes; return fzr_available() ? 0 : -ENOSYS; }
 const char* fzfs_codec_name(void) { return "libzstd (reference restatement, one thread)"; }
+int fzfs_codec_threads(void) { return 1; }          /* fuser's session loop: one request at a time */
 
 int fzfs_decode(int src_fd, int dst_fd, uint64_t ino, uint64_t* out_size) { (void)ino; return fzr_copy_decode_fd(src_fd, dst_fd, out_size); }
 
@@ -44,3 +45,5 @@ void fzfs_invalidate(uint64_t ino) { (void)ino; }
 void fzfs_codec_shutdown(void) { }
 int fzfs_view(int src_fd, uint64_t ino, const void** data, uint64_t* size, void** pin) { (void)src_fd; (void)ino; (void)data; (void)size; (void)pin; return -1; }
 void fzfs_unview(void* pin) { (void)pin; }
+void fzfs_wait(uint64_t ino) { (void)ino; }
+int fzfs_pending(uint64_t ino) { (void)ino; return 0; }

@@ -30,7 +30,8 @@ class Mount:
     def __init__(self, host, *extra):
         self.data = tempfile.mkdtemp(prefix="fzdata")
         self.mp = tempfile.mkdtemp(prefix="fzmnt")
-        self.proc = subprocess.Popen([host, "--data-dir", self.data, "--mount-point", self.mp, *extra], stderr=subprocess.PIPE)
+        host, *opts = host.split(" ")                    # "path --threads 4": a host with options (see _hosts)
+        self.proc = subprocess.Popen([host, "--data-dir", self.data, "--mount-point", self.mp, *opts, *extra], stderr=subprocess.PIPE)
         for _ in range(400):
             if os.path.ismount(self.mp) or self.proc.poll() is not None:
                 break
@@ -57,8 +58,11 @@ class Mount:
 
 
 def _hosts():
-    out = [pytest.param(REF_HOST, id="reference-codec")]
+    # the serving threads: the reference's codec defaults to 1 (fuser's loop), the GPU's to 8; both hosts are run both ways so that the
+    # locking of the multi-threaded loop is exercised here on the CPU too
+    out = [pytest.param(REF_HOST, id="reference-codec"), pytest.param(REF_HOST + " --threads 4", id="reference-codec-4-threads")]
     out.append(pytest.param(GPU_HOST, id="gpu-codec", marks=pytest.mark.gpu))
+    out.append(pytest.param(GPU_HOST + " --threads 1", id="gpu-codec-1-thread", marks=pytest.mark.gpu))
     return out
 
 
@@ -284,6 +288,76 @@ def test_readers_served_in_place_then_a_writer_joins(host, ref, corpus, oracle):
         os.truncate(t, 1234)
         assert os.fstat(r).st_size == 1234 and os.pread(r, 5000, 0) == files["d/f005"][:1234]
         os.close(r)
+
+
+@pytest.mark.parametrize("host", _hosts())
+def test_many_readers_beside_writers(host, ref, corpus, oracle):
+    """the serving threads (Fs::loop): eight readers walk a directory of pre-compressed files with random preads while two
+    writers create, append to, rewrite, rename and delete files of their own in the same directory; every byte read is compared,
+    every stored file is decoded by the oracle at the end.  With one serving thread this is the reference's behaviour, with
+    several the READs overlap each other and wait for everything else."""
+    if not ref.available:
+        pytest.skip("system libzstd absent")
+    import random
+    import threading
+    files = {("f%03d" % i): corpus.json_file(990000 + i, 200000 + 4097 * i).tobytes() for i in range(12)}
+    with Mount(host) as m:
+        os.makedirs(os.path.join(m.data, "d"))
+        for rel, plain in files.items():
+            with open(os.path.join(m.data, "d", rel + ".zst"), "wb") as fh:
+                fh.write(ref.writer_encode(plain, 3))
+        errors = []
+
+        def reader(seed):
+            try:
+                rnd = random.Random(seed)
+                for _ in range(12):
+                    name = rnd.choice(sorted(files)); plain = files[name]
+                    fd = os.open(os.path.join(m.mp, "d", name), os.O_RDONLY)
+                    try:
+                        assert os.fstat(fd).st_size == len(plain)
+                        for _ in range(20):
+                            o = rnd.randrange(len(plain)); n = rnd.choice((1, 4096, 65536, 131072))
+                            assert os.pread(fd, n, o) == plain[o:o + n], (name, o, n)
+                    finally:
+                        os.close(fd)
+            except Exception as e:                                        # noqa: BLE001 -- reported by the main thread
+                errors.append(repr(e))
+
+        stored = {}
+
+        def writer(k):
+            try:
+                body = corpus.json_file(995000 + k, 150000).tobytes()
+                for r in range(4):
+                    p = os.path.join(m.mp, "d", "w%d_%d" % (k, r))
+                    with open(p, "wb") as fh:
+                        fh.write(body[:100000])
+                    with open(p, "ab") as fh:
+                        fh.write(body[100000:])
+                    with open(p, "r+b") as fh:
+                        fh.seek(5000); fh.write(b"REWRITTEN")
+                    want = body[:5000] + b"REWRITTEN" + body[5009:]
+                    assert open(p, "rb").read() == want
+                    if r % 2:
+                        q = p + "_moved"; os.rename(p, q); stored["w%d_%d_moved" % (k, r)] = want
+                    elif r == 2:
+                        os.unlink(p)
+                    else:
+                        stored["w%d_%d" % (k, r)] = want
+            except Exception as e:                                        # noqa: BLE001
+                errors.append(repr(e))
+
+        th = [threading.Thread(target=reader, args=(s,)) for s in range(8)] + [threading.Thread(target=writer, args=(k,)) for k in range(2)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert not errors, errors[:3]
+        for name, want in stored.items():
+            st, back = oracle.decode(open(os.path.join(m.data, "d", name + ".zst"), "rb").read(), cap=len(want))
+            assert st == 0 and back == want, name
+        assert sorted(n for n in os.listdir(os.path.join(m.mp, "d"))) == sorted(list(files) + list(stored))
 
 
 def test_product_host_fails_loudly_without_a_gpu():

@@ -5,7 +5,8 @@ reader processes, same fzfs host source (fuse-zstd_b200/csrc/fzfs.cpp):
   gpu        fuse-zstd_b200/fzfs      GPU codec, directory readahead + decoded-file cache
   reference  oracle/_ref/fzfs_ref     the reference's libzstd calls on the host's one FUSE thread (the restated CPU path; the
                                       unmodified fuse-zstd binary cannot be built here: no Rust toolchain)
-usage: mount_bench.py [--jobs 16] [--nrfiles 125] [--filesize-kib 1024] [--arms gpu,reference]"""
+An arm may name its serving threads: gpu:1 (one request at a time, as fuser), gpu:16; plain `gpu` / `reference` use the hosts' defaults (8 / 1).
+usage: mount_bench.py [--jobs 16] [--nrfiles 125] [--filesize-kib 1024] [--arms reference,gpu:1,gpu]"""
 import argparse, importlib, json, multiprocessing as mp, os, shutil, subprocess, sys, tempfile, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
@@ -102,9 +103,11 @@ def main():
     hosts = {"gpu": [os.path.join(ROOT, "fuse-zstd_b200", "fzfs"), "--cache-mb", str(a.cache_mb)], "reference": [os.path.join(ROOT, "oracle", "_ref", "fzfs_ref")]}
     out = {"metric": "mount_read_MBps", "unit": "MB/s", "jobs": a.jobs, "nrfiles": a.nrfiles, "filesize": size, "bs": 131072,
            "workload": "benchmarks/parallel-files.fio shape (jobs x nrfiles x filesize, one open file per job) + sequential 128 KiB reads of every file"}
-    for arm in a.arms.split(","):
+    for arm_spec in a.arms.split(","):
+        arm, _, nthr = arm_spec.partition(":")
         mpnt = tempfile.mkdtemp(prefix="fzbench_mnt")
-        proc = subprocess.Popen(hosts[arm] + ["--data-dir", data, "--mount-point", mpnt])
+        proc = subprocess.Popen(hosts[arm] + (["--threads", nthr] if nthr else []) + os.environ.get("FZFS_EXTRA_ARGS", "").split() + ["--data-dir", data, "--mount-point", mpnt])
+        arm = arm if not nthr else "%s_%s_threads" % (arm, nthr)
         for _ in range(2400):                         # the GPU host allocates its pinned cache before it mounts
             if os.path.ismount(mpnt) or proc.poll() is not None:
                 break
