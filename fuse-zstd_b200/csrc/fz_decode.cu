@@ -429,6 +429,37 @@ __device__ __forceinline__ void st_stage(uint8_t* p, uint64_t v, uint32_t nb)
 }
 #undef FZ_ST_BYTE
 
+// the same through 32-bit shared-memory addresses (k_execute_cta: the stage and the bitmap are addressed from one conversion
+// per block instead of one per access, and stage reads are LDS instead of generic loads)
+#define FZ_ST_BYTE_S(I, W, SH) asm volatile("{ .reg .pred q; .reg .b32 t; setp.gt.u32 q, %2, " #I "; shr.b32 t, %1, " #SH "; @q st.shared.u8 [%0+" #I "], t; }" ::"r"(a), "r"(W), "r"(nb) : "memory")
+__device__ __forceinline__ void st_stage_s(uint32_t a, uint64_t v, uint32_t nb)
+{
+    const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    FZ_ST_BYTE_S(0, lo, 0); FZ_ST_BYTE_S(1, lo, 8); FZ_ST_BYTE_S(2, lo, 16); FZ_ST_BYTE_S(3, lo, 24);
+    FZ_ST_BYTE_S(4, hi, 0); FZ_ST_BYTE_S(5, hi, 8); FZ_ST_BYTE_S(6, hi, 16); FZ_ST_BYTE_S(7, hi, 24);
+}
+#undef FZ_ST_BYTE_S
+#ifndef FZ_EXEC_ADDRSPACE
+#define FZ_EXEC_ADDRSPACE 1          // k_execute: explicit ld.global / ld.shared / st.shared addresses instead of generic ones (measured, see profiles/r02_notes.md)
+#endif
+__device__ __forceinline__ uint64_t ld8_global(const uint8_t* g, uint32_t nb)       // nb (1..8) bytes at a GLOBAL address
+{
+    const uintptr_t a = (uintptr_t)g & ~(uintptr_t)7;
+    const uint32_t sh = (uint32_t)((uintptr_t)g & 7);
+    uint32_t x0, x1, x2 = 0, x3 = 0;
+    asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(x0), "=r"(x1) : "l"(a) : "memory");
+    if (sh + nb > 8) asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(x2), "=r"(x3) : "l"(a + 8) : "memory");
+    return funnel8(x0, x1, x2, x3, sh);
+}
+__device__ __forceinline__ uint64_t ld8_shared(uint32_t g, uint32_t nb)
+{
+    const uint32_t a = g & ~7u, sh = g & 7u;
+    uint32_t x0, x1, x2 = 0, x3 = 0;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x0), "=r"(x1) : "r"(a) : "memory");
+    if (sh + nb > 8) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x2), "=r"(x3) : "r"(a + 8) : "memory");
+    return funnel8(x0, x1, x2, x3, sh);
+}
+
 // warp-cooperative copy / fill, any alignment, any size
 __device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane)
 {
@@ -487,6 +518,9 @@ __device__ __forceinline__ void exec_block_warp(uint8_t* stage, const Block& b, 
     const uint8_t* __restrict__ lit = b.lit;
     const uint32_t in0 = b.rep_in[0], in1 = b.rep_in[1], in2 = b.rep_in[2];
     const uint64_t pol = l2_stream_policy();
+#if FZ_EXEC_ADDRSPACE
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+#endif
     uint32_t Ecarry = 0, LEcarry = 0;
     uint64_t rcur = lane < nseq ? ldrec_stream(sq + lane, pol) : 0;          // records of the current round; the next round's are loaded a round early
     for (uint32_t g = 0; g < nseq;) {
@@ -517,6 +551,16 @@ __device__ __forceinline__ void exec_block_warp(uint8_t* stage, const Block& b, 
         const uint32_t gE = __shfl_sync(kFull, E, m - 1);         // end of the round's output
         const uint32_t a = (uint32_t)((uintptr_t)(g0 + gS) & 15); // stage[a + i] <-> g0[gS + i]: same low address bits as HBM
         uint8_t* const st = stage + a - gS;                       // st[p] is the stage byte of output position p (gS <= p < gE)
+#if FZ_EXEC_ADDRSPACE
+        const uint32_t sts = stage_s + a - gS;                    // the same as a shared-memory address
+#define FZ_STAGE_ST(pos, v, nb) st_stage_s(sts + (pos), v, nb)
+#define FZ_STAGE_LD(s, nb) ld8_shared(sts + (uint32_t)(s), nb)
+#define FZ_GLOBAL_LD(p, nb) ld8_global(p, nb)
+#else
+#define FZ_STAGE_ST(pos, v, nb) st_stage(st + (pos), v, nb)
+#define FZ_STAGE_LD(s, nb) ld8_any((const uint8_t*)st + (s), nb)
+#define FZ_GLOBAL_LD(p, nb) ld8_stream(p, nb, pol)
+#endif
         // ---- 1. literal runs
         {
             uint32_t pos = S; const uint8_t* src = lit + LEp;
@@ -524,7 +568,7 @@ __device__ __forceinline__ void exec_block_warp(uint8_t* stage, const Block& b, 
             while (__any_sync(kFull, go)) {
                 if (go) {
                     const uint32_t nb = min(8u, M - pos);
-                    st_stage(st + pos, ld8_stream(src, nb, pol), nb);
+                    FZ_STAGE_ST(pos, FZ_GLOBAL_LD(src, nb), nb);
                     pos += nb; src += nb; go = pos < M;
                 }
             }
@@ -549,10 +593,9 @@ __device__ __forceinline__ void exec_block_warp(uint8_t* stage, const Block& b, 
                             const int32_t s0 = (int32_t)pos - (int32_t)off;
                             const bool ok = lane == first || (uint32_t)(s0 + (int32_t)off) <= front || s0 >= (int32_t)M;   // period written?
                             if (ok) {
-                                const uint8_t* sp = s0 < (int32_t)gS ? (const uint8_t*)g0 + s0 : (const uint8_t*)st + s0;
                                 const uint32_t take = s0 < (int32_t)gS ? min(off, gS - (uint32_t)s0) : off;   // a period straddling the round start
-                                uint64_t pat = ld8_any(sp, take);
-                                if (take < off) pat = (pat & ((1ull << (8 * take)) - 1)) | (ld8_any((const uint8_t*)st + gS, off - take) << (8 * take));
+                                uint64_t pat = s0 < (int32_t)gS ? FZ_GLOBAL_LD((const uint8_t*)g0 + s0, take) : FZ_STAGE_LD(s0, take);
+                                if (take < off) pat = (pat & ((1ull << (8 * take)) - 1)) | (FZ_STAGE_LD(gS, off - take) << (8 * take));
                                 for (uint32_t i = 0; i < nb; i++) v |= ((pat >> (8 * (i % off))) & 0xFF) << (8 * i);
                             } else nb = 0;
                         } else {
@@ -561,12 +604,12 @@ __device__ __forceinline__ void exec_block_warp(uint8_t* stage, const Block& b, 
                             const uint32_t lim = lane == first ? pos : ((s >= (int32_t)M) ? pos : front);
                             if (s < (int32_t)gS) {                 // before the round: HBM / L2 (earlier rounds, earlier blocks)
                                 nb = min(nb, gS - (uint32_t)s);    // a step straddling the round start is split
-                                v = ld8_stream((const uint8_t*)g0 + s, nb, pol);
-                            } else if ((uint32_t)s + nb <= lim) v = ld8_any((const uint8_t*)st + s, nb);
-                            else if ((uint32_t)s < lim) { nb = lim - (uint32_t)s; v = ld8_any((const uint8_t*)st + s, nb); }
+                                v = FZ_GLOBAL_LD((const uint8_t*)g0 + s, nb);
+                            } else if ((uint32_t)s + nb <= lim) v = FZ_STAGE_LD(s, nb);
+                            else if ((uint32_t)s < lim) { nb = lim - (uint32_t)s; v = FZ_STAGE_LD(s, nb); }
                             else nb = 0;
                         }
-                        if (nb) { st_stage(st + pos, v, nb); pos += nb; go = pos < E; }
+                        if (nb) { FZ_STAGE_ST(pos, v, nb); pos += nb; go = pos < E; }
                         else go = false;                          // its source is still being produced by a lower lane
                     }
                 }
@@ -580,13 +623,18 @@ __device__ __forceinline__ void exec_block_warp(uint8_t* stage, const Block& b, 
             const uint32_t n = gE - gS;
             uint8_t* gd = g0 + gS;
             const uint32_t head = min(n, (16 - a) & 15);
-            if (lane < head) gd[lane] = stage[a + lane];
             const uint32_t nvec = (n - head) >> 4;
-            for (uint32_t i = lane; i < nvec; i += 32) *(uint4*)(gd + head + 16 * i) = *(const uint4*)(stage + a + head + 16 * i);
             const uint32_t tail0 = head + (nvec << 4);
+            // (explicit ld.shared / st.global here as well was measured slower: 25.6 -> 26.1 ms)
+            if (lane < head) gd[lane] = stage[a + lane];
+            for (uint32_t i = lane; i < nvec; i += 32) *(uint4*)(gd + head + 16 * i) = *(const uint4*)(stage + a + head + 16 * i);
             if (tail0 + lane < n) gd[tail0 + lane] = stage[a + tail0 + lane];
         }
         __syncwarp();
+#undef FZ_STAGE_ST
+#undef FZ_STAGE_LD
+#undef FZ_GLOBAL_LD
+        (void)st;
         Ecarry = gE; LEcarry = __shfl_sync(kFull, LE, m - 1);
         g += m;
 #if FZ_EXEC_PREFETCH
@@ -679,17 +727,17 @@ template <int W> __device__ __forceinline__ void exec_sync()
 }
 
 // stage bytes [o, o + nb) are stored: publish them (release: the byte stores above are visible to whoever sees the bits)
-__device__ __forceinline__ void bm_mark(uint32_t* bm, uint32_t o, uint32_t nb)
+__device__ __forceinline__ void bm_mark(uint32_t bm_s, uint32_t o, uint32_t nb)          // bm_s: shared-memory address of the bitmap
 {
     const uint32_t sh = o & 31u, m = (1u << nb) - 1u;
-    const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(bm + (o >> 5));
+    const uint32_t a0 = bm_s + ((o >> 5) << 2);
     asm volatile("red.release.cta.shared.or.b32 [%0], %1;" ::"r"(a0), "r"(m << sh) : "memory");
     if (sh + nb > 32) asm volatile("red.relaxed.cta.shared.or.b32 [%0], %1;" ::"r"(a0 + 4), "r"(m >> (32 - sh)) : "memory");
 }
 // how many of the stage bytes starting at o are stored (0 .. 32)
-__device__ __forceinline__ uint32_t bm_ready(const uint32_t* bm, uint32_t o)
+__device__ __forceinline__ uint32_t bm_ready(uint32_t bm_s, uint32_t o)
 {
-    const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(bm + (o >> 5));
+    const uint32_t a0 = bm_s + ((o >> 5) << 2);
     uint32_t w0, w1;
     asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(w0) : "r"(a0) : "memory");
     asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(w1) : "r"(a0 + 4) : "memory");
@@ -744,6 +792,7 @@ __device__ __forceinline__ void exec_block_cta(uint8_t* stage, uint32_t* bm, uin
     const uint32_t in0 = b.rep_in[0], in1 = b.rep_in[1], in2 = b.rep_in[2];
     for (uint32_t i = tid; i < ExecCta<W>::bitmap_words; i += T) bm[i] = 0;
     exec_sync<W>();
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage), bm_s = (uint32_t)__cvta_generic_to_shared(bm);
     uint32_t Ecarry = 0, LEcarry = 0;                            // CTA-uniform
     uint64_t rcur = tid < nseq ? __ldg(sq + tid) : 0;            // the round's records; the next round's are loaded a round early
     uint64_t rprev = (lane == 0 && warp > 0 && tid <= nseq) ? __ldg(sq + tid - 1) : 0;   // record before a warp's first one
@@ -794,7 +843,7 @@ __device__ __forceinline__ void exec_block_cta(uint8_t* stage, uint32_t* bm, uin
         if (!mine) { S = gE; E = gE; LE = LEend; LEp = LEend; }
         const uint32_t M = S + (LE - LEp);
         const uint32_t a = (uint32_t)((uintptr_t)(g0 + gS) & 15); // stage[a + i] <-> g0[gS + i]: same low address bits as HBM
-        uint8_t* const st = stage + a - gS;                       // st[p] is the stage byte of output position p (gS <= p < gE)
+        const uint32_t st = stage_s + a - gS;                     // st + p: shared-memory address of the stage byte of output position p (gS <= p < gE)
         const uint32_t ob = a - gS;                               // ob + p: bitmap index of output position p
         // ---- 1. literal runs
         {
@@ -803,8 +852,8 @@ __device__ __forceinline__ void exec_block_cta(uint8_t* stage, uint32_t* bm, uin
             while (__any_sync(kFull, go)) {
                 if (go) {
                     const uint32_t nb = min(8u, M - pos);
-                    st_stage(st + pos, ld8_any(src, nb), nb);
-                    bm_mark(bm, ob + pos, nb);
+                    st_stage_s(st + pos, ld8_any(src, nb), nb);
+                    bm_mark(bm_s, ob + pos, nb);
                     pos += nb; src += nb; go = pos < M;
                 }
             }
@@ -827,11 +876,11 @@ __device__ __forceinline__ void exec_block_cta(uint8_t* stage, uint32_t* bm, uin
                             nb = min(nb, gS - (uint32_t)s);       // a step straddling the round start is split
                             v = ld8_any((const uint8_t*)g0 + s, nb);
                         } else {
-                            nb = min(nb, bm_ready(bm, ob + (uint32_t)s));
-                            if (nb) v = ld8_any((const uint8_t*)st + s, nb);
+                            nb = min(nb, bm_ready(bm_s, ob + (uint32_t)s));
+                            if (nb) v = ld8_shared(st + (uint32_t)s, nb);
                         }
                     }
-                    if (nb) { st_stage(st + pos, v, nb); bm_mark(bm, ob + pos, nb); pos += nb; pending = pos < E; moved = true; }
+                    if (nb) { st_stage_s(st + pos, v, nb); bm_mark(bm_s, ob + pos, nb); pos += nb; pending = pos < E; moved = true; }
                 }
                 if (!__any_sync(kFull, moved)) __nanosleep(32);   // every unfinished lane waits for another warp
             }
