@@ -545,6 +545,30 @@ void Fs::dispatch(const struct fuse_in_header* in, const uint8_t* arg, size_t ar
         if (n < 0) return reply(u, errno);
         return reply(u, 0, rbuf.data(), (size_t)n);
     }
+    if (in->opcode == FUSE_WRITE) {
+        // like READ: the lock for the lookup, the pwrite beside everything else.  Appends stay exclusive (end-of-file + write must not
+        // interleave between handles of one file, src/main.rs:576-588), and so does a handle without a file of its own.
+        const struct fuse_write_in* w = (const struct fuse_write_in*)arg;
+        std::shared_ptr<std::atomic<int>> busy; int fd = -1;
+        {
+            std::shared_lock<std::shared_mutex> lk(mu_);
+            if (g_stats) t_wait_ns = now_ns() - w0;
+            auto h = handles_.find(w->fh);
+            if (h == handles_.end()) { lk.unlock(); return reply(u, EBADF); }
+            if (!(h->second.flags & O_APPEND) && h->second.fd >= 0) {
+                busy = h->second.busy; busy->fetch_add(1, std::memory_order_acquire);
+                fd = h->second.fd;
+                __atomic_store_n(&h->second.needs_sync, true, __ATOMIC_RELAXED);      // several writers may say so at once
+            }
+        }
+        if (busy) {
+            struct Idle { std::atomic<int>& b; ~Idle() { b.fetch_sub(1, std::memory_order_release); } } idle{ *busy };
+            const ssize_t n = pwrite(fd, arg + sizeof *w, w->size, (off_t)w->offset);
+            if (n < 0) return reply(u, errno);
+            struct fuse_write_out o; memset(&o, 0, sizeof o); o.size = (uint32_t)n;
+            return reply(u, 0, &o, sizeof o);
+        }
+    }
     std::unique_lock<std::shared_mutex> lk(mu_);
     if (g_stats) t_wait_ns = now_ns() - w0;
     switch (in->opcode) {
