@@ -51,6 +51,13 @@ extern "C" int fzg_init(const int* devices, int n_devices)
             cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
             fprintf(stderr, "fzgpu: L2 fetch granularity: asked %s, set -> %s, now %zu\n", g, cudaGetErrorString(e), got);
         }
+        if (const char* g = getenv("FZG_L2_PERSIST_MB")) {                                                                 // experiment knob (FZ_EXEC_L2OUT)
+            int mx = 0; cudaDeviceGetAttribute(&mx, cudaDevAttrMaxPersistingL2CacheSize, d);
+            const size_t want = std::min<size_t>((size_t)atoi(g) << 20, (size_t)mx);
+            cudaError_t e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want); size_t got = 0;
+            cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize);
+            fprintf(stderr, "fzgpu: persisting L2: max %d, asked %zu, set -> %s, now %zu\n", mx, want, cudaGetErrorString(e), got);
+        }
         FzCtx* c = new FzCtx();
         c->dev = d;
         const char* nl = getenv("FZG_LANES");

@@ -383,6 +383,9 @@ __device__ __forceinline__ uint64_t ld8_any(const uint8_t* g, uint32_t nb)
 // 55 GB of fills per 12 ms turn the 126 MB L2 over every ~26 us, in which a frame produces 2 KB -- so only matches closer than
 // that find their source in L2 (15 % of them), although 47 % lie within the 26 KB that are a frame's fair share.  With the
 // hint the streaming data (window misses, records, literals) is marked evict-first and leaves the plain output stores alone.
+#ifndef FZ_EXEC_L2OUT
+#define FZ_EXEC_L2OUT 0
+#endif
 #ifndef FZ_EXEC_L2HINT
 #define FZ_EXEC_L2HINT 0
 #endif
@@ -521,6 +524,10 @@ __device__ __forceinline__ void exec_block_warp(uint8_t* stage, const Block& b, 
 #if FZ_EXEC_ADDRSPACE
     const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
 #endif
+#if FZ_EXEC_L2OUT
+    uint64_t opol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(opol));
+#endif
     uint32_t Ecarry = 0, LEcarry = 0;
     uint64_t rcur = lane < nseq ? ldrec_stream(sq + lane, pol) : 0;          // records of the current round; the next round's are loaded a round early
     for (uint32_t g = 0; g < nseq;) {
@@ -626,9 +633,20 @@ __device__ __forceinline__ void exec_block_warp(uint8_t* stage, const Block& b, 
             const uint32_t nvec = (n - head) >> 4;
             const uint32_t tail0 = head + (nvec << 4);
             // (explicit ld.shared / st.global here as well was measured slower: 25.6 -> 26.1 ms)
+#if FZ_EXEC_L2OUT
+            // the output IS the window of the sequences to come: stored with an L2 policy that keeps it resident longer than the
+            // window lines that misses bring in (experiment, see profiles/r02_notes.md)
+            if (lane < head) asm volatile("st.global.L2::cache_hint.u8 [%0], %1, %2;" ::"l"(gd + lane), "r"((uint32_t)stage[a + lane]), "l"(opol) : "memory");
+            for (uint32_t i = lane; i < nvec; i += 32) {
+                const uint4 v = *(const uint4*)(stage + a + head + 16 * i);
+                asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(gd + head + 16 * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(opol) : "memory");
+            }
+            if (tail0 + lane < n) asm volatile("st.global.L2::cache_hint.u8 [%0], %1, %2;" ::"l"(gd + tail0 + lane), "r"((uint32_t)stage[a + tail0 + lane]), "l"(opol) : "memory");
+#else
             if (lane < head) gd[lane] = stage[a + lane];
             for (uint32_t i = lane; i < nvec; i += 32) *(uint4*)(gd + head + 16 * i) = *(const uint4*)(stage + a + head + 16 * i);
             if (tail0 + lane < n) gd[tail0 + lane] = stage[a + tail0 + lane];
+#endif
         }
         __syncwarp();
 #undef FZ_STAGE_ST
