@@ -517,8 +517,8 @@ def run_b200(args, rank, local_rank, world):
     mount = None
     if not args.no_mount and world == 1 and args.config == 2:
         try:
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "mount_bench.py"), "--jobs", "16", "--nrfiles", "250", "--fio-write",
-                                "--arms", "reference,gpu:1,gpu"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=400)
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "mount_bench.py"), "--jobs", "16", "--nrfiles", "625", "--fio-write",
+                                "--arms", "reference,gpu:1,gpu"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)   # (a run of 250 files per job lasts 0.4 s: mostly the first windows)
             if r.returncode == 0:
                 mj = json.loads(r.stdout.decode().strip().splitlines()[-1])
                 mount = {"gpu_MBps": mj.get("gpu"), "gpu_1_serving_thread_MBps": mj.get("gpu_1_threads"), "reference_cpu_MBps": mj.get("reference"),
