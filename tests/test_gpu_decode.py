@@ -411,3 +411,50 @@ def test_large_frames_go_home_behind_the_execute_stage(ref, corpus):
                 assert st == codec.E_CHECKSUM, (i, codec.strerror(st))
             else:
                 assert st == 0 and out == plains[i], i
+
+
+def test_pinned_sources_in_several_allocations(ref, corpus):
+    """host-resident batches whose items live in pinned memory: one span is copied as it is, items scattered over several pinned
+    allocations (the cache's merged readahead batches) are copied one by one, and items that look like one span but are two
+    allocations must not be taken for one (a span ends at a gap of more than 256 KiB; a failed span copy falls back to copies
+    per item).  Pinned and pageable destinations, results compared byte for byte."""
+    if not ref.available:
+        pytest.skip("system libzstd absent")
+    import torch
+    n = 24
+    plains = [corpus.json_file(6100 + i, 150000 + 1237 * i).tobytes() for i in range(n)]
+    blobs = [ref.writer_encode(b, 3) for b in plains]
+    bufs = [torch.empty(8 << 20, dtype=torch.uint8).pin_memory() for _ in range(3)]
+    fill = [0, 0, 0]
+    sp, sl = [], []
+    for i, b in enumerate(blobs):                       # round-robin over the three allocations: never one increasing span
+        k = i % 3
+        a = bufs[k].numpy()
+        a[fill[k]:fill[k] + len(b)] = np.frombuffer(b, dtype=np.uint8)
+        sp.append(a.ctypes.data + fill[k]); sl.append(len(b))
+        fill[k] += (len(b) + 63) & ~63
+    caps = [len(p_) for p_ in plains]
+    out_pinned = torch.empty(sum(caps) + 64 * n, dtype=torch.uint8).pin_memory().numpy()
+    out_paged = np.zeros(sum(caps) + 64 * n, dtype=np.uint8)
+    for out in (out_pinned, out_paged):
+        dp, o = [], 0
+        for c in caps:
+            dp.append(out.ctypes.data + o); o += c + 64
+        dl, st = codec.decode_batch_ptrs(0, sp, sl, dp, caps, 0)
+        assert not st.any() and (dl == np.array(caps, dtype=np.uint64)).all()
+        o = 0
+        for i, c in enumerate(caps):
+            assert out[o:o + c].tobytes() == plains[i], i
+            o += c + 64
+    # increasing addresses across two allocations: sorted by address, the items of buffer A then those of buffer B
+    order = sorted(range(n), key=lambda i: sp[i])
+    dp, o = [], 0
+    for i in order:
+        dp.append(out_paged.ctypes.data + o); o += caps[i] + 64
+    out_paged[:] = 0
+    dl, st = codec.decode_batch_ptrs(0, [sp[i] for i in order], [sl[i] for i in order], dp, [caps[i] for i in order], 0)
+    assert not st.any()
+    o = 0
+    for i in order:
+        assert out_paged[o:o + caps[i]].tobytes() == plains[i], i
+        o += caps[i] + 64
