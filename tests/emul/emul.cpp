@@ -18,6 +18,9 @@ using namespace fz;
 
 static uint64_t g_far_records = 0;     // RAW records in the far form (extra bits > 32) seen so far
 extern "C" uint64_t fze_far_records(void) { return g_far_records; }
+// table logs seen so far: [0] LL, [1] OF, [2] ML, 16 counters each (what a stream of stage A really needs of its shared memory)
+static uint64_t g_table_logs[3][16];
+extern "C" void fze_table_logs(uint64_t* out) { for (int t = 0; t < 3; t++) for (int l = 0; l < 16; l++) out[t * 16 + l] = g_table_logs[t][l]; }
 static const SeqConsts kConsts = { FZ_LL_BASE, FZ_ML_BASE, FZ_LL_BITS, FZ_ML_BITS, FZ_LL_DEF, FZ_OF_DEF, FZ_ML_DEF };
 
 // TEST-ONLY serial restatement of stage B (k_records in fz_decode.cu is warp-parallel CUDA): RAW records ->
@@ -119,6 +122,7 @@ extern "C" int fze_decode_batch(size_t n, const void* const* src, const size_t* 
         const TabWork tw{ { w_sym, 1 }, { w_norm, 1 }, { w_cnt, 1 } };
         seq_tables_thread(blocks.data(), b, kConsts, tab, h, tw);
         if (h.bad && !b.status) b.status = FZG_E_CORRUPT;
+        if (!h.bad) { g_table_logs[0][h.logLL & 15]++; g_table_logs[1][h.logOF & 15]++; g_table_logs[2][h.logML & 15]++; }
         seq_chain_thread(b, tab, h, chain_mem, seqs.data(), b.nseq - 1, 1);
         if (!b.status) for (uint32_t i = 0; i < b.nseq; i++) g_far_records += seqs[b.seq_base + i] >> 63;
         records_serial(blocks.data(), b, frames[b.frame].block_max, seqs.data(), tab, h);
