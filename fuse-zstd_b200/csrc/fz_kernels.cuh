@@ -78,42 +78,46 @@ FZ_HD void seq_chain_thread(Block& b, const uint8_t* gtab, const SeqJobHdr& h, u
 }
 
 // ------------------------------------------------------------------ checksum pass (four threads per frame)
+#ifndef FZ_XX_DEPTH
+#define FZ_XX_DEPTH 32
+#endif
+constexpr int kXxDepth = FZ_XX_DEPTH;            // loads in flight per accumulator chain of k_checksum (see xx_lane)
 FZ_HD uint64_t xx_lane(const uint8_t* p, uint64_t len, uint32_t j)   // accumulator j over all 32-byte stripes
 {
     uint64_t acc = j == 0 ? XP1 + XP2 : (j == 1 ? XP2 : (j == 2 ? 0 : 0 - XP1));
     const uint64_t stripes = len >> 5;
     const uint8_t* q = p + 8 * j;
     if (((uintptr_t)p & 7) == 0) {
-        // a serial multiply chain fed from HBM: two batches of sixteen loads, the next one in flight while this one is consumed
+        // a serial multiply chain fed from HBM: two batches of kXxDepth loads, the next one in flight while this one is consumed
         uint64_t s = 0;
-        uint64_t cur[16], nxt[16];
-        const bool any = stripes >= 16;
+        uint64_t cur[kXxDepth], nxt[kXxDepth];
+        const bool any = stripes >= kXxDepth;
         if (any) {
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-            for (int k = 0; k < 16; k++) cur[k] = *(const uint64_t*)(q + 32 * k);
+            for (int k = 0; k < kXxDepth; k++) cur[k] = *(const uint64_t*)(q + 32 * k);
         }
-        for (; s + 32 <= stripes; s += 16) {
+        for (; s + 2 * kXxDepth <= stripes; s += kXxDepth) {
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-            for (int k = 0; k < 16; k++) nxt[k] = *(const uint64_t*)(q + 32 * (s + 16 + k));
+            for (int k = 0; k < kXxDepth; k++) nxt[k] = *(const uint64_t*)(q + 32 * (s + kXxDepth + k));
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-            for (int k = 0; k < 16; k++) acc = xx_round(acc, cur[k]);
+            for (int k = 0; k < kXxDepth; k++) acc = xx_round(acc, cur[k]);
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-            for (int k = 0; k < 16; k++) cur[k] = nxt[k];
+            for (int k = 0; k < kXxDepth; k++) cur[k] = nxt[k];
         }
         if (any) {
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-            for (int k = 0; k < 16; k++) acc = xx_round(acc, cur[k]);
-            s += 16;
+            for (int k = 0; k < kXxDepth; k++) acc = xx_round(acc, cur[k]);
+            s += kXxDepth;
         }
         for (; s < stripes; s++) acc = xx_round(acc, *(const uint64_t*)(q + 32 * s));
     } else {
